@@ -1,0 +1,115 @@
+"""CPU: the oracle restatement (oracle/*.py) against golden vectors produced by executing the reference's own
+Python (tests/golden/make_golden.py).  No GPU, no /root/reference needed."""
+import numpy as np
+import pytest
+from conftest import golden, checksum, rel_err
+from oracle import relation_np as R, learn_nms_np as L, proposal_np as P
+
+REL_CASES = ['relation_cfg0_ref', 'relation_cfg0_fanin', 'relation_n300_d1024', 'relation_n120_m100']
+
+
+def _rel_case(g):
+    M = int(g['M']); N = int(g['N'])
+    c = R.make_relation_case(int(g['seed']), N, int(g['d']), int(g['H']), init=str(g['init']),
+                             M=None if M == N else M)
+    assert abs(checksum(c) - float(g['input_checksum'])) < 1e-6 * abs(float(g['input_checksum'])), 'generator drift'
+    return c, N, M
+
+
+@pytest.mark.parametrize('name', REL_CASES)
+def test_relation_oracle_matches_reference_execution(name):
+    g = golden(name)
+    c, N, M = _rel_case(g)
+    H = int(g['H'])
+    eps = R.position_matrix(c['boxes'], M)
+    np.testing.assert_allclose(eps[:g['position_matrix'].shape[0]], g['position_matrix'], rtol=1e-5, atol=1e-5)
+    phi = R.position_embedding(eps[:8])
+    np.testing.assert_allclose(phi, g['position_embedding'], rtol=0, atol=2e-4)   # sin/cos of args up to +-690 in fp32
+    args = (c['X'], c['boxes'], c['Wq'], c['bq'], c['Wk'], c['bk'], c['Wg'], c['bg'], c['Wout'], c['bout'])
+    att = R.relation_forward(*args, key_index=M, group=H)
+    assert rel_err(att, g['attention']) < 2e-5
+    out = R.relation_forward(*args, key_index=M, group=H, residual_relu=True)
+    assert rel_err(out, g['out']) < 2e-5
+    # fp64 twin and the reordered (V' = V.Wout^T, g*exp(s)) form the CUDA kernel evaluates agree to rounding
+    att64 = R.relation_forward(*args, key_index=M, group=H, dtype=np.float64)
+    re64 = R.relation_forward_reordered(*args, key_index=M, group=H, dtype=np.float64)
+    assert rel_err(re64, att64) < 1e-10
+    # float32 reference arithmetic is itself ~3e-4 (max-norm) away from exact: sin/cos of 100*eps up to +-690 rad
+    # lose ~5e-5 rad to argument rounding and log(max(relu(x),1e-6)) amplifies it for barely-alive geometry units
+    assert rel_err(att, att64) < 1e-3
+
+
+def test_relation_self_consistency():
+    c = R.make_relation_case(5, 64, 256, 4)
+    args = (c['Wq'], c['bq'], c['Wk'], c['bk'], c['Wg'], c['bg'], c['Wout'], c['bout'])
+    r = R.relation_forward(c['X'], c['boxes'], *args, group=4, return_all=True, dtype=np.float64)
+    np.testing.assert_allclose(r['softmax'].sum(axis=2), 1.0, atol=1e-12)
+    # translation invariance of the geometry; permutation equivariance when N == M
+    sh = c['boxes'].astype(np.float64) + np.array([13.0, -7.0, 13.0, -7.0])
+    np.testing.assert_allclose(R.position_matrix(sh, dtype=np.float64), R.position_matrix(c['boxes'], dtype=np.float64),
+                               atol=1e-9)
+    perm = np.random.default_rng(0).permutation(64)
+    o1 = R.relation_forward(c['X'], c['boxes'], *args, group=4, dtype=np.float64)
+    o2 = R.relation_forward(c['X'][perm], c['boxes'][perm], *args, group=4, dtype=np.float64)
+    np.testing.assert_allclose(o2, o1[perm], atol=1e-10)
+    # identical boxes -> eps = (log 1e-3, log 1e-3, 0, 0)
+    same = np.tile(c['boxes'][:1], (3, 1))
+    e = R.position_matrix(same, dtype=np.float64)
+    np.testing.assert_allclose(e[0, 1], [np.log(1e-3), np.log(1e-3), 0, 0], atol=1e-12)
+
+
+@pytest.mark.parametrize('name', ['learn_nms_r300_c80', 'learn_nms_r60_c8'])
+def test_learn_nms_oracle_matches_reference_execution(name):
+    g = golden(name)
+    c = L.make_learn_nms_case(int(g['seed']), R=int(g['R']), C=int(g['C']), init=str(g['init']))
+    assert abs(checksum(dict(c, **c['P'])) - float(g['input_checksum'])) < 1e-6 * float(g['input_checksum'])
+    multi, sbbox, sscore, final = L.learn_nms_forward(
+        c['cls_score'], c['bbox_pred'], c['rois'], c['im_info'], c['feat'], c['P'], first_n=int(g['first_n']),
+        num_fg_classes=int(g['C']), nongt_dim=int(g['R']))
+    np.testing.assert_allclose(sscore, g['sorted_score'], rtol=1e-5, atol=1e-8)
+    np.testing.assert_allclose(sbbox, g['sorted_bbox'], rtol=1e-5, atol=1e-3)
+    assert rel_err(multi, g['nms_multi_score']) < 5e-5
+    assert rel_err(final, g['final_score']) < 5e-5
+    # pruned classes are exactly zero in both
+    assert np.array_equal(multi.max(axis=(0, 2)) > 0, g['nms_multi_score'].max(axis=(0, 2)) > 0)
+
+
+@pytest.mark.parametrize('name', ['proposal_38x63', 'proposal_small'])
+def test_proposal_oracle_matches_reference_execution(name):
+    g = golden(name)
+    scales = tuple(int(s) for s in g['scales'])
+    cls_prob, bbox_pred, info = P.make_proposal_case(int(g['seed']), H=int(g['H']), W=int(g['W']), A=3 * len(scales),
+                                                     im_info=tuple(g['im_info'][0]))
+    assert abs(checksum(dict(a=cls_prob, b=bbox_pred)) - float(g['input_checksum'])) < 1e-6 * float(g['input_checksum'])
+    np.testing.assert_array_equal(P.generate_anchors(16, (0.5, 1, 2), scales), g['anchors'])
+    rois, sc, aux = P.proposal_forward(cls_prob, bbox_pred, info, scales=scales, pre_nms_top_n=int(g['pre']),
+                                       post_nms_top_n=int(g['post']), return_aux=True)
+    # scores identify the selected anchors exactly (scores are unique): bit-exact proposal indices
+    k = aux['n_kept']
+    np.testing.assert_array_equal(sc[:k], g['scores'][:k])
+    # coordinates: the reference's float32 np.exp may differ from the correctly-rounded one by 1 ulp
+    np.testing.assert_allclose(rois[:k], g['rois'][:k], rtol=2e-6, atol=1e-4)
+
+
+def test_proposal_target_oracle_matches_reference_execution():
+    g = golden('proposal_target_300_7')
+    rois, label, bt, bw = P.proposal_target_forward(g['rois'], g['gt_boxes'])
+    np.testing.assert_array_equal(rois, g['rois_out'])
+    np.testing.assert_array_equal(label, g['label'])
+    np.testing.assert_array_equal(bw, g['bbox_weight'])
+    np.testing.assert_allclose(bt, g['bbox_target'], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(P.bbox_overlaps(g['rois'][:, 1:], g['gt_boxes'][:, :4]), g['overlaps_py'], rtol=1e-14)
+
+
+def test_misc_helpers_match_reference_execution():
+    g = golden('misc_helpers')
+    np.testing.assert_allclose(L.refine_boxes(g['boxes'], g['deltas'], g['im_info'])[:, :, 0], g['refined'][:, :, 0],
+                               rtol=1e-6, atol=1e-4)
+    np.testing.assert_allclose(L.refine_boxes(g['boxes'], g['deltas'], g['im_info'], (0, 0, 0, 0), (.1, .1, .2, .2)),
+                               g['refined_ms'], rtol=1e-6, atol=1e-4)
+    np.testing.assert_allclose(L.rank_embedding(100), g['rank_embedding'], atol=1e-5)
+    sb = g['sorted_bbox']
+    for c in range(sb.shape[1]):
+        np.testing.assert_allclose(R.position_matrix(sb[:, c]), g['multi_position_matrix'][c], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(P.decode_boxes(g['boxes'].astype(np.float64), g['deltas']), g['decoded'], rtol=1e-6)
+    np.testing.assert_allclose(P.encode_boxes(g['boxes'], g['boxes'][::-1].copy()), g['encoded'], rtol=1e-6, atol=1e-6)
