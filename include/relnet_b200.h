@@ -1,0 +1,220 @@
+/* relnet_b200.h -- C ABI of the B200-native Relation-Networks hot path (librelnet_b200.so).
+ *
+ * One shared library, extern "C", plain pointers and sizes: no torch / C++ types cross this boundary.
+ * Every entry point
+ *   - takes raw DEVICE pointers (unless a parameter says "host"), explicit shapes and a cudaStream_t (passed as
+ *     void*; NULL = legacy default stream);
+ *   - returns 0 on success, non-zero on error, with a thread-local message in rn_last_error();
+ *   - allocates nothing on the device: the caller passes a workspace of at least *_workspace_bytes(...);
+ *   - never synchronises the host with the device and never copies to the host;
+ *   - is safe to call concurrently from different threads on different streams.
+ * (One exception to "allocates nothing": the first plain-GEMM call on a thread creates that thread's cuBLAS handle.)
+ *
+ * All tensors are dense row-major float32 unless stated; MXNet layouts are kept (FC weight = [out, in]).
+ * Reference = msracver/Relation-Networks-for-Object-Detection; aliases as in SURVEY.md:
+ *   SYM_REL = relation_rcnn/symbols/resnet_v1_101_rcnn_attention_1024_pairwise_position_multi_head_16.py
+ *   LNMS    = relation_rcnn/operator_py/learn_nms.py
+ */
+#ifndef RELNET_B200_H_
+#define RELNET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RN_OK 0
+#define RN_ERR_INVALID 1   /* bad argument / unsupported shape */
+#define RN_ERR_WORKSPACE 2 /* workspace too small */
+#define RN_ERR_CUDA 3      /* CUDA / cuBLAS runtime error */
+
+typedef void* rn_stream_t; /* cudaStream_t */
+
+const char* rn_last_error(void);
+int rn_version(void);
+/* 1 when the running device is sm_100 (tcgen05/TMA paths usable); fills *sm_count if non-NULL */
+int rn_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Object-relation module.  Replaces extract_position_matrix (SYM_REL:47-83, FPN: SYM_FPN_REL_NMS:860-905),
+ * extract_position_embedding (SYM_REL:30-44), attention_module_multi_head (SYM_REL:85-151, FPN :907-977) and the
+ * caller's `fc_all = fc_new + attention; relu` (SYM_REL:267-268).  Also the per-class relation inside learn_nms
+ * (LNMS:45-127) through `batch`.
+ *
+ *   g[n,h,m] = max(relu(Wg[h,:].phi(eps(box_n, box_m)) + bg[h]), 1e-6)
+ *   p[n,h,:] = softmax_m( log g[n,h,m] + <q_h[n], k_h[m]>/sqrt(dk) )          q = X Wq^T + bq, k = X[keys] Wk^T + bk
+ *   o[n, h*dv:(h+1)*dv] = sum_m p[n,h,m] (X[keys] Wout^T)[m, h*dv:(h+1)*dv] + bout
+ *   out = fuse_residual_relu ? relu(X + o) : o
+ */
+enum { RN_PREC_FP32 = 0,  /* SIMT fp32 attention + cuBLAS fp32 projections: the bit-conservative parity mode */
+       RN_PREC_F16 = 1 }; /* fp16 operands / fp32 accumulate on tcgen05 tensor cores (sm_100a only) */
+
+typedef struct rn_relation_desc {
+  int32_t batch;      /* independent problems sharing the weights (1 for the detection head, #classes for learn-NMS) */
+  int32_t N;          /* queries per problem */
+  int32_t M;          /* keys per problem: rows key_index[0..M) of X, or the first M rows when key_index == NULL */
+  int32_t d;          /* feature dim of X */
+  int32_t dq;         /* total query/key dim = H * dk          (1024) */
+  int32_t dout;       /* total output dim    = H * dv          (1024; 128 in learn-NMS) */
+  int32_t H;          /* heads ("group" / fc_dim in the reference, 16) */
+  int32_t E;          /* position-embedding dim (64) */
+  float wave_length;  /* 1000 */
+  int32_t fuse_residual_relu; /* 1: out = relu(X + o) (needs dout == d) */
+  int32_t precision;  /* RN_PREC_* */
+} rn_relation_desc;
+
+size_t rn_relation_workspace_bytes(const rn_relation_desc* desc);
+
+/* X [batch, N, d]; boxes [batch, N, 4] (x1,y1,x2,y2); key_index int32 [M] or NULL (shared by the batch);
+ * Wq,Wk [dq,d]; bq,bk [dq]; Wg [H,E]; bg [H]; Wout [dout,d] (grouped 1x1 conv weight [dout,d,1,1]); bout [dout];
+ * out [batch, N, dout].  softmax_out (optional, may be NULL) [batch, N, H, M] = p, as the reference's 2nd output of
+ * attention_module_nms_multi_head (SYM_REL_NMS:158-238). */
+int rn_relation_fwd(const rn_relation_desc* desc, const float* X, const float* boxes, const int32_t* key_index,
+                    const float* Wq, const float* bq, const float* Wk, const float* bk, const float* Wg,
+                    const float* bg, const float* Wout, const float* bout, float* out, float* softmax_out,
+                    void* workspace, size_t workspace_bytes, rn_stream_t stream);
+
+/* Standalone a1+a2 for tests: eps_out [N,M,4] and/or emb_out [N,M,E] (either may be NULL). */
+int rn_pos_embed_fwd(const float* boxes, const int32_t* key_index, int32_t N, int32_t M, int32_t E, float wave_length,
+                     float* eps_out, float* emb_out, rn_stream_t stream);
+
+/* Geometry weight only: g_out [batch, H, N, M] = max(relu(Wg.phi + bg), 1e-6)  (SYM_REL:107-116 + the clamp of :139) */
+int rn_geometry_weight_fwd(const float* boxes, const int32_t* key_index, int32_t batch, int32_t N, int32_t M, int32_t H,
+                           int32_t E, float wave_length, const float* Wg, const float* bg, float* g_out,
+                           rn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Plain dense layer y = act(x W^T + b) used either side of the relation module (fc_new_1/2, cls_score, bbox_pred:
+ * SYM_REL:261-280).  x [rows, in], W [out, in], b [out] or NULL, y [rows, out]. relu: 0/1.  precision as above
+ * (RN_PREC_FP32 = cuBLAS SGEMM; RN_PREC_F16 = tcgen05 fp16 GEMM with fp32 accumulate). */
+size_t rn_linear_workspace_bytes(int32_t rows, int32_t in, int32_t out, int32_t precision);
+int rn_linear_fwd(const float* x, const float* W, const float* b, float* y, int32_t rows, int32_t in, int32_t out,
+                  int32_t relu, int32_t precision, void* workspace, size_t workspace_bytes, rn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * learn_nms CustomOp forward (LNMS:238-401) + test-time merge (SYM_REL_NMS:553-560).
+ * Inputs in the order of LearnNmsProp.list_arguments (LNMS:429-441). */
+typedef struct rn_learn_nms_desc {
+  int32_t R;              /* rows of cls_score / bbox_pred / rois / feat */
+  int32_t num_classes;    /* incl. background (81) */
+  int32_t num_reg_classes;/* 2 when class agnostic */
+  int32_t feat_dim;       /* 1024 */
+  int32_t first_n;        /* 100 */
+  int32_t num_thresh;     /* 5 */
+  double class_thresh;    /* TEST.LEARN_NMS_CLASS_SCORE_TH, 0.01 (python float in the reference) */
+  int32_t class_agnostic; /* 1 */
+  int32_t has_means_stds; /* 0 at test time (already folded into bbox_pred weights, SYM_REL_NMS:420-421) */
+  float means[4], stds[4];
+  int32_t nongt_dim;      /* >0: use the first nongt_dim rows; 0: use non_gt_index if given, else all rows */
+  int32_t num_non_gt;     /* length of non_gt_index (when nongt_dim == 0 and non_gt_index != NULL) */
+  int32_t merge_method;   /* -1 mean, -2 max, k>=0 pick threshold k   (config.TEST.MERGE_METHOD) */
+  int32_t precision;      /* RN_PREC_* for the projections / relation inside */
+} rn_learn_nms_desc;
+
+typedef struct rn_learn_nms_weights {
+  const float *nms_rank_weight, *nms_rank_bias;                 /* [128,1024],[128] */
+  const float *roi_feat_embedding_weight, *roi_feat_embedding_bias; /* [128,feat_dim],[128] */
+  const float *nms_pair_pos_fc1_1_weight, *nms_pair_pos_fc1_1_bias; /* [16,64],[16] */
+  const float *nms_query_1_weight, *nms_query_1_bias;           /* [1024,128],[1024] */
+  const float *nms_key_1_weight, *nms_key_1_bias;               /* [1024,128],[1024] */
+  const float *nms_linear_out_1_weight, *nms_linear_out_1_bias; /* [128,128,1,1],[128] */
+  const float *nms_logit_weight, *nms_logit_bias;               /* [T,128],[T] */
+} rn_learn_nms_weights;
+
+size_t rn_learn_nms_workspace_bytes(const rn_learn_nms_desc* desc);
+/* cls_score [R,num_classes], bbox_pred [R,4*num_reg_classes], rois [R,5], im_info [3] (device), feat [R,feat_dim],
+ * non_gt_index int32 [num_non_gt] or NULL.
+ * Outputs: nms_multi_score [n,C,T], sorted_bbox [n,C,4], sorted_score [n,C], final_score [n,C] (may be NULL). */
+int rn_learn_nms_fwd(const rn_learn_nms_desc* desc, const float* cls_score, const float* bbox_pred, const float* rois,
+                     const float* im_info, const float* feat, const rn_learn_nms_weights* w,
+                     const int32_t* non_gt_index, float* nms_multi_score, float* sorted_bbox, float* sorted_score,
+                     float* final_score, void* workspace, size_t workspace_bytes, rn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * `proposal` CustomOp forward (relation_rcnn/operator_py/proposal.py:51-168), device resident end to end.
+ * cls_prob [1,2A,Hf,Wf], bbox_pred [1,4A,Hf,Wf], im_info [3] (device).  scales/ratios are HOST arrays.
+ * rois_out [post,5], scores_out [post,1] or NULL.  num_kept_out (device int32[1], may be NULL) = boxes that survived
+ * NMS before padding.  Tie/padding rules: DESIGN.md "proposal". */
+typedef struct rn_proposal_desc {
+  int32_t Hf, Wf;           /* feature-map size of the inputs */
+  int32_t feat_stride;      /* 16 */
+  int32_t num_scales, num_ratios;
+  int32_t pre_nms_top_n;    /* 6000 */
+  int32_t post_nms_top_n;   /* 300 */
+  float nms_thresh;         /* 0.7 */
+  float min_size;           /* 0 */
+} rn_proposal_desc;
+size_t rn_proposal_workspace_bytes(const rn_proposal_desc* desc);
+int rn_proposal_fwd(const rn_proposal_desc* desc, const float* scales_host, const float* ratios_host,
+                    const float* cls_prob, const float* bbox_pred, const float* im_info, float* rois_out,
+                    float* scores_out, int32_t* num_kept_out, void* workspace, size_t workspace_bytes,
+                    rn_stream_t stream);
+
+/* Replaces `_nms` (lib/nms/gpu_nms.hpp:1, lib/nms/nms_kernel.cu:91-144) with device in/out and no host sweep.
+ * boxes [n, box_dim>=4] sorted by score; keep_out int32 [max_keep]; num_out int32[1].  IoU in float32, '>' thresh. */
+size_t rn_nms_workspace_bytes(int32_t n);
+int rn_nms(const float* boxes_sorted, int32_t n, int32_t box_dim, float thresh, int32_t max_keep, int32_t* keep_out,
+           int32_t* num_out, void* workspace, size_t workspace_bytes, rn_stream_t stream);
+
+/* Replaces bbox_overlaps_cython (lib/bbox/bbox.pyx:15-55): float64, +1 areas.  boxes [N,4] f64, query [K,4] f64. */
+int rn_bbox_overlaps(const double* boxes, const double* query, int32_t N, int32_t K, double* out, rn_stream_t stream);
+
+/* `proposal_target` CustomOp forward, BATCH_ROIS == -1 path (proposal_target.py:44-93 -> core/rcnn.py:288-325).
+ * rois [N,5], gt_boxes [G,5] -> rois_out [N+G,5], label [N+G], bbox_target [N+G,4R], bbox_weight [N+G,4R]. */
+typedef struct rn_proposal_target_desc {
+  int32_t N, G;
+  int32_t num_reg_classes;  /* R = 2 when class agnostic */
+  int32_t class_agnostic;
+  float bg_thresh_hi;       /* TRAIN.BG_THRESH_HI 0.5 */
+  int32_t normalize;        /* TRAIN.BBOX_NORMALIZATION_PRECOMPUTED */
+  double means[4], stds[4];
+  float bbox_weights[4];
+} rn_proposal_target_desc;
+int rn_proposal_target_fwd(const rn_proposal_target_desc* desc, const float* rois, const float* gt_boxes,
+                           float* rois_out, float* label, float* bbox_target, float* bbox_weight, rn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * ROIPooling (max; MXNet built-in used at SYM_REL:252-253).  data [B,C,H,W], rois [R,5] -> out [R,C,PH,PW],
+ * argmax int32 same shape (may be NULL). */
+int rn_roi_pool_fwd(const float* data, const float* rois, int32_t R, int32_t C, int32_t H, int32_t W, int32_t PH,
+                    int32_t PW, float spatial_scale, float* out, int32_t* argmax, rn_stream_t stream);
+
+/* DeformablePSROIPooling forward (operator_cxx/deformable_psroi_pooling.cu:52-138; = average ROIAlign when no_trans,
+ * group_size 1).  trans [R, 2*num_classes, part, part] or NULL when no_trans.  top_count may be NULL. */
+typedef struct rn_psroi_desc {
+  int32_t R, channels, H, W;
+  float spatial_scale;
+  int32_t output_dim, group_size, pooled_size, part_size, sample_per_part;
+  float trans_std;
+  int32_t no_trans, num_classes;
+} rn_psroi_desc;
+int rn_deform_psroi_pool_fwd(const rn_psroi_desc* desc, const float* data, const float* rois, const float* trans,
+                             float* out, float* top_count, rn_stream_t stream);
+
+/* DeformableConvolution forward (operator_cxx/deformable_convolution-inl.h:91-144 + nn/deformable_im2col.cuh:216-309).
+ * data [B,C,H,W], offset [B, dg*2*kh*kw, Ho, Wo], weight [Co, C/groups, kh, kw], bias [Co] or NULL -> out [B,Co,Ho,Wo] */
+typedef struct rn_deform_conv_desc {
+  int32_t B, C, H, W, Co;
+  int32_t kh, kw, pad_h, pad_w, stride_h, stride_w, dil_h, dil_w;
+  int32_t num_group, num_deformable_group;
+  int32_t precision;
+} rn_deform_conv_desc;
+size_t rn_deform_conv_workspace_bytes(const rn_deform_conv_desc* desc);
+int rn_deform_conv_fwd(const rn_deform_conv_desc* desc, const float* data, const float* offset, const float* weight,
+                       const float* bias, float* out, void* workspace, size_t workspace_bytes, rn_stream_t stream);
+/* the im2col stage alone (tests): col [C*kh*kw, Ho, Wo] for image b */
+int rn_deform_im2col(const rn_deform_conv_desc* desc, const float* data_b, const float* offset_b, float* col,
+                     rn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * tcgen05 self-test (sm_100a only): runs one 128x128x64 K-major and one 128x64x128 MN-major-B UMMA through TMA/TMEM and
+ * writes the fp32 results to out_s [128,128], out_o [128,64] for checking against a host product. */
+int rn_umma_selftest(const void* a_f16, const void* b_f16, const void* p_f16, const void* v_f16, float* out_s,
+                     float* out_o, rn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RELNET_B200_H_ */

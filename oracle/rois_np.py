@@ -1,0 +1,115 @@
+"""ctypes front-end to oracle_c.c (TEST INFRASTRUCTURE): ROIPooling(max), DeformablePSROIPooling, deformable conv,
+NMS sweep, and -- on the GPU box -- the reference's own compiled nms_kernel.cu (oracle/_ref/libref_gpu_nms.so)."""
+import ctypes
+import os
+import subprocess
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+
+
+def build(quiet=True):
+    subprocess.check_call(['make', '-C', HERE] + (['-s'] if quiet else []))
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(HERE, '_build', 'liboracle_c.so')
+        if not os.path.exists(path):
+            build()
+        _lib = ctypes.CDLL(path)
+    return _lib
+
+
+def _p(a, t=ctypes.c_float):
+    return a.ctypes.data_as(ctypes.POINTER(t))
+
+
+def roi_pool(data, rois, pooled=(7, 7), spatial_scale=0.0625):
+    data = np.ascontiguousarray(data, np.float32); rois = np.ascontiguousarray(rois, np.float32)
+    B, C, H, W = data.shape; R = rois.shape[0]
+    out = np.empty((R, C, pooled[0], pooled[1]), np.float32)
+    arg = np.empty(out.shape, np.int32)
+    lib().oracle_roi_pool(_p(data), _p(rois), R, C, H, W, pooled[0], pooled[1], ctypes.c_float(spatial_scale),
+                          _p(out), _p(arg, ctypes.c_int))
+    return out, arg
+
+
+def deform_psroi_pool(data, rois, trans=None, spatial_scale=0.0625, output_dim=256, group_size=1, pooled_size=7,
+                      part_size=0, sample_per_part=4, trans_std=0.0, no_trans=None):
+    data = np.ascontiguousarray(data, np.float32); rois = np.ascontiguousarray(rois, np.float32)
+    if no_trans is None:
+        no_trans = trans is None
+    part = part_size or pooled_size
+    B, C, H, W = data.shape; R = rois.shape[0]
+    ncls = 1 if no_trans else trans.shape[1] // 2
+    t = np.zeros(1, np.float32) if no_trans else np.ascontiguousarray(trans, np.float32)
+    out = np.empty((R, output_dim, pooled_size, pooled_size), np.float32)
+    cnt = np.empty_like(out)
+    lib().oracle_deform_psroi_pool(_p(data), _p(rois), _p(t), R, C, H, W, int(bool(no_trans)),
+                                   ctypes.c_float(spatial_scale), output_dim, group_size, pooled_size, part,
+                                   sample_per_part, ctypes.c_float(trans_std), ncls, _p(out), _p(cnt))
+    return out, cnt
+
+
+def deform_im2col(im, offset, kernel=(3, 3), pad=(2, 2), stride=(1, 1), dilate=(2, 2), num_deformable_group=4):
+    im = np.ascontiguousarray(im, np.float32); offset = np.ascontiguousarray(offset, np.float32)
+    C, H, W = im.shape
+    kh, kw = kernel
+    Ho = (H + 2 * pad[0] - (dilate[0] * (kh - 1) + 1)) // stride[0] + 1
+    Wo = (W + 2 * pad[1] - (dilate[1] * (kw - 1) + 1)) // stride[1] + 1
+    assert offset.shape == (num_deformable_group * 2 * kh * kw, Ho, Wo), offset.shape
+    col = np.empty((C * kh * kw, Ho, Wo), np.float32)
+    lib().oracle_deform_im2col(_p(im), _p(offset), C, H, W, kh, kw, pad[0], pad[1], stride[0], stride[1],
+                               dilate[0], dilate[1], num_deformable_group, Ho, Wo, _p(col))
+    return col
+
+
+def deform_conv(data, offset, weight, bias=None, kernel=(3, 3), pad=(2, 2), stride=(1, 1), dilate=(2, 2),
+                num_deformable_group=4, num_group=1):
+    """DeformableConvolutionOp::Forward (deformable_convolution-inl.h:91-144): im2col then W[g].col[g] per group."""
+    data = np.asarray(data, np.float32)
+    outs = []
+    for n in range(data.shape[0]):
+        col = deform_im2col(data[n], offset[n], kernel, pad, stride, dilate, num_deformable_group)
+        K, Ho, Wo = col.shape
+        Co = weight.shape[0]
+        w2 = np.asarray(weight, np.float32).reshape(num_group, Co // num_group, -1)
+        c2 = col.reshape(num_group, K // num_group, Ho * Wo)
+        o = np.matmul(w2, c2).reshape(Co, Ho, Wo)
+        if bias is not None:
+            o = o + np.asarray(bias, np.float32).reshape(-1, 1, 1)
+        outs.append(o)
+    return np.stack(outs).astype(np.float32)
+
+
+def nms_sorted(boxes, thresh):
+    boxes = np.ascontiguousarray(boxes, np.float32)
+    keep = np.empty(boxes.shape[0], np.int32)
+    n = lib().oracle_nms_sorted(_p(boxes), boxes.shape[0], boxes.shape[1], ctypes.c_float(thresh),
+                                _p(keep, ctypes.c_int))
+    return keep[:n].astype(np.int64)
+
+
+# ---------------------------------------------------------------------------------------------------------
+_ref = None
+
+
+def ref_gpu_nms_available():
+    return os.path.exists(os.path.join(HERE, '_ref', 'libref_gpu_nms.so'))
+
+
+def ref_gpu_nms(sorted_dets, thresh, device_id=0):
+    """Call the REFERENCE's own `_nms` (lib/nms/nms_kernel.cu:91-144, compiled into oracle/_ref) on host data.
+    sorted_dets [n,5] float32 sorted by score.  Needs a GPU."""
+    global _ref
+    if _ref is None:
+        _ref = ctypes.CDLL(os.path.join(HERE, '_ref', 'libref_gpu_nms.so'))
+    fn = getattr(_ref, '_Z4_nmsPiS_PKfiifi')      # void _nms(int*, int*, const float*, int, int, float, int)
+    d = np.ascontiguousarray(sorted_dets, np.float32)
+    keep = np.zeros(d.shape[0], np.int32)
+    num = ctypes.c_int(0)
+    fn(_p(keep, ctypes.c_int), ctypes.byref(num), _p(d), d.shape[0], d.shape[1], ctypes.c_float(thresh), device_id)
+    return keep[:num.value].astype(np.int64)

@@ -1,0 +1,95 @@
+// api.cu -- error string, device info and the cuBLAS plumbing for the *plain* GEMMs of the path.
+// (cuBLAS is used only for library-shaped dense layers in the fp32 parity mode; the fused relation kernels and the
+//  fp16 GEMMs are hand-written tcgen05 code in gemm_tc.cu / relation_tc.cu.)
+#include "common.cuh"
+#include <cublas_v2.h>
+#include <mutex>
+
+namespace rn {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static int g_sm_count = -1, g_cc_major = -1, g_cc_minor = -1;
+static std::once_flag g_dev_once;
+static void query_dev() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { g_sm_count = 0; g_cc_major = g_cc_minor = 0; cudaGetLastError(); return; }
+  cudaDeviceProp p;
+  if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) { g_sm_count = 0; g_cc_major = g_cc_minor = 0; cudaGetLastError(); return; }
+  g_sm_count = p.multiProcessorCount; g_cc_major = p.major; g_cc_minor = p.minor;
+}
+int sm_count() { std::call_once(g_dev_once, query_dev); return g_sm_count; }
+bool is_sm100() { std::call_once(g_dev_once, query_dev); return g_cc_major == 10; }
+
+struct CublasTls {
+  cublasHandle_t h = nullptr;
+  ~CublasTls() { if (h) cublasDestroy(h); }
+};
+static thread_local CublasTls g_cublas;
+
+static int get_cublas(cudaStream_t st, cublasHandle_t* out) {
+  if (!g_cublas.h) {
+    cublasStatus_t s = cublasCreate(&g_cublas.h);
+    if (s != CUBLAS_STATUS_SUCCESS) { set_error("cublasCreate failed: %d", (int)s); g_cublas.h = nullptr; return RN_ERR_CUDA; }
+    cublasSetMathMode(g_cublas.h, CUBLAS_PEDANTIC_MATH);   // true fp32: no TF32, no reduced-precision reductions
+  }
+  cublasStatus_t s = cublasSetStream(g_cublas.h, st);
+  if (s != CUBLAS_STATUS_SUCCESS) { set_error("cublasSetStream failed: %d", (int)s); return RN_ERR_CUDA; }
+  *out = g_cublas.h;
+  return RN_OK;
+}
+
+// row-major C[M,N] = A[M,K] . B[N,K]^T   <=> col-major C^T[N,M] = op_T(B as [K,N] ld ldb) . A^T ([K,M] ld lda)
+int sgemm_nt(cudaStream_t st, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+             int batch, long long sA, long long sB, long long sC) {
+  cublasHandle_t h;
+  int r = get_cublas(st, &h);
+  if (r) return r;
+  const float one = 1.f, zero = 0.f;
+  cublasStatus_t s;
+  if (batch == 1)
+    s = cublasSgemm(h, CUBLAS_OP_T, CUBLAS_OP_N, N, M, K, &one, B, ldb, A, lda, &zero, C, ldc);
+  else
+    s = cublasSgemmStridedBatched(h, CUBLAS_OP_T, CUBLAS_OP_N, N, M, K, &one, B, ldb, sB, A, lda, sA, &zero, C, ldc, sC,
+                                  batch);
+  if (s != CUBLAS_STATUS_SUCCESS) { set_error("cublasSgemm(nt %dx%dx%d) failed: %d", M, N, K, (int)s); return RN_ERR_CUDA; }
+  return RN_OK;
+}
+
+// row-major C[M,N] = A[M,K] . B[K,N]   <=> col-major C^T[N,M] = B^T ([N,K] ld ldb, op N) . A^T ([K,M] ld lda, op N)
+int sgemm_nn(cudaStream_t st, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+             int batch, long long sA, long long sB, long long sC) {
+  cublasHandle_t h;
+  int r = get_cublas(st, &h);
+  if (r) return r;
+  const float one = 1.f, zero = 0.f;
+  cublasStatus_t s;
+  if (batch == 1)
+    s = cublasSgemm(h, CUBLAS_OP_N, CUBLAS_OP_N, N, M, K, &one, B, ldb, A, lda, &zero, C, ldc);
+  else
+    s = cublasSgemmStridedBatched(h, CUBLAS_OP_N, CUBLAS_OP_N, N, M, K, &one, B, ldb, sB, A, lda, sA, &zero, C, ldc, sC,
+                                  batch);
+  if (s != CUBLAS_STATUS_SUCCESS) { set_error("cublasSgemm(nn %dx%dx%d) failed: %d", M, N, K, (int)s); return RN_ERR_CUDA; }
+  return RN_OK;
+}
+
+}  // namespace rn
+
+extern "C" {
+const char* rn_last_error(void) { return rn::g_err; }
+int rn_version(void) { return 100; }
+int rn_device_info(int* sm, int* major, int* minor) {
+  int n = rn::sm_count();
+  if (sm) *sm = n;
+  if (major) *major = rn::g_cc_major;
+  if (minor) *minor = rn::g_cc_minor;
+  return rn::is_sm100() ? 1 : 0;
+}
+}

@@ -1,0 +1,126 @@
+// deform_conv.cu -- DeformableConvolution forward (operator_cxx/deformable_convolution-inl.h:91-144):
+// deformable im2col (nn/deformable_im2col.cuh:216-262, bilinear :77-113) followed by a per-group GEMM W[g].col[g].
+// Compiled with -fmad=false so the bilinear arithmetic is bit-comparable with oracle/oracle_c.c.
+//
+// HBM layout: data [B,C,H,W], offset [B, dg*2*kh*kw, Ho, Wo], weight [Co, C/g*kh*kw], col workspace [C*kh*kw, Ho*Wo]
+// (44 MB at 512ch/38x63, written once and re-read by the GEMM -- round-1 shape of the op; the implicit-GEMM form that
+// never materialises col is listed under "next" in DESIGN.md).
+// Roofline: GEMM 2*Co*C*kh*kw*Ho*Wo FLOP (11.3 GFLOP/layer) on the tensor pipe; im2col is HBM-write bound (4*C*kh*kw*Ho*Wo B).
+#include "common.cuh"
+
+namespace rn {
+
+__device__ __forceinline__ float dim2col_bilinear(const float* __restrict__ d, int data_width, int height, int width,
+                                                  float h, float w) {
+  int h_low = (int)floorf(h), w_low = (int)floorf(w), h_high, w_high;
+  if (h_low >= height - 1) { h_high = h_low = height - 1; h = (float)h_low; } else h_high = h_low + 1;
+  if (w_low >= width - 1) { w_high = w_low = width - 1; w = (float)w_low; } else w_high = w_low + 1;
+  const float lh = h - h_low, lw = w - w_low, hh = 1 - lh, hw = 1 - lw;
+  const float v1 = __ldg(d + h_low * data_width + w_low), v2 = __ldg(d + h_low * data_width + w_high);
+  const float v3 = __ldg(d + h_high * data_width + w_low), v4 = __ldg(d + h_high * data_width + w_high);
+  const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
+  return w1 * v1 + w2 * v2 + w3 * v3 + w4 * v4;
+}
+
+// one thread = one (c_im, h_col, w_col); writes kh*kw column entries (coalesced along w_col)
+__global__ void __launch_bounds__(256) deform_im2col_kernel(size_t n, const float* __restrict__ im,
+                                                            const float* __restrict__ off, int H, int W, int kh, int kw,
+                                                            int pad_h, int pad_w, int sh, int sw, int dil_h, int dil_w,
+                                                            int cpg, int Ho, int Wo, float* __restrict__ col) {
+  for (size_t index = (size_t)blockIdx.x * blockDim.x + threadIdx.x; index < n; index += (size_t)gridDim.x * blockDim.x) {
+    const int w_col = index % Wo, h_col = (index / Wo) % Ho, c_im = (index / Wo) / Ho;
+    const int g = c_im / cpg;
+    const int h_in = h_col * sh - pad_h, w_in = w_col * sw - pad_w;
+    float* col_ptr = col + (((size_t)c_im * kh * kw) * Ho + h_col) * Wo + w_col;
+    const float* im_ptr = im + ((ptrdiff_t)c_im * H + h_in) * W + w_in;
+    const float* off_ptr = off + (size_t)g * 2 * kh * kw * Ho * Wo;
+    for (int i = 0; i < kh; ++i)
+      for (int j = 0; j < kw; ++j) {
+        const float oh = __ldg(off_ptr + ((size_t)(2 * (i * kw + j)) * Ho + h_col) * Wo + w_col);
+        const float ow = __ldg(off_ptr + ((size_t)(2 * (i * kw + j) + 1) * Ho + h_col) * Wo + w_col);
+        float val = 0.f;
+        const float h_im = h_in + i * dil_h + oh, w_im = w_in + j * dil_w + ow;
+        if (h_im >= 0 && w_im >= 0 && h_im < H && w_im < W) {
+          const float map_h = i * dil_h + oh, map_w = j * dil_w + ow;
+          val = dim2col_bilinear(im_ptr, W, H - h_in, W - w_in, map_h, map_w);
+        }
+        *col_ptr = val;
+        col_ptr += (size_t)Ho * Wo;
+      }
+  }
+}
+
+__global__ void add_channel_bias_kernel(float* __restrict__ y, const float* __restrict__ bias, int Co, size_t spatial) {
+  size_t total = (size_t)Co * spatial;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    y[i] += bias[i / spatial];
+}
+
+static void out_hw(const rn_deform_conv_desc* d, int* Ho, int* Wo) {
+  *Ho = (d->H + 2 * d->pad_h - (d->dil_h * (d->kh - 1) + 1)) / d->stride_h + 1;
+  *Wo = (d->W + 2 * d->pad_w - (d->dil_w * (d->kw - 1) + 1)) / d->stride_w + 1;
+}
+
+static int check(const rn_deform_conv_desc* d) {
+  RN_CHECK_ARG(d, "rn_deform_conv: null descriptor");
+  RN_CHECK_ARG(d->B > 0 && d->C > 0 && d->H > 0 && d->W > 0 && d->Co > 0 && d->kh > 0 && d->kw > 0, "rn_deform_conv: bad sizes");
+  RN_CHECK_ARG(d->num_group > 0 && d->C % d->num_group == 0 && d->Co % d->num_group == 0, "rn_deform_conv: bad num_group");
+  RN_CHECK_ARG(d->num_deformable_group > 0 && d->C % d->num_deformable_group == 0, "rn_deform_conv: bad num_deformable_group");
+  RN_CHECK_ARG(d->stride_h > 0 && d->stride_w > 0 && d->dil_h > 0 && d->dil_w > 0, "rn_deform_conv: bad stride/dilate");
+  return RN_OK;
+}
+
+static int launch_im2col(const rn_deform_conv_desc* d, const float* im, const float* off, float* col, cudaStream_t st) {
+  int Ho, Wo; out_hw(d, &Ho, &Wo);
+  size_t n = (size_t)d->C * Ho * Wo;
+  size_t blocks = (n + 255) / 256, cap = (size_t)(sm_count() > 0 ? sm_count() : 148) * 16;
+  deform_im2col_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(
+      n, im, off, d->H, d->W, d->kh, d->kw, d->pad_h, d->pad_w, d->stride_h, d->stride_w, d->dil_h, d->dil_w,
+      d->C / d->num_deformable_group, Ho, Wo, col);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
+
+}  // namespace rn
+
+extern "C" size_t rn_deform_conv_workspace_bytes(const rn_deform_conv_desc* d) {
+  if (!d) return 0;
+  int Ho, Wo; rn::out_hw(d, &Ho, &Wo);
+  return rn::ws_slice((size_t)d->C * d->kh * d->kw * Ho * Wo, 4) + 256;
+}
+
+extern "C" int rn_deform_im2col(const rn_deform_conv_desc* d, const float* data_b, const float* offset_b, float* col,
+                                rn_stream_t stream) {
+  int r = rn::check(d);
+  if (r) return r;
+  RN_CHECK_ARG(data_b && offset_b && col, "rn_deform_im2col: null pointer");
+  return rn::launch_im2col(d, data_b, offset_b, col, (cudaStream_t)stream);
+}
+
+extern "C" int rn_deform_conv_fwd(const rn_deform_conv_desc* d, const float* data, const float* offset,
+                                  const float* weight, const float* bias, float* out, void* wsp, size_t ws_bytes,
+                                  rn_stream_t stream) {
+  int r = rn::check(d);
+  if (r) return r;
+  RN_CHECK_ARG(data && offset && weight && out && wsp, "rn_deform_conv_fwd: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  int Ho, Wo; rn::out_hw(d, &Ho, &Wo);
+  const int K = d->C * d->kh * d->kw, Nsp = Ho * Wo, G = d->num_group;
+  rn::Workspace ws(wsp, ws_bytes);
+  float* col = ws.take<float>((size_t)K * Nsp);
+  if (!col) { rn::set_error("rn_deform_conv_fwd: workspace too small"); return RN_ERR_WORKSPACE; }
+  const size_t off_per = (size_t)d->num_deformable_group * 2 * d->kh * d->kw * Nsp;
+  for (int b = 0; b < d->B; ++b) {
+    if ((r = rn::launch_im2col(d, data + (size_t)b * d->C * d->H * d->W, offset + b * off_per, col, st))) return r;
+    float* ob = out + (size_t)b * d->Co * Nsp;
+    // out[g] (Co/G x Nsp) = W[g] (Co/G x K/G) . col[g] (K/G x Nsp)
+    if ((r = rn::sgemm_nn(st, d->Co / G, Nsp, K / G, weight, K / G, col, Nsp, ob, Nsp, G,
+                          (long long)(d->Co / G) * (K / G), (long long)(K / G) * Nsp, (long long)(d->Co / G) * Nsp)))
+      return r;
+    if (bias) {
+      rn::add_channel_bias_kernel<<<rn::cdiv(d->Co * Nsp, 256), 256, 0, st>>>(ob, bias, d->Co, (size_t)Nsp);
+      RN_LAUNCH_CHECK();
+    }
+  }
+  return RN_OK;
+}

@@ -1,0 +1,265 @@
+// learn_nms.cu -- learned-NMS duplicate-removal head, device resident (operator_py/learn_nms.py:238-401 = LNMS).
+// The reference op syncs with the host twice (LNMS:296, :382) and builds its index arrays in numpy; here every step
+// stays on the stream:
+//   prep     softmax over classes (LNMS:289) + refine_bbox_nd (LNMS:175-217)               1 thread / roi
+//   sort     per-class descending sort of the fg probabilities (LNMS:291, :306-308)        1 CTA / class (bitonic)
+//   valid    class pruning threshold min(class_thresh, global max) (LNMS:298-303)          1 warp
+//   gather   sorted_bbox (LNMS:311-323) and per-class features emb[idx] + rank_feat (LNMS:339-345)
+//   relation per-class object relation (LNMS:347-352 = nms_attention_nd) via rn_relation_fwd, batch = classes
+//   logits   128 -> T logits, sigmoid, times sorted score, pruned classes -> 0, merge over thresholds
+//            (LNMS:357-381, SYM_REL_NMS:553-560)
+// Layouts: prob [Rn,C], refined [Rn,4,K], rank_idx [n,C] int32, feat_cls [C,n,128], boxes_cls [C,n,4].
+#include "common.cuh"
+#include "relation.cuh"
+
+namespace rn {
+
+constexpr int kNmsFeat = 128;    // nms_attention_feat_dim (LNMS:223)
+constexpr int kRankDim = 1024;   // rank embedding dim (LNMS:328)
+
+__global__ void lnms_prep_kernel(rn_learn_nms_desc d, int Rn, const int* __restrict__ sel,
+                                 const float* __restrict__ cls_score, const float* __restrict__ bbox_pred,
+                                 const float* __restrict__ rois, const float* __restrict__ im_info,
+                                 float* __restrict__ prob, float* __restrict__ refined) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= Rn) return;
+  const int src = sel ? sel[r] : r;
+  const int NC = d.num_classes, C = NC - 1;
+  const float* s = cls_score + (size_t)src * NC;
+  float mx = s[0];
+  for (int c = 1; c < NC; ++c) mx = fmaxf(mx, s[c]);
+  float sum = 0.f;
+  for (int c = 0; c < NC; ++c) sum += expf(s[c] - mx);
+  for (int c = 1; c < NC; ++c) prob[(size_t)r * C + (c - 1)] = expf(s[c] - mx) / sum;
+  // refine_bbox_nd, LNMS:175-217
+  const float* b = rois + (size_t)src * 5 + 1;
+  const float w = b[2] - b[0] + 1.f, h = b[3] - b[1] + 1.f;
+  const float cx = 0.5f * (b[0] + b[2]), cy = 0.5f * (b[1] + b[3]);
+  const int K = d.num_reg_classes - 1;
+  const float lim_w = im_info[1] - 1.f, lim_h = im_info[0] - 1.f;
+  for (int k = 0; k < K; ++k) {
+    const float* dl = bbox_pred + (size_t)src * 4 * d.num_reg_classes + 4 + 4 * k;
+    float dx = dl[0], dy = dl[1], dw = dl[2], dh = dl[3];
+    if (d.has_means_stds) {
+      dx = dx * d.stds[0] + d.means[0]; dy = dy * d.stds[1] + d.means[1];
+      dw = dw * d.stds[2] + d.means[2]; dh = dh * d.stds[3] + d.means[3];
+    }
+    const float rcx = cx + w * dx, rcy = cy + h * dy;
+    const float rw = w * expf(dw), rh = h * expf(dh);
+    const float wo = 0.5f * (rw - 1.f), ho = 0.5f * (rh - 1.f);
+    float o[4] = {rcx - wo, rcy - ho, rcx + wo, rcy + ho};
+    o[0] = fmaxf(fminf(o[0], lim_w), 0.f); o[1] = fmaxf(fminf(o[1], lim_h), 0.f);
+    o[2] = fmaxf(fminf(o[2], lim_w), 0.f); o[3] = fmaxf(fminf(o[3], lim_h), 0.f);
+    for (int j = 0; j < 4; ++j) refined[((size_t)r * 4 + j) * K + k] = o[j];
+  }
+}
+
+// one CTA per fg class: descending bitonic sort of prob[:, c] with index, ties -> lower roi index first
+__global__ void __launch_bounds__(512) lnms_sort_kernel(const float* __restrict__ prob, int Rn, int C, int n,
+                                                        float* __restrict__ sorted_score, int* __restrict__ rank_idx,
+                                                        float* __restrict__ cmax) {
+  extern __shared__ uint8_t sm[];
+  int P = 1;
+  while (P < Rn) P <<= 1;
+  float* k = reinterpret_cast<float*>(sm);
+  int* ix = reinterpret_cast<int*>(sm + (size_t)P * 4);
+  const int c = blockIdx.x;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    k[i] = i < Rn ? prob[(size_t)i * C + c] : -INFINITY;
+    ix[i] = i < Rn ? i : 0x7fffffff;
+  }
+  __syncthreads();
+  for (int size = 2; size <= P; size <<= 1)
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+        const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const float ka = k[lo], kb = k[hi];
+        const int ia = ix[lo], ib = ix[hi];
+        const bool a_before_b = (ka > kb) || (ka == kb && ia < ib);
+        if (a_before_b != desc) { k[lo] = kb; k[hi] = ka; ix[lo] = ib; ix[hi] = ia; }
+      }
+      __syncthreads();
+    }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    sorted_score[(size_t)i * C + c] = k[i];
+    rank_idx[(size_t)i * C + c] = ix[i];
+  }
+  if (threadIdx.x == 0) cmax[c] = k[0];
+}
+
+__global__ void lnms_valid_kernel(const float* __restrict__ cmax, int C, double class_thresh, int* __restrict__ valid) {
+  float g = -INFINITY;
+  for (int c = threadIdx.x; c < C; c += 32) g = fmaxf(g, cmax[c]);
+  for (int o = 16; o; o >>= 1) g = fmaxf(g, __shfl_xor_sync(0xffffffffu, g, o));
+  const double th = fmin(class_thresh, (double)g);       // np.minimum(python float, float32 max) -> float64
+  for (int c = threadIdx.x; c < C; c += 32) valid[c] = ((double)cmax[c] >= th) ? 1 : 0;
+}
+
+// extract_rank_embedding_nd, LNMS:129-140: [n, 1024] = [sin(r / 1000^(2k/1024)), cos(...)], k < 512
+__global__ void lnms_rank_embed_kernel(int n, float* __restrict__ emb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int half = kRankDim / 2;
+  if (i >= n * half) return;
+  const int r = i / half, k = i % half;
+  const float dim = powf(1000.0f, (2.0f / (float)kRankDim) * (float)k);
+  float s, c;
+  sincosf((float)r / dim, &s, &c);
+  emb[(size_t)r * kRankDim + k] = s;
+  emb[(size_t)r * kRankDim + half + k] = c;
+}
+
+// sorted_bbox [n,C,4]; feat_cls [C,n,128] = emb[rank_idx] + rank_feat; boxes_cls [C,n,4]
+__global__ void lnms_gather_kernel(int n, int C, int K, int class_agnostic, const int* __restrict__ rank_idx,
+                                   const float* __restrict__ refined, const float* __restrict__ emb,
+                                   const float* __restrict__ rank_feat, float* __restrict__ sorted_bbox,
+                                   float* __restrict__ feat_cls, float* __restrict__ boxes_cls) {
+  const int i = blockIdx.x, c = blockIdx.y;
+  const int src = rank_idx[(size_t)i * C + c];
+  if (threadIdx.x < 4) {
+    const int k = class_agnostic ? 0 : c;
+    const float v = refined[((size_t)src * 4 + threadIdx.x) * K + k];
+    sorted_bbox[((size_t)i * C + c) * 4 + threadIdx.x] = v;
+    boxes_cls[((size_t)c * n + i) * 4 + threadIdx.x] = v;
+  }
+  for (int j = threadIdx.x; j < kNmsFeat; j += blockDim.x)
+    feat_cls[((size_t)c * n + i) * kNmsFeat + j] = emb[(size_t)src * kNmsFeat + j] + rank_feat[(size_t)i * kNmsFeat + j];
+}
+
+// one warp per (i, c): logits, sigmoid, score product, class pruning, merge
+__global__ void __launch_bounds__(128) lnms_logit_kernel(int n, int C, int T, const float* __restrict__ feat_out,
+                                                         const float* __restrict__ Wl, const float* __restrict__ bl,
+                                                         const float* __restrict__ sorted_score,
+                                                         const int* __restrict__ valid, int merge_method,
+                                                         float* __restrict__ multi, float* __restrict__ final_score) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n * C) return;
+  const int i = warp / C, c = warp % C;
+  const float* f = feat_out + ((size_t)c * n + i) * kNmsFeat;
+  float x[kNmsFeat / 32];
+#pragma unroll
+  for (int j = 0; j < kNmsFeat / 32; ++j) x[j] = f[lane + 32 * j];
+  const float sc = sorted_score[(size_t)i * C + c];
+  const bool ok = valid[c] != 0;
+  float acc_mean = 0.f, acc_max = -INFINITY, pick = 0.f;
+  for (int t = 0; t < T; ++t) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < kNmsFeat / 32; ++j) s = fmaf(x[j], Wl[(size_t)t * kNmsFeat + lane + 32 * j], s);
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    s += bl[t];
+    const float cond = ok ? 1.f / (1.f + expf(-s)) : 0.f;
+    const float m = sc * cond;
+    if (lane == 0) multi[((size_t)i * C + c) * T + t] = m;
+    acc_mean += m; acc_max = fmaxf(acc_max, m);
+    if (t == merge_method) pick = m;
+  }
+  if (lane == 0 && final_score)
+    final_score[(size_t)i * C + c] = merge_method == -1 ? acc_mean / (float)T : merge_method == -2 ? acc_max : pick;
+}
+
+struct LnmsWs {
+  float *prob, *refined, *cmax, *rank_emb, *rank_feat, *emb, *feat_cls, *boxes_cls, *feat_out;
+  int *rank_idx, *valid;
+  void* rel_ws; size_t rel_ws_bytes;
+};
+
+static rn_relation_desc inner_desc(const rn_learn_nms_desc* d) {
+  rn_relation_desc r;
+  r.batch = d->num_classes - 1; r.N = d->first_n; r.M = d->first_n; r.d = kNmsFeat; r.dq = 1024; r.dout = kNmsFeat;
+  r.H = 16; r.E = 64; r.wave_length = 1000.f; r.fuse_residual_relu = 1; r.precision = d->precision;
+  return r;
+}
+
+static size_t carve(const rn_learn_nms_desc* d, int Rn, void* base, size_t bytes, LnmsWs* w) {
+  const size_t C = d->num_classes - 1, n = d->first_n, K = d->num_reg_classes - 1;
+  rn_relation_desc rd = inner_desc(d);
+  const size_t rel = rn_relation_workspace_bytes(&rd);
+  size_t need = ws_slice((size_t)Rn * C, 4) + ws_slice((size_t)Rn * 4 * K, 4) + ws_slice(C, 4) +
+                ws_slice(n * kRankDim, 4) + ws_slice(n * kNmsFeat, 4) + ws_slice((size_t)d->R * kNmsFeat, 4) +
+                ws_slice(C * n * kNmsFeat, 4) + ws_slice(C * n * 4, 4) + ws_slice(C * n * kNmsFeat, 4) +
+                ws_slice(n * C, 4) + ws_slice(C, 4) + align_up(rel, 256);
+  if (!w) return need;
+  Workspace ws(base, bytes);
+  w->prob = ws.take<float>((size_t)Rn * C);
+  w->refined = ws.take<float>((size_t)Rn * 4 * K);
+  w->cmax = ws.take<float>(C);
+  w->rank_emb = ws.take<float>(n * kRankDim);
+  w->rank_feat = ws.take<float>(n * kNmsFeat);
+  w->emb = ws.take<float>((size_t)d->R * kNmsFeat);
+  w->feat_cls = ws.take<float>(C * n * kNmsFeat);
+  w->boxes_cls = ws.take<float>(C * n * 4);
+  w->feat_out = ws.take<float>(C * n * kNmsFeat);
+  w->rank_idx = ws.take<int>(n * C);
+  w->valid = ws.take<int>(C);
+  w->rel_ws = ws.take<char>(rel);
+  w->rel_ws_bytes = rel;
+  return w->rel_ws ? need : 0;
+}
+
+static int selected_rows(const rn_learn_nms_desc* d, const int* non_gt_index) {
+  if (d->nongt_dim > 0) return d->nongt_dim;
+  if (non_gt_index) return d->num_non_gt;
+  return d->R;
+}
+
+}  // namespace rn
+
+extern "C" size_t rn_learn_nms_workspace_bytes(const rn_learn_nms_desc* d) {
+  if (!d) return 0;
+  return rn::carve(d, d->R, nullptr, 0, nullptr) + 256;
+}
+
+extern "C" int rn_learn_nms_fwd(const rn_learn_nms_desc* d, const float* cls_score, const float* bbox_pred,
+                                const float* rois, const float* im_info, const float* feat,
+                                const rn_learn_nms_weights* w, const int32_t* non_gt_index, float* nms_multi_score,
+                                float* sorted_bbox, float* sorted_score, float* final_score, void* wsp, size_t ws_bytes,
+                                rn_stream_t stream) {
+  using namespace rn;
+  RN_CHECK_ARG(d && cls_score && bbox_pred && rois && im_info && feat && w && nms_multi_score && sorted_bbox &&
+                   sorted_score && wsp, "rn_learn_nms_fwd: null argument");
+  const int C = d->num_classes - 1, n = d->first_n, T = d->num_thresh, K = d->num_reg_classes - 1;
+  const int Rn = selected_rows(d, non_gt_index);
+  RN_CHECK_ARG(C >= 1 && n >= 1 && T >= 1 && K >= 1, "rn_learn_nms_fwd: bad sizes C=%d n=%d T=%d K=%d", C, n, T, K);
+  RN_CHECK_ARG(Rn >= n && Rn <= d->R, "rn_learn_nms_fwd: need first_n=%d <= non-gt rois=%d <= R=%d", n, Rn, d->R);
+  RN_CHECK_ARG(Rn <= 8192, "rn_learn_nms_fwd: %d rois exceed the per-class sort capacity 8192", Rn);
+  RN_CHECK_ARG(d->class_agnostic || K == C, "rn_learn_nms_fwd: class-specific boxes need num_reg_classes == num_classes");
+  RN_CHECK_ARG(d->merge_method >= -2 && d->merge_method < T, "rn_learn_nms_fwd: unknown merge method %d", d->merge_method);
+  cudaStream_t st = (cudaStream_t)stream;
+  LnmsWs W;
+  if (!carve(d, Rn, wsp, ws_bytes, &W)) { set_error("rn_learn_nms_fwd: workspace too small (%zu < %zu)", ws_bytes, rn_learn_nms_workspace_bytes(d)); return RN_ERR_WORKSPACE; }
+  const int* sel = d->nongt_dim > 0 ? nullptr : non_gt_index;
+  int r;
+  lnms_prep_kernel<<<cdiv(Rn, 128), 128, 0, st>>>(*d, Rn, sel, cls_score, bbox_pred, rois, im_info, W.prob, W.refined);
+  RN_LAUNCH_CHECK();
+  int P = 1; while (P < Rn) P <<= 1;
+  static thread_local bool sort_cfg = false;
+  if (!sort_cfg) {
+    RN_CUDA(cudaFuncSetAttribute(lnms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
+    sort_cfg = true;
+  }
+  lnms_sort_kernel<<<C, 512, (size_t)P * 8, st>>>(W.prob, Rn, C, n, sorted_score, W.rank_idx, W.cmax);
+  RN_LAUNCH_CHECK();
+  lnms_valid_kernel<<<1, 32, 0, st>>>(W.cmax, C, d->class_thresh, W.valid);
+  RN_LAUNCH_CHECK();
+  // rank feature (depends on weights only) and roi feature embedding
+  lnms_rank_embed_kernel<<<cdiv(n * kRankDim / 2, 256), 256, 0, st>>>(n, W.rank_emb);
+  RN_LAUNCH_CHECK();
+  if ((r = rn_linear_fwd(W.rank_emb, w->nms_rank_weight, w->nms_rank_bias, W.rank_feat, n, kRankDim, kNmsFeat, 0,
+                         RN_PREC_FP32, W.rel_ws, W.rel_ws_bytes, stream))) return r;
+  if ((r = rn_linear_fwd(feat, w->roi_feat_embedding_weight, w->roi_feat_embedding_bias, W.emb, d->R, d->feat_dim,
+                         kNmsFeat, 0, d->precision, W.rel_ws, W.rel_ws_bytes, stream))) return r;
+  lnms_gather_kernel<<<dim3(n, C), 128, 0, st>>>(n, C, K, d->class_agnostic, W.rank_idx, W.refined, W.emb, W.rank_feat,
+                                                 sorted_bbox, W.feat_cls, W.boxes_cls);
+  RN_LAUNCH_CHECK();
+  rn_relation_desc rd = inner_desc(d);
+  if ((r = rn_relation_fwd(&rd, W.feat_cls, W.boxes_cls, nullptr, w->nms_query_1_weight, w->nms_query_1_bias,
+                           w->nms_key_1_weight, w->nms_key_1_bias, w->nms_pair_pos_fc1_1_weight,
+                           w->nms_pair_pos_fc1_1_bias, w->nms_linear_out_1_weight, w->nms_linear_out_1_bias, W.feat_out,
+                           nullptr, W.rel_ws, W.rel_ws_bytes, stream))) return r;
+  lnms_logit_kernel<<<cdiv(n * C * 32, 128), 128, 0, st>>>(n, C, T, W.feat_out, w->nms_logit_weight, w->nms_logit_bias,
+                                                           sorted_score, W.valid, d->merge_method, nms_multi_score,
+                                                           final_score);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}

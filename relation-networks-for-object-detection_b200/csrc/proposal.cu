@@ -1,0 +1,421 @@
+// proposal.cu -- device-resident `proposal` op (operator_py/proposal.py:51-168), NMS (lib/nms/nms_kernel.cu),
+// fp64 IoU (lib/bbox/bbox.pyx) and `proposal_target` (operator_py/proposal_target.py:44-93, core/rcnn.py:288-325).
+// Compiled with -fmad=false: decode/encode follow numpy's separate mul/add roundings so indices are bit-exact.
+//
+// Pipeline (no host round trip, no hidden allocation; the reference does 2 full D2H copies, a numpy argsort, a
+// cudaMalloc'd NMS with a 4.5 MB mask D2H and a serial host sweep):
+//   decode+clip+filter (fp64, 1 thread/anchor)  -> keys (order-preserving uint32 of the fg score, 0 = filtered out)
+//   single-CTA bitonic sort of (key, index) in 192 KB of shared memory (n <= 32768), descending, ties -> larger index
+//   gather top pre_nms boxes as float32 -> 64x64 IoU bitmask tiles (upper triangle) -> one-CTA block sweep with early
+//   exit after post_nms kept -> emit rois (+ deterministic padding keep[i % kept]).
+// HBM traffic is ~1 MB of maps + <= 4.5 MB of mask: latency bound, not bandwidth bound (DESIGN.md "proposal").
+#include "common.cuh"
+
+namespace rn {
+
+constexpr int kMaxAnchors = 64;
+struct AnchorSet { double a[kMaxAnchors][4]; int A; };
+
+// lib/rpn/generate_anchor.py:22-86 in double (np.round = half-to-even; the products here never land on .5 for the
+// configured ratios/scales, and nearbyint() in the default rounding mode implements half-to-even anyway)
+static void generate_anchors_host(int base, const float* ratios, int nr, const float* scales, int ns, AnchorSet* out) {
+  const double w = base, h = base, xc = 0.5 * (base - 1), yc = 0.5 * (base - 1);
+  int k = 0;
+  for (int i = 0; i < nr; ++i) {
+    const double ws = nearbyint(sqrt(w * h / (double)ratios[i]));
+    const double hs = nearbyint(ws * (double)ratios[i]);
+    for (int j = 0; j < ns; ++j, ++k) {
+      const double W = ws * (double)scales[j], H = hs * (double)scales[j];
+      out->a[k][0] = xc - 0.5 * (W - 1); out->a[k][1] = yc - 0.5 * (H - 1);
+      out->a[k][2] = xc + 0.5 * (W - 1); out->a[k][3] = yc + 0.5 * (H - 1);
+    }
+  }
+  out->A = k;
+}
+
+__device__ __forceinline__ uint32_t float_to_ordered(float f) {
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// proposal.py:75-137 + bbox_transform.py:103-140 (nonlinear_pred, float64) + :45-60 (clip_boxes)
+__global__ void __launch_bounds__(256) proposal_decode_kernel(AnchorSet anc, const float* __restrict__ cls_prob,
+                                                              const float* __restrict__ bbox_pred,
+                                                              const float* __restrict__ im_info, int Hf, int Wf,
+                                                              int feat_stride, float min_size, double* __restrict__ props,
+                                                              uint32_t* __restrict__ keys, int* __restrict__ n_total_out) {
+  const int A = anc.A;
+  const float im_h = im_info[0], im_w = im_info[1], im_s = im_info[2];
+  const int height = min((int)(im_h / (float)feat_stride), Hf), width = min((int)(im_w / (float)feat_stride), Wf);
+  const int n = height * width * A;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *n_total_out = n;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int a = i % A, x = (i / A) % width, y = i / (A * width);
+  const size_t plane = (size_t)Hf * Wf, pix = (size_t)y * Wf + x;
+  const float score = cls_prob[(size_t)(A + a) * plane + pix];
+  const float dx = bbox_pred[(size_t)(4 * a + 0) * plane + pix], dy = bbox_pred[(size_t)(4 * a + 1) * plane + pix];
+  const float dw = bbox_pred[(size_t)(4 * a + 2) * plane + pix], dh = bbox_pred[(size_t)(4 * a + 3) * plane + pix];
+  const double sx = (double)(x * feat_stride), sy = (double)(y * feat_stride);
+  const double x1 = anc.a[a][0] + sx, y1 = anc.a[a][1] + sy, x2 = anc.a[a][2] + sx, y2 = anc.a[a][3] + sy;
+  const double w = x2 - x1 + 1.0, h = y2 - y1 + 1.0;
+  const double cx = x1 + 0.5 * (w - 1.0), cy = y1 + 0.5 * (h - 1.0);
+  const double pcx = (double)dx * w + cx, pcy = (double)dy * h + cy;
+  // np.exp on the float32 delta: defined as the correctly rounded float32 exp (oracle/proposal_np.py:decode_boxes)
+  const double pw = (double)(float)exp((double)dw) * w, ph = (double)(float)exp((double)dh) * h;
+  double bx1 = pcx - 0.5 * (pw - 1.0), by1 = pcy - 0.5 * (ph - 1.0);
+  double bx2 = pcx + 0.5 * (pw - 1.0), by2 = pcy + 0.5 * (ph - 1.0);
+  const double lim_w = (double)(im_w - 1.0f), lim_h = (double)(im_h - 1.0f);
+  bx1 = fmax(fmin(bx1, lim_w), 0.0); by1 = fmax(fmin(by1, lim_h), 0.0);
+  bx2 = fmax(fmin(bx2, lim_w), 0.0); by2 = fmax(fmin(by2, lim_h), 0.0);
+  const double ms = (double)(min_size * im_s);
+  const bool ok = (bx2 - bx1 + 1.0 >= ms) && (by2 - by1 + 1.0 >= ms);
+  double* p = props + (size_t)i * 4;
+  p[0] = bx1; p[1] = by1; p[2] = bx2; p[3] = by2;
+  keys[i] = ok ? float_to_ordered(score) : 0u;
+}
+
+// Single-CTA bitonic sort, descending by (key, index).  P = next power of two >= n, P <= 32768.
+__global__ void __launch_bounds__(1024) proposal_sort_kernel(const uint32_t* __restrict__ keys, const int* __restrict__ n_ptr,
+                                                             int pre_nms_top_n, int* __restrict__ order,
+                                                             int* __restrict__ n_pre_out) {
+  extern __shared__ uint8_t sm[];
+  const int n = *n_ptr;
+  int P = 1;
+  while (P < n) P <<= 1;
+  uint32_t* k = reinterpret_cast<uint32_t*>(sm);
+  uint16_t* ix = reinterpret_cast<uint16_t*>(sm + (size_t)P * 4);
+  __shared__ int s_valid;
+  if (threadIdx.x == 0) s_valid = 0;
+  __syncthreads();
+  int local_valid = 0;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    uint32_t key = i < n ? keys[i] : 0u;
+    k[i] = key; ix[i] = (uint16_t)(i < n ? i : 0xFFFF);
+    local_valid += (key != 0u);
+  }
+  atomicAdd(&s_valid, local_valid);
+  __syncthreads();
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+        const int lo = 2 * t - (t & (stride - 1));   // index with bit `stride` cleared
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);        // this bitonic block sorts descending
+        const uint32_t ka = k[lo], kb = k[hi];
+        const uint16_t ia = ix[lo], ib = ix[hi];
+        const bool a_before_b = (ka > kb) || (ka == kb && ia > ib);
+        if (a_before_b != desc) { k[lo] = kb; k[hi] = ka; ix[lo] = ib; ix[hi] = ia; }
+      }
+      __syncthreads();
+    }
+  }
+  int n_pre = s_valid;
+  if (pre_nms_top_n > 0 && n_pre > pre_nms_top_n) n_pre = pre_nms_top_n;
+  for (int i = threadIdx.x; i < n_pre; i += blockDim.x) order[i] = (int)ix[i];
+  if (threadIdx.x == 0) *n_pre_out = n_pre;
+}
+
+// det = hstack(proposals, scores).astype(float32)  (proposal.py:149)
+__global__ void proposal_gather_kernel(const double* __restrict__ props, const float* __restrict__ cls_prob,
+                                       const int* __restrict__ order, const int* __restrict__ n_pre_ptr, int A, int Hf,
+                                       int Wf, const float* __restrict__ im_info, int feat_stride,
+                                       float* __restrict__ det) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= *n_pre_ptr) return;
+  const int src = order[i];
+  const int width = min((int)(im_info[1] / (float)feat_stride), Wf);
+  const int a = src % A, x = (src / A) % width, y = src / (A * width);
+  const double* p = props + (size_t)src * 4;
+  float* d = det + (size_t)i * 5;
+  d[0] = (float)p[0]; d[1] = (float)p[1]; d[2] = (float)p[2]; d[3] = (float)p[3];
+  d[4] = cls_prob[(size_t)(A + a) * Hf * Wf + (size_t)y * Wf + x];
+}
+
+// lib/nms/nms_kernel.cu:24-32, float32 op for op
+__device__ __forceinline__ float dev_iou(const float* a, const float* b) {
+  const float left = fmaxf(a[0], b[0]), right = fminf(a[2], b[2]);
+  const float top = fmaxf(a[1], b[1]), bottom = fminf(a[3], b[3]);
+  const float width = fmaxf(right - left + 1, 0.f), height = fmaxf(bottom - top + 1, 0.f);
+  const float interS = width * height;
+  const float Sa = (a[2] - a[0] + 1) * (a[3] - a[1] + 1);
+  const float Sb = (b[2] - b[0] + 1) * (b[3] - b[1] + 1);
+  return interS / (Sa + Sb - interS);
+}
+
+// 64x64 tile of the suppression matrix (nms_kernel.cu:34-78); only tiles on/above the diagonal are needed by the sweep
+__global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ boxes, int box_dim,
+                                                      const int* __restrict__ n_ptr, int col_blocks_ld, float thresh,
+                                                      unsigned long long* __restrict__ mask) {
+  const int n = *n_ptr;
+  const int row_start = blockIdx.y, col_start = blockIdx.x;
+  if (row_start > col_start) return;
+  if (row_start * 64 >= n || col_start * 64 >= n) return;
+  const int row_size = min(n - row_start * 64, 64), col_size = min(n - col_start * 64, 64);
+  __shared__ float bb[64 * 4];
+  if (threadIdx.x < col_size) {
+    const float* s = boxes + (size_t)(64 * col_start + threadIdx.x) * box_dim;
+    bb[threadIdx.x * 4 + 0] = s[0]; bb[threadIdx.x * 4 + 1] = s[1];
+    bb[threadIdx.x * 4 + 2] = s[2]; bb[threadIdx.x * 4 + 3] = s[3];
+  }
+  __syncthreads();
+  if (threadIdx.x < row_size) {
+    const int cur = 64 * row_start + threadIdx.x;
+    const float* cb = boxes + (size_t)cur * box_dim;
+    const float c4[4] = {cb[0], cb[1], cb[2], cb[3]};
+    unsigned long long t = 0;
+    const int start = (row_start == col_start) ? threadIdx.x + 1 : 0;
+    for (int i = start; i < col_size; ++i)
+      if (dev_iou(c4, bb + i * 4) > thresh) t |= 1ULL << i;
+    mask[(size_t)cur * col_blocks_ld + col_start] = t;
+  }
+}
+
+// Greedy sweep (nms_kernel.cu:124-139) on the device, 64 boxes per step, early exit once max_keep are kept.
+__global__ void __launch_bounds__(128) nms_sweep_kernel(const unsigned long long* __restrict__ mask,
+                                                        const int* __restrict__ n_ptr, int col_blocks_ld, int max_keep,
+                                                        int* __restrict__ keep_out, int* __restrict__ num_out) {
+  extern __shared__ unsigned long long remv[];      // [col_blocks]
+  __shared__ unsigned long long diag[64];
+  __shared__ int kept_local[64];
+  __shared__ int s_nk_local, s_total;
+  const int n = *n_ptr;
+  const int col_blocks = (n + 63) / 64;
+  for (int i = threadIdx.x; i < col_blocks; i += blockDim.x) remv[i] = 0ULL;
+  if (threadIdx.x == 0) s_total = 0;
+  __syncthreads();
+  for (int blk = 0; blk < col_blocks; ++blk) {
+    const int base = blk * 64, cnt = min(64, n - base);
+    if (threadIdx.x < 64) diag[threadIdx.x] = threadIdx.x < cnt ? mask[(size_t)(base + threadIdx.x) * col_blocks_ld + blk] : 0ULL;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long cur = remv[blk];
+      int nk = 0, total = s_total;
+      for (int i = 0; i < cnt && total < max_keep; ++i) {
+        if (!((cur >> i) & 1ULL)) {
+          kept_local[nk++] = i;
+          keep_out[total++] = base + i;
+          cur |= diag[i];
+        }
+      }
+      s_nk_local = nk; s_total = total;
+    }
+    __syncthreads();
+    if (s_total >= max_keep) break;
+    const int nk = s_nk_local;
+    for (int w = blk + 1 + threadIdx.x; w < col_blocks; w += blockDim.x) {
+      unsigned long long acc = remv[w];
+      for (int j = 0; j < nk; ++j) acc |= mask[(size_t)(base + kept_local[j]) * col_blocks_ld + w];
+      remv[w] = acc;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *num_out = s_total;
+}
+
+// proposal.py:151-168: take post_nms, pad, emit [0, x1, y1, x2, y2] float32 (+ scores)
+__global__ void proposal_emit_kernel(const float* __restrict__ det, const int* __restrict__ keep,
+                                     const int* __restrict__ num_kept_ptr, int post, float* __restrict__ rois,
+                                     float* __restrict__ scores, int* __restrict__ num_kept_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nk = *num_kept_ptr;
+  if (i == 0 && num_kept_out) *num_kept_out = nk;
+  if (i >= post) return;
+  float* r = rois + (size_t)i * 5;
+  if (nk <= 0) { r[0] = r[1] = r[2] = r[3] = r[4] = 0.f; if (scores) scores[i] = 0.f; return; }
+  const int src = keep[i < nk ? i : (i - nk) % nk];
+  const float* d = det + (size_t)src * 5;
+  r[0] = 0.f; r[1] = d[0]; r[2] = d[1]; r[3] = d[2]; r[4] = d[3];
+  if (scores) scores[i] = d[4];
+}
+
+// lib/bbox/bbox.pyx:15-55
+__device__ __forceinline__ double iou_f64(const double* b, const double* q) {
+  const double iw = fmin(b[2], q[2]) - fmax(b[0], q[0]) + 1;
+  if (iw <= 0) return 0.0;
+  const double ih = fmin(b[3], q[3]) - fmax(b[1], q[1]) + 1;
+  if (ih <= 0) return 0.0;
+  const double qa = (q[2] - q[0] + 1) * (q[3] - q[1] + 1);
+  const double ua = (b[2] - b[0] + 1) * (b[3] - b[1] + 1) + qa - iw * ih;
+  return iw * ih / ua;
+}
+
+__global__ void bbox_overlaps_kernel(const double* __restrict__ boxes, const double* __restrict__ query, int N, int K,
+                                     double* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)N * K) return;
+  const int n = i / K, k = i % K;
+  out[i] = iou_f64(boxes + (size_t)n * 4, query + (size_t)k * 4);
+}
+
+// proposal_target.py:44-93 (BATCH_ROIS = -1) -> rcnn.py:288-325 -> bbox_transform.py:74-100 -> bbox_regression.py:120-140
+__global__ void proposal_target_kernel(rn_proposal_target_desc d, const float* __restrict__ rois,
+                                       const float* __restrict__ gt, float* __restrict__ rois_out,
+                                       float* __restrict__ label, float* __restrict__ bt, float* __restrict__ bw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int T = d.N + d.G;
+  if (i >= T) return;
+  float r[5];
+  if (i < d.N) { for (int j = 0; j < 5; ++j) r[j] = rois[(size_t)i * 5 + j]; }
+  else { const float* g = gt + (size_t)(i - d.N) * 5; r[0] = 0.f; r[1] = g[0]; r[2] = g[1]; r[3] = g[2]; r[4] = g[3]; }
+  for (int j = 0; j < 5; ++j) rois_out[(size_t)i * 5 + j] = r[j];
+  const int R = d.class_agnostic ? 2 : d.num_reg_classes;
+  for (int j = 0; j < 4 * R; ++j) { bt[(size_t)i * 4 * R + j] = 0.f; bw[(size_t)i * 4 * R + j] = 0.f; }
+  if (d.G == 0) { label[i] = 0.f; return; }
+  const double b[4] = {(double)r[1], (double)r[2], (double)r[3], (double)r[4]};
+  double best = -1.0; int arg = 0;
+  for (int k = 0; k < d.G; ++k) {
+    const float* g = gt + (size_t)k * 5;
+    const double q[4] = {(double)g[0], (double)g[1], (double)g[2], (double)g[3]};
+    const double ov = iou_f64(b, q);
+    if (ov > best) { best = ov; arg = k; }            // first maximum, like ndarray.argmax
+  }
+  const float* g = gt + (size_t)arg * 5;
+  float lab = g[4];
+  if (best < (double)d.bg_thresh_hi) lab = 0.f;
+  label[i] = lab;
+  if (lab > 0.f) {
+    // nonlinear_transform in float32 (inputs are float32 arrays)
+    const float ew = r[3] - r[1] + 1.0f, eh = r[4] - r[2] + 1.0f;
+    const float ecx = r[1] + 0.5f * (ew - 1.0f), ecy = r[2] + 0.5f * (eh - 1.0f);
+    const float gw = g[2] - g[0] + 1.0f, gh = g[3] - g[1] + 1.0f;
+    const float gcx = g[0] + 0.5f * (gw - 1.0f), gcy = g[1] + 0.5f * (gh - 1.0f);
+    float t[4] = {(gcx - ecx) / (ew + 1e-14f), (gcy - ecy) / (eh + 1e-14f), logf(gw / ew), logf(gh / eh)};
+    const int s = d.class_agnostic ? 4 : 4 * (int)lab;
+    for (int j = 0; j < 4; ++j) {
+      const float v = d.normalize ? (float)(((double)t[j] - d.means[j]) / d.stds[j]) : t[j];
+      bt[(size_t)i * 4 * R + s + j] = v;
+      bw[(size_t)i * 4 * R + s + j] = d.bbox_weights[j];
+    }
+  }
+}
+
+__global__ void set_int_kernel(int* p, int v) { *p = v; }
+
+struct ProposalWs {
+  double* props; uint32_t* keys; int* order; float* det; unsigned long long* mask; int* keep; int* counters;
+  int n_max, pre, col_blocks;
+};
+
+static size_t carve(const rn_proposal_desc* d, void* base, size_t bytes, ProposalWs* w) {
+  const int A = d->num_scales * d->num_ratios;
+  const int n_max = d->Hf * d->Wf * A;
+  const int pre = d->pre_nms_top_n > 0 ? (d->pre_nms_top_n < n_max ? d->pre_nms_top_n : n_max) : n_max;
+  const int cb = (pre + 63) / 64;
+  size_t need = ws_slice((size_t)n_max * 4, 8) + ws_slice(n_max, 4) + ws_slice(pre, 4) + ws_slice((size_t)pre * 5, 4) +
+                ws_slice((size_t)pre * cb, 8) + ws_slice(d->post_nms_top_n > 0 ? d->post_nms_top_n : pre, 4) + ws_slice(8, 4);
+  if (!w) return need;
+  Workspace ws(base, bytes);
+  w->n_max = n_max; w->pre = pre; w->col_blocks = cb;
+  w->props = ws.take<double>((size_t)n_max * 4);
+  w->keys = ws.take<uint32_t>(n_max);
+  w->order = ws.take<int>(pre);
+  w->det = ws.take<float>((size_t)pre * 5);
+  w->mask = ws.take<unsigned long long>((size_t)pre * cb);
+  w->keep = ws.take<int>(d->post_nms_top_n > 0 ? d->post_nms_top_n : pre);
+  w->counters = ws.take<int>(8);
+  return w->counters ? need : 0;
+}
+
+static int launch_nms(cudaStream_t st, const float* boxes, int box_dim, const int* n_ptr, int n_max, float thresh,
+                      int max_keep, unsigned long long* mask, int* keep, int* num_out) {
+  const int cb = (n_max + 63) / 64;
+  nms_mask_kernel<<<dim3(cb, cb), 64, 0, st>>>(boxes, box_dim, n_ptr, cb, thresh, mask);
+  RN_LAUNCH_CHECK();
+  nms_sweep_kernel<<<1, 128, (size_t)cb * 8, st>>>(mask, n_ptr, cb, max_keep, keep, num_out);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
+
+}  // namespace rn
+
+extern "C" size_t rn_proposal_workspace_bytes(const rn_proposal_desc* d) {
+  if (!d) return 0;
+  return rn::carve(d, nullptr, 0, nullptr) + 256;
+}
+
+extern "C" int rn_proposal_fwd(const rn_proposal_desc* d, const float* scales_host, const float* ratios_host,
+                               const float* cls_prob, const float* bbox_pred, const float* im_info, float* rois_out,
+                               float* scores_out, int32_t* num_kept_out, void* wsp, size_t ws_bytes, rn_stream_t stream) {
+  using namespace rn;
+  RN_CHECK_ARG(d && scales_host && ratios_host && cls_prob && bbox_pred && im_info && rois_out && wsp,
+               "rn_proposal_fwd: null argument");
+  const int A = d->num_scales * d->num_ratios;
+  RN_CHECK_ARG(A > 0 && A <= kMaxAnchors, "rn_proposal_fwd: %d anchors per cell unsupported (1..%d)", A, kMaxAnchors);
+  RN_CHECK_ARG(d->post_nms_top_n > 0, "rn_proposal_fwd: post_nms_top_n must be > 0");
+  const int n_max = d->Hf * d->Wf * A;
+  RN_CHECK_ARG(n_max > 0 && n_max <= 32768, "rn_proposal_fwd: %d anchors exceed the single-CTA sort capacity 32768", n_max);
+  ProposalWs w;
+  if (!carve(d, wsp, ws_bytes, &w)) { set_error("rn_proposal_fwd: workspace too small (%zu < %zu)", ws_bytes, rn_proposal_workspace_bytes(d)); return RN_ERR_WORKSPACE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  AnchorSet anc;
+  generate_anchors_host(d->feat_stride, ratios_host, d->num_ratios, scales_host, d->num_scales, &anc);
+  int* n_total = w.counters; int* n_pre = w.counters + 1; int* n_kept = w.counters + 2;
+  proposal_decode_kernel<<<cdiv(n_max, 256), 256, 0, st>>>(anc, cls_prob, bbox_pred, im_info, d->Hf, d->Wf,
+                                                           d->feat_stride, d->min_size, w.props, w.keys, n_total);
+  RN_LAUNCH_CHECK();
+  int P = 1; while (P < n_max) P <<= 1;
+  const size_t sort_smem = (size_t)P * 6;
+  static thread_local size_t configured = 0;
+  if (sort_smem > configured) {
+    RN_CUDA(cudaFuncSetAttribute(proposal_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
+    configured = sort_smem;
+  }
+  proposal_sort_kernel<<<1, 1024, sort_smem, st>>>(w.keys, n_total, d->pre_nms_top_n, w.order, n_pre);
+  RN_LAUNCH_CHECK();
+  proposal_gather_kernel<<<cdiv(w.pre, 256), 256, 0, st>>>(w.props, cls_prob, w.order, n_pre, A, d->Hf, d->Wf, im_info,
+                                                           d->feat_stride, w.det);
+  RN_LAUNCH_CHECK();
+  int r = launch_nms(st, w.det, 5, n_pre, w.pre, d->nms_thresh, d->post_nms_top_n, w.mask, w.keep, n_kept);
+  if (r) return r;
+  proposal_emit_kernel<<<cdiv(d->post_nms_top_n, 128), 128, 0, st>>>(w.det, w.keep, n_kept, d->post_nms_top_n, rois_out,
+                                                                     scores_out, num_kept_out);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
+
+extern "C" size_t rn_nms_workspace_bytes(int32_t n) {
+  const size_t cb = (n + 63) / 64;
+  return rn::ws_slice((size_t)n * cb, 8) + rn::ws_slice(4, 4) + 256;
+}
+
+extern "C" int rn_nms(const float* boxes_sorted, int32_t n, int32_t box_dim, float thresh, int32_t max_keep,
+                      int32_t* keep_out, int32_t* num_out, void* wsp, size_t ws_bytes, rn_stream_t stream) {
+  using namespace rn;
+  RN_CHECK_ARG(boxes_sorted && keep_out && num_out && wsp && n >= 0 && box_dim >= 4 && max_keep > 0, "rn_nms: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace ws(wsp, ws_bytes);
+  const int cb = (n + 63) / 64;
+  unsigned long long* mask = ws.take<unsigned long long>((size_t)n * cb + 1);
+  int* n_dev = ws.take<int>(4);
+  if (!n_dev) { set_error("rn_nms: workspace too small"); return RN_ERR_WORKSPACE; }
+  RN_CUDA(cudaMemsetAsync(num_out, 0, sizeof(int), st));
+  if (n == 0) return RN_OK;
+  // the mask/sweep kernels read n from device memory (in rn_proposal_fwd it is produced on the device); here it is a
+  // host value, staged by a 1-thread kernel so the call stays asynchronous
+  set_int_kernel<<<1, 1, 0, st>>>(n_dev, n);
+  RN_LAUNCH_CHECK();
+  return launch_nms(st, boxes_sorted, box_dim, n_dev, n, thresh, max_keep, mask, keep_out, num_out);
+}
+
+extern "C" int rn_bbox_overlaps(const double* boxes, const double* query, int32_t N, int32_t K, double* out,
+                                rn_stream_t stream) {
+  RN_CHECK_ARG(N >= 0 && K >= 0, "rn_bbox_overlaps: bad sizes");
+  if (N == 0 || K == 0) return RN_OK;
+  RN_CHECK_ARG(boxes && query && out, "rn_bbox_overlaps: null pointer");
+  rn::bbox_overlaps_kernel<<<rn::cdiv(N * K, 256), 256, 0, (cudaStream_t)stream>>>(boxes, query, N, K, out);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
+
+extern "C" int rn_proposal_target_fwd(const rn_proposal_target_desc* d, const float* rois, const float* gt_boxes,
+                                      float* rois_out, float* label, float* bbox_target, float* bbox_weight,
+                                      rn_stream_t stream) {
+  RN_CHECK_ARG(d && rois_out && label && bbox_target && bbox_weight && d->N >= 0 && d->G >= 0, "rn_proposal_target_fwd: bad arguments");
+  RN_CHECK_ARG((d->N == 0 || rois) && (d->G == 0 || gt_boxes), "rn_proposal_target_fwd: null input");
+  if (d->N + d->G == 0) return RN_OK;
+  rn::proposal_target_kernel<<<rn::cdiv(d->N + d->G, 128), 128, 0, (cudaStream_t)stream>>>(*d, rois, gt_boxes, rois_out,
+                                                                                         label, bbox_target, bbox_weight);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}

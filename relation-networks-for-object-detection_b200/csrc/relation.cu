@@ -1,0 +1,213 @@
+// relation.cu -- rn_relation_fwd / rn_linear_fwd: argument checking, workspace carving and the fp32 parity path.
+//
+// RN_PREC_FP32 evaluates the module with the reference's own op decomposition (SYM_REL:104-151) on library GEMMs:
+//   Q,K,V' projections (cuBLAS SGEMM, pedantic fp32) -> geometry weight kernel (geom.cu) -> S_h = Q_h K_h^T (batched
+//   SGEMM over heads) -> row softmax of log g + s/sqrt(dk), evaluated as g*exp(s - max) (exp(log g) == g) -> O_h =
+//   P_h V'_h (batched SGEMM) -> bias / residual / relu epilogue.   V' = X_keys Wout^T is the SURVEY section 3.3
+//   identity (project once instead of P.V over the full d then a grouped 1x1 conv).
+// RN_PREC_F16 dispatches to the fused tcgen05 kernels in relation_tc.cu (sm_100a).
+#include "common.cuh"
+#include "geom.cuh"
+#include "relation.cuh"
+
+namespace rn {
+
+__global__ void bias_act_kernel(float* __restrict__ y, const float* __restrict__ bias, size_t rows, int cols, int relu) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = rows * (size_t)cols;
+  for (; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    float v = y[i] + (bias ? bias[i % cols] : 0.f);
+    y[i] = relu ? fmaxf(v, 0.f) : v;
+  }
+}
+
+int launch_bias_act(cudaStream_t st, float* y, const float* bias, size_t rows, int cols, int relu) {
+  if (!bias && !relu) return RN_OK;
+  size_t total = rows * (size_t)cols;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  bias_act_kernel<<<blocks, 256, 0, st>>>(y, bias, rows, cols, relu);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ X, const int* __restrict__ idx, int B, int N, int M, int d,
+                                   float* __restrict__ out) {
+  const int m = blockIdx.x, b = blockIdx.y;
+  const float* src = X + ((size_t)b * N + idx[m]) * d;
+  float* dst = out + ((size_t)b * M + m) * d;
+  for (int i = threadIdx.x; i < d; i += blockDim.x) dst[i] = src[i];
+}
+
+// one warp per (b,h,n) row: p = g*exp2((s - max s)*c) / sum   (in place over s; optional copy to softmax_out [B,N,H,M])
+__global__ void __launch_bounds__(256) geo_softmax_rows_kernel(float* __restrict__ S, const float* __restrict__ g,
+                                                               int B, int H, int N, int M, int ld, float scale,
+                                                               float* __restrict__ softmax_out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int rows = B * H * N;
+  if (warp >= rows) return;
+  float* s = S + (size_t)warp * ld;
+  const float* gr = g + (size_t)warp * ld;
+  // the reference takes the max over log g + s; any stabiliser gives the same softmax -- we use the same one
+  float mx = -INFINITY;
+  for (int m = lane; m < M; m += 32) mx = fmaxf(mx, logf(gr[m]) + s[m] * scale);
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+  for (int m = lane; m < M; m += 32) {
+    float e = expf(logf(gr[m]) + s[m] * scale - mx);
+    s[m] = e; sum += e;
+  }
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = 1.f / sum;
+  const int n = warp % N, h = (warp / N) % H, b = warp / (N * H);
+  for (int m = lane; m < M; m += 32) {
+    float p = s[m] * inv;
+    s[m] = p;
+    if (softmax_out) softmax_out[(((size_t)b * N + n) * H + h) * M + m] = p;
+  }
+}
+
+// out = (residual_relu ? relu(X + o + bout) : o + bout)
+__global__ void relation_epilogue_kernel(const float* __restrict__ O, const float* __restrict__ bout,
+                                         const float* __restrict__ X, size_t rows, int dout, int residual_relu,
+                                         float* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = rows * (size_t)dout;
+  for (; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    float v = O[i] + bout[i % dout];
+    if (residual_relu) v = fmaxf(X[i] + v, 0.f);
+    out[i] = v;
+  }
+}
+
+static int check_desc(const rn_relation_desc* d) {
+  RN_CHECK_ARG(d, "rn_relation: null descriptor");
+  RN_CHECK_ARG(d->batch >= 1 && d->N >= 1 && d->M >= 1 && d->d >= 1, "rn_relation: bad sizes batch=%d N=%d M=%d d=%d",
+               d->batch, d->N, d->M, d->d);
+  RN_CHECK_ARG(d->H >= 1 && d->H <= 16, "rn_relation: H=%d unsupported (1..16)", d->H);
+  RN_CHECK_ARG(d->dq % d->H == 0 && d->dout % d->H == 0, "rn_relation: dq=%d / dout=%d not divisible by H=%d", d->dq,
+               d->dout, d->H);
+  RN_CHECK_ARG(!d->fuse_residual_relu || d->dout == d->d, "rn_relation: residual needs dout == d (%d vs %d)", d->dout,
+               d->d);
+  RN_CHECK_ARG(d->precision == RN_PREC_FP32 || d->precision == RN_PREC_F16, "rn_relation: unknown precision %d",
+               d->precision);
+  return RN_OK;
+}
+
+static size_t fp32_ws_bytes(const rn_relation_desc* d) {
+  size_t B = d->batch, N = d->N, M = d->M;
+  int ld = (int)align_up(M, 4);
+  size_t t = 0;
+  t += ws_slice(B * N * d->dq, 4);      // Q
+  t += ws_slice(B * M * d->dq, 4);      // K
+  t += ws_slice(B * M * d->dout, 4);    // V'
+  t += ws_slice(B * d->H * N * ld, 4);  // g
+  t += ws_slice(B * d->H * N * ld, 4);  // S / P
+  t += ws_slice(B * N * d->dout, 4);    // O
+  t += ws_slice(B * M * d->d, 4);       // gathered keys
+  return t;
+}
+
+static int relation_fp32(const rn_relation_desc* d, const float* X, const float* boxes, const int* key_index,
+                         const float* Wq, const float* bq, const float* Wk, const float* bk, const float* Wg,
+                         const float* bg, const float* Wout, const float* bout, float* out, float* softmax_out,
+                         void* wsp, size_t ws_bytes, cudaStream_t st) {
+  const int B = d->batch, N = d->N, M = d->M, D = d->d, dq = d->dq, dout = d->dout, H = d->H;
+  const int dk = dq / H, dv = dout / H, ld = (int)align_up(M, 4);
+  Workspace ws(wsp, ws_bytes);
+  float* Q = ws.take<float>((size_t)B * N * dq);
+  float* K = ws.take<float>((size_t)B * M * dq);
+  float* Vp = ws.take<float>((size_t)B * M * dout);
+  float* g = ws.take<float>((size_t)B * H * N * ld);
+  float* S = ws.take<float>((size_t)B * H * N * ld);
+  float* O = ws.take<float>((size_t)B * N * dout);
+  float* Xk = ws.take<float>((size_t)B * M * D);
+  if (!Xk) { set_error("rn_relation_fwd: workspace too small (%zu < %zu)", ws_bytes, fp32_ws_bytes(d)); return RN_ERR_WORKSPACE; }
+  int r;
+  // projections
+  if ((r = sgemm_nt(st, B * N, dq, D, X, D, Wq, D, Q, dq))) return r;
+  if ((r = launch_bias_act(st, Q, bq, (size_t)B * N, dq, 0))) return r;
+  const float* keys = X; long long key_stride = (long long)N * D;
+  if (key_index) {
+    gather_rows_kernel<<<dim3(M, B), 128, 0, st>>>(X, key_index, B, N, M, D, Xk);
+    RN_LAUNCH_CHECK();
+    keys = Xk; key_stride = (long long)M * D;
+  }
+  if (key_index || B == 1 || M == N) {
+    // keys are contiguous rows [B*M, D] (gathered, or the whole X when M == N, or a single prefix)
+    const int rows = (key_index || M == N) ? B * M : M;
+    if ((r = sgemm_nt(st, rows, dq, D, keys, D, Wk, D, K, dq))) return r;
+    if ((r = sgemm_nt(st, rows, dout, D, keys, D, Wout, D, Vp, dout))) return r;
+  } else {
+    if ((r = sgemm_nt(st, M, dq, D, keys, D, Wk, D, K, dq, B, key_stride, 0, (long long)M * dq))) return r;
+    if ((r = sgemm_nt(st, M, dout, D, keys, D, Wout, D, Vp, dout, B, key_stride, 0, (long long)M * dout))) return r;
+  }
+  if ((r = launch_bias_act(st, K, bk, (size_t)B * M, dq, 0))) return r;
+  // geometry weights g [B,H,N,ld]
+  if ((r = launch_geom_weight(st, boxes, key_index, B, N, M, H, d->E, d->wave_length, Wg, bg, g, ld))) return r;
+  // scores, softmax, aggregate (per problem; heads batched)
+  for (int b = 0; b < B; ++b) {
+    const float* Qb = Q + (size_t)b * N * dq;
+    const float* Kb = K + (size_t)b * M * dq;
+    float* Sb = S + (size_t)b * H * N * ld;
+    if ((r = sgemm_nt(st, N, M, dk, Qb, dq, Kb, dq, Sb, ld, H, dk, dk, (long long)N * ld))) return r;
+  }
+  {
+    const int rows = B * H * N;
+    geo_softmax_rows_kernel<<<cdiv(rows, 8), 256, 0, st>>>(S, g, B, H, N, M, ld, 1.0f / sqrtf((float)dk), softmax_out);
+    RN_LAUNCH_CHECK();
+  }
+  for (int b = 0; b < B; ++b) {
+    const float* Sb = S + (size_t)b * H * N * ld;
+    const float* Vb = Vp + (size_t)b * M * dout;
+    float* Ob = O + (size_t)b * N * dout;
+    if ((r = sgemm_nn(st, N, dv, M, Sb, ld, Vb, dout, Ob, dout, H, (long long)N * ld, dv, dv))) return r;
+  }
+  {
+    size_t total = (size_t)B * N * dout;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    relation_epilogue_kernel<<<blocks, 256, 0, st>>>(O, bout, X, (size_t)B * N, dout, d->fuse_residual_relu, out);
+    RN_LAUNCH_CHECK();
+  }
+  return RN_OK;
+}
+
+}  // namespace rn
+
+extern "C" size_t rn_relation_workspace_bytes(const rn_relation_desc* d) {
+  if (!d) return 0;
+  size_t a = rn::fp32_ws_bytes(d);
+  size_t b = rn::relation_tc_workspace_bytes(d);
+  return (a > b ? a : b) + 256;
+}
+
+extern "C" int rn_relation_fwd(const rn_relation_desc* d, const float* X, const float* boxes, const int32_t* key_index,
+                               const float* Wq, const float* bq, const float* Wk, const float* bk, const float* Wg,
+                               const float* bg, const float* Wout, const float* bout, float* out, float* softmax_out,
+                               void* ws, size_t ws_bytes, rn_stream_t stream) {
+  int r = rn::check_desc(d);
+  if (r) return r;
+  RN_CHECK_ARG(X && boxes && Wq && bq && Wk && bk && Wg && bg && Wout && bout && out && ws,
+               "rn_relation_fwd: null pointer argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->precision == RN_PREC_F16)
+    return rn::relation_tc(d, X, boxes, key_index, Wq, bq, Wk, bk, Wg, bg, Wout, bout, out, softmax_out, ws, ws_bytes, st);
+  return rn::relation_fp32(d, X, boxes, key_index, Wq, bq, Wk, bk, Wg, bg, Wout, bout, out, softmax_out, ws, ws_bytes, st);
+}
+
+extern "C" size_t rn_linear_workspace_bytes(int32_t rows, int32_t in, int32_t out, int32_t precision) {
+  if (precision == RN_PREC_F16) return rn::linear_tc_workspace_bytes(rows, in, out) + 256;
+  return 256;
+}
+
+extern "C" int rn_linear_fwd(const float* x, const float* W, const float* b, float* y, int32_t rows, int32_t in,
+                             int32_t out, int32_t relu, int32_t precision, void* ws, size_t ws_bytes,
+                             rn_stream_t stream) {
+  RN_CHECK_ARG(x && W && y && rows > 0 && in > 0 && out > 0, "rn_linear_fwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (precision == RN_PREC_F16) return rn::linear_tc(x, W, b, y, rows, in, out, relu, ws, ws_bytes, st);
+  int r = rn::sgemm_nt(st, rows, out, in, x, in, W, in, y, out);
+  if (r) return r;
+  return rn::launch_bias_act(st, y, b, (size_t)rows, out, relu);
+}

@@ -1,0 +1,20 @@
+// relation.cuh -- internal interfaces between relation.cu (dispatch + fp32 path) and relation_tc.cu / gemm_tc.cu
+#pragma once
+#include "common.cuh"
+
+namespace rn {
+
+int launch_bias_act(cudaStream_t st, float* y, const float* bias, size_t rows, int cols, int relu);
+
+// fused tcgen05 path (relation_tc.cu)
+size_t relation_tc_workspace_bytes(const rn_relation_desc* d);
+int relation_tc(const rn_relation_desc* d, const float* X, const float* boxes, const int* key_index, const float* Wq,
+                const float* bq, const float* Wk, const float* bk, const float* Wg, const float* bg, const float* Wout,
+                const float* bout, float* out, float* softmax_out, void* ws, size_t ws_bytes, cudaStream_t st);
+
+// tcgen05 fp16 GEMM (gemm_tc.cu): y = act(x W^T + b)
+size_t linear_tc_workspace_bytes(int rows, int in, int out);
+int linear_tc(const float* x, const float* W, const float* b, float* y, int rows, int in, int out, int relu, void* ws,
+              size_t ws_bytes, cudaStream_t st);
+
+}  // namespace rn

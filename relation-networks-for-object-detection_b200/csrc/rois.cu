@@ -1,0 +1,146 @@
+// rois.cu -- ROIPooling (max, MXNet semantics) and DeformablePSROIPooling forward (= average ROIAlign when no_trans).
+// Compiled with -fmad=false: the float/double op order of the reference kernels is kept literally so results are
+// bit-comparable with the plain-C oracle (oracle/oracle_c.c).
+//
+// HBM layout: data [B,C,H,W] fp32 (the 38x63x256 map is 2.4 MB -> L2 resident), out [R,C,P,P] fp32.
+// Roofline: HBM-write bound -- algorithmic bytes = R*C*P*P*4 (out) + the feature map once; the gathers hit L2.
+// Grid: one thread per output element, blocks of 256, grid-stride capped at 148*8 CTAs.
+#include "common.cuh"
+#include <cfloat>
+
+namespace rn {
+
+// Restates MXNet 1.1.0 src/operator/roi_pooling.cu ROIPoolForwardKernel (not in the reference tree; call site SYM_REL:252)
+__global__ void __launch_bounds__(256) roi_pool_fwd_kernel(const float* __restrict__ data, const float* __restrict__ rois,
+                                                           size_t count, int C, int H, int W, int PH, int PW,
+                                                           float spatial_scale, float* __restrict__ out,
+                                                           int* __restrict__ argmax) {
+  for (size_t index = (size_t)blockIdx.x * blockDim.x + threadIdx.x; index < count;
+       index += (size_t)gridDim.x * blockDim.x) {
+    const int pw = index % PW, ph = (index / PW) % PH;
+    const int c = (index / PW / PH) % C;
+    const int n = index / PW / PH / C;
+    const float* roi = rois + 5 * n;
+    const int b = (int)roi[0];
+    const int rsw = (int)roundf(roi[1] * spatial_scale), rsh = (int)roundf(roi[2] * spatial_scale);
+    const int rew = (int)roundf(roi[3] * spatial_scale), reh = (int)roundf(roi[4] * spatial_scale);
+    const int rh = max(reh - rsh + 1, 1), rw = max(rew - rsw + 1, 1);
+    const float bh = (float)rh / (float)PH, bw = (float)rw / (float)PW;
+    int hs = (int)floorf((float)ph * bh), ws = (int)floorf((float)pw * bw);
+    int he = (int)ceilf((float)(ph + 1) * bh), we = (int)ceilf((float)(pw + 1) * bw);
+    hs = min(max(hs + rsh, 0), H); he = min(max(he + rsh, 0), H);
+    ws = min(max(ws + rsw, 0), W); we = min(max(we + rsw, 0), W);
+    const bool empty = (he <= hs) || (we <= ws);
+    float m = empty ? 0.f : -FLT_MAX;
+    int mi = -1;
+    const float* d = data + ((size_t)b * C + c) * H * W;
+    for (int h = hs; h < he; ++h)
+      for (int w = ws; w < we; ++w) {
+        const float v = __ldg(d + h * W + w);
+        if (v > m) { m = v; mi = h * W + w; }
+      }
+    out[index] = m;
+    if (argmax) argmax[index] = mi;
+  }
+}
+
+// operator_cxx/deformable_psroi_pooling.cu:29-49
+__device__ __forceinline__ float psroi_bilinear(const float* __restrict__ data, float x, float y, int width) {
+  const int x1 = (int)floorf(x), x2 = (int)ceilf(x), y1 = (int)floorf(y), y2 = (int)ceilf(y);
+  const float dx = x - (float)x1, dy = y - (float)y1;
+  const float v11 = __ldg(data + y1 * width + x1), v12 = __ldg(data + y2 * width + x1);
+  const float v21 = __ldg(data + y1 * width + x2), v22 = __ldg(data + y2 * width + x2);
+  return (1 - dx) * (1 - dy) * v11 + (1 - dx) * dy * v12 + dx * (1 - dy) * v21 + dx * dy * v22;
+}
+
+// operator_cxx/deformable_psroi_pooling.cu:52-138, float/double mixing kept literally
+__global__ void __launch_bounds__(256) deform_psroi_fwd_kernel(rn_psroi_desc p, size_t count, const float* __restrict__ data,
+                                                               const float* __restrict__ rois,
+                                                               const float* __restrict__ trans, float* __restrict__ out,
+                                                               float* __restrict__ top_count) {
+  const int pooled = p.pooled_size, part_size = p.part_size, spp = p.sample_per_part, gs = p.group_size;
+  const int H = p.H, W = p.W;
+  const int num_classes = p.no_trans ? 1 : p.num_classes;
+  const int channels_each_class = p.no_trans ? p.output_dim : p.output_dim / num_classes;
+  for (size_t index = (size_t)blockIdx.x * blockDim.x + threadIdx.x; index < count;
+       index += (size_t)gridDim.x * blockDim.x) {
+    const int pw = index % pooled, ph = (index / pooled) % pooled;
+    const int ctop = (index / pooled / pooled) % p.output_dim;
+    const int n = index / pooled / pooled / p.output_dim;
+    const float* roi = rois + 5 * n;
+    const int b = (int)roi[0];
+    const float rsw = (float)((double)(roundf(roi[1]) * p.spatial_scale) - 0.5);
+    const float rsh = (float)((double)(roundf(roi[2]) * p.spatial_scale) - 0.5);
+    const float rew = (float)((double)((float)((double)roundf(roi[3]) + 1.) * p.spatial_scale) - 0.5);
+    const float reh = (float)((double)((float)((double)roundf(roi[4]) + 1.) * p.spatial_scale) - 0.5);
+    const float roi_w = (float)fmax((double)(rew - rsw), 0.1);
+    const float roi_h = (float)fmax((double)(reh - rsh), 0.1);
+    const float bin_h = roi_h / (float)pooled, bin_w = roi_w / (float)pooled;
+    const float sub_h = bin_h / (float)spp, sub_w = bin_w / (float)spp;
+    const int part_h = (int)floorf((float)ph / pooled * part_size);
+    const int part_w = (int)floorf((float)pw / pooled * part_size);
+    const int class_id = ctop / channels_each_class;
+    const float tx = p.no_trans ? 0.f
+        : trans[(((size_t)(n * num_classes + class_id) * 2) * part_size + part_h) * part_size + part_w] * p.trans_std;
+    const float ty = p.no_trans ? 0.f
+        : trans[(((size_t)(n * num_classes + class_id) * 2 + 1) * part_size + part_h) * part_size + part_w] * p.trans_std;
+    float wstart = (float)pw * bin_w + rsw; wstart += tx * roi_w;
+    float hstart = (float)ph * bin_h + rsh; hstart += ty * roi_h;
+    float sum = 0.f; int cnt = 0;
+    int gw = (int)floorf((float)pw * gs / pooled), gh = (int)floorf((float)ph * gs / pooled);
+    gw = min(max(gw, 0), gs - 1); gh = min(max(gh, 0), gs - 1);
+    const float* d0 = data + (size_t)b * p.channels * H * W;
+    const int c = (ctop * gs + gh) * gs + gw;
+    for (int ih = 0; ih < spp; ++ih)
+      for (int iw = 0; iw < spp; ++iw) {
+        float w = wstart + iw * sub_w, h = hstart + ih * sub_h;
+        if ((double)w < -0.5 || (double)w > W - 0.5 || (double)h < -0.5 || (double)h > H - 0.5) continue;
+        w = (float)fmin(fmax((double)w, 0.), W - 1.);
+        h = (float)fmin(fmax((double)h, 0.), H - 1.);
+        sum += psroi_bilinear(d0 + (size_t)c * H * W, w, h, W);
+        cnt++;
+      }
+    out[index] = cnt == 0 ? 0.f : sum / cnt;
+    if (top_count) top_count[index] = (float)cnt;
+  }
+}
+
+static inline int grid_for(size_t count) {
+  size_t blocks = (count + 255) / 256;
+  size_t cap = (size_t)(sm_count() > 0 ? sm_count() : 148) * 8;
+  return (int)(blocks < cap ? blocks : cap);
+}
+
+}  // namespace rn
+
+extern "C" int rn_roi_pool_fwd(const float* data, const float* rois, int32_t R, int32_t C, int32_t H, int32_t W,
+                               int32_t PH, int32_t PW, float spatial_scale, float* out, int32_t* argmax,
+                               rn_stream_t stream) {
+  RN_CHECK_ARG(data && rois && out && R >= 0 && C > 0 && H > 0 && W > 0 && PH > 0 && PW > 0, "rn_roi_pool_fwd: bad arguments");
+  if (R == 0) return RN_OK;
+  size_t count = (size_t)R * C * PH * PW;
+  rn::roi_pool_fwd_kernel<<<rn::grid_for(count), 256, 0, (cudaStream_t)stream>>>(data, rois, count, C, H, W, PH, PW,
+                                                                                spatial_scale, out, argmax);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
+
+extern "C" int rn_deform_psroi_pool_fwd(const rn_psroi_desc* desc, const float* data, const float* rois,
+                                        const float* trans, float* out, float* top_count, rn_stream_t stream) {
+  RN_CHECK_ARG(desc && data && rois && out, "rn_deform_psroi_pool_fwd: null argument");
+  rn_psroi_desc p = *desc;
+  if (p.part_size == 0) p.part_size = p.pooled_size;
+  RN_CHECK_ARG(p.no_trans || trans, "rn_deform_psroi_pool_fwd: trans required when no_trans == 0");
+  RN_CHECK_ARG(p.group_size > 0 && p.pooled_size > 0 && p.sample_per_part > 0 && p.output_dim > 0,
+               "rn_deform_psroi_pool_fwd: bad geometry");
+  RN_CHECK_ARG(p.channels == p.output_dim * p.group_size * p.group_size,
+               "rn_deform_psroi_pool_fwd: channels %d != output_dim*group_size^2 = %d", p.channels,
+               p.output_dim * p.group_size * p.group_size);
+  if (!p.no_trans) RN_CHECK_ARG(p.num_classes > 0 && p.output_dim % p.num_classes == 0, "rn_deform_psroi_pool_fwd: bad num_classes");
+  if (p.R == 0) return RN_OK;
+  size_t count = (size_t)p.R * p.output_dim * p.pooled_size * p.pooled_size;
+  rn::deform_psroi_fwd_kernel<<<rn::grid_for(count), 256, 0, (cudaStream_t)stream>>>(p, count, data, rois, trans, out,
+                                                                                    top_count);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}

@@ -1,0 +1,292 @@
+"""Host-side wrappers: torch CUDA tensors in, torch CUDA tensors out, every byte of arithmetic in librelnet_b200.so.
+
+PyTorch is used for device memory, streams and (elsewhere) torch.distributed only.  No op here has a CPU or eager
+fallback: non-CUDA tensors raise.
+"""
+import ctypes as C
+import torch
+from . import _lib as L
+
+PREC = {'fp32': 0, 'f16': 1, 0: 0, 1: 1}
+_ws = {}
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _workspace(nbytes, device):
+    """Grow-only per-device scratch buffer handed to the C ABI (the library itself never allocates)."""
+    key = (device.index, torch.cuda.current_stream().cuda_stream)
+    buf = _ws.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=device)
+        _ws[key] = buf
+    return buf
+
+
+def _f32(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise L.RelnetError('%s must be a CUDA tensor (relnet_b200 has no CPU path)' % name)
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.contiguous().float()
+    return t
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def device_info():
+    sm, ma, mi = C.c_int(), C.c_int(), C.c_int()
+    ok = L.lib().rn_device_info(C.byref(sm), C.byref(ma), C.byref(mi))
+    return dict(sm100=bool(ok), sm_count=sm.value, cc=(ma.value, mi.value))
+
+
+def default_precision():
+    return 'f16' if device_info()['sm100'] else 'fp32'
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def relation(X, boxes, Wq, bq, Wk, bk, Wg, bg, Wout, bout, key_index=None, M=None, group=16, residual_relu=False,
+             precision=None, wave_length=1000.0, return_softmax=False):
+    """Object-relation module (SYM_REL:30-151 + :267-268).  X [N,d] or [B,N,d]; boxes [N,4] or [B,N,4]."""
+    precision = precision or default_precision()
+    X = _f32(X, 'X'); boxes = _f32(boxes, 'boxes')
+    batched = X.dim() == 3
+    B = X.shape[0] if batched else 1
+    N, d = X.shape[-2], X.shape[-1]
+    ws_ = [_f32(w, n) for w, n in ((Wq, 'Wq'), (bq, 'bq'), (Wk, 'Wk'), (bk, 'bk'), (Wg, 'Wg'), (bg, 'bg'),
+                                   (Wout, 'Wout'), (bout, 'bout'))]
+    Wq, bq, Wk, bk, Wg, bg, Wout, bout = ws_
+    Wout2 = Wout.reshape(Wout.shape[0], -1)
+    kidx = None
+    if key_index is not None:
+        kidx = key_index.to(device=X.device, dtype=torch.int32).contiguous()
+        M = kidx.numel()
+    M = int(M) if M is not None else N
+    desc = L.RelationDesc(B, N, M, d, Wq.shape[0], Wout2.shape[0], group, Wg.shape[1], wave_length,
+                          int(residual_relu), PREC[precision])
+    out = torch.empty((B, N, Wout2.shape[0]) if batched else (N, Wout2.shape[0]), dtype=torch.float32, device=X.device)
+    sm = torch.empty((B, N, group, M) if batched else (N, group, M), dtype=torch.float32, device=X.device) \
+        if return_softmax else None
+    lib = L.lib()
+    nbytes = lib.rn_relation_workspace_bytes(C.byref(desc))
+    ws = _workspace(nbytes, X.device)
+    L.check(lib.rn_relation_fwd(C.byref(desc), _ptr(X), _ptr(boxes), _ptr(kidx), _ptr(Wq), _ptr(bq), _ptr(Wk), _ptr(bk),
+                                _ptr(Wg), _ptr(bg), _ptr(Wout2), _ptr(bout), _ptr(out), _ptr(sm), _ptr(ws), ws.numel(),
+                                _stream()), 'rn_relation_fwd')
+    return (out, sm) if return_softmax else out
+
+
+def pos_embed(boxes, M=None, key_index=None, E=64, wave_length=1000.0, want_eps=True, want_emb=True):
+    boxes = _f32(boxes, 'boxes')
+    N = boxes.shape[0]
+    kidx = key_index.to(device=boxes.device, dtype=torch.int32).contiguous() if key_index is not None else None
+    M = kidx.numel() if kidx is not None else (int(M) if M is not None else N)
+    eps = torch.empty((N, M, 4), dtype=torch.float32, device=boxes.device) if want_eps else None
+    emb = torch.empty((N, M, E), dtype=torch.float32, device=boxes.device) if want_emb else None
+    L.check(L.lib().rn_pos_embed_fwd(_ptr(boxes), _ptr(kidx), N, M, E, wave_length, _ptr(eps), _ptr(emb), _stream()),
+            'rn_pos_embed_fwd')
+    return eps, emb
+
+
+def geometry_weight(boxes, Wg, bg, M=None, key_index=None, wave_length=1000.0):
+    boxes = _f32(boxes, 'boxes'); Wg = _f32(Wg, 'Wg'); bg = _f32(bg, 'bg')
+    batched = boxes.dim() == 3
+    B = boxes.shape[0] if batched else 1
+    N = boxes.shape[-2]
+    kidx = key_index.to(device=boxes.device, dtype=torch.int32).contiguous() if key_index is not None else None
+    M = kidx.numel() if kidx is not None else (int(M) if M is not None else N)
+    H, E = Wg.shape
+    g = torch.empty((B, H, N, M) if batched else (H, N, M), dtype=torch.float32, device=boxes.device)
+    L.check(L.lib().rn_geometry_weight_fwd(_ptr(boxes), _ptr(kidx), B, N, M, H, E, wave_length, _ptr(Wg), _ptr(bg),
+                                           _ptr(g), _stream()), 'rn_geometry_weight_fwd')
+    return g
+
+
+def linear(x, W, b=None, relu=False, precision=None):
+    precision = precision or default_precision()
+    x = _f32(x, 'x'); W = _f32(W, 'W'); b = _f32(b, 'b') if b is not None else None
+    x2 = x.reshape(x.shape[0], -1)
+    rows, cin = x2.shape
+    cout = W.shape[0]
+    assert W.shape[1] == cin, (W.shape, cin)
+    y = torch.empty((rows, cout), dtype=torch.float32, device=x.device)
+    lib = L.lib()
+    ws = _workspace(lib.rn_linear_workspace_bytes(rows, cin, cout, PREC[precision]), x.device)
+    L.check(lib.rn_linear_fwd(_ptr(x2), _ptr(W), _ptr(b), _ptr(y), rows, cin, cout, int(relu), PREC[precision], _ptr(ws),
+                              ws.numel(), _stream()), 'rn_linear_fwd')
+    return y
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def learn_nms(cls_score, bbox_pred, rois, im_info, feat, weights, first_n=100, num_thresh=5, class_thresh=0.01,
+              class_agnostic=True, means=None, stds=None, nongt_dim=None, non_gt_index=None, merge_method=-1,
+              precision=None):
+    """learn_nms CustomOp forward (LNMS:238-401) + merge.  ``weights``: dict by checkpoint name (LNMS:429-441)."""
+    precision = precision or default_precision()
+    cls_score = _f32(cls_score, 'cls_score'); bbox_pred = _f32(bbox_pred, 'bbox_pred'); rois = _f32(rois, 'rois')
+    im_info = _f32(im_info, 'im_info').reshape(-1); feat = _f32(feat, 'feat')
+    R, NC = cls_score.shape
+    desc = L.LearnNmsDesc()
+    desc.R, desc.num_classes, desc.num_reg_classes = R, NC, bbox_pred.shape[1] // 4
+    desc.feat_dim, desc.first_n, desc.num_thresh, desc.class_thresh = feat.shape[1], first_n, num_thresh, class_thresh
+    desc.class_agnostic = int(class_agnostic)
+    desc.has_means_stds = int(means is not None and stds is not None)
+    if desc.has_means_stds:
+        desc.means = (C.c_float * 4)(*[float(v) for v in means]); desc.stds = (C.c_float * 4)(*[float(v) for v in stds])
+    kidx = None
+    desc.nongt_dim = int(nongt_dim) if nongt_dim is not None else 0
+    if nongt_dim is None and non_gt_index is not None:
+        kidx = non_gt_index.to(device=rois.device, dtype=torch.int32).contiguous()
+        desc.num_non_gt = kidx.numel()
+    desc.merge_method, desc.precision = merge_method, PREC[precision]
+    keep = [_f32(weights[n], n) for n in L.LearnNmsWeights.NAMES]
+    w = L.LearnNmsWeights(*[t.data_ptr() for t in keep])
+    C_ = NC - 1
+    dev = rois.device
+    multi = torch.empty((first_n, C_, num_thresh), dtype=torch.float32, device=dev)
+    sbbox = torch.empty((first_n, C_, 4), dtype=torch.float32, device=dev)
+    sscore = torch.empty((first_n, C_), dtype=torch.float32, device=dev)
+    final = torch.empty((first_n, C_), dtype=torch.float32, device=dev)
+    lib = L.lib()
+    ws = _workspace(lib.rn_learn_nms_workspace_bytes(C.byref(desc)), dev)
+    L.check(lib.rn_learn_nms_fwd(C.byref(desc), _ptr(cls_score), _ptr(bbox_pred), _ptr(rois), _ptr(im_info), _ptr(feat),
+                                 C.byref(w), _ptr(kidx), _ptr(multi), _ptr(sbbox), _ptr(sscore), _ptr(final), _ptr(ws),
+                                 ws.numel(), _stream()), 'rn_learn_nms_fwd')
+    return multi, sbbox, sscore, final
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def proposal(cls_prob, bbox_pred, im_info, feat_stride=16, scales=(4, 8, 16, 32), ratios=(0.5, 1, 2),
+             pre_nms_top_n=6000, post_nms_top_n=300, thresh=0.7, min_size=0, return_num_kept=False):
+    cls_prob = _f32(cls_prob, 'cls_prob'); bbox_pred = _f32(bbox_pred, 'bbox_pred')
+    im_info = _f32(im_info, 'im_info').reshape(-1)
+    if cls_prob.shape[0] != 1:
+        raise ValueError('Sorry, multiple images each device is not implemented')      # proposal.py:54-56
+    Hf, Wf = cls_prob.shape[2], cls_prob.shape[3]
+    desc = L.ProposalDesc(Hf, Wf, feat_stride, len(scales), len(ratios), pre_nms_top_n, post_nms_top_n, thresh,
+                          float(min_size))
+    sc = (C.c_float * len(scales))(*[float(s) for s in scales])
+    ra = (C.c_float * len(ratios))(*[float(r) for r in ratios])
+    dev = cls_prob.device
+    rois = torch.empty((post_nms_top_n, 5), dtype=torch.float32, device=dev)
+    scores = torch.empty((post_nms_top_n, 1), dtype=torch.float32, device=dev)
+    nk = torch.zeros(1, dtype=torch.int32, device=dev)
+    lib = L.lib()
+    ws = _workspace(lib.rn_proposal_workspace_bytes(C.byref(desc)), dev)
+    L.check(lib.rn_proposal_fwd(C.byref(desc), sc, ra, _ptr(cls_prob), _ptr(bbox_pred), _ptr(im_info), _ptr(rois),
+                                _ptr(scores), _ptr(nk), _ptr(ws), ws.numel(), _stream()), 'rn_proposal_fwd')
+    return (rois, scores, nk) if return_num_kept else (rois, scores)
+
+
+def nms(boxes_sorted, thresh, max_keep=None):
+    """Device NMS over boxes already sorted by score; returns (keep int32 [max_keep], num int32[1]) on the device."""
+    b = _f32(boxes_sorted, 'boxes')
+    n, dim = b.shape
+    max_keep = max_keep or max(n, 1)
+    keep = torch.empty(max_keep, dtype=torch.int32, device=b.device)
+    num = torch.zeros(1, dtype=torch.int32, device=b.device)
+    lib = L.lib()
+    ws = _workspace(lib.rn_nms_workspace_bytes(n), b.device)
+    L.check(lib.rn_nms(_ptr(b), n, dim, thresh, max_keep, _ptr(keep), _ptr(num), _ptr(ws), ws.numel(), _stream()), 'rn_nms')
+    return keep, num
+
+
+def bbox_overlaps(boxes, query):
+    if not boxes.is_cuda:
+        raise L.RelnetError('bbox_overlaps: CUDA tensors required')
+    b = boxes.contiguous().double(); q = query.contiguous().double()
+    out = torch.zeros((b.shape[0], q.shape[0]), dtype=torch.float64, device=b.device)
+    L.check(L.lib().rn_bbox_overlaps(_ptr(b), _ptr(q), b.shape[0], q.shape[0], _ptr(out), _stream()), 'rn_bbox_overlaps')
+    return out
+
+
+def proposal_target(rois, gt_boxes, num_reg_classes=2, class_agnostic=True, bg_thresh_hi=0.5, normalize=True,
+                    means=(0.0, 0.0, 0.0, 0.0), stds=(0.1, 0.1, 0.2, 0.2), bbox_weights=(1.0, 1.0, 1.0, 1.0)):
+    rois = _f32(rois, 'rois'); gt = _f32(gt_boxes, 'gt_boxes')
+    N, G = rois.shape[0], gt.shape[0]
+    desc = L.ProposalTargetDesc()
+    desc.N, desc.G, desc.num_reg_classes, desc.class_agnostic = N, G, num_reg_classes, int(class_agnostic)
+    desc.bg_thresh_hi, desc.normalize = bg_thresh_hi, int(normalize)
+    desc.means = (C.c_double * 4)(*means); desc.stds = (C.c_double * 4)(*stds)
+    desc.bbox_weights = (C.c_float * 4)(*bbox_weights)
+    R = 2 if class_agnostic else num_reg_classes
+    dev = rois.device
+    ro = torch.empty((N + G, 5), dtype=torch.float32, device=dev)
+    lab = torch.empty((N + G,), dtype=torch.float32, device=dev)
+    bt = torch.empty((N + G, 4 * R), dtype=torch.float32, device=dev)
+    bw = torch.empty((N + G, 4 * R), dtype=torch.float32, device=dev)
+    L.check(L.lib().rn_proposal_target_fwd(C.byref(desc), _ptr(rois), _ptr(gt), _ptr(ro), _ptr(lab), _ptr(bt), _ptr(bw),
+                                           _stream()), 'rn_proposal_target_fwd')
+    return ro, lab, bt, bw
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def roi_pool(data, rois, pooled_size=(7, 7), spatial_scale=0.0625, return_argmax=False):
+    data = _f32(data, 'data'); rois = _f32(rois, 'rois')
+    B, Cc, H, W = data.shape
+    R = rois.shape[0]
+    out = torch.empty((R, Cc, pooled_size[0], pooled_size[1]), dtype=torch.float32, device=data.device)
+    arg = torch.empty(out.shape, dtype=torch.int32, device=data.device) if return_argmax else None
+    L.check(L.lib().rn_roi_pool_fwd(_ptr(data), _ptr(rois), R, Cc, H, W, pooled_size[0], pooled_size[1], spatial_scale,
+                                    _ptr(out), _ptr(arg), _stream()), 'rn_roi_pool_fwd')
+    return (out, arg) if return_argmax else out
+
+
+def deform_psroi_pool(data, rois, trans=None, spatial_scale=0.0625, output_dim=256, group_size=1, pooled_size=7,
+                      part_size=0, sample_per_part=4, trans_std=0.0, no_trans=None, return_count=False):
+    data = _f32(data, 'data'); rois = _f32(rois, 'rois')
+    if no_trans is None:
+        no_trans = trans is None
+    t = _f32(trans, 'trans') if not no_trans else None
+    B, Cc, H, W = data.shape
+    R = rois.shape[0]
+    desc = L.PsroiDesc(R, Cc, H, W, spatial_scale, output_dim, group_size, pooled_size, part_size or pooled_size,
+                       sample_per_part, trans_std, int(bool(no_trans)), 1 if no_trans else t.shape[1] // 2)
+    out = torch.empty((R, output_dim, pooled_size, pooled_size), dtype=torch.float32, device=data.device)
+    cnt = torch.empty_like(out) if return_count else None
+    L.check(L.lib().rn_deform_psroi_pool_fwd(C.byref(desc), _ptr(data), _ptr(rois), _ptr(t), _ptr(out), _ptr(cnt),
+                                             _stream()), 'rn_deform_psroi_pool_fwd')
+    return (out, cnt) if return_count else out
+
+
+def _dc_desc(data, weight, kernel, pad, stride, dilate, num_group, num_deformable_group, precision):
+    B, Cc, H, W = data.shape
+    return L.DeformConvDesc(B, Cc, H, W, weight.shape[0], kernel[0], kernel[1], pad[0], pad[1], stride[0], stride[1],
+                            dilate[0], dilate[1], num_group, num_deformable_group, PREC[precision])
+
+
+def deform_conv(data, offset, weight, bias=None, kernel=(3, 3), pad=(2, 2), stride=(1, 1), dilate=(2, 2),
+                num_group=1, num_deformable_group=4, precision='fp32'):
+    data = _f32(data, 'data'); offset = _f32(offset, 'offset'); weight = _f32(weight, 'weight')
+    bias = _f32(bias, 'bias') if bias is not None else None
+    desc = _dc_desc(data, weight, kernel, pad, stride, dilate, num_group, num_deformable_group, precision)
+    Ho, Wo = offset.shape[2], offset.shape[3]
+    out = torch.empty((data.shape[0], weight.shape[0], Ho, Wo), dtype=torch.float32, device=data.device)
+    lib = L.lib()
+    ws = _workspace(lib.rn_deform_conv_workspace_bytes(C.byref(desc)), data.device)
+    L.check(lib.rn_deform_conv_fwd(C.byref(desc), _ptr(data), _ptr(offset), _ptr(weight), _ptr(bias), _ptr(out), _ptr(ws),
+                                   ws.numel(), _stream()), 'rn_deform_conv_fwd')
+    return out
+
+
+def deform_im2col(im, offset, kernel=(3, 3), pad=(2, 2), stride=(1, 1), dilate=(2, 2), num_deformable_group=4):
+    im = _f32(im, 'im'); offset = _f32(offset, 'offset')
+    Cc, H, W = im.shape
+    desc = L.DeformConvDesc(1, Cc, H, W, 1, kernel[0], kernel[1], pad[0], pad[1], stride[0], stride[1], dilate[0],
+                            dilate[1], 1, num_deformable_group, 0)
+    col = torch.empty((Cc * kernel[0] * kernel[1], offset.shape[1], offset.shape[2]), dtype=torch.float32, device=im.device)
+    L.check(L.lib().rn_deform_im2col(C.byref(desc), _ptr(im), _ptr(offset), _ptr(col), _stream()), 'rn_deform_im2col')
+    return col
+
+
+def umma_selftest(a, b, p, v):
+    """tcgen05/TMA self-test: a,b [128,64], p [128,128], v [128,64] fp16 -> (a b^T [128,128], p v [128,64]) fp32."""
+    for t in (a, b, p, v):
+        assert t.is_cuda and t.dtype == torch.float16 and t.is_contiguous()
+    s = torch.zeros((128, 128), dtype=torch.float32, device=a.device)
+    o = torch.zeros((128, 64), dtype=torch.float32, device=a.device)
+    L.check(L.lib().rn_umma_selftest(_ptr(a), _ptr(b), _ptr(p), _ptr(v), _ptr(s), _ptr(o), _stream()), 'rn_umma_selftest')
+    return s, o
