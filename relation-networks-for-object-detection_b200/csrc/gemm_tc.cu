@@ -1,0 +1,312 @@
+// gemm_tc.cu -- hand-written tcgen05 GEMM for the dense layers of the path (fp16 operands, fp32 accumulate in TMEM):
+//     C[M,N] = act( A[M,K] . B[N,K]^T + bias )          A,B row-major with K contiguous ("K-major")
+// Used for the Q/K/V' projections of the relation module, fc_new_1/2, cls/bbox heads, the learn-NMS projections and
+// the deformable-conv GEMM.
+//
+// Structure (one CTA = one 128 x BN output tile, optionally one K-split): warp 4 = TMA producer (one elected lane),
+// warp 5 = TMEM allocator + MMA issuer (one elected lane), warps 0-3 = epilogue (TMEM lane quarter w%4 each).
+// 4-stage smem ring (A 128x64 + B BNx64 halfs per stage, SWIZZLE_128B, filled by cp.async.bulk.tensor), full/empty
+// mbarriers, tcgen05.commit frees a stage and finally signals the epilogue.  Out-of-range rows/cols/K are zero-filled
+// by TMA; the epilogue masks its stores.
+// HBM/L2 traffic per CTA: (128 + BN) * K * 2 B in, 128*BN*4 B out; roofline: tensor pipe for large M, L2->SM
+// bandwidth / latency for the M = 300 layers of this path.
+#include "common.cuh"
+#include "relation.cuh"
+#include "umma.cuh"
+#include "gemm_tc.cuh"
+
+namespace rn {
+using namespace umma;
+
+constexpr int kStages = 4;
+constexpr int kBM = 128, kBK = 64;
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int kA = kBM * kBK * 2;            // 16 KB
+  static constexpr int kB = BN * kBK * 2;
+  static constexpr int kStage = kA + kB;
+  static constexpr int kBar = kStages * kStage;       // barriers live after the ring
+  static constexpr int kTotal = kBar + 256 + 1024;    // + alignment slack
+};
+
+struct GemmParams {
+  int M, N, K;
+  int k_blocks_per_split;     // K blocks (of 64) per grid.z slice
+  const float* bias;          // [N] (bias_per_row == 0) or [M] (bias_per_row == 1) or nullptr
+  int bias_per_row;
+  int relu;
+  float* C32; long long ldc32;        // may be nullptr
+  __half* C16; long long ldc16;       // may be nullptr
+  float* partial;                     // split-K partials [splits][M][N] (when gridDim.z > 1)
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1) gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                             const __grid_constant__ CUtensorMap tmB, GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  using S = GemmSmem<BN>;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::kBar);
+  uint64_t* empty = full + kStages;
+  uint64_t* tmem_full = empty + kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * BN;
+  const int total_kb = (p.K + kBK - 1) / kBK;
+  const int kb_begin = blockIdx.z * p.k_blocks_per_split;
+  const int kb_end = min(total_kb, kb_begin + p.k_blocks_per_split);
+  const int num_kb = kb_end - kb_begin;
+
+  if (warp == 4 && lane == 0) {
+    prefetch_tmap(&tmA); prefetch_tmap(&tmB);
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc<(BN < 32 ? 32 : BN)>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % kStages, it = i / kStages;
+        mbar_wait(&empty[s], (it & 1) ^ 1);
+        mbar_arrive_expect_tx(&full[s], S::kStage);
+        uint8_t* sa = smem + s * S::kStage;
+        tma_load_2d(sa, &tmA, &full[s], (kb_begin + i) * kBK, m0);
+        tma_load_2d(sa + S::kA, &tmB, &full[s], (kb_begin + i) * kBK, n0);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(kBM, BN, false, false, false);
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % kStages, it = i / kStages;
+        mbar_wait(&full[s], it & 1);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * S::kStage), sb = sa + S::kA;
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k)
+          mma_f16_ss(tmem_base, make_smem_desc_sw128(sa + k * 32, 16, 1024), make_smem_desc_sw128(sb + k * 32, 16, 1024),
+                     idesc, (i | k) != 0);
+        mma_commit(&empty[s]);
+      }
+      mma_commit(tmem_full);
+    }
+  } else {
+    // epilogue: thread t of warps 0..3 owns accumulator row (32*warp + lane)
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int row = m0 + warp * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const bool split = gridDim.z > 1;
+    const float rbias = (!split && p.bias && p.bias_per_row && row < p.M) ? p.bias[row] : 0.f;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t v[32];
+      if (num_kb > 0) { tmem_ld_32x32b_x32(lane_base + c * 32, v); tmem_ld_wait(); }
+      else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+      const int col0 = n0 + c * 32;
+      if (row < p.M && col0 < p.N) {
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (split) {
+          float* dst = p.partial + ((size_t)blockIdx.z * p.M + row) * p.N + col0;
+          if (col0 + 32 <= p.N && (p.N & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+          } else {
+            for (int j = 0; j < 32 && col0 + j < p.N; ++j) dst[j] = f[j];
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float b = rbias;
+            if (p.bias && !p.bias_per_row && col0 + j < p.N) b = __ldg(p.bias + col0 + j);
+            f[j] += b;
+            if (p.relu) f[j] = fmaxf(f[j], 0.f);
+          }
+          const bool full_chunk = col0 + 32 <= p.N;
+          if (p.C32) {
+            float* dst = p.C32 + (size_t)row * p.ldc32 + col0;
+            if (full_chunk && (p.ldc32 & 3) == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            } else {
+              for (int j = 0; j < 32 && col0 + j < p.N; ++j) dst[j] = f[j];
+            }
+          }
+          if (p.C16) {
+            __half* dst = p.C16 + (size_t)row * p.ldc16 + col0;
+            if (full_chunk && (p.ldc16 & 7) == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                __half2 h0 = __floats2half2_rn(f[j], f[j + 1]), h1 = __floats2half2_rn(f[j + 2], f[j + 3]);
+                __half2 h2 = __floats2half2_rn(f[j + 4], f[j + 5]), h3 = __floats2half2_rn(f[j + 6], f[j + 7]);
+                uint4 u;
+                u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+                u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+                *reinterpret_cast<uint4*>(dst + j) = u;
+              }
+            } else {
+              for (int j = 0; j < 32 && col0 + j < p.N; ++j) dst[j] = __float2half_rn(f[j]);
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc<(BN < 32 ? 32 : BN)>(tmem_base);
+}
+
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N, const float* bias,
+                                     int bias_per_row, int relu, float* C32, long long ldc32, __half* C16, long long ldc16) {
+  const size_t total = (size_t)M * N;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = i / N, c = i % N;
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += partial[(size_t)z * total + i];
+    if (bias) s += bias_per_row ? bias[r] : bias[c];
+    if (relu) s = fmaxf(s, 0.f);
+    if (C32) C32[(size_t)r * ldc32 + c] = s;
+    if (C16) C16[(size_t)r * ldc16 + c] = __float2half_rn(s);
+  }
+}
+
+__global__ void cast_f32_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, size_t n) {
+  const size_t n4 = n / 4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    uint2 u; u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+    reinterpret_cast<uint2*>(dst)[i] = u;
+  }
+  for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = __float2half_rn(src[i]);
+}
+
+int cast_f32_f16(cudaStream_t st, const float* src, __half* dst, size_t n) {
+  if (n == 0) return RN_OK;
+  size_t blocks = (n / 4 + 255) / 256 + 1;
+  const size_t cap = (size_t)(sm_count() > 0 ? sm_count() : 148) * 8;
+  cast_f32_f16_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(src, dst, n);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
+
+size_t gemm_tc_workspace_bytes(int M, int N, int K) {
+  // worst case split-K partials
+  const int tiles = cdiv(M, kBM) * cdiv(N, 64);
+  int splits = 1;
+  const int kb = cdiv(K, kBK);
+  const int sms = 148;
+  if (tiles < sms) splits = std::min(std::max(sms / tiles, 1), std::max(kb / 4, 1));
+  return splits > 1 ? ws_slice((size_t)splits * M * N, 4) : 0;
+}
+
+template <int BN>
+static int launch(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, dim3 grid) {
+  static thread_local bool configured = false;
+  if (!configured) {
+    RN_CUDA(cudaFuncSetAttribute(gemm_f16_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::kTotal));
+    configured = true;
+  }
+  gemm_f16_tc_kernel<BN><<<grid, 192, GemmSmem<BN>::kTotal, st>>>(tmA, tmB, p);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
+
+int gemm_tc(cudaStream_t st, const __half* A, long long lda, const __half* B, long long ldb, int M, int N, int K,
+            const float* bias, int bias_per_row, int relu, float* C32, long long ldc32, __half* C16, long long ldc16,
+            void* ws, size_t ws_bytes) {
+  RN_CHECK_ARG(is_sm100(), "tcgen05 GEMM needs an sm_100 device");
+  RN_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm_tc: bad sizes %dx%dx%d", M, N, K);
+  RN_CHECK_ARG((lda % 8) == 0 && (ldb % 8) == 0 && (((uintptr_t)A | (uintptr_t)B) & 15) == 0,
+               "gemm_tc: operand pitch must be a multiple of 8 halfs and 16-byte aligned (lda=%lld ldb=%lld)", lda, ldb);
+  const int sms = sm_count() > 0 ? sm_count() : 148;
+  const int tiles_m = cdiv(M, kBM);
+  // BN = 64 when 128-wide tiles would leave most SMs idle
+  const bool bn64 = (tiles_m * cdiv(N, 128) < sms / 2) || N <= 64;
+  const int BN = bn64 ? 64 : 128;
+  const int tiles = tiles_m * cdiv(N, BN);
+  const int kb = cdiv(K, kBK);
+  int splits = 1;
+  if (tiles < sms) splits = std::min(std::max(sms / tiles, 1), std::max(kb / 4, 1));
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K; p.k_blocks_per_split = cdiv(kb, splits);
+  splits = cdiv(kb, p.k_blocks_per_split);
+  p.bias = bias; p.bias_per_row = bias_per_row; p.relu = relu;
+  p.C32 = C32; p.ldc32 = ldc32; p.C16 = C16; p.ldc16 = ldc16; p.partial = nullptr;
+  if (splits > 1) {
+    const size_t need = ws_slice((size_t)splits * M * N, 4);
+    if (!ws || ws_bytes < need) { splits = 1; p.k_blocks_per_split = kb; }     // no room: fall back to a single pass
+    else p.partial = (float*)ws;
+  }
+  CUtensorMap tmA, tmB;
+  int r;
+  if ((r = encode_tmap_2d_f16(&tmA, A, M, K, lda, kBM, kBK))) return r;
+  if ((r = encode_tmap_2d_f16(&tmB, B, N, K, ldb, BN, kBK))) return r;
+  dim3 grid(cdiv(N, BN), tiles_m, splits);
+  r = bn64 ? launch<64>(st, tmA, tmB, p, grid) : launch<128>(st, tmA, tmB, p, grid);
+  if (r) return r;
+  if (splits > 1) {
+    const size_t total = (size_t)M * N;
+    size_t blocks = (total + 255) / 256;
+    const size_t cap = (size_t)sms * 8;
+    splitk_reduce_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(p.partial, splits, M, N, bias, bias_per_row,
+                                                                            relu, C32, ldc32, C16, ldc16);
+    RN_LAUNCH_CHECK();
+  }
+  return RN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------- rn_linear (F16)
+size_t linear_tc_workspace_bytes(int rows, int in, int out) {
+  const int in8 = (int)align_up(in, 8);
+  return ws_slice((size_t)rows * in8, 2) + ws_slice((size_t)out * in8, 2) + gemm_tc_workspace_bytes(rows, out, in) + 512;
+}
+
+__global__ void cast_pad_rows_kernel(const float* __restrict__ src, __half* __restrict__ dst, int rows, int cols, int ld) {
+  const size_t total = (size_t)rows * ld;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = i / ld, c = i % ld;
+    dst[i] = c < cols ? __float2half_rn(src[(size_t)r * cols + c]) : __float2half_rn(0.f);
+  }
+}
+
+int cast_rows_f16(cudaStream_t st, const float* src, __half* dst, int rows, int cols, int ld) {
+  if (ld == cols) return cast_f32_f16(st, src, dst, (size_t)rows * cols);
+  const size_t total = (size_t)rows * ld;
+  size_t blocks = (total + 255) / 256;
+  const size_t cap = (size_t)(sm_count() > 0 ? sm_count() : 148) * 8;
+  cast_pad_rows_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(src, dst, rows, cols, ld);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
+
+int linear_tc(const float* x, const float* W, const float* b, float* y, int rows, int in, int out, int relu, void* wsp,
+              size_t ws_bytes, cudaStream_t st) {
+  const int in8 = (int)align_up(in, 8);
+  Workspace ws(wsp, ws_bytes);
+  __half* x16 = ws.take<__half>((size_t)rows * in8);
+  __half* w16 = ws.take<__half>((size_t)out * in8);
+  if (!w16) { set_error("rn_linear_fwd(F16): workspace too small"); return RN_ERR_WORKSPACE; }
+  int r;
+  if ((r = cast_rows_f16(st, x, x16, rows, in, in8))) return r;
+  if ((r = cast_rows_f16(st, W, w16, out, in, in8))) return r;
+  return gemm_tc(st, x16, in8, w16, in8, rows, out, in8, b, 0, relu, y, out, nullptr, 0, ws.base + ws.off, ws.size - ws.off);
+}
+
+}  // namespace rn

@@ -14,7 +14,7 @@ template <int MAXH>
 __global__ void __launch_bounds__(128) geom_weight_kernel(const float* __restrict__ boxes, const int* __restrict__ key_index,
                                                           int N, int M, int H, int E, GeomFreq fr,
                                                           const float* __restrict__ Wg, const float* __restrict__ bg,
-                                                          float* __restrict__ g, int ldg) {
+                                                          float* __restrict__ g, int ldg, int log2_out) {
   extern __shared__ float wg_s[];   // [E][MAXH] transposed, then bias [MAXH]
   const int b = blockIdx.z, n = blockIdx.y;
   const int m = blockIdx.x * 128 + threadIdx.x;
@@ -55,7 +55,10 @@ __global__ void __launch_bounds__(128) geom_weight_kernel(const float* __restric
   }
 #pragma unroll
   for (int h = 0; h < MAXH; ++h)
-    if (h < H) g[(((size_t)b * H + h) * N + n) * ldg + m] = fmaxf(acc[h], 1e-6f);   // max(relu(x),1e-6) == max(x,1e-6)
+    if (h < H) {
+      const float gv = fmaxf(acc[h], 1e-6f);                                   // max(relu(x),1e-6) == max(x,1e-6)
+      g[(((size_t)b * H + h) * N + n) * ldg + m] = log2_out ? log2f(gv) : gv;
+    }
 }
 
 __global__ void pos_embed_kernel(const float* __restrict__ boxes, const int* __restrict__ key_index, int N, int M, int E,
@@ -91,8 +94,24 @@ int make_freq(int E, float wave_length, GeomFreq* fr) {
   return RN_OK;
 }
 
+static int launch_geom_weight_impl(cudaStream_t st, const float* boxes, const int* key_index, int B, int N, int M, int H,
+                                   int E, float wave_length, const float* Wg, const float* bg, float* g, int ldg,
+                                   int log2_out);
+
 int launch_geom_weight(cudaStream_t st, const float* boxes, const int* key_index, int B, int N, int M, int H, int E,
                        float wave_length, const float* Wg, const float* bg, float* g, int ldg) {
+  return launch_geom_weight_impl(st, boxes, key_index, B, N, M, H, E, wave_length, Wg, bg, g, ldg, 0);
+}
+
+// log2 of the geometry weight, the form the fused tcgen05 kernel adds to the scaled logits (relation_tc.cu)
+int launch_geom_weight_log2(cudaStream_t st, const float* boxes, const int* key_index, int B, int N, int M, int H, int E,
+                            float wave_length, const float* Wg, const float* bg, float* g, int ldg) {
+  return launch_geom_weight_impl(st, boxes, key_index, B, N, M, H, E, wave_length, Wg, bg, g, ldg, 1);
+}
+
+static int launch_geom_weight_impl(cudaStream_t st, const float* boxes, const int* key_index, int B, int N, int M, int H,
+                                   int E, float wave_length, const float* Wg, const float* bg, float* g, int ldg,
+                                   int log2_out) {
   GeomFreq fr;
   int r = make_freq(E, wave_length, &fr);
   if (r) return r;
@@ -100,10 +119,10 @@ int launch_geom_weight(cudaStream_t st, const float* boxes, const int* key_index
   dim3 grid(cdiv(M, 128), N, B);
   if (H <= 4) {
     size_t smem = (size_t)(E * 4 + 4) * sizeof(float);
-    geom_weight_kernel<4><<<grid, 128, smem, st>>>(boxes, key_index, N, M, H, E, fr, Wg, bg, g, ldg);
+    geom_weight_kernel<4><<<grid, 128, smem, st>>>(boxes, key_index, N, M, H, E, fr, Wg, bg, g, ldg, log2_out);
   } else {
     size_t smem = (size_t)(E * 16 + 16) * sizeof(float);
-    geom_weight_kernel<16><<<grid, 128, smem, st>>>(boxes, key_index, N, M, H, E, fr, Wg, bg, g, ldg);
+    geom_weight_kernel<16><<<grid, 128, smem, st>>>(boxes, key_index, N, M, H, E, fr, Wg, bg, g, ldg, log2_out);
   }
   RN_LAUNCH_CHECK();
   return RN_OK;

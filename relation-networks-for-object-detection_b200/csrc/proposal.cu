@@ -112,7 +112,18 @@ __global__ void __launch_bounds__(1024) proposal_sort_kernel(const uint32_t* __r
   }
   int n_pre = s_valid;
   if (pre_nms_top_n > 0 && n_pre > pre_nms_top_n) n_pre = pre_nms_top_n;
-  for (int i = threadIdx.x; i < n_pre; i += blockDim.x) order[i] = (int)ix[i];
+  // gpu_nms re-sorts the selected boxes by score (lib/nms/gpu_nms.pyx:26, `argsort()[::-1]`): under the stable-sort
+  // tie rule that reverses every run of equal scores once more.  Mirror position i inside its run [lo, hi].
+  for (int i = threadIdx.x; i < n_pre; i += blockDim.x) {
+    const uint32_t key = k[i];
+    int a = 0, b = i;                       // first position with k == key (keys are descending)
+    while (a < b) { const int mid = (a + b) >> 1; if (k[mid] > key) a = mid + 1; else b = mid; }
+    const int lo = a;
+    a = i; b = n_pre - 1;                   // last position with k == key
+    while (a < b) { const int mid = (a + b + 1) >> 1; if (k[mid] < key) b = mid - 1; else a = mid; }
+    const int hi = a;
+    order[lo + hi - i] = (int)ix[i];
+  }
   if (threadIdx.x == 0) *n_pre_out = n_pre;
 }
 

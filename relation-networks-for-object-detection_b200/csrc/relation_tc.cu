@@ -1,17 +1,387 @@
-// relation_tc.cu -- fused tcgen05 relation path (placeholder until the kernels land in this file)
+// relation_tc.cu -- the fused object-relation kernel on tcgen05 tensor cores (RN_PREC_F16, sm_100a).
+//
+// Per module:   cast X -> fp16            (1 launch; skipped when the producer already emitted fp16)
+//               QKV' = X . [Wq;Wk;Wout']^T + [bq;bk;bout]   tcgen05 GEMM (gemm_tc.cu), fp16 out, one launch
+//               lg   = log2 max(Wg.phi(boxes)+bg, 1e-6)     geometry kernel (geom.cu), fp32 [B,H,N,ld]
+//               out  = relu(X + softmax_m(lg + q.k/sqrt(dk)) . V')   relation_attn_tc_kernel, one launch
+// Wout' is the grouped 1x1 conv weight padded to 64 output columns per head, so one kernel shape (dk = dv = 64)
+// serves both the detection head (dv = 64) and the learn-NMS relation (dv = 8); bout is folded into V' (softmax rows
+// sum to one).
+//
+// relation_attn_tc_kernel: one CTA per (128-query tile, head, problem).  Warp roles: warps 0-3 = softmax/epilogue (one
+// query row per thread = one TMEM lane), warp 4 = MMA issuer + TMEM allocator, warp 5 = TMA producer.  Streams 128-key
+// tiles (flash style, online softmax, any M): S = Q K^T (UMMA 128x128x64, fp32 in TMEM, double buffered) -> threads
+// read their row from TMEM, add the geometry term, exp2, write P (fp16, SWIZZLE_128B K-major) to smem -> O_tile = P V'
+// (UMMA 128x64x128, V' MN-major straight from the projection output) -> accumulated in registers with the usual
+// rescale.  K/V' tiles arrive by TMA into a 3-stage ring; nothing N x M ever goes to HBM except the geometry term.
+// Algorithmic work per CTA-tile: 2*128*128*64*2 FLOP on the tensor pipe, 128*128 exp2 on the SFU.
 #include "common.cuh"
+#include "geom.cuh"
 #include "relation.cuh"
+#include "gemm_tc.cuh"
+#include "umma.cuh"
+
 namespace rn {
-size_t relation_tc_workspace_bytes(const rn_relation_desc*) { return 0; }
-int relation_tc(const rn_relation_desc*, const float*, const float*, const int*, const float*, const float*, const float*,
-                const float*, const float*, const float*, const float*, const float*, float*, float*, void*, size_t,
-                cudaStream_t) {
-  set_error("RN_PREC_F16 relation path not built");
-  return RN_ERR_INVALID;
+using namespace umma;
+
+constexpr int kKV = 3;                       // K/V' ring stages
+constexpr int kQ = 16384, kKt = 16384, kVt = 16384, kPt = 32768;
+constexpr int kAttnBar = kQ + kKV * (kKt + kVt) + 2 * kPt;      // 180224
+constexpr int kAttnSmem = kAttnBar + 256 + 1024;
+
+struct AttnParams {
+  int N, M, H, T;                 // T = number of 128-key tiles
+  const float* lg; int ldg;       // [B,H,N,ldg] log2 geometry weight
+  const float* X; int ldx;        // residual source [B,N,ldx] (nullptr: none)
+  float* out; int ldo;            // [B,N,ldo]
+  int dv;                         // valid output columns per head (<= 64)
+  int relu;
+  float scale_log2;               // log2(e)/sqrt(dk)
+};
+
+__global__ void __launch_bounds__(192, 1) relation_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                  const __grid_constant__ CUtensorMap tmK,
+                                                                  const __grid_constant__ CUtensorMap tmV, AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  uint8_t* sQ = smem;
+  uint8_t* sKV = smem + kQ;                          // stage s: K at s*(32K), V' at +16K
+  uint8_t* sP = smem + kQ + kKV * (kKt + kVt);       // 2 buffers of 32 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kAttnBar);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;            // [kKV]
+  uint64_t* kv_empty = kv_full + kKV;      // [kKV]
+  uint64_t* s_full = kv_empty + kKV;       // [2]
+  uint64_t* s_free = s_full + 2;           // [2]
+  uint64_t* p_full = s_free + 2;           // [2]
+  uint64_t* pv_full = p_full + 2;          // [2]
+  uint64_t* pv_free = pv_full + 2;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_free + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int T = p.T;
+
+  if (warp == 5 && lane == 0) {
+    prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < kKV; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&s_full[s], 1); mbar_init(&s_free[s], 128); mbar_init(&p_full[s], 128);
+      mbar_init(&pv_full[s], 1); mbar_init(&pv_free[s], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tPV = tmem_base + 256;          // S[2] at +0,+128 ; PV[2] at +256,+320
+
+  if (warp == 5) {
+    // ------------------------------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, kQ);
+      tma_load_3d(sQ, &tmQ, q_full, h * 64, q0, b);
+      for (int j = 0; j < T; ++j) {
+        const int s = j % kKV;
+        mbar_wait(&kv_empty[s], ((j / kKV) & 1) ^ 1);
+        mbar_arrive_expect_tx(&kv_full[s], kKt + kVt);
+        tma_load_3d(sKV + s * (kKt + kVt), &tmK, &kv_full[s], h * 64, j * 128, b);
+        tma_load_3d(sKV + s * (kKt + kVt) + kKt, &tmV, &kv_full[s], h * 64, j * 128, b);
+      }
+    }
+  } else if (warp == 4) {
+    // ------------------------------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_f16(128, 128, false, false, false);
+      const uint32_t idesc_o = make_idesc_f16(128, 64, false, false, true);
+      const uint32_t aQ = smem_u32(sQ);
+      auto issue_pv = [&](int i) {
+        const int bf = i & 1, s = i % kKV;
+        mbar_wait(&p_full[bf], (i >> 1) & 1);
+        if (i >= 2) mbar_wait(&pv_free[bf], ((i - 2) >> 1) & 1);
+        tc_fence_after();
+        const uint32_t aP = smem_u32(sP + bf * kPt), aV = smem_u32(sKV + s * (kKt + kVt) + kKt);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          mma_f16_ss(tPV + bf * 64, make_smem_desc_sw128(aP + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                     make_smem_desc_sw128(aV + k * 2048, 1024, 1024), idesc_o, k > 0);
+        mma_commit(&pv_full[bf]);
+        mma_commit(&kv_empty[s]);
+      };
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < T; ++j) {
+        const int bf = j & 1, s = j % kKV;
+        mbar_wait(&kv_full[s], (j / kKV) & 1);
+        if (j >= 2) mbar_wait(&s_free[bf], ((j - 2) >> 1) & 1);
+        tc_fence_after();
+        const uint32_t aK = smem_u32(sKV + s * (kKt + kVt));
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          mma_f16_ss(tS + bf * 128, make_smem_desc_sw128(aQ + k * 32, 16, 1024), make_smem_desc_sw128(aK + k * 32, 16, 1024),
+                     idesc_s, k > 0);
+        mma_commit(&s_full[bf]);
+        if (j >= 1) issue_pv(j - 1);
+      }
+      issue_pv(T - 1);
+    }
+  } else {
+    // ------------------------------------------------------------------------------------------ softmax + epilogue
+    const int r = warp * 32 + lane;                  // row inside the tile == TMEM lane
+    const int n = q0 + r;
+    const bool row_ok = n < p.N;
+    const uint32_t lane_base = ((uint32_t)(warp * 32) << 16);
+    const float* lg_row = p.lg + (((size_t)b * p.H + h) * p.N + (row_ok ? n : 0)) * p.ldg;
+    float o[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) o[i] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
+
+    auto fold_pv = [&](int i, float alpha) {       // o = o*alpha + PV_i
+      const int bf = i & 1;
+      mbar_wait(&pv_full[bf], (i >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tPV + bf * 64 + c * 32 + lane_base, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 32; ++q) o[c * 32 + q] = fmaf(o[c * 32 + q], alpha, __uint_as_float(v[q]));
+      }
+      tc_fence_before();
+      mbar_arrive(&pv_free[bf]);
+    };
+
+    for (int j = 0; j < T; ++j) {
+      const int bf = j & 1;
+      const int m0 = j * 128;
+      mbar_wait(&s_full[bf], (j >> 1) & 1);
+      tc_fence_after();
+      // pass 1: row maximum of t = lg + s*scale over the valid keys of this tile
+      float mt = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        const int mc = m0 + c * 32;
+        if (mc >= p.M) break;                                  // warp-uniform
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tS + bf * 128 + c * 32 + lane_base, v);
+        float gl[32];
+#pragma unroll
+        for (int q = 0; q < 32; q += 4) {
+          float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (mc + q < p.ldg) t4 = __ldg(reinterpret_cast<const float4*>(lg_row + mc + q));
+          gl[q] = t4.x; gl[q + 1] = t4.y; gl[q + 2] = t4.z; gl[q + 3] = t4.w;
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          const float t = fmaf(__uint_as_float(v[q]), p.scale_log2, gl[q]);
+          mt = fmaxf(mt, (mc + q < p.M) ? t : -INFINITY);
+        }
+      }
+      const float m_new = fmaxf(m_run, mt);
+      const float alpha = exp2f(m_run - m_new);                // first tile: exp2(-inf) = 0
+      m_run = m_new;
+      // pass 2: p = exp2(t - m), row sum, fp16 P tile into shared memory (K-major, SWIZZLE_128B)
+      float lsum = 0.f;
+      uint8_t* sPb = sP + bf * kPt;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        const int mc = m0 + c * 32;
+        uint32_t pk[16];
+        if (mc < p.M) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tS + bf * 128 + c * 32 + lane_base, v);
+          float gl[32];
+#pragma unroll
+          for (int q = 0; q < 32; q += 4) {
+            float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (mc + q < p.ldg) t4 = __ldg(reinterpret_cast<const float4*>(lg_row + mc + q));
+            gl[q] = t4.x; gl[q + 1] = t4.y; gl[q + 2] = t4.z; gl[q + 3] = t4.w;
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 32; q += 2) {
+            float p0 = exp2f(fmaf(__uint_as_float(v[q]), p.scale_log2, gl[q]) - m_new);
+            float p1 = exp2f(fmaf(__uint_as_float(v[q + 1]), p.scale_log2, gl[q + 1]) - m_new);
+            p0 = (mc + q < p.M) ? p0 : 0.f;
+            p1 = (mc + q + 1 < p.M) ? p1 : 0.f;
+            lsum += p0 + p1;
+            __half2 hh = __floats2half2_rn(p0, p1);
+            pk[q >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) pk[q] = 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {                          // 4 chunks of 8 halfs
+          const int kc = c * 4 + i;                            // 16-byte chunk index along the 128 keys
+          *reinterpret_cast<uint4*>(sPb + (kc >> 3) * 16384 + sw128_offset(r, kc & 7)) =
+              make_uint4(pk[i * 4], pk[i * 4 + 1], pk[i * 4 + 2], pk[i * 4 + 3]);
+        }
+      }
+      l_run = fmaf(l_run, alpha, lsum);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(&p_full[bf]);
+      mbar_arrive(&s_free[bf]);
+      if (j >= 1) fold_pv(j - 1, alpha_prev);
+      alpha_prev = alpha;
+    }
+    fold_pv(T - 1, alpha_prev);
+    // epilogue: normalise, residual, relu, store the dv valid columns of this head
+    if (row_ok) {
+      const float inv = 1.f / l_run;
+      float* dst = p.out + ((size_t)b * p.N + n) * p.ldo + (size_t)h * p.dv;
+      const float* res = p.X ? p.X + ((size_t)b * p.N + n) * p.ldx + (size_t)h * p.dv : nullptr;
+      if (p.dv == 64 && (p.ldo & 3) == 0 && (!res || (p.ldx & 3) == 0)) {
+#pragma unroll
+        for (int q = 0; q < 64; q += 4) {
+          float4 y = make_float4(o[q] * inv, o[q + 1] * inv, o[q + 2] * inv, o[q + 3] * inv);
+          if (res) {
+            const float4 x4 = __ldg(reinterpret_cast<const float4*>(res + q));
+            y.x += x4.x; y.y += x4.y; y.z += x4.z; y.w += x4.w;
+          }
+          if (p.relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+          *reinterpret_cast<float4*>(dst + q) = y;
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 64; ++q)
+          if (q < p.dv) {
+            float y = o[q] * inv;
+            if (res) y += res[q];
+            if (p.relu) y = fmaxf(y, 0.f);
+            dst[q] = y;
+          }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc<512>(tmem_base);
 }
-size_t linear_tc_workspace_bytes(int, int, int) { return 0; }
-int linear_tc(const float*, const float*, const float*, float*, int, int, int, int, void*, size_t, cudaStream_t) {
-  set_error("RN_PREC_F16 linear path not built");
-  return RN_ERR_INVALID;
+
+// [Wq; Wk; Wout'] -> fp16 [3*H*64, d8] and bias [3*H*64] (Wout' / bout padded from dv to 64 columns per head)
+__global__ void pack_relation_weights_kernel(const float* __restrict__ Wq, const float* __restrict__ bq,
+                                             const float* __restrict__ Wk, const float* __restrict__ bk,
+                                             const float* __restrict__ Wout, const float* __restrict__ bout, int d, int d8,
+                                             int H, int dv, __half* __restrict__ W16, float* __restrict__ bias) {
+  const int rows = 3 * H * 64;
+  const size_t total = (size_t)rows * d8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = i / d8, c = i % d8;
+    const int part = r / (H * 64), rr = r % (H * 64);
+    float v = 0.f, bv = 0.f;
+    if (part == 0) { if (c < d) v = Wq[(size_t)rr * d + c]; bv = bq[rr]; }
+    else if (part == 1) { if (c < d) v = Wk[(size_t)rr * d + c]; bv = bk[rr]; }
+    else {
+      const int hh = rr / 64, jj = rr % 64;
+      if (jj < dv) { if (c < d) v = Wout[(size_t)(hh * dv + jj) * d + c]; bv = bout[hh * dv + jj]; }
+    }
+    W16[i] = __float2half_rn(v);
+    if (c == 0) bias[r] = bv;
+  }
 }
+
+static bool tc_shape_ok(const rn_relation_desc* d) {
+  return d->dq == d->H * 64 && d->dout % d->H == 0 && d->dout / d->H <= 64 && d->dout / d->H >= 1;
+}
+
+size_t relation_tc_workspace_bytes(const rn_relation_desc* d) {
+  if (!tc_shape_ok(d)) return 0;
+  const size_t B = d->batch, N = d->N, M = d->M, H = d->H;
+  const size_t d8 = align_up(d->d, 8), W3 = 3 * H * 64, ldg = align_up(M, 4);
+  size_t t = 0;
+  t += ws_slice(B * N * d8, 2);          // X fp16
+  t += ws_slice(B * M * d8, 2);          // gathered keys fp16
+  t += ws_slice(W3 * d8, 2);             // packed weights
+  t += ws_slice(W3, 4);                  // packed bias
+  t += ws_slice(B * N * W3, 2);          // QKV' fp16
+  t += ws_slice(B * M * 2 * H * 64, 2);  // KV' of gathered keys
+  t += ws_slice(B * H * N * ldg, 4);     // log2 geometry weight
+  t += gemm_tc_workspace_bytes((int)(B * N), (int)W3, (int)d8) + 512;
+  return t;
+}
+
+__global__ void gather_rows_f16_kernel(const __half* __restrict__ X, const int* __restrict__ idx, int N, int M, int d8,
+                                       __half* __restrict__ out) {
+  const int m = blockIdx.x, b = blockIdx.y;
+  const uint4* src = reinterpret_cast<const uint4*>(X + ((size_t)b * N + idx[m]) * d8);
+  uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)b * M + m) * d8);
+  for (int i = threadIdx.x; i < d8 / 8; i += blockDim.x) dst[i] = src[i];
+}
+
+int launch_geom_weight_log2(cudaStream_t st, const float* boxes, const int* key_index, int B, int N, int M, int H, int E,
+                            float wave_length, const float* Wg, const float* bg, float* g, int ldg);
+
+int relation_tc(const rn_relation_desc* d, const float* X, const float* boxes, const int* key_index, const float* Wq,
+                const float* bq, const float* Wk, const float* bk, const float* Wg, const float* bg, const float* Wout,
+                const float* bout, float* out, float* softmax_out, void* wsp, size_t ws_bytes, cudaStream_t st) {
+  RN_CHECK_ARG(is_sm100(), "RN_PREC_F16 needs an sm_100 device (tcgen05); use RN_PREC_FP32");
+  RN_CHECK_ARG(tc_shape_ok(d), "RN_PREC_F16 relation kernel supports dq == 64*H and dout/H <= 64 (got dq=%d dout=%d H=%d); "
+               "use RN_PREC_FP32 for this shape", d->dq, d->dout, d->H);
+  RN_CHECK_ARG(!softmax_out, "RN_PREC_F16 relation kernel never materialises the softmax; request it with RN_PREC_FP32");
+  const int B = d->batch, N = d->N, M = d->M, D = d->d, H = d->H, dv = d->dout / H;
+  const int d8 = (int)align_up(D, 8), W3 = 3 * H * 64, ldg = (int)align_up(M, 4);
+  Workspace ws(wsp, ws_bytes);
+  __half* x16 = ws.take<__half>((size_t)B * N * d8);
+  __half* xk16 = ws.take<__half>((size_t)B * M * d8);
+  __half* w16 = ws.take<__half>((size_t)W3 * d8);
+  float* bias = ws.take<float>(W3);
+  __half* qkv = ws.take<__half>((size_t)B * N * W3);
+  __half* kv = ws.take<__half>((size_t)B * M * 2 * H * 64);
+  float* lg = ws.take<float>((size_t)B * H * N * ldg);
+  if (!lg) { set_error("rn_relation_fwd(F16): workspace too small (%zu < %zu)", ws_bytes, relation_tc_workspace_bytes(d)); return RN_ERR_WORKSPACE; }
+  void* gws = ws.base + ws.off; const size_t gws_bytes = ws.size - ws.off;
+  int r;
+  {
+    const size_t total = (size_t)W3 * d8;
+    size_t blocks = (total + 255) / 256;
+    const size_t cap = (size_t)sm_count() * 8;
+    pack_relation_weights_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(Wq, bq, Wk, bk, Wout, bout, D, d8, H, dv,
+                                                                                   w16, bias);
+    RN_LAUNCH_CHECK();
+  }
+  if ((r = cast_rows_f16(st, X, x16, B * N, D, d8))) return r;
+  const __half *Qp, *Kp, *Vp; long long ldq, ldk; long long bq_pitch, bk_pitch;
+  if (key_index) {
+    gather_rows_f16_kernel<<<dim3(M, B), 128, 0, st>>>(x16, key_index, N, M, d8, xk16);
+    RN_LAUNCH_CHECK();
+    if ((r = gemm_tc(st, x16, d8, w16, d8, B * N, H * 64, d8, bias, 0, 0, nullptr, 0, qkv, H * 64, gws, gws_bytes))) return r;
+    if ((r = gemm_tc(st, xk16, d8, w16 + (size_t)H * 64 * d8, d8, B * M, 2 * H * 64, d8, bias + H * 64, 0, 0, nullptr, 0, kv,
+                     2 * H * 64, gws, gws_bytes))) return r;
+    Qp = qkv; ldq = H * 64; bq_pitch = (long long)N * ldq;
+    Kp = kv; Vp = kv + H * 64; ldk = 2 * H * 64; bk_pitch = (long long)M * ldk;
+  } else {
+    if ((r = gemm_tc(st, x16, d8, w16, d8, B * N, W3, d8, bias, 0, 0, nullptr, 0, qkv, W3, gws, gws_bytes))) return r;
+    Qp = qkv; Kp = qkv + H * 64; Vp = qkv + 2 * H * 64; ldq = ldk = W3; bq_pitch = bk_pitch = (long long)N * W3;
+  }
+  if ((r = launch_geom_weight_log2(st, boxes, key_index, B, N, M, H, d->E, d->wave_length, Wg, bg, lg, ldg))) return r;
+
+  CUtensorMap tmQ, tmK, tmV;
+  if ((r = encode_tmap_3d_f16(&tmQ, Qp, B, N, H * 64, ldq, bq_pitch, 128, 64))) return r;
+  if ((r = encode_tmap_3d_f16(&tmK, Kp, B, M, H * 64, ldk, bk_pitch, 128, 64))) return r;
+  if ((r = encode_tmap_3d_f16(&tmV, Vp, B, M, H * 64, ldk, bk_pitch, 128, 64))) return r;
+  AttnParams p;
+  p.N = N; p.M = M; p.H = H; p.T = cdiv(M, 128);
+  p.lg = lg; p.ldg = ldg;
+  p.X = d->fuse_residual_relu ? X : nullptr; p.ldx = D;
+  p.out = out; p.ldo = d->dout; p.dv = dv; p.relu = d->fuse_residual_relu;
+  p.scale_log2 = 1.4426950408889634f / sqrtf(64.f);
+  static thread_local bool configured = false;
+  if (!configured) {
+    RN_CUDA(cudaFuncSetAttribute(relation_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    configured = true;
+  }
+  relation_attn_tc_kernel<<<dim3(cdiv(N, 128), H, B), 192, kAttnSmem, st>>>(tmQ, tmK, tmV, p);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
+
 }  // namespace rn

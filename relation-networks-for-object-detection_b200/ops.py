@@ -65,6 +65,8 @@ def relation(X, boxes, Wq, bq, Wk, bk, Wg, bg, Wout, bout, key_index=None, M=Non
         kidx = key_index.to(device=X.device, dtype=torch.int32).contiguous()
         M = kidx.numel()
     M = int(M) if M is not None else N
+    if precision == 'f16' and not relation_tc_supported(Wq.shape[0], Wout2.shape[0], group, return_softmax):
+        precision = 'fp32'      # same library, the general fp32 kernels: the fused tcgen05 kernel is dk == 64 only
     desc = L.RelationDesc(B, N, M, d, Wq.shape[0], Wout2.shape[0], group, Wg.shape[1], wave_length,
                           int(residual_relu), PREC[precision])
     out = torch.empty((B, N, Wout2.shape[0]) if batched else (N, Wout2.shape[0]), dtype=torch.float32, device=X.device)
@@ -77,6 +79,11 @@ def relation(X, boxes, Wq, bq, Wk, bk, Wg, bg, Wout, bout, key_index=None, M=Non
                                 _ptr(Wg), _ptr(bg), _ptr(Wout2), _ptr(bout), _ptr(out), _ptr(sm), _ptr(ws), ws.numel(),
                                 _stream()), 'rn_relation_fwd')
     return (out, sm) if return_softmax else out
+
+
+def relation_tc_supported(dq, dout, group, return_softmax=False):
+    """Shapes the fused tcgen05 relation kernel covers (relation_tc.cu:tc_shape_ok)."""
+    return dq == 64 * group and dout % group == 0 and 1 <= dout // group <= 64 and not return_softmax
 
 
 def pos_embed(boxes, M=None, key_index=None, E=64, wave_length=1000.0, want_eps=True, want_emb=True):
