@@ -93,6 +93,20 @@ size_t rn_linear_workspace_bytes(int32_t rows, int32_t in, int32_t out, int32_t 
 int rn_linear_fwd(const float* x, const float* W, const float* b, float* y, int32_t rows, int32_t in, int32_t out,
                   int32_t relu, int32_t precision, void* workspace, size_t workspace_bytes, rn_stream_t stream);
 
+/* Pre-packed fp16 operands for RN_PREC_F16: pack once per weight update (one small kernel), reuse every forward.
+ * The packed relation block is [Wq; Wk; Wout padded to 64 cols/head] as fp16 [3*H*64, ceil8(d)] followed by the fp32
+ * bias [bq; bk; bout padded]; the packed linear weight is fp16 [out, ceil8(in)]. */
+size_t rn_relation_packed_bytes(const rn_relation_desc* desc);
+int rn_relation_pack(const rn_relation_desc* desc, const float* Wq, const float* bq, const float* Wk, const float* bk,
+                     const float* Wout, const float* bout, void* packed, rn_stream_t stream);
+int rn_relation_packed_fwd(const rn_relation_desc* desc, const float* X, const float* boxes, const int32_t* key_index,
+                           const void* packed, const float* Wg, const float* bg, float* out, void* workspace,
+                           size_t workspace_bytes, rn_stream_t stream);
+size_t rn_linear_packed_bytes(int32_t in, int32_t out);
+int rn_linear_pack(const float* W, int32_t in, int32_t out, void* packed, rn_stream_t stream);
+int rn_linear_packed_fwd(const float* x, const void* packed_W, const float* b, float* y, int32_t rows, int32_t in,
+                         int32_t out, int32_t relu, void* workspace, size_t workspace_bytes, rn_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * learn_nms CustomOp forward (LNMS:238-401) + test-time merge (SYM_REL_NMS:553-560).
  * Inputs in the order of LearnNmsProp.list_arguments (LNMS:429-441). */

@@ -64,6 +64,12 @@ SIGNATURES = {
     'rn_geometry_weight_fwd': (C.c_int, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_p, c_p, c_p, c_p]),
     'rn_linear_workspace_bytes': (c_sz, [c_i, c_i, c_i, c_i]),
     'rn_linear_fwd': (C.c_int, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_sz, c_p]),
+    'rn_relation_packed_bytes': (c_sz, [C.POINTER(RelationDesc)]),
+    'rn_relation_pack': (C.c_int, [C.POINTER(RelationDesc)] + [c_p] * 7 + [c_p]),
+    'rn_relation_packed_fwd': (C.c_int, [C.POINTER(RelationDesc)] + [c_p] * 7 + [c_p, c_sz, c_p]),
+    'rn_linear_packed_bytes': (c_sz, [c_i, c_i]),
+    'rn_linear_pack': (C.c_int, [c_p, c_i, c_i, c_p, c_p]),
+    'rn_linear_packed_fwd': (C.c_int, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_sz, c_p]),
     'rn_learn_nms_workspace_bytes': (c_sz, [C.POINTER(LearnNmsDesc)]),
     'rn_learn_nms_fwd': (C.c_int, [C.POINTER(LearnNmsDesc)] + [c_p] * 5 + [C.POINTER(LearnNmsWeights), c_p] + [c_p] * 4 +
                          [c_p, c_sz, c_p]),

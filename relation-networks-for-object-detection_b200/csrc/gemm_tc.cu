@@ -296,6 +296,24 @@ int cast_rows_f16(cudaStream_t st, const float* src, __half* dst, int rows, int 
   return RN_OK;
 }
 
+size_t linear_tc_packed_bytes(int in, int out) { return ws_slice((size_t)out * align_up(in, 8), 2); }
+
+int linear_tc_pack(const float* W, int in, int out, void* packed, cudaStream_t st) {
+  return cast_rows_f16(st, W, (__half*)packed, out, in, (int)align_up(in, 8));
+}
+
+int linear_tc_packed(const float* x, const void* packed_W, const float* b, float* y, int rows, int in, int out, int relu,
+                     void* wsp, size_t ws_bytes, cudaStream_t st) {
+  const int in8 = (int)align_up(in, 8);
+  Workspace ws(wsp, ws_bytes);
+  __half* x16 = ws.take<__half>((size_t)rows * in8);
+  if (!x16) { set_error("rn_linear_packed_fwd: workspace too small"); return RN_ERR_WORKSPACE; }
+  int r;
+  if ((r = cast_rows_f16(st, x, x16, rows, in, in8))) return r;
+  return gemm_tc(st, x16, in8, (const __half*)packed_W, in8, rows, out, in8, b, 0, relu, y, out, nullptr, 0, ws.base + ws.off,
+                 ws.size - ws.off);
+}
+
 int linear_tc(const float* x, const float* W, const float* b, float* y, int rows, int in, int out, int relu, void* wsp,
               size_t ws_bytes, cudaStream_t st) {
   const int in8 = (int)align_up(in, 8);

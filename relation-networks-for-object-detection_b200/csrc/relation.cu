@@ -211,3 +211,36 @@ extern "C" int rn_linear_fwd(const float* x, const float* W, const float* b, flo
   if (r) return r;
   return rn::launch_bias_act(st, y, b, (size_t)rows, out, relu);
 }
+
+// ---- pre-packed fp16 operands (RN_PREC_F16): pack once per weight update, reuse every forward
+extern "C" size_t rn_relation_packed_bytes(const rn_relation_desc* d) { return d ? rn::relation_tc_packed_bytes(d) : 0; }
+
+extern "C" int rn_relation_pack(const rn_relation_desc* d, const float* Wq, const float* bq, const float* Wk,
+                                const float* bk, const float* Wout, const float* bout, void* packed, rn_stream_t stream) {
+  int r = rn::check_desc(d);
+  if (r) return r;
+  RN_CHECK_ARG(Wq && bq && Wk && bk && Wout && bout && packed, "rn_relation_pack: null pointer argument");
+  return rn::relation_tc_pack(d, Wq, bq, Wk, bk, Wout, bout, packed, (cudaStream_t)stream);
+}
+
+extern "C" int rn_relation_packed_fwd(const rn_relation_desc* d, const float* X, const float* boxes,
+                                      const int32_t* key_index, const void* packed, const float* Wg, const float* bg,
+                                      float* out, void* ws, size_t ws_bytes, rn_stream_t stream) {
+  int r = rn::check_desc(d);
+  if (r) return r;
+  RN_CHECK_ARG(X && boxes && packed && Wg && bg && out && ws, "rn_relation_packed_fwd: null pointer argument");
+  return rn::relation_tc_packed(d, X, boxes, key_index, packed, Wg, bg, out, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" size_t rn_linear_packed_bytes(int32_t in, int32_t out) { return rn::linear_tc_packed_bytes(in, out); }
+
+extern "C" int rn_linear_pack(const float* W, int32_t in, int32_t out, void* packed, rn_stream_t stream) {
+  RN_CHECK_ARG(W && packed && in > 0 && out > 0, "rn_linear_pack: bad arguments");
+  return rn::linear_tc_pack(W, in, out, packed, (cudaStream_t)stream);
+}
+
+extern "C" int rn_linear_packed_fwd(const float* x, const void* packed_W, const float* b, float* y, int32_t rows,
+                                    int32_t in, int32_t out, int32_t relu, void* ws, size_t ws_bytes, rn_stream_t stream) {
+  RN_CHECK_ARG(x && packed_W && y && rows > 0 && in > 0 && out > 0 && ws, "rn_linear_packed_fwd: bad arguments");
+  return rn::linear_tc_packed(x, packed_W, b, y, rows, in, out, relu, ws, ws_bytes, (cudaStream_t)stream);
+}

@@ -12,9 +12,20 @@ int relation_tc(const rn_relation_desc* d, const float* X, const float* boxes, c
                 const float* bq, const float* Wk, const float* bk, const float* Wg, const float* bg, const float* Wout,
                 const float* bout, float* out, float* softmax_out, void* ws, size_t ws_bytes, cudaStream_t st);
 
+size_t relation_tc_packed_bytes(const rn_relation_desc* d);
+int relation_tc_pack(const rn_relation_desc* d, const float* Wq, const float* bq, const float* Wk, const float* bk,
+                     const float* Wout, const float* bout, void* packed, cudaStream_t st);
+int relation_tc_packed(const rn_relation_desc* d, const float* X, const float* boxes, const int* key_index,
+                       const void* packed, const float* Wg, const float* bg, float* out, void* ws, size_t ws_bytes,
+                       cudaStream_t st);
+
 // tcgen05 fp16 GEMM (gemm_tc.cu): y = act(x W^T + b)
 size_t linear_tc_workspace_bytes(int rows, int in, int out);
 int linear_tc(const float* x, const float* W, const float* b, float* y, int rows, int in, int out, int relu, void* ws,
               size_t ws_bytes, cudaStream_t st);
+size_t linear_tc_packed_bytes(int in, int out);
+int linear_tc_pack(const float* W, int in, int out, void* packed, cudaStream_t st);
+int linear_tc_packed(const float* x, const void* packed_W, const float* b, float* y, int rows, int in, int out, int relu,
+                     void* ws, size_t ws_bytes, cudaStream_t st);
 
 }  // namespace rn

@@ -300,8 +300,7 @@ size_t relation_tc_workspace_bytes(const rn_relation_desc* d) {
   size_t t = 0;
   t += ws_slice(B * N * d8, 2);          // X fp16
   t += ws_slice(B * M * d8, 2);          // gathered keys fp16
-  t += ws_slice(W3 * d8, 2);             // packed weights
-  t += ws_slice(W3, 4);                  // packed bias
+  t += relation_tc_packed_bytes(d);       // packed weights + bias (unpacked entry point)
   t += ws_slice(B * N * W3, 2);          // QKV' fp16
   t += ws_slice(B * M * 2 * H * 64, 2);  // KV' of gathered keys
   t += ws_slice(B * H * N * ldg, 4);     // log2 geometry weight
@@ -320,34 +319,47 @@ __global__ void gather_rows_f16_kernel(const __half* __restrict__ X, const int* 
 int launch_geom_weight_log2(cudaStream_t st, const float* boxes, const int* key_index, int B, int N, int M, int H, int E,
                             float wave_length, const float* Wg, const float* bg, float* g, int ldg);
 
-int relation_tc(const rn_relation_desc* d, const float* X, const float* boxes, const int* key_index, const float* Wq,
-                const float* bq, const float* Wk, const float* bk, const float* Wg, const float* bg, const float* Wout,
-                const float* bout, float* out, float* softmax_out, void* wsp, size_t ws_bytes, cudaStream_t st) {
+size_t relation_tc_packed_bytes(const rn_relation_desc* d) {
+  if (!tc_shape_ok(d)) return 0;
+  const size_t d8 = align_up(d->d, 8), W3 = 3 * (size_t)d->H * 64;
+  return ws_slice(W3 * d8, 2) + ws_slice(W3, 4);
+}
+
+int relation_tc_pack(const rn_relation_desc* d, const float* Wq, const float* bq, const float* Wk, const float* bk,
+                     const float* Wout, const float* bout, void* packed, cudaStream_t st) {
+  RN_CHECK_ARG(tc_shape_ok(d), "rn_relation_pack: shape not covered by the tcgen05 kernel (dq=%d dout=%d H=%d)", d->dq,
+               d->dout, d->H);
+  const int D = d->d, H = d->H, dv = d->dout / H, d8 = (int)align_up(D, 8), W3 = 3 * H * 64;
+  __half* w16 = (__half*)packed;
+  float* bias = (float*)((char*)packed + ws_slice((size_t)W3 * d8, 2));
+  const size_t total = (size_t)W3 * d8;
+  size_t blocks = (total + 255) / 256;
+  const size_t cap = (size_t)(sm_count() > 0 ? sm_count() : 148) * 8;
+  pack_relation_weights_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(Wq, bq, Wk, bk, Wout, bout, D, d8, H, dv,
+                                                                                 w16, bias);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
+
+int relation_tc_packed(const rn_relation_desc* d, const float* X, const float* boxes, const int* key_index,
+                       const void* packed, const float* Wg, const float* bg, float* out, void* wsp, size_t ws_bytes,
+                       cudaStream_t st) {
   RN_CHECK_ARG(is_sm100(), "RN_PREC_F16 needs an sm_100 device (tcgen05); use RN_PREC_FP32");
   RN_CHECK_ARG(tc_shape_ok(d), "RN_PREC_F16 relation kernel supports dq == 64*H and dout/H <= 64 (got dq=%d dout=%d H=%d); "
                "use RN_PREC_FP32 for this shape", d->dq, d->dout, d->H);
-  RN_CHECK_ARG(!softmax_out, "RN_PREC_F16 relation kernel never materialises the softmax; request it with RN_PREC_FP32");
   const int B = d->batch, N = d->N, M = d->M, D = d->d, H = d->H, dv = d->dout / H;
   const int d8 = (int)align_up(D, 8), W3 = 3 * H * 64, ldg = (int)align_up(M, 4);
+  const __half* w16 = (const __half*)packed;
+  const float* bias = (const float*)((const char*)packed + ws_slice((size_t)W3 * d8, 2));
   Workspace ws(wsp, ws_bytes);
   __half* x16 = ws.take<__half>((size_t)B * N * d8);
   __half* xk16 = ws.take<__half>((size_t)B * M * d8);
-  __half* w16 = ws.take<__half>((size_t)W3 * d8);
-  float* bias = ws.take<float>(W3);
   __half* qkv = ws.take<__half>((size_t)B * N * W3);
   __half* kv = ws.take<__half>((size_t)B * M * 2 * H * 64);
   float* lg = ws.take<float>((size_t)B * H * N * ldg);
   if (!lg) { set_error("rn_relation_fwd(F16): workspace too small (%zu < %zu)", ws_bytes, relation_tc_workspace_bytes(d)); return RN_ERR_WORKSPACE; }
   void* gws = ws.base + ws.off; const size_t gws_bytes = ws.size - ws.off;
   int r;
-  {
-    const size_t total = (size_t)W3 * d8;
-    size_t blocks = (total + 255) / 256;
-    const size_t cap = (size_t)sm_count() * 8;
-    pack_relation_weights_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(Wq, bq, Wk, bk, Wout, bout, D, d8, H, dv,
-                                                                                   w16, bias);
-    RN_LAUNCH_CHECK();
-  }
   if ((r = cast_rows_f16(st, X, x16, B * N, D, d8))) return r;
   const __half *Qp, *Kp, *Vp; long long ldq, ldk; long long bq_pitch, bk_pitch;
   if (key_index) {
@@ -382,6 +394,20 @@ int relation_tc(const rn_relation_desc* d, const float* X, const float* boxes, c
   relation_attn_tc_kernel<<<dim3(cdiv(N, 128), H, B), 192, kAttnSmem, st>>>(tmQ, tmK, tmV, p);
   RN_LAUNCH_CHECK();
   return RN_OK;
+}
+
+// unpacked entry (rn_relation_fwd with RN_PREC_F16): pack the weights into the workspace, then run
+int relation_tc(const rn_relation_desc* d, const float* X, const float* boxes, const int* key_index, const float* Wq,
+                const float* bq, const float* Wk, const float* bk, const float* Wg, const float* bg, const float* Wout,
+                const float* bout, float* out, float* softmax_out, void* wsp, size_t ws_bytes, cudaStream_t st) {
+  RN_CHECK_ARG(!softmax_out, "RN_PREC_F16 relation kernel never materialises the softmax; request it with RN_PREC_FP32");
+  const size_t pk = relation_tc_packed_bytes(d);
+  RN_CHECK_ARG(pk > 0, "RN_PREC_F16 relation kernel supports dq == 64*H and dout/H <= 64 (got dq=%d dout=%d H=%d); use "
+               "RN_PREC_FP32 for this shape", d->dq, d->dout, d->H);
+  if (ws_bytes < pk) { set_error("rn_relation_fwd(F16): workspace too small"); return RN_ERR_WORKSPACE; }
+  int r = relation_tc_pack(d, Wq, bq, Wk, bk, Wout, bout, wsp, st);
+  if (r) return r;
+  return relation_tc_packed(d, X, boxes, key_index, wsp, Wg, bg, out, (char*)wsp + pk, ws_bytes - pk, st);
 }
 
 }  // namespace rn

@@ -37,6 +37,29 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
+class _PackCache(object):
+    """fp16 operand cache for RN_PREC_F16: keyed by the weight tensors' storage + in-place version counter, so an
+    optimizer step (in-place update) repacks and anything else reuses the packed block."""
+
+    def __init__(self):
+        self.d = {}
+
+    def get(self, tensors, nbytes, pack_fn):
+        key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors)
+        hit = self.d.get(key)
+        if hit is None:
+            if len(self.d) > 256:
+                self.d.clear()
+            buf = torch.empty(nbytes, dtype=torch.uint8, device=tensors[0].device)
+            pack_fn(buf)
+            hit = (buf, tensors)          # keep the sources alive so data_ptr stays unique
+            self.d[key] = hit
+        return hit[0]
+
+
+_packs = _PackCache()
+
+
 def device_info():
     sm, ma, mi = C.c_int(), C.c_int(), C.c_int()
     ok = L.lib().rn_device_info(C.byref(sm), C.byref(ma), C.byref(mi))
@@ -75,6 +98,14 @@ def relation(X, boxes, Wq, bq, Wk, bk, Wg, bg, Wout, bout, key_index=None, M=Non
     lib = L.lib()
     nbytes = lib.rn_relation_workspace_bytes(C.byref(desc))
     ws = _workspace(nbytes, X.device)
+    if precision == 'f16':
+        def pack(buf):
+            L.check(lib.rn_relation_pack(C.byref(desc), _ptr(Wq), _ptr(bq), _ptr(Wk), _ptr(bk), _ptr(Wout2), _ptr(bout),
+                                         _ptr(buf), _stream()), 'rn_relation_pack')
+        packed = _packs.get((Wq, bq, Wk, bk, Wout2, bout), lib.rn_relation_packed_bytes(C.byref(desc)), pack)
+        L.check(lib.rn_relation_packed_fwd(C.byref(desc), _ptr(X), _ptr(boxes), _ptr(kidx), _ptr(packed), _ptr(Wg),
+                                           _ptr(bg), _ptr(out), _ptr(ws), ws.numel(), _stream()), 'rn_relation_packed_fwd')
+        return out
     L.check(lib.rn_relation_fwd(C.byref(desc), _ptr(X), _ptr(boxes), _ptr(kidx), _ptr(Wq), _ptr(bq), _ptr(Wk), _ptr(bk),
                                 _ptr(Wg), _ptr(bg), _ptr(Wout2), _ptr(bout), _ptr(out), _ptr(sm), _ptr(ws), ws.numel(),
                                 _stream()), 'rn_relation_fwd')
@@ -122,6 +153,13 @@ def linear(x, W, b=None, relu=False, precision=None):
     y = torch.empty((rows, cout), dtype=torch.float32, device=x.device)
     lib = L.lib()
     ws = _workspace(lib.rn_linear_workspace_bytes(rows, cin, cout, PREC[precision]), x.device)
+    if precision == 'f16':
+        def pack(buf):
+            L.check(lib.rn_linear_pack(_ptr(W), cin, cout, _ptr(buf), _stream()), 'rn_linear_pack')
+        packed = _packs.get((W,), lib.rn_linear_packed_bytes(cin, cout), pack)
+        L.check(lib.rn_linear_packed_fwd(_ptr(x2), _ptr(packed), _ptr(b), _ptr(y), rows, cin, cout, int(relu), _ptr(ws),
+                                         ws.numel(), _stream()), 'rn_linear_packed_fwd')
+        return y
     L.check(lib.rn_linear_fwd(_ptr(x2), _ptr(W), _ptr(b), _ptr(y), rows, cin, cout, int(relu), PREC[precision], _ptr(ws),
                               ws.numel(), _stream()), 'rn_linear_fwd')
     return y
