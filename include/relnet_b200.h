@@ -102,6 +102,12 @@ int rn_relation_pack(const rn_relation_desc* desc, const float* Wq, const float*
 int rn_relation_packed_fwd(const rn_relation_desc* desc, const float* X, const float* boxes, const int32_t* key_index,
                            const void* packed, const float* Wg, const float* bg, float* out, void* workspace,
                            size_t workspace_bytes, rn_stream_t stream);
+/* measurement hook: run only the stages in stage_mask (1 = cast + projection GEMM, 2 = geometry kernel, 4 = fused attention
+ * kernel) on the intermediates a previous full call left in the same workspace -- used by bench.py to time one kernel
+ * with CUDA events */
+int rn_relation_packed_stages(const rn_relation_desc* desc, const float* X, const float* boxes, const int32_t* key_index,
+                              const void* packed, const float* Wg, const float* bg, float* out, void* workspace,
+                              size_t workspace_bytes, int32_t stage_mask, rn_stream_t stream);
 size_t rn_linear_packed_bytes(int32_t in, int32_t out);
 int rn_linear_pack(const float* W, int32_t in, int32_t out, void* packed, rn_stream_t stream);
 int rn_linear_packed_fwd(const float* x, const void* packed_W, const float* b, float* y, int32_t rows, int32_t in,

@@ -67,6 +67,7 @@ SIGNATURES = {
     'rn_relation_packed_bytes': (c_sz, [C.POINTER(RelationDesc)]),
     'rn_relation_pack': (C.c_int, [C.POINTER(RelationDesc)] + [c_p] * 7 + [c_p]),
     'rn_relation_packed_fwd': (C.c_int, [C.POINTER(RelationDesc)] + [c_p] * 7 + [c_p, c_sz, c_p]),
+    'rn_relation_packed_stages': (C.c_int, [C.POINTER(RelationDesc)] + [c_p] * 7 + [c_p, c_sz, c_i, c_p]),
     'rn_linear_packed_bytes': (c_sz, [c_i, c_i]),
     'rn_linear_pack': (C.c_int, [c_p, c_i, c_i, c_p, c_p]),
     'rn_linear_packed_fwd': (C.c_int, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_sz, c_p]),

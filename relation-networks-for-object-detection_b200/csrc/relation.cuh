@@ -17,7 +17,7 @@ int relation_tc_pack(const rn_relation_desc* d, const float* Wq, const float* bq
                      const float* Wout, const float* bout, void* packed, cudaStream_t st);
 int relation_tc_packed(const rn_relation_desc* d, const float* X, const float* boxes, const int* key_index,
                        const void* packed, const float* Wg, const float* bg, float* out, void* ws, size_t ws_bytes,
-                       cudaStream_t st);
+                       cudaStream_t st, int stage_mask);
 
 // tcgen05 fp16 GEMM (gemm_tc.cu): y = act(x W^T + b)
 size_t linear_tc_workspace_bytes(int rows, int in, int out);

@@ -343,7 +343,8 @@ int relation_tc_pack(const rn_relation_desc* d, const float* Wq, const float* bq
 
 int relation_tc_packed(const rn_relation_desc* d, const float* X, const float* boxes, const int* key_index,
                        const void* packed, const float* Wg, const float* bg, float* out, void* wsp, size_t ws_bytes,
-                       cudaStream_t st) {
+                       cudaStream_t st, int stage_mask) {
+  const bool do_proj = stage_mask & 1, do_geom = stage_mask & 2, do_attn = stage_mask & 4;
   RN_CHECK_ARG(is_sm100(), "RN_PREC_F16 needs an sm_100 device (tcgen05); use RN_PREC_FP32");
   RN_CHECK_ARG(tc_shape_ok(d), "RN_PREC_F16 relation kernel supports dq == 64*H and dout/H <= 64 (got dq=%d dout=%d H=%d); "
                "use RN_PREC_FP32 for this shape", d->dq, d->dout, d->H);
@@ -360,21 +361,24 @@ int relation_tc_packed(const rn_relation_desc* d, const float* X, const float* b
   if (!lg) { set_error("rn_relation_fwd(F16): workspace too small (%zu < %zu)", ws_bytes, relation_tc_workspace_bytes(d)); return RN_ERR_WORKSPACE; }
   void* gws = ws.base + ws.off; const size_t gws_bytes = ws.size - ws.off;
   int r;
-  if ((r = cast_rows_f16(st, X, x16, B * N, D, d8))) return r;
+  if (do_proj && (r = cast_rows_f16(st, X, x16, B * N, D, d8))) return r;
   const __half *Qp, *Kp, *Vp; long long ldq, ldk; long long bq_pitch, bk_pitch;
   if (key_index) {
-    gather_rows_f16_kernel<<<dim3(M, B), 128, 0, st>>>(x16, key_index, N, M, d8, xk16);
-    RN_LAUNCH_CHECK();
-    if ((r = gemm_tc(st, x16, d8, w16, d8, B * N, H * 64, d8, bias, 0, 0, nullptr, 0, qkv, H * 64, gws, gws_bytes))) return r;
-    if ((r = gemm_tc(st, xk16, d8, w16 + (size_t)H * 64 * d8, d8, B * M, 2 * H * 64, d8, bias + H * 64, 0, 0, nullptr, 0, kv,
-                     2 * H * 64, gws, gws_bytes))) return r;
+    if (do_proj) {
+      gather_rows_f16_kernel<<<dim3(M, B), 128, 0, st>>>(x16, key_index, N, M, d8, xk16);
+      RN_LAUNCH_CHECK();
+      if ((r = gemm_tc(st, x16, d8, w16, d8, B * N, H * 64, d8, bias, 0, 0, nullptr, 0, qkv, H * 64, gws, gws_bytes))) return r;
+      if ((r = gemm_tc(st, xk16, d8, w16 + (size_t)H * 64 * d8, d8, B * M, 2 * H * 64, d8, bias + H * 64, 0, 0, nullptr, 0,
+                       kv, 2 * H * 64, gws, gws_bytes))) return r;
+    }
     Qp = qkv; ldq = H * 64; bq_pitch = (long long)N * ldq;
     Kp = kv; Vp = kv + H * 64; ldk = 2 * H * 64; bk_pitch = (long long)M * ldk;
   } else {
-    if ((r = gemm_tc(st, x16, d8, w16, d8, B * N, W3, d8, bias, 0, 0, nullptr, 0, qkv, W3, gws, gws_bytes))) return r;
+    if (do_proj && (r = gemm_tc(st, x16, d8, w16, d8, B * N, W3, d8, bias, 0, 0, nullptr, 0, qkv, W3, gws, gws_bytes))) return r;
     Qp = qkv; Kp = qkv + H * 64; Vp = qkv + 2 * H * 64; ldq = ldk = W3; bq_pitch = bk_pitch = (long long)N * W3;
   }
-  if ((r = launch_geom_weight_log2(st, boxes, key_index, B, N, M, H, d->E, d->wave_length, Wg, bg, lg, ldg))) return r;
+  if (do_geom && (r = launch_geom_weight_log2(st, boxes, key_index, B, N, M, H, d->E, d->wave_length, Wg, bg, lg, ldg))) return r;
+  if (!do_attn) return RN_OK;
 
   CUtensorMap tmQ, tmK, tmV;
   if ((r = encode_tmap_3d_f16(&tmQ, Qp, B, N, H * 64, ldq, bq_pitch, 128, 64))) return r;
@@ -407,7 +411,7 @@ int relation_tc(const rn_relation_desc* d, const float* X, const float* boxes, c
   if (ws_bytes < pk) { set_error("rn_relation_fwd(F16): workspace too small"); return RN_ERR_WORKSPACE; }
   int r = relation_tc_pack(d, Wq, bq, Wk, bk, Wout, bout, wsp, st);
   if (r) return r;
-  return relation_tc_packed(d, X, boxes, key_index, wsp, Wg, bg, out, (char*)wsp + pk, ws_bytes - pk, st);
+  return relation_tc_packed(d, X, boxes, key_index, wsp, Wg, bg, out, (char*)wsp + pk, ws_bytes - pk, st, 7);
 }
 
 }  // namespace rn

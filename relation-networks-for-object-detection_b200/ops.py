@@ -72,7 +72,7 @@ def default_precision():
 
 # ------------------------------------------------------------------------------------------------------------------
 def relation(X, boxes, Wq, bq, Wk, bk, Wg, bg, Wout, bout, key_index=None, M=None, group=16, residual_relu=False,
-             precision=None, wave_length=1000.0, return_softmax=False):
+             precision=None, wave_length=1000.0, return_softmax=False, stage_mask=7):
     """Object-relation module (SYM_REL:30-151 + :267-268).  X [N,d] or [B,N,d]; boxes [N,4] or [B,N,4]."""
     precision = precision or default_precision()
     X = _f32(X, 'X'); boxes = _f32(boxes, 'boxes')
@@ -103,6 +103,11 @@ def relation(X, boxes, Wq, bq, Wk, bk, Wg, bg, Wout, bout, key_index=None, M=Non
             L.check(lib.rn_relation_pack(C.byref(desc), _ptr(Wq), _ptr(bq), _ptr(Wk), _ptr(bk), _ptr(Wout2), _ptr(bout),
                                          _ptr(buf), _stream()), 'rn_relation_pack')
         packed = _packs.get((Wq, bq, Wk, bk, Wout2, bout), lib.rn_relation_packed_bytes(C.byref(desc)), pack)
+        if stage_mask != 7:     # measurement hook: rerun a subset of the stages on the previous call's intermediates
+            L.check(lib.rn_relation_packed_stages(C.byref(desc), _ptr(X), _ptr(boxes), _ptr(kidx), _ptr(packed), _ptr(Wg),
+                                                  _ptr(bg), _ptr(out), _ptr(ws), ws.numel(), stage_mask, _stream()),
+                    'rn_relation_packed_stages')
+            return out
         L.check(lib.rn_relation_packed_fwd(C.byref(desc), _ptr(X), _ptr(boxes), _ptr(kidx), _ptr(packed), _ptr(Wg),
                                            _ptr(bg), _ptr(out), _ptr(ws), ws.numel(), _stream()), 'rn_relation_packed_fwd')
         return out

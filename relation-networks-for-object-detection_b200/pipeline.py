@@ -1,0 +1,99 @@
+"""Host-side assembly of the hot path for one image (the body of get_symbol after the trunk, SYM_REL_NMS:324-565):
+
+    rpn cls_prob / bbox_pred --proposal--> rois --ROIPooling(conv_new_1 relu)--> fc_new_1 --relation#1(+res,relu)-->
+    fc_new_2 --relation#2(+res,relu)--> cls_score / bbox_pred --learn_nms--> sorted_bbox, nms_final_score
+
+Every arrow is a call into librelnet_b200.so (ops.py); weights are addressed by their checkpoint names like the
+reference (SURVEY.md section 8a parameter inventory).  Test-time (is_train=False) graph only.
+"""
+import math
+import torch
+from . import ops
+
+HEAD_PARAM_SHAPES = {
+    'fc_new_1_weight': (1024, 12544), 'fc_new_1_bias': (1024,),
+    'fc_new_2_weight': (1024, 1024), 'fc_new_2_bias': (1024,),
+    'cls_score_weight': (81, 1024), 'cls_score_bias': (81,),
+    'bbox_pred_weight': (8, 1024), 'bbox_pred_bias': (8,),
+    'nms_rank_weight': (128, 1024), 'nms_rank_bias': (128,),
+    'roi_feat_embedding_weight': (128, 1024), 'roi_feat_embedding_bias': (128,),
+    'nms_pair_pos_fc1_1_weight': (16, 64), 'nms_pair_pos_fc1_1_bias': (16,),
+    'nms_query_1_weight': (1024, 128), 'nms_query_1_bias': (1024,),
+    'nms_key_1_weight': (1024, 128), 'nms_key_1_bias': (1024,),
+    'nms_linear_out_1_weight': (128, 128, 1, 1), 'nms_linear_out_1_bias': (128,),
+    'nms_logit_weight': (5, 128), 'nms_logit_bias': (5,),
+}
+for _i in (1, 2):
+    HEAD_PARAM_SHAPES.update({
+        'pair_pos_fc1_%d_weight' % _i: (16, 64), 'pair_pos_fc1_%d_bias' % _i: (16,),
+        'query_%d_weight' % _i: (1024, 1024), 'query_%d_bias' % _i: (1024,),
+        'key_%d_weight' % _i: (1024, 1024), 'key_%d_bias' % _i: (1024,),
+        'linear_out_%d_weight' % _i: (1024, 1024, 1, 1), 'linear_out_%d_bias' % _i: (1024,)})
+
+NMS_NAMES = [k for k in HEAD_PARAM_SHAPES if k.startswith(('nms_', 'roi_feat_embedding'))]
+
+
+def init_head_params(seed=0, device='cpu', init='fan_in'):
+    """'ref' = the reference initialiser (Normal(0, 0.01), zero bias, nms_logit_bias = -3: SYM_REL:327-360,
+    SYM_REL_NMS:571-600); 'fan_in' = Normal(0, 1/sqrt(fan_in)) so logits are O(1) and every branch is exercised."""
+    g = torch.Generator().manual_seed(seed)
+    P = {}
+    for k, shp in HEAD_PARAM_SHAPES.items():
+        if k.endswith('_bias'):
+            t = torch.zeros(shp)
+            if init != 'ref':
+                t = torch.randn(shp, generator=g) * 0.02
+        else:
+            fan = 1
+            for s in shp[1:]:
+                fan *= s
+            t = torch.randn(shp, generator=g) * (0.01 if init == 'ref' else 1.0 / math.sqrt(fan))
+        P[k] = t
+    if init == 'ref':
+        P['nms_logit_bias'] = torch.full((5,), -3.0)
+    else:
+        for i in (1, 2):
+            P['pair_pos_fc1_%d_weight' % i] = torch.randn(16, 64, generator=g) * 0.125
+            P['pair_pos_fc1_%d_bias' % i] = torch.rand(16, generator=g) * 0.5
+        P['nms_pair_pos_fc1_1_weight'] = torch.randn(16, 64, generator=g) * 0.125
+        P['nms_pair_pos_fc1_1_bias'] = torch.rand(16, generator=g) * 0.5
+    return {k: v.float().to(device).contiguous() for k, v in P.items()}
+
+
+class RelationHead(object):
+    """Faster-RCNN 2FC + Relation + Learn-NMS head at test time (config values: ...relation_learn_nms_8epoch.yaml)."""
+
+    def __init__(self, params, precision=None, feat_stride=16, scales=(4, 8, 16, 32), ratios=(0.5, 1, 2),
+                 pre_nms_top_n=6000, post_nms_top_n=300, nms_thresh=0.7, min_size=0, first_n=100,
+                 class_thresh=0.01, merge_method=-1):
+        self.P = params
+        self.precision = precision or ops.default_precision()
+        self.cfg = dict(feat_stride=feat_stride, scales=scales, ratios=ratios, pre_nms_top_n=pre_nms_top_n,
+                        post_nms_top_n=post_nms_top_n, thresh=nms_thresh, min_size=min_size)
+        self.first_n, self.class_thresh, self.merge_method = first_n, class_thresh, merge_method
+        self.nongt_dim = post_nms_top_n
+
+    def relation(self, x, boxes, idx, nongt_dim):
+        P = self.P
+        return ops.relation(x, boxes, P['query_%d_weight' % idx], P['query_%d_bias' % idx], P['key_%d_weight' % idx],
+                            P['key_%d_bias' % idx], P['pair_pos_fc1_%d_weight' % idx], P['pair_pos_fc1_%d_bias' % idx],
+                            P['linear_out_%d_weight' % idx], P['linear_out_%d_bias' % idx], M=nongt_dim, group=16,
+                            residual_relu=True, precision=self.precision)
+
+    def forward(self, rpn_cls_prob, rpn_bbox_pred, conv_feat, im_info):
+        P, prec = self.P, self.precision
+        rois, _ = ops.proposal(rpn_cls_prob, rpn_bbox_pred, im_info, **self.cfg)                  # SYM_REL_NMS:324-329
+        pooled = ops.roi_pool(conv_feat, rois, (7, 7), 1.0 / self.cfg['feat_stride'])             # :335
+        boxes = rois[:, 1:].contiguous()                                                          # :337
+        fc1 = ops.linear(pooled, P['fc_new_1_weight'], P['fc_new_1_bias'], precision=prec)        # :344
+        fc_all_1 = self.relation(fc1, boxes, 1, self.nongt_dim)                                   # :346-351
+        fc2 = ops.linear(fc_all_1, P['fc_new_2_weight'], P['fc_new_2_bias'], precision=prec)      # :353
+        fc_all_2 = self.relation(fc2, boxes, 2, self.nongt_dim)                                   # :354-359
+        cls_score = ops.linear(fc_all_2, P['cls_score_weight'], P['cls_score_bias'], precision=prec)
+        bbox_pred = ops.linear(fc_all_2, P['bbox_pred_weight'], P['bbox_pred_bias'], precision=prec)
+        multi, sorted_bbox, sorted_score, final = ops.learn_nms(                                  # :518-560
+            cls_score, bbox_pred, rois, im_info, fc_all_2, {k: P[k] for k in NMS_NAMES}, first_n=self.first_n,
+            class_thresh=self.class_thresh, nongt_dim=self.nongt_dim, merge_method=self.merge_method, precision=prec)
+        return dict(rois=rois, cls_score=cls_score, bbox_pred=bbox_pred, fc_all_2_relu=fc_all_2,
+                    nms_multi_score=multi, learn_nms_sorted_bbox=sorted_bbox, sorted_score=sorted_score,
+                    nms_final_score_output=final)

@@ -1,0 +1,94 @@
+"""ResNet-101 v1 trunk + RPN + conv_new_1 as plain torch/cuDNN modules (random init, frozen-BN folded into the convs).
+
+OUT OF SCOPE as kernels: the trunk only exists to feed the hot path realistic tensors and
+to report images/sec on BASELINE.json's configs[1]; nothing here is hand-written.  Layer layout follows
+relation_rcnn/symbols/resnet_v1_101_rcnn_base.py: conv1 7x7/2, ceil-mode 3x3/2 max pool, res2..res4 (3, 4, 23 blocks,
+stride on the first 1x1), res5 with dilation 2 / stride 1 (:621-683), RPN 3x3+relu -> 1x1 cls (2A) / 1x1 bbox (4A)
+(:685-693), softmax over {bg, fg} per anchor, conv_new_1 1x1 2048->256 + relu (SYM_REL:249-250).
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class Bottleneck(nn.Module):
+    def __init__(self, cin, mid, cout, stride=1, dilation=1, project=False):
+        super().__init__()
+        self.c1 = nn.Conv2d(cin, mid, 1, stride=stride)
+        self.c2 = nn.Conv2d(mid, mid, 3, padding=dilation, dilation=dilation)
+        self.c3 = nn.Conv2d(mid, cout, 1)
+        self.proj = nn.Conv2d(cin, cout, 1, stride=stride) if project else None
+
+    def forward(self, x):
+        y = F.relu(self.c1(x)); y = F.relu(self.c2(y)); y = self.c3(y)
+        return F.relu(y + (self.proj(x) if self.proj is not None else x))
+
+
+def _stage(cin, mid, cout, n, stride, dilation=1):
+    blocks = [Bottleneck(cin, mid, cout, stride, dilation, project=True)]
+    blocks += [Bottleneck(cout, mid, cout, 1, dilation) for _ in range(n - 1)]
+    return nn.Sequential(*blocks)
+
+
+class Trunk(nn.Module):
+    def __init__(self, num_anchors=12):
+        super().__init__()
+        self.A = num_anchors
+        self.conv1 = nn.Conv2d(3, 64, 7, stride=2, padding=3)
+        self.res2 = _stage(64, 64, 256, 3, 1)
+        self.res3 = _stage(256, 128, 512, 4, 2)
+        self.res4 = _stage(512, 256, 1024, 23, 2)
+        self.res5 = _stage(1024, 512, 2048, 3, 1, dilation=2)
+        self.rpn_conv = nn.Conv2d(1024, 512, 3, padding=1)
+        self.rpn_cls = nn.Conv2d(512, 2 * num_anchors, 1)
+        self.rpn_bbox = nn.Conv2d(512, 4 * num_anchors, 1)
+        self.conv_new_1 = nn.Conv2d(2048, 256, 1)
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode='fan_in', nonlinearity='relu')
+                nn.init.zeros_(m.bias)
+        # frozen BN is folded into the convs; emulate its normalisation so 33 residual blocks stay O(1):
+        self.conv1.weight.data.mul_(1.0 / 50.0)                 # input is mean-subtracted pixels, std ~50
+        for m in self.modules():
+            if isinstance(m, Bottleneck):
+                m.c3.weight.data.mul_(0.25)
+
+    @torch.no_grad()
+    def calibrate(self, image):
+        """Data-dependent rescale of the four head convs (deterministic given the seed): RPN scores std 1.5, deltas std
+        0.15, pooled feature std 1 -- a realistic top-k / NMS / ROI workload instead of saturated garbage."""
+        x = F.max_pool2d(F.relu(self.conv1(image)), 3, 2, ceil_mode=True)
+        c4 = self.res4(self.res3(self.res2(x)))
+        c5 = self.res5(c4)
+        self.rpn_conv.weight.data.div_(F.relu(self.rpn_conv(c4)).float().std().clamp_min(1e-6))
+        r = F.relu(self.rpn_conv(c4))
+        self.rpn_cls.weight.data.mul_(1.5 / self.rpn_cls(r).float().std().clamp_min(1e-6))
+        self.rpn_bbox.weight.data.mul_(0.15 / self.rpn_bbox(r).float().std().clamp_min(1e-6))
+        self.conv_new_1.weight.data.div_(F.relu(self.conv_new_1(c5)).float().std().clamp_min(1e-6))
+
+    @torch.no_grad()
+    def forward(self, image):
+        """image [1,3,H,W] -> (rpn_cls_prob [1,2A,h,w] fp32, rpn_bbox_pred [1,4A,h,w] fp32, conv_new_1_relu [1,256,h,w] fp32)"""
+        x = F.relu(self.conv1(image))
+        x = F.max_pool2d(x, 3, 2, ceil_mode=True)
+        c4 = self.res4(self.res3(self.res2(x)))
+        c5 = self.res5(c4)
+        r = F.relu(self.rpn_conv(c4))
+        score = self.rpn_cls(r).float()
+        b, _, h, w = score.shape
+        prob = F.softmax(score.reshape(b, 2, self.A * h, w), dim=1).reshape(b, 2 * self.A, h, w)
+        bbox = self.rpn_bbox(r).float()
+        feat = F.relu(self.conv_new_1(c5)).float()
+        return prob.contiguous(), bbox.contiguous(), feat.contiguous()
+
+
+def make_trunk(device, dtype=torch.bfloat16, seed=0):
+    torch.manual_seed(seed)
+    t = Trunk().eval()
+    g = torch.Generator().manual_seed(seed + 1)
+    t = t.to(device=device)
+    t.calibrate((torch.randn((1, 3, 600, 1000), generator=g) * 50.0).to(device))
+    t = t.to(dtype=dtype)
+    if device != 'cpu' and str(device) != 'cpu':
+        t = t.to(memory_format=torch.channels_last)
+    return t
