@@ -8,7 +8,7 @@ proposal -> ROI pool -> fc_new_1 -> relation#1 -> fc_new_2 -> relation#2 -> cls/
   e2e        same through the public API with the image in pinned HOST memory (H2D inside the timed region) and the
              detections (sorted boxes + final scores) copied back to the host every step
   hot_path   the same step without the trunk (trunk outputs resident) + relation-module microseconds
-  roofline   the fused tcgen05 relation kernel (relation_attn_tc_kernel) timed alone with CUDA events at N=M=300, d=1024,
+  roofline   the fused tcgen05 relation kernel (relation_attn_tile_kernel + combine at this size) timed alone with CUDA events at N=M=300, d=1024,
              H=16: achieved = 4*N*M*d FLOP / duration against the measured bf16 peak (MEASURED_PEAKS.json)
   cpu_baseline  the numpy/C oracle of the hot path (oracle/pipeline_np.py) on this host, one image
   --impl reference   the CPU arm: torch-CPU fp32 trunk + oracle hot path, same metric/config (rank 0 only)
@@ -170,7 +170,7 @@ def relation_kernel_roofline(ops, pk, device):
     times['module_warm'] = e0.elapsed_time(e1) * 1e3 / 50
     flops = 4.0 * 300 * 300 * 1024
     achieved = flops / (times['attn'] * 1e-6) / 1e12
-    return dict(bound='tensor', kernel='relation_attn_tc_kernel', achieved=round(achieved, 3), peak=pk['tflops'],
+    return dict(bound='tensor', kernel='relation_attn_tile_kernel (+combine)', achieved=round(achieved, 3), peak=pk['tflops'],
                 unit='TFLOP/s', frac=round(achieved / pk['tflops'], 5), traffic=None,
                 algorithmic_flops=flops, duration_us=round(times['attn'], 2), peak_source=pk['source'],
                 note='N=M=300,d=1024,H=16: 0.37 GFLOP is launch-latency sized (SURVEY 7); sweep in profiles/'), times

@@ -61,6 +61,118 @@ __global__ void __launch_bounds__(128) geom_weight_kernel(const float* __restric
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// E = 64 fast path: the 64 -> H pair FC runs on mma.sync (m16n8k16, fp16 x fp16 -> fp32) with the A fragment produced
+// IN REGISTERS: a warp owns 16 (query, key) pairs; for coordinate c the 16 embedding values [sin f0..f7, cos f0..f7] of
+// a pair are exactly one K=16 step, and lane (g = lane/4, q = lane%4) needs sin/cos of frequencies 2q, 2q+1 for the
+// pairs g and g+8 -- i.e. every sin/cos is computed once, by the lane whose fragment slot it fills.  phi and Wg are
+// split into fp16 hi + lo parts (3 MMAs per step: hi*hi + lo*hi + hi*lo), so the result is fp32-accurate (~1e-6).
+// sin/cos: Cody-Waite reduction by 2*pi in two FMAs, then MUFU.SIN/COS on [-pi, pi] (|err| < 5e-7); arguments reach
+// +-690 rad.  The SIMT kernel above (libdevice sincosf + 1024 FMA per pair) measured 23 us at N = M = 300 and 145 us on
+// the learn-NMS batch (profiles/r01_launches_hot_v1.csv); this form does ~1/50 of the instructions.
+__device__ __forceinline__ void sincos_2pi(float x, float* s, float* c) {
+  const float n = rintf(x * 0.15915494309189535f);
+  float r = fmaf(n, -6.2831854820251465f, x);
+  r = fmaf(n, 1.7484555e-7f, r);
+  *s = __sinf(r);
+  *c = __cosf(r);
+}
+
+__device__ __forceinline__ void split_h2(float v0, float v1, uint32_t* hi, uint32_t* lo) {
+  const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+  const __half l0 = __float2half_rn(v0 - __half2float(h0)), l1 = __float2half_rn(v1 - __half2float(h1));
+  __half2 H = __halves2half2(h0, h1), L = __halves2half2(l0, l1);
+  *hi = *reinterpret_cast<uint32_t*>(&H);
+  *lo = *reinterpret_cast<uint32_t*>(&L);
+}
+
+__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// grid (ceil(M / (16*TILES*4)), N, B), 128 threads: warp w handles TILES consecutive 16-key tiles of query n
+template <int NHALF>     // number of 8-head halves (1: H <= 8, 2: H <= 16)
+__global__ void __launch_bounds__(128) geom_weight_mma_kernel(const float* __restrict__ boxes,
+                                                              const int* __restrict__ key_index, int N, int M, int H,
+                                                              GeomFreq fr, const float* __restrict__ Wg,
+                                                              const float* __restrict__ bg, float* __restrict__ out,
+                                                              int ldg, int log2_out, int tiles_per_warp) {
+  const int b = blockIdx.z, n = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, q = lane & 3;
+  // B fragments of Wg^T: element (k, col) = Wg[nh*8 + col][c*16 + k]; this lane holds col = g, k = 2q,2q+1 | 2q+8,2q+9
+  uint32_t bh[4][NHALF][2], bl[4][NHALF][2];
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int nh = 0; nh < NHALF; ++nh) {
+      const int h = nh * 8 + g;
+      const float* w = Wg + (size_t)(h < H ? h : 0) * 64 + c * 16;
+      const float z = h < H ? 1.f : 0.f;
+      split_h2(z * w[2 * q], z * w[2 * q + 1], &bh[c][nh][0], &bl[c][nh][0]);
+      split_h2(z * w[2 * q + 8], z * w[2 * q + 9], &bh[c][nh][1], &bl[c][nh][1]);
+    }
+  float bias[NHALF][2];
+#pragma unroll
+  for (int nh = 0; nh < NHALF; ++nh) {
+    const int h = nh * 8 + 2 * q;
+    bias[nh][0] = h < H ? bg[h] : 0.f;
+    bias[nh][1] = h + 1 < H ? bg[h + 1] : 0.f;
+  }
+  const float d0 = fr.dim[2 * q], d1 = fr.dim[2 * q + 1];
+  const float4 bn = reinterpret_cast<const float4*>(boxes)[(size_t)b * N + n];
+  const int m_warp = (blockIdx.x * 4 + warp) * tiles_per_warp * 16;
+  for (int t = 0; t < tiles_per_warp; ++t) {
+    const int m0 = m_warp + t * 16;
+    if (m0 >= M) break;                                        // warp-uniform
+    float acc[NHALF][4];
+#pragma unroll
+    for (int nh = 0; nh < NHALF; ++nh) { acc[nh][0] = acc[nh][1] = acc[nh][2] = acc[nh][3] = 0.f; }
+    float eps[2][4];
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int m = min(m0 + g + 8 * rr, M - 1);
+      const int mi = key_index ? key_index[m] : m;
+      pair_eps(bn, reinterpret_cast<const float4*>(boxes)[(size_t)b * N + mi], eps[rr]);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float sn[2][2], cs[2][2];
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const float a = 100.0f * eps[rr][c];
+        sincos_2pi(__fdiv_rn(a, d0), &sn[rr][0], &cs[rr][0]);
+        sincos_2pi(__fdiv_rn(a, d1), &sn[rr][1], &cs[rr][1]);
+      }
+      uint32_t ah[4], al[4];
+      split_h2(sn[0][0], sn[0][1], &ah[0], &al[0]);            // a0: row g,   cols 2q,2q+1   (sin)
+      split_h2(sn[1][0], sn[1][1], &ah[1], &al[1]);            // a1: row g+8
+      split_h2(cs[0][0], cs[0][1], &ah[2], &al[2]);            // a2: row g,   cols 2q+8,2q+9 (cos)
+      split_h2(cs[1][0], cs[1][1], &ah[3], &al[3]);            // a3: row g+8
+#pragma unroll
+      for (int nh = 0; nh < NHALF; ++nh) {
+        mma16816(acc[nh], ah[0], ah[1], ah[2], ah[3], bh[c][nh][0], bh[c][nh][1]);
+        mma16816(acc[nh], al[0], al[1], al[2], al[3], bh[c][nh][0], bh[c][nh][1]);
+        mma16816(acc[nh], ah[0], ah[1], ah[2], ah[3], bl[c][nh][0], bl[c][nh][1]);
+      }
+    }
+    // C fragment: c0 (row g, head 2q), c1 (row g, head 2q+1), c2 (row g+8, head 2q), c3 (row g+8, head 2q+1)
+#pragma unroll
+    for (int nh = 0; nh < NHALF; ++nh)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int h = nh * 8 + 2 * q + (i & 1), m = m0 + g + 8 * (i >> 1);
+        if (h < H && m < M) {
+          const float gv = fmaxf(acc[nh][i] + bias[nh][i & 1], 1e-6f);
+          out[(((size_t)b * H + h) * N + n) * ldg + m] = log2_out ? __log2f(gv) : gv;
+        }
+      }
+  }
+}
+
 __global__ void pos_embed_kernel(const float* __restrict__ boxes, const int* __restrict__ key_index, int N, int M, int E,
                                  GeomFreq fr, float* __restrict__ eps_out, float* __restrict__ emb_out) {
   const int n = blockIdx.y;
@@ -116,6 +228,18 @@ static int launch_geom_weight_impl(cudaStream_t st, const float* boxes, const in
   int r = make_freq(E, wave_length, &fr);
   if (r) return r;
   RN_CHECK_ARG(H >= 1 && H <= 16, "geometry heads H=%d unsupported (1..16)", H);
+  if (E == 64) {
+    // tensor-core FC path: 16 pairs per warp-tile; pick tiles/warp so that one CTA (4 warps) covers <= M keys of a row
+    const int tiles = cdiv(M, 16);
+    const int tpw = tiles >= 16 ? 2 : 1;
+    dim3 grid(cdiv(tiles, 4 * tpw), N, B);
+    if (H <= 8)
+      geom_weight_mma_kernel<1><<<grid, 128, 0, st>>>(boxes, key_index, N, M, H, fr, Wg, bg, g, ldg, log2_out, tpw);
+    else
+      geom_weight_mma_kernel<2><<<grid, 128, 0, st>>>(boxes, key_index, N, M, H, fr, Wg, bg, g, ldg, log2_out, tpw);
+    RN_LAUNCH_CHECK();
+    return RN_OK;
+  }
   dim3 grid(cdiv(M, 128), N, B);
   if (H <= 4) {
     size_t smem = (size_t)(E * 4 + 4) * sizeof(float);

@@ -10,6 +10,7 @@
 //   exit after post_nms kept -> emit rois (+ deterministic padding keep[i % kept]).
 // HBM traffic is ~1 MB of maps + <= 4.5 MB of mask: latency bound, not bandwidth bound (DESIGN.md "proposal").
 #include "common.cuh"
+#include <algorithm>
 
 namespace rn {
 
@@ -75,56 +76,104 @@ __global__ void __launch_bounds__(256) proposal_decode_kernel(AnchorSet anc, con
   keys[i] = ok ? float_to_ordered(score) : 0u;
 }
 
-// Single-CTA bitonic sort, descending by (key, index).  P = next power of two >= n, P <= 32768.
-__global__ void __launch_bounds__(1024) proposal_sort_kernel(const uint32_t* __restrict__ keys, const int* __restrict__ n_ptr,
+// ---- sort: descending by (key, index), top pre_nms_top_n only.  Two launches, all SMs busy:
+//  (1) proposal_sort_chunks_kernel: every CTA bitonic-sorts one 1024-element chunk in shared memory;
+//  (2) proposal_rank_kernel: every CTA stages ALL sorted chunks (6 B/element, <= 192 KB) in shared memory; one warp per
+//      element, one lane per chunk: three binary searches give the element's exact global rank and the bounds of its
+//      run of equal scores, and the element is scattered straight to its final slot.  (A single-CTA bitonic sort of
+//      32768 keys is shared-memory-bandwidth bound on ONE SM: 356 us measured, profiles/r01_launches_hot_v1.csv.)
+constexpr int kChunk = 1024;
+
+__device__ __forceinline__ bool comp_before(uint32_t ka, uint32_t ia, uint32_t kb, uint32_t ib) {
+  return (ka > kb) || (ka == kb && ia > ib);       // score descending, ties -> larger index first
+}
+
+__global__ void __launch_bounds__(512) proposal_sort_chunks_kernel(const uint32_t* __restrict__ keys,
+                                                                   const int* __restrict__ n_ptr,
+                                                                   uint32_t* __restrict__ skeys, uint16_t* __restrict__ sidx) {
+  __shared__ uint32_t k[kChunk];
+  __shared__ uint16_t ix[kChunk];
+  const int n = *n_ptr, base = blockIdx.x * kChunk;
+  for (int i = threadIdx.x; i < kChunk; i += 512) {
+    const int g = base + i;
+    k[i] = g < n ? keys[g] : 0u;
+    ix[i] = (uint16_t)(g < n ? g : 0xFFFF);
+  }
+  __syncthreads();
+  for (int size = 2; size <= kChunk; size <<= 1)
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      const int t = threadIdx.x;
+      const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+      const bool desc = ((lo & size) == 0);
+      const uint32_t ka = k[lo], kb = k[hi];
+      const uint16_t ia = ix[lo], ib = ix[hi];
+      if (comp_before(ka, ia, kb, ib) != desc) { k[lo] = kb; k[hi] = ka; ix[lo] = ib; ix[hi] = ia; }
+      __syncthreads();
+    }
+  for (int i = threadIdx.x; i < kChunk; i += 512) { skeys[base + i] = k[i]; sidx[base + i] = ix[i]; }
+}
+
+__global__ void __launch_bounds__(1024) proposal_rank_kernel(const uint32_t* __restrict__ skeys,
+                                                             const uint16_t* __restrict__ sidx, int num_chunks,
                                                              int pre_nms_top_n, int* __restrict__ order,
                                                              int* __restrict__ n_pre_out) {
   extern __shared__ uint8_t sm[];
-  const int n = *n_ptr;
-  int P = 1;
-  while (P < n) P <<= 1;
+  const int P = num_chunks * kChunk;
   uint32_t* k = reinterpret_cast<uint32_t*>(sm);
   uint16_t* ix = reinterpret_cast<uint16_t*>(sm + (size_t)P * 4);
-  __shared__ int s_valid;
-  if (threadIdx.x == 0) s_valid = 0;
+  __shared__ int s_n_pre;
+  for (int i = threadIdx.x; i < P / 4; i += blockDim.x) reinterpret_cast<uint4*>(k)[i] = reinterpret_cast<const uint4*>(skeys)[i];
+  for (int i = threadIdx.x; i < P / 8; i += blockDim.x) reinterpret_cast<uint4*>(ix)[i] = reinterpret_cast<const uint4*>(sidx)[i];
   __syncthreads();
-  int local_valid = 0;
-  for (int i = threadIdx.x; i < P; i += blockDim.x) {
-    uint32_t key = i < n ? keys[i] : 0u;
-    k[i] = key; ix[i] = (uint16_t)(i < n ? i : 0xFFFF);
-    local_valid += (key != 0u);
-  }
-  atomicAdd(&s_valid, local_valid);
-  __syncthreads();
-  for (int size = 2; size <= P; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
-        const int lo = 2 * t - (t & (stride - 1));   // index with bit `stride` cleared
-        const int hi = lo + stride;
-        const bool desc = ((lo & size) == 0);        // this bitonic block sorts descending
-        const uint32_t ka = k[lo], kb = k[hi];
-        const uint16_t ia = ix[lo], ib = ix[hi];
-        const bool a_before_b = (ka > kb) || (ka == kb && ia > ib);
-        if (a_before_b != desc) { k[lo] = kb; k[hi] = ka; ix[lo] = ib; ix[hi] = ia; }
-      }
-      __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool has_chunk = lane < num_chunks;
+  const uint32_t* kc = k + lane * kChunk;
+  const uint16_t* ic = ix + lane * kChunk;
+  if (warp == 0) {
+    // number of valid (key != 0) elements: zeros sit at the end of every sorted chunk
+    int a = 0, b = kChunk;
+    if (has_chunk) { while (a < b) { const int mid = (a + b) >> 1; if (kc[mid] != 0u) a = mid + 1; else b = mid; } } else a = 0;
+    for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) {
+      int np = a;
+      if (pre_nms_top_n > 0 && np > pre_nms_top_n) np = pre_nms_top_n;
+      s_n_pre = np;
+      if (blockIdx.x == 0) *n_pre_out = np;
     }
   }
-  int n_pre = s_valid;
-  if (pre_nms_top_n > 0 && n_pre > pre_nms_top_n) n_pre = pre_nms_top_n;
-  // gpu_nms re-sorts the selected boxes by score (lib/nms/gpu_nms.pyx:26, `argsort()[::-1]`): under the stable-sort
-  // tie rule that reverses every run of equal scores once more.  Mirror position i inside its run [lo, hi].
-  for (int i = threadIdx.x; i < n_pre; i += blockDim.x) {
-    const uint32_t key = k[i];
-    int a = 0, b = i;                       // first position with k == key (keys are descending)
-    while (a < b) { const int mid = (a + b) >> 1; if (k[mid] > key) a = mid + 1; else b = mid; }
-    const int lo = a;
-    a = i; b = n_pre - 1;                   // last position with k == key
-    while (a < b) { const int mid = (a + b + 1) >> 1; if (k[mid] < key) b = mid - 1; else a = mid; }
-    const int hi = a;
-    order[lo + hi - i] = (int)ix[i];
+  __syncthreads();
+  const int n_pre = s_n_pre;
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  for (int e = blockIdx.x * (blockDim.x >> 5) + warp; e < P; e += warps_total) {
+    const uint32_t ke = k[e];
+    const uint32_t ie = ix[e];
+    const int li = e & (kChunk - 1), ce = e >> 10;
+    if (ke == 0u || li >= n_pre) continue;          // warp-uniform
+    int gt_comp = 0, gt_key = 0, ge_key = 0;
+    if (has_chunk) {
+      int a = 0, b = kChunk;                         // first position not strictly before e in the composite order
+      if (lane == ce) a = li;
+      else while (a < b) { const int mid = (a + b) >> 1; if (comp_before(kc[mid], ic[mid], ke, ie)) a = mid + 1; else b = mid; }
+      gt_comp = a;
+      a = 0; b = kChunk;
+      while (a < b) { const int mid = (a + b) >> 1; if (kc[mid] > ke) a = mid + 1; else b = mid; }
+      gt_key = a;
+      b = kChunk;                                    // a == gt_key is a valid lower bound
+      while (a < b) { const int mid = (a + b) >> 1; if (kc[mid] >= ke) a = mid + 1; else b = mid; }
+      ge_key = a;
+    }
+    for (int o = 16; o; o >>= 1) {
+      gt_comp += __shfl_xor_sync(0xffffffffu, gt_comp, o);
+      gt_key += __shfl_xor_sync(0xffffffffu, gt_key, o);
+      ge_key += __shfl_xor_sync(0xffffffffu, ge_key, o);
+    }
+    if (lane == 0 && gt_comp < n_pre) {
+      // gpu_nms re-sorts the selected boxes by score (lib/nms/gpu_nms.pyx:26, `argsort()[::-1]`): under the stable-sort
+      // tie rule that reverses every run of equal scores once more -> mirror the rank inside its run [lo, hi]
+      const int lo = gt_key, hi = min(ge_key, n_pre) - 1;
+      order[lo + hi - gt_comp] = (int)ie;
+    }
   }
-  if (threadIdx.x == 0) *n_pre_out = n_pre;
 }
 
 // det = hstack(proposals, scores).astype(float32)  (proposal.py:149)
@@ -224,6 +273,74 @@ __global__ void __launch_bounds__(128) nms_sweep_kernel(const unsigned long long
   if (threadIdx.x == 0) *num_out = s_total;
 }
 
+// Greedy NMS without the n x n/64 mask (used when max_keep is small, e.g. post_nms_top_n = 300): one CTA walks the sorted
+// boxes 64 at a time; the <= max_keep kept boxes live in shared memory.  Per block: (1) 64 candidates x kept boxes IoU
+// in parallel, (2) the 64x64 upper-triangle IoU bits, (3) a 64-step serial resolve on one 64-bit word; stops as soon as
+// max_keep boxes are kept.  Same float32 IoU and '>' as lib/nms/nms_kernel.cu, so the kept set is bit-identical to the
+// mask + sweep form (which took 57 + 264 us at n = 6000: profiles/r01_launches_hot_v1.csv).
+__global__ void __launch_bounds__(256) nms_greedy_kernel(const float* __restrict__ boxes, int box_dim,
+                                                         const int* __restrict__ n_ptr, float thresh, int max_keep,
+                                                         int* __restrict__ keep_out, int* __restrict__ num_out) {
+  extern __shared__ float4 kept[];                 // [max_keep]
+  __shared__ float4 cand[64];
+  __shared__ unsigned int supp[2];                 // candidate suppressed by an earlier kept box (bit c)
+  __shared__ unsigned short m16[64][4];            // intra-block suppression bits, 16 columns per slice
+  __shared__ int s_nkept;
+  const int n = *n_ptr;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_nkept = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 64) {
+    const int cnt = min(64, n - base);
+    if (tid < 64) {
+      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (tid < cnt) { const float* p = boxes + (size_t)(base + tid) * box_dim; b = make_float4(p[0], p[1], p[2], p[3]); }
+      cand[tid] = b;
+    }
+    if (tid < 2) supp[tid] = 0u;
+    __syncthreads();
+    const int nkept = s_nkept;
+    const int c = tid & 63, part = tid >> 6;
+    {
+      const float4 cb = cand[c];
+      const float cf[4] = {cb.x, cb.y, cb.z, cb.w};
+      bool hit = false;
+      for (int kk = part; kk < nkept && !hit; kk += 4) {
+        const float4 kb = kept[kk];
+        const float kf[4] = {kb.x, kb.y, kb.z, kb.w};
+        hit = dev_iou(kf, cf) > thresh;
+      }
+      if (hit && c < cnt) atomicOr(&supp[c >> 5], 1u << (c & 31));
+      unsigned int bits = 0;
+      for (int j = part * 16; j < part * 16 + 16; ++j) {
+        if (j > c && j < cnt) {
+          const float4 jb = cand[j];
+          const float jf[4] = {jb.x, jb.y, jb.z, jb.w};
+          if (dev_iou(cf, jf) > thresh) bits |= 1u << (j - part * 16);
+        }
+      }
+      m16[c][part] = (unsigned short)bits;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long cur = (unsigned long long)supp[0] | ((unsigned long long)supp[1] << 32);
+      int nk = nkept;
+      for (int i = 0; i < cnt && nk < max_keep; ++i) {
+        if (!((cur >> i) & 1ULL)) {
+          kept[nk] = cand[i];
+          keep_out[nk++] = base + i;
+          cur |= (unsigned long long)m16[i][0] | ((unsigned long long)m16[i][1] << 16) |
+                 ((unsigned long long)m16[i][2] << 32) | ((unsigned long long)m16[i][3] << 48);
+        }
+      }
+      s_nkept = nk;
+    }
+    __syncthreads();
+    if (s_nkept >= max_keep) break;
+  }
+  if (tid == 0) *num_out = s_nkept;
+}
+
 // proposal.py:151-168: take post_nms, pad, emit [0, x1, y1, x2, y2] float32 (+ scores)
 __global__ void proposal_emit_kernel(const float* __restrict__ det, const int* __restrict__ keep,
                                      const int* __restrict__ num_kept_ptr, int post, float* __restrict__ rois,
@@ -304,7 +421,7 @@ __global__ void proposal_target_kernel(rn_proposal_target_desc d, const float* _
 __global__ void set_int_kernel(int* p, int v) { *p = v; }
 
 struct ProposalWs {
-  double* props; uint32_t* keys; int* order; float* det; unsigned long long* mask; int* keep; int* counters;
+  double* props; uint32_t* keys; uint32_t* skeys; uint16_t* sidx; int* order; float* det; unsigned long long* mask; int* keep; int* counters;
   int n_max, pre, col_blocks;
 };
 
@@ -313,13 +430,17 @@ static size_t carve(const rn_proposal_desc* d, void* base, size_t bytes, Proposa
   const int n_max = d->Hf * d->Wf * A;
   const int pre = d->pre_nms_top_n > 0 ? (d->pre_nms_top_n < n_max ? d->pre_nms_top_n : n_max) : n_max;
   const int cb = (pre + 63) / 64;
-  size_t need = ws_slice((size_t)n_max * 4, 8) + ws_slice(n_max, 4) + ws_slice(pre, 4) + ws_slice((size_t)pre * 5, 4) +
+  const int P = cdiv(n_max, kChunk) * kChunk;
+  size_t need = ws_slice((size_t)n_max * 4, 8) + ws_slice(n_max, 4) + ws_slice(P, 4) + ws_slice(P, 2) + ws_slice(pre, 4) +
+                ws_slice((size_t)pre * 5, 4) +
                 ws_slice((size_t)pre * cb, 8) + ws_slice(d->post_nms_top_n > 0 ? d->post_nms_top_n : pre, 4) + ws_slice(8, 4);
   if (!w) return need;
   Workspace ws(base, bytes);
   w->n_max = n_max; w->pre = pre; w->col_blocks = cb;
   w->props = ws.take<double>((size_t)n_max * 4);
   w->keys = ws.take<uint32_t>(n_max);
+  w->skeys = ws.take<uint32_t>(P);
+  w->sidx = ws.take<uint16_t>(P);
   w->order = ws.take<int>(pre);
   w->det = ws.take<float>((size_t)pre * 5);
   w->mask = ws.take<unsigned long long>((size_t)pre * cb);
@@ -330,6 +451,17 @@ static size_t carve(const rn_proposal_desc* d, void* base, size_t bytes, Proposa
 
 static int launch_nms(cudaStream_t st, const float* boxes, int box_dim, const int* n_ptr, int n_max, float thresh,
                       int max_keep, unsigned long long* mask, int* keep, int* num_out) {
+  if (max_keep <= 8192) {
+    const size_t smem = (size_t)max_keep * sizeof(float4);
+    static thread_local size_t configured = 48 * 1024;
+    if (smem > configured) {
+      RN_CUDA(cudaFuncSetAttribute(nms_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+    nms_greedy_kernel<<<1, 256, smem, st>>>(boxes, box_dim, n_ptr, thresh, max_keep, keep, num_out);
+    RN_LAUNCH_CHECK();
+    return RN_OK;
+  }
   const int cb = (n_max + 63) / 64;
   nms_mask_kernel<<<dim3(cb, cb), 64, 0, st>>>(boxes, box_dim, n_ptr, cb, thresh, mask);
   RN_LAUNCH_CHECK();
@@ -365,15 +497,21 @@ extern "C" int rn_proposal_fwd(const rn_proposal_desc* d, const float* scales_ho
   proposal_decode_kernel<<<cdiv(n_max, 256), 256, 0, st>>>(anc, cls_prob, bbox_pred, im_info, d->Hf, d->Wf,
                                                            d->feat_stride, d->min_size, w.props, w.keys, n_total);
   RN_LAUNCH_CHECK();
-  int P = 1; while (P < n_max) P <<= 1;
-  const size_t sort_smem = (size_t)P * 6;
+  const int num_chunks = cdiv(n_max, kChunk);
+  const size_t rank_smem = (size_t)num_chunks * kChunk * 6;
   static thread_local size_t configured = 0;
-  if (sort_smem > configured) {
-    RN_CUDA(cudaFuncSetAttribute(proposal_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
-    configured = sort_smem;
+  if (rank_smem > configured) {
+    RN_CUDA(cudaFuncSetAttribute(proposal_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rank_smem));
+    configured = rank_smem;
   }
-  proposal_sort_kernel<<<1, 1024, sort_smem, st>>>(w.keys, n_total, d->pre_nms_top_n, w.order, n_pre);
+  proposal_sort_chunks_kernel<<<num_chunks, 512, 0, st>>>(w.keys, n_total, w.skeys, w.sidx);
   RN_LAUNCH_CHECK();
+  {
+    const int sms = sm_count() > 0 ? sm_count() : 148;
+    const int g = std::min(sms, cdiv(num_chunks * kChunk, 256));
+    proposal_rank_kernel<<<g, 1024, rank_smem, st>>>(w.skeys, w.sidx, num_chunks, d->pre_nms_top_n, w.order, n_pre);
+    RN_LAUNCH_CHECK();
+  }
   proposal_gather_kernel<<<cdiv(w.pre, 256), 256, 0, st>>>(w.props, cls_prob, w.order, n_pre, A, d->Hf, d->Wf, im_info,
                                                            d->feat_stride, w.det);
   RN_LAUNCH_CHECK();

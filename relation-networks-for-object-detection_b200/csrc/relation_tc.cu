@@ -25,6 +25,7 @@ namespace rn {
 using namespace umma;
 
 constexpr int kKV = 3;                       // K/V' ring stages
+constexpr int kMaxTileSplits = 4;            // <= this many key tiles: one CTA per tile + combine
 constexpr int kQ = 16384, kKt = 16384, kVt = 16384, kPt = 32768;
 constexpr int kAttnBar = kQ + kKV * (kKt + kVt) + 2 * kPt;      // 180224
 constexpr int kAttnSmem = kAttnBar + 256 + 1024;
@@ -267,6 +268,194 @@ __global__ void __launch_bounds__(192, 1) relation_attn_tc_kernel(const __grid_c
   if (warp == 4) tmem_dealloc<512>(tmem_base);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Single-key-tile variant (M <= 512: the N = 300 detection head and the n = 100 learn-NMS batch).  One CTA per
+// (128-query tile, head, problem, 128-key tile): 80 KB of shared memory and 256 TMEM columns, so two CTAs share an SM,
+// and at N = M = 300 the grid is 3 x 16 x 3 = 144 CTAs = one wave of the 148 SMs instead of 48 CTAs streaming 3 tiles
+// each.  Each thread pulls its whole 128-float geometry row into registers BEFORE the S tile lands (one L2 latency
+// instead of eight dependent ones) and makes a single pass over TMEM.  With more than one key tile the CTAs write
+// un-normalised partials (O, m, l) and relation_attn_combine_kernel merges them (flash-decoding style).
+constexpr int kTileBar = 16384 * 3 + 32768;            // Q, K, V', P
+constexpr int kTileSmem = kTileBar + 128 + 1024;
+
+struct TileParams {
+  AttnParams a;
+  int splits;                    // key tiles per query tile (gridDim.x = qtiles * splits)
+  float* part_o;                 // [splits][B][H][N][64] un-normalised partial outputs
+  float* part_ml;                // [splits][B][H][N][2]  (row max in log2 units, row sum)
+};
+
+__global__ void __launch_bounds__(160, 2) relation_attn_tile_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                    const __grid_constant__ CUtensorMap tmK,
+                                                                    const __grid_constant__ CUtensorMap tmV, TileParams tp) {
+  extern __shared__ uint8_t smem_raw[];
+  const AttnParams& p = tp.a;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  uint8_t* sQ = smem; uint8_t* sK = smem + 16384; uint8_t* sV = smem + 32768; uint8_t* sP = smem + 49152;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTileBar);
+  uint64_t* ld_full = bars; uint64_t* s_full = bars + 1; uint64_t* p_full = bars + 2; uint64_t* pv_full = bars + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x / tp.splits, kt = blockIdx.x % tp.splits;
+  const int q0 = qt * 128, m0 = kt * 128, h = blockIdx.y, b = blockIdx.z;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
+      mbar_init(ld_full, 1); mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(pv_full, 1);
+      fence_barrier_init();
+      mbar_arrive_expect_tx(ld_full, 3 * 16384);
+      tma_load_3d(sQ, &tmQ, ld_full, h * 64, q0, b);
+      tma_load_3d(sK, &tmK, ld_full, h * 64, m0, b);
+      tma_load_3d(sV, &tmV, ld_full, h * 64, m0, b);
+    }
+    __syncwarp();
+    tmem_alloc<256>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tPV = tmem_base + 128;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_wait(ld_full, 0);
+      tc_fence_after();
+      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aP = smem_u32(sP), aV = smem_u32(sV);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        mma_f16_ss(tS, make_smem_desc_sw128(aQ + k * 32, 16, 1024), make_smem_desc_sw128(aK + k * 32, 16, 1024),
+                   make_idesc_f16(128, 128, false, false, false), k > 0);
+      mma_commit(s_full);
+      mbar_wait(p_full, 0);
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        mma_f16_ss(tPV, make_smem_desc_sw128(aP + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                   make_smem_desc_sw128(aV + k * 2048, 1024, 1024), make_idesc_f16(128, 64, false, false, true), k > 0);
+      mma_commit(pv_full);
+    }
+  } else {
+    const int r = warp * 32 + lane, n = q0 + r;
+    const bool row_ok = n < p.N;
+    const uint32_t lane_base = ((uint32_t)(warp * 32) << 16);
+    const float* lg_row = p.lg + (((size_t)b * p.H + h) * p.N + (row_ok ? n : 0)) * p.ldg + m0;
+    // the whole geometry row of this tile, issued before the S tile is ready
+    float t[128];
+#pragma unroll
+    for (int q = 0; q < 128; q += 4) {
+      float4 t4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      if (m0 + q < p.M) t4 = __ldg(reinterpret_cast<const float4*>(lg_row + q));      // ldg >= M rounded up to 4
+      t[q] = t4.x; t[q + 1] = t4.y; t[q + 2] = t4.z; t[q + 3] = t4.w;
+    }
+    mbar_wait(s_full, 0);
+    tc_fence_after();
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tS + c * 32 + lane_base, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        const float tt = (m0 + c * 32 + q < p.M) ? fmaf(__uint_as_float(v[q]), p.scale_log2, t[c * 32 + q]) : -INFINITY;
+        t[c * 32 + q] = tt;
+        mx = fmaxf(mx, tt);
+      }
+    }
+    float lsum = 0.f;
+#pragma unroll
+    for (int kc = 0; kc < 16; ++kc) {                          // 16-byte chunks of 8 keys
+      uint32_t pk[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float p0 = exp2f(t[kc * 8 + 2 * i] - mx), p1 = exp2f(t[kc * 8 + 2 * i + 1] - mx);   // exp2(-inf) = 0
+        lsum += p0 + p1;
+        __half2 hh = __floats2half2_rn(p0, p1);
+        pk[i] = *reinterpret_cast<uint32_t*>(&hh);
+      }
+      *reinterpret_cast<uint4*>(sP + (kc >> 3) * 16384 + sw128_offset(r, kc & 7)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    mbar_arrive(p_full);
+    mbar_wait(pv_full, 0);
+    tc_fence_after();
+    float o[64];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tPV + c * 32 + lane_base, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 32; ++q) o[c * 32 + q] = __uint_as_float(v[q]);
+    }
+    if (row_ok) {
+      if (tp.splits > 1) {
+        const size_t row = (((size_t)kt * gridDim.z + b) * p.H + h) * p.N + n;
+        float4* dst = reinterpret_cast<float4*>(tp.part_o + row * 64);
+#pragma unroll
+        for (int q = 0; q < 64; q += 4) dst[q >> 2] = make_float4(o[q], o[q + 1], o[q + 2], o[q + 3]);
+        reinterpret_cast<float2*>(tp.part_ml)[row] = make_float2(mx, lsum);
+      } else {
+        const float inv = 1.f / lsum;
+        float* dst = p.out + ((size_t)b * p.N + n) * p.ldo + (size_t)h * p.dv;
+        const float* res = p.X ? p.X + ((size_t)b * p.N + n) * p.ldx + (size_t)h * p.dv : nullptr;
+#pragma unroll
+        for (int q = 0; q < 64; ++q)
+          if (q < p.dv) {
+            float y = o[q] * inv;
+            if (res) y += res[q];
+            if (p.relu) y = fmaxf(y, 0.f);
+            dst[q] = y;
+          }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc<256>(tmem_base);
+}
+
+// merge the per-key-tile partials: one thread per (b, n, h, 4 output columns)
+__global__ void __launch_bounds__(256) relation_attn_combine_kernel(TileParams tp, int B) {
+  const AttnParams& p = tp.a;
+  const size_t total = (size_t)B * p.N * p.H * 16;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c4 = i & 15, h = (i >> 4) % p.H;
+    const int n = (i / (16 * p.H)) % p.N, b = i / ((size_t)16 * p.H * p.N);
+    float mx = -INFINITY;
+    for (int s = 0; s < tp.splits; ++s)
+      mx = fmaxf(mx, tp.part_ml[((((size_t)s * B + b) * p.H + h) * p.N + n) * 2]);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float l = 0.f;
+    for (int s = 0; s < tp.splits; ++s) {
+      const size_t row = (((size_t)s * B + b) * p.H + h) * p.N + n;
+      const float2 ml = reinterpret_cast<const float2*>(tp.part_ml)[row];
+      const float w = exp2f(ml.x - mx);
+      const float4 o = reinterpret_cast<const float4*>(tp.part_o + row * 64)[c4];
+      acc.x = fmaf(w, o.x, acc.x); acc.y = fmaf(w, o.y, acc.y); acc.z = fmaf(w, o.z, acc.z); acc.w = fmaf(w, o.w, acc.w);
+      l = fmaf(w, ml.y, l);
+    }
+    const float inv = 1.f / l;
+    float y[4] = {acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv};
+    float* dst = p.out + ((size_t)b * p.N + n) * p.ldo + (size_t)h * p.dv;
+    const float* res = p.X ? p.X + ((size_t)b * p.N + n) * p.ldx + (size_t)h * p.dv : nullptr;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int q = c4 * 4 + j;
+      if (q < p.dv) {
+        float v = y[j];
+        if (res) v += res[q];
+        if (p.relu) v = fmaxf(v, 0.f);
+        dst[q] = v;
+      }
+    }
+  }
+}
+
 // [Wq; Wk; Wout'] -> fp16 [3*H*64, d8] and bias [3*H*64] (Wout' / bout padded from dv to 64 columns per head)
 __global__ void pack_relation_weights_kernel(const float* __restrict__ Wq, const float* __restrict__ bq,
                                              const float* __restrict__ Wk, const float* __restrict__ bk,
@@ -305,6 +494,8 @@ size_t relation_tc_workspace_bytes(const rn_relation_desc* d) {
   t += ws_slice(B * M * 2 * H * 64, 2);  // KV' of gathered keys
   t += ws_slice(B * H * N * ldg, 4);     // log2 geometry weight
   t += gemm_tc_workspace_bytes((int)(B * N), (int)W3, (int)d8) + 512;
+  const size_t T = (M + 127) / 128;
+  if (T > 1 && T <= kMaxTileSplits) t += ws_slice(T * B * H * N * 64, 4) + ws_slice(T * B * H * N * 2, 4);
   return t;
 }
 
@@ -358,7 +549,13 @@ int relation_tc_packed(const rn_relation_desc* d, const float* X, const float* b
   __half* qkv = ws.take<__half>((size_t)B * N * W3);
   __half* kv = ws.take<__half>((size_t)B * M * 2 * H * 64);
   float* lg = ws.take<float>((size_t)B * H * N * ldg);
-  if (!lg) { set_error("rn_relation_fwd(F16): workspace too small (%zu < %zu)", ws_bytes, relation_tc_workspace_bytes(d)); return RN_ERR_WORKSPACE; }
+  const int T = cdiv(M, 128);
+  float *part_o = nullptr, *part_ml = nullptr;
+  if (T > 1 && T <= kMaxTileSplits) {
+    part_o = ws.take<float>((size_t)T * B * H * N * 64);
+    part_ml = ws.take<float>((size_t)T * B * H * N * 2);
+  }
+  if (!lg || (T > 1 && T <= kMaxTileSplits && !part_ml)) { set_error("rn_relation_fwd(F16): workspace too small (%zu < %zu)", ws_bytes, relation_tc_workspace_bytes(d)); return RN_ERR_WORKSPACE; }
   void* gws = ws.base + ws.off; const size_t gws_bytes = ws.size - ws.off;
   int r;
   if (do_proj && (r = cast_rows_f16(st, X, x16, B * N, D, d8))) return r;
@@ -385,7 +582,7 @@ int relation_tc_packed(const rn_relation_desc* d, const float* X, const float* b
   if ((r = encode_tmap_3d_f16(&tmK, Kp, B, M, H * 64, ldk, bk_pitch, 128, 64))) return r;
   if ((r = encode_tmap_3d_f16(&tmV, Vp, B, M, H * 64, ldk, bk_pitch, 128, 64))) return r;
   AttnParams p;
-  p.N = N; p.M = M; p.H = H; p.T = cdiv(M, 128);
+  p.N = N; p.M = M; p.H = H; p.T = T;
   p.lg = lg; p.ldg = ldg;
   p.X = d->fuse_residual_relu ? X : nullptr; p.ldx = D;
   p.out = out; p.ldo = d->dout; p.dv = dv; p.relu = d->fuse_residual_relu;
@@ -393,7 +590,22 @@ int relation_tc_packed(const rn_relation_desc* d, const float* X, const float* b
   static thread_local bool configured = false;
   if (!configured) {
     RN_CUDA(cudaFuncSetAttribute(relation_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    RN_CUDA(cudaFuncSetAttribute(relation_attn_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem));
     configured = true;
+  }
+  if (T <= kMaxTileSplits) {
+    TileParams tp;
+    tp.a = p; tp.splits = T; tp.part_o = part_o; tp.part_ml = part_ml;
+    relation_attn_tile_kernel<<<dim3(cdiv(N, 128) * T, H, B), 160, kTileSmem, st>>>(tmQ, tmK, tmV, tp);
+    RN_LAUNCH_CHECK();
+    if (T > 1) {
+      const size_t total = (size_t)B * N * H * 16;
+      size_t blocks = (total + 255) / 256;
+      const size_t cap = (size_t)sm_count() * 8;
+      relation_attn_combine_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(tp, B);
+      RN_LAUNCH_CHECK();
+    }
+    return RN_OK;
   }
   relation_attn_tc_kernel<<<dim3(cdiv(N, 128), H, B), 192, kAttnSmem, st>>>(tmQ, tmK, tmV, p);
   RN_LAUNCH_CHECK();

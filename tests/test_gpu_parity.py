@@ -246,6 +246,11 @@ def test_nms_matches_oracle_and_reference_kernel(ops):
     same = np.tile(dets[:1], (130, 1))
     keep4, num4 = ops.nms(T(same), 0.7)
     assert int(num4.item()) == 1 and int(keep4[0].item()) == 0
+    # n > 8192 with max_keep = n takes the bitmask + sweep form (lib/nms/nms_kernel.cu layout) instead of the greedy CTA
+    big = np.vstack([dets, dets + np.float32(0.25), dets + np.float32(500.0)])[:9000]
+    big = big[np.argsort(-big[:, 4], kind='stable')].astype(np.float32)
+    keep5, num5 = ops.nms(T(big), 0.7)
+    np.testing.assert_array_equal(keep5.cpu().numpy()[:int(num5.item())], RO.nms_sorted(big, 0.7))
 
 
 def test_bbox_overlaps_and_proposal_target(ops):
