@@ -312,7 +312,7 @@ def main():
             'hot_path': {'ms_per_image': round(ms_hot / args.steps, 4), 'images_per_sec': round(args.steps / (ms_hot / 1e3), 2),
                          'trunk_ms_per_image': round(ms_trunk / args.steps, 4),
                          'relation_module_us': {k: round(v, 2) for k, v in rel_times.items()},
-                         'proposals_kept_before_pad': None},
+                         'proposals_kept_before_pad': int(ops.proposal(trunk_out[0], trunk_out[1], im_info, return_num_kept=True, **head.cfg)[2].item())},
             'clocks': sampler.summary() if sampler else None,
             'roofline': roof,
         }

@@ -6,6 +6,7 @@
 // the g write (4*B*H*N*M) + boxes.
 #include "common.cuh"
 #include "geom.cuh"
+#include <algorithm>
 
 namespace rn {
 
@@ -93,14 +94,17 @@ __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-// grid (ceil(M / (16*TILES*4)), N, B), 128 threads: warp w handles TILES consecutive 16-key tiles of query n
-template <int NHALF>     // number of 8-head halves (1: H <= 8, 2: H <= 16)
+// persistent: grid ~ 8 CTAs/SM x 4 warps; work item = (problem b, query n, 16-key tile), consecutive warps take
+// consecutive key tiles of the same query so their stores land next to each other.
+// EXACT = true keeps the reference's IEEE divisions (|dcx|/w, w_n/w_m, a/dim: the fp32 parity mode); EXACT = false
+// multiplies by IEEE reciprocals instead (<= 1 ulp on eps and on the sin/cos argument; changes the module output by
+// ~2e-6 relative, measured on the oracle) and is what the tcgen05 path uses.
+template <int NHALF, bool EXACT>     // NHALF: number of 8-head halves (1: H <= 8, 2: H <= 16)
 __global__ void __launch_bounds__(128) geom_weight_mma_kernel(const float* __restrict__ boxes,
-                                                              const int* __restrict__ key_index, int N, int M, int H,
-                                                              GeomFreq fr, const float* __restrict__ Wg,
+                                                              const int* __restrict__ key_index, int B, int N, int M,
+                                                              int H, GeomFreq fr, const float* __restrict__ Wg,
                                                               const float* __restrict__ bg, float* __restrict__ out,
-                                                              int ldg, int log2_out, int tiles_per_warp) {
-  const int b = blockIdx.z, n = blockIdx.y;
+                                                              int ldg, int log2_out) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, q = lane & 3;
   // B fragments of Wg^T: element (k, col) = Wg[nh*8 + col][c*16 + k]; this lane holds col = g, k = 2q,2q+1 | 2q+8,2q+9
@@ -123,11 +127,14 @@ __global__ void __launch_bounds__(128) geom_weight_mma_kernel(const float* __res
     bias[nh][1] = h + 1 < H ? bg[h + 1] : 0.f;
   }
   const float d0 = fr.dim[2 * q], d1 = fr.dim[2 * q + 1];
-  const float4 bn = reinterpret_cast<const float4*>(boxes)[(size_t)b * N + n];
-  const int m_warp = (blockIdx.x * 4 + warp) * tiles_per_warp * 16;
-  for (int t = 0; t < tiles_per_warp; ++t) {
-    const int m0 = m_warp + t * 16;
-    if (m0 >= M) break;                                        // warp-uniform
+  const float r0 = __frcp_rn(d0), r1 = __frcp_rn(d1);
+  const int tiles_m = (M + 15) >> 4;
+  const long long total = (long long)B * N * tiles_m;
+  for (long long item = (long long)blockIdx.x * 4 + warp; item < total; item += (long long)gridDim.x * 4) {
+    const int tm = (int)(item % tiles_m);
+    const int n = (int)((item / tiles_m) % N), b = (int)(item / ((long long)tiles_m * N));
+    const int m0 = tm * 16;
+    const float4 bn = reinterpret_cast<const float4*>(boxes)[(size_t)b * N + n];
     float acc[NHALF][4];
 #pragma unroll
     for (int nh = 0; nh < NHALF; ++nh) { acc[nh][0] = acc[nh][1] = acc[nh][2] = acc[nh][3] = 0.f; }
@@ -136,7 +143,18 @@ __global__ void __launch_bounds__(128) geom_weight_mma_kernel(const float* __res
     for (int rr = 0; rr < 2; ++rr) {
       const int m = min(m0 + g + 8 * rr, M - 1);
       const int mi = key_index ? key_index[m] : m;
-      pair_eps(bn, reinterpret_cast<const float4*>(boxes)[(size_t)b * N + mi], eps[rr]);
+      const float4 bm = reinterpret_cast<const float4*>(boxes)[(size_t)b * N + mi];
+      if (EXACT) {
+        pair_eps(bn, bm, eps[rr]);
+      } else {
+        const float wn = bn.z - bn.x + 1.f, hn = bn.w - bn.y + 1.f;
+        const float wm = bm.z - bm.x + 1.f, hm = bm.w - bm.y + 1.f;
+        const float dcx = 0.5f * (bn.x + bn.z) - 0.5f * (bm.x + bm.z), dcy = 0.5f * (bn.y + bn.w) - 0.5f * (bm.y + bm.w);
+        eps[rr][0] = __logf(fmaxf(fabsf(dcx * __frcp_rn(wn)), 1e-3f));
+        eps[rr][1] = __logf(fmaxf(fabsf(dcy * __frcp_rn(hn)), 1e-3f));
+        eps[rr][2] = __logf(wn * __frcp_rn(wm));
+        eps[rr][3] = __logf(hn * __frcp_rn(hm));
+      }
     }
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -144,8 +162,8 @@ __global__ void __launch_bounds__(128) geom_weight_mma_kernel(const float* __res
 #pragma unroll
       for (int rr = 0; rr < 2; ++rr) {
         const float a = 100.0f * eps[rr][c];
-        sincos_2pi(__fdiv_rn(a, d0), &sn[rr][0], &cs[rr][0]);
-        sincos_2pi(__fdiv_rn(a, d1), &sn[rr][1], &cs[rr][1]);
+        sincos_2pi(EXACT ? __fdiv_rn(a, d0) : a * r0, &sn[rr][0], &cs[rr][0]);
+        sincos_2pi(EXACT ? __fdiv_rn(a, d1) : a * r1, &sn[rr][1], &cs[rr][1]);
       }
       uint32_t ah[4], al[4];
       split_h2(sn[0][0], sn[0][1], &ah[0], &al[0]);            // a0: row g,   cols 2q,2q+1   (sin)
@@ -230,13 +248,17 @@ static int launch_geom_weight_impl(cudaStream_t st, const float* boxes, const in
   RN_CHECK_ARG(H >= 1 && H <= 16, "geometry heads H=%d unsupported (1..16)", H);
   if (E == 64) {
     // tensor-core FC path: 16 pairs per warp-tile; pick tiles/warp so that one CTA (4 warps) covers <= M keys of a row
-    const int tiles = cdiv(M, 16);
-    const int tpw = tiles >= 16 ? 2 : 1;
-    dim3 grid(cdiv(tiles, 4 * tpw), N, B);
-    if (H <= 8)
-      geom_weight_mma_kernel<1><<<grid, 128, 0, st>>>(boxes, key_index, N, M, H, fr, Wg, bg, g, ldg, log2_out, tpw);
-    else
-      geom_weight_mma_kernel<2><<<grid, 128, 0, st>>>(boxes, key_index, N, M, H, fr, Wg, bg, g, ldg, log2_out, tpw);
+    const long long items = (long long)B * N * cdiv(M, 16);
+    const int sms = sm_count() > 0 ? sm_count() : 148;
+    const int grid = (int)std::min<long long>((items + 3) / 4, (long long)sms * 8);
+    const bool exact = !log2_out;               // fp32 parity mode asks for g, the tcgen05 path for log2 g
+    if (H <= 8) {
+      if (exact) geom_weight_mma_kernel<1, true><<<grid, 128, 0, st>>>(boxes, key_index, B, N, M, H, fr, Wg, bg, g, ldg, log2_out);
+      else geom_weight_mma_kernel<1, false><<<grid, 128, 0, st>>>(boxes, key_index, B, N, M, H, fr, Wg, bg, g, ldg, log2_out);
+    } else {
+      if (exact) geom_weight_mma_kernel<2, true><<<grid, 128, 0, st>>>(boxes, key_index, B, N, M, H, fr, Wg, bg, g, ldg, log2_out);
+      else geom_weight_mma_kernel<2, false><<<grid, 128, 0, st>>>(boxes, key_index, B, N, M, H, fr, Wg, bg, g, ldg, log2_out);
+    }
     RN_LAUNCH_CHECK();
     return RN_OK;
   }

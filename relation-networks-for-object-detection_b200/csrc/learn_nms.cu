@@ -17,27 +17,37 @@ namespace rn {
 constexpr int kNmsFeat = 128;    // nms_attention_feat_dim (LNMS:223)
 constexpr int kRankDim = 1024;   // rank embedding dim (LNMS:328)
 
-__global__ void lnms_prep_kernel(rn_learn_nms_desc d, int Rn, const int* __restrict__ sel,
-                                 const float* __restrict__ cls_score, const float* __restrict__ bbox_pred,
-                                 const float* __restrict__ rois, const float* __restrict__ im_info,
-                                 float* __restrict__ prob, float* __restrict__ refined) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per roi: the class softmax is evaluated in float32 with MXNet's order (max, then a sequential sum of
+// exp(x - max)); lanes compute the exps in parallel, lane 0 adds them in class order so the sum matches bit for bit
+__global__ void __launch_bounds__(128) lnms_prep_kernel(rn_learn_nms_desc d, int Rn, const int* __restrict__ sel,
+                                                        const float* __restrict__ cls_score,
+                                                        const float* __restrict__ bbox_pred, const float* __restrict__ rois,
+                                                        const float* __restrict__ im_info, float* __restrict__ prob,
+                                                        float* __restrict__ refined) {
+  extern __shared__ float ex[];                          // [4 warps][num_classes]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 4 + warp;
   if (r >= Rn) return;
   const int src = sel ? sel[r] : r;
   const int NC = d.num_classes, C = NC - 1;
   const float* s = cls_score + (size_t)src * NC;
-  float mx = s[0];
-  for (int c = 1; c < NC; ++c) mx = fmaxf(mx, s[c]);
+  float* e = ex + warp * NC;
+  float mx = -INFINITY;
+  for (int c = lane; c < NC; c += 32) mx = fmaxf(mx, s[c]);
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  for (int c = lane; c < NC; c += 32) e[c] = expf(s[c] - mx);
+  __syncwarp();
   float sum = 0.f;
-  for (int c = 0; c < NC; ++c) sum += expf(s[c] - mx);
-  for (int c = 1; c < NC; ++c) prob[(size_t)r * C + (c - 1)] = expf(s[c] - mx) / sum;
+  if (lane == 0) for (int c = 0; c < NC; ++c) sum += e[c];
+  sum = __shfl_sync(0xffffffffu, sum, 0);
+  for (int c = 1 + lane; c < NC; c += 32) prob[(size_t)r * C + (c - 1)] = e[c] / sum;
   // refine_bbox_nd, LNMS:175-217
   const float* b = rois + (size_t)src * 5 + 1;
   const float w = b[2] - b[0] + 1.f, h = b[3] - b[1] + 1.f;
   const float cx = 0.5f * (b[0] + b[2]), cy = 0.5f * (b[1] + b[3]);
   const int K = d.num_reg_classes - 1;
   const float lim_w = im_info[1] - 1.f, lim_h = im_info[0] - 1.f;
-  for (int k = 0; k < K; ++k) {
+  for (int k = lane; k < K; k += 32) {
     const float* dl = bbox_pred + (size_t)src * 4 * d.num_reg_classes + 4 + 4 * k;
     float dx = dl[0], dy = dl[1], dw = dl[2], dh = dl[3];
     if (d.has_means_stds) {
@@ -230,7 +240,7 @@ extern "C" int rn_learn_nms_fwd(const rn_learn_nms_desc* d, const float* cls_sco
   if (!carve(d, Rn, wsp, ws_bytes, &W)) { set_error("rn_learn_nms_fwd: workspace too small (%zu < %zu)", ws_bytes, rn_learn_nms_workspace_bytes(d)); return RN_ERR_WORKSPACE; }
   const int* sel = d->nongt_dim > 0 ? nullptr : non_gt_index;
   int r;
-  lnms_prep_kernel<<<cdiv(Rn, 128), 128, 0, st>>>(*d, Rn, sel, cls_score, bbox_pred, rois, im_info, W.prob, W.refined);
+  lnms_prep_kernel<<<cdiv(Rn, 4), 128, (size_t)4 * d->num_classes * sizeof(float), st>>>(*d, Rn, sel, cls_score, bbox_pred, rois, im_info, W.prob, W.refined);
   RN_LAUNCH_CHECK();
   int P = 1; while (P < Rn) P <<= 1;
   static thread_local bool sort_cfg = false;

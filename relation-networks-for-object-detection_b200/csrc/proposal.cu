@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(256) proposal_decode_kernel(AnchorSet anc, con
 //      run of equal scores, and the element is scattered straight to its final slot.  (A single-CTA bitonic sort of
 //      32768 keys is shared-memory-bandwidth bound on ONE SM: 356 us measured, profiles/r01_launches_hot_v1.csv.)
 constexpr int kChunk = 1024;
+constexpr int kKS = 1025, kIS = 1026;      // padded shared-memory strides of a chunk (keys / indices)
 
 __device__ __forceinline__ bool comp_before(uint32_t ka, uint32_t ia, uint32_t kb, uint32_t ib) {
   return (ka > kb) || (ka == kb && ia > ib);       // score descending, ties -> larger index first
@@ -119,16 +120,21 @@ __global__ void __launch_bounds__(1024) proposal_rank_kernel(const uint32_t* __r
                                                              int* __restrict__ n_pre_out) {
   extern __shared__ uint8_t sm[];
   const int P = num_chunks * kChunk;
+  // chunk c lives at c*kKS keys / c*kIS indices: the odd strides put equal offsets of different chunks in different
+  // banks (lane c probes chunk c at the same `mid` in the lock-step binary searches below)
   uint32_t* k = reinterpret_cast<uint32_t*>(sm);
-  uint16_t* ix = reinterpret_cast<uint16_t*>(sm + (size_t)P * 4);
+  uint16_t* ix = reinterpret_cast<uint16_t*>(sm + (size_t)num_chunks * kKS * 4);
   __shared__ int s_n_pre;
-  for (int i = threadIdx.x; i < P / 4; i += blockDim.x) reinterpret_cast<uint4*>(k)[i] = reinterpret_cast<const uint4*>(skeys)[i];
-  for (int i = threadIdx.x; i < P / 8; i += blockDim.x) reinterpret_cast<uint4*>(ix)[i] = reinterpret_cast<const uint4*>(sidx)[i];
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    const int c = i >> 10, o = i & (kChunk - 1);
+    k[c * kKS + o] = skeys[i];
+    ix[c * kIS + o] = sidx[i];
+  }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool has_chunk = lane < num_chunks;
-  const uint32_t* kc = k + lane * kChunk;
-  const uint16_t* ic = ix + lane * kChunk;
+  const uint32_t* kc = k + lane * kKS;
+  const uint16_t* ic = ix + lane * kIS;
   if (warp == 0) {
     // number of valid (key != 0) elements: zeros sit at the end of every sorted chunk
     int a = 0, b = kChunk;
@@ -145,9 +151,9 @@ __global__ void __launch_bounds__(1024) proposal_rank_kernel(const uint32_t* __r
   const int n_pre = s_n_pre;
   const int warps_total = gridDim.x * (blockDim.x >> 5);
   for (int e = blockIdx.x * (blockDim.x >> 5) + warp; e < P; e += warps_total) {
-    const uint32_t ke = k[e];
-    const uint32_t ie = ix[e];
     const int li = e & (kChunk - 1), ce = e >> 10;
+    const uint32_t ke = k[ce * kKS + li];
+    const uint32_t ie = ix[ce * kIS + li];
     if (ke == 0u || li >= n_pre) continue;          // warp-uniform
     int gt_comp = 0, gt_key = 0, ge_key = 0;
     if (has_chunk) {
@@ -203,13 +209,19 @@ __device__ __forceinline__ float dev_iou(const float* a, const float* b) {
   return interS / (Sa + Sb - interS);
 }
 
-// 64x64 tile of the suppression matrix (nms_kernel.cu:34-78); only tiles on/above the diagonal are needed by the sweep
+// 64x64 tile of the suppression matrix (nms_kernel.cu:34-78); only tiles on/above the diagonal are needed by the
+// sweep, so the grid enumerates the upper triangle linearly (row-major over row blocks).
 __global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ boxes, int box_dim,
                                                       const int* __restrict__ n_ptr, int col_blocks_ld, float thresh,
                                                       unsigned long long* __restrict__ mask) {
   const int n = *n_ptr;
-  const int row_start = blockIdx.y, col_start = blockIdx.x;
-  if (row_start > col_start) return;
+  const int cb = col_blocks_ld;
+  // t = row*cb - row*(row-1)/2 + (col - row)  ->  row = floor(((2cb+1) - sqrt((2cb+1)^2 - 8t)) / 2)
+  const int t = blockIdx.x;
+  int row_start = (int)(((2.0f * cb + 1.0f) - sqrtf((2.0f * cb + 1.0f) * (2.0f * cb + 1.0f) - 8.0f * (float)t)) * 0.5f);
+  while (row_start > 0 && row_start * cb - row_start * (row_start - 1) / 2 > t) --row_start;
+  while ((row_start + 1) * cb - (row_start + 1) * row_start / 2 <= t) ++row_start;
+  const int col_start = row_start + (t - (row_start * cb - row_start * (row_start - 1) / 2));
   if (row_start * 64 >= n || col_start * 64 >= n) return;
   const int row_size = min(n - row_start * 64, 64), col_size = min(n - col_start * 64, 64);
   __shared__ float bb[64 * 4];
@@ -221,42 +233,67 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ 
   __syncthreads();
   if (threadIdx.x < row_size) {
     const int cur = 64 * row_start + threadIdx.x;
-    const float* cb = boxes + (size_t)cur * box_dim;
-    const float c4[4] = {cb[0], cb[1], cb[2], cb[3]};
-    unsigned long long t = 0;
+    const float* cbx = boxes + (size_t)cur * box_dim;
+    const float c4[4] = {cbx[0], cbx[1], cbx[2], cbx[3]};
+    unsigned long long bits = 0;
     const int start = (row_start == col_start) ? threadIdx.x + 1 : 0;
     for (int i = start; i < col_size; ++i)
-      if (dev_iou(c4, bb + i * 4) > thresh) t |= 1ULL << i;
-    mask[(size_t)cur * col_blocks_ld + col_start] = t;
+      if (dev_iou(c4, bb + i * 4) > thresh) bits |= 1ULL << i;
+    mask[(size_t)cur * col_blocks_ld + col_start] = bits;
   }
 }
 
 // Greedy sweep (nms_kernel.cu:124-139) on the device, 64 boxes per step, early exit once max_keep are kept.
-__global__ void __launch_bounds__(128) nms_sweep_kernel(const unsigned long long* __restrict__ mask,
+// The 64 mask rows of a step (words >= blk only) are staged in shared memory with cp.async one step AHEAD (double
+// buffer), so the serial part of a step is ~a few hundred cycles: a find-first-set loop over the still-alive bits by one
+// thread, then a parallel OR of the kept rows into the running suppression words.
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(256) nms_sweep_kernel(const unsigned long long* __restrict__ mask,
                                                         const int* __restrict__ n_ptr, int col_blocks_ld, int max_keep,
                                                         int* __restrict__ keep_out, int* __restrict__ num_out) {
-  extern __shared__ unsigned long long remv[];      // [col_blocks]
-  __shared__ unsigned long long diag[64];
+  extern __shared__ unsigned long long sm64[];       // remv[col_blocks_ld] | stage[2][64][col_blocks_ld]
+  unsigned long long* remv = sm64;
+  unsigned long long* stage = sm64 + col_blocks_ld;
   __shared__ int kept_local[64];
   __shared__ int s_nk_local, s_total;
   const int n = *n_ptr;
   const int col_blocks = (n + 63) / 64;
   for (int i = threadIdx.x; i < col_blocks; i += blockDim.x) remv[i] = 0ULL;
   if (threadIdx.x == 0) s_total = 0;
+  auto stage_block = [&](int blk) {
+    const int base = blk * 64, cnt = min(64, n - base), width = col_blocks - blk;
+    unsigned long long* dst = stage + (size_t)(blk & 1) * 64 * col_blocks_ld;
+    for (int i = threadIdx.x; i < cnt * width; i += blockDim.x) {
+      const int r = i / width, w = i % width;
+      cp_async8(dst + (size_t)r * col_blocks_ld + w, mask + (size_t)(base + r) * col_blocks_ld + blk + w);
+    }
+    cp_async_commit();
+  };
+  if (col_blocks > 0) stage_block(0);
   __syncthreads();
   for (int blk = 0; blk < col_blocks; ++blk) {
     const int base = blk * 64, cnt = min(64, n - base);
-    if (threadIdx.x < 64) diag[threadIdx.x] = threadIdx.x < cnt ? mask[(size_t)(base + threadIdx.x) * col_blocks_ld + blk] : 0ULL;
+    if (blk + 1 < col_blocks) { stage_block(blk + 1); cp_async_wait<1>(); } else cp_async_wait<0>();
     __syncthreads();
+    const unsigned long long* rows = stage + (size_t)(blk & 1) * 64 * col_blocks_ld;
     if (threadIdx.x == 0) {
       unsigned long long cur = remv[blk];
+      const unsigned long long valid = cnt == 64 ? ~0ULL : ((1ULL << cnt) - 1ULL);
+      unsigned long long avail = ~cur & valid;
       int nk = 0, total = s_total;
-      for (int i = 0; i < cnt && total < max_keep; ++i) {
-        if (!((cur >> i) & 1ULL)) {
-          kept_local[nk++] = i;
-          keep_out[total++] = base + i;
-          cur |= diag[i];
-        }
+      while (avail && total < max_keep) {
+        const int i = __ffsll((long long)avail) - 1;
+        kept_local[nk++] = i;
+        keep_out[total++] = base + i;
+        cur |= rows[(size_t)i * col_blocks_ld];                 // diagonal word: bits j > i of this block
+        avail = ~cur & valid & ~((2ULL << i) - 1ULL);           // only bits above i remain candidates
       }
       s_nk_local = nk; s_total = total;
     }
@@ -265,11 +302,12 @@ __global__ void __launch_bounds__(128) nms_sweep_kernel(const unsigned long long
     const int nk = s_nk_local;
     for (int w = blk + 1 + threadIdx.x; w < col_blocks; w += blockDim.x) {
       unsigned long long acc = remv[w];
-      for (int j = 0; j < nk; ++j) acc |= mask[(size_t)(base + kept_local[j]) * col_blocks_ld + w];
+      for (int j = 0; j < nk; ++j) acc |= rows[(size_t)kept_local[j] * col_blocks_ld + (w - blk)];
       remv[w] = acc;
     }
     __syncthreads();
   }
+  cp_async_wait<0>();
   if (threadIdx.x == 0) *num_out = s_total;
 }
 
@@ -451,9 +489,9 @@ static size_t carve(const rn_proposal_desc* d, void* base, size_t bytes, Proposa
 
 static int launch_nms(cudaStream_t st, const float* boxes, int box_dim, const int* n_ptr, int n_max, float thresh,
                       int max_keep, unsigned long long* mask, int* keep, int* num_out) {
-  if (max_keep <= 8192) {
+  if (n_max <= 256) {
     const size_t smem = (size_t)max_keep * sizeof(float4);
-    static thread_local size_t configured = 48 * 1024;
+    static thread_local size_t configured = 40 * 1024;
     if (smem > configured) {
       RN_CUDA(cudaFuncSetAttribute(nms_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       configured = smem;
@@ -463,10 +501,19 @@ static int launch_nms(cudaStream_t st, const float* boxes, int box_dim, const in
     return RN_OK;
   }
   const int cb = (n_max + 63) / 64;
-  nms_mask_kernel<<<dim3(cb, cb), 64, 0, st>>>(boxes, box_dim, n_ptr, cb, thresh, mask);
+  nms_mask_kernel<<<cb * (cb + 1) / 2, 64, 0, st>>>(boxes, box_dim, n_ptr, cb, thresh, mask);
   RN_LAUNCH_CHECK();
-  nms_sweep_kernel<<<1, 128, (size_t)cb * 8, st>>>(mask, n_ptr, cb, max_keep, keep, num_out);
-  RN_LAUNCH_CHECK();
+  {
+    const size_t smem = (size_t)cb * 8 * (1 + 2 * 64);
+    RN_CHECK_ARG(smem <= 220 * 1024, "rn_nms: %d boxes exceed the staged sweep capacity (~13400)", n_max);
+    static thread_local size_t configured = 40 * 1024;
+    if (smem > configured) {
+      RN_CUDA(cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+    nms_sweep_kernel<<<1, 256, smem, st>>>(mask, n_ptr, cb, max_keep, keep, num_out);
+    RN_LAUNCH_CHECK();
+  }
   return RN_OK;
 }
 
@@ -498,7 +545,7 @@ extern "C" int rn_proposal_fwd(const rn_proposal_desc* d, const float* scales_ho
                                                            d->feat_stride, d->min_size, w.props, w.keys, n_total);
   RN_LAUNCH_CHECK();
   const int num_chunks = cdiv(n_max, kChunk);
-  const size_t rank_smem = (size_t)num_chunks * kChunk * 6;
+  const size_t rank_smem = (size_t)num_chunks * (kKS * 4 + kIS * 2) + 16;
   static thread_local size_t configured = 0;
   if (rank_smem > configured) {
     RN_CUDA(cudaFuncSetAttribute(proposal_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rank_smem));
