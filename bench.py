@@ -261,23 +261,33 @@ def main():
     out_pin = {'b': torch.empty((100, 80, 4), dtype=torch.float32).pin_memory(),
                's': torch.empty((100, 80), dtype=torch.float32).pin_memory()}
 
-    def step_resident():
-        prob, bbox, feat = trunk(image_d)
+    from relnet_b200.pipeline import GraphedStep
+
+    def full_step(img32):                       # fp32 NCHW image -> detections (cast + trunk + hot path)
+        img = img32.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        prob, bbox, feat = trunk(img)
         return head.forward(prob, bbox, feat, im_info)
 
+    image32_d = image_h.to(device)
+    eager_ms = timed(lambda: full_step(image32_d), max(5, args.steps // 2), 3, dist_on)    # un-graphed, for reference
+    graphed = GraphedStep(full_step, [image32_d])       # the public fast path: one CUDA-graph replay per image
+
+    def step_resident():
+        return graphed(image32_d)
+
     def step_e2e():
-        img = image_pin.to(device, non_blocking=True).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-        prob, bbox, feat = trunk(img)
-        o = head.forward(prob, bbox, feat, im_info)
+        o = graphed(image_pin)                  # H2D of the pinned host image into the graph's static input, replay
         out_pin['b'].copy_(o['learn_nms_sorted_bbox'], non_blocking=True)
         out_pin['s'].copy_(o['nms_final_score_output'], non_blocking=True)
         torch.cuda.current_stream().synchronize()          # the caller holds the detections on the host
         return o
 
     trunk_out = trunk(image_d)
+    hot_graph = GraphedStep(lambda a, b, c: head.forward(a, b, c, im_info), list(trunk_out))
+    trunk_graph = GraphedStep(lambda im: trunk(im), [image_d])
 
     def step_hot():
-        return head.forward(trunk_out[0], trunk_out[1], trunk_out[2], im_info)
+        return hot_graph(*trunk_out)
 
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -287,22 +297,20 @@ def main():
         sampler.stop_flag = True
     ms_e2e = timed(step_e2e, args.steps, max(3, args.warmup // 2), dist_on)
     ms_hot = timed(step_hot, args.steps, 3, dist_on)
-    ms_trunk = timed(lambda: trunk(image_d), args.steps, 3, dist_on)
+    ms_trunk = timed(lambda: trunk_graph(image_d), args.steps, 3, dist_on)
 
     if rank == 0:
         pk = peaks()
-        ours, lib, names = count_launches(step_resident)
+        ours, lib, names = count_launches(lambda: full_step(image32_d))
         roof, rel_times = (None, {})
         if ops.device_info()['sm100'] and prec == 'f16':
             roof, rel_times = relation_kernel_roofline(ops, pk, device)
-        o = step_resident()
-        torch.cuda.synchronize()
         line = {
             'metric': 'images/sec', 'value': round(world * args.steps / (ms / 1e3), 3), 'unit': 'images/sec',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(ms / args.steps, 4),
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f16' if prec == 'f16' else 'f32', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'global_batch': world, 'parallelism': 'replicas x%d (1 image/GPU)' % world,
+            'config': {'workload': WORKLOAD, 'global_batch': world, 'parallelism': 'replicas x%d (1 image/GPU)' % world, 'launch': 'one CUDA-graph replay per image',
                        'trunk': 'torch/cuDNN bf16 channels_last ResNet-101 (library, out of scope)',
                        'hot_path_precision': prec, 'l2': 'inputs (7.2 MB image) + 180 MB of trunk activations per step '
                        'exceed the 126 MB L2; relation kernel timed with an explicit 256 MB L2 flush'},
@@ -311,6 +319,7 @@ def main():
             'gpu_launches': (ours or 0) * args.steps, 'gpu_launches_per_step': ours, 'library_launches_per_step': lib,
             'hot_path': {'ms_per_image': round(ms_hot / args.steps, 4), 'images_per_sec': round(args.steps / (ms_hot / 1e3), 2),
                          'trunk_ms_per_image': round(ms_trunk / args.steps, 4),
+                         'eager_ms_per_step_no_graph': round(eager_ms / max(5, args.steps // 2), 4),
                          'relation_module_us': {k: round(v, 2) for k, v in rel_times.items()},
                          'proposals_kept_before_pad': int(ops.proposal(trunk_out[0], trunk_out[1], im_info, return_num_kept=True, **head.cfg)[2].item())},
             'clocks': sampler.summary() if sampler else None,

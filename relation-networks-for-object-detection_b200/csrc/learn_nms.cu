@@ -256,7 +256,7 @@ extern "C" int rn_learn_nms_fwd(const rn_learn_nms_desc* d, const float* cls_sco
   lnms_rank_embed_kernel<<<cdiv(n * kRankDim / 2, 256), 256, 0, st>>>(n, W.rank_emb);
   RN_LAUNCH_CHECK();
   if ((r = rn_linear_fwd(W.rank_emb, w->nms_rank_weight, w->nms_rank_bias, W.rank_feat, n, kRankDim, kNmsFeat, 0,
-                         RN_PREC_FP32, W.rel_ws, W.rel_ws_bytes, stream))) return r;
+                         d->precision, W.rel_ws, W.rel_ws_bytes, stream))) return r;
   if ((r = rn_linear_fwd(feat, w->roi_feat_embedding_weight, w->roi_feat_embedding_bias, W.emb, d->R, d->feat_dim,
                          kNmsFeat, 0, d->precision, W.rel_ws, W.rel_ws_bytes, stream))) return r;
   lnms_gather_kernel<<<dim3(n, C), 128, 0, st>>>(n, C, K, d->class_agnostic, W.rank_idx, W.refined, W.emb, W.rank_feat,

@@ -10,6 +10,7 @@
 //   exit after post_nms kept -> emit rois (+ deterministic padding keep[i % kept]).
 // HBM traffic is ~1 MB of maps + <= 4.5 MB of mask: latency bound, not bandwidth bound (DESIGN.md "proposal").
 #include "common.cuh"
+#include "umma.cuh"
 #include <algorithm>
 
 namespace rn {
@@ -125,10 +126,14 @@ __global__ void __launch_bounds__(1024) proposal_rank_kernel(const uint32_t* __r
   uint32_t* k = reinterpret_cast<uint32_t*>(sm);
   uint16_t* ix = reinterpret_cast<uint16_t*>(sm + (size_t)num_chunks * kKS * 4);
   __shared__ int s_n_pre;
-  for (int i = threadIdx.x; i < P; i += blockDim.x) {
-    const int c = i >> 10, o = i & (kChunk - 1);
-    k[c * kKS + o] = skeys[i];
-    ix[c * kIS + o] = sidx[i];
+  for (int i = threadIdx.x; i < P / 8; i += blockDim.x) {      // 8 elements per thread-iteration: 2 x uint4 keys, 1 x uint4 idx
+    const int e0 = i * 8, c = e0 >> 10, o = e0 & (kChunk - 1);
+    const uint4 k0 = reinterpret_cast<const uint4*>(skeys)[2 * i], k1 = reinterpret_cast<const uint4*>(skeys)[2 * i + 1];
+    const uint4 i0 = reinterpret_cast<const uint4*>(sidx)[i];
+    uint32_t* kd = k + c * kKS + o;
+    kd[0] = k0.x; kd[1] = k0.y; kd[2] = k0.z; kd[3] = k0.w; kd[4] = k1.x; kd[5] = k1.y; kd[6] = k1.z; kd[7] = k1.w;
+    uint32_t* id = reinterpret_cast<uint32_t*>(ix + c * kIS + o);    // kIS and o are even -> 4-byte aligned
+    id[0] = i0.x; id[1] = i0.y; id[2] = i0.z; id[3] = i0.w;
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -212,10 +217,9 @@ __device__ __forceinline__ float dev_iou(const float* a, const float* b) {
 // 64x64 tile of the suppression matrix (nms_kernel.cu:34-78); only tiles on/above the diagonal are needed by the
 // sweep, so the grid enumerates the upper triangle linearly (row-major over row blocks).
 __global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ boxes, int box_dim,
-                                                      const int* __restrict__ n_ptr, int col_blocks_ld, float thresh,
-                                                      unsigned long long* __restrict__ mask) {
+                                                      const int* __restrict__ n_ptr, int cb, int col_blocks_ld,
+                                                      float thresh, unsigned long long* __restrict__ mask) {
   const int n = *n_ptr;
-  const int cb = col_blocks_ld;
   // t = row*cb - row*(row-1)/2 + (col - row)  ->  row = floor(((2cb+1) - sqrt((2cb+1)^2 - 8t)) / 2)
   const int t = blockIdx.x;
   int row_start = (int)(((2.0f * cb + 1.0f) - sqrtf((2.0f * cb + 1.0f) * (2.0f * cb + 1.0f) - 8.0f * (float)t)) * 0.5f);
@@ -237,52 +241,59 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ 
     const float c4[4] = {cbx[0], cbx[1], cbx[2], cbx[3]};
     unsigned long long bits = 0;
     const int start = (row_start == col_start) ? threadIdx.x + 1 : 0;
-    for (int i = start; i < col_size; ++i)
-      if (dev_iou(c4, bb + i * 4) > thresh) bits |= 1ULL << i;
+    const bool shortcut = thresh >= 0.f;      // disjoint boxes have IoU == +0 exactly: skip the areas and the division
+    for (int i = start; i < col_size; ++i) {
+      const float* o = bb + i * 4;
+      if (shortcut && (fminf(c4[2], o[2]) - fmaxf(c4[0], o[0]) + 1 <= 0.f || fminf(c4[3], o[3]) - fmaxf(c4[1], o[1]) + 1 <= 0.f))
+        continue;
+      if (dev_iou(c4, o) > thresh) bits |= 1ULL << i;
+    }
     mask[(size_t)cur * col_blocks_ld + col_start] = bits;
   }
 }
 
 // Greedy sweep (nms_kernel.cu:124-139) on the device, 64 boxes per step, early exit once max_keep are kept.
-// The 64 mask rows of a step (words >= blk only) are staged in shared memory with cp.async one step AHEAD (double
-// buffer), so the serial part of a step is ~a few hundred cycles: a find-first-set loop over the still-alive bits by one
-// thread, then a parallel OR of the kept rows into the running suppression words.
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
+// The 64 mask rows of a step are staged in shared memory one step AHEAD by bulk async copies (cp.async.bulk, one per
+// row, issued by warp 0, completion on an mbarrier; double buffer), so a step is: wait barrier -> one thread resolves the
+// block with a find-first-set loop over the still-alive bits -> all threads OR the kept rows into the running
+// suppression words.  col_blocks_ld is even so every row segment is 16-byte aligned.
 __global__ void __launch_bounds__(256) nms_sweep_kernel(const unsigned long long* __restrict__ mask,
                                                         const int* __restrict__ n_ptr, int col_blocks_ld, int max_keep,
                                                         int* __restrict__ keep_out, int* __restrict__ num_out) {
-  extern __shared__ unsigned long long sm64[];       // remv[col_blocks_ld] | stage[2][64][col_blocks_ld]
-  unsigned long long* remv = sm64;
-  unsigned long long* stage = sm64 + col_blocks_ld;
+  extern __shared__ __align__(16) unsigned long long sm64[];       // stage[2][64][col_blocks_ld] | remv[col_blocks_ld]
+  unsigned long long* stage = sm64;
+  unsigned long long* remv = sm64 + (size_t)2 * 64 * col_blocks_ld;
+  __shared__ __align__(8) uint64_t bar[2];
   __shared__ int kept_local[64];
   __shared__ int s_nk_local, s_total;
   const int n = *n_ptr;
   const int col_blocks = (n + 63) / 64;
-  for (int i = threadIdx.x; i < col_blocks; i += blockDim.x) remv[i] = 0ULL;
-  if (threadIdx.x == 0) s_total = 0;
-  auto stage_block = [&](int blk) {
-    const int base = blk * 64, cnt = min(64, n - base), width = col_blocks - blk;
-    unsigned long long* dst = stage + (size_t)(blk & 1) * 64 * col_blocks_ld;
-    for (int i = threadIdx.x; i < cnt * width; i += blockDim.x) {
-      const int r = i / width, w = i % width;
-      cp_async8(dst + (size_t)r * col_blocks_ld + w, mask + (size_t)(base + r) * col_blocks_ld + blk + w);
-    }
-    cp_async_commit();
-  };
-  if (col_blocks > 0) stage_block(0);
+  const int ld = col_blocks_ld;
+  for (int i = threadIdx.x; i < ld; i += blockDim.x) remv[i] = 0ULL;
+  if (threadIdx.x == 0) {
+    s_total = 0;
+    umma::mbar_init(&bar[0], 1); umma::mbar_init(&bar[1], 1);
+    umma::fence_barrier_init();
+  }
   __syncthreads();
+  auto stage_block = [&](int blk) {                     // warp 0 only
+    const int base = blk * 64, cnt = min(64, n - base), w0 = blk & ~1;
+    const uint32_t row_bytes = (uint32_t)(ld - w0) * 8u;
+    unsigned long long* dst = stage + (size_t)(blk & 1) * 64 * ld;
+    if (threadIdx.x == 0) {
+      umma::fence_proxy_async_smem();
+      umma::mbar_arrive_expect_tx(&bar[blk & 1], (uint32_t)cnt * row_bytes);
+    }
+    __syncwarp();
+    for (int r = threadIdx.x; r < cnt; r += 32)
+      umma::bulk_copy_g2s(dst + (size_t)r * ld, mask + (size_t)(base + r) * ld + w0, row_bytes, &bar[blk & 1]);
+  };
+  if (threadIdx.x < 32 && col_blocks > 0) stage_block(0);
   for (int blk = 0; blk < col_blocks; ++blk) {
-    const int base = blk * 64, cnt = min(64, n - base);
-    if (blk + 1 < col_blocks) { stage_block(blk + 1); cp_async_wait<1>(); } else cp_async_wait<0>();
-    __syncthreads();
-    const unsigned long long* rows = stage + (size_t)(blk & 1) * 64 * col_blocks_ld;
+    const int base = blk * 64, cnt = min(64, n - base), w0 = blk & ~1;
+    if (threadIdx.x < 32 && blk + 1 < col_blocks) stage_block(blk + 1);
+    umma::mbar_wait(&bar[blk & 1], (blk >> 1) & 1);
+    const unsigned long long* rows = stage + (size_t)(blk & 1) * 64 * ld;      // rows[r*ld + (w - w0)]
     if (threadIdx.x == 0) {
       unsigned long long cur = remv[blk];
       const unsigned long long valid = cnt == 64 ? ~0ULL : ((1ULL << cnt) - 1ULL);
@@ -292,22 +303,22 @@ __global__ void __launch_bounds__(256) nms_sweep_kernel(const unsigned long long
         const int i = __ffsll((long long)avail) - 1;
         kept_local[nk++] = i;
         keep_out[total++] = base + i;
-        cur |= rows[(size_t)i * col_blocks_ld];                 // diagonal word: bits j > i of this block
-        avail = ~cur & valid & ~((2ULL << i) - 1ULL);           // only bits above i remain candidates
+        cur |= rows[(size_t)i * ld + (blk - w0)];              // diagonal word: bits j > i of this block
+        avail = ~cur & valid & ~((2ULL << i) - 1ULL);          // only bits above i remain candidates
       }
       s_nk_local = nk; s_total = total;
     }
     __syncthreads();
     if (s_total >= max_keep) break;
     const int nk = s_nk_local;
-    for (int w = blk + 1 + threadIdx.x; w < col_blocks; w += blockDim.x) {
-      unsigned long long acc = remv[w];
-      for (int j = 0; j < nk; ++j) acc |= rows[(size_t)kept_local[j] * col_blocks_ld + (w - blk)];
-      remv[w] = acc;
-    }
+    if (nk > 0)
+      for (int w = blk + 1 + threadIdx.x; w < col_blocks; w += blockDim.x) {
+        unsigned long long acc = remv[w];
+        for (int j = 0; j < nk; ++j) acc |= rows[(size_t)kept_local[j] * ld + (w - w0)];
+        remv[w] = acc;
+      }
     __syncthreads();
   }
-  cp_async_wait<0>();
   if (threadIdx.x == 0) *num_out = s_total;
 }
 
@@ -467,7 +478,7 @@ static size_t carve(const rn_proposal_desc* d, void* base, size_t bytes, Proposa
   const int A = d->num_scales * d->num_ratios;
   const int n_max = d->Hf * d->Wf * A;
   const int pre = d->pre_nms_top_n > 0 ? (d->pre_nms_top_n < n_max ? d->pre_nms_top_n : n_max) : n_max;
-  const int cb = (pre + 63) / 64;
+  const int cb = ((pre + 63) / 64 + 1) & ~1;      // even: 16-byte aligned mask rows
   const int P = cdiv(n_max, kChunk) * kChunk;
   size_t need = ws_slice((size_t)n_max * 4, 8) + ws_slice(n_max, 4) + ws_slice(P, 4) + ws_slice(P, 2) + ws_slice(pre, 4) +
                 ws_slice((size_t)pre * 5, 4) +
@@ -500,8 +511,9 @@ static int launch_nms(cudaStream_t st, const float* boxes, int box_dim, const in
     RN_LAUNCH_CHECK();
     return RN_OK;
   }
-  const int cb = (n_max + 63) / 64;
-  nms_mask_kernel<<<cb * (cb + 1) / 2, 64, 0, st>>>(boxes, box_dim, n_ptr, cb, thresh, mask);
+  const int cbv = (n_max + 63) / 64;              // valid 64-box blocks
+  const int cb = (cbv + 1) & ~1;                  // even leading dimension of the mask rows
+  nms_mask_kernel<<<cbv * (cbv + 1) / 2, 64, 0, st>>>(boxes, box_dim, n_ptr, cbv, cb, thresh, mask);
   RN_LAUNCH_CHECK();
   {
     const size_t smem = (size_t)cb * 8 * (1 + 2 * 64);
@@ -571,7 +583,7 @@ extern "C" int rn_proposal_fwd(const rn_proposal_desc* d, const float* scales_ho
 }
 
 extern "C" size_t rn_nms_workspace_bytes(int32_t n) {
-  const size_t cb = (n + 63) / 64;
+  const size_t cb = (((size_t)n + 63) / 64 + 1) & ~(size_t)1;
   return rn::ws_slice((size_t)n * cb, 8) + rn::ws_slice(4, 4) + 256;
 }
 
@@ -581,8 +593,8 @@ extern "C" int rn_nms(const float* boxes_sorted, int32_t n, int32_t box_dim, flo
   RN_CHECK_ARG(boxes_sorted && keep_out && num_out && wsp && n >= 0 && box_dim >= 4 && max_keep > 0, "rn_nms: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   Workspace ws(wsp, ws_bytes);
-  const int cb = (n + 63) / 64;
-  unsigned long long* mask = ws.take<unsigned long long>((size_t)n * cb + 1);
+  const int cb = ((n + 63) / 64 + 1) & ~1;
+  unsigned long long* mask = ws.take<unsigned long long>((size_t)n * cb + 2);
   int* n_dev = ws.take<int>(4);
   if (!n_dev) { set_error("rn_nms: workspace too small"); return RN_ERR_WORKSPACE; }
   RN_CUDA(cudaMemsetAsync(num_out, 0, sizeof(int), st));

@@ -69,6 +69,14 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// 1-D bulk copy global -> shared (16-byte aligned, size multiple of 16); completes tx bytes on `bar`
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------ TMEM
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result) {   // one full warp; COLS power of two in [32,512]
