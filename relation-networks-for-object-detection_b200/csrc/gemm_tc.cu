@@ -27,12 +27,13 @@ struct GemmSmem {
   static constexpr int kB = BN * kBK * 2;
   static constexpr int kStage = kA + kB;
   static constexpr int kBar = kStages * kStage;       // barriers live after the ring
-  static constexpr int kTotal = kBar + 256 + 1024;    // + alignment slack
+  static constexpr int kTotal = kBar + 256 + 1024;    // + barriers + alignment slack
 };
 
 struct GemmParams {
   int M, N, K;
-  int k_blocks_per_split;     // K blocks (of 64) per grid.z slice
+  int k_blocks_per_split;     // K blocks (of 64) per K-split
+  int splits;                 // number of K-splits (work units = tiles * splits)
   const float* bias;          // [N] (bias_per_row == 0) or [M] (bias_per_row == 1) or nullptr
   int bias_per_row;
   int relu;
@@ -41,6 +42,9 @@ struct GemmParams {
   float* partial;                     // split-K partials [splits][M][N] (when gridDim.z > 1)
 };
 
+// Persistent: CTA b processes work units b, b+grid, ... ; a unit = (K-split z, output tile (m, n)).  The smem ring and
+// its phases run on across units, the accumulator is double buffered in TMEM (2 x BN columns) so the epilogue of unit i
+// overlaps the MMAs of unit i+1 (tfull / tempty barriers).
 template <int BN>
 __global__ void __launch_bounds__(192, 1) gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                              const __grid_constant__ CUtensorMap tmB, GemmParams p) {
@@ -50,23 +54,23 @@ __global__ void __launch_bounds__(192, 1) gemm_f16_tc_kernel(const __grid_consta
   using S = GemmSmem<BN>;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::kBar);
   uint64_t* empty = full + kStages;
-  uint64_t* tmem_full = empty + kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tfull = empty + kStages;      // [2]
+  uint64_t* tempty = tfull + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * BN;
   const int total_kb = (p.K + kBK - 1) / kBK;
-  const int kb_begin = blockIdx.z * p.k_blocks_per_split;
-  const int kb_end = min(total_kb, kb_begin + p.k_blocks_per_split);
-  const int num_kb = kb_end - kb_begin;
+  const int tiles_n = (p.N + BN - 1) / BN, tiles = ((p.M + kBM - 1) / kBM) * tiles_n;
+  const int units = tiles * p.splits;
 
   if (warp == 4 && lane == 0) {
     prefetch_tmap(&tmA); prefetch_tmap(&tmB);
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(tmem_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 128); }
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc<(BN < 32 ? 32 : BN)>(tmem_slot);
+  if (warp == 5) tmem_alloc<kTmemCols>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -74,101 +78,124 @@ __global__ void __launch_bounds__(192, 1) gemm_f16_tc_kernel(const __grid_consta
 
   if (warp == 4) {
     if (lane == 0) {
-      for (int i = 0; i < num_kb; ++i) {
-        const int s = i % kStages, it = i / kStages;
-        mbar_wait(&empty[s], (it & 1) ^ 1);
-        mbar_arrive_expect_tx(&full[s], S::kStage);
-        uint8_t* sa = smem + s * S::kStage;
-        tma_load_2d(sa, &tmA, &full[s], (kb_begin + i) * kBK, m0);
-        tma_load_2d(sa + S::kA, &tmB, &full[s], (kb_begin + i) * kBK, n0);
+      int it = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        const int z = u / tiles, t = u % tiles;
+        const int m0 = (t / tiles_n) * kBM, n0 = (t % tiles_n) * BN;
+        const int kb_begin = z * p.k_blocks_per_split, kb_end = min(total_kb, kb_begin + p.k_blocks_per_split);
+        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+          const int s = it % kStages;
+          mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
+          mbar_arrive_expect_tx(&full[s], S::kStage);
+          uint8_t* sa = smem + s * S::kStage;
+          tma_load_2d(sa, &tmA, &full[s], kb * kBK, m0);
+          tma_load_2d(sa + S::kA, &tmB, &full[s], kb * kBK, n0);
+        }
       }
     }
   } else if (warp == 5) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc_f16(kBM, BN, false, false, false);
-      for (int i = 0; i < num_kb; ++i) {
-        const int s = i % kStages, it = i / kStages;
-        mbar_wait(&full[s], it & 1);
+      int it = 0, li = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x, ++li) {
+        const int z = u / tiles;
+        const int kb_begin = z * p.k_blocks_per_split, kb_end = min(total_kb, kb_begin + p.k_blocks_per_split);
+        const int as = li & 1;
+        mbar_wait(&tempty[as], ((li >> 1) & 1) ^ 1);           // epilogue has drained this accumulator stage
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * S::kStage), sb = sa + S::kA;
+        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+          const int s = it % kStages;
+          mbar_wait(&full[s], (it / kStages) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * S::kStage), sb = sa + S::kA;
 #pragma unroll
-        for (int k = 0; k < kBK / 16; ++k)
-          mma_f16_ss(tmem_base, make_smem_desc_sw128(sa + k * 32, 16, 1024), make_smem_desc_sw128(sb + k * 32, 16, 1024),
-                     idesc, (i | k) != 0);
-        mma_commit(&empty[s]);
+          for (int k = 0; k < kBK / 16; ++k)
+            mma_f16_ss(tmem_base + as * BN, make_smem_desc_sw128(sa + k * 32, 16, 1024),
+                       make_smem_desc_sw128(sb + k * 32, 16, 1024), idesc, (kb > kb_begin) || k > 0);
+          mma_commit(&empty[s]);
+        }
+        mma_commit(&tfull[as]);
       }
-      mma_commit(tmem_full);
     }
   } else {
     // epilogue: thread t of warps 0..3 owns accumulator row (32*warp + lane)
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-    const int row = m0 + warp * 32 + lane;
-    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-    const bool split = gridDim.z > 1;
-    const float rbias = (!split && p.bias && p.bias_per_row && row < p.M) ? p.bias[row] : 0.f;
+    const bool split = p.splits > 1;
+    int li = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x, ++li) {
+      const int z = u / tiles, t = u % tiles;
+      const int m0 = (t / tiles_n) * kBM, n0 = (t % tiles_n) * BN;
+      const int kb_begin = z * p.k_blocks_per_split, kb_end = min(total_kb, kb_begin + p.k_blocks_per_split);
+      const int as = li & 1;
+      mbar_wait(&tfull[as], (li >> 1) & 1);
+      tc_fence_after();
+      const int row = m0 + warp * 32 + lane;
+      const uint32_t lane_base = tmem_base + as * BN + ((uint32_t)(warp * 32) << 16);
+      const float rbias = (!split && p.bias && p.bias_per_row && row < p.M) ? p.bias[row] : 0.f;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t v[32];
-      if (num_kb > 0) { tmem_ld_32x32b_x32(lane_base + c * 32, v); tmem_ld_wait(); }
-      else {
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        if (kb_end > kb_begin) { tmem_ld_32x32b_x32(lane_base + c * 32, v); tmem_ld_wait(); }
+        else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0u;
-      }
-      const int col0 = n0 + c * 32;
-      if (row < p.M && col0 < p.N) {
-        float f[32];
+          for (int j = 0; j < 32; ++j) v[j] = 0u;
+        }
+        const int col0 = n0 + c * 32;
+        if (row < p.M && col0 < p.N) {
+          float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (split) {
-          float* dst = p.partial + ((size_t)blockIdx.z * p.M + row) * p.N + col0;
-          if (col0 + 32 <= p.N && (p.N & 3) == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-          } else {
-            for (int j = 0; j < 32 && col0 + j < p.N; ++j) dst[j] = f[j];
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float b = rbias;
-            if (p.bias && !p.bias_per_row && col0 + j < p.N) b = __ldg(p.bias + col0 + j);
-            f[j] += b;
-            if (p.relu) f[j] = fmaxf(f[j], 0.f);
-          }
-          const bool full_chunk = col0 + 32 <= p.N;
-          if (p.C32) {
-            float* dst = p.C32 + (size_t)row * p.ldc32 + col0;
-            if (full_chunk && (p.ldc32 & 3) == 0) {
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (split) {
+            float* dst = p.partial + ((size_t)z * p.M + row) * p.N + col0;
+            if (col0 + 32 <= p.N && (p.N & 3) == 0) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
             } else {
               for (int j = 0; j < 32 && col0 + j < p.N; ++j) dst[j] = f[j];
             }
-          }
-          if (p.C16) {
-            __half* dst = p.C16 + (size_t)row * p.ldc16 + col0;
-            if (full_chunk && (p.ldc16 & 7) == 0) {
+          } else {
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                __half2 h0 = __floats2half2_rn(f[j], f[j + 1]), h1 = __floats2half2_rn(f[j + 2], f[j + 3]);
-                __half2 h2 = __floats2half2_rn(f[j + 4], f[j + 5]), h3 = __floats2half2_rn(f[j + 6], f[j + 7]);
-                uint4 u;
-                u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
-                u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
-                *reinterpret_cast<uint4*>(dst + j) = u;
+            for (int j = 0; j < 32; ++j) {
+              float b = rbias;
+              if (p.bias && !p.bias_per_row && col0 + j < p.N) b = __ldg(p.bias + col0 + j);
+              f[j] += b;
+              if (p.relu) f[j] = fmaxf(f[j], 0.f);
+            }
+            const bool full_chunk = col0 + 32 <= p.N;
+            if (p.C32) {
+              float* dst = p.C32 + (size_t)row * p.ldc32 + col0;
+              if (full_chunk && (p.ldc32 & 3) == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+              } else {
+                for (int j = 0; j < 32 && col0 + j < p.N; ++j) dst[j] = f[j];
               }
-            } else {
-              for (int j = 0; j < 32 && col0 + j < p.N; ++j) dst[j] = __float2half_rn(f[j]);
+            }
+            if (p.C16) {
+              __half* dst = p.C16 + (size_t)row * p.ldc16 + col0;
+              if (full_chunk && (p.ldc16 & 7) == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                  __half2 h0 = __floats2half2_rn(f[j], f[j + 1]), h1 = __floats2half2_rn(f[j + 2], f[j + 3]);
+                  __half2 h2 = __floats2half2_rn(f[j + 4], f[j + 5]), h3 = __floats2half2_rn(f[j + 6], f[j + 7]);
+                  uint4 uu;
+                  uu.x = *reinterpret_cast<uint32_t*>(&h0); uu.y = *reinterpret_cast<uint32_t*>(&h1);
+                  uu.z = *reinterpret_cast<uint32_t*>(&h2); uu.w = *reinterpret_cast<uint32_t*>(&h3);
+                  *reinterpret_cast<uint4*>(dst + j) = uu;
+                }
+              } else {
+                for (int j = 0; j < 32 && col0 + j < p.N; ++j) dst[j] = __float2half_rn(f[j]);
+              }
             }
           }
         }
       }
+      tc_fence_before();
+      mbar_arrive(&tempty[as]);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc<(BN < 32 ? 32 : BN)>(tmem_base);
+  if (warp == 5) tmem_dealloc<kTmemCols>(tmem_base);
 }
 
 __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N, const float* bias,
@@ -258,7 +285,9 @@ int gemm_tc(cudaStream_t st, const __half* A, long long lda, const __half* B, lo
   int r;
   if ((r = encode_tmap_2d_f16(&tmA, A, M, K, lda, kBM, kBK))) return r;
   if ((r = encode_tmap_2d_f16(&tmB, B, N, K, ldb, BN, kBK))) return r;
-  dim3 grid(cdiv(N, BN), tiles_m, splits);
+  p.splits = splits;
+  const int units = tiles * splits;
+  dim3 grid(std::min(units, sms));                       // persistent: one CTA per SM, units round-robin
   r = bn64 ? launch<64>(st, tmA, tmB, p, grid) : launch<128>(st, tmA, tmB, p, grid);
   if (r) return r;
   if (splits > 1) {

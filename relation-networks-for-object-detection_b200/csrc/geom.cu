@@ -172,11 +172,11 @@ __global__ void __launch_bounds__(128) geom_weight_mma_kernel(const float* __res
       split_h2(cs[1][0], cs[1][1], &ah[3], &al[3]);            // a3: row g+8
 #pragma unroll
       for (int nh = 0; nh < NHALF; ++nh) {
+        // hi/lo split of both operands -> fp32-accurate FC (plain fp16 operands cost ~1e-3 on the module output when
+        // the geometry weights are O(0.1): measured, tests/test_gpu_parity.py relation_cfg0_fanin)
         mma16816(acc[nh], ah[0], ah[1], ah[2], ah[3], bh[c][nh][0], bh[c][nh][1]);
-        if (EXACT) {     // hi/lo split of both operands -> fp32-accurate FC; the fast variant keeps plain fp16 operands
-          mma16816(acc[nh], al[0], al[1], al[2], al[3], bh[c][nh][0], bh[c][nh][1]);   // (legacy HMMA costs ~64 issue
-          mma16816(acc[nh], ah[0], ah[1], ah[2], ah[3], bl[c][nh][0], bl[c][nh][1]);   //  cycles per SMSP on sm_100)
-        }
+        mma16816(acc[nh], al[0], al[1], al[2], al[3], bh[c][nh][0], bh[c][nh][1]);
+        mma16816(acc[nh], ah[0], ah[1], ah[2], ah[3], bl[c][nh][0], bl[c][nh][1]);
       }
     }
     // C fragment: c0 (row g, head 2q), c1 (row g, head 2q+1), c2 (row g+8, head 2q), c3 (row g+8, head 2q+1)

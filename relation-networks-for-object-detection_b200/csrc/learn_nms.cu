@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(128) lnms_logit_kernel(int n, int C, int T, co
 }
 
 struct LnmsWs {
-  float *prob, *refined, *cmax, *rank_emb, *rank_feat, *emb, *feat_cls, *boxes_cls, *feat_out;
+  float *prob, *refined, *cmax, *rank_emb, *rank_feat, *emb, *feat_cls, *boxes_cls, *feat_out, *lg_roi;
   int *rank_idx, *valid;
   void* rel_ws; size_t rel_ws_bytes;
 };
@@ -188,7 +188,7 @@ static size_t carve(const rn_learn_nms_desc* d, int Rn, void* base, size_t bytes
   size_t need = ws_slice((size_t)Rn * C, 4) + ws_slice((size_t)Rn * 4 * K, 4) + ws_slice(C, 4) +
                 ws_slice(n * kRankDim, 4) + ws_slice(n * kNmsFeat, 4) + ws_slice((size_t)d->R * kNmsFeat, 4) +
                 ws_slice(C * n * kNmsFeat, 4) + ws_slice(C * n * 4, 4) + ws_slice(C * n * kNmsFeat, 4) +
-                ws_slice(n * C, 4) + ws_slice(C, 4) + align_up(rel, 256);
+                ws_slice(n * C, 4) + ws_slice(C, 4) + ws_slice((size_t)16 * Rn * align_up(Rn, 4), 4) + align_up(rel, 256);
   if (!w) return need;
   Workspace ws(base, bytes);
   w->prob = ws.take<float>((size_t)Rn * C);
@@ -202,6 +202,7 @@ static size_t carve(const rn_learn_nms_desc* d, int Rn, void* base, size_t bytes
   w->feat_out = ws.take<float>(C * n * kNmsFeat);
   w->rank_idx = ws.take<int>(n * C);
   w->valid = ws.take<int>(C);
+  w->lg_roi = ws.take<float>((size_t)16 * Rn * align_up(Rn, 4));
   w->rel_ws = ws.take<char>(rel);
   w->rel_ws_bytes = rel;
   return w->rel_ws ? need : 0;
@@ -263,7 +264,17 @@ extern "C" int rn_learn_nms_fwd(const rn_learn_nms_desc* d, const float* cls_sco
                                                  sorted_bbox, W.feat_cls, W.boxes_cls);
   RN_LAUNCH_CHECK();
   rn_relation_desc rd = inner_desc(d);
-  if ((r = rn_relation_fwd(&rd, W.feat_cls, W.boxes_cls, nullptr, w->nms_query_1_weight, w->nms_query_1_bias,
+  if (d->precision == RN_PREC_F16 && d->class_agnostic && n <= 512 && relation_tc_shape_ok(&rd)) {
+    // class-agnostic boxes: every class sorts the SAME refined rois, so the per-class pair geometry is a gather from
+    // one [16, Rn, Rn] table (LNMS:332 builds [C, n, n, 4] position matrices -- 9x the pairs at C = 80, n = 100)
+    const int ldr = (int)align_up(Rn, 4);
+    if ((r = launch_geom_weight_log2(st, W.refined, nullptr, 1, Rn, Rn, 16, 64, 1000.f, w->nms_pair_pos_fc1_1_weight,
+                                     w->nms_pair_pos_fc1_1_bias, W.lg_roi, ldr))) return r;
+    GeomGather gg = {W.lg_roi, ldr, Rn, W.rank_idx, C, 1};
+    if ((r = relation_tc_gathered(&rd, W.feat_cls, &gg, w->nms_query_1_weight, w->nms_query_1_bias, w->nms_key_1_weight,
+                                  w->nms_key_1_bias, w->nms_linear_out_1_weight, w->nms_linear_out_1_bias, W.feat_out,
+                                  W.rel_ws, W.rel_ws_bytes, st))) return r;
+  } else if ((r = rn_relation_fwd(&rd, W.feat_cls, W.boxes_cls, nullptr, w->nms_query_1_weight, w->nms_query_1_bias,
                            w->nms_key_1_weight, w->nms_key_1_bias, w->nms_pair_pos_fc1_1_weight,
                            w->nms_pair_pos_fc1_1_bias, w->nms_linear_out_1_weight, w->nms_linear_out_1_bias, W.feat_out,
                            nullptr, W.rel_ws, W.rel_ws_bytes, stream))) return r;

@@ -248,19 +248,20 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ 
         continue;
       if (dev_iou(c4, o) > thresh) bits |= 1ULL << i;
     }
-    mask[(size_t)cur * col_blocks_ld + col_start] = bits;
+    mask[((size_t)row_start * col_blocks_ld + col_start) * 64 + threadIdx.x] = bits;   // blocked layout [rb][w][r]
   }
 }
 
 // Greedy sweep (nms_kernel.cu:124-139) on the device, 64 boxes per step, early exit once max_keep are kept.
-// The 64 mask rows of a step are staged in shared memory one step AHEAD by bulk async copies (cp.async.bulk, one per
-// row, issued by warp 0, completion on an mbarrier; double buffer), so a step is: wait barrier -> one thread resolves the
-// block with a find-first-set loop over the still-alive bits -> all threads OR the kept rows into the running
-// suppression words.  col_blocks_ld is even so every row segment is 16-byte aligned.
+// The mask is stored blocked, [row block][word][row in block], so the 64 rows x (col_blocks - blk) words a step needs
+// are ONE contiguous span: a single cp.async.bulk stages it in shared memory one step ahead (double buffer, mbarrier
+// completion).  (64 per-row bulk copies cost ~50 cycles of TMA issue each and made the step slower: 164 us measured.)
+// A step = wait barrier -> one thread resolves the block with a find-first-set loop over the still-alive bits -> all
+// threads OR the kept rows into the running suppression words.
 __global__ void __launch_bounds__(256) nms_sweep_kernel(const unsigned long long* __restrict__ mask,
                                                         const int* __restrict__ n_ptr, int col_blocks_ld, int max_keep,
                                                         int* __restrict__ keep_out, int* __restrict__ num_out) {
-  extern __shared__ __align__(16) unsigned long long sm64[];       // stage[2][64][col_blocks_ld] | remv[col_blocks_ld]
+  extern __shared__ __align__(16) unsigned long long sm64[];       // stage[2][col_blocks_ld][64] | remv[col_blocks_ld]
   unsigned long long* stage = sm64;
   unsigned long long* remv = sm64 + (size_t)2 * 64 * col_blocks_ld;
   __shared__ __align__(8) uint64_t bar[2];
@@ -276,24 +277,18 @@ __global__ void __launch_bounds__(256) nms_sweep_kernel(const unsigned long long
     umma::fence_barrier_init();
   }
   __syncthreads();
-  auto stage_block = [&](int blk) {                     // warp 0 only
-    const int base = blk * 64, cnt = min(64, n - base), w0 = blk & ~1;
-    const uint32_t row_bytes = (uint32_t)(ld - w0) * 8u;
-    unsigned long long* dst = stage + (size_t)(blk & 1) * 64 * ld;
-    if (threadIdx.x == 0) {
-      umma::fence_proxy_async_smem();
-      umma::mbar_arrive_expect_tx(&bar[blk & 1], (uint32_t)cnt * row_bytes);
-    }
-    __syncwarp();
-    for (int r = threadIdx.x; r < cnt; r += 32)
-      umma::bulk_copy_g2s(dst + (size_t)r * ld, mask + (size_t)(base + r) * ld + w0, row_bytes, &bar[blk & 1]);
+  auto stage_block = [&](int blk) {                     // thread 0 only
+    const uint32_t bytes = (uint32_t)(col_blocks - blk) * 64u * 8u;
+    umma::fence_proxy_async_smem();
+    umma::mbar_arrive_expect_tx(&bar[blk & 1], bytes);
+    umma::bulk_copy_g2s(stage + (size_t)(blk & 1) * 64 * ld, mask + ((size_t)blk * ld + blk) * 64, bytes, &bar[blk & 1]);
   };
-  if (threadIdx.x < 32 && col_blocks > 0) stage_block(0);
+  if (threadIdx.x == 0 && col_blocks > 0) stage_block(0);
   for (int blk = 0; blk < col_blocks; ++blk) {
-    const int base = blk * 64, cnt = min(64, n - base), w0 = blk & ~1;
-    if (threadIdx.x < 32 && blk + 1 < col_blocks) stage_block(blk + 1);
+    const int base = blk * 64, cnt = min(64, n - base);
+    if (threadIdx.x == 0 && blk + 1 < col_blocks) stage_block(blk + 1);
     umma::mbar_wait(&bar[blk & 1], (blk >> 1) & 1);
-    const unsigned long long* rows = stage + (size_t)(blk & 1) * 64 * ld;      // rows[r*ld + (w - w0)]
+    const unsigned long long* rows = stage + (size_t)(blk & 1) * 64 * ld;      // rows[(w - blk)*64 + r]
     if (threadIdx.x == 0) {
       unsigned long long cur = remv[blk];
       const unsigned long long valid = cnt == 64 ? ~0ULL : ((1ULL << cnt) - 1ULL);
@@ -303,7 +298,7 @@ __global__ void __launch_bounds__(256) nms_sweep_kernel(const unsigned long long
         const int i = __ffsll((long long)avail) - 1;
         kept_local[nk++] = i;
         keep_out[total++] = base + i;
-        cur |= rows[(size_t)i * ld + (blk - w0)];              // diagonal word: bits j > i of this block
+        cur |= rows[i];                                        // diagonal word: bits j > i of this block
         avail = ~cur & valid & ~((2ULL << i) - 1ULL);          // only bits above i remain candidates
       }
       s_nk_local = nk; s_total = total;
@@ -314,7 +309,7 @@ __global__ void __launch_bounds__(256) nms_sweep_kernel(const unsigned long long
     if (nk > 0)
       for (int w = blk + 1 + threadIdx.x; w < col_blocks; w += blockDim.x) {
         unsigned long long acc = remv[w];
-        for (int j = 0; j < nk; ++j) acc |= rows[(size_t)kept_local[j] * ld + (w - w0)];
+        for (int j = 0; j < nk; ++j) acc |= rows[(size_t)(w - blk) * 64 + kept_local[j]];
         remv[w] = acc;
       }
     __syncthreads();
@@ -482,7 +477,7 @@ static size_t carve(const rn_proposal_desc* d, void* base, size_t bytes, Proposa
   const int P = cdiv(n_max, kChunk) * kChunk;
   size_t need = ws_slice((size_t)n_max * 4, 8) + ws_slice(n_max, 4) + ws_slice(P, 4) + ws_slice(P, 2) + ws_slice(pre, 4) +
                 ws_slice((size_t)pre * 5, 4) +
-                ws_slice((size_t)pre * cb, 8) + ws_slice(d->post_nms_top_n > 0 ? d->post_nms_top_n : pre, 4) + ws_slice(8, 4);
+                ws_slice((size_t)(pre + 63) / 64 * 64 * cb, 8) + ws_slice(d->post_nms_top_n > 0 ? d->post_nms_top_n : pre, 4) + ws_slice(8, 4);
   if (!w) return need;
   Workspace ws(base, bytes);
   w->n_max = n_max; w->pre = pre; w->col_blocks = cb;
@@ -492,7 +487,7 @@ static size_t carve(const rn_proposal_desc* d, void* base, size_t bytes, Proposa
   w->sidx = ws.take<uint16_t>(P);
   w->order = ws.take<int>(pre);
   w->det = ws.take<float>((size_t)pre * 5);
-  w->mask = ws.take<unsigned long long>((size_t)pre * cb);
+  w->mask = ws.take<unsigned long long>((size_t)(pre + 63) / 64 * 64 * cb);
   w->keep = ws.take<int>(d->post_nms_top_n > 0 ? d->post_nms_top_n : pre);
   w->counters = ws.take<int>(8);
   return w->counters ? need : 0;
@@ -584,7 +579,7 @@ extern "C" int rn_proposal_fwd(const rn_proposal_desc* d, const float* scales_ho
 
 extern "C" size_t rn_nms_workspace_bytes(int32_t n) {
   const size_t cb = (((size_t)n + 63) / 64 + 1) & ~(size_t)1;
-  return rn::ws_slice((size_t)n * cb, 8) + rn::ws_slice(4, 4) + 256;
+  return rn::ws_slice(((size_t)n + 63) / 64 * 64 * cb, 8) + rn::ws_slice(4, 4) + 256;
 }
 
 extern "C" int rn_nms(const float* boxes_sorted, int32_t n, int32_t box_dim, float thresh, int32_t max_keep,
@@ -594,7 +589,7 @@ extern "C" int rn_nms(const float* boxes_sorted, int32_t n, int32_t box_dim, flo
   cudaStream_t st = (cudaStream_t)stream;
   Workspace ws(wsp, ws_bytes);
   const int cb = ((n + 63) / 64 + 1) & ~1;
-  unsigned long long* mask = ws.take<unsigned long long>((size_t)n * cb + 2);
+  unsigned long long* mask = ws.take<unsigned long long>(((size_t)n + 63) / 64 * 64 * cb);
   int* n_dev = ws.take<int>(4);
   if (!n_dev) { set_error("rn_nms: workspace too small"); return RN_ERR_WORKSPACE; }
   RN_CUDA(cudaMemsetAsync(num_out, 0, sizeof(int), st));

@@ -229,7 +229,7 @@ extern "C" int rn_relation_packed_fwd(const rn_relation_desc* d, const float* X,
   int r = rn::check_desc(d);
   if (r) return r;
   RN_CHECK_ARG(X && boxes && packed && Wg && bg && out && ws, "rn_relation_packed_fwd: null pointer argument");
-  return rn::relation_tc_packed(d, X, boxes, key_index, packed, Wg, bg, out, ws, ws_bytes, (cudaStream_t)stream, 7);
+  return rn::relation_tc_packed(d, X, boxes, key_index, packed, Wg, bg, out, ws, ws_bytes, (cudaStream_t)stream, 7, nullptr);
 }
 
 // measurement hook: run only the selected stages (1 = cast + projection GEMM, 2 = geometry, 4 = fused attention) on the
@@ -241,7 +241,7 @@ extern "C" int rn_relation_packed_stages(const rn_relation_desc* d, const float*
   if (r) return r;
   RN_CHECK_ARG(X && boxes && packed && Wg && bg && out && ws, "rn_relation_packed_stages: null pointer argument");
   return rn::relation_tc_packed(d, X, boxes, key_index, packed, Wg, bg, out, ws, ws_bytes, (cudaStream_t)stream,
-                                stage_mask);
+                                stage_mask, nullptr);
 }
 
 extern "C" size_t rn_linear_packed_bytes(int32_t in, int32_t out) { return rn::linear_tc_packed_bytes(in, out); }

@@ -12,12 +12,21 @@ int relation_tc(const rn_relation_desc* d, const float* X, const float* boxes, c
                 const float* bq, const float* Wk, const float* bk, const float* Wg, const float* bg, const float* Wout,
                 const float* bout, float* out, float* softmax_out, void* ws, size_t ws_bytes, cudaStream_t st);
 
+struct GeomGather;
 size_t relation_tc_packed_bytes(const rn_relation_desc* d);
 int relation_tc_pack(const rn_relation_desc* d, const float* Wq, const float* bq, const float* Wk, const float* bk,
                      const float* Wout, const float* bout, void* packed, cudaStream_t st);
 int relation_tc_packed(const rn_relation_desc* d, const float* X, const float* boxes, const int* key_index,
                        const void* packed, const float* Wg, const float* bg, float* out, void* ws, size_t ws_bytes,
-                       cudaStream_t st, int stage_mask);
+                       cudaStream_t st, int stage_mask, const struct GeomGather* gg = nullptr);
+// geometry gathered from one roi-level table lg_table [H, R, ld]: row i of problem b is roi idx[i*stride_i + b*stride_b]
+struct GeomGather { const float* lg_table; int ld; int R; const int* idx; int stride_i; int stride_b; };
+int relation_tc_gathered(const rn_relation_desc* d, const float* X, const GeomGather* gg, const float* Wq, const float* bq,
+                         const float* Wk, const float* bk, const float* Wout, const float* bout, float* out, void* ws,
+                         size_t ws_bytes, cudaStream_t st);
+bool relation_tc_shape_ok(const rn_relation_desc* d);
+int launch_geom_weight_log2(cudaStream_t st, const float* boxes, const int* key_index, int B, int N, int M, int H, int E,
+                            float wave_length, const float* Wg, const float* bg, float* g, int ldg);
 
 // tcgen05 fp16 GEMM (gemm_tc.cu): y = act(x W^T + b)
 size_t linear_tc_workspace_bytes(int rows, int in, int out);

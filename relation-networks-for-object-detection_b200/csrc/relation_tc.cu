@@ -38,6 +38,9 @@ struct AttnParams {
   int dv;                         // valid output columns per head (<= 64)
   int relu;
   float scale_log2;               // log2(e)/sqrt(dk)
+  // optional gather mode (learn-NMS with class-agnostic boxes): lg is ONE table [H, R, ldg] over the image's rois and
+  // row i of problem b is roi gidx[i*gs_i + b*gs_b] -- the per-class geometry is a gather, not 80 recomputations
+  const int* gidx; int gs_i, gs_b; int R;
 };
 
 __global__ void __launch_bounds__(192, 1) relation_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
@@ -296,9 +299,14 @@ __global__ void __launch_bounds__(160, 2) relation_attn_tile_kernel(const __grid
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTileBar);
   uint64_t* ld_full = bars; uint64_t* s_full = bars + 1; uint64_t* p_full = bars + 2; uint64_t* pv_full = bars + 3;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  __shared__ int s_gidx[128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x / tp.splits, kt = blockIdx.x % tp.splits;
   const int q0 = qt * 128, m0 = kt * 128, h = blockIdx.y, b = blockIdx.z;
+  if (p.gidx && threadIdx.x < 128) {
+    const int m = m0 + threadIdx.x;
+    s_gidx[threadIdx.x] = m < p.M ? p.gidx[(size_t)m * p.gs_i + (size_t)b * p.gs_b] : 0;
+  }
 
   if (warp == 4) {
     if (lane == 0) {
@@ -341,14 +349,21 @@ __global__ void __launch_bounds__(160, 2) relation_attn_tile_kernel(const __grid
     const int r = warp * 32 + lane, n = q0 + r;
     const bool row_ok = n < p.N;
     const uint32_t lane_base = ((uint32_t)(warp * 32) << 16);
-    const float* lg_row = p.lg + (((size_t)b * p.H + h) * p.N + (row_ok ? n : 0)) * p.ldg + m0;
     // the whole geometry row of this tile, issued before the S tile is ready
     float t[128];
+    if (p.gidx) {
+      const int ri = p.gidx[(size_t)(row_ok ? n : 0) * p.gs_i + (size_t)b * p.gs_b];
+      const float* lg_row = p.lg + ((size_t)h * p.R + ri) * p.ldg;
 #pragma unroll
-    for (int q = 0; q < 128; q += 4) {
-      float4 t4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-      if (m0 + q < p.M) t4 = __ldg(reinterpret_cast<const float4*>(lg_row + q));      // ldg >= M rounded up to 4
-      t[q] = t4.x; t[q + 1] = t4.y; t[q + 2] = t4.z; t[q + 3] = t4.w;
+      for (int q = 0; q < 128; ++q) t[q] = (m0 + q < p.M) ? __ldg(lg_row + s_gidx[q]) : -INFINITY;
+    } else {
+      const float* lg_row = p.lg + (((size_t)b * p.H + h) * p.N + (row_ok ? n : 0)) * p.ldg + m0;
+#pragma unroll
+      for (int q = 0; q < 128; q += 4) {
+        float4 t4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        if (m0 + q < p.M) t4 = __ldg(reinterpret_cast<const float4*>(lg_row + q));      // ldg >= M rounded up to 4
+        t[q] = t4.x; t[q + 1] = t4.y; t[q + 2] = t4.z; t[q + 3] = t4.w;
+      }
     }
     mbar_wait(s_full, 0);
     tc_fence_after();
@@ -534,7 +549,7 @@ int relation_tc_pack(const rn_relation_desc* d, const float* Wq, const float* bq
 
 int relation_tc_packed(const rn_relation_desc* d, const float* X, const float* boxes, const int* key_index,
                        const void* packed, const float* Wg, const float* bg, float* out, void* wsp, size_t ws_bytes,
-                       cudaStream_t st, int stage_mask) {
+                       cudaStream_t st, int stage_mask, const GeomGather* gg) {
   const bool do_proj = stage_mask & 1, do_geom = stage_mask & 2, do_attn = stage_mask & 4;
   RN_CHECK_ARG(is_sm100(), "RN_PREC_F16 needs an sm_100 device (tcgen05); use RN_PREC_FP32");
   RN_CHECK_ARG(tc_shape_ok(d), "RN_PREC_F16 relation kernel supports dq == 64*H and dout/H <= 64 (got dq=%d dout=%d H=%d); "
@@ -574,7 +589,8 @@ int relation_tc_packed(const rn_relation_desc* d, const float* X, const float* b
     if (do_proj && (r = gemm_tc(st, x16, d8, w16, d8, B * N, W3, d8, bias, 0, 0, nullptr, 0, qkv, W3, gws, gws_bytes))) return r;
     Qp = qkv; Kp = qkv + H * 64; Vp = qkv + 2 * H * 64; ldq = ldk = W3; bq_pitch = bk_pitch = (long long)N * W3;
   }
-  if (do_geom && (r = launch_geom_weight_log2(st, boxes, key_index, B, N, M, H, d->E, d->wave_length, Wg, bg, lg, ldg))) return r;
+  if (gg) RN_CHECK_ARG(!key_index && cdiv(M, 128) <= kMaxTileSplits, "gathered geometry needs M <= %d and no key_index", 128 * kMaxTileSplits);
+  if (!gg && do_geom && (r = launch_geom_weight_log2(st, boxes, key_index, B, N, M, H, d->E, d->wave_length, Wg, bg, lg, ldg))) return r;
   if (!do_attn) return RN_OK;
 
   CUtensorMap tmQ, tmK, tmV;
@@ -584,6 +600,8 @@ int relation_tc_packed(const rn_relation_desc* d, const float* X, const float* b
   AttnParams p;
   p.N = N; p.M = M; p.H = H; p.T = T;
   p.lg = lg; p.ldg = ldg;
+  p.gidx = nullptr; p.gs_i = p.gs_b = 0; p.R = 0;
+  if (gg) { p.lg = gg->lg_table; p.ldg = gg->ld; p.R = gg->R; p.gidx = gg->idx; p.gs_i = gg->stride_i; p.gs_b = gg->stride_b; }
   p.X = d->fuse_residual_relu ? X : nullptr; p.ldx = D;
   p.out = out; p.ldo = d->dout; p.dv = dv; p.relu = d->fuse_residual_relu;
   p.scale_log2 = 1.4426950408889634f / sqrtf(64.f);
@@ -623,7 +641,22 @@ int relation_tc(const rn_relation_desc* d, const float* X, const float* boxes, c
   if (ws_bytes < pk) { set_error("rn_relation_fwd(F16): workspace too small"); return RN_ERR_WORKSPACE; }
   int r = relation_tc_pack(d, Wq, bq, Wk, bk, Wout, bout, wsp, st);
   if (r) return r;
-  return relation_tc_packed(d, X, boxes, key_index, wsp, Wg, bg, out, (char*)wsp + pk, ws_bytes - pk, st, 7);
+  return relation_tc_packed(d, X, boxes, key_index, wsp, Wg, bg, out, (char*)wsp + pk, ws_bytes - pk, st, 7, nullptr);
 }
 
+}  // namespace rn
+
+namespace rn {
+// learn-NMS entry: pack the weights into the workspace, then run with the geometry gathered from a roi-level table
+int relation_tc_gathered(const rn_relation_desc* d, const float* X, const GeomGather* gg, const float* Wq, const float* bq,
+                         const float* Wk, const float* bk, const float* Wout, const float* bout, float* out, void* wsp,
+                         size_t ws_bytes, cudaStream_t st) {
+  const size_t pk = relation_tc_packed_bytes(d);
+  RN_CHECK_ARG(pk > 0 && gg, "relation_tc_gathered: unsupported shape");
+  if (ws_bytes < pk) { set_error("relation_tc_gathered: workspace too small"); return RN_ERR_WORKSPACE; }
+  int r = relation_tc_pack(d, Wq, bq, Wk, bk, Wout, bout, wsp, st);
+  if (r) return r;
+  return relation_tc_packed(d, X, nullptr, nullptr, wsp, nullptr, nullptr, out, (char*)wsp + pk, ws_bytes - pk, st, 7, gg);
+}
+bool relation_tc_shape_ok(const rn_relation_desc* d) { return tc_shape_ok(d); }
 }  // namespace rn
