@@ -113,6 +113,18 @@ int rn_linear_pack(const float* W, int32_t in, int32_t out, void* packed, rn_str
 int rn_linear_packed_fwd(const float* x, const void* packed_W, const float* b, float* y, int32_t rows, int32_t in,
                          int32_t out, int32_t relu, void* workspace, size_t workspace_bytes, rn_stream_t stream);
 
+/* Fused-head fast path (same arithmetic, fewer bytes): ROI max-pool straight from the trunk's channels-last feature map
+ * to an fp16 [R, PH*PW, C] tensor, consumed by fc_new_1 through a K-permuted packed weight (no fp32 pooled tensor, no
+ * cast kernel).  data_nhwc [B,H,W,C] fp32; out_f16 [R, PH*PW*C] fp16. */
+int rn_roi_pool_nhwc_f16_fwd(const float* data_nhwc, const float* rois, int32_t R, int32_t C, int32_t H, int32_t W,
+                             int32_t PH, int32_t PW, float spatial_scale, void* out_f16, rn_stream_t stream);
+/* W [out, C*S] (FC over a flattened [C, S] input, S = PH*PW) -> packed fp16 [out, S*C] */
+int rn_linear_pack_chw_to_hwc(const float* W, int32_t out, int32_t C, int32_t S, void* packed, rn_stream_t stream);
+/* y = act(x W^T + b) with x already fp16 [rows, in] (in % 8 == 0); y (fp32) and/or y_f16 may be NULL */
+int rn_linear_packed_f16in_fwd(const void* x_f16, const void* packed_W, const float* b, float* y, void* y_f16,
+                               int32_t rows, int32_t in, int32_t out, int32_t relu, void* workspace,
+                               size_t workspace_bytes, rn_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * learn_nms CustomOp forward (LNMS:238-401) + test-time merge (SYM_REL_NMS:553-560).
  * Inputs in the order of LearnNmsProp.list_arguments (LNMS:429-441). */

@@ -343,6 +343,35 @@ int linear_tc_packed(const float* x, const void* packed_W, const float* b, float
                  ws.size - ws.off);
 }
 
+// W [out, C*S] (MXNet FC weight over a flattened [C, S] = [channels, ph*pw] input) -> fp16 [out, S*C]: the K order of
+// the channels-last pooled tensor written by rn_roi_pool_nhwc_f16_fwd
+__global__ void pack_chw_to_hwc_kernel(const float* __restrict__ W, int out, int C, int S, __half* __restrict__ dst) {
+  const size_t total = (size_t)out * C * S;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = i % C, sidx = (i / C) % S;
+    const size_t o = i / ((size_t)C * S);
+    dst[i] = __float2half_rn(W[(o * C + c) * S + sidx]);
+  }
+}
+
+int linear_tc_pack_chw_to_hwc(const float* W, int out, int C, int S, void* packed, cudaStream_t st) {
+  RN_CHECK_ARG(((size_t)C * S) % 8 == 0, "rn_linear_pack_chw_to_hwc: C*S must be a multiple of 8");
+  const size_t total = (size_t)out * C * S;
+  size_t blocks = (total + 255) / 256;
+  const size_t cap = (size_t)(sm_count() > 0 ? sm_count() : 148) * 16;
+  pack_chw_to_hwc_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(W, out, C, S, (__half*)packed);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
+
+// x already fp16 [rows, in] (in % 8 == 0): no cast, straight into the GEMM; optional fp16 copy of the output
+int linear_tc_packed_f16in(const void* x16, const void* packed_W, const float* b, float* y, void* y16, int rows, int in,
+                           int out, int relu, void* wsp, size_t ws_bytes, cudaStream_t st) {
+  RN_CHECK_ARG(in % 8 == 0, "rn_linear_packed_f16in_fwd: in must be a multiple of 8");
+  return gemm_tc(st, (const __half*)x16, in, (const __half*)packed_W, in, rows, out, in, b, 0, relu, y, out, (__half*)y16,
+                 out, wsp, ws_bytes);
+}
+
 int linear_tc(const float* x, const float* W, const float* b, float* y, int rows, int in, int out, int relu, void* wsp,
               size_t ws_bytes, cudaStream_t st) {
   const int in8 = (int)align_up(in, 8);

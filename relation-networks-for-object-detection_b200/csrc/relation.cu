@@ -256,3 +256,16 @@ extern "C" int rn_linear_packed_fwd(const float* x, const void* packed_W, const 
   RN_CHECK_ARG(x && packed_W && y && rows > 0 && in > 0 && out > 0 && ws, "rn_linear_packed_fwd: bad arguments");
   return rn::linear_tc_packed(x, packed_W, b, y, rows, in, out, relu, ws, ws_bytes, (cudaStream_t)stream);
 }
+
+extern "C" int rn_linear_pack_chw_to_hwc(const float* W, int32_t out, int32_t C, int32_t S, void* packed,
+                                         rn_stream_t stream) {
+  RN_CHECK_ARG(W && packed && out > 0 && C > 0 && S > 0, "rn_linear_pack_chw_to_hwc: bad arguments");
+  return rn::linear_tc_pack_chw_to_hwc(W, out, C, S, packed, (cudaStream_t)stream);
+}
+
+extern "C" int rn_linear_packed_f16in_fwd(const void* x_f16, const void* packed_W, const float* b, float* y, void* y_f16,
+                                          int32_t rows, int32_t in, int32_t out, int32_t relu, void* ws, size_t ws_bytes,
+                                          rn_stream_t stream) {
+  RN_CHECK_ARG(x_f16 && packed_W && (y || y_f16) && rows > 0 && in > 0 && out > 0, "rn_linear_packed_f16in_fwd: bad arguments");
+  return rn::linear_tc_packed_f16in(x_f16, packed_W, b, y, y_f16, rows, in, out, relu, ws, ws_bytes, (cudaStream_t)stream);
+}

@@ -33,6 +33,9 @@ size_t linear_tc_workspace_bytes(int rows, int in, int out);
 int linear_tc(const float* x, const float* W, const float* b, float* y, int rows, int in, int out, int relu, void* ws,
               size_t ws_bytes, cudaStream_t st);
 size_t linear_tc_packed_bytes(int in, int out);
+int linear_tc_pack_chw_to_hwc(const float* W, int out, int C, int S, void* packed, cudaStream_t st);
+int linear_tc_packed_f16in(const void* x16, const void* packed_W, const float* b, float* y, void* y16, int rows, int in,
+                           int out, int relu, void* ws, size_t ws_bytes, cudaStream_t st);
 int linear_tc_pack(const float* W, int in, int out, void* packed, cudaStream_t st);
 int linear_tc_packed(const float* x, const void* packed_W, const float* b, float* y, int rows, int in, int out, int relu,
                      void* ws, size_t ws_bytes, cudaStream_t st);

@@ -44,6 +44,38 @@ __global__ void __launch_bounds__(256) roi_pool_fwd_kernel(const float* __restri
   }
 }
 
+// Same op for the fused head: channels-last input (what the cuDNN trunk produces) and fp16 output in [R, PH*PW, C] order
+// (the K order of the permuted fc_new_1 weight, see rn_linear_pack_chw_to_hwc) -- one CTA per (roi, bin), threads along
+// channels: every load and store is coalesced, the bin window is shared by the CTA, and the 15 MB fp32 pooled tensor
+// plus its fp16 cast kernel disappear.  Same bin arithmetic as above -> same maxima (then rounded to fp16).
+__global__ void __launch_bounds__(128) roi_pool_nhwc_f16_kernel(const float* __restrict__ data, const float* __restrict__ rois,
+                                                                int C, int H, int W, int PH, int PW, float spatial_scale,
+                                                                __half* __restrict__ out) {
+  const int bin = blockIdx.x, n = blockIdx.y;
+  const int ph = bin / PW, pw = bin % PW;
+  const float* roi = rois + 5 * n;
+  const int b = (int)roi[0];
+  const int rsw = (int)roundf(roi[1] * spatial_scale), rsh = (int)roundf(roi[2] * spatial_scale);
+  const int rew = (int)roundf(roi[3] * spatial_scale), reh = (int)roundf(roi[4] * spatial_scale);
+  const int rh = max(reh - rsh + 1, 1), rw = max(rew - rsw + 1, 1);
+  const float bh = (float)rh / (float)PH, bw = (float)rw / (float)PW;
+  int hs = (int)floorf((float)ph * bh), ws = (int)floorf((float)pw * bw);
+  int he = (int)ceilf((float)(ph + 1) * bh), we = (int)ceilf((float)(pw + 1) * bw);
+  hs = min(max(hs + rsh, 0), H); he = min(max(he + rsh, 0), H);
+  ws = min(max(ws + rsw, 0), W); we = min(max(we + rsw, 0), W);
+  const bool empty = (he <= hs) || (we <= ws);
+  const float* d = data + (size_t)b * H * W * C;
+  for (int c = threadIdx.x * 2; c < C; c += blockDim.x * 2) {
+    float m0 = empty ? 0.f : -FLT_MAX, m1 = m0;
+    for (int h = hs; h < he; ++h)
+      for (int w = ws; w < we; ++w) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(d + ((size_t)h * W + w) * C + c));
+        m0 = fmaxf(m0, v.x); m1 = fmaxf(m1, v.y);
+      }
+    *reinterpret_cast<__half2*>(out + ((size_t)n * PH * PW + bin) * C + c) = __floats2half2_rn(m0, m1);
+  }
+}
+
 // operator_cxx/deformable_psroi_pooling.cu:29-49
 __device__ __forceinline__ float psroi_bilinear(const float* __restrict__ data, float x, float y, int width) {
   const int x1 = (int)floorf(x), x2 = (int)ceilf(x), y1 = (int)floorf(y), y2 = (int)ceilf(y);
@@ -141,6 +173,18 @@ extern "C" int rn_deform_psroi_pool_fwd(const rn_psroi_desc* desc, const float* 
   size_t count = (size_t)p.R * p.output_dim * p.pooled_size * p.pooled_size;
   rn::deform_psroi_fwd_kernel<<<rn::grid_for(count), 256, 0, (cudaStream_t)stream>>>(p, count, data, rois, trans, out,
                                                                                     top_count);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
+
+extern "C" int rn_roi_pool_nhwc_f16_fwd(const float* data_nhwc, const float* rois, int32_t R, int32_t C, int32_t H,
+                                        int32_t W, int32_t PH, int32_t PW, float spatial_scale, void* out_f16,
+                                        rn_stream_t stream) {
+  RN_CHECK_ARG(data_nhwc && rois && out_f16 && R >= 0 && C > 0 && (C % 2) == 0 && H > 0 && W > 0 && PH > 0 && PW > 0,
+               "rn_roi_pool_nhwc_f16_fwd: bad arguments (C must be even)");
+  if (R == 0) return RN_OK;
+  rn::roi_pool_nhwc_f16_kernel<<<dim3(PH * PW, R), 128, 0, (cudaStream_t)stream>>>(data_nhwc, rois, C, H, W, PH, PW,
+                                                                                 spatial_scale, (__half*)out_f16);
   RN_LAUNCH_CHECK();
   return RN_OK;
 }

@@ -44,8 +44,11 @@ class _PackCache(object):
     def __init__(self):
         self.d = {}
 
-    def get(self, tensors, nbytes, pack_fn):
-        key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors)
+    def get_tagged(self, tag, tensors, nbytes, pack_fn):
+        return self.get(tensors, nbytes, pack_fn, tag)
+
+    def get(self, tensors, nbytes, pack_fn, tag=None):
+        key = (tag,) + tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors)
         hit = self.d.get(key)
         if hit is None:
             if len(self.d) > 256:
@@ -283,6 +286,34 @@ def roi_pool(data, rois, pooled_size=(7, 7), spatial_scale=0.0625, return_argmax
     L.check(L.lib().rn_roi_pool_fwd(_ptr(data), _ptr(rois), R, Cc, H, W, pooled_size[0], pooled_size[1], spatial_scale,
                                     _ptr(out), _ptr(arg), _stream()), 'rn_roi_pool_fwd')
     return (out, arg) if return_argmax else out
+
+
+def roi_pool_fc(data, rois, W, b, pooled_size=(7, 7), spatial_scale=0.0625, relu=False):
+    """ROIPooling + FullyConnected fused at the data-layout level (SYM_REL:252-262 with RN_PREC_F16): channels-last
+    feature map -> fp16 pooled [R, PH*PW*C] -> tcgen05 GEMM against the K-permuted packed weight.  Returns fp32 [R, out].
+    ``data`` is an NCHW-shaped tensor; a channels_last one is consumed without a copy."""
+    if not data.is_cuda:
+        raise L.RelnetError('roi_pool_fc: CUDA tensors required (no CPU path)')
+    B, Cc, H, Wd = data.shape
+    nhwc = data.float().contiguous(memory_format=torch.channels_last)      # no-op for the trunk's output
+    rois = _f32(rois, 'rois'); W = _f32(W, 'W'); b = _f32(b, 'b') if b is not None else None
+    R = rois.shape[0]
+    S = pooled_size[0] * pooled_size[1]
+    cin, cout = Cc * S, W.shape[0]
+    assert W.shape[1] == cin
+    lib = L.lib()
+    pooled = torch.empty((R, cin), dtype=torch.float16, device=data.device)
+    L.check(lib.rn_roi_pool_nhwc_f16_fwd(_ptr(nhwc), _ptr(rois), R, Cc, H, Wd, pooled_size[0], pooled_size[1],
+                                         spatial_scale, _ptr(pooled), _stream()), 'rn_roi_pool_nhwc_f16_fwd')
+
+    def pack(buf):
+        L.check(lib.rn_linear_pack_chw_to_hwc(_ptr(W), cout, Cc, S, _ptr(buf), _stream()), 'rn_linear_pack_chw_to_hwc')
+    packed = _packs.get_tagged('chw2hwc', (W,), lib.rn_linear_packed_bytes(cin, cout), pack)
+    y = torch.empty((R, cout), dtype=torch.float32, device=data.device)
+    ws = _workspace(lib.rn_linear_workspace_bytes(R, cin, cout, 1), data.device)
+    L.check(lib.rn_linear_packed_f16in_fwd(_ptr(pooled), _ptr(packed), _ptr(b), _ptr(y), None, R, cin, cout, int(relu),
+                                           _ptr(ws), ws.numel(), _stream()), 'rn_linear_packed_f16in_fwd')
+    return y
 
 
 def deform_psroi_pool(data, rois, trans=None, spatial_scale=0.0625, output_dim=256, group_size=1, pooled_size=7,

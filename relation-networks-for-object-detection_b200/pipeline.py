@@ -83,9 +83,13 @@ class RelationHead(object):
     def forward(self, rpn_cls_prob, rpn_bbox_pred, conv_feat, im_info):
         P, prec = self.P, self.precision
         rois, _ = ops.proposal(rpn_cls_prob, rpn_bbox_pred, im_info, **self.cfg)                  # SYM_REL_NMS:324-329
-        pooled = ops.roi_pool(conv_feat, rois, (7, 7), 1.0 / self.cfg['feat_stride'])             # :335
         boxes = rois[:, 1:].contiguous()                                                          # :337
-        fc1 = ops.linear(pooled, P['fc_new_1_weight'], P['fc_new_1_bias'], precision=prec)        # :344
+        if prec == 'f16':        # :335 + :344 at the layout level: channels-last pool -> fp16 -> K-permuted fc_new_1
+            fc1 = ops.roi_pool_fc(conv_feat, rois, P['fc_new_1_weight'], P['fc_new_1_bias'], (7, 7),
+                                  1.0 / self.cfg['feat_stride'])
+        else:
+            pooled = ops.roi_pool(conv_feat, rois, (7, 7), 1.0 / self.cfg['feat_stride'])         # :335
+            fc1 = ops.linear(pooled, P['fc_new_1_weight'], P['fc_new_1_bias'], precision=prec)    # :344
         fc_all_1 = self.relation(fc1, boxes, 1, self.nongt_dim)                                   # :346-351
         fc2 = ops.linear(fc_all_1, P['fc_new_2_weight'], P['fc_new_2_bias'], precision=prec)      # :353
         fc_all_2 = self.relation(fc2, boxes, 2, self.nongt_dim)                                   # :354-359

@@ -79,7 +79,7 @@ class Trunk(nn.Module):
         prob = F.softmax(score.reshape(b, 2, self.A * h, w), dim=1).reshape(b, 2 * self.A, h, w)
         bbox = self.rpn_bbox(r).float()
         feat = F.relu(self.conv_new_1(c5)).float()
-        return prob.contiguous(), bbox.contiguous(), feat.contiguous()
+        return prob.contiguous(), bbox.contiguous(), feat          # feat stays channels-last (consumed as NHWC)
 
 
 def make_trunk(device, dtype=torch.bfloat16, seed=0):

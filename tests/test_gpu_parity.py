@@ -310,3 +310,39 @@ def test_deform_conv_matches_oracle(ops):
     torch.backends.cudnn.allow_tf32 = False
     ref0 = torch.nn.functional.conv2d(T(data), T(wgt), padding=2, dilation=2)
     assert float((out0 - ref0).abs().max() / ref0.abs().max()) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ fused head / pipeline
+def test_roi_pool_fc_fast_path(ops):
+    if not ops.device_info()['sm100']:
+        pytest.skip('tcgen05 path')
+    data, rois = _roi_case(5, nroi=120, C=64)
+    rng = np.random.default_rng(9)
+    W = (rng.standard_normal((96, 64 * 49)) / 56).astype(np.float32); b = rng.standard_normal(96).astype(np.float32)
+    pooled, _ = RO.roi_pool(data, rois)
+    ref = pooled.reshape(120, -1).astype(np.float64) @ W.astype(np.float64).T + b
+    for fmt in (torch.contiguous_format, torch.channels_last):
+        y = ops.roi_pool_fc(T(data).contiguous(memory_format=fmt), T(rois), T(W), T(b)).cpu().numpy()
+        assert rel_err(y, ref) < 1e-3
+
+
+def test_hot_path_pipeline_matches_oracle(ops):
+    """proposal -> ROI pool -> fc -> relation x2 -> cls/bbox -> learn_nms, CUDA vs the numpy/C oracle (one image)."""
+    import relnet_b200
+    from relnet_b200.pipeline import RelationHead, init_head_params
+    from oracle import pipeline_np
+    prm = init_head_params(3, 'cpu')
+    cls_prob, bbox_pred, info = P.make_proposal_case(5)
+    feat = np.maximum(np.random.default_rng(5).standard_normal((1, 256, 38, 63)), 0).astype(np.float32)
+    ref = pipeline_np.head_forward({k: v.numpy() for k, v in prm.items()}, cls_prob, bbox_pred, feat, info)
+    for prec in precisions(ops):
+        head = RelationHead({k: v.cuda() for k, v in prm.items()}, precision=prec)
+        out = head.forward(T(cls_prob), T(bbox_pred), T(feat), T(info))
+        np.testing.assert_array_equal(out['rois'].cpu().numpy(), ref['rois'])
+        e_feat = rel_err(out['fc_all_2_relu'].cpu().numpy(), ref['fc_all_2_relu'])
+        e_cls = rel_err(out['cls_score'].cpu().numpy(), ref['cls_score'])
+        e_ss = rel_err(out['sorted_score'].cpu().numpy(), ref['sorted_score'])
+        e_fin = rel_err(out['nms_final_score_output'].cpu().numpy(), ref['nms_final_score_output'])
+        print('pipeline[%s]: fc_all_2 %.2e cls_score %.2e sorted_score %.2e final %.2e' % (prec, e_feat, e_cls, e_ss, e_fin))
+        tol = 3e-4 if prec == 'fp32' else 3e-3          # two relation modules + 4 fp16 GEMMs (K up to 12544) in sequence
+        assert e_feat < tol and e_cls < tol and e_ss < tol and e_fin < 2 * tol
