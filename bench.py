@@ -108,10 +108,9 @@ def timed(fn, steps, warmup, dist_on):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     if dist_on:
+        from relnet_b200 import replicas
         dist.barrier()
-        t = torch.tensor([ms], device='cuda')
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        ms = replicas.max_over_ranks(ms, device='cuda')
     return ms
 
 
