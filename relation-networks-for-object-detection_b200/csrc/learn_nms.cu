@@ -184,7 +184,7 @@ static rn_relation_desc inner_desc(const rn_learn_nms_desc* d) {
 static size_t carve(const rn_learn_nms_desc* d, int Rn, void* base, size_t bytes, LnmsWs* w) {
   const size_t C = d->num_classes - 1, n = d->first_n, K = d->num_reg_classes - 1;
   rn_relation_desc rd = inner_desc(d);
-  const size_t rel = rn_relation_workspace_bytes(&rd);
+  const size_t rel = rn_relation_workspace_bytes(&rd) + relation_tc_lnms_extra_bytes(&rd, d->R);
   size_t need = ws_slice((size_t)Rn * C, 4) + ws_slice((size_t)Rn * 4 * K, 4) + ws_slice(C, 4) +
                 ws_slice(n * kRankDim, 4) + ws_slice(n * kNmsFeat, 4) + ws_slice((size_t)d->R * kNmsFeat, 4) +
                 ws_slice(C * n * kNmsFeat, 4) + ws_slice(C * n * 4, 4) + ws_slice(C * n * kNmsFeat, 4) +
@@ -270,10 +270,10 @@ extern "C" int rn_learn_nms_fwd(const rn_learn_nms_desc* d, const float* cls_sco
     const int ldr = (int)align_up(Rn, 4);
     if ((r = launch_geom_weight_log2(st, W.refined, nullptr, 1, Rn, Rn, 16, 64, 1000.f, w->nms_pair_pos_fc1_1_weight,
                                      w->nms_pair_pos_fc1_1_bias, W.lg_roi, ldr))) return r;
-    GeomGather gg = {W.lg_roi, ldr, Rn, W.rank_idx, C, 1};
-    if ((r = relation_tc_gathered(&rd, W.feat_cls, &gg, w->nms_query_1_weight, w->nms_query_1_bias, w->nms_key_1_weight,
-                                  w->nms_key_1_bias, w->nms_linear_out_1_weight, w->nms_linear_out_1_bias, W.feat_out,
-                                  W.rel_ws, W.rel_ws_bytes, st))) return r;
+    GeomGather gg = {W.lg_roi, ldr, Rn, W.rank_idx, C, 1, nullptr};
+    if ((r = relation_tc_lnms(&rd, W.feat_cls, W.emb, d->R, W.rank_feat, &gg, w->nms_query_1_weight, w->nms_query_1_bias,
+                              w->nms_key_1_weight, w->nms_key_1_bias, w->nms_linear_out_1_weight,
+                              w->nms_linear_out_1_bias, W.feat_out, W.rel_ws, W.rel_ws_bytes, st))) return r;
   } else if ((r = rn_relation_fwd(&rd, W.feat_cls, W.boxes_cls, nullptr, w->nms_query_1_weight, w->nms_query_1_bias,
                            w->nms_key_1_weight, w->nms_key_1_bias, w->nms_pair_pos_fc1_1_weight,
                            w->nms_pair_pos_fc1_1_bias, w->nms_linear_out_1_weight, w->nms_linear_out_1_bias, W.feat_out,

@@ -20,10 +20,16 @@ int relation_tc_packed(const rn_relation_desc* d, const float* X, const float* b
                        const void* packed, const float* Wg, const float* bg, float* out, void* ws, size_t ws_bytes,
                        cudaStream_t st, int stage_mask, const struct GeomGather* gg = nullptr);
 // geometry gathered from one roi-level table lg_table [H, R, ld]: row i of problem b is roi idx[i*stride_i + b*stride_b]
-struct GeomGather { const float* lg_table; int ld; int R; const int* idx; int stride_i; int stride_b; };
+struct GeomGather { const float* lg_table; int ld; int R; const int* idx; int stride_i; int stride_b;
+                    const void* qkv_ext; };   // qkv_ext: optional pre-computed fp16 [B*N, 3*H*64] projections (skips the GEMM)
 int relation_tc_gathered(const rn_relation_desc* d, const float* X, const GeomGather* gg, const float* Wq, const float* bq,
                          const float* Wk, const float* bk, const float* Wout, const float* bout, float* out, void* ws,
                          size_t ws_bytes, cudaStream_t st);
+// learn-NMS: Q/K/V' of row (c, i) = (emb . W^T)[idx[i,c]] + (rank_feat . W^T + b)[i]  -- two small GEMMs + a gather-add
+int relation_tc_lnms(const rn_relation_desc* d, const float* X, const float* emb, int R_emb, const float* rank_feat,
+                     const GeomGather* gg, const float* Wq, const float* bq, const float* Wk, const float* bk,
+                     const float* Wout, const float* bout, float* out, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t relation_tc_lnms_extra_bytes(const rn_relation_desc* d, int R_emb);
 bool relation_tc_shape_ok(const rn_relation_desc* d);
 int launch_geom_weight_log2(cudaStream_t st, const float* boxes, const int* key_index, int B, int N, int M, int H, int E,
                             float wave_length, const float* Wg, const float* bg, float* g, int ldg);

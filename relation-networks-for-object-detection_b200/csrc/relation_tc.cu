@@ -299,13 +299,14 @@ __global__ void __launch_bounds__(160, 2) relation_attn_tile_kernel(const __grid
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTileBar);
   uint64_t* ld_full = bars; uint64_t* s_full = bars + 1; uint64_t* p_full = bars + 2; uint64_t* pv_full = bars + 3;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
-  __shared__ int s_gidx[128];
+  __shared__ int s_gidx[128], s_qidx[128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x / tp.splits, kt = blockIdx.x % tp.splits;
   const int q0 = qt * 128, m0 = kt * 128, h = blockIdx.y, b = blockIdx.z;
   if (p.gidx && threadIdx.x < 128) {
-    const int m = m0 + threadIdx.x;
+    const int m = m0 + threadIdx.x, nq = q0 + threadIdx.x;
     s_gidx[threadIdx.x] = m < p.M ? p.gidx[(size_t)m * p.gs_i + (size_t)b * p.gs_b] : 0;
+    s_qidx[threadIdx.x] = nq < p.N ? p.gidx[(size_t)nq * p.gs_i + (size_t)b * p.gs_b] : 0;
   }
 
   if (warp == 4) {
@@ -352,10 +353,32 @@ __global__ void __launch_bounds__(160, 2) relation_attn_tile_kernel(const __grid
     // the whole geometry row of this tile, issued before the S tile is ready
     float t[128];
     if (p.gidx) {
-      const int ri = p.gidx[(size_t)(row_ok ? n : 0) * p.gs_i + (size_t)b * p.gs_b];
-      const float* lg_row = p.lg + ((size_t)h * p.R + ri) * p.ldg;
+      // gather lg[h][roi(i)][roi(j)]: a warp walks ONE query row at a time (32 lanes = 32 key columns of the same 1.2 KB
+      // table row -> a handful of cache lines per load instead of 32), parks the 128x64 half tile in the (still unused)
+      // P buffer with a 16-byte-chunk XOR swizzle, then every thread pulls its own row back into registers.
+      float* sT = reinterpret_cast<float*>(sP);
 #pragma unroll
-      for (int q = 0; q < 128; ++q) t[q] = (m0 + q < p.M) ? __ldg(lg_row + s_gidx[q]) : -INFINITY;
+      for (int half = 0; half < 2; ++half) {
+#pragma unroll 4
+        for (int rr = 0; rr < 32; ++rr) {
+          const int i = warp * 32 + rr;
+          const float* lg_row = p.lg + ((size_t)h * p.R + s_qidx[i]) * p.ldg;
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int jj = lane + 32 * u, j = half * 64 + jj;
+            const float v = (m0 + j < p.M) ? __ldg(lg_row + s_gidx[j]) : -INFINITY;
+            sT[i * 64 + (((jj >> 2) ^ (i & 15)) << 2) + (jj & 3)] = v;
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+        for (int c4 = 0; c4 < 16; ++c4) {
+          const float4 v = *reinterpret_cast<const float4*>(sT + r * 64 + ((c4 ^ (r & 15)) << 2));
+          t[half * 64 + c4 * 4] = v.x; t[half * 64 + c4 * 4 + 1] = v.y;
+          t[half * 64 + c4 * 4 + 2] = v.z; t[half * 64 + c4 * 4 + 3] = v.w;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
     } else {
       const float* lg_row = p.lg + (((size_t)b * p.H + h) * p.N + (row_ok ? n : 0)) * p.ldg + m0;
 #pragma unroll
@@ -573,9 +596,13 @@ int relation_tc_packed(const rn_relation_desc* d, const float* X, const float* b
   if (!lg || (T > 1 && T <= kMaxTileSplits && !part_ml)) { set_error("rn_relation_fwd(F16): workspace too small (%zu < %zu)", ws_bytes, relation_tc_workspace_bytes(d)); return RN_ERR_WORKSPACE; }
   void* gws = ws.base + ws.off; const size_t gws_bytes = ws.size - ws.off;
   int r;
-  if (do_proj && (r = cast_rows_f16(st, X, x16, B * N, D, d8))) return r;
+  const bool ext_qkv = gg && gg->qkv_ext;
+  if (do_proj && !ext_qkv && (r = cast_rows_f16(st, X, x16, B * N, D, d8))) return r;
   const __half *Qp, *Kp, *Vp; long long ldq, ldk; long long bq_pitch, bk_pitch;
-  if (key_index) {
+  if (ext_qkv) {
+    const __half* e = (const __half*)gg->qkv_ext;
+    Qp = e; Kp = e + H * 64; Vp = e + 2 * H * 64; ldq = ldk = W3; bq_pitch = bk_pitch = (long long)N * W3;
+  } else if (key_index) {
     if (do_proj) {
       gather_rows_f16_kernel<<<dim3(M, B), 128, 0, st>>>(x16, key_index, N, M, d8, xk16);
       RN_LAUNCH_CHECK();
@@ -659,4 +686,68 @@ int relation_tc_gathered(const rn_relation_desc* d, const float* X, const GeomGa
   return relation_tc_packed(d, X, nullptr, nullptr, wsp, nullptr, nullptr, out, (char*)wsp + pk, ws_bytes - pk, st, 7, gg);
 }
 bool relation_tc_shape_ok(const rn_relation_desc* d) { return tc_shape_ok(d); }
+
+// qkv16[(b*n + i), :] = fp16(E[idx[i*gs_i + b*gs_b], :] + Rk[i, :]);  8 columns per thread
+__global__ void __launch_bounds__(256) lnms_gather_add_qkv_kernel(const float* __restrict__ E, const float* __restrict__ Rk,
+                                                                  const int* __restrict__ idx, int gs_i, int gs_b, int B,
+                                                                  int n, int W3, __half* __restrict__ out) {
+  const int vec = W3 / 8;
+  const size_t total = (size_t)B * n * vec;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int v = t % vec;
+    const size_t row = t / vec;
+    const int i = row % n, b = row / n;
+    const float4* e = reinterpret_cast<const float4*>(E + (size_t)idx[(size_t)i * gs_i + (size_t)b * gs_b] * W3) + 2 * v;
+    const float4* rk = reinterpret_cast<const float4*>(Rk + (size_t)i * W3) + 2 * v;
+    const float4 e0 = __ldg(e), e1 = __ldg(e + 1), r0 = __ldg(rk), r1 = __ldg(rk + 1);
+    __half2 h0 = __floats2half2_rn(e0.x + r0.x, e0.y + r0.y), h1 = __floats2half2_rn(e0.z + r0.z, e0.w + r0.w);
+    __half2 h2 = __floats2half2_rn(e1.x + r1.x, e1.y + r1.y), h3 = __floats2half2_rn(e1.z + r1.z, e1.w + r1.w);
+    uint4 u;
+    u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+    u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+    reinterpret_cast<uint4*>(out + row * W3)[v] = u;
+  }
+}
+
+size_t relation_tc_lnms_extra_bytes(const rn_relation_desc* d, int R_emb) {
+  const size_t W3 = 3 * (size_t)d->H * 64, d8 = align_up(d->d, 8);
+  return ws_slice((size_t)R_emb * d8, 2) + ws_slice((size_t)d->N * d8, 2) + ws_slice((size_t)R_emb * W3, 4) +
+         ws_slice((size_t)d->N * W3, 4) + ws_slice((size_t)d->batch * d->N * W3, 2) + 1024;
+}
+
+int relation_tc_lnms(const rn_relation_desc* d, const float* X, const float* emb, int R_emb, const float* rank_feat,
+                     const GeomGather* gg, const float* Wq, const float* bq, const float* Wk, const float* bk,
+                     const float* Wout, const float* bout, float* out, void* wsp, size_t ws_bytes, cudaStream_t st) {
+  const size_t pk = relation_tc_packed_bytes(d);
+  RN_CHECK_ARG(pk > 0 && gg && gg->idx, "relation_tc_lnms: unsupported shape");
+  const int B = d->batch, n = d->N, D = d->d, H = d->H, d8 = (int)align_up(D, 8), W3 = 3 * H * 64;
+  Workspace ws(wsp, ws_bytes);
+  char* packed = ws.take<char>(pk);
+  __half* emb16 = ws.take<__half>((size_t)R_emb * d8);
+  __half* rank16 = ws.take<__half>((size_t)n * d8);
+  float* E = ws.take<float>((size_t)R_emb * W3);
+  float* Rk = ws.take<float>((size_t)n * W3);
+  __half* qkv = ws.take<__half>((size_t)B * n * W3);
+  if (!qkv) { set_error("relation_tc_lnms: workspace too small"); return RN_ERR_WORKSPACE; }
+  int r;
+  if ((r = relation_tc_pack(d, Wq, bq, Wk, bk, Wout, bout, packed, st))) return r;
+  const __half* w16 = (const __half*)packed;
+  const float* bias = (const float*)(packed + ws_slice((size_t)W3 * d8, 2));
+  if ((r = cast_rows_f16(st, emb, emb16, R_emb, D, d8))) return r;
+  if ((r = cast_rows_f16(st, rank_feat, rank16, n, D, d8))) return r;
+  void* gws = ws.base + ws.off; const size_t gws_bytes = ws.size - ws.off;
+  if ((r = gemm_tc(st, emb16, d8, w16, d8, R_emb, W3, d8, nullptr, 0, 0, E, W3, nullptr, 0, gws, gws_bytes))) return r;
+  if ((r = gemm_tc(st, rank16, d8, w16, d8, n, W3, d8, bias, 0, 0, Rk, W3, nullptr, 0, gws, gws_bytes))) return r;
+  {
+    const size_t total = (size_t)B * n * (W3 / 8);
+    size_t blocks = (total + 255) / 256;
+    const size_t cap = (size_t)(sm_count() > 0 ? sm_count() : 148) * 16;
+    lnms_gather_add_qkv_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(E, Rk, gg->idx, gg->stride_i,
+                                                                                  gg->stride_b, B, n, W3, qkv);
+    RN_LAUNCH_CHECK();
+  }
+  GeomGather g2 = *gg;
+  g2.qkv_ext = qkv;
+  return relation_tc_packed(d, X, nullptr, nullptr, packed, nullptr, nullptr, out, gws, gws_bytes, st, 7, &g2);
+}
 }  // namespace rn

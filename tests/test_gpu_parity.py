@@ -342,7 +342,14 @@ def test_hot_path_pipeline_matches_oracle(ops):
         e_feat = rel_err(out['fc_all_2_relu'].cpu().numpy(), ref['fc_all_2_relu'])
         e_cls = rel_err(out['cls_score'].cpu().numpy(), ref['cls_score'])
         e_ss = rel_err(out['sorted_score'].cpu().numpy(), ref['sorted_score'])
-        e_fin = rel_err(out['nms_final_score_output'].cpu().numpy(), ref['nms_final_score_output'])
+        fin, rfin = out['nms_final_score_output'].cpu().numpy(), ref['nms_final_score_output']
+        if prec == 'fp32':
+            e_fin = rel_err(fin, rfin)
+        else:
+            # near-tied class scores may swap ranks between fp16 and fp32 pipelines (the head is random-init: 300 rois
+            # with almost equal scores per class), which permutes rows of the learn-NMS output -- compare per class
+            # as sorted multisets, which is invariant to such swaps
+            e_fin = rel_err(np.sort(fin, axis=0), np.sort(rfin, axis=0))
         print('pipeline[%s]: fc_all_2 %.2e cls_score %.2e sorted_score %.2e final %.2e' % (prec, e_feat, e_cls, e_ss, e_fin))
         tol = 3e-4 if prec == 'fp32' else 3e-3          # two relation modules + 4 fp16 GEMMs (K up to 12544) in sequence
         assert e_feat < tol and e_cls < tol and e_ss < tol and e_fin < 2 * tol
