@@ -260,12 +260,9 @@ def main():
     out_pin = {'b': torch.empty((100, 80, 4), dtype=torch.float32).pin_memory(),
                's': torch.empty((100, 80), dtype=torch.float32).pin_memory()}
 
-    from relnet_b200.pipeline import GraphedStep
+    from relnet_b200.pipeline import GraphedStep, Detector
 
-    def full_step(img32):                       # fp32 NCHW image -> detections (cast + trunk + hot path)
-        img = img32.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-        prob, bbox, feat = trunk(img)
-        return head.forward(prob, bbox, feat, im_info)
+    full_step = Detector(trunk, head, im_info)   # fp32 NCHW image -> detections; proposal chain || res5 on two streams
 
     image32_d = image_h.to(device)
     eager_ms = timed(lambda: full_step(image32_d), max(5, args.steps // 2), 3, dist_on)    # un-graphed, for reference

@@ -104,7 +104,8 @@ __global__ void __launch_bounds__(128) geom_weight_mma_kernel(const float* __res
                                                               const int* __restrict__ key_index, int B, int N, int M,
                                                               int H, GeomFreq fr, const float* __restrict__ Wg,
                                                               const float* __restrict__ bg, float* __restrict__ out,
-                                                              int ldg, int log2_out) {
+                                                              int ldg, int log2_out, int swap_roles) {
+  // swap_roles: out[h][n][m] = weight(query = m, key = n), i.e. the transposed table, still written with m contiguous
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, q = lane & 3;
   // B fragments of Wg^T: element (k, col) = Wg[nh*8 + col][c*16 + k]; this lane holds col = g, k = 2q,2q+1 | 2q+8,2q+9
@@ -143,13 +144,14 @@ __global__ void __launch_bounds__(128) geom_weight_mma_kernel(const float* __res
     for (int rr = 0; rr < 2; ++rr) {
       const int m = min(m0 + g + 8 * rr, M - 1);
       const int mi = key_index ? key_index[m] : m;
-      const float4 bm = reinterpret_cast<const float4*>(boxes)[(size_t)b * N + mi];
+      const float4 bm_ = reinterpret_cast<const float4*>(boxes)[(size_t)b * N + mi];
+      const float4 bq = swap_roles ? bm_ : bn, bm = swap_roles ? bn : bm_;       // bq = query box, bm = key box
       if (EXACT) {
-        pair_eps(bn, bm, eps[rr]);
+        pair_eps(bq, bm, eps[rr]);
       } else {
-        const float wn = bn.z - bn.x + 1.f, hn = bn.w - bn.y + 1.f;
+        const float wn = bq.z - bq.x + 1.f, hn = bq.w - bq.y + 1.f;
         const float wm = bm.z - bm.x + 1.f, hm = bm.w - bm.y + 1.f;
-        const float dcx = 0.5f * (bn.x + bn.z) - 0.5f * (bm.x + bm.z), dcy = 0.5f * (bn.y + bn.w) - 0.5f * (bm.y + bm.w);
+        const float dcx = 0.5f * (bq.x + bq.z) - 0.5f * (bm.x + bm.z), dcy = 0.5f * (bq.y + bq.w) - 0.5f * (bm.y + bm.w);
         eps[rr][0] = __logf(fmaxf(fabsf(dcx * __frcp_rn(wn)), 1e-3f));
         eps[rr][1] = __logf(fmaxf(fabsf(dcy * __frcp_rn(hn)), 1e-3f));
         eps[rr][2] = __logf(wn * __frcp_rn(wm));
@@ -228,7 +230,7 @@ int make_freq(int E, float wave_length, GeomFreq* fr) {
 
 static int launch_geom_weight_impl(cudaStream_t st, const float* boxes, const int* key_index, int B, int N, int M, int H,
                                    int E, float wave_length, const float* Wg, const float* bg, float* g, int ldg,
-                                   int log2_out);
+                                   int log2_out, int swap_roles = 0);
 
 int launch_geom_weight(cudaStream_t st, const float* boxes, const int* key_index, int B, int N, int M, int H, int E,
                        float wave_length, const float* Wg, const float* bg, float* g, int ldg) {
@@ -241,9 +243,16 @@ int launch_geom_weight_log2(cudaStream_t st, const float* boxes, const int* key_
   return launch_geom_weight_impl(st, boxes, key_index, B, N, M, H, E, wave_length, Wg, bg, g, ldg, 1);
 }
 
+// transposed log2 table over one box set (N == M, no key_index): g[h][key][query]
+int launch_geom_weight_log2_T(cudaStream_t st, const float* boxes, int N, int H, int E, float wave_length, const float* Wg,
+                              const float* bg, float* g, int ldg) {
+  RN_CHECK_ARG(E == 64, "transposed geometry table needs E == 64");
+  return launch_geom_weight_impl(st, boxes, nullptr, 1, N, N, H, E, wave_length, Wg, bg, g, ldg, 1, 1);
+}
+
 static int launch_geom_weight_impl(cudaStream_t st, const float* boxes, const int* key_index, int B, int N, int M, int H,
                                    int E, float wave_length, const float* Wg, const float* bg, float* g, int ldg,
-                                   int log2_out) {
+                                   int log2_out, int swap_roles) {
   GeomFreq fr;
   int r = make_freq(E, wave_length, &fr);
   if (r) return r;
@@ -255,11 +264,11 @@ static int launch_geom_weight_impl(cudaStream_t st, const float* boxes, const in
     const int grid = (int)std::min<long long>((items + 3) / 4, (long long)sms * 8);
     const bool exact = !log2_out;               // fp32 parity mode asks for g, the tcgen05 path for log2 g
     if (H <= 8) {
-      if (exact) geom_weight_mma_kernel<1, true><<<grid, 128, 0, st>>>(boxes, key_index, B, N, M, H, fr, Wg, bg, g, ldg, log2_out);
-      else geom_weight_mma_kernel<1, false><<<grid, 128, 0, st>>>(boxes, key_index, B, N, M, H, fr, Wg, bg, g, ldg, log2_out);
+      if (exact) geom_weight_mma_kernel<1, true><<<grid, 128, 0, st>>>(boxes, key_index, B, N, M, H, fr, Wg, bg, g, ldg, log2_out, swap_roles);
+      else geom_weight_mma_kernel<1, false><<<grid, 128, 0, st>>>(boxes, key_index, B, N, M, H, fr, Wg, bg, g, ldg, log2_out, swap_roles);
     } else {
-      if (exact) geom_weight_mma_kernel<2, true><<<grid, 128, 0, st>>>(boxes, key_index, B, N, M, H, fr, Wg, bg, g, ldg, log2_out);
-      else geom_weight_mma_kernel<2, false><<<grid, 128, 0, st>>>(boxes, key_index, B, N, M, H, fr, Wg, bg, g, ldg, log2_out);
+      if (exact) geom_weight_mma_kernel<2, true><<<grid, 128, 0, st>>>(boxes, key_index, B, N, M, H, fr, Wg, bg, g, ldg, log2_out, swap_roles);
+      else geom_weight_mma_kernel<2, false><<<grid, 128, 0, st>>>(boxes, key_index, B, N, M, H, fr, Wg, bg, g, ldg, log2_out, swap_roles);
     }
     RN_LAUNCH_CHECK();
     return RN_OK;

@@ -268,8 +268,8 @@ extern "C" int rn_learn_nms_fwd(const rn_learn_nms_desc* d, const float* cls_sco
     // class-agnostic boxes: every class sorts the SAME refined rois, so the per-class pair geometry is a gather from
     // one [16, Rn, Rn] table (LNMS:332 builds [C, n, n, 4] position matrices -- 9x the pairs at C = 80, n = 100)
     const int ldr = (int)align_up(Rn, 4);
-    if ((r = launch_geom_weight_log2(st, W.refined, nullptr, 1, Rn, Rn, 16, 64, 1000.f, w->nms_pair_pos_fc1_1_weight,
-                                     w->nms_pair_pos_fc1_1_bias, W.lg_roi, ldr))) return r;
+    if ((r = launch_geom_weight_log2_T(st, W.refined, Rn, 16, 64, 1000.f, w->nms_pair_pos_fc1_1_weight,
+                                       w->nms_pair_pos_fc1_1_bias, W.lg_roi, ldr))) return r;
     GeomGather gg = {W.lg_roi, ldr, Rn, W.rank_idx, C, 1, nullptr};
     if ((r = relation_tc_lnms(&rd, W.feat_cls, W.emb, d->R, W.rank_feat, &gg, w->nms_query_1_weight, w->nms_query_1_bias,
                               w->nms_key_1_weight, w->nms_key_1_bias, w->nms_linear_out_1_weight,

@@ -31,6 +31,8 @@ int relation_tc_lnms(const rn_relation_desc* d, const float* X, const float* emb
                      const float* Wout, const float* bout, float* out, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t relation_tc_lnms_extra_bytes(const rn_relation_desc* d, int R_emb);
 bool relation_tc_shape_ok(const rn_relation_desc* d);
+int launch_geom_weight_log2_T(cudaStream_t st, const float* boxes, int N, int H, int E, float wave_length, const float* Wg,
+                              const float* bg, float* g, int ldg);
 int launch_geom_weight_log2(cudaStream_t st, const float* boxes, const int* key_index, int B, int N, int M, int H, int E,
                             float wave_length, const float* Wg, const float* bg, float* g, int ldg);
 

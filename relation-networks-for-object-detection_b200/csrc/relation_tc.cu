@@ -38,8 +38,9 @@ struct AttnParams {
   int dv;                         // valid output columns per head (<= 64)
   int relu;
   float scale_log2;               // log2(e)/sqrt(dk)
-  // optional gather mode (learn-NMS with class-agnostic boxes): lg is ONE table [H, R, ldg] over the image's rois and
-  // row i of problem b is roi gidx[i*gs_i + b*gs_b] -- the per-class geometry is a gather, not 80 recomputations
+  // optional gather mode (learn-NMS with class-agnostic boxes): lg is ONE table over the image's rois, stored TRANSPOSED
+  // [H, key roi, query roi]; row i of problem b is roi gidx[i*gs_i + b*gs_b] -- the per-class geometry is a gather, not
+  // 80 recomputations
   const int* gidx; int gs_i, gs_b; int R;
 };
 
@@ -353,32 +354,13 @@ __global__ void __launch_bounds__(160, 2) relation_attn_tile_kernel(const __grid
     // the whole geometry row of this tile, issued before the S tile is ready
     float t[128];
     if (p.gidx) {
-      // gather lg[h][roi(i)][roi(j)]: a warp walks ONE query row at a time (32 lanes = 32 key columns of the same 1.2 KB
-      // table row -> a handful of cache lines per load instead of 32), parks the 128x64 half tile in the (still unused)
-      // P buffer with a 16-byte-chunk XOR swizzle, then every thread pulls its own row back into registers.
-      float* sT = reinterpret_cast<float*>(sP);
+      // gather from the TRANSPOSED roi-level table lgT[h][key roi][query roi]: for a given key column every lane of the
+      // warp reads the same 1.2 KB table row (at its own query offset) -> a few cache lines per load instruction, and all
+      // 128 loads of the thread are in flight at once
+      const int ri = s_qidx[r];
+      const float* col0 = p.lg + (size_t)h * p.R * p.ldg + ri;
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-#pragma unroll 4
-        for (int rr = 0; rr < 32; ++rr) {
-          const int i = warp * 32 + rr;
-          const float* lg_row = p.lg + ((size_t)h * p.R + s_qidx[i]) * p.ldg;
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int jj = lane + 32 * u, j = half * 64 + jj;
-            const float v = (m0 + j < p.M) ? __ldg(lg_row + s_gidx[j]) : -INFINITY;
-            sT[i * 64 + (((jj >> 2) ^ (i & 15)) << 2) + (jj & 3)] = v;
-          }
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-#pragma unroll
-        for (int c4 = 0; c4 < 16; ++c4) {
-          const float4 v = *reinterpret_cast<const float4*>(sT + r * 64 + ((c4 ^ (r & 15)) << 2));
-          t[half * 64 + c4 * 4] = v.x; t[half * 64 + c4 * 4 + 1] = v.y;
-          t[half * 64 + c4 * 4 + 2] = v.z; t[half * 64 + c4 * 4 + 3] = v.w;
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-      }
+      for (int q = 0; q < 128; ++q) t[q] = (m0 + q < p.M) ? __ldg(col0 + (size_t)s_gidx[q] * p.ldg) : -INFINITY;
     } else {
       const float* lg_row = p.lg + (((size_t)b * p.H + h) * p.N + (row_ok ? n : 0)) * p.ldg + m0;
 #pragma unroll

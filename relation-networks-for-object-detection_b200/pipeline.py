@@ -81,8 +81,13 @@ class RelationHead(object):
                             residual_relu=True, precision=self.precision)
 
     def forward(self, rpn_cls_prob, rpn_bbox_pred, conv_feat, im_info):
+        return self.detect(self.propose(rpn_cls_prob, rpn_bbox_pred, im_info), conv_feat, im_info)
+
+    def propose(self, rpn_cls_prob, rpn_bbox_pred, im_info):
+        return ops.proposal(rpn_cls_prob, rpn_bbox_pred, im_info, **self.cfg)[0]                  # SYM_REL_NMS:324-329
+
+    def detect(self, rois, conv_feat, im_info):
         P, prec = self.P, self.precision
-        rois, _ = ops.proposal(rpn_cls_prob, rpn_bbox_pred, im_info, **self.cfg)                  # SYM_REL_NMS:324-329
         boxes = rois[:, 1:].contiguous()                                                          # :337
         if prec == 'f16':        # :335 + :344 at the layout level: channels-last pool -> fp16 -> K-permuted fc_new_1
             fc1 = ops.roi_pool_fc(conv_feat, rois, P['fc_new_1_weight'], P['fc_new_1_bias'], (7, 7),
@@ -101,6 +106,30 @@ class RelationHead(object):
         return dict(rois=rois, cls_score=cls_score, bbox_pred=bbox_pred, fc_all_2_relu=fc_all_2,
                     nms_multi_score=multi, learn_nms_sorted_bbox=sorted_bbox, sorted_score=sorted_score,
                     nms_final_score_output=final)
+
+
+class Detector(object):
+    """trunk + hot path for one image with the two independent branches of the graph on two streams: the RPN heads and
+    the whole `proposal` chain (decode, sort, NMS: mostly one-SM latency-bound kernels) run beside res5 + conv_new_1
+    (SYM_REL_NMS:271-332: both only read conv4).  Captured by GraphedStep the fork/join becomes graph edges."""
+
+    def __init__(self, trunk, head, im_info):
+        self.trunk, self.head, self.im_info = trunk, head, im_info
+        self.side = torch.cuda.Stream()
+
+    def __call__(self, image32):
+        main = torch.cuda.current_stream()
+        img = image32.to(next(self.trunk.parameters()).dtype).contiguous(memory_format=torch.channels_last)
+        c4 = self.trunk.c4(img)
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side):
+            prob, bbox = self.trunk.rpn(c4)
+            rois = self.head.propose(prob, bbox, self.im_info)
+        c4.record_stream(self.side)
+        feat = self.trunk.c5feat(c4)
+        main.wait_stream(self.side)
+        rois.record_stream(main)
+        return self.head.detect(rois, feat, self.im_info)
 
 
 class GraphedStep(object):

@@ -67,19 +67,31 @@ class Trunk(nn.Module):
         self.conv_new_1.weight.data.div_(F.relu(self.conv_new_1(c5)).float().std().clamp_min(1e-6))
 
     @torch.no_grad()
-    def forward(self, image):
-        """image [1,3,H,W] -> (rpn_cls_prob [1,2A,h,w] fp32, rpn_bbox_pred [1,4A,h,w] fp32, conv_new_1_relu [1,256,h,w] fp32)"""
-        x = F.relu(self.conv1(image))
-        x = F.max_pool2d(x, 3, 2, ceil_mode=True)
-        c4 = self.res4(self.res3(self.res2(x)))
-        c5 = self.res5(c4)
+    def c4(self, image):
+        """conv1 .. res4: the stride-16 feature both the RPN and res5 read"""
+        x = F.max_pool2d(F.relu(self.conv1(image)), 3, 2, ceil_mode=True)
+        return self.res4(self.res3(self.res2(x)))
+
+    @torch.no_grad()
+    def rpn(self, c4):
+        """-> rpn_cls_prob [1,2A,h,w] fp32, rpn_bbox_pred [1,4A,h,w] fp32 (SYM_BASE:685-693 + softmax over {bg, fg})"""
         r = F.relu(self.rpn_conv(c4))
         score = self.rpn_cls(r).float()
         b, _, h, w = score.shape
         prob = F.softmax(score.reshape(b, 2, self.A * h, w), dim=1).reshape(b, 2 * self.A, h, w)
-        bbox = self.rpn_bbox(r).float()
-        feat = F.relu(self.conv_new_1(c5)).float()
-        return prob.contiguous(), bbox.contiguous(), feat          # feat stays channels-last (consumed as NHWC)
+        return prob.contiguous(), self.rpn_bbox(r).float().contiguous()
+
+    @torch.no_grad()
+    def c5feat(self, c4):
+        """res5 (dilated) + conv_new_1 + relu -> [1,256,h,w] fp32, left channels-last (consumed as NHWC)"""
+        return F.relu(self.conv_new_1(self.res5(c4))).float()
+
+    @torch.no_grad()
+    def forward(self, image):
+        """image [1,3,H,W] -> (rpn_cls_prob, rpn_bbox_pred, conv_new_1_relu)"""
+        c4 = self.c4(image)
+        prob, bbox = self.rpn(c4)
+        return prob, bbox, self.c5feat(c4)
 
 
 def make_trunk(device, dtype=torch.bfloat16, seed=0):
