@@ -7,6 +7,7 @@
 // never materialises col is listed under "next" in DESIGN.md).
 // Roofline: GEMM 2*Co*C*kh*kw*Ho*Wo FLOP (11.3 GFLOP/layer) on the tensor pipe; im2col is HBM-write bound (4*C*kh*kw*Ho*Wo B).
 #include "common.cuh"
+#include "gemm_tc.cuh"
 
 namespace rn {
 
@@ -50,6 +51,35 @@ __global__ void __launch_bounds__(256) deform_im2col_kernel(size_t n, const floa
   }
 }
 
+// RN_PREC_F16 form: the column buffer is written TRANSPOSED and in fp16, colT[pos][c*kh*kw + k] (K contiguous), which
+// is exactly the K-major B operand of the tcgen05 GEMM  out[Co, pos] = W16[Co, K] . colT[pos, K]^T  -- half the bytes of
+// the fp32 col buffer and no SGEMM.  Same bilinear arithmetic as above, rounded to fp16 at the store.
+__global__ void __launch_bounds__(256) deform_im2col_t_f16_kernel(size_t n, const float* __restrict__ im,
+                                                                  const float* __restrict__ off, int H, int W, int kh,
+                                                                  int kw, int pad_h, int pad_w, int sh, int sw, int dil_h,
+                                                                  int dil_w, int cpg, int Ho, int Wo, int C, int ldk,
+                                                                  __half* __restrict__ colT) {
+  for (size_t index = (size_t)blockIdx.x * blockDim.x + threadIdx.x; index < n; index += (size_t)gridDim.x * blockDim.x) {
+    const int c_im = index % C;                         // channel fastest: consecutive threads write 2*kh*kw B apart
+    const int pos = index / C, w_col = pos % Wo, h_col = pos / Wo;
+    const int g = c_im / cpg;
+    const int h_in = h_col * sh - pad_h, w_in = w_col * sw - pad_w;
+    const float* im_ptr = im + ((ptrdiff_t)c_im * H + h_in) * W + w_in;
+    const float* off_ptr = off + (size_t)g * 2 * kh * kw * Ho * Wo;
+    __half* dst = colT + (size_t)pos * ldk + (size_t)c_im * kh * kw;
+    for (int i = 0; i < kh; ++i)
+      for (int j = 0; j < kw; ++j) {
+        const float oh = __ldg(off_ptr + ((size_t)(2 * (i * kw + j)) * Ho + h_col) * Wo + w_col);
+        const float ow = __ldg(off_ptr + ((size_t)(2 * (i * kw + j) + 1) * Ho + h_col) * Wo + w_col);
+        float val = 0.f;
+        const float h_im = h_in + i * dil_h + oh, w_im = w_in + j * dil_w + ow;
+        if (h_im >= 0 && w_im >= 0 && h_im < H && w_im < W)
+          val = dim2col_bilinear(im_ptr, W, H - h_in, W - w_in, i * dil_h + oh, j * dil_w + ow);
+        dst[i * kw + j] = __float2half_rn(val);
+      }
+  }
+}
+
 __global__ void add_channel_bias_kernel(float* __restrict__ y, const float* __restrict__ bias, int Co, size_t spatial) {
   size_t total = (size_t)Co * spatial;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
@@ -86,7 +116,11 @@ static int launch_im2col(const rn_deform_conv_desc* d, const float* im, const fl
 extern "C" size_t rn_deform_conv_workspace_bytes(const rn_deform_conv_desc* d) {
   if (!d) return 0;
   int Ho, Wo; rn::out_hw(d, &Ho, &Wo);
-  return rn::ws_slice((size_t)d->C * d->kh * d->kw * Ho * Wo, 4) + 256;
+  const size_t K = (size_t)d->C * d->kh * d->kw, K8 = rn::align_up(K / d->num_group, 8);
+  const size_t f32 = rn::ws_slice(K * Ho * Wo, 4);
+  const size_t f16 = rn::ws_slice((size_t)Ho * Wo * K8, 2) + rn::ws_slice((size_t)d->Co * K8, 2) +
+                     rn::gemm_tc_workspace_bytes(d->Co / d->num_group, Ho * Wo, (int)K8) + 512;
+  return (f32 > f16 ? f32 : f16) + 256;
 }
 
 extern "C" int rn_deform_im2col(const rn_deform_conv_desc* d, const float* data_b, const float* offset_b, float* col,
@@ -106,6 +140,29 @@ extern "C" int rn_deform_conv_fwd(const rn_deform_conv_desc* d, const float* dat
   cudaStream_t st = (cudaStream_t)stream;
   int Ho, Wo; rn::out_hw(d, &Ho, &Wo);
   const int K = d->C * d->kh * d->kw, Nsp = Ho * Wo, G = d->num_group;
+  if (d->precision == RN_PREC_F16 && G == 1 && rn::is_sm100()) {
+    // tensor-core path: fp16 transposed column buffer + tcgen05 GEMM (fp32 accumulate, fp32 output)
+    const int K8 = (int)rn::align_up(K, 8);
+    rn::Workspace w2(wsp, ws_bytes);
+    __half* colT = w2.take<__half>((size_t)Nsp * K8);
+    __half* w16 = w2.take<__half>((size_t)d->Co * K8);
+    if (!w16) { rn::set_error("rn_deform_conv_fwd(F16): workspace too small"); return RN_ERR_WORKSPACE; }
+    if ((r = rn::cast_rows_f16(st, weight, w16, d->Co, K, K8))) return r;
+    if (K8 != K) RN_CUDA(cudaMemsetAsync(colT, 0, (size_t)Nsp * K8 * 2, st));
+    const size_t off_per16 = (size_t)d->num_deformable_group * 2 * d->kh * d->kw * Nsp;
+    for (int b = 0; b < d->B; ++b) {
+      const size_t n = (size_t)d->C * Nsp;
+      size_t blocks = (n + 255) / 256, cap = (size_t)(rn::sm_count() > 0 ? rn::sm_count() : 148) * 16;
+      rn::deform_im2col_t_f16_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(
+          n, data + (size_t)b * d->C * d->H * d->W, offset + b * off_per16, d->H, d->W, d->kh, d->kw, d->pad_h, d->pad_w,
+          d->stride_h, d->stride_w, d->dil_h, d->dil_w, d->C / d->num_deformable_group, Ho, Wo, d->C, K8, colT);
+      RN_LAUNCH_CHECK();
+      float* ob = out + (size_t)b * d->Co * Nsp;
+      if ((r = rn::gemm_tc(st, w16, K8, colT, K8, d->Co, Nsp, K8, bias, 1, 0, ob, Nsp, nullptr, 0, w2.base + w2.off,
+                           w2.size - w2.off))) return r;
+    }
+    return RN_OK;
+  }
   rn::Workspace ws(wsp, ws_bytes);
   float* col = ws.take<float>((size_t)K * Nsp);
   if (!col) { rn::set_error("rn_deform_conv_fwd: workspace too small"); return RN_ERR_WORKSPACE; }

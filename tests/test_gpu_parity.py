@@ -305,6 +305,9 @@ def test_deform_conv_matches_oracle(ops):
     np.testing.assert_array_equal(col, RO.deform_im2col(data[0], off[0]))
     out = ops.deform_conv(T(data), T(off), T(wgt)).cpu().numpy()
     assert rel_err(out, RO.deform_conv(data, off, wgt)) < 1e-5
+    if ops.device_info()['sm100']:      # tensor-core form: fp16 transposed col buffer + tcgen05 GEMM
+        out16 = ops.deform_conv(T(data), T(off), T(wgt), precision='f16').cpu().numpy()
+        assert rel_err(out16, RO.deform_conv(data, off, wgt)) < 2e-3
     # zero offsets == plain dilated convolution
     out0 = ops.deform_conv(T(data), T(off * 0), T(wgt))
     torch.backends.cudnn.allow_tf32 = False
