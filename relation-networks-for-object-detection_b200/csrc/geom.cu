@@ -10,6 +10,10 @@
 
 namespace rn {
 
+int launch_geom_weight_tc(cudaStream_t st, const float* boxes, const int* key_index, int B, int N, int M, int H,
+                          const GeomFreq& fr, const float* Wg, const float* bg, float* g, int ldg, int log2_out,
+                          int swap_roles, bool exact);
+
 // one thread = one (query n, key m) pair; one block = 128 keys of one query row
 template <int MAXH>
 __global__ void __launch_bounds__(128) geom_weight_kernel(const float* __restrict__ boxes, const int* __restrict__ key_index,
@@ -257,8 +261,10 @@ static int launch_geom_weight_impl(cudaStream_t st, const float* boxes, const in
   int r = make_freq(E, wave_length, &fr);
   if (r) return r;
   RN_CHECK_ARG(H >= 1 && H <= 16, "geometry heads H=%d unsupported (1..16)", H);
+  if (E == 64 && is_sm100())      // sm_100a: pair FC on tcgen05 (geom_tc.cu)
+    return launch_geom_weight_tc(st, boxes, key_index, B, N, M, H, fr, Wg, bg, g, ldg, log2_out, swap_roles, !log2_out);
   if (E == 64) {
-    // tensor-core FC path: 16 pairs per warp-tile; pick tiles/warp so that one CTA (4 warps) covers <= M keys of a row
+    // mma.sync FC path: 16 pairs per warp-tile
     const long long items = (long long)B * N * cdiv(M, 16);
     const int sms = sm_count() > 0 ? sm_count() : 148;
     const int grid = (int)std::min<long long>((items + 3) / 4, (long long)sms * 8);
