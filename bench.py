@@ -175,8 +175,22 @@ def relation_kernel_roofline(ops, pk, device):
                 note='N=M=300,d=1024,H=16: 0.37 GFLOP is launch-latency sized (SURVEY 7); sweep in profiles/'), times
 
 
+def cpu_threads():
+    """Host threads for the CPU arm: 16 was the fastest of {8,16,32,64,128} for the torch-CPU trunk on the 128-core B200
+    host (128 threads: 30 s/image from oversubscription; tools/cpu_threads_probe.py), and OpenBLAS behaves alike."""
+    n = min(16, os.cpu_count() or 1)
+    torch.set_num_threads(n)
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=n)
+    except Exception:
+        pass
+    return n
+
+
 def cpu_baseline(steps=1):
     from oracle import pipeline_np, proposal_np as P
+    ncores = cpu_threads()
     from relnet_b200.pipeline import init_head_params
     prm = {k: v.numpy() for k, v in init_head_params(0, 'cpu').items()}
     cls_prob, bbox_pred, info = P.make_proposal_case(0)
@@ -185,7 +199,7 @@ def cpu_baseline(steps=1):
     for _ in range(steps):
         pipeline_np.head_forward(prm, cls_prob, bbox_pred, feat, info)
     dt = (time.perf_counter() - t0) / steps
-    return dict(value=round(1.0 / dt, 4), unit='images/sec', cores=os.cpu_count(), kind='port',
+    return dict(value=round(1.0 / dt, 4), unit='images/sec', cores=ncores, kind='port',
                 sample='hot path only (proposal..learn_nms) of %d image(s), numpy float32 + C oracle; trunk excluded' % steps,
                 seconds_per_image=round(dt, 3))
 
@@ -198,7 +212,7 @@ def run_reference(args):
     from oracle import pipeline_np
     from relnet_b200.pipeline import init_head_params
     from relnet_b200.trunk import make_trunk
-    torch.set_num_threads(os.cpu_count() or 1)
+    ncores = cpu_threads()
     trunk = make_trunk('cpu', torch.float32)
     prm = {k: v.numpy() for k, v in init_head_params(0, 'cpu').items()}
     image, im_info = make_inputs()
@@ -220,7 +234,7 @@ def run_reference(args):
         'warmup': warm, 'ms_per_step': round(dt * 1e3, 2), 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'global_batch': 1, 'parallelism': 'cpu'},
-        'cpu_baseline': {'value': v, 'unit': 'images/sec', 'cores': os.cpu_count(), 'kind': 'port', 'sample': sample},
+        'cpu_baseline': {'value': v, 'unit': 'images/sec', 'cores': ncores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': v, 'unit': 'images/sec', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
 
 

@@ -1,9 +1,9 @@
 // geom_tc.cu -- geometry weight with the 64 -> H pair FC on tcgen05 (sm_100a), E = 64.
 //
-// One thread owns one (query, key) pair: it evaluates eps, the 32 sin/cos pairs of the embedding, splits every value into
-// fp16 hi + lo and writes its 64-wide row of the A operand (128 pairs x 64, SWIZZLE_128B K-major) straight into shared
-// memory.  One elected thread then issues 12 UMMAs (M=128, N=16, K=16: A_hi.W_hi + A_lo.W_hi + A_hi.W_lo over 4 K-steps)
-// into a 16-column TMEM accumulator, every thread reads its pair's 16 head values back with one tcgen05.ld, applies
+// A CTA of 512 threads owns 128 (query, key) pairs, 4 threads per pair (one per box coordinate): each evaluates its eps,
+// the 8 sin/cos pairs of that coordinate, splits every value into fp16 hi + lo and writes its two 16-byte chunks of the
+// pair's 64-wide row of the A operand (128 pairs x 64, SWIZZLE_128B K-major) straight into shared memory.  One elected thread then issues 12 UMMAs (M=128, N=16, K=16: A_hi.W_hi + A_lo.W_hi + A_hi.W_lo over 4 K-steps)
+// into a 16-column TMEM accumulator, every thread reads 4 of its pair's 16 head values back with one tcgen05.ld, applies
 // bias / max(.,1e-6) / log2 and stores them -- for a fixed head, consecutive threads are consecutive keys, so stores
 // are fully coalesced.  Replaces the mma.sync form (geom.cu) on sm_100: legacy HMMA costs ~64 issue cycles per SMSP there
 // (measured: 635 us of geometry at N = 3000, profiles/r01_relation_sweep_1.jsonl), while these UMMAs are ~free and the
@@ -36,7 +36,7 @@ __device__ __forceinline__ void split2(float v0, float v1, uint32_t* hi, uint32_
 }
 
 template <bool EXACT>
-__global__ void __launch_bounds__(128) geom_weight_tc_kernel(const float* __restrict__ boxes, const int* __restrict__ key_index,
+__global__ void __launch_bounds__(512) geom_weight_tc_kernel(const float* __restrict__ boxes, const int* __restrict__ key_index,
                                                              int B, int N, int M, int H, GeomFreq fr,
                                                              const float* __restrict__ Wg, const float* __restrict__ bg,
                                                              float* __restrict__ out, int ldg, int log2_out,
@@ -49,9 +49,10 @@ __global__ void __launch_bounds__(128) geom_weight_tc_kernel(const float* __rest
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
   __shared__ float s_bias[16];
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int pr = tid & 127, cc = tid >> 7;       // 4 threads per pair: thread (pr, cc) evaluates coordinate cc of pair pr
 
   // B operand: Wg [16 heads (rows >= H zero)] x [64] as hi / lo fp16, K-major SWIZZLE_128B (16 rows x 128 B)
-  {
+  if (tid < 128) {
     const int row = tid >> 3, chunk = tid & 7;
     uint32_t hi[4], lo[4];
 #pragma unroll
@@ -82,26 +83,29 @@ __global__ void __launch_bounds__(128) geom_weight_tc_kernel(const float* __rest
   for (long long item = blockIdx.x; item < total; item += gridDim.x) {
     const int tm = (int)(item % tiles_m);
     const int n = (int)((item / tiles_m) % N), b = (int)(item / ((long long)tiles_m * N));
-    const int m = tm * 128 + tid;
+    const int m = tm * 128 + pr;
     const int mc = min(m, M - 1);
     const float4 bfix = reinterpret_cast<const float4*>(boxes)[(size_t)b * N + n];
     const float4 bvar = reinterpret_cast<const float4*>(boxes)[(size_t)b * N + (key_index ? key_index[mc] : mc)];
     const float4 bq = swap_roles ? bvar : bfix, bk = swap_roles ? bfix : bvar;     // query box / key box
-    float eps[4];
-    if (EXACT) {
-      pair_eps(bq, bk, eps);
-    } else {
+    float e;                                             // eps[cc] of SYM_REL:56-75
+    {
       const float wn = bq.z - bq.x + 1.f, hn = bq.w - bq.y + 1.f, wm = bk.z - bk.x + 1.f, hm = bk.w - bk.y + 1.f;
-      const float dcx = 0.5f * (bq.x + bq.z) - 0.5f * (bk.x + bk.z), dcy = 0.5f * (bq.y + bq.w) - 0.5f * (bk.y + bk.w);
-      eps[0] = __logf(fmaxf(fabsf(dcx * __frcp_rn(wn)), 1e-3f));
-      eps[1] = __logf(fmaxf(fabsf(dcy * __frcp_rn(hn)), 1e-3f));
-      eps[2] = __logf(wn * __frcp_rn(wm));
-      eps[3] = __logf(hn * __frcp_rn(hm));
+      if (cc == 0) {
+        const float dcx = 0.5f * (bq.x + bq.z) - 0.5f * (bk.x + bk.z);
+        e = EXACT ? logf(fmaxf(fabsf(dcx / wn), 1e-3f)) : __logf(fmaxf(fabsf(dcx * __frcp_rn(wn)), 1e-3f));
+      } else if (cc == 1) {
+        const float dcy = 0.5f * (bq.y + bq.w) - 0.5f * (bk.y + bk.w);
+        e = EXACT ? logf(fmaxf(fabsf(dcy / hn), 1e-3f)) : __logf(fmaxf(fabsf(dcy * __frcp_rn(hn)), 1e-3f));
+      } else if (cc == 2) {
+        e = EXACT ? logf(wn / wm) : __logf(wn * __frcp_rn(wm));
+      } else {
+        e = EXACT ? logf(hn / hm) : __logf(hn * __frcp_rn(hm));
+      }
     }
-    // row `tid` of A: [coord c][sin f0..f7 | cos f0..f7] -> chunk 2c = sins, chunk 2c+1 = coses (8 halfs each)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const float a = 100.0f * eps[c];
+    // row `pr` of A: [coord c][sin f0..f7 | cos f0..f7] -> chunk 2c = sins, chunk 2c+1 = coses (8 halfs each)
+    {
+      const float a = 100.0f * e;
       float sn[8], cs[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) sincos_2pi_tc(EXACT ? __fdiv_rn(a, rdim[k]) : a * rdim[k], &sn[k], &cs[k]);
@@ -111,10 +115,10 @@ __global__ void __launch_bounds__(128) geom_weight_tc_kernel(const float* __rest
         split2(sn[2 * j], sn[2 * j + 1], &sh[j], &sl[j]);
         split2(cs[2 * j], cs[2 * j + 1], &ch[j], &cl[j]);
       }
-      *reinterpret_cast<uint4*>(sAh + sw128_offset(tid, 2 * c)) = make_uint4(sh[0], sh[1], sh[2], sh[3]);
-      *reinterpret_cast<uint4*>(sAl + sw128_offset(tid, 2 * c)) = make_uint4(sl[0], sl[1], sl[2], sl[3]);
-      *reinterpret_cast<uint4*>(sAh + sw128_offset(tid, 2 * c + 1)) = make_uint4(ch[0], ch[1], ch[2], ch[3]);
-      *reinterpret_cast<uint4*>(sAl + sw128_offset(tid, 2 * c + 1)) = make_uint4(cl[0], cl[1], cl[2], cl[3]);
+      *reinterpret_cast<uint4*>(sAh + sw128_offset(pr, 2 * cc)) = make_uint4(sh[0], sh[1], sh[2], sh[3]);
+      *reinterpret_cast<uint4*>(sAl + sw128_offset(pr, 2 * cc)) = make_uint4(sl[0], sl[1], sl[2], sl[3]);
+      *reinterpret_cast<uint4*>(sAh + sw128_offset(pr, 2 * cc + 1)) = make_uint4(ch[0], ch[1], ch[2], ch[3]);
+      *reinterpret_cast<uint4*>(sAl + sw128_offset(pr, 2 * cc + 1)) = make_uint4(cl[0], cl[1], cl[2], cl[3]);
     }
     fence_proxy_async_smem();
     tc_fence_before();
@@ -136,17 +140,22 @@ __global__ void __launch_bounds__(128) geom_weight_tc_kernel(const float* __rest
     mbar_wait(bar, phase);
     phase ^= 1;
     tc_fence_after();
-    uint32_t v[16];
-    tmem_ld_32x32b_x16(tmem_d + ((uint32_t)(warp * 32) << 16), v);
-    tmem_ld_wait();
-    if (m < M) {
-      float* o = out + (((size_t)b * H) * N + n) * ldg + m;
+    {
+      // warp w may read TMEM lanes 32*(w%4)..: thread (pr, cc) reads heads 4cc..4cc+3 of its own pair
+      uint32_t v[4];
+      tmem_ld_32x32b_x4(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + 4 * cc, v);
+      tmem_ld_wait();
+      if (m < M) {
+        float* o = out + (((size_t)b * H) * N + n) * ldg + m;
 #pragma unroll
-      for (int h = 0; h < 16; ++h)
-        if (h < H) {
-          const float gv = fmaxf(__uint_as_float(v[h]) + s_bias[h], 1e-6f);
-          o[(size_t)h * N * ldg] = log2_out ? __log2f(gv) : gv;
+        for (int j = 0; j < 4; ++j) {
+          const int h = 4 * cc + j;
+          if (h < H) {
+            const float gv = fmaxf(__uint_as_float(v[j]) + s_bias[h], 1e-6f);
+            o[(size_t)h * N * ldg] = log2_out ? __log2f(gv) : gv;
+          }
         }
+      }
     }
     tc_fence_before();
     __syncthreads();          // TMEM accumulator and the A tiles are free again
@@ -161,7 +170,7 @@ int launch_geom_weight_tc(cudaStream_t st, const float* boxes, const int* key_in
                           int swap_roles, bool exact) {
   const long long items = (long long)B * N * cdiv(M, 128);
   const int sms = sm_count() > 0 ? sm_count() : 148;
-  const int grid = (int)std::min<long long>(items, (long long)sms * 5);
+  const int grid = (int)std::min<long long>(items, (long long)sms * 4);
   static thread_local bool configured = false;
   if (!configured) {
     RN_CUDA(cudaFuncSetAttribute(geom_weight_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGeomSmem));
@@ -169,9 +178,9 @@ int launch_geom_weight_tc(cudaStream_t st, const float* boxes, const int* key_in
     configured = true;
   }
   if (exact)
-    geom_weight_tc_kernel<true><<<grid, 128, kGeomSmem, st>>>(boxes, key_index, B, N, M, H, fr, Wg, bg, g, ldg, log2_out, swap_roles);
+    geom_weight_tc_kernel<true><<<grid, 512, kGeomSmem, st>>>(boxes, key_index, B, N, M, H, fr, Wg, bg, g, ldg, log2_out, swap_roles);
   else
-    geom_weight_tc_kernel<false><<<grid, 128, kGeomSmem, st>>>(boxes, key_index, B, N, M, H, fr, Wg, bg, g, ldg, log2_out, swap_roles);
+    geom_weight_tc_kernel<false><<<grid, 512, kGeomSmem, st>>>(boxes, key_index, B, N, M, H, fr, Wg, bg, g, ldg, log2_out, swap_roles);
   RN_LAUNCH_CHECK();
   return RN_OK;
 }
