@@ -75,7 +75,7 @@ def default_precision():
 
 # ------------------------------------------------------------------------------------------------------------------
 def relation(X, boxes, Wq, bq, Wk, bk, Wg, bg, Wout, bout, key_index=None, M=None, group=16, residual_relu=False,
-             precision=None, wave_length=1000.0, return_softmax=False, stage_mask=7):
+             precision=None, wave_length=1000.0, return_softmax=False, stage_mask=7, workspace=None, out=None):
     """Object-relation module (SYM_REL:30-151 + :267-268).  X [N,d] or [B,N,d]; boxes [N,4] or [B,N,4]."""
     precision = precision or default_precision()
     X = _f32(X, 'X'); boxes = _f32(boxes, 'boxes')
@@ -86,6 +86,14 @@ def relation(X, boxes, Wq, bq, Wk, bk, Wg, bg, Wout, bout, key_index=None, M=Non
                                    (Wout, 'Wout'), (bout, 'bout'))]
     Wq, bq, Wk, bk, Wg, bg, Wout, bout = ws_
     Wout2 = Wout.reshape(Wout.shape[0], -1)
+    dq, dout = Wq.shape[0], Wout2.shape[0]
+    if not (boxes.shape[-1] == 4 and boxes.shape[:-1] == X.shape[:-1] and tuple(Wq.shape) == (dq, d)
+            and tuple(Wk.shape) == (dq, d) and Wout2.shape[1] == d and bq.numel() == dq and bk.numel() == dq
+            and bout.numel() == dout and Wg.shape[0] == group and bg.numel() == group and dq % group == 0
+            and dout % group == 0):
+        raise L.RelnetError('relation: inconsistent shapes X%s boxes%s Wq%s Wk%s Wg%s Wout%s group=%d' % (
+            tuple(X.shape), tuple(boxes.shape), tuple(Wq.shape), tuple(Wk.shape), tuple(Wg.shape), tuple(Wout.shape), group))
+    assert Wq.shape[0] == Wk.shape[0], 'Matrix multiply requires same dimensions!'         # SYM_REL:119
     kidx = None
     if key_index is not None:
         kidx = key_index.to(device=X.device, dtype=torch.int32).contiguous()
@@ -95,12 +103,18 @@ def relation(X, boxes, Wq, bq, Wk, bk, Wg, bg, Wout, bout, key_index=None, M=Non
         precision = 'fp32'      # same library, the general fp32 kernels: the fused tcgen05 kernel is dk == 64 only
     desc = L.RelationDesc(B, N, M, d, Wq.shape[0], Wout2.shape[0], group, Wg.shape[1], wave_length,
                           int(residual_relu), PREC[precision])
-    out = torch.empty((B, N, Wout2.shape[0]) if batched else (N, Wout2.shape[0]), dtype=torch.float32, device=X.device)
+    if out is None:
+        out = torch.empty((B, N, Wout2.shape[0]) if batched else (N, Wout2.shape[0]), dtype=torch.float32, device=X.device)
     sm = torch.empty((B, N, group, M) if batched else (N, group, M), dtype=torch.float32, device=X.device) \
         if return_softmax else None
     lib = L.lib()
     nbytes = lib.rn_relation_workspace_bytes(C.byref(desc))
-    ws = _workspace(nbytes, X.device)
+    if workspace is not None:          # caller-owned scratch: lets stages of one module run on different streams
+        if workspace.numel() < nbytes:
+            raise L.RelnetError('relation: workspace of %d bytes < %d needed' % (workspace.numel(), nbytes))
+        ws = workspace
+    else:
+        ws = _workspace(nbytes, X.device)
     if precision == 'f16':
         def pack(buf):
             L.check(lib.rn_relation_pack(C.byref(desc), _ptr(Wq), _ptr(bq), _ptr(Wk), _ptr(bk), _ptr(Wout2), _ptr(bout),
@@ -118,6 +132,11 @@ def relation(X, boxes, Wq, bq, Wk, bk, Wg, bg, Wout, bout, key_index=None, M=Non
                                 _ptr(Wg), _ptr(bg), _ptr(Wout2), _ptr(bout), _ptr(out), _ptr(sm), _ptr(ws), ws.numel(),
                                 _stream()), 'rn_relation_fwd')
     return (out, sm) if return_softmax else out
+
+
+def relation_workspace_bytes(N, M, d, dq, dout, group, batch=1, E=64, precision='f16'):
+    desc = L.RelationDesc(batch, N, M, d, dq, dout, group, E, 1000.0, 0, PREC[precision])
+    return int(L.lib().rn_relation_workspace_bytes(C.byref(desc)))
 
 
 def relation_tc_supported(dq, dout, group, return_softmax=False):

@@ -72,22 +72,54 @@ class RelationHead(object):
                         post_nms_top_n=post_nms_top_n, thresh=nms_thresh, min_size=min_size)
         self.first_n, self.class_thresh, self.merge_method = first_n, class_thresh, merge_method
         self.nongt_dim = post_nms_top_n
+        self._ws, self._dummy, self._side = {}, {}, None
 
-    def relation(self, x, boxes, idx, nongt_dim):
+    def relation(self, x, boxes, idx, nongt_dim, stage_mask=7):
         P = self.P
+        ws = None
+        if self.precision == 'f16':        # module-owned scratch so the geometry stage can run early on another stream
+            ws = self._ws.get(idx)
+            if ws is None:
+                nbytes = ops.relation_workspace_bytes(boxes.shape[0], nongt_dim, 1024, 1024, 1024, 16)
+                ws = self._ws[idx] = torch.empty(nbytes + 4096, dtype=torch.uint8, device=boxes.device)
         return ops.relation(x, boxes, P['query_%d_weight' % idx], P['query_%d_bias' % idx], P['key_%d_weight' % idx],
                             P['key_%d_bias' % idx], P['pair_pos_fc1_%d_weight' % idx], P['pair_pos_fc1_%d_bias' % idx],
                             P['linear_out_%d_weight' % idx], P['linear_out_%d_bias' % idx], M=nongt_dim, group=16,
-                            residual_relu=True, precision=self.precision)
+                            residual_relu=True, precision=self.precision, stage_mask=stage_mask, workspace=ws)
+
+    def geometry_early(self, rois):
+        """Both relation modules' geometry terms depend only on the rois: run them now (on whatever stream is current,
+        e.g. beside res5 / the ROI-pool + fc_new_1 GEMM); detect(..., geometry_done=True) then skips that stage."""
+        if self.precision != 'f16':
+            return False
+        boxes = rois[:, 1:].contiguous()
+        dummy = self._dummy.get(boxes.shape[0])
+        if dummy is None:
+            dummy = self._dummy[boxes.shape[0]] = torch.zeros((boxes.shape[0], 1024), device=boxes.device)
+        for idx in (1, 2):
+            self.relation(dummy, boxes, idx, self.nongt_dim, stage_mask=2)
+        return True
 
     def forward(self, rpn_cls_prob, rpn_bbox_pred, conv_feat, im_info):
-        return self.detect(self.propose(rpn_cls_prob, rpn_bbox_pred, im_info), conv_feat, im_info)
+        rois = self.propose(rpn_cls_prob, rpn_bbox_pred, im_info)
+        done = False
+        if self.precision == 'f16':        # geometry of both modules on a side stream, beside ROI pool + fc_new_1
+            if self._side is None:
+                self._side = torch.cuda.Stream()
+            main = torch.cuda.current_stream()
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                done = self.geometry_early(rois)
+            out = self.detect(rois, conv_feat, im_info, geometry_done=done, join=self._side)
+            return out
+        return self.detect(rois, conv_feat, im_info)
 
     def propose(self, rpn_cls_prob, rpn_bbox_pred, im_info):
         return ops.proposal(rpn_cls_prob, rpn_bbox_pred, im_info, **self.cfg)[0]                  # SYM_REL_NMS:324-329
 
-    def detect(self, rois, conv_feat, im_info):
+    def detect(self, rois, conv_feat, im_info, geometry_done=False, join=None):
         P, prec = self.P, self.precision
+        rel_mask = 5 if geometry_done else 7        # 1 = projection, 2 = geometry, 4 = fused attention
         boxes = rois[:, 1:].contiguous()                                                          # :337
         if prec == 'f16':        # :335 + :344 at the layout level: channels-last pool -> fp16 -> K-permuted fc_new_1
             fc1 = ops.roi_pool_fc(conv_feat, rois, P['fc_new_1_weight'], P['fc_new_1_bias'], (7, 7),
@@ -95,9 +127,11 @@ class RelationHead(object):
         else:
             pooled = ops.roi_pool(conv_feat, rois, (7, 7), 1.0 / self.cfg['feat_stride'])         # :335
             fc1 = ops.linear(pooled, P['fc_new_1_weight'], P['fc_new_1_bias'], precision=prec)    # :344
-        fc_all_1 = self.relation(fc1, boxes, 1, self.nongt_dim)                                   # :346-351
+        if join is not None:
+            torch.cuda.current_stream().wait_stream(join)
+        fc_all_1 = self.relation(fc1, boxes, 1, self.nongt_dim, rel_mask)                         # :346-351
         fc2 = ops.linear(fc_all_1, P['fc_new_2_weight'], P['fc_new_2_bias'], precision=prec)      # :353
-        fc_all_2 = self.relation(fc2, boxes, 2, self.nongt_dim)                                   # :354-359
+        fc_all_2 = self.relation(fc2, boxes, 2, self.nongt_dim, rel_mask)                         # :354-359
         cls_score = ops.linear(fc_all_2, P['cls_score_weight'], P['cls_score_bias'], precision=prec)
         bbox_pred = ops.linear(fc_all_2, P['bbox_pred_weight'], P['bbox_pred_bias'], precision=prec)
         multi, sorted_bbox, sorted_score, final = ops.learn_nms(                                  # :518-560
@@ -125,11 +159,12 @@ class Detector(object):
         with torch.cuda.stream(self.side):
             prob, bbox = self.trunk.rpn(c4)
             rois = self.head.propose(prob, bbox, self.im_info)
+            done = self.head.geometry_early(rois)          # both modules' geometry terms, still beside res5
         c4.record_stream(self.side)
         feat = self.trunk.c5feat(c4)
         main.wait_stream(self.side)
         rois.record_stream(main)
-        return self.head.detect(rois, feat, self.im_info)
+        return self.head.detect(rois, feat, self.im_info, geometry_done=done)
 
 
 class GraphedStep(object):
