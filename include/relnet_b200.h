@@ -164,6 +164,11 @@ int rn_learn_nms_fwd(const rn_learn_nms_desc* desc, const float* cls_score, cons
                      const int32_t* non_gt_index, float* nms_multi_score, float* sorted_bbox, float* sorted_score,
                      float* final_score, void* workspace, size_t workspace_bytes, rn_stream_t stream);
 
+/* `nms_multi_target` CustomOp forward (relation_rcnn/operator_py/nms_multi_target.py:24-74): learn-NMS training labels.
+ * bbox [n,C,4], gt_boxes [G,5] (x1,y1,x2,y2,cls), score [n,C], target_thresh HOST double[T] -> out [n,C,T] (0/1). */
+int rn_nms_multi_target_fwd(const float* bbox, const float* gt_boxes, const float* score, int32_t n, int32_t C, int32_t G,
+                            const double* target_thresh_host, int32_t T, float* out, rn_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * `proposal` CustomOp forward (relation_rcnn/operator_py/proposal.py:51-168), device resident end to end.
  * cls_prob [1,2A,Hf,Wf], bbox_pred [1,4A,Hf,Wf], im_info [3] (device).  scales/ratios are HOST arrays.

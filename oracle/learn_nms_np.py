@@ -147,3 +147,34 @@ def make_learn_nms_case(seed, R=300, C=80, d=1024, init='fan_in', n_peaky=12):
     P['nms_logit_bias'] = np.full(5, -3.0, np.float32) if init == 'ref' else P['nms_logit_bias']
     im_info = np.array([[600.0, 1000.0, 1.0]], np.float32)
     return dict(cls_score=cls_score, bbox_pred=bbox_pred, rois=rois, im_info=im_info, feat=feat, P=P)
+
+
+def nms_multi_target(bbox, gt_box, score, target_thresh):
+    """Learn-NMS training labels (relation_rcnn/operator_py/nms_multi_target.py:24-74), restated.
+
+    bbox [n,C,4], gt_box [1,G,5] (x1,y1,x2,y2,cls), score [n,C] -> [n,C,T] float32.  Per class and threshold: every gt of
+    that class claims the highest-scoring box among those whose IoU with it exceeds the threshold AND whose best-matching
+    gt (first argmax) it is; a gt nobody qualifies for "claims" box 0 (argmax of zeros), which only counts if box 0
+    overlaps some gt of the class above the threshold -- kept literally.
+    """
+    from .proposal_np import bbox_overlaps
+    bbox = np.asarray(bbox, np.float32); score = np.asarray(score, np.float32); gt_box = np.asarray(gt_box, np.float32)
+    n, C = bbox.shape[0], bbox.shape[1]
+    T = len(target_thresh)
+    out = np.zeros((n, C, T), np.float32)
+    for c in range(C):
+        gts = gt_box[0, gt_box[0, :, -1].astype(np.int32) == c + 1, :4]
+        if len(gts) == 0:
+            continue
+        ov = bbox_overlaps(bbox[:, c, :].astype(np.float64), gts.astype(np.float64))      # [n,G]
+        best_gt = ov.argmax(axis=1)
+        for t, th in enumerate(target_thresh):
+            mask = ov > th
+            qual = mask & (best_gt[:, None] == np.arange(len(gts))[None, :])
+            s = np.where(qual, score[:, c:c + 1], np.float32(0)).astype(np.float32)
+            winners = s.argmax(axis=0)
+            any_ov = mask.any(axis=1)
+            for i in winners:
+                if any_ov[i]:
+                    out[i, c, t] = 1.0
+    return out

@@ -77,6 +77,7 @@ SIGNATURES = {
     'rn_learn_nms_workspace_bytes': (c_sz, [C.POINTER(LearnNmsDesc)]),
     'rn_learn_nms_fwd': (C.c_int, [C.POINTER(LearnNmsDesc)] + [c_p] * 5 + [C.POINTER(LearnNmsWeights), c_p] + [c_p] * 4 +
                          [c_p, c_sz, c_p]),
+    'rn_nms_multi_target_fwd': (C.c_int, [c_p, c_p, c_p, c_i, c_i, c_i, C.POINTER(C.c_double), c_i, c_p, c_p]),
     'rn_proposal_workspace_bytes': (c_sz, [C.POINTER(ProposalDesc)]),
     'rn_proposal_fwd': (C.c_int, [C.POINTER(ProposalDesc), C.POINTER(c_f), C.POINTER(c_f)] + [c_p] * 6 + [c_p, c_sz, c_p]),
     'rn_nms_workspace_bytes': (c_sz, [c_i]),

@@ -11,5 +11,5 @@ Tensors are torch CUDA tensors where the reference has NDArrays / symbols.
 """
 from .symbols import RelationSymbols                                   # noqa: F401
 from .operators import (REGISTRY, ProposalProp, ProposalOperator, ProposalTargetProp, ProposalTargetOperator,   # noqa: F401
-                        LearnNmsProp, LearnNmsOperator, Custom, gpu_nms, bbox_overlaps_cython,
+                        LearnNmsProp, LearnNmsOperator, NmsMultiTargetProp, NmsMultiTargetOp, Custom, gpu_nms, bbox_overlaps_cython,
                         DeformableConvolution, DeformablePSROIPooling, ROIPooling)

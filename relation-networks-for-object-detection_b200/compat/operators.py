@@ -233,6 +233,44 @@ class LearnNmsProp(CustomOpProp):
                                 self.num_thresh, self.class_thresh, self.nongt_dim, self.has_non_gt_index)
 
 
+# ----------------------------------------------------------------------------------------------- nms_multi_target
+class NmsMultiTargetOp(CustomOp):
+    """operator_py/nms_multi_target.py:18-79"""
+
+    def __init__(self, target_thresh):
+        self._target_thresh = target_thresh
+        self._num_thresh = len(target_thresh)
+
+    def forward(self, is_train, req, in_data, out_data, aux):
+        self.assign(out_data[0], req[0], ops.nms_multi_target(in_data[0], in_data[1], in_data[2], self._target_thresh))
+
+
+@register('nms_multi_target')
+class NmsMultiTargetProp(CustomOpProp):
+    """operator_py/nms_multi_target.py:82-112 (target_thresh arrives as the string '[0.5 0.6 0.7 0.8 0.9]')"""
+
+    def __init__(self, target_thresh):
+        super(NmsMultiTargetProp, self).__init__(need_top_grad=False)
+        if isinstance(target_thresh, str):
+            target_thresh = [float(v) for v in target_thresh.strip('[]() ').replace(',', ' ').split()]
+        self._target_thresh = np.asarray(target_thresh, dtype=float)
+        self._num_thresh = len(self._target_thresh)
+
+    def list_arguments(self):
+        return ['bbox', 'gt_bbox', 'score']
+
+    def list_outputs(self):
+        return ['nms_multi_target']
+
+    def infer_shape(self, in_shape):
+        bbox_shape, score_shape = in_shape[0], in_shape[2]
+        assert bbox_shape[0] == score_shape[0], 'ROI number should be same for bbox and score'
+        return in_shape, [(bbox_shape[0], bbox_shape[1], self._num_thresh)]
+
+    def create_operator(self, ctx=None, shapes=None, dtypes=None):
+        return NmsMultiTargetOp(self._target_thresh)
+
+
 def Custom(op_type, name=None, **kwargs):
     """``mx.sym.Custom(op_type=..., tensor kwargs..., string kwargs...)`` evaluated eagerly on torch tensors."""
     tensors = {k: v for k, v in kwargs.items() if isinstance(v, torch.Tensor)}

@@ -168,6 +168,75 @@ __global__ void __launch_bounds__(128) lnms_logit_kernel(int n, int C, int T, co
     final_score[(size_t)i * C + c] = merge_method == -1 ? acc_mean / (float)T : merge_method == -2 ? acc_max : pick;
 }
 
+// nms_multi_target (operator_py/nms_multi_target.py:24-74): learn-NMS training labels.  One CTA per fg class.
+// qual(i,g,t) = (first-argmax_g IoU(i,.) == g) && IoU(i,g) > th[t]; winner(g,t) = first argmax_i (qual ? score : 0)
+// (box 0 when nobody qualifies); out[winner] = 1 iff max_g IoU(winner,.) > th[t].  IoU in float64 (bbox.pyx:15-55).
+__device__ __forceinline__ double lnms_iou_f64(const double* b, const double* q) {
+  const double iw = fmin(b[2], q[2]) - fmax(b[0], q[0]) + 1;
+  if (iw <= 0) return 0.0;
+  const double ih = fmin(b[3], q[3]) - fmax(b[1], q[1]) + 1;
+  if (ih <= 0) return 0.0;
+  const double qa = (q[2] - q[0] + 1) * (q[3] - q[1] + 1);
+  const double ua = (b[2] - b[0] + 1) * (b[3] - b[1] + 1) + qa - iw * ih;
+  return iw * ih / ua;
+}
+
+struct ThreshSet { double v[16]; int T; };
+
+__global__ void __launch_bounds__(128) nms_multi_target_kernel(const float* __restrict__ bbox, const float* __restrict__ gt,
+                                                               const float* __restrict__ score, int n, int C, int G,
+                                                               ThreshSet th, float* __restrict__ out) {
+  extern __shared__ double sm_d[];                 // ov_best[n] | then int best_gt[n] | float sc[n] | uchar flag[n*T]
+  double* ov_best = sm_d;
+  int* best_gt = reinterpret_cast<int*>(ov_best + n);
+  float* sc = reinterpret_cast<float*>(best_gt + n);
+  unsigned char* flag = reinterpret_cast<unsigned char*>(sc + n);
+  __shared__ int cls_gt[256];
+  __shared__ int n_cls_gt;
+  const int c = blockIdx.x, T = th.T;
+  if (threadIdx.x == 0) {
+    int k = 0;
+    for (int g = 0; g < G && k < 256; ++g)
+      if ((int)gt[(size_t)g * 5 + 4] == c + 1) cls_gt[k++] = g;
+    n_cls_gt = k;
+  }
+  for (int i = threadIdx.x; i < n * T; i += blockDim.x) flag[i] = 0;
+  __syncthreads();
+  const int Gc = n_cls_gt;
+  if (Gc > 0) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const float* b = bbox + ((size_t)i * C + c) * 4;
+      const double bd[4] = {(double)b[0], (double)b[1], (double)b[2], (double)b[3]};
+      double best = -1.0; int arg = 0;
+      for (int k = 0; k < Gc; ++k) {
+        const float* q = gt + (size_t)cls_gt[k] * 5;
+        const double qd[4] = {(double)q[0], (double)q[1], (double)q[2], (double)q[3]};
+        const double ov = lnms_iou_f64(bd, qd);
+        if (ov > best) { best = ov; arg = k; }
+      }
+      ov_best[i] = best; best_gt[i] = arg; sc[i] = score[(size_t)i * C + c];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int pair = warp; pair < Gc * T; pair += 4) {
+      const int k = pair / T, t = pair % T;
+      float bv = -1.f; int bi = 0x7fffffff;
+      for (int i = lane; i < n; i += 32) {
+        const float v = (best_gt[i] == k && ov_best[i] > th.v[t]) ? sc[i] : 0.f;
+        if (v > bv) { bv = v; bi = i; }                 // strict '>' keeps the first maximum of this lane's stride
+      }
+      for (int o = 16; o; o >>= 1) {
+        const float ov_ = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov_ > bv || (ov_ == bv && oi < bi)) { bv = ov_; bi = oi; }
+      }
+      if (lane == 0 && bi < n && ov_best[bi] > th.v[t]) flag[bi * T + t] = 1;
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < n * T; i += blockDim.x) out[((size_t)(i / T) * C + c) * T + (i % T)] = flag[i] ? 1.f : 0.f;
+}
+
 struct LnmsWs {
   float *prob, *refined, *cmax, *rank_emb, *rank_feat, *emb, *feat_cls, *boxes_cls, *feat_out, *lg_roi;
   int *rank_idx, *valid;
@@ -281,6 +350,26 @@ extern "C" int rn_learn_nms_fwd(const rn_learn_nms_desc* d, const float* cls_sco
   lnms_logit_kernel<<<cdiv(n * C * 32, 128), 128, 0, st>>>(n, C, T, W.feat_out, w->nms_logit_weight, w->nms_logit_bias,
                                                            sorted_score, W.valid, d->merge_method, nms_multi_score,
                                                            final_score);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
+
+extern "C" int rn_nms_multi_target_fwd(const float* bbox, const float* gt_boxes, const float* score, int32_t n, int32_t C,
+                                       int32_t G, const double* target_thresh_host, int32_t T, float* out,
+                                       rn_stream_t stream) {
+  using namespace rn;
+  RN_CHECK_ARG(bbox && score && out && n >= 1 && n <= 4096 && C >= 1 && G >= 0 && T >= 1 && T <= 16 && target_thresh_host,
+               "rn_nms_multi_target_fwd: bad arguments (n <= 4096, T <= 16)");
+  RN_CHECK_ARG(G == 0 || gt_boxes, "rn_nms_multi_target_fwd: null gt_boxes");
+  ThreshSet th; th.T = T;
+  for (int i = 0; i < T; ++i) th.v[i] = target_thresh_host[i];
+  const size_t smem = (size_t)n * (8 + 4 + 4) + (size_t)n * T + 16;
+  static thread_local size_t configured = 40 * 1024;
+  if (smem > configured) {
+    RN_CUDA(cudaFuncSetAttribute(nms_multi_target_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  nms_multi_target_kernel<<<C, 128, smem, (cudaStream_t)stream>>>(bbox, gt_boxes, score, n, C, G, th, out);
   RN_LAUNCH_CHECK();
   return RN_OK;
 }

@@ -585,15 +585,17 @@ extern "C" size_t rn_nms_workspace_bytes(int32_t n) {
 extern "C" int rn_nms(const float* boxes_sorted, int32_t n, int32_t box_dim, float thresh, int32_t max_keep,
                       int32_t* keep_out, int32_t* num_out, void* wsp, size_t ws_bytes, rn_stream_t stream) {
   using namespace rn;
-  RN_CHECK_ARG(boxes_sorted && keep_out && num_out && wsp && n >= 0 && box_dim >= 4 && max_keep > 0, "rn_nms: bad arguments");
+  RN_CHECK_ARG(keep_out && num_out && n >= 0 && box_dim >= 4 && max_keep > 0, "rn_nms: bad arguments");
+  RN_CHECK_ARG(n == 0 || (boxes_sorted && wsp), "rn_nms: null boxes / workspace");
   cudaStream_t st = (cudaStream_t)stream;
+  RN_CUDA(cudaMemsetAsync(num_out, 0, sizeof(int), st));
+  if (n == 0) return RN_OK;
   Workspace ws(wsp, ws_bytes);
   const int cb = ((n + 63) / 64 + 1) & ~1;
   unsigned long long* mask = ws.take<unsigned long long>(((size_t)n + 63) / 64 * 64 * cb);
   int* n_dev = ws.take<int>(4);
   if (!n_dev) { set_error("rn_nms: workspace too small"); return RN_ERR_WORKSPACE; }
-  RN_CUDA(cudaMemsetAsync(num_out, 0, sizeof(int), st));
-  if (n == 0) return RN_OK;
+
   // the mask/sweep kernels read n from device memory (in rn_proposal_fwd it is produced on the device); here it is a
   // host value, staged by a 1-thread kernel so the call stays asynchronous
   set_int_kernel<<<1, 1, 0, st>>>(n_dev, n);

@@ -148,8 +148,9 @@ static inline int grid_for(size_t count) {
 extern "C" int rn_roi_pool_fwd(const float* data, const float* rois, int32_t R, int32_t C, int32_t H, int32_t W,
                                int32_t PH, int32_t PW, float spatial_scale, float* out, int32_t* argmax,
                                rn_stream_t stream) {
-  RN_CHECK_ARG(data && rois && out && R >= 0 && C > 0 && H > 0 && W > 0 && PH > 0 && PW > 0, "rn_roi_pool_fwd: bad arguments");
+  RN_CHECK_ARG(R >= 0 && C > 0 && H > 0 && W > 0 && PH > 0 && PW > 0, "rn_roi_pool_fwd: bad arguments");
   if (R == 0) return RN_OK;
+  RN_CHECK_ARG(data && rois && out, "rn_roi_pool_fwd: null pointer");
   size_t count = (size_t)R * C * PH * PW;
   rn::roi_pool_fwd_kernel<<<rn::grid_for(count), 256, 0, (cudaStream_t)stream>>>(data, rois, count, C, H, W, PH, PW,
                                                                                 spatial_scale, out, argmax);
@@ -159,7 +160,9 @@ extern "C" int rn_roi_pool_fwd(const float* data, const float* rois, int32_t R, 
 
 extern "C" int rn_deform_psroi_pool_fwd(const rn_psroi_desc* desc, const float* data, const float* rois,
                                         const float* trans, float* out, float* top_count, rn_stream_t stream) {
-  RN_CHECK_ARG(desc && data && rois && out, "rn_deform_psroi_pool_fwd: null argument");
+  RN_CHECK_ARG(desc, "rn_deform_psroi_pool_fwd: null descriptor");
+  if (desc->R == 0) return RN_OK;
+  RN_CHECK_ARG(data && rois && out, "rn_deform_psroi_pool_fwd: null argument");
   rn_psroi_desc p = *desc;
   if (p.part_size == 0) p.part_size = p.pooled_size;
   RN_CHECK_ARG(p.no_trans || trans, "rn_deform_psroi_pool_fwd: trans required when no_trans == 0");

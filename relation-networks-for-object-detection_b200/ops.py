@@ -230,6 +230,23 @@ def learn_nms(cls_score, bbox_pred, rois, im_info, feat, weights, first_n=100, n
     return multi, sbbox, sscore, final
 
 
+def nms_multi_target(bbox, gt_boxes, score, target_thresh):
+    """nms_multi_target CustomOp forward: bbox [n,C,4], gt_boxes [G,5] or [1,G,5], score [n,C] -> [n,C,T] of 0/1."""
+    bbox = _f32(bbox, 'bbox'); score = _f32(score, 'score'); gt = _f32(gt_boxes, 'gt_boxes')
+    if gt.dim() == 3:
+        assert gt.shape[0] == 1, 'only support batch_image=1, but receive %d' % gt.shape[0]
+        gt = gt[0].contiguous()
+    assert gt.shape[-1] == 5, 'code_size of gt should be 5, but receive %d' % gt.shape[-1]
+    assert score.dim() == 2 and score.shape[1] == bbox.shape[1], 'number of fg classes should be same for boxes and scores'
+    n, Cc = bbox.shape[0], bbox.shape[1]
+    T = len(target_thresh)
+    th = (C.c_double * T)(*[float(t) for t in target_thresh])
+    out = torch.empty((n, Cc, T), dtype=torch.float32, device=bbox.device)
+    L.check(L.lib().rn_nms_multi_target_fwd(_ptr(bbox), _ptr(gt), _ptr(score), n, Cc, gt.shape[0], th, T, _ptr(out),
+                                            _stream()), 'rn_nms_multi_target_fwd')
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------------------
 def proposal(cls_prob, bbox_pred, im_info, feat_stride=16, scales=(4, 8, 16, 32), ratios=(0.5, 1, 2),
              pre_nms_top_n=6000, post_nms_top_n=300, thresh=0.7, min_size=0, return_num_kept=False):

@@ -126,6 +126,32 @@ def proposal_target_case(ns, name, seed, N, G):
     print(name, 'fg', int((out_data[1].a > 0).sum()), 'of', N + G)
 
 
+def nms_multi_target_case(ns, name):
+    """learn-NMS training labels: NmsMultiTargetOp.forward (operator_py/nms_multi_target.py:24-74)"""
+    shim = ns.mxshim
+    rng = np.random.default_rng(41)
+    n, C, G = 100, 8, 9
+    boxes = relation_np.make_boxes(rng, n * C).reshape(n, C, 4)
+    gt = relation_np.make_boxes(rng, G)
+    cls = rng.integers(1, C + 1, G).astype(np.float32)
+    cls[:2] = 3
+    for g in range(G):                     # several boxes of the right class overlap every gt
+        c = int(cls[g]) - 1
+        for k in range(6):
+            boxes[(g * 7 + k) % n, c] = gt[g] + rng.normal(0, 4 + 3 * k, 4)
+    boxes[..., 2] = np.maximum(boxes[..., 2], boxes[..., 0] + 1); boxes[..., 3] = np.maximum(boxes[..., 3], boxes[..., 1] + 1)
+    boxes = boxes.astype(np.float32)
+    gt5 = np.hstack([gt, cls[:, None]]).astype(np.float32)[None]
+    score = rng.random((n, C)).astype(np.float32)
+    th = np.array([0.5, 0.6, 0.7, 0.8, 0.9])
+    op = ns.nms_multi_target.NmsMultiTargetProp('[0.5 0.6 0.7 0.8 0.9]').create_operator(None, None, None)
+    out = [shim.ND(np.zeros((n, C, 5), np.float32))]
+    op.forward(True, ['write'], [shim.ND(boxes), shim.ND(gt5), shim.ND(score)], out, [])
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), bbox=boxes, gt_box=gt5, score=score, target_thresh=th,
+                        target=out[0].a)
+    print(name, 'positives', int(out[0].a.sum()))
+
+
 def misc_case(ns, name):
     """Small pure-python reference helpers: refine_bbox_nd, rank embedding, multi position matrix, decode/encode."""
     shim = ns.mxshim
@@ -160,6 +186,7 @@ def main():
     proposal_case(ns, 'proposal_small', 22, 10, 12, (160.0, 200.0, 1.0), 200, 32, scales=(8, 16))
     proposal_target_case(ns, 'proposal_target_300_7', 31, 300, 7)
     misc_case(ns, 'misc_helpers')
+    nms_multi_target_case(ns, 'nms_multi_target')
 
 
 if __name__ == '__main__':

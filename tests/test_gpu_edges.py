@@ -149,3 +149,24 @@ def test_errors_are_loud(ops):
     with pytest.raises(Err):
         ops.proposal(torch.zeros((1, 24, 200, 200), device='cuda'), torch.zeros((1, 48, 200, 200), device='cuda'),
                      torch.tensor([[3200.0, 3200.0, 1.0]], device='cuda'))            # 480000 anchors > sort capacity
+
+
+def test_nms_multi_target_matches_reference_execution(ops):
+    from conftest import golden
+    g = golden('nms_multi_target')
+    out = ops.nms_multi_target(T(g['bbox']), T(g['gt_box']), T(g['score']), list(g['target_thresh'])).cpu().numpy()
+    np.testing.assert_array_equal(out, g['target'])
+    # random second case against the oracle, incl. classes without gt and gts nobody overlaps
+    rng = np.random.default_rng(3)
+    bbox = R.make_boxes(rng, 150 * 5).reshape(150, 5, 4)
+    gt = np.hstack([R.make_boxes(rng, 12), rng.integers(1, 7, (12, 1))]).astype(np.float32)
+    bbox[:12, 2] = gt[:, :4] + rng.normal(0, 5, (12, 4)).astype(np.float32)
+    score = rng.random((150, 5)).astype(np.float32)
+    th = [0.5, 0.6, 0.7, 0.8, 0.9]
+    out = ops.nms_multi_target(T(bbox), T(gt), T(score), th).cpu().numpy()
+    np.testing.assert_array_equal(out, L.nms_multi_target(bbox, gt[None], score, th))
+    import relnet_b200
+    from relnet_b200 import compat
+    o2 = compat.Custom(op_type='nms_multi_target', bbox=T(g['bbox']), gt_bbox=T(g['gt_box']), score=T(g['score']),
+                       target_thresh='[0.5 0.6 0.7 0.8 0.9]')
+    np.testing.assert_array_equal(o2.cpu().numpy(), g['target'])

@@ -113,3 +113,13 @@ def test_misc_helpers_match_reference_execution():
         np.testing.assert_allclose(R.position_matrix(sb[:, c]), g['multi_position_matrix'][c], rtol=1e-5, atol=1e-5)
     np.testing.assert_allclose(P.decode_boxes(g['boxes'].astype(np.float64), g['deltas']), g['decoded'], rtol=1e-6)
     np.testing.assert_allclose(P.encode_boxes(g['boxes'], g['boxes'][::-1].copy()), g['encoded'], rtol=1e-6, atol=1e-6)
+
+
+def test_nms_multi_target_oracle_matches_reference_execution():
+    g = golden('nms_multi_target')
+    out = L.nms_multi_target(g['bbox'], g['gt_box'], g['score'], g['target_thresh'])
+    assert out.sum() > 10
+    np.testing.assert_array_equal(out, g['target'])
+    # a class without gt boxes, and a gt nobody overlaps, produce no positives
+    gt2 = g['gt_box'].copy(); gt2[0, :, :4] += 5000
+    assert L.nms_multi_target(g['bbox'], gt2, g['score'], g['target_thresh']).sum() == 0
