@@ -169,8 +169,18 @@ def relation_kernel_roofline(ops, pk, device):
     times['module_warm'] = e0.elapsed_time(e1) * 1e3 / 50
     flops = 4.0 * 300 * 300 * 1024
     achieved = flops / (times['attn'] * 1e-6) / 1e12
+    traffic = None          # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
+    try:
+        recs = json.load(open(os.path.join(ROOT, 'profiles', 'r01_ncu_relation_attn_tile_full.json')))
+        r0 = [r for r in recs if r['launch__grid_size'] == '144'][0]
+        mult = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+        traffic = int(float(r0['dram__bytes_read.sum']) * mult[r0['units']['dram__bytes_read.sum']] +
+                      float(r0['dram__bytes_write.sum']) * mult[r0['units']['dram__bytes_write.sum']])
+    except Exception:
+        pass
     return dict(bound='tensor', kernel='relation_attn_tile_kernel (+combine)', achieved=round(achieved, 3), peak=pk['tflops'],
-                unit='TFLOP/s', frac=round(achieved / pk['tflops'], 5), traffic=None,
+                unit='TFLOP/s', frac=round(achieved / pk['tflops'], 5), traffic=traffic,
+                algorithmic_bytes=int(2 * (300 + 2 * 300) * 1024 + 4 * 16 * 300 * 300 + 4 * 300 * 1024),
                 algorithmic_flops=flops, duration_us=round(times['attn'], 2), peak_source=pk['source'],
                 note='N=M=300,d=1024,H=16: 0.37 GFLOP is launch-latency sized (SURVEY 7); sweep in profiles/'), times
 
