@@ -108,6 +108,18 @@ int rn_relation_packed_fwd(const rn_relation_desc* desc, const float* X, const f
 int rn_relation_packed_stages(const rn_relation_desc* desc, const float* X, const float* boxes, const int32_t* key_index,
                               const void* packed, const float* Wg, const float* bg, float* out, void* workspace,
                               size_t workspace_bytes, int32_t stage_mask, rn_stream_t stream);
+/* Backward of the relation module (training: the reference differentiates the symbol graph of
+ * attention_module_multi_head, resnet_v1_101_rcnn_attention_1024_pairwise_position_multi_head_16.py:104-151, through MXNet
+ * autograd; there is no explicit backward source to cite).  fp32; the forward intermediates are recomputed, nothing has to
+ * be saved from rn_relation_fwd.  dOut [batch*N, dout] is the gradient of the loss w.r.t. rn_relation_fwd's `out`; every
+ * gradient buffer is OVERWRITTEN (not accumulated) and has the shape of its parameter: dX [batch*N, d], dWq/dWk [dq, d],
+ * dbq/dbk [dq], dWg [H, E], dbg [H], dWout [dout, d], dbout [dout].  Boxes receive no gradient (proposal.py:170-173). */
+size_t rn_relation_bwd_workspace_bytes(const rn_relation_desc* desc);
+int rn_relation_bwd(const rn_relation_desc* desc, const float* X, const float* boxes, const int32_t* key_index,
+                    const float* Wq, const float* bq, const float* Wk, const float* bk, const float* Wg, const float* bg,
+                    const float* Wout, const float* bout, const float* dOut, float* dX, float* dWq, float* dbq, float* dWk,
+                    float* dbk, float* dWg, float* dbg, float* dWout, float* dbout, void* workspace,
+                    size_t workspace_bytes, rn_stream_t stream);
 size_t rn_linear_packed_bytes(int32_t in, int32_t out);
 int rn_linear_pack(const float* W, int32_t in, int32_t out, void* packed, rn_stream_t stream);
 int rn_linear_packed_fwd(const float* x, const void* packed_W, const float* b, float* y, int32_t rows, int32_t in,

@@ -60,6 +60,8 @@ SIGNATURES = {
     'rn_device_info': (C.c_int, [C.POINTER(C.c_int)] * 3),
     'rn_relation_workspace_bytes': (c_sz, [C.POINTER(RelationDesc)]),
     'rn_relation_fwd': (C.c_int, [C.POINTER(RelationDesc)] + [c_p] * 13 + [c_p, c_sz, c_p]),
+    'rn_relation_bwd_workspace_bytes': (c_sz, [C.POINTER(RelationDesc)]),
+    'rn_relation_bwd': (C.c_int, [C.POINTER(RelationDesc)] + [c_p] * 21 + [c_p, c_sz, c_p]),
     'rn_pos_embed_fwd': (C.c_int, [c_p, c_p, c_i, c_i, c_i, c_f, c_p, c_p, c_p]),
     'rn_geometry_weight_fwd': (C.c_int, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_p, c_p, c_p, c_p]),
     'rn_linear_workspace_bytes': (c_sz, [c_i, c_i, c_i, c_i]),

@@ -80,6 +80,22 @@ int sgemm_nn(cudaStream_t st, int M, int N, int K, const float* A, int lda, cons
   return RN_OK;
 }
 
+// general row-major C[M,N] = alpha * op(A) . op(B) + beta * C, optional strided batch
+int sgemm_rm(cudaStream_t st, bool transA, bool transB, int M, int N, int K, float alpha, const float* A, int lda,
+             const float* B, int ldb, float beta, float* C, int ldc, int batch, long long sA, long long sB, long long sC) {
+  cublasHandle_t h;
+  int r = get_cublas(st, &h);
+  if (r) return r;
+  const cublasOperation_t opb = transB ? CUBLAS_OP_T : CUBLAS_OP_N, opa = transA ? CUBLAS_OP_T : CUBLAS_OP_N;
+  cublasStatus_t s;
+  if (batch == 1)
+    s = cublasSgemm(h, opb, opa, N, M, K, &alpha, B, ldb, A, lda, &beta, C, ldc);
+  else
+    s = cublasSgemmStridedBatched(h, opb, opa, N, M, K, &alpha, B, ldb, sB, A, lda, sA, &beta, C, ldc, sC, batch);
+  if (s != CUBLAS_STATUS_SUCCESS) { set_error("cublasSgemm(rm %dx%dx%d) failed: %d", M, N, K, (int)s); return RN_ERR_CUDA; }
+  return RN_OK;
+}
+
 }  // namespace rn
 
 extern "C" {

@@ -60,4 +60,9 @@ int sgemm_nt(cudaStream_t st, int M, int N, int K, const float* A, int lda, cons
 int sgemm_nn(cudaStream_t st, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
              int batch = 1, long long sA = 0, long long sB = 0, long long sC = 0);
 
+// general row-major C[M,N] = alpha * op(A) . op(B) + beta * C (cuBLAS fp32, pedantic)
+int sgemm_rm(cudaStream_t st, bool transA, bool transB, int M, int N, int K, float alpha, const float* A, int lda,
+             const float* B, int ldb, float beta, float* C, int ldc, int batch = 1, long long sA = 0, long long sB = 0,
+             long long sC = 0);
+
 }  // namespace rn

@@ -80,7 +80,7 @@ __global__ void relation_epilogue_kernel(const float* __restrict__ O, const floa
   }
 }
 
-static int check_desc(const rn_relation_desc* d) {
+int relation_check_desc(const rn_relation_desc* d) {
   RN_CHECK_ARG(d, "rn_relation: null descriptor");
   RN_CHECK_ARG(d->batch >= 1 && d->N >= 1 && d->M >= 1 && d->d >= 1, "rn_relation: bad sizes batch=%d N=%d M=%d d=%d",
                d->batch, d->N, d->M, d->d);
@@ -94,7 +94,7 @@ static int check_desc(const rn_relation_desc* d) {
   return RN_OK;
 }
 
-static size_t fp32_ws_bytes(const rn_relation_desc* d) {
+size_t relation_fp32_ws_bytes(const rn_relation_desc* d) {
   size_t B = d->batch, N = d->N, M = d->M;
   int ld = (int)align_up(M, 4);
   size_t t = 0;
@@ -108,21 +108,33 @@ static size_t fp32_ws_bytes(const rn_relation_desc* d) {
   return t;
 }
 
-static int relation_fp32(const rn_relation_desc* d, const float* X, const float* boxes, const int* key_index,
+// carve the fp32 path's intermediates out of a workspace (the backward re-uses them after recomputing the forward)
+bool relation_fp32_carve(const rn_relation_desc* d, void* wsp, size_t ws_bytes, Fp32State* fs) {
+  const size_t B = d->batch, N = d->N, M = d->M, H = d->H;
+  const size_t ld = align_up(M, 4);
+  Workspace ws(wsp, ws_bytes);
+  fs->ld = (int)ld;
+  fs->Q = ws.take<float>(B * N * d->dq);
+  fs->K = ws.take<float>(B * M * d->dq);
+  fs->Vp = ws.take<float>(B * M * d->dout);
+  fs->g = ws.take<float>(B * H * N * ld);
+  fs->S = ws.take<float>(B * H * N * ld);
+  fs->O = ws.take<float>(B * N * d->dout);
+  fs->Xk = ws.take<float>(B * M * d->d);
+  fs->used = ws.off;
+  return fs->Xk != nullptr;
+}
+
+int relation_fp32(const rn_relation_desc* d, const float* X, const float* boxes, const int* key_index,
                          const float* Wq, const float* bq, const float* Wk, const float* bk, const float* Wg,
                          const float* bg, const float* Wout, const float* bout, float* out, float* softmax_out,
                          void* wsp, size_t ws_bytes, cudaStream_t st) {
   const int B = d->batch, N = d->N, M = d->M, D = d->d, dq = d->dq, dout = d->dout, H = d->H;
   const int dk = dq / H, dv = dout / H, ld = (int)align_up(M, 4);
-  Workspace ws(wsp, ws_bytes);
-  float* Q = ws.take<float>((size_t)B * N * dq);
-  float* K = ws.take<float>((size_t)B * M * dq);
-  float* Vp = ws.take<float>((size_t)B * M * dout);
-  float* g = ws.take<float>((size_t)B * H * N * ld);
-  float* S = ws.take<float>((size_t)B * H * N * ld);
-  float* O = ws.take<float>((size_t)B * N * dout);
-  float* Xk = ws.take<float>((size_t)B * M * D);
-  if (!Xk) { set_error("rn_relation_fwd: workspace too small (%zu < %zu)", ws_bytes, fp32_ws_bytes(d)); return RN_ERR_WORKSPACE; }
+  Fp32State fs;
+  const bool carved = relation_fp32_carve(d, wsp, ws_bytes, &fs);
+  float *Q = fs.Q, *K = fs.K, *Vp = fs.Vp, *g = fs.g, *S = fs.S, *O = fs.O, *Xk = fs.Xk;
+  if (!carved) { set_error("rn_relation_fwd: workspace too small (%zu < %zu)", ws_bytes, relation_fp32_ws_bytes(d)); return RN_ERR_WORKSPACE; }
   int r;
   // projections
   if ((r = sgemm_nt(st, B * N, dq, D, X, D, Wq, D, Q, dq))) return r;
@@ -177,7 +189,7 @@ static int relation_fp32(const rn_relation_desc* d, const float* X, const float*
 
 extern "C" size_t rn_relation_workspace_bytes(const rn_relation_desc* d) {
   if (!d) return 0;
-  size_t a = rn::fp32_ws_bytes(d);
+  size_t a = rn::relation_fp32_ws_bytes(d);
   size_t b = rn::relation_tc_workspace_bytes(d);
   return (a > b ? a : b) + 256;
 }
@@ -186,7 +198,7 @@ extern "C" int rn_relation_fwd(const rn_relation_desc* d, const float* X, const 
                                const float* Wq, const float* bq, const float* Wk, const float* bk, const float* Wg,
                                const float* bg, const float* Wout, const float* bout, float* out, float* softmax_out,
                                void* ws, size_t ws_bytes, rn_stream_t stream) {
-  int r = rn::check_desc(d);
+  int r = rn::relation_check_desc(d);
   if (r) return r;
   RN_CHECK_ARG(X && boxes && Wq && bq && Wk && bk && Wg && bg && Wout && bout && out && ws,
                "rn_relation_fwd: null pointer argument");
@@ -217,7 +229,7 @@ extern "C" size_t rn_relation_packed_bytes(const rn_relation_desc* d) { return d
 
 extern "C" int rn_relation_pack(const rn_relation_desc* d, const float* Wq, const float* bq, const float* Wk,
                                 const float* bk, const float* Wout, const float* bout, void* packed, rn_stream_t stream) {
-  int r = rn::check_desc(d);
+  int r = rn::relation_check_desc(d);
   if (r) return r;
   RN_CHECK_ARG(Wq && bq && Wk && bk && Wout && bout && packed, "rn_relation_pack: null pointer argument");
   return rn::relation_tc_pack(d, Wq, bq, Wk, bk, Wout, bout, packed, (cudaStream_t)stream);
@@ -226,7 +238,7 @@ extern "C" int rn_relation_pack(const rn_relation_desc* d, const float* Wq, cons
 extern "C" int rn_relation_packed_fwd(const rn_relation_desc* d, const float* X, const float* boxes,
                                       const int32_t* key_index, const void* packed, const float* Wg, const float* bg,
                                       float* out, void* ws, size_t ws_bytes, rn_stream_t stream) {
-  int r = rn::check_desc(d);
+  int r = rn::relation_check_desc(d);
   if (r) return r;
   RN_CHECK_ARG(X && boxes && packed && Wg && bg && out && ws, "rn_relation_packed_fwd: null pointer argument");
   return rn::relation_tc_packed(d, X, boxes, key_index, packed, Wg, bg, out, ws, ws_bytes, (cudaStream_t)stream, 7, nullptr);
@@ -237,7 +249,7 @@ extern "C" int rn_relation_packed_fwd(const rn_relation_desc* d, const float* X,
 extern "C" int rn_relation_packed_stages(const rn_relation_desc* d, const float* X, const float* boxes,
                                          const int32_t* key_index, const void* packed, const float* Wg, const float* bg,
                                          float* out, void* ws, size_t ws_bytes, int32_t stage_mask, rn_stream_t stream) {
-  int r = rn::check_desc(d);
+  int r = rn::relation_check_desc(d);
   if (r) return r;
   RN_CHECK_ARG(X && boxes && packed && Wg && bg && out && ws, "rn_relation_packed_stages: null pointer argument");
   return rn::relation_tc_packed(d, X, boxes, key_index, packed, Wg, bg, out, ws, ws_bytes, (cudaStream_t)stream,

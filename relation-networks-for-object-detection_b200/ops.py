@@ -134,6 +134,43 @@ def relation(X, boxes, Wq, bq, Wk, bk, Wg, bg, Wout, bout, key_index=None, M=Non
     return (out, sm) if return_softmax else out
 
 
+def relation_backward(grad_out, X, boxes, Wq, bq, Wk, bk, Wg, bg, Wout, bout, key_index=None, M=None, group=16,
+                      residual_relu=False, wave_length=1000.0):
+    """Gradients of `relation` (fp32; forward intermediates are recomputed) -- rn_relation_bwd.
+    Returns a dict with the gradient of X and of every parameter, shaped like the argument it belongs to."""
+    X = _f32(X, 'X'); boxes = _f32(boxes, 'boxes'); grad_out = _f32(grad_out, 'grad_out')
+    batched = X.dim() == 3
+    B = X.shape[0] if batched else 1
+    N, d = X.shape[-2], X.shape[-1]
+    Wq, bq, Wk, bk, Wg, bg, Wout, bout = [_f32(w, n) for w, n in ((Wq, 'Wq'), (bq, 'bq'), (Wk, 'Wk'), (bk, 'bk'), (Wg, 'Wg'),
+                                                                  (bg, 'bg'), (Wout, 'Wout'), (bout, 'bout'))]
+    Wout2 = Wout.reshape(Wout.shape[0], -1)
+    dq, dout = Wq.shape[0], Wout2.shape[0]
+    if not (boxes.shape[-1] == 4 and boxes.shape[:-1] == X.shape[:-1] and tuple(Wq.shape) == (dq, d)
+            and tuple(Wk.shape) == (dq, d) and Wout2.shape[1] == d and bq.numel() == dq and bk.numel() == dq
+            and bout.numel() == dout and Wg.shape[0] == group and bg.numel() == group and dq % group == 0
+            and dout % group == 0 and grad_out.numel() == B * N * dout):
+        raise L.RelnetError('relation_backward: inconsistent shapes X%s boxes%s grad_out%s Wq%s Wk%s Wg%s Wout%s group=%d' % (
+            tuple(X.shape), tuple(boxes.shape), tuple(grad_out.shape), tuple(Wq.shape), tuple(Wk.shape), tuple(Wg.shape),
+            tuple(Wout.shape), group))
+    kidx = None
+    if key_index is not None:
+        kidx = key_index.to(device=X.device, dtype=torch.int32).contiguous()
+        M = kidx.numel()
+    M = int(M) if M is not None else N
+    desc = L.RelationDesc(B, N, M, d, dq, dout, group, Wg.shape[1], wave_length, int(residual_relu), PREC['fp32'])
+    g = {'X': torch.empty_like(X), 'Wq': torch.empty_like(Wq), 'bq': torch.empty_like(bq), 'Wk': torch.empty_like(Wk),
+         'bk': torch.empty_like(bk), 'Wg': torch.empty_like(Wg), 'bg': torch.empty_like(bg), 'Wout': torch.empty_like(Wout),
+         'bout': torch.empty_like(bout)}
+    lib = L.lib()
+    ws = _workspace(lib.rn_relation_bwd_workspace_bytes(C.byref(desc)), X.device)
+    L.check(lib.rn_relation_bwd(C.byref(desc), _ptr(X), _ptr(boxes), _ptr(kidx), _ptr(Wq), _ptr(bq), _ptr(Wk), _ptr(bk),
+                                _ptr(Wg), _ptr(bg), _ptr(Wout2), _ptr(bout), _ptr(grad_out), _ptr(g['X']), _ptr(g['Wq']),
+                                _ptr(g['bq']), _ptr(g['Wk']), _ptr(g['bk']), _ptr(g['Wg']), _ptr(g['bg']), _ptr(g['Wout']),
+                                _ptr(g['bout']), _ptr(ws), ws.numel(), _stream()), 'rn_relation_bwd')
+    return g
+
+
 def relation_workspace_bytes(N, M, d, dq, dout, group, batch=1, E=64, precision='f16'):
     desc = L.RelationDesc(batch, N, M, d, dq, dout, group, E, 1000.0, 0, PREC[precision])
     return int(L.lib().rn_relation_workspace_bytes(C.byref(desc)))

@@ -1,0 +1,87 @@
+"""GPU: rn_relation_bwd against autograd through the torch restatement of the module (oracle/relation_torch.py).
+
+The oracle's forward is pinned to the numpy oracle (tests/test_oracle_golden.py), which is pinned by reference execution;
+the reference's own backward IS autograd over the same graph (MXNet), so autograd over the pinned forward is the
+reference gradient.  Target: the FLOAT32 autograd gradients (the reference's arithmetic type), max-norm relative error
+<= 2e-3 per gradient tensor; the float64 gradients are printed for information (the float32 geometry is ill-conditioned
+for near-concentric boxes, see test_gpu_parity.py)."""
+import numpy as np
+import pytest
+import torch
+from conftest import rel_err
+from oracle import relation_np as R, relation_torch as RT
+
+pytestmark = pytest.mark.gpu
+NAMES = ('X', 'Wq', 'bq', 'Wk', 'bk', 'Wg', 'bg', 'Wout', 'bout')
+
+
+@pytest.fixture(scope='module')
+def ops(cuda_device):
+    import __graft_entry__ as g
+    g.build()
+    import relnet_b200
+    torch.cuda.set_device(cuda_device)
+    return relnet_b200.ops
+
+
+def autograd_grads(c, dOut, dtype, **kw):
+    t = {k: torch.tensor(c[k], dtype=dtype, requires_grad=(k != 'boxes')) for k in NAMES + ('boxes',)}
+    out = RT.relation_forward(t['X'], t['boxes'], t['Wq'], t['bq'], t['Wk'], t['bk'], t['Wg'], t['bg'], t['Wout'], t['bout'], **kw)
+    out.backward(torch.tensor(dOut, dtype=dtype))
+    return {k: t[k].grad.numpy() for k in NAMES}, out.detach().numpy()
+
+
+@pytest.mark.parametrize('seed,N,d,H,M,kidx,res', [
+    (11, 70, 256, 4, 50, False, True),        # key prefix (FPN form, SYM_REL fpn :104-151), residual + relu
+    (12, 300, 1024, 16, None, False, True),   # the module at its training size
+    (13, 131, 256, 16, None, True, False),    # permuted key_index (learn-NMS form), no residual
+])
+def test_relation_backward_matches_autograd(ops, seed, N, d, H, M, kidx, res):
+    c = R.make_relation_case(seed, N, d, H, M=M)
+    rng = np.random.RandomState(seed)
+    key_index = rng.permutation(N)[:97].astype(np.int32) if kidx else None
+    dOut = rng.randn(N, d).astype(np.float32)
+    kw = dict(group=H, residual_relu=res)
+    kw['key_index'] = key_index if kidx else (M if M is not None else None)
+    g32, out32 = autograd_grads(c, dOut, torch.float32, **kw)
+    g64, _ = autograd_grads(c, dOut, torch.float64, **kw)
+    dev = {k: torch.from_numpy(np.ascontiguousarray(c[k])).cuda() for k in NAMES + ('boxes',)}
+    got = ops.relation_backward(torch.from_numpy(dOut).cuda(), dev['X'], dev['boxes'], dev['Wq'], dev['bq'], dev['Wk'], dev['bk'],
+                                dev['Wg'], dev['bg'], dev['Wout'], dev['bout'],
+                                key_index=torch.from_numpy(key_index).cuda() if kidx else None, M=M, group=H, residual_relu=res)
+    torch.cuda.synchronize()
+    for k in NAMES:
+        a = got[k].cpu().numpy().reshape(g32[k].shape)
+        if k == 'bk':
+            # exactly zero in exact arithmetic (a key bias shifts every logit of a row alike; softmax is shift-invariant):
+            # both sides are rounding noise, so hold it to the scale of the query-bias gradient instead
+            scale = np.abs(g32['bq']).max()
+            print('dbk    |got| %.2e  |float32 autograd| %.2e  (dbq scale %.2e)' % (np.abs(a).max(), np.abs(g32[k]).max(), scale))
+            assert np.abs(a).max() <= 1e-4 * scale
+            continue
+        e32 = rel_err(a, g32[k])
+        e64 = rel_err(a, g64[k])
+        print('d%-5s vs float32 autograd %.2e   vs float64 %.2e' % (k, e32, e64))
+        assert e32 <= 2e-3, (k, e32)
+
+
+def test_relation_backward_batched_and_loud(ops):
+    """batch = 2 problems == two single calls with the parameter gradients summed; bad shapes raise."""
+    import relnet_b200
+    H, N, d = 4, 40, 128
+    cs = [R.make_relation_case(s, N, d, H) for s in (21, 22)]
+    P = {k: torch.from_numpy(cs[0][k]).cuda() for k in NAMES if k != 'X'}
+    X = torch.stack([torch.from_numpy(c['X']) for c in cs]).cuda()
+    boxes = torch.stack([torch.from_numpy(c['boxes']) for c in cs]).cuda()
+    dOut = torch.randn(2, N, d, device='cuda')
+    args = [P[k] for k in ('Wq', 'bq', 'Wk', 'bk', 'Wg', 'bg', 'Wout', 'bout')]
+    both = ops.relation_backward(dOut, X, boxes, *args, group=H, residual_relu=True)
+    singles = [ops.relation_backward(dOut[b], X[b], boxes[b], *args, group=H, residual_relu=True) for b in range(2)]
+    for k in NAMES:
+        want = torch.stack([s['X'] for s in singles]) if k == 'X' else singles[0][k] + singles[1][k]
+        if k == 'bk':
+            assert both[k].abs().max().item() <= 1e-4 * both['bq'].abs().max().item()
+            continue
+        assert rel_err(both[k].cpu().numpy(), want.cpu().numpy()) <= 1e-5, k
+    with pytest.raises(relnet_b200._lib.RelnetError):
+        ops.relation_backward(dOut[0, :, :7], X[0], boxes[0], *args, group=H)

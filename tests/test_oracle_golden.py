@@ -123,3 +123,15 @@ def test_nms_multi_target_oracle_matches_reference_execution():
     # a class without gt boxes, and a gt nobody overlaps, produce no positives
     gt2 = g['gt_box'].copy(); gt2[0, :, :4] += 5000
     assert L.nms_multi_target(g['bbox'], gt2, g['score'], g['target_thresh']).sum() == 0
+
+
+def test_torch_oracle_forward_equals_numpy_oracle():
+    """oracle/relation_torch.py (autograd oracle of rn_relation_bwd) restates the same function as relation_np."""
+    import torch
+    from oracle import relation_np as R, relation_torch as RT
+    for seed, N, d, H, M, res in ((3, 70, 256, 4, 50, True), (4, 60, 128, 16, None, False)):
+        c = R.make_relation_case(seed, N, d, H, M=M)
+        args = [c[k] for k in ('X', 'boxes', 'Wq', 'bq', 'Wk', 'bk', 'Wg', 'bg', 'Wout', 'bout')]
+        ref = R.relation_forward(*args, key_index=M, group=H, residual_relu=res, dtype=np.float64)
+        out = RT.relation_forward(*[torch.tensor(a, dtype=torch.float64) for a in args], key_index=M, group=H, residual_relu=res)
+        assert np.abs(out.numpy() - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
