@@ -230,6 +230,11 @@ int rn_proposal_target_fwd(const rn_proposal_target_desc* desc, const float* roi
 int rn_roi_pool_fwd(const float* data, const float* rois, int32_t R, int32_t C, int32_t H, int32_t W, int32_t PH,
                     int32_t PW, float spatial_scale, float* out, int32_t* argmax, rn_stream_t stream);
 
+/* ROIPooling backward (MXNet 1.1.0 ROIPoolBackwardAcc): ddata [B,C,H,W] is OVERWRITTEN with the gradient routed to the
+ * argmax elements recorded by rn_roi_pool_fwd. */
+int rn_roi_pool_bwd(const float* dout, const int32_t* argmax, const float* rois, int32_t R, int32_t B, int32_t C, int32_t H,
+                    int32_t W, int32_t PH, int32_t PW, float* ddata, rn_stream_t stream);
+
 /* DeformablePSROIPooling forward (operator_cxx/deformable_psroi_pooling.cu:52-138; = average ROIAlign when no_trans,
  * group_size 1).  trans [R, 2*num_classes, part, part] or NULL when no_trans.  top_count may be NULL. */
 typedef struct rn_psroi_desc {
@@ -242,6 +247,13 @@ typedef struct rn_psroi_desc {
 int rn_deform_psroi_pool_fwd(const rn_psroi_desc* desc, const float* data, const float* rois, const float* trans,
                              float* out, float* top_count, rn_stream_t stream);
 
+/* DeformablePSROIPooling backward (operator_cxx/deformable_psroi_pooling.cu:177-289).  B = batch size of data; dout and
+ * top_count as produced by the forward; ddata [B,channels,H,W] and dtrans (shape of trans; NULL when no_trans) are
+ * OVERWRITTEN.  Accumulation uses atomics: equal to the reference up to float summation order. */
+int rn_deform_psroi_pool_bwd(const rn_psroi_desc* desc, int32_t B, const float* dout, const float* top_count,
+                             const float* data, const float* rois, const float* trans, float* ddata, float* dtrans,
+                             rn_stream_t stream);
+
 /* DeformableConvolution forward (operator_cxx/deformable_convolution-inl.h:91-144 + nn/deformable_im2col.cuh:216-309).
  * data [B,C,H,W], offset [B, dg*2*kh*kw, Ho, Wo], weight [Co, C/groups, kh, kw], bias [Co] or NULL -> out [B,Co,Ho,Wo] */
 typedef struct rn_deform_conv_desc {
@@ -253,6 +265,13 @@ typedef struct rn_deform_conv_desc {
 size_t rn_deform_conv_workspace_bytes(const rn_deform_conv_desc* desc);
 int rn_deform_conv_fwd(const rn_deform_conv_desc* desc, const float* data, const float* offset, const float* weight,
                        const float* bias, float* out, void* workspace, size_t workspace_bytes, rn_stream_t stream);
+/* DeformableConvolution backward (operator_cxx/deformable_convolution-inl.h:145-233; col2im / col2im_coord kernels
+ * nn/deformable_im2col.cuh:315-458).  ddata, doffset, dweight, dbias (NULL when no bias) are OVERWRITTEN; workspace as for
+ * the forward (rn_deform_conv_workspace_bytes).  weight_grad_deformed = 0 is the REFERENCE: its dWeight is computed from
+ * the plain (un-deformed) im2col of data (:215); 1 uses the deformed sampling (the gradient later MXNet releases compute). */
+int rn_deform_conv_bwd(const rn_deform_conv_desc* desc, const float* dout, const float* data, const float* offset,
+                       const float* weight, int32_t weight_grad_deformed, float* ddata, float* doffset, float* dweight,
+                       float* dbias, void* workspace, size_t workspace_bytes, rn_stream_t stream);
 /* the im2col stage alone (tests): col [C*kh*kw, Ho, Wo] for image b */
 int rn_deform_im2col(const rn_deform_conv_desc* desc, const float* data_b, const float* offset_b, float* col,
                      rn_stream_t stream);

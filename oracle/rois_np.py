@@ -113,3 +113,72 @@ def ref_gpu_nms(sorted_dets, thresh, device_id=0):
     num = ctypes.c_int(0)
     fn(_p(keep, ctypes.c_int), ctypes.byref(num), _p(d), d.shape[0], d.shape[1], ctypes.c_float(thresh), device_id)
     return keep[:num.value].astype(np.int64)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# backward (training) restatements
+def roi_pool_backward(dout, argmax, rois, data_shape):
+    dout = np.ascontiguousarray(dout, np.float32); argmax = np.ascontiguousarray(argmax, np.int32)
+    rois = np.ascontiguousarray(rois, np.float32)
+    B, C, H, W = data_shape
+    R, _, PH, PW = dout.shape
+    dd = np.empty(data_shape, np.float32)
+    lib().oracle_roi_pool_bwd(_p(dout), _p(argmax, ctypes.c_int), _p(rois), R, B, C, H, W, PH, PW, _p(dd))
+    return dd
+
+
+def deform_psroi_pool_backward(dout, top_count, data, rois, trans=None, spatial_scale=0.0625, output_dim=256,
+                               group_size=1, pooled_size=7, part_size=0, sample_per_part=4, trans_std=0.0, no_trans=None):
+    data = np.ascontiguousarray(data, np.float32); rois = np.ascontiguousarray(rois, np.float32)
+    dout = np.ascontiguousarray(dout, np.float32); top_count = np.ascontiguousarray(top_count, np.float32)
+    if no_trans is None:
+        no_trans = trans is None
+    part = part_size or pooled_size
+    B, C, H, W = data.shape; R = rois.shape[0]
+    ncls = 1 if no_trans else trans.shape[1] // 2
+    t = np.zeros(1, np.float32) if no_trans else np.ascontiguousarray(trans, np.float32)
+    dd = np.empty_like(data)
+    dt = np.zeros(1, np.float32) if no_trans else np.empty_like(t)
+    lib().oracle_deform_psroi_pool_bwd(_p(dout), _p(top_count), _p(data), _p(rois), _p(t), R, B, C, H, W,
+                                       int(bool(no_trans)), ctypes.c_float(spatial_scale), output_dim, group_size,
+                                       pooled_size, part, sample_per_part, ctypes.c_float(trans_std), ncls, _p(dd), _p(dt))
+    return dd, (None if no_trans else dt)
+
+
+def _conv_geom(shape, kernel, pad, stride, dilate):
+    C, H, W = shape
+    kh, kw = kernel
+    Ho = (H + 2 * pad[0] - (dilate[0] * (kh - 1) + 1)) // stride[0] + 1
+    Wo = (W + 2 * pad[1] - (dilate[1] * (kw - 1) + 1)) // stride[1] + 1
+    return C, H, W, kh, kw, Ho, Wo
+
+
+def deform_conv_backward(dout, data, offset, weight, kernel=(3, 3), pad=(2, 2), stride=(1, 1), dilate=(2, 2),
+                         num_deformable_group=4, num_group=1, weight_grad_deformed=False, has_bias=False):
+    """DeformableConvolutionOp::Backward (deformable_convolution-inl.h:145-233).  Returns ddata, doffset, dweight[, dbias].
+    weight_grad_deformed=False is the REFERENCE: its dWeight uses the plain im2col of the data (:215), not the deformed
+    sampling; True gives the mathematically consistent gradient (later MXNet releases)."""
+    data = np.ascontiguousarray(data, np.float32); offset = np.ascontiguousarray(offset, np.float32)
+    dout = np.ascontiguousarray(dout, np.float32); weight = np.asarray(weight, np.float32)
+    B = data.shape[0]
+    C, H, W, kh, kw, Ho, Wo = _conv_geom(data.shape[1:], kernel, pad, stride, dilate)
+    Co = weight.shape[0]
+    G = num_group
+    w3 = weight.reshape(G, Co // G, -1)
+    ddata = np.zeros_like(data); doff = np.empty_like(offset); dw = np.zeros_like(w3)
+    geo = (C, H, W, kh, kw, pad[0], pad[1], stride[0], stride[1], dilate[0], dilate[1])
+    for n in range(B):
+        og = dout[n].reshape(G, Co // G, Ho * Wo)
+        col = np.ascontiguousarray(np.matmul(w3.transpose(0, 2, 1), og).reshape(C * kh * kw, Ho, Wo), np.float32)
+        lib().oracle_deform_col2im_coord(_p(col), _p(data[n]), _p(offset[n]), *geo, num_deformable_group, Ho, Wo, _p(doff[n]))
+        lib().oracle_deform_col2im(_p(col), _p(offset[n]), *geo, num_deformable_group, Ho, Wo, _p(ddata[n]))
+        if weight_grad_deformed:
+            c2 = deform_im2col(data[n], offset[n], kernel, pad, stride, dilate, num_deformable_group)
+        else:
+            c2 = np.empty((C * kh * kw, Ho, Wo), np.float32)
+            lib().oracle_im2col(_p(data[n]), *geo, Ho, Wo, _p(c2))
+        dw += np.matmul(og, c2.reshape(G, -1, Ho * Wo).transpose(0, 2, 1))
+    res = [ddata, doff, dw.reshape(weight.shape).astype(np.float32)]
+    if has_bias:
+        res.append(dout.sum(axis=(0, 2, 3)).astype(np.float32))
+    return res

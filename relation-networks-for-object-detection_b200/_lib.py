@@ -87,6 +87,9 @@ SIGNATURES = {
     'rn_bbox_overlaps': (C.c_int, [c_p, c_p, c_i, c_i, c_p, c_p]),
     'rn_proposal_target_fwd': (C.c_int, [C.POINTER(ProposalTargetDesc)] + [c_p] * 6 + [c_p]),
     'rn_roi_pool_fwd': (C.c_int, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p, c_p, c_p]),
+    'rn_roi_pool_bwd': (C.c_int, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
+    'rn_deform_psroi_pool_bwd': (C.c_int, [C.POINTER(PsroiDesc), c_i] + [c_p] * 7 + [c_p]),
+    'rn_deform_conv_bwd': (C.c_int, [C.POINTER(DeformConvDesc)] + [c_p] * 4 + [c_i] + [c_p] * 4 + [c_p, c_sz, c_p]),
     'rn_deform_psroi_pool_fwd': (C.c_int, [C.POINTER(PsroiDesc)] + [c_p] * 5 + [c_p]),
     'rn_deform_conv_workspace_bytes': (c_sz, [C.POINTER(DeformConvDesc)]),
     'rn_deform_conv_fwd': (C.c_int, [C.POINTER(DeformConvDesc)] + [c_p] * 5 + [c_p, c_sz, c_p]),

@@ -361,6 +361,19 @@ def roi_pool(data, rois, pooled_size=(7, 7), spatial_scale=0.0625, return_argmax
     return (out, arg) if return_argmax else out
 
 
+def roi_pool_backward(grad_out, argmax, rois, data_shape):
+    """Gradient of `roi_pool` w.r.t. data (argmax from roi_pool(..., return_argmax=True)) -- rn_roi_pool_bwd."""
+    grad_out = _f32(grad_out, 'grad_out'); rois = _f32(rois, 'rois')
+    if argmax.dtype != torch.int32 or not argmax.is_cuda or tuple(argmax.shape) != tuple(grad_out.shape):
+        raise L.RelnetError('roi_pool_backward: argmax must be the int32 CUDA tensor returned by roi_pool')
+    B, Cc, H, W = data_shape
+    R, _, PH, PW = grad_out.shape
+    dd = torch.empty(tuple(data_shape), dtype=torch.float32, device=grad_out.device)
+    L.check(L.lib().rn_roi_pool_bwd(_ptr(grad_out), _ptr(argmax.contiguous()), _ptr(rois), R, B, Cc, H, W, PH, PW, _ptr(dd),
+                                    _stream()), 'rn_roi_pool_bwd')
+    return dd
+
+
 def roi_pool_fc(data, rois, W, b, pooled_size=(7, 7), spatial_scale=0.0625, relu=False):
     """ROIPooling + FullyConnected fused at the data-layout level (SYM_REL:252-262 with RN_PREC_F16): channels-last
     feature map -> fp16 pooled [R, PH*PW*C] -> tcgen05 GEMM against the K-permuted packed weight.  Returns fp32 [R, out].
@@ -406,6 +419,27 @@ def deform_psroi_pool(data, rois, trans=None, spatial_scale=0.0625, output_dim=2
     return (out, cnt) if return_count else out
 
 
+def deform_psroi_pool_backward(grad_out, top_count, data, rois, trans=None, spatial_scale=0.0625, output_dim=256,
+                               group_size=1, pooled_size=7, part_size=0, sample_per_part=4, trans_std=0.0, no_trans=None):
+    """Gradients of `deform_psroi_pool` w.r.t. data and trans -- rn_deform_psroi_pool_bwd."""
+    data = _f32(data, 'data'); rois = _f32(rois, 'rois'); grad_out = _f32(grad_out, 'grad_out')
+    top_count = _f32(top_count, 'top_count')
+    if no_trans is None:
+        no_trans = trans is None
+    t = _f32(trans, 'trans') if not no_trans else None
+    B, Cc, H, W = data.shape
+    R = rois.shape[0]
+    if tuple(grad_out.shape) != (R, output_dim, pooled_size, pooled_size) or grad_out.shape != top_count.shape:
+        raise L.RelnetError('deform_psroi_pool_backward: grad_out / top_count shape %s / %s' % (tuple(grad_out.shape), tuple(top_count.shape)))
+    desc = L.PsroiDesc(R, Cc, H, W, spatial_scale, output_dim, group_size, pooled_size, part_size or pooled_size,
+                       sample_per_part, trans_std, int(bool(no_trans)), 1 if no_trans else t.shape[1] // 2)
+    dd = torch.empty_like(data)
+    dt = torch.empty_like(t) if t is not None else None
+    L.check(L.lib().rn_deform_psroi_pool_bwd(C.byref(desc), B, _ptr(grad_out), _ptr(top_count), _ptr(data), _ptr(rois),
+                                             _ptr(t), _ptr(dd), _ptr(dt), _stream()), 'rn_deform_psroi_pool_bwd')
+    return dd, dt
+
+
 def _dc_desc(data, weight, kernel, pad, stride, dilate, num_group, num_deformable_group, precision):
     B, Cc, H, W = data.shape
     return L.DeformConvDesc(B, Cc, H, W, weight.shape[0], kernel[0], kernel[1], pad[0], pad[1], stride[0], stride[1],
@@ -424,6 +458,25 @@ def deform_conv(data, offset, weight, bias=None, kernel=(3, 3), pad=(2, 2), stri
     L.check(lib.rn_deform_conv_fwd(C.byref(desc), _ptr(data), _ptr(offset), _ptr(weight), _ptr(bias), _ptr(out), _ptr(ws),
                                    ws.numel(), _stream()), 'rn_deform_conv_fwd')
     return out
+
+
+def deform_conv_backward(grad_out, data, offset, weight, kernel=(3, 3), pad=(2, 2), stride=(1, 1), dilate=(2, 2),
+                         num_group=1, num_deformable_group=4, has_bias=False, weight_grad_deformed=False):
+    """Gradients of `deform_conv` -- rn_deform_conv_bwd.  Returns (ddata, doffset, dweight, dbias or None).
+    weight_grad_deformed=False reproduces the reference's dWeight (plain im2col, deformable_convolution-inl.h:215)."""
+    data = _f32(data, 'data'); offset = _f32(offset, 'offset'); weight = _f32(weight, 'weight')
+    grad_out = _f32(grad_out, 'grad_out')
+    desc = _dc_desc(data, weight, kernel, pad, stride, dilate, num_group, num_deformable_group, 'fp32')
+    if tuple(grad_out.shape) != (data.shape[0], weight.shape[0], offset.shape[2], offset.shape[3]):
+        raise L.RelnetError('deform_conv_backward: grad_out shape %s' % (tuple(grad_out.shape),))
+    dd = torch.empty_like(data); do = torch.empty_like(offset); dw = torch.empty_like(weight)
+    db = torch.empty(weight.shape[0], dtype=torch.float32, device=data.device) if has_bias else None
+    lib = L.lib()
+    ws = _workspace(lib.rn_deform_conv_workspace_bytes(C.byref(desc)), data.device)
+    L.check(lib.rn_deform_conv_bwd(C.byref(desc), _ptr(grad_out), _ptr(data), _ptr(offset), _ptr(weight),
+                                   int(bool(weight_grad_deformed)), _ptr(dd), _ptr(do), _ptr(dw), _ptr(db), _ptr(ws),
+                                   ws.numel(), _stream()), 'rn_deform_conv_bwd')
+    return dd, do, dw, db
 
 
 def deform_im2col(im, offset, kernel=(3, 3), pad=(2, 2), stride=(1, 1), dilate=(2, 2), num_deformable_group=4):

@@ -85,3 +85,98 @@ def test_relation_backward_batched_and_loud(ops):
         assert rel_err(both[k].cpu().numpy(), want.cpu().numpy()) <= 1e-5, k
     with pytest.raises(relnet_b200._lib.RelnetError):
         ops.relation_backward(dOut[0, :, :7], X[0], boxes[0], *args, group=H)
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def test_roi_pool_backward_matches_oracle(ops):
+    from oracle import rois_np as RO
+    rng = np.random.RandomState(31)
+    data = rng.randn(2, 64, 38, 63).astype(np.float32)
+    R = 200
+    x1 = rng.uniform(0, 800, R); y1 = rng.uniform(0, 450, R)
+    rois = np.stack([rng.randint(0, 2, R), x1, y1, np.minimum(x1 + rng.uniform(8, 500, R), 999),
+                     np.minimum(y1 + rng.uniform(8, 400, R), 599)], 1).astype(np.float32)
+    out, arg = ops.roi_pool(T(data), T(rois), (7, 7), 0.0625, return_argmax=True)
+    o_ref, a_ref = RO.roi_pool(data, rois, (7, 7), 0.0625)
+    assert np.array_equal(arg.cpu().numpy(), a_ref)
+    dout = rng.randn(*o_ref.shape).astype(np.float32)
+    got = ops.roi_pool_backward(T(dout), arg, T(rois), data.shape).cpu().numpy()
+    want = RO.roi_pool_backward(dout, a_ref, rois, data.shape)
+    assert rel_err(got, want) <= 1e-5
+    assert ops.roi_pool_backward(T(dout[:0]), arg[:0], T(rois[:0]), data.shape).abs().max().item() == 0.0   # no rois
+
+
+@pytest.mark.parametrize('with_trans', [False, True])
+def test_deform_psroi_pool_backward_matches_oracle(ops, with_trans):
+    from oracle import rois_np as RO
+    rng = np.random.RandomState(32)
+    B, C, H, W, R = 1, 256, 38, 63, 128
+    data = rng.randn(B, C, H, W).astype(np.float32)
+    x1 = rng.uniform(0, 800, R); y1 = rng.uniform(0, 450, R)
+    rois = np.stack([np.zeros(R), x1, y1, np.minimum(x1 + rng.uniform(8, 500, R), 999),
+                     np.minimum(y1 + rng.uniform(8, 400, R), 599)], 1).astype(np.float32)
+    trans = (rng.randn(R, 2, 7, 7)).astype(np.float32) if with_trans else None
+    kw = dict(spatial_scale=0.0625, output_dim=C, group_size=1, pooled_size=7, sample_per_part=4, trans_std=0.1)
+    out, cnt = RO.deform_psroi_pool(data, rois, trans, **kw)
+    dout = rng.randn(*out.shape).astype(np.float32)
+    want_d, want_t = RO.deform_psroi_pool_backward(dout, cnt, data, rois, trans, **kw)
+    o, c = ops.deform_psroi_pool(T(data), T(rois), T(trans) if with_trans else None, return_count=True, **kw)
+    assert np.array_equal(c.cpu().numpy(), cnt)
+    dd, dt = ops.deform_psroi_pool_backward(T(dout), c, T(data), T(rois), T(trans) if with_trans else None, **kw)
+    assert rel_err(dd.cpu().numpy(), want_d) <= 1e-5        # atomics: summation order only
+    if with_trans:
+        assert rel_err(dt.cpu().numpy(), want_t) <= 1e-4
+    else:
+        assert dt is None
+
+
+@pytest.mark.parametrize('deformed', [False, True])
+def test_deform_conv_backward_matches_oracle(ops, deformed):
+    from oracle import rois_np as RO
+    rng = np.random.RandomState(33)
+    B, C, H, W, Co, dg = 2, 32, 19, 23, 24, 4
+    data = rng.randn(B, C, H, W).astype(np.float32)
+    offset = (rng.randn(B, dg * 18, H, W) * 1.5).astype(np.float32)      # many samples leave the map / hit the borders
+    weight = (rng.randn(Co, C, 3, 3) * 0.1).astype(np.float32)
+    dout = rng.randn(B, Co, H, W).astype(np.float32)
+    want = RO.deform_conv_backward(dout, data, offset, weight, num_deformable_group=dg, weight_grad_deformed=deformed,
+                                   has_bias=True)
+    got = ops.deform_conv_backward(T(dout), T(data), T(offset), T(weight), num_deformable_group=dg,
+                                   weight_grad_deformed=deformed, has_bias=True)
+    for g, w, name in zip(got, want, ('data', 'offset', 'weight', 'bias')):
+        e = rel_err(g.cpu().numpy(), w)
+        print('deform_conv d%-6s %.2e' % (name, e))
+        assert e <= 2e-5, name
+
+
+def test_deform_conv_weight_grad_modes_differ(ops):
+    """the reference's plain-im2col dWeight and the deformed one are different functions once offsets are non-zero, and
+    coincide for zero offsets (the reference's offset convs are zero-initialised, SYM_DCN_REL_NMS:1525-1530)"""
+    rng = np.random.RandomState(35)
+    data = T(rng.randn(1, 8, 12, 14).astype(np.float32)); weight = T((rng.randn(6, 8, 3, 3) * 0.1).astype(np.float32))
+    dout = T(rng.randn(1, 6, 12, 14).astype(np.float32))
+    off = T((rng.randn(1, 36, 12, 14)).astype(np.float32))
+    a = ops.deform_conv_backward(dout, data, off, weight, num_deformable_group=2, weight_grad_deformed=False)[2]
+    b = ops.deform_conv_backward(dout, data, off, weight, num_deformable_group=2, weight_grad_deformed=True)[2]
+    assert rel_err(a.cpu().numpy(), b.cpu().numpy()) > 1e-2
+    z = torch.zeros_like(off)
+    a = ops.deform_conv_backward(dout, data, z, weight, num_deformable_group=2, weight_grad_deformed=False)[2]
+    b = ops.deform_conv_backward(dout, data, z, weight, num_deformable_group=2, weight_grad_deformed=True)[2]
+    assert rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 1e-6
+
+
+def test_deform_conv_backward_grouped(ops):
+    from oracle import rois_np as RO
+    rng = np.random.RandomState(34)
+    B, C, H, W, Co, dg, G = 1, 16, 10, 12, 8, 2, 2
+    data = rng.randn(B, C, H, W).astype(np.float32)
+    offset = (rng.randn(B, dg * 18, H, W) * 0.7).astype(np.float32)
+    weight = (rng.randn(Co, C // G, 3, 3) * 0.1).astype(np.float32)
+    dout = rng.randn(B, Co, H, W).astype(np.float32)
+    want = RO.deform_conv_backward(dout, data, offset, weight, num_deformable_group=dg, num_group=G)
+    got = ops.deform_conv_backward(T(dout), T(data), T(offset), T(weight), num_deformable_group=dg, num_group=G)
+    for g, w, name in zip(got[:3], want, ('data', 'offset', 'weight')):
+        assert rel_err(g.cpu().numpy(), w) <= 2e-5, name

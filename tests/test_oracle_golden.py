@@ -135,3 +135,77 @@ def test_torch_oracle_forward_equals_numpy_oracle():
         ref = R.relation_forward(*args, key_index=M, group=H, residual_relu=res, dtype=np.float64)
         out = RT.relation_forward(*[torch.tensor(a, dtype=torch.float64) for a in args], key_index=M, group=H, residual_relu=res)
         assert np.abs(out.numpy() - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
+
+
+def _deform_conv_case(seed, B=2, C=8, H=9, W=11, Co=6, dg=2, scale=0.6):
+    rng = np.random.RandomState(seed)
+    data = rng.randn(B, C, H, W).astype(np.float32)
+    offset = (rng.randn(B, dg * 18, H, W) * scale).astype(np.float32)
+    weight = (rng.randn(Co, C, 3, 3) * 0.2).astype(np.float32)
+    dout = rng.randn(B, Co, H, W).astype(np.float32)
+    return data, offset, weight, dout
+
+
+def test_oracle_deform_conv_backward_equals_autograd():
+    """C restatement of the reference's col2im / col2im_coord kernels == autograd through the (C-oracle-checked) forward."""
+    import torch
+    from oracle import rois_np as RO, rois_torch as RT
+    data, offset, weight, dout = _deform_conv_case(5)
+    t = [torch.tensor(a, dtype=torch.float64, requires_grad=True) for a in (data, offset, weight)]
+    out = RT.deform_conv(t[0], t[1], t[2], num_deformable_group=2)
+    fwd = RO.deform_conv(data, offset, weight, num_deformable_group=2)
+    assert np.abs(out.detach().numpy() - fwd).max() <= 1e-4
+    out.backward(torch.tensor(dout, dtype=torch.float64))
+    dd, do, dw = RO.deform_conv_backward(dout, data, offset, weight, num_deformable_group=2, weight_grad_deformed=True)
+    for got, want, name in ((dd, t[0].grad, 'data'), (do, t[1].grad, 'offset'), (dw, t[2].grad, 'weight')):
+        assert rel_err(got, want.numpy()) <= 1e-4, name
+    # the reference's dWeight (deformable_convolution-inl.h:215) is the gradient of the UN-deformed dilated convolution
+    tw = torch.tensor(weight, dtype=torch.float64, requires_grad=True)
+    torch.nn.functional.conv2d(torch.tensor(data, dtype=torch.float64), tw, padding=2, dilation=2).backward(
+        torch.tensor(dout, dtype=torch.float64))
+    dw_ref = RO.deform_conv_backward(dout, data, offset, weight, num_deformable_group=2)[2]
+    assert rel_err(dw_ref, tw.grad.numpy()) <= 1e-4
+
+
+def test_oracle_deform_psroi_backward_equals_autograd():
+    import torch
+    from oracle import rois_np as RO, rois_torch as RT
+    rng = np.random.RandomState(9)
+    B, C, H, W, R, P = 2, 8, 12, 16, 10, 3
+    data = rng.randn(B, C, H, W).astype(np.float32)
+    x1 = rng.uniform(0, 150, R); y1 = rng.uniform(0, 100, R)
+    rois = np.stack([rng.randint(0, B, R), x1, y1, x1 + rng.uniform(20, 100, R), y1 + rng.uniform(20, 90, R)], 1).astype(np.float32)
+    trans = rng.randn(R, 2, P, P).astype(np.float32)
+    kw = dict(spatial_scale=0.0625, output_dim=C, group_size=1, pooled_size=P, sample_per_part=2, trans_std=0.1)
+    for tr in (None, trans):
+        out, cnt = RO.deform_psroi_pool(data, rois, tr, **kw)
+        dout = rng.randn(*out.shape).astype(np.float32)
+        td = torch.tensor(data, dtype=torch.float64, requires_grad=True)
+        tt = None if tr is None else torch.tensor(tr, dtype=torch.float64, requires_grad=True)
+        o, c = RT.deform_psroi_pool(td, torch.tensor(rois, dtype=torch.float64), tt, **kw)
+        assert np.abs(o.detach().numpy() - out).max() <= 1e-5 and np.array_equal(c.numpy(), cnt)
+        o.backward(torch.tensor(dout, dtype=torch.float64))
+        dd, dt = RO.deform_psroi_pool_backward(dout, cnt, data, rois, tr, **kw)
+        assert rel_err(dd, td.grad.numpy()) <= 1e-5
+        if tr is not None:
+            assert rel_err(dt, tt.grad.numpy()) <= 1e-4
+
+
+def test_oracle_roi_pool_backward_routes_to_argmax():
+    import torch
+    from oracle import rois_np as RO
+    rng = np.random.RandomState(2)
+    data = rng.randn(2, 4, 20, 30).astype(np.float32)
+    rois = np.array([[0, 10, 20, 300, 200], [1, 100, 50, 400, 310], [0, 0, 0, 479, 319]], np.float32)
+    out, arg = RO.roi_pool(data, rois, (7, 7), 0.0625)
+    dout = rng.randn(*out.shape).astype(np.float32)
+    dd = RO.roi_pool_backward(dout, arg, rois, data.shape)
+    # max pooling: d out / d data is 1 at the argmax; compare with a direct scatter in float64
+    want = np.zeros(data.shape, np.float64)
+    for n in range(3):
+        for c in range(4):
+            for p in range(49):
+                a = arg[n, c].reshape(-1)[p]
+                if a >= 0:
+                    want[int(rois[n, 0]), c].reshape(-1)[a] += dout[n, c].reshape(-1)[p]
+    assert rel_err(dd, want) <= 1e-6
