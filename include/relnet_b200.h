@@ -176,6 +176,45 @@ int rn_learn_nms_fwd(const rn_learn_nms_desc* desc, const float* cls_score, cons
                      const int32_t* non_gt_index, float* nms_multi_score, float* sorted_bbox, float* sorted_score,
                      float* final_score, void* workspace, size_t workspace_bytes, rn_stream_t stream);
 
+/* ---- training side of the learn-NMS head ------------------------------------------------------------------------
+ * Gradient buffers, one per entry of rn_learn_nms_weights (same shapes); all are OVERWRITTEN by rn_learn_nms_bwd. */
+typedef struct rn_learn_nms_grads {
+  float *nms_rank_weight, *nms_rank_bias;
+  float *roi_feat_embedding_weight, *roi_feat_embedding_bias;
+  float *nms_pair_pos_fc1_1_weight, *nms_pair_pos_fc1_1_bias;
+  float *nms_query_1_weight, *nms_query_1_bias;
+  float *nms_key_1_weight, *nms_key_1_bias;
+  float *nms_linear_out_1_weight, *nms_linear_out_1_bias;
+  float *nms_logit_weight, *nms_logit_bias;
+} rn_learn_nms_grads;
+
+/* Backward of the learn-NMS head (the reference differentiates the train graph, ..._multi_head_16_learn_nms.py:424-501,
+ * with MXNet autograd; no backward source exists).  Inputs as rn_learn_nms_fwd (use class_thresh = 0 for the train graph,
+ * which prunes no class); d_multi [n,C,T] = d loss / d nms_multi_score.  Outputs: the 14 weight gradients, d_cls_score
+ * [R,num_classes] (through the sorted softmax scores) and d_feat [R,feat_dim] (through roi_feat_embedding); bbox_pred /
+ * rois get none (BlockGrad, :428).  fp32; the forward is recomputed inside, nothing has to be saved. */
+size_t rn_learn_nms_bwd_workspace_bytes(const rn_learn_nms_desc* desc);
+int rn_learn_nms_bwd(const rn_learn_nms_desc* desc, const float* cls_score, const float* bbox_pred, const float* rois,
+                     const float* im_info, const float* feat, const rn_learn_nms_weights* w, const int32_t* non_gt_index,
+                     const float* d_multi, const rn_learn_nms_grads* grads, float* d_cls_score, float* d_feat,
+                     void* workspace, size_t workspace_bytes, rn_stream_t stream);
+
+/* learn-NMS loss (..._learn_nms.py:539-551): pos = -target*log(score+eps)*loss_scale/(first_n*num_thresh), neg likewise
+ * with (1-target), (1-score); d_multi = pos_grad_scale * d pos + d neg  (MakeLoss sends grad_scale back; TRAIN.nms_pos_scale
+ * = 4, nms_loss_scale = 1, eps = 1e-8: config.py:73-74).  Any of pos_loss / neg_loss / d_multi [n,C,T] may be NULL. */
+int rn_nms_loss(const float* nms_multi_score, const float* nms_multi_target, int32_t first_n, int32_t C, int32_t num_thresh,
+                float loss_scale, float pos_grad_scale, float eps, float* pos_loss, float* neg_loss, float* d_multi,
+                rn_stream_t stream);
+
+/* `BoxAnnotatorOHEM` CustomOp forward (relation_rcnn/operator_py/box_annotator_ohem.py:26-53): keep the roi_per_img rois
+ * of largest (softmax cross-entropy + weighted smooth-L1) loss; the others get label -1 and zero box weights.
+ * cls_score [R,num_classes], bbox_pred/bbox_targets/bbox_weights [R,4*num_reg_classes], labels [R] (float-valued).
+ * per_roi_loss [R] is written too.  Ties: larger roi index ranks first. */
+int rn_box_annotator_ohem(const float* cls_score, const float* bbox_pred, const float* labels, const float* bbox_targets,
+                          const float* bbox_weights, int32_t R, int32_t num_classes, int32_t num_reg_classes,
+                          int32_t roi_per_img, float* labels_ohem, float* bbox_weights_ohem, float* per_roi_loss,
+                          rn_stream_t stream);
+
 /* `nms_multi_target` CustomOp forward (relation_rcnn/operator_py/nms_multi_target.py:24-74): learn-NMS training labels.
  * bbox [n,C,4], gt_boxes [G,5] (x1,y1,x2,y2,cls), score [n,C], target_thresh HOST double[T] -> out [n,C,T] (0/1). */
 int rn_nms_multi_target_fwd(const float* bbox, const float* gt_boxes, const float* score, int32_t n, int32_t C, int32_t G,

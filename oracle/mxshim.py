@@ -198,7 +198,14 @@ def Activation(data=None, act_type=None, name=None):
     return {'relu': relu, 'sigmoid': sigmoid}[act_type](data)
 def mean(data=None, axis=None, name=None): return ND(_a(data).mean(axis=axis, dtype=F32))
 def max(data=None, axis=None, name=None): return ND(_a(data).max(axis=axis))   # noqa: A001
-def sum(data=None, axis=None, name=None): return ND(_a(data).sum(axis=axis, dtype=F32))   # noqa: A001
+def sum(data=None, axis=None, name=None):   # noqa: A001
+    x = _a(data)
+    if axis == 1 and x.ndim == 2:       # sequential float32 accumulation (MXNet CPU reduce order), not numpy's pairwise
+        acc = np.zeros(x.shape[0], F32)
+        for j in range(x.shape[1]):
+            acc = (acc + x[:, j].astype(F32)).astype(F32)
+        return ND(acc)
+    return ND(x.sum(axis=axis, dtype=F32))
 
 
 # ----------------------------------------------------------------------------------------------
@@ -258,6 +265,24 @@ def softmax(data=None, axis=-1, name=None):
     m = x.max(axis=axis, keepdims=True)
     e = np.exp(x - m)
     return ND(e / e.sum(axis=axis, keepdims=True, dtype=F32))
+
+
+def SoftmaxActivation(data=None, mode='instance', name=None):
+    """softmax over axis 1 (mode='instance'); exp(x - max) summed sequentially in float32 like mshadow's Softmax"""
+    x = _a(data).astype(F32)
+    e = np.exp(x - x.max(axis=1, keepdims=True))
+    s = np.zeros(x.shape[0], F32)
+    for c in range(x.shape[1]):
+        s = (s + e[:, c]).astype(F32)
+    return ND((e / s[:, None]).astype(F32))
+
+
+def smooth_l1(data=None, scalar=1.0, name=None):
+    """f(x) = 0.5 (sigma x)^2 if |x| < 1/sigma^2 else |x| - 0.5/sigma^2   (mshadow_op::smooth_l1_loss)"""
+    x = _a(data).astype(F32)
+    b = F32(scalar); bsq = F32(b * b); ibsq = F32(1.0) / bsq
+    inner = F32(0.5) * ((x * b) * (x * b))
+    return ND(np.where(x > ibsq, x - F32(0.5) * ibsq, np.where(x < -ibsq, -x - F32(0.5) * ibsq, inner)).astype(F32))
 
 
 def sort(data=None, axis=-1, is_ascend=True, name=None):

@@ -149,8 +149,7 @@ def load_reference():
     proposal_target = _load('operator_py.proposal_target', 'relation_rcnn/operator_py/proposal_target.py')
     learn_nms = _load('operator_py.learn_nms', 'relation_rcnn/operator_py/learn_nms.py')
     nms_multi_target = _load('operator_py.nms_multi_target', 'relation_rcnn/operator_py/nms_multi_target.py')
-    ohem = types.ModuleType('operator_py.box_annotator_ohem')
-    sys.modules['operator_py.box_annotator_ohem'] = ohem
+    ohem = _load('operator_py.box_annotator_ohem', 'relation_rcnn/operator_py/box_annotator_ohem.py')
 
     S = 'relation_rcnn/symbols/'
     base = _load('resnet_v1_101_rcnn_base', S + 'resnet_v1_101_rcnn_base.py')
@@ -164,7 +163,7 @@ def load_reference():
     ns = types.SimpleNamespace(
         mx=mx, nd=nd, mxshim=mxshim, bbox_transform=bt, bbox_regression=br, generate_anchor=ga, rcnn=rcnn,
         proposal=proposal, proposal_target=proposal_target, learn_nms=learn_nms,
-        nms_multi_target=nms_multi_target, sym_rel=sym_rel, sym_rel_nms=sym_rel_nms,
+        nms_multi_target=nms_multi_target, box_annotator_ohem=ohem, sym_rel=sym_rel, sym_rel_nms=sym_rel_nms,
         sym_fpn_rel_nms=sym_fpn_rel_nms, nms_base=nms_base, EasyDict=EasyDict)
     _loaded['ns'] = ns
     return ns

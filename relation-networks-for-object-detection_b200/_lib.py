@@ -79,6 +79,11 @@ SIGNATURES = {
     'rn_learn_nms_workspace_bytes': (c_sz, [C.POINTER(LearnNmsDesc)]),
     'rn_learn_nms_fwd': (C.c_int, [C.POINTER(LearnNmsDesc)] + [c_p] * 5 + [C.POINTER(LearnNmsWeights), c_p] + [c_p] * 4 +
                          [c_p, c_sz, c_p]),
+    'rn_learn_nms_bwd_workspace_bytes': (c_sz, [C.POINTER(LearnNmsDesc)]),
+    'rn_learn_nms_bwd': (C.c_int, [C.POINTER(LearnNmsDesc)] + [c_p] * 5 + [C.POINTER(LearnNmsWeights), c_p, c_p, C.POINTER(LearnNmsWeights), c_p, c_p] +
+                         [c_p, c_sz, c_p]),
+    'rn_nms_loss': (C.c_int, [c_p, c_p, c_i, c_i, c_i, c_f, c_f, c_f, c_p, c_p, c_p, c_p]),
+    'rn_box_annotator_ohem': (C.c_int, [c_p] * 5 + [c_i] * 4 + [c_p] * 3 + [c_p]),
     'rn_nms_multi_target_fwd': (C.c_int, [c_p, c_p, c_p, c_i, c_i, c_i, C.POINTER(C.c_double), c_i, c_p, c_p]),
     'rn_proposal_workspace_bytes': (c_sz, [C.POINTER(ProposalDesc)]),
     'rn_proposal_fwd': (C.c_int, [C.POINTER(ProposalDesc), C.POINTER(c_f), C.POINTER(c_f)] + [c_p] * 6 + [c_p, c_sz, c_p]),

@@ -271,6 +271,43 @@ class NmsMultiTargetProp(CustomOpProp):
         return NmsMultiTargetOp(self._target_thresh)
 
 
+# ----------------------------------------------------------------------------------------------- BoxAnnotatorOHEM
+class BoxAnnotatorOHEMOperator(CustomOp):
+    """operator_py/box_annotator_ohem.py:19-58"""
+
+    def __init__(self, num_classes, num_reg_classes, roi_per_img):
+        self._num_classes, self._num_reg_classes, self._roi_per_img = num_classes, num_reg_classes, roi_per_img
+
+    def forward(self, is_train, req, in_data, out_data, aux):
+        lab, w = ops.box_annotator_ohem(in_data[0], in_data[1], in_data[2], in_data[3], in_data[4], self._num_classes,
+                                        self._num_reg_classes, self._roi_per_img)
+        for ind, val in enumerate([lab, w]):
+            self.assign(out_data[ind], req[ind], val)
+
+
+@register('BoxAnnotatorOHEM')
+class BoxAnnotatorOHEMProp(CustomOpProp):
+    """operator_py/box_annotator_ohem.py:61-88 (kwargs arrive as strings)"""
+
+    def __init__(self, num_classes, num_reg_classes, roi_per_img):
+        super(BoxAnnotatorOHEMProp, self).__init__(need_top_grad=False)
+        self._num_classes = int(num_classes)
+        self._num_reg_classes = int(num_reg_classes)
+        self._roi_per_img = int(roi_per_img)
+
+    def list_arguments(self):
+        return ['cls_score', 'bbox_pred', 'labels', 'bbox_targets', 'bbox_weights']
+
+    def list_outputs(self):
+        return ['labels_ohem', 'bbox_weights_ohem']
+
+    def infer_shape(self, in_shape):
+        return in_shape, [in_shape[2], in_shape[4]]
+
+    def create_operator(self, ctx=None, shapes=None, dtypes=None):
+        return BoxAnnotatorOHEMOperator(self._num_classes, self._num_reg_classes, self._roi_per_img)
+
+
 def Custom(op_type, name=None, **kwargs):
     """``mx.sym.Custom(op_type=..., tensor kwargs..., string kwargs...)`` evaluated eagerly on torch tensors."""
     tensors = {k: v for k, v in kwargs.items() if isinstance(v, torch.Tensor)}

@@ -11,11 +11,10 @@
 // Layouts: prob [Rn,C], refined [Rn,4,K], rank_idx [n,C] int32, feat_cls [C,n,128], boxes_cls [C,n,4].
 #include "common.cuh"
 #include "relation.cuh"
+#include "learn_nms.cuh"
 
 namespace rn {
 
-constexpr int kNmsFeat = 128;    // nms_attention_feat_dim (LNMS:223)
-constexpr int kRankDim = 1024;   // rank embedding dim (LNMS:328)
 
 // one warp per roi: the class softmax is evaluated in float32 with MXNet's order (max, then a sequential sum of
 // exp(x - max)); lanes compute the exps in parallel, lane 0 adds them in class order so the sum matches bit for bit
@@ -237,22 +236,16 @@ __global__ void __launch_bounds__(128) nms_multi_target_kernel(const float* __re
   for (int i = threadIdx.x; i < n * T; i += blockDim.x) out[((size_t)(i / T) * C + c) * T + (i % T)] = flag[i] ? 1.f : 0.f;
 }
 
-struct LnmsWs {
-  float *prob, *refined, *cmax, *rank_emb, *rank_feat, *emb, *feat_cls, *boxes_cls, *feat_out, *lg_roi;
-  int *rank_idx, *valid;
-  void* rel_ws; size_t rel_ws_bytes;
-};
-
-static rn_relation_desc inner_desc(const rn_learn_nms_desc* d) {
+rn_relation_desc lnms_inner_desc(const rn_learn_nms_desc* d) {
   rn_relation_desc r;
   r.batch = d->num_classes - 1; r.N = d->first_n; r.M = d->first_n; r.d = kNmsFeat; r.dq = 1024; r.dout = kNmsFeat;
   r.H = 16; r.E = 64; r.wave_length = 1000.f; r.fuse_residual_relu = 1; r.precision = d->precision;
   return r;
 }
 
-static size_t carve(const rn_learn_nms_desc* d, int Rn, void* base, size_t bytes, LnmsWs* w) {
+size_t lnms_carve(const rn_learn_nms_desc* d, int Rn, void* base, size_t bytes, LnmsWs* w) {
   const size_t C = d->num_classes - 1, n = d->first_n, K = d->num_reg_classes - 1;
-  rn_relation_desc rd = inner_desc(d);
+  rn_relation_desc rd = lnms_inner_desc(d);
   const size_t rel = rn_relation_workspace_bytes(&rd) + relation_tc_lnms_extra_bytes(&rd, d->R);
   size_t need = ws_slice((size_t)Rn * C, 4) + ws_slice((size_t)Rn * 4 * K, 4) + ws_slice(C, 4) +
                 ws_slice(n * kRankDim, 4) + ws_slice(n * kNmsFeat, 4) + ws_slice((size_t)d->R * kNmsFeat, 4) +
@@ -277,7 +270,7 @@ static size_t carve(const rn_learn_nms_desc* d, int Rn, void* base, size_t bytes
   return w->rel_ws ? need : 0;
 }
 
-static int selected_rows(const rn_learn_nms_desc* d, const int* non_gt_index) {
+int lnms_selected_rows(const rn_learn_nms_desc* d, const int* non_gt_index) {
   if (d->nongt_dim > 0) return d->nongt_dim;
   if (non_gt_index) return d->num_non_gt;
   return d->R;
@@ -287,7 +280,7 @@ static int selected_rows(const rn_learn_nms_desc* d, const int* non_gt_index) {
 
 extern "C" size_t rn_learn_nms_workspace_bytes(const rn_learn_nms_desc* d) {
   if (!d) return 0;
-  return rn::carve(d, d->R, nullptr, 0, nullptr) + 256;
+  return rn::lnms_carve(d, d->R, nullptr, 0, nullptr) + 256;
 }
 
 extern "C" int rn_learn_nms_fwd(const rn_learn_nms_desc* d, const float* cls_score, const float* bbox_pred,
@@ -299,7 +292,7 @@ extern "C" int rn_learn_nms_fwd(const rn_learn_nms_desc* d, const float* cls_sco
   RN_CHECK_ARG(d && cls_score && bbox_pred && rois && im_info && feat && w && nms_multi_score && sorted_bbox &&
                    sorted_score && wsp, "rn_learn_nms_fwd: null argument");
   const int C = d->num_classes - 1, n = d->first_n, T = d->num_thresh, K = d->num_reg_classes - 1;
-  const int Rn = selected_rows(d, non_gt_index);
+  const int Rn = lnms_selected_rows(d, non_gt_index);
   RN_CHECK_ARG(C >= 1 && n >= 1 && T >= 1 && K >= 1, "rn_learn_nms_fwd: bad sizes C=%d n=%d T=%d K=%d", C, n, T, K);
   RN_CHECK_ARG(Rn >= n && Rn <= d->R, "rn_learn_nms_fwd: need first_n=%d <= non-gt rois=%d <= R=%d", n, Rn, d->R);
   RN_CHECK_ARG(Rn <= 8192, "rn_learn_nms_fwd: %d rois exceed the per-class sort capacity 8192", Rn);
@@ -307,7 +300,7 @@ extern "C" int rn_learn_nms_fwd(const rn_learn_nms_desc* d, const float* cls_sco
   RN_CHECK_ARG(d->merge_method >= -2 && d->merge_method < T, "rn_learn_nms_fwd: unknown merge method %d", d->merge_method);
   cudaStream_t st = (cudaStream_t)stream;
   LnmsWs W;
-  if (!carve(d, Rn, wsp, ws_bytes, &W)) { set_error("rn_learn_nms_fwd: workspace too small (%zu < %zu)", ws_bytes, rn_learn_nms_workspace_bytes(d)); return RN_ERR_WORKSPACE; }
+  if (!lnms_carve(d, Rn, wsp, ws_bytes, &W)) { set_error("rn_learn_nms_fwd: workspace too small (%zu < %zu)", ws_bytes, rn_learn_nms_workspace_bytes(d)); return RN_ERR_WORKSPACE; }
   const int* sel = d->nongt_dim > 0 ? nullptr : non_gt_index;
   int r;
   lnms_prep_kernel<<<cdiv(Rn, 4), 128, (size_t)4 * d->num_classes * sizeof(float), st>>>(*d, Rn, sel, cls_score, bbox_pred, rois, im_info, W.prob, W.refined);
@@ -332,7 +325,7 @@ extern "C" int rn_learn_nms_fwd(const rn_learn_nms_desc* d, const float* cls_sco
   lnms_gather_kernel<<<dim3(n, C), 128, 0, st>>>(n, C, K, d->class_agnostic, W.rank_idx, W.refined, W.emb, W.rank_feat,
                                                  sorted_bbox, W.feat_cls, W.boxes_cls);
   RN_LAUNCH_CHECK();
-  rn_relation_desc rd = inner_desc(d);
+  rn_relation_desc rd = lnms_inner_desc(d);
   if (d->precision == RN_PREC_F16 && d->class_agnostic && n <= 512 && relation_tc_shape_ok(&rd)) {
     // class-agnostic boxes: every class sorts the SAME refined rois, so the per-class pair geometry is a gather from
     // one [16, Rn, Rn] table (LNMS:332 builds [C, n, n, 4] position matrices -- 9x the pairs at C = 80, n = 100)

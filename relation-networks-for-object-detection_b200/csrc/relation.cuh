@@ -15,6 +15,14 @@ int relation_fp32(const rn_relation_desc* d, const float* X, const float* boxes,
                   const float* bq, const float* Wk, const float* bk, const float* Wg, const float* bg, const float* Wout,
                   const float* bout, float* out, float* softmax_out, void* ws, size_t ws_bytes, cudaStream_t st);
 
+// backward (relation_bwd.cu); every gradient buffer is overwritten
+size_t relation_bwd_ws_bytes(const rn_relation_desc* d);
+int relation_bwd(const rn_relation_desc* d, const float* X, const float* boxes, const int* key_index, const float* Wq,
+                 const float* bq, const float* Wk, const float* bk, const float* Wg, const float* bg, const float* Wout,
+                 const float* bout, const float* dOut, float* dX, float* dWq, float* dbq, float* dWk, float* dbk,
+                 float* dWg, float* dbg, float* dWout, float* dbout, void* ws, size_t ws_bytes, cudaStream_t st);
+int launch_colsum(cudaStream_t st, const float* A, int rows, int cols, float* out);   // out[c] = sum_r A[r][c]
+
 // fused tcgen05 path (relation_tc.cu)
 size_t relation_tc_workspace_bytes(const rn_relation_desc* d);
 int relation_tc(const rn_relation_desc* d, const float* X, const float* boxes, const int* key_index, const float* Wq,

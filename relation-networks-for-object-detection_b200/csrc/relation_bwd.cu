@@ -151,13 +151,19 @@ __global__ void scatter_add_rows_kernel(const float* __restrict__ dXk, const int
   }
 }
 
+int launch_colsum(cudaStream_t st, const float* A, int rows, int cols, float* out) {
+  colsum_kernel<<<cdiv(cols, 128), 128, 0, st>>>(A, rows, cols, out);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
+
 static int geom_grad_grid(const rn_relation_desc* d) {
   const long long items = (long long)d->batch * d->N * cdiv(d->M, 128);
   const int sms = sm_count() > 0 ? sm_count() : 148;
   return (int)std::max<long long>(1, std::min<long long>(items, (long long)sms * 2));
 }
 
-static size_t bwd_ws_bytes(const rn_relation_desc* d) {
+size_t relation_bwd_ws_bytes(const rn_relation_desc* d) {
   const size_t B = d->batch, N = d->N, M = d->M, H = d->H, ld = align_up(M, 4);
   size_t t = relation_fp32_ws_bytes(d);
   t += 2 * ws_slice(B * N * d->dout, 4);          // Y, dO
@@ -170,7 +176,7 @@ static size_t bwd_ws_bytes(const rn_relation_desc* d) {
   return t;
 }
 
-static int relation_bwd(const rn_relation_desc* d, const float* X, const float* boxes, const int* key_index,
+int relation_bwd(const rn_relation_desc* d, const float* X, const float* boxes, const int* key_index,
                         const float* Wq, const float* bq, const float* Wk, const float* bk, const float* Wg,
                         const float* bg, const float* Wout, const float* bout, const float* dOut, float* dX, float* dWq,
                         float* dbq, float* dWk, float* dbk, float* dWg, float* dbg, float* dWout, float* dbout,
@@ -179,7 +185,7 @@ static int relation_bwd(const rn_relation_desc* d, const float* X, const float* 
   const int dk = dq / H, dv = dout / H;
   Fp32State fs;
   if (!relation_fp32_carve(d, wsp, ws_bytes, &fs)) {
-    set_error("rn_relation_bwd: workspace too small (%zu < %zu)", ws_bytes, bwd_ws_bytes(d));
+    set_error("rn_relation_bwd: workspace too small (%zu < %zu)", ws_bytes, relation_bwd_ws_bytes(d));
     return RN_ERR_WORKSPACE;
   }
   const int ld = fs.ld;
@@ -194,7 +200,7 @@ static int relation_bwd(const rn_relation_desc* d, const float* X, const float* 
   float* dXk = ws.take<float>((size_t)B * M * D);
   float* partial = ws.take<float>((size_t)ggrid * H * (E + 1));
   if (!partial) {
-    set_error("rn_relation_bwd: workspace too small (%zu < %zu)", ws_bytes, bwd_ws_bytes(d));
+    set_error("rn_relation_bwd: workspace too small (%zu < %zu)", ws_bytes, relation_bwd_ws_bytes(d));
     return RN_ERR_WORKSPACE;
   }
   GeomFreq fr;
@@ -271,7 +277,7 @@ static int relation_bwd(const rn_relation_desc* d, const float* X, const float* 
 
 extern "C" size_t rn_relation_bwd_workspace_bytes(const rn_relation_desc* d) {
   if (!d || d->H < 1 || d->M < 1) return 0;
-  return rn::bwd_ws_bytes(d) + 256;
+  return rn::relation_bwd_ws_bytes(d) + 256;
 }
 
 extern "C" int rn_relation_bwd(const rn_relation_desc* d, const float* X, const float* boxes, const int32_t* key_index,

@@ -230,13 +230,8 @@ def linear(x, W, b=None, relu=False, precision=None):
 
 
 # ------------------------------------------------------------------------------------------------------------------
-def learn_nms(cls_score, bbox_pred, rois, im_info, feat, weights, first_n=100, num_thresh=5, class_thresh=0.01,
-              class_agnostic=True, means=None, stds=None, nongt_dim=None, non_gt_index=None, merge_method=-1,
-              precision=None):
-    """learn_nms CustomOp forward (LNMS:238-401) + merge.  ``weights``: dict by checkpoint name (LNMS:429-441)."""
-    precision = precision or default_precision()
-    cls_score = _f32(cls_score, 'cls_score'); bbox_pred = _f32(bbox_pred, 'bbox_pred'); rois = _f32(rois, 'rois')
-    im_info = _f32(im_info, 'im_info').reshape(-1); feat = _f32(feat, 'feat')
+def _learn_nms_desc(cls_score, bbox_pred, rois, feat, first_n, num_thresh, class_thresh, class_agnostic, means, stds,
+                    nongt_dim, non_gt_index, merge_method, precision):
     R, NC = cls_score.shape
     desc = L.LearnNmsDesc()
     desc.R, desc.num_classes, desc.num_reg_classes = R, NC, bbox_pred.shape[1] // 4
@@ -251,6 +246,19 @@ def learn_nms(cls_score, bbox_pred, rois, im_info, feat, weights, first_n=100, n
         kidx = non_gt_index.to(device=rois.device, dtype=torch.int32).contiguous()
         desc.num_non_gt = kidx.numel()
     desc.merge_method, desc.precision = merge_method, PREC[precision]
+    return desc, kidx
+
+
+def learn_nms(cls_score, bbox_pred, rois, im_info, feat, weights, first_n=100, num_thresh=5, class_thresh=0.01,
+              class_agnostic=True, means=None, stds=None, nongt_dim=None, non_gt_index=None, merge_method=-1,
+              precision=None):
+    """learn_nms CustomOp forward (LNMS:238-401) + merge.  ``weights``: dict by checkpoint name (LNMS:429-441)."""
+    precision = precision or default_precision()
+    cls_score = _f32(cls_score, 'cls_score'); bbox_pred = _f32(bbox_pred, 'bbox_pred'); rois = _f32(rois, 'rois')
+    im_info = _f32(im_info, 'im_info').reshape(-1); feat = _f32(feat, 'feat')
+    NC = cls_score.shape[1]
+    desc, kidx = _learn_nms_desc(cls_score, bbox_pred, rois, feat, first_n, num_thresh, class_thresh, class_agnostic, means,
+                                 stds, nongt_dim, non_gt_index, merge_method, precision)
     keep = [_f32(weights[n], n) for n in L.LearnNmsWeights.NAMES]
     w = L.LearnNmsWeights(*[t.data_ptr() for t in keep])
     C_ = NC - 1
@@ -265,6 +273,59 @@ def learn_nms(cls_score, bbox_pred, rois, im_info, feat, weights, first_n=100, n
                                  C.byref(w), _ptr(kidx), _ptr(multi), _ptr(sbbox), _ptr(sscore), _ptr(final), _ptr(ws),
                                  ws.numel(), _stream()), 'rn_learn_nms_fwd')
     return multi, sbbox, sscore, final
+
+
+def learn_nms_backward(grad_multi, cls_score, bbox_pred, rois, im_info, feat, weights, first_n=100, num_thresh=5,
+                       class_thresh=0.0, class_agnostic=True, means=None, stds=None, nongt_dim=None, non_gt_index=None):
+    """Gradients of nms_multi_score (train graph SYM_REL_NMS:424-501) -- rn_learn_nms_bwd.  Returns (dict of the 14 weight
+    gradients by checkpoint name, d_cls_score [R,num_classes], d_feat [R,feat_dim])."""
+    cls_score = _f32(cls_score, 'cls_score'); bbox_pred = _f32(bbox_pred, 'bbox_pred'); rois = _f32(rois, 'rois')
+    im_info = _f32(im_info, 'im_info').reshape(-1); feat = _f32(feat, 'feat'); grad_multi = _f32(grad_multi, 'grad_multi')
+    NC = cls_score.shape[1]
+    if tuple(grad_multi.shape) != (first_n, NC - 1, num_thresh):
+        raise L.RelnetError('learn_nms_backward: grad_multi shape %s != %s' % (tuple(grad_multi.shape), (first_n, NC - 1, num_thresh)))
+    desc, kidx = _learn_nms_desc(cls_score, bbox_pred, rois, feat, first_n, num_thresh, class_thresh, class_agnostic, means,
+                                 stds, nongt_dim, non_gt_index, -1, 'fp32')
+    keep = [_f32(weights[n], n) for n in L.LearnNmsWeights.NAMES]
+    w = L.LearnNmsWeights(*[t.data_ptr() for t in keep])
+    grads = {n: torch.empty_like(t) for n, t in zip(L.LearnNmsWeights.NAMES, keep)}
+    g = L.LearnNmsWeights(*[grads[n].data_ptr() for n in L.LearnNmsWeights.NAMES])
+    d_cls = torch.empty_like(cls_score); d_feat = torch.empty_like(feat)
+    lib = L.lib()
+    ws = _workspace(lib.rn_learn_nms_bwd_workspace_bytes(C.byref(desc)), rois.device)
+    L.check(lib.rn_learn_nms_bwd(C.byref(desc), _ptr(cls_score), _ptr(bbox_pred), _ptr(rois), _ptr(im_info), _ptr(feat),
+                                 C.byref(w), _ptr(kidx), _ptr(grad_multi), C.byref(g), _ptr(d_cls), _ptr(d_feat), _ptr(ws),
+                                 ws.numel(), _stream()), 'rn_learn_nms_bwd')
+    return grads, d_cls, d_feat
+
+
+def nms_loss(nms_multi_score, nms_multi_target, loss_scale=1.0, pos_grad_scale=4.0, eps=1e-8):
+    """learn-NMS loss terms and gradient (SYM_REL_NMS:539-551) -- rn_nms_loss.  Returns (pos_loss, neg_loss, d_multi)."""
+    m = _f32(nms_multi_score, 'nms_multi_score'); t = _f32(nms_multi_target, 'nms_multi_target')
+    if m.dim() != 3 or m.shape != t.shape:
+        raise L.RelnetError('nms_loss: score %s / target %s must both be [n,C,T]' % (tuple(m.shape), tuple(t.shape)))
+    pos = torch.empty_like(m); neg = torch.empty_like(m); d = torch.empty_like(m)
+    L.check(L.lib().rn_nms_loss(_ptr(m), _ptr(t), m.shape[0], m.shape[1], m.shape[2], loss_scale, pos_grad_scale, eps,
+                                _ptr(pos), _ptr(neg), _ptr(d), _stream()), 'rn_nms_loss')
+    return pos, neg, d
+
+
+def box_annotator_ohem(cls_score, bbox_pred, labels, bbox_targets, bbox_weights, num_classes, num_reg_classes, roi_per_img,
+                       return_loss=False):
+    """'BoxAnnotatorOHEM' CustomOp forward (box_annotator_ohem.py:26-53) -> labels_ohem [R], bbox_weights_ohem."""
+    cls_score = _f32(cls_score, 'cls_score'); bbox_pred = _f32(bbox_pred, 'bbox_pred'); labels = _f32(labels, 'labels')
+    bbox_targets = _f32(bbox_targets, 'bbox_targets'); bbox_weights = _f32(bbox_weights, 'bbox_weights')
+    R = cls_score.shape[0]
+    D = 4 * int(num_reg_classes)
+    if not (cls_score.shape[1] == int(num_classes) and labels.numel() == R and tuple(bbox_pred.shape) == (R, D)
+            and bbox_targets.shape == bbox_pred.shape and bbox_weights.shape == bbox_pred.shape):
+        raise L.RelnetError('box_annotator_ohem: inconsistent shapes')
+    lab = torch.empty_like(labels); w = torch.empty_like(bbox_weights)
+    loss = torch.empty(R, dtype=torch.float32, device=cls_score.device)
+    L.check(L.lib().rn_box_annotator_ohem(_ptr(cls_score), _ptr(bbox_pred), _ptr(labels), _ptr(bbox_targets),
+                                          _ptr(bbox_weights), R, int(num_classes), int(num_reg_classes), int(roi_per_img),
+                                          _ptr(lab), _ptr(w), _ptr(loss), _stream()), 'rn_box_annotator_ohem')
+    return (lab, w, loss) if return_loss else (lab, w)
 
 
 def nms_multi_target(bbox, gt_boxes, score, target_thresh):

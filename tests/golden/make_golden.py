@@ -152,6 +152,29 @@ def nms_multi_target_case(ns, name):
     print(name, 'positives', int(out[0].a.sum()))
 
 
+def ohem_case(ns, name):
+    """BoxAnnotatorOHEMOperator.forward (operator_py/box_annotator_ohem.py:26-53) under the numpy MXNet shim"""
+    shim = ns.mxshim
+    rng = np.random.default_rng(51)
+    R, NC, K = 307, 81, 2
+    cls_score = (rng.standard_normal((R, NC)) * 2).astype(np.float32)
+    labels = np.where(rng.random(R) < 0.25, rng.integers(1, NC, R), 0).astype(np.float32)
+    bbox_pred = (rng.standard_normal((R, 4 * K)) * 0.5).astype(np.float32)
+    bbox_targets = np.zeros((R, 4 * K), np.float32); bbox_weights = np.zeros((R, 4 * K), np.float32)
+    fg = labels > 0
+    bbox_targets[fg, 4:] = (rng.standard_normal((int(fg.sum()), 4)) * 1.5).astype(np.float32)
+    bbox_weights[fg, 4:] = 1
+    cls_score[5] = cls_score[6]; labels[5] = labels[6] = 0          # an exact loss tie among background rois
+    op = ns.box_annotator_ohem.BoxAnnotatorOHEMProp('81', '2', '128').create_operator(None, None, None)
+    out = [shim.ND(np.zeros(R, np.float32)), shim.ND(np.zeros((R, 4 * K), np.float32))]
+    op.forward(True, ['write', 'write'], [shim.ND(cls_score), shim.ND(bbox_pred), shim.ND(labels.copy()),
+                                          shim.ND(bbox_targets), shim.ND(bbox_weights)], out, [])
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), cls_score=cls_score, bbox_pred=bbox_pred, labels=labels,
+                        bbox_targets=bbox_targets, bbox_weights=bbox_weights, roi_per_img=128,
+                        labels_ohem=out[0].a, bbox_weights_ohem=out[1].a)
+    print(name, 'kept', int((out[0].a >= 0).sum()))
+
+
 def misc_case(ns, name):
     """Small pure-python reference helpers: refine_bbox_nd, rank embedding, multi position matrix, decode/encode."""
     shim = ns.mxshim
@@ -187,6 +210,7 @@ def main():
     proposal_target_case(ns, 'proposal_target_300_7', 31, 300, 7)
     misc_case(ns, 'misc_helpers')
     nms_multi_target_case(ns, 'nms_multi_target')
+    ohem_case(ns, 'box_annotator_ohem')
 
 
 if __name__ == '__main__':

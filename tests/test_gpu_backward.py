@@ -180,3 +180,70 @@ def test_deform_conv_backward_grouped(ops):
     got = ops.deform_conv_backward(T(dout), T(data), T(offset), T(weight), num_deformable_group=dg, num_group=G)
     for g, w, name in zip(got[:3], want, ('data', 'offset', 'weight')):
         assert rel_err(g.cpu().numpy(), w) <= 2e-5, name
+
+
+@pytest.mark.parametrize('seed,R,C,d,n,nongt', [(41, 60, 8, 256, 20, 50), (42, 300, 80, 1024, 100, 300)])
+def test_learn_nms_backward_matches_autograd(ops, seed, R, C, d, n, nongt):
+    """rn_learn_nms_bwd vs autograd through oracle/learn_nms_torch.py (forward pinned to the numpy oracle / reference)."""
+    from oracle import learn_nms_np as LN, learn_nms_torch as LT
+    c = LN.make_learn_nms_case(seed, R=R, C=C, d=d)
+    if d != 1024:
+        c['P']['roi_feat_embedding_weight'] = c['P']['roi_feat_embedding_weight'][:, :d].copy()
+    rng = np.random.RandomState(seed)
+    d_multi = rng.randn(n, C, 5).astype(np.float32)
+    means, stds = (0.0, 0.0, 0.0, 0.0), (0.1, 0.1, 0.2, 0.2)
+
+    def autograd(dtype):
+        P = {k: torch.tensor(v, dtype=dtype, requires_grad=True) for k, v in c['P'].items()}
+        cs = torch.tensor(c['cls_score'], dtype=dtype, requires_grad=True)
+        ft = torch.tensor(c['feat'], dtype=dtype, requires_grad=True)
+        multi, _, _ = LT.learn_nms_forward(cs, c['bbox_pred'], c['rois'], c['im_info'], ft, P, first_n=n, num_fg_classes=C,
+                                           class_thresh=0.0, means=means, stds=stds, nongt_dim=nongt)
+        multi.backward(torch.tensor(d_multi, dtype=dtype))
+        return {k: v.grad.numpy() for k, v in P.items()}, cs.grad.numpy(), ft.grad.numpy(), multi.detach().numpy()
+    gP, gcs, gft, multi_ref = autograd(torch.float32)
+    gP64 = autograd(torch.float64)[0]
+    W = {k: T(v) for k, v in c['P'].items()}
+    args = (T(c['cls_score']), T(c['bbox_pred']), T(c['rois']), T(c['im_info']), T(c['feat']), W)
+    kw = dict(first_n=n, class_thresh=0.0, means=means, stds=stds, nongt_dim=nongt)
+    multi = ops.learn_nms(*args, precision='fp32', **kw)[0]
+    assert rel_err(multi.cpu().numpy(), multi_ref) <= 1e-4
+    grads, d_cls, d_feat = ops.learn_nms_backward(T(d_multi), *args, **kw)
+    torch.cuda.synchronize()
+    worst = 0.0
+    for k in gP:
+        want = gP[k]
+        got = grads[k].cpu().numpy().reshape(want.shape)
+        if k == 'nms_key_1_bias':          # exactly zero in exact arithmetic (softmax shift invariance): rounding noise
+            assert np.abs(got).max() <= 1e-4 * np.abs(gP['nms_query_1_bias']).max()
+            continue
+        e = rel_err(got, want)
+        e64, ref64 = rel_err(got, gP64[k]), rel_err(want, gP64[k])
+        print('d%-28s vs float32 autograd %.2e | vs float64 %.2e (float32 autograd itself: %.2e)' % (k, e, e64, ref64))
+        worst = max(worst, e)
+        # the geometry-FC gradient carries 1/g weights up to 1e6 next to the 1e-6 clamp: float32 evaluations of it differ
+        # among themselves, so it is held to the float32 oracle's OWN distance from exact arithmetic instead
+        assert e <= 2e-3 or e64 <= 3.0 * ref64 + 1e-4, (k, e, e64, ref64)
+    e_cs, e_ft = rel_err(d_cls.cpu().numpy(), gcs), rel_err(d_feat.cpu().numpy(), gft)
+    print('d_cls_score %.2e  d_feat %.2e' % (e_cs, e_ft))
+    assert e_cs <= 2e-3 and e_ft <= 2e-3
+    assert np.abs(d_cls.cpu().numpy()[nongt:]).max(initial=0.0) == 0.0      # gt rows are outside the non-gt slice
+
+
+def test_nms_loss_and_ohem_match_oracle(ops):
+    from conftest import golden
+    from oracle import train_np as TN
+    rng = np.random.default_rng(5)
+    m = rng.uniform(0.0, 1.0, (100, 80, 5)).astype(np.float32); t = (rng.random((100, 80, 5)) < 0.05).astype(np.float32)
+    m[0, 0, 0] = 0.0; m[0, 0, 1] = 1.0                          # the eps guards
+    pos, neg, d = ops.nms_loss(T(m), T(t), loss_scale=1.0, pos_grad_scale=4.0)
+    wp, wn, wd = TN.nms_loss(m, t, 100, 5)
+    assert rel_err(pos.cpu().numpy(), wp) <= 1e-5 and rel_err(neg.cpu().numpy(), wn) <= 1e-5
+    assert rel_err(d.cpu().numpy(), wd) <= 1e-5
+    g = golden('box_annotator_ohem')
+    lab, w, loss = ops.box_annotator_ohem(T(g['cls_score']), T(g['bbox_pred']), T(g['labels']), T(g['bbox_targets']),
+                                          T(g['bbox_weights']), 81, 2, int(g['roi_per_img']), return_loss=True)
+    assert np.array_equal(lab.cpu().numpy(), g['labels_ohem'])               # bit-exact vs the reference execution
+    assert np.array_equal(w.cpu().numpy(), g['bbox_weights_ohem'])
+    assert rel_err(loss.cpu().numpy(), TN.box_annotator_ohem(g['cls_score'], g['bbox_pred'], g['labels'], g['bbox_targets'],
+                                                             g['bbox_weights'], 128)[2]) <= 1e-6

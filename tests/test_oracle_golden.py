@@ -209,3 +209,41 @@ def test_oracle_roi_pool_backward_routes_to_argmax():
                 if a >= 0:
                     want[int(rois[n, 0]), c].reshape(-1)[a] += dout[n, c].reshape(-1)[p]
     assert rel_err(dd, want) <= 1e-6
+
+
+def test_torch_learn_nms_forward_equals_numpy_oracle():
+    import torch
+    from oracle import learn_nms_np as LN, learn_nms_torch as LT
+    c = LN.make_learn_nms_case(7, R=60, C=8, d=256)
+    c['P']['roi_feat_embedding_weight'] = c['P']['roi_feat_embedding_weight'][:, :256].copy()
+    want = LN.learn_nms_forward(c['cls_score'], c['bbox_pred'], c['rois'], c['im_info'], c['feat'], c['P'], first_n=20,
+                                num_fg_classes=8, class_thresh=0.0, nongt_dim=50, dtype=np.float64)
+    P = {k: torch.tensor(v, dtype=torch.float64) for k, v in c['P'].items()}
+    multi, ss, order = LT.learn_nms_forward(torch.tensor(c['cls_score'], dtype=torch.float64), c['bbox_pred'], c['rois'],
+                                            c['im_info'], torch.tensor(c['feat'], dtype=torch.float64), P, first_n=20,
+                                            num_fg_classes=8, class_thresh=0.0, nongt_dim=50)
+    assert np.abs(multi.numpy() - want[0]).max() <= 1e-10
+    assert np.abs(ss.numpy() - want[2]).max() <= 1e-12
+
+
+def test_ohem_oracle_matches_reference_execution():
+    """oracle/train_np.box_annotator_ohem == the reference's BoxAnnotatorOHEMOperator.forward run under the numpy shim"""
+    from oracle import train_np as TN
+    g = golden('box_annotator_ohem')
+    lab, w, _ = TN.box_annotator_ohem(g['cls_score'], g['bbox_pred'], g['labels'], g['bbox_targets'], g['bbox_weights'],
+                                      int(g['roi_per_img']))
+    assert np.array_equal(lab, g['labels_ohem']) and np.array_equal(w, g['bbox_weights_ohem'])
+    assert int((lab >= 0).sum()) == int(g['roi_per_img'])
+
+
+def test_nms_loss_oracle_gradient_is_autograd():
+    import torch
+    from oracle import train_np as TN, learn_nms_torch as LT
+    rng = np.random.default_rng(3)
+    m = rng.uniform(0.0, 1.0, (30, 8, 5)).astype(np.float32); t = (rng.random((30, 8, 5)) < 0.1).astype(np.float32)
+    pos, neg, d = TN.nms_loss(m, t, 30, 5, loss_scale=1.0, pos_grad_scale=4.0)
+    tm = torch.tensor(m, dtype=torch.float64, requires_grad=True)
+    p, n = LT.nms_loss(tm, torch.tensor(t, dtype=torch.float64), 30, 5)
+    (4.0 * p.sum() + n.sum()).backward()
+    assert rel_err(pos, p.detach().numpy()) <= 1e-5 and rel_err(neg, n.detach().numpy()) <= 1e-5
+    assert rel_err(d, tm.grad.numpy()) <= 1e-5
