@@ -134,8 +134,21 @@ def relation(X, boxes, Wq, bq, Wk, bk, Wg, bg, Wout, bout, key_index=None, M=Non
     return (out, sm) if return_softmax else out
 
 
+def _grad_buffers(out, like):
+    """gradient outputs: fresh tensors, or the caller's (e.g. windows of a replicas.GradientBucket) when `out` has them"""
+    res = {}
+    for n, t in like.items():
+        o = out.get(n) if out else None
+        if o is None:
+            o = torch.empty_like(t)
+        elif not (o.is_cuda and o.dtype == torch.float32 and o.is_contiguous() and o.numel() == t.numel()):
+            raise L.RelnetError('gradient buffer %s must be a contiguous float32 CUDA tensor of %d elements' % (n, t.numel()))
+        res[n] = o
+    return res
+
+
 def relation_backward(grad_out, X, boxes, Wq, bq, Wk, bk, Wg, bg, Wout, bout, key_index=None, M=None, group=16,
-                      residual_relu=False, wave_length=1000.0):
+                      residual_relu=False, wave_length=1000.0, out=None):
     """Gradients of `relation` (fp32; forward intermediates are recomputed) -- rn_relation_bwd.
     Returns a dict with the gradient of X and of every parameter, shaped like the argument it belongs to."""
     X = _f32(X, 'X'); boxes = _f32(boxes, 'boxes'); grad_out = _f32(grad_out, 'grad_out')
@@ -159,9 +172,7 @@ def relation_backward(grad_out, X, boxes, Wq, bq, Wk, bk, Wg, bg, Wout, bout, ke
         M = kidx.numel()
     M = int(M) if M is not None else N
     desc = L.RelationDesc(B, N, M, d, dq, dout, group, Wg.shape[1], wave_length, int(residual_relu), PREC['fp32'])
-    g = {'X': torch.empty_like(X), 'Wq': torch.empty_like(Wq), 'bq': torch.empty_like(bq), 'Wk': torch.empty_like(Wk),
-         'bk': torch.empty_like(bk), 'Wg': torch.empty_like(Wg), 'bg': torch.empty_like(bg), 'Wout': torch.empty_like(Wout),
-         'bout': torch.empty_like(bout)}
+    g = _grad_buffers(out, {'X': X, 'Wq': Wq, 'bq': bq, 'Wk': Wk, 'bk': bk, 'Wg': Wg, 'bg': bg, 'Wout': Wout, 'bout': bout})
     lib = L.lib()
     ws = _workspace(lib.rn_relation_bwd_workspace_bytes(C.byref(desc)), X.device)
     L.check(lib.rn_relation_bwd(C.byref(desc), _ptr(X), _ptr(boxes), _ptr(kidx), _ptr(Wq), _ptr(bq), _ptr(Wk), _ptr(bk),
@@ -276,7 +287,8 @@ def learn_nms(cls_score, bbox_pred, rois, im_info, feat, weights, first_n=100, n
 
 
 def learn_nms_backward(grad_multi, cls_score, bbox_pred, rois, im_info, feat, weights, first_n=100, num_thresh=5,
-                       class_thresh=0.0, class_agnostic=True, means=None, stds=None, nongt_dim=None, non_gt_index=None):
+                       class_thresh=0.0, class_agnostic=True, means=None, stds=None, nongt_dim=None, non_gt_index=None,
+                       out=None):
     """Gradients of nms_multi_score (train graph SYM_REL_NMS:424-501) -- rn_learn_nms_bwd.  Returns (dict of the 14 weight
     gradients by checkpoint name, d_cls_score [R,num_classes], d_feat [R,feat_dim])."""
     cls_score = _f32(cls_score, 'cls_score'); bbox_pred = _f32(bbox_pred, 'bbox_pred'); rois = _f32(rois, 'rois')
@@ -288,7 +300,7 @@ def learn_nms_backward(grad_multi, cls_score, bbox_pred, rois, im_info, feat, we
                                  stds, nongt_dim, non_gt_index, -1, 'fp32')
     keep = [_f32(weights[n], n) for n in L.LearnNmsWeights.NAMES]
     w = L.LearnNmsWeights(*[t.data_ptr() for t in keep])
-    grads = {n: torch.empty_like(t) for n, t in zip(L.LearnNmsWeights.NAMES, keep)}
+    grads = _grad_buffers(out, dict(zip(L.LearnNmsWeights.NAMES, keep)))
     g = L.LearnNmsWeights(*[grads[n].data_ptr() for n in L.LearnNmsWeights.NAMES])
     d_cls = torch.empty_like(cls_score); d_feat = torch.empty_like(feat)
     lib = L.lib()

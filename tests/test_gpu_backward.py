@@ -247,3 +247,22 @@ def test_nms_loss_and_ohem_match_oracle(ops):
     assert np.array_equal(w.cpu().numpy(), g['bbox_weights_ohem'])
     assert rel_err(loss.cpu().numpy(), TN.box_annotator_ohem(g['cls_score'], g['bbox_pred'], g['labels'], g['bbox_targets'],
                                                              g['bbox_weights'], 128)[2]) <= 1e-6
+
+
+def test_backward_writes_into_gradient_bucket(ops):
+    """the backward kernels fill windows of one flat bucket in place (what the NCCL allreduce then sums)"""
+    from relnet_b200 import replicas
+    H, N, d = 4, 40, 128
+    c = R.make_relation_case(51, N, d, H)
+    dev = {k: T(c[k]) for k in NAMES + ('boxes',)}
+    names = ('Wq', 'bq', 'Wk', 'bk', 'Wg', 'bg', 'Wout', 'bout')
+    bucket = replicas.GradientBucket({k: tuple(c[k].shape) for k in names}, device='cuda')
+    dOut = torch.randn(N, d, device='cuda')
+    args = [dev[k] for k in names]
+    ref = ops.relation_backward(dOut, dev['X'], dev['boxes'], *args, group=H, residual_relu=True)
+    got = ops.relation_backward(dOut, dev['X'], dev['boxes'], *args, group=H, residual_relu=True, out=bucket.views)
+    torch.cuda.synchronize()
+    for k in names:
+        assert got[k].data_ptr() == bucket.views[k].data_ptr()
+        assert torch.equal(bucket.views[k], ref[k])
+    assert bucket.allreduce() is None                     # single process: no group, nothing to do

@@ -96,13 +96,11 @@ def test_c_symbol_replacements(compat):
     np.testing.assert_allclose(ov, P.bbox_overlaps(boxes[:50], boxes[50:60]), rtol=1e-14)
 
 
-def test_box_annotator_ohem_custom_op(ops):
+def test_box_annotator_ohem_custom_op(compat):
     """mx.sym.Custom(op_type='BoxAnnotatorOHEM', ...) call form (SYM_REL:299-305) against the reference-executed golden"""
-    from conftest import golden
-    import relnet_b200
     g = golden('box_annotator_ohem')
     dev = lambda k: torch.from_numpy(g[k]).cuda()
-    lab, w = relnet_b200.compat.Custom(op_type='BoxAnnotatorOHEM', num_classes=81, num_reg_classes=2, roi_per_img=128,
+    lab, w = compat.Custom(op_type='BoxAnnotatorOHEM', num_classes=81, num_reg_classes=2, roi_per_img=128,
                                        cls_score=dev('cls_score'), bbox_pred=dev('bbox_pred'), labels=dev('labels'),
                                        bbox_targets=dev('bbox_targets'), bbox_weights=dev('bbox_weights'))
     assert np.array_equal(lab.cpu().numpy(), g['labels_ohem']) and np.array_equal(w.cpu().numpy(), g['bbox_weights_ohem'])
