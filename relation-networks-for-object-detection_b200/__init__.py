@@ -7,5 +7,6 @@ library is missing or the tensors are not on a CUDA device.
 """
 from . import _lib          # noqa: F401
 from . import ops           # noqa: F401
+from ._lib import RelnetError   # noqa: F401
 
 __version__ = '0.1.0'

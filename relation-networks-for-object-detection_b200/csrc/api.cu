@@ -96,6 +96,39 @@ int sgemm_rm(cudaStream_t st, bool transA, bool transB, int M, int N, int K, flo
   return RN_OK;
 }
 
+// ---- two-level batch: problem (o, i), o < outer, i < inner, operands at base + o*s_outer + i*s_inner.  One
+// cublasSgemmBatched over outer*inner pointer triples built on the device (ptr_ws: 3*outer*inner pointers) -- the
+// per-class x per-head GEMMs of the learn-NMS head (80 x 16 problems) become one launch instead of 80.
+__global__ void fill_gemm_ptrs_kernel(const float* A, long long sAo, long long sAi, const float* B, long long sBo,
+                                      long long sBi, float* C, long long sCo, long long sCi, int outer, int inner,
+                                      const float** pa, const float** pb, float** pc) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= outer * inner) return;
+  const int o = t / inner, i = t % inner;
+  pa[t] = A + o * sAo + i * sAi;
+  pb[t] = B + o * sBo + i * sBi;
+  pc[t] = C + o * sCo + i * sCi;
+}
+
+int sgemm_rm_2level(cudaStream_t st, bool transA, bool transB, int M, int N, int K, float alpha, const float* A, int lda,
+                    long long sAo, long long sAi, const float* B, int ldb, long long sBo, long long sBi, float beta, float* C,
+                    int ldc, long long sCo, long long sCi, int outer, int inner, void* ptr_ws) {
+  if (outer == 1) return sgemm_rm(st, transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, inner, sAi, sBi, sCi);
+  cublasHandle_t h;
+  int r = get_cublas(st, &h);
+  if (r) return r;
+  const int cnt = outer * inner;
+  const float** pa = (const float**)ptr_ws;
+  const float** pb = pa + cnt;
+  float** pc = (float**)(pb + cnt);
+  fill_gemm_ptrs_kernel<<<(cnt + 127) / 128, 128, 0, st>>>(A, sAo, sAi, B, sBo, sBi, C, sCo, sCi, outer, inner, pa, pb, pc);
+  RN_LAUNCH_CHECK();
+  const cublasOperation_t opb = transB ? CUBLAS_OP_T : CUBLAS_OP_N, opa = transA ? CUBLAS_OP_T : CUBLAS_OP_N;
+  cublasStatus_t s = cublasSgemmBatched(h, opb, opa, N, M, K, &alpha, pb, ldb, pa, lda, &beta, pc, ldc, cnt);
+  if (s != CUBLAS_STATUS_SUCCESS) { set_error("cublasSgemmBatched(%dx%dx%d x%d) failed: %d", M, N, K, cnt, (int)s); return RN_ERR_CUDA; }
+  return RN_OK;
+}
+
 }  // namespace rn
 
 extern "C" {

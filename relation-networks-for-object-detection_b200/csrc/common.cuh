@@ -65,4 +65,9 @@ int sgemm_rm(cudaStream_t st, bool transA, bool transB, int M, int N, int K, flo
              const float* B, int ldb, float beta, float* C, int ldc, int batch = 1, long long sA = 0, long long sB = 0,
              long long sC = 0);
 
+// two-level batched variant: problem (o, i) at base + o*s_outer + i*s_inner; ptr_ws holds 3*outer*inner device pointers
+int sgemm_rm_2level(cudaStream_t st, bool transA, bool transB, int M, int N, int K, float alpha, const float* A, int lda,
+                    long long sAo, long long sAi, const float* B, int ldb, long long sBo, long long sBi, float beta, float* C,
+                    int ldc, long long sCo, long long sCi, int outer, int inner, void* ptr_ws);
+
 }  // namespace rn

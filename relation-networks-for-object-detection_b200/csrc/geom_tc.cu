@@ -1,6 +1,6 @@
 // geom_tc.cu -- geometry weight with the 64 -> H pair FC on tcgen05 (sm_100a), E = 64.
 //
-// A CTA of 512 threads owns 128 (query, key) pairs, 4 threads per pair (one per box coordinate): each evaluates its eps,
+// A CTA of 512 threads owns 128 consecutive (query, key) pairs (flattened n*M + m), 4 threads per pair (one per box coordinate): each evaluates its eps,
 // the 8 sin/cos pairs of that coordinate, splits every value into fp16 hi + lo and writes its two 16-byte chunks of the
 // pair's 64-wide row of the A operand (128 pairs x 64, SWIZZLE_128B K-major) straight into shared memory.  One elected thread then issues 12 UMMAs (M=128, N=16, K=16: A_hi.W_hi + A_lo.W_hi + A_hi.W_lo over 4 K-steps)
 // into a 16-column TMEM accumulator, every thread reads 4 of its pair's 16 head values back with one tcgen05.ld, applies
@@ -36,7 +36,7 @@ __device__ __forceinline__ void split2(float v0, float v1, uint32_t* hi, uint32_
 }
 
 template <bool EXACT>
-__global__ void __launch_bounds__(512) geom_weight_tc_kernel(const float* __restrict__ boxes, const int* __restrict__ key_index,
+__global__ void __launch_bounds__(512, 2) geom_weight_tc_kernel(const float* __restrict__ boxes, const int* __restrict__ key_index,
                                                              int B, int N, int M, int H, GeomFreq fr,
                                                              const float* __restrict__ Wg, const float* __restrict__ bg,
                                                              float* __restrict__ out, int ldg, int log2_out,
@@ -77,14 +77,21 @@ __global__ void __launch_bounds__(512) geom_weight_tc_kernel(const float* __rest
 #pragma unroll
   for (int k = 0; k < 8; ++k) rdim[k] = EXACT ? fr.dim[k] : __frcp_rn(fr.dim[k]);
 
-  const int tiles_m = (M + 127) >> 7;
-  const long long total = (long long)B * N * tiles_m;
+  // work item = 128 consecutive pairs of the flattened (n, m) index space of one problem: no partially filled key tiles
+  // (M = 300 would waste a third of the third tile), rows still land contiguously in the output
+  // (32-bit index arithmetic: the launcher guarantees N*M < 2^31 and B*tiles < 2^31 -- 64-bit div/mod was a sixth of
+  //  the instructions of this kernel, profiles/r01_ncu_geom_tc_n300.txt)
+  const uint32_t pairs = (uint32_t)N * (uint32_t)M;
+  const uint32_t tiles = (pairs + 127u) >> 7;
+  const uint32_t total = (uint32_t)B * tiles;
   uint32_t phase = 0;
-  for (long long item = blockIdx.x; item < total; item += gridDim.x) {
-    const int tm = (int)(item % tiles_m);
-    const int n = (int)((item / tiles_m) % N), b = (int)(item / ((long long)tiles_m * N));
-    const int m = tm * 128 + pr;
-    const int mc = min(m, M - 1);
+  for (uint32_t item = blockIdx.x; item < total; item += gridDim.x) {
+    const int b = (int)(item / tiles);
+    const uint32_t p = (item - (uint32_t)b * tiles) * 128u + (uint32_t)pr;
+    const bool live = p < pairs;
+    const uint32_t pc = live ? p : pairs - 1u;
+    const int n = (int)(pc / (uint32_t)M), mc = (int)(pc - (uint32_t)n * (uint32_t)M);
+    const int m = live ? mc : M;                       // m == M marks a dead lane (no store)
     const float4 bfix = reinterpret_cast<const float4*>(boxes)[(size_t)b * N + n];
     const float4 bvar = reinterpret_cast<const float4*>(boxes)[(size_t)b * N + (key_index ? key_index[mc] : mc)];
     const float4 bq = swap_roles ? bvar : bfix, bk = swap_roles ? bfix : bvar;     // query box / key box
@@ -168,15 +175,20 @@ __global__ void __launch_bounds__(512) geom_weight_tc_kernel(const float* __rest
 int launch_geom_weight_tc(cudaStream_t st, const float* boxes, const int* key_index, int B, int N, int M, int H,
                           const GeomFreq& fr, const float* Wg, const float* bg, float* g, int ldg, int log2_out,
                           int swap_roles, bool exact) {
-  const long long items = (long long)B * N * cdiv(M, 128);
+  const long long items = (long long)B * (((long long)N * M + 127) / 128);
   const int sms = sm_count() > 0 ? sm_count() : 148;
-  const int grid = (int)std::min<long long>(items, (long long)sms * 4);
+  // persistent: exactly as many CTAs as are co-resident (register-limited: 2 per SM), so the per-CTA prologue (Wg split,
+  // TMEM allocation, barrier init) is paid once and no CTA waits for a second wave
+  // __launch_bounds__(512, 2) keeps the kernel at <= 64 registers, so two CTAs are co-resident per SM: one computes while
+  // the other waits for its UMMA / drains TMEM
   static thread_local bool configured = false;
   if (!configured) {
     RN_CUDA(cudaFuncSetAttribute(geom_weight_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGeomSmem));
     RN_CUDA(cudaFuncSetAttribute(geom_weight_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGeomSmem));
     configured = true;
   }
+  RN_CHECK_ARG((long long)N * M < (1ll << 31) && items < (1ll << 31), "geometry: N*M = %lld exceeds the 32-bit pair index", (long long)N * M);
+  const int grid = (int)std::min<long long>(items, (long long)sms * 2);
   if (exact)
     geom_weight_tc_kernel<true><<<grid, 512, kGeomSmem, st>>>(boxes, key_index, B, N, M, H, fr, Wg, bg, g, ldg, log2_out, swap_roles);
   else

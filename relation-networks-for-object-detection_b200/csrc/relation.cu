@@ -105,6 +105,7 @@ size_t relation_fp32_ws_bytes(const rn_relation_desc* d) {
   t += ws_slice(B * d->H * N * ld, 4);  // S / P
   t += ws_slice(B * N * d->dout, 4);    // O
   t += ws_slice(B * M * d->d, 4);       // gathered keys
+  t += ws_slice(3 * B * d->H, 8);       // pointer triples of the (problem, head) batched GEMMs
   return t;
 }
 
@@ -121,8 +122,9 @@ bool relation_fp32_carve(const rn_relation_desc* d, void* wsp, size_t ws_bytes, 
   fs->S = ws.take<float>(B * H * N * ld);
   fs->O = ws.take<float>(B * N * d->dout);
   fs->Xk = ws.take<float>(B * M * d->d);
+  fs->ptrs = ws.take<void*>(3 * B * H);
   fs->used = ws.off;
-  return fs->Xk != nullptr;
+  return fs->ptrs != nullptr;
 }
 
 int relation_fp32(const rn_relation_desc* d, const float* X, const float* boxes, const int* key_index,
@@ -158,23 +160,15 @@ int relation_fp32(const rn_relation_desc* d, const float* X, const float* boxes,
   // geometry weights g [B,H,N,ld]
   if ((r = launch_geom_weight(st, boxes, key_index, B, N, M, H, d->E, d->wave_length, Wg, bg, g, ld))) return r;
   // scores, softmax, aggregate (per problem; heads batched)
-  for (int b = 0; b < B; ++b) {
-    const float* Qb = Q + (size_t)b * N * dq;
-    const float* Kb = K + (size_t)b * M * dq;
-    float* Sb = S + (size_t)b * H * N * ld;
-    if ((r = sgemm_nt(st, N, M, dk, Qb, dq, Kb, dq, Sb, ld, H, dk, dk, (long long)N * ld))) return r;
-  }
+  if ((r = sgemm_rm_2level(st, false, true, N, M, dk, 1.f, Q, dq, (long long)N * dq, dk, K, dq, (long long)M * dq, dk, 0.f, S,
+                           ld, (long long)H * N * ld, (long long)N * ld, B, H, fs.ptrs))) return r;
   {
     const int rows = B * H * N;
     geo_softmax_rows_kernel<<<cdiv(rows, 8), 256, 0, st>>>(S, g, B, H, N, M, ld, 1.0f / sqrtf((float)dk), softmax_out);
     RN_LAUNCH_CHECK();
   }
-  for (int b = 0; b < B; ++b) {
-    const float* Sb = S + (size_t)b * H * N * ld;
-    const float* Vb = Vp + (size_t)b * M * dout;
-    float* Ob = O + (size_t)b * N * dout;
-    if ((r = sgemm_nn(st, N, dv, M, Sb, ld, Vb, dout, Ob, dout, H, (long long)N * ld, dv, dv))) return r;
-  }
+  if ((r = sgemm_rm_2level(st, false, false, N, dv, M, 1.f, S, ld, (long long)H * N * ld, (long long)N * ld, Vp, dout,
+                           (long long)M * dout, dv, 0.f, O, dout, (long long)N * dout, dv, B, H, fs.ptrs))) return r;
   {
     size_t total = (size_t)B * N * dout;
     int blocks = (int)((total + 255) / 256);

@@ -7,7 +7,7 @@ namespace rn {
 int launch_bias_act(cudaStream_t st, float* y, const float* bias, size_t rows, int cols, int relu);
 
 // fp32 path (relation.cu) -- also the recomputation step of rn_relation_bwd (relation_bwd.cu)
-struct Fp32State { float *Q, *K, *Vp, *g, *S, *O, *Xk; int ld; size_t used; };
+struct Fp32State { float *Q, *K, *Vp, *g, *S, *O, *Xk; void** ptrs; int ld; size_t used; };
 int relation_check_desc(const rn_relation_desc* d);
 size_t relation_fp32_ws_bytes(const rn_relation_desc* d);
 bool relation_fp32_carve(const rn_relation_desc* d, void* ws, size_t ws_bytes, Fp32State* fs);

@@ -220,15 +220,11 @@ int relation_bwd(const rn_relation_desc* d, const float* X, const float* boxes, 
     RN_LAUNCH_CHECK();
   }
   // 3. dV'_h = P_h^T dO_h,  dP_h = dO_h V'_h^T   (heads batched)
-  for (int b = 0; b < B; ++b) {
-    const float* Pb = P + (size_t)b * H * N * ld;
-    const float* dOb = dO + (size_t)b * N * dout;
-    const float* Vb = fs.Vp + (size_t)b * M * dout;
-    if ((r = sgemm_rm(st, true, false, M, dv, N, 1.f, Pb, ld, dOb, dout, 0.f, dVp + (size_t)b * M * dout, dout, H,
-                      (long long)N * ld, dv, dv))) return r;
-    if ((r = sgemm_rm(st, false, true, N, M, dv, 1.f, dOb, dout, Vb, dout, 0.f, dP + (size_t)b * H * N * ld, ld, H, dv, dv,
-                      (long long)N * ld))) return r;
-  }
+  const long long sS = (long long)H * N * ld, sSh = (long long)N * ld;      // [B,H,N,ld] tensors: problem / head strides
+  if ((r = sgemm_rm_2level(st, true, false, M, dv, N, 1.f, P, ld, sS, sSh, dO, dout, (long long)N * dout, dv, 0.f, dVp, dout,
+                           (long long)M * dout, dv, B, H, fs.ptrs))) return r;
+  if ((r = sgemm_rm_2level(st, false, true, N, M, dv, 1.f, dO, dout, (long long)N * dout, dv, fs.Vp, dout, (long long)M * dout,
+                           dv, 0.f, dP, ld, sS, sSh, B, H, fs.ptrs))) return r;
   // 4. softmax backward; dP <- dS/sqrt(dk), g <- dx
   {
     const int rows = B * H * N;
@@ -236,13 +232,10 @@ int relation_bwd(const rn_relation_desc* d, const float* X, const float* boxes, 
     RN_LAUNCH_CHECK();
   }
   // 5. dQ_h = dS_h K_h, dK_h = dS_h^T Q_h
-  for (int b = 0; b < B; ++b) {
-    const float* dSb = dP + (size_t)b * H * N * ld;
-    if ((r = sgemm_rm(st, false, false, N, dk, M, 1.f, dSb, ld, fs.K + (size_t)b * M * dq, dq, 0.f,
-                      dQ + (size_t)b * N * dq, dq, H, (long long)N * ld, dk, dk))) return r;
-    if ((r = sgemm_rm(st, true, false, M, dk, N, 1.f, dSb, ld, fs.Q + (size_t)b * N * dq, dq, 0.f,
-                      dK + (size_t)b * M * dq, dq, H, (long long)N * ld, dk, dk))) return r;
-  }
+  if ((r = sgemm_rm_2level(st, false, false, N, dk, M, 1.f, dP, ld, sS, sSh, fs.K, dq, (long long)M * dq, dk, 0.f, dQ, dq,
+                           (long long)N * dq, dk, B, H, fs.ptrs))) return r;
+  if ((r = sgemm_rm_2level(st, true, false, M, dk, N, 1.f, dP, ld, sS, sSh, fs.Q, dq, (long long)N * dq, dk, 0.f, dK, dq,
+                           (long long)M * dq, dk, B, H, fs.ptrs))) return r;
   // 6. geometry FC gradients
   {
     const size_t smem = ((size_t)128 * (E + 1) + (size_t)H * 128) * sizeof(float);
@@ -258,11 +251,18 @@ int relation_bwd(const rn_relation_desc* d, const float* X, const float* boxes, 
   RN_LAUNCH_CHECK();
   colsum_kernel<<<cdiv(dq, 128), 128, 0, st>>>(dK, B * M, dq, dbk);
   RN_LAUNCH_CHECK();
-  for (int b = 0; b < B; ++b) {
-    const float* keys = key_index ? fs.Xk + (size_t)b * M * D : X + (size_t)b * N * D;
-    const float beta = b ? 1.f : 0.f;
-    if ((r = sgemm_rm(st, true, false, dq, D, M, 1.f, dK + (size_t)b * M * dq, dq, keys, D, beta, dWk, D))) return r;
-    if ((r = sgemm_rm(st, true, false, dout, D, M, 1.f, dVp + (size_t)b * M * dout, dout, keys, D, beta, dWout, D))) return r;
+  if (key_index || M == N || B == 1) {
+    // key rows are one contiguous [B*M, D] matrix (gathered copy, or X itself): a single GEMM each
+    const float* keys = key_index ? fs.Xk : X;
+    if ((r = sgemm_rm(st, true, false, dq, D, B * M, 1.f, dK, dq, keys, D, 0.f, dWk, D))) return r;
+    if ((r = sgemm_rm(st, true, false, dout, D, B * M, 1.f, dVp, dout, keys, D, 0.f, dWout, D))) return r;
+  } else {
+    for (int b = 0; b < B; ++b) {
+      const float* keys = X + (size_t)b * N * D;
+      const float beta = b ? 1.f : 0.f;
+      if ((r = sgemm_rm(st, true, false, dq, D, M, 1.f, dK + (size_t)b * M * dq, dq, keys, D, beta, dWk, D))) return r;
+      if ((r = sgemm_rm(st, true, false, dout, D, M, 1.f, dVp + (size_t)b * M * dout, dout, keys, D, beta, dWout, D))) return r;
+    }
   }
   // 8. input gradient
   if ((r = sgemm_rm(st, false, false, B * N, D, dq, 1.f, dQ, dq, Wq, D, 1.f, dX, D))) return r;

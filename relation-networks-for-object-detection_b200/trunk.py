@@ -6,9 +6,28 @@ relation_rcnn/symbols/resnet_v1_101_rcnn_base.py: conv1 7x7/2, ceil-mode 3x3/2 m
 stride on the first 1x1), res5 with dilation 2 / stride 1 (:621-683), RPN 3x3+relu -> 1x1 cls (2A) / 1x1 bbox (4A)
 (:685-693), softmax over {bg, fg} per anchor, conv_new_1 1x1 2048->256 + relu (SYM_REL:249-250).
 """
+import os
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+
+# cuDNN's fused conv + bias (+ residual) + relu (cudnnConvolutionBiasActivationForward via ATen): one library launch per
+# conv instead of conv / bias / relu / add -- 3 launches per bottleneck instead of ~11, and the elementwise passes over the
+# activations disappear.  RELNET_TRUNK_FUSED=0 falls back to the plain module calls (same arithmetic, more launches).
+FUSED = os.environ.get('RELNET_TRUNK_FUSED', '1') != '0'
+
+
+def _conv_relu(conv, x):
+    if FUSED and x.is_cuda:
+        return torch.cudnn_convolution_relu(x, conv.weight, conv.bias, conv.stride, conv.padding, conv.dilation, conv.groups)
+    return F.relu(conv(x))
+
+
+def _conv_add_relu(conv, x, z):
+    if FUSED and x.is_cuda:
+        return torch.cudnn_convolution_add_relu(x, conv.weight, z, 1.0, conv.bias, conv.stride, conv.padding, conv.dilation,
+                                                conv.groups)
+    return F.relu(conv(x) + z)
 
 
 class Bottleneck(nn.Module):
@@ -20,8 +39,8 @@ class Bottleneck(nn.Module):
         self.proj = nn.Conv2d(cin, cout, 1, stride=stride) if project else None
 
     def forward(self, x):
-        y = F.relu(self.c1(x)); y = F.relu(self.c2(y)); y = self.c3(y)
-        return F.relu(y + (self.proj(x) if self.proj is not None else x))
+        y = _conv_relu(self.c2, _conv_relu(self.c1, x))
+        return _conv_add_relu(self.c3, y, self.proj(x) if self.proj is not None else x)
 
 
 def _stage(cin, mid, cout, n, stride, dilation=1):
@@ -69,13 +88,13 @@ class Trunk(nn.Module):
     @torch.no_grad()
     def c4(self, image):
         """conv1 .. res4: the stride-16 feature both the RPN and res5 read"""
-        x = F.max_pool2d(F.relu(self.conv1(image)), 3, 2, ceil_mode=True)
+        x = F.max_pool2d(_conv_relu(self.conv1, image), 3, 2, ceil_mode=True)
         return self.res4(self.res3(self.res2(x)))
 
     @torch.no_grad()
     def rpn(self, c4):
         """-> rpn_cls_prob [1,2A,h,w] fp32, rpn_bbox_pred [1,4A,h,w] fp32 (SYM_BASE:685-693 + softmax over {bg, fg})"""
-        r = F.relu(self.rpn_conv(c4))
+        r = _conv_relu(self.rpn_conv, c4)
         score = self.rpn_cls(r).float()
         b, _, h, w = score.shape
         prob = F.softmax(score.reshape(b, 2, self.A * h, w), dim=1).reshape(b, 2 * self.A, h, w)
@@ -84,7 +103,7 @@ class Trunk(nn.Module):
     @torch.no_grad()
     def c5feat(self, c4):
         """res5 (dilated) + conv_new_1 + relu -> [1,256,h,w] fp32, left channels-last (consumed as NHWC)"""
-        return F.relu(self.conv_new_1(self.res5(c4))).float()
+        return _conv_relu(self.conv_new_1, self.res5(c4)).float()
 
     @torch.no_grad()
     def forward(self, image):

@@ -266,3 +266,50 @@ def test_backward_writes_into_gradient_bucket(ops):
         assert got[k].data_ptr() == bucket.views[k].data_ptr()
         assert torch.equal(bucket.views[k], ref[k])
     assert bucket.allreduce() is None                     # single process: no group, nothing to do
+
+
+def test_autograd_bindings_train_a_small_head(ops):
+    """torch.autograd Functions over the C-ABI fwd/bwd pairs: a 2FC + relation + learn-NMS head differentiates end to end
+    and agrees with autograd through the torch oracles (float32)."""
+    from relnet_b200 import autograd as AG
+    from oracle import learn_nms_np as LN, learn_nms_torch as LT
+    H, R_, d, C, n = 4, 50, 256, 6, 16
+    c = R.make_relation_case(61, R_, d, H)
+    l = LN.make_learn_nms_case(62, R=R_, C=C, d=d)
+    l['P']['roi_feat_embedding_weight'] = l['P']['roi_feat_embedding_weight'][:, :d].copy()
+    rng = np.random.RandomState(63)
+    Wc = (rng.randn(C + 1, d) * 0.05).astype(np.float32)
+    tgt = (rng.rand(n, C, 5) < 0.1).astype(np.float32)
+    rel_names = ('Wq', 'bq', 'Wk', 'bk', 'Wg', 'bg', 'Wout', 'bout')
+
+    def run(device, fwd):
+        f = torch.float32
+        X = torch.tensor(c['X'], dtype=f, device=device, requires_grad=True)
+        boxes = torch.tensor(l['rois'][:, 1:], dtype=f, device=device)
+        P = {k: torch.tensor(c[k], dtype=f, device=device, requires_grad=True) for k in rel_names}
+        Wcls = torch.tensor(Wc, dtype=f, device=device, requires_grad=True)
+        Q = {k: torch.tensor(v, dtype=f, device=device, requires_grad=True) for k, v in l['P'].items()}
+        A = fwd['relation'](X, boxes, *[P[k] for k in rel_names])
+        cls_score = A @ Wcls.T + torch.tensor(l['cls_score'], dtype=f, device=device)    # keeps the peaked classes
+        multi = fwd['learn_nms'](cls_score, A, Q)
+        t = torch.tensor(tgt, dtype=f, device=device)
+        loss = (4.0 * -(t * torch.log(multi + 1e-8)) - (1 - t) * torch.log(1 - multi + 1e-8)).sum() / (n * 5)
+        loss.backward()
+        g = {'X': X.grad, 'Wcls': Wcls.grad}
+        g.update({k: P[k].grad for k in rel_names}); g.update({k: Q[k].grad for k in Q})
+        return float(loss), {k: v.detach().cpu().numpy() for k, v in g.items()}
+
+    bp, rois, info = l['bbox_pred'], l['rois'], l['im_info']
+    ours = dict(relation=lambda X, b, *w: AG.relation(X, b, *w, group=H, residual_relu=True),
+                learn_nms=lambda cs, A, Q: AG.learn_nms(cs, T(bp), T(rois), T(info), A, Q, first_n=n)[0])
+    oracle = dict(relation=lambda X, b, *w: RT.relation_forward(X, b, *w, group=H, residual_relu=True),
+                  learn_nms=lambda cs, A, Q: LT.learn_nms_forward(cs, bp, rois, info, A, Q, first_n=n, num_fg_classes=C)[0])
+    loss_g, g_g = run('cuda', ours)
+    loss_o, g_o = run('cpu', oracle)
+    assert abs(loss_g - loss_o) <= 1e-4 * abs(loss_o)
+    for k in g_o:
+        if k in ('bk', 'nms_key_1_bias'):
+            continue                                    # identically zero in exact arithmetic
+        e = rel_err(g_g[k], g_o[k])
+        print('%-28s %.2e' % (k, e))
+        assert e <= 5e-3, (k, e)
