@@ -239,16 +239,32 @@ def run_reference(args):
     dt = (time.perf_counter() - t0) / steps
     v = round(1.0 / dt, 4)
     sample = 'full step (torch-CPU fp32 trunk + numpy/C oracle hot path), %d timed image(s) of the %d requested' % (steps, args.steps)
-    print(json.dumps({
+    emit({
         'impl': 'reference', 'metric': 'images/sec', 'value': v, 'unit': 'images/sec', 'n_gpus': args.gpus, 'steps': steps,
         'warmup': warm, 'ms_per_step': round(dt * 1e3, 2), 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'global_batch': 1, 'parallelism': 'cpu'},
         'cpu_baseline': {'value': v, 'unit': 'images/sec', 'cores': ncores, 'kind': 'port', 'sample': sample},
-        'e2e': {'value': v, 'unit': 'images/sec', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+        'e2e': {'value': v, 'unit': 'images/sec', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}})
+
+
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """the ONE JSON line, on the process's original stdout"""
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(obj) + '\n')
+    out.flush()
 
 
 def main():
+    # stdout carries exactly one JSON line: library chatter (e.g. NCCL's "NCCL version ..." banner, make output) is sent
+    # to stderr by pointing fd 1 at fd 2 for the whole run and keeping a private handle on the original stdout
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
     args = parse()
     if args.impl == 'reference':
         return run_reference(args)
@@ -348,7 +364,7 @@ def main():
         if not args.no_cpu_baseline:
             line['cpu_baseline'] = cpu_baseline()
         line['kernels'] = names
-        print(json.dumps(line))
+        emit(line)
     if dist_on:
         import torch.distributed as dist
         dist.barrier()
