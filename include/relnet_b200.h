@@ -176,6 +176,18 @@ int rn_learn_nms_fwd(const rn_learn_nms_desc* desc, const float* cls_score, cons
                      const int32_t* non_gt_index, float* nms_multi_score, float* sorted_bbox, float* sorted_score,
                      float* final_score, void* workspace, size_t workspace_bytes, rn_stream_t stream);
 
+/* Weight-only half of the head, done once per weight update (RN_PREC_F16 + class-agnostic boxes only; packed_bytes returns
+ * 0 otherwise): rank embedding -> nms_rank FC (LNMS:328-331), fp16 copies of the roi_feat_embedding / query / key /
+ * linear_out weights and the rank half of the factored projection.  rn_learn_nms_packed_fwd == rn_learn_nms_fwd minus that
+ * work (`w` is still needed for the biases, pair_pos_fc1 and nms_logit); workspace as for rn_learn_nms_fwd (also for pack). */
+size_t rn_learn_nms_packed_bytes(const rn_learn_nms_desc* desc);
+int rn_learn_nms_pack(const rn_learn_nms_desc* desc, const rn_learn_nms_weights* w, void* packed, void* workspace,
+                      size_t workspace_bytes, rn_stream_t stream);
+int rn_learn_nms_packed_fwd(const rn_learn_nms_desc* desc, const float* cls_score, const float* bbox_pred, const float* rois,
+                            const float* im_info, const float* feat, const rn_learn_nms_weights* w, const void* packed,
+                            const int32_t* non_gt_index, float* nms_multi_score, float* sorted_bbox, float* sorted_score,
+                            float* final_score, void* workspace, size_t workspace_bytes, rn_stream_t stream);
+
 /* ---- training side of the learn-NMS head ------------------------------------------------------------------------
  * Gradient buffers, one per entry of rn_learn_nms_weights (same shapes); all are OVERWRITTEN by rn_learn_nms_bwd. */
 typedef struct rn_learn_nms_grads {

@@ -79,6 +79,10 @@ SIGNATURES = {
     'rn_learn_nms_workspace_bytes': (c_sz, [C.POINTER(LearnNmsDesc)]),
     'rn_learn_nms_fwd': (C.c_int, [C.POINTER(LearnNmsDesc)] + [c_p] * 5 + [C.POINTER(LearnNmsWeights), c_p] + [c_p] * 4 +
                          [c_p, c_sz, c_p]),
+    'rn_learn_nms_packed_bytes': (c_sz, [C.POINTER(LearnNmsDesc)]),
+    'rn_learn_nms_pack': (C.c_int, [C.POINTER(LearnNmsDesc), C.POINTER(LearnNmsWeights), c_p, c_p, c_sz, c_p]),
+    'rn_learn_nms_packed_fwd': (C.c_int, [C.POINTER(LearnNmsDesc)] + [c_p] * 5 + [C.POINTER(LearnNmsWeights), c_p, c_p] + [c_p] * 4 +
+                                [c_p, c_sz, c_p]),
     'rn_learn_nms_bwd_workspace_bytes': (c_sz, [C.POINTER(LearnNmsDesc)]),
     'rn_learn_nms_bwd': (C.c_int, [C.POINTER(LearnNmsDesc)] + [c_p] * 5 + [C.POINTER(LearnNmsWeights), c_p, c_p, C.POINTER(LearnNmsWeights), c_p, c_p] +
                          [c_p, c_sz, c_p]),

@@ -269,8 +269,10 @@ int gemm_tc(cudaStream_t st, const __half* A, long long lda, const __half* B, lo
   const int BN = bn64 ? 64 : 128;
   const int tiles = tiles_m * cdiv(N, BN);
   const int kb = cdiv(K, kBK);
+  // split K only when every split keeps >= 16 K-blocks (1024 of K): below that the separate reduce launch (~3-4 us)
+  // costs more than the K loop it shortens (measured: fc_new_2 / cls_score / embedding GEMMs at M = 300, K = 1024)
   int splits = 1;
-  if (tiles < sms) splits = std::min(std::max(sms / tiles, 1), std::max(kb / 4, 1));
+  if (tiles < sms) splits = std::min(std::max(sms / tiles, 1), std::max(kb / 16, 1));
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.k_blocks_per_split = cdiv(kb, splits);
   splits = cdiv(kb, p.k_blocks_per_split);

@@ -283,12 +283,33 @@ extern "C" size_t rn_learn_nms_workspace_bytes(const rn_learn_nms_desc* d) {
   return rn::lnms_carve(d, d->R, nullptr, 0, nullptr) + 256;
 }
 
-extern "C" int rn_learn_nms_fwd(const rn_learn_nms_desc* d, const float* cls_score, const float* bbox_pred,
-                                const float* rois, const float* im_info, const float* feat,
-                                const rn_learn_nms_weights* w, const int32_t* non_gt_index, float* nms_multi_score,
-                                float* sorted_bbox, float* sorted_score, float* final_score, void* wsp, size_t ws_bytes,
-                                rn_stream_t stream) {
-  using namespace rn;
+namespace rn {
+
+// prepared (weight-only) state of the F16 class-agnostic path -- rn_learn_nms_pack
+struct LnmsPrepared {
+  const float* rank_feat;     // [n, 128] fp32
+  const void* w_emb16;        // roi_feat_embedding weight, fp16 [128, ceil8(feat_dim)]
+  const void* rel;            // relation_tc_lnms prepared blob (packed fp16 Q/K/V' weights + RQKV)
+};
+
+static bool lnms_fast_path(const rn_learn_nms_desc* d) {
+  rn_relation_desc rd = lnms_inner_desc(d);
+  return d->precision == RN_PREC_F16 && d->class_agnostic && d->first_n <= 512 && relation_tc_shape_ok(&rd) && is_sm100();
+}
+
+static size_t lnms_prepared_layout(const rn_learn_nms_desc* d, size_t* o_rank, size_t* o_emb, size_t* o_rel) {
+  rn_relation_desc rd = lnms_inner_desc(d);
+  size_t off = 0;
+  *o_rank = off; off += ws_slice((size_t)d->first_n * kNmsFeat, 4);
+  *o_emb = off; off += align_up(linear_tc_packed_bytes(d->feat_dim, kNmsFeat), 256);
+  *o_rel = off; off += align_up(relation_tc_lnms_prepared_bytes(&rd), 256);
+  return off;
+}
+
+static int lnms_forward(const rn_learn_nms_desc* d, const float* cls_score, const float* bbox_pred, const float* rois,
+                        const float* im_info, const float* feat, const rn_learn_nms_weights* w, const LnmsPrepared* prep,
+                        const int32_t* non_gt_index, float* nms_multi_score, float* sorted_bbox, float* sorted_score,
+                        float* final_score, void* wsp, size_t ws_bytes, rn_stream_t stream) {
   RN_CHECK_ARG(d && cls_score && bbox_pred && rois && im_info && feat && w && nms_multi_score && sorted_bbox &&
                    sorted_score && wsp, "rn_learn_nms_fwd: null argument");
   const int C = d->num_classes - 1, n = d->first_n, T = d->num_thresh, K = d->num_reg_classes - 1;
@@ -315,27 +336,35 @@ extern "C" int rn_learn_nms_fwd(const rn_learn_nms_desc* d, const float* cls_sco
   RN_LAUNCH_CHECK();
   lnms_valid_kernel<<<1, 32, 0, st>>>(W.cmax, C, d->class_thresh, W.valid);
   RN_LAUNCH_CHECK();
-  // rank feature (depends on weights only) and roi feature embedding
-  lnms_rank_embed_kernel<<<cdiv(n * kRankDim / 2, 256), 256, 0, st>>>(n, W.rank_emb);
-  RN_LAUNCH_CHECK();
-  if ((r = rn_linear_fwd(W.rank_emb, w->nms_rank_weight, w->nms_rank_bias, W.rank_feat, n, kRankDim, kNmsFeat, 0,
-                         d->precision, W.rel_ws, W.rel_ws_bytes, stream))) return r;
-  if ((r = rn_linear_fwd(feat, w->roi_feat_embedding_weight, w->roi_feat_embedding_bias, W.emb, d->R, d->feat_dim,
-                         kNmsFeat, 0, d->precision, W.rel_ws, W.rel_ws_bytes, stream))) return r;
-  lnms_gather_kernel<<<dim3(n, C), 128, 0, st>>>(n, C, K, d->class_agnostic, W.rank_idx, W.refined, W.emb, W.rank_feat,
+  // rank feature (depends on weights only: taken from the prepared blob when there is one) and roi feature embedding
+  const float* rank_feat = W.rank_feat;
+  if (prep) {
+    rank_feat = prep->rank_feat;
+    if ((r = linear_tc_packed(feat, prep->w_emb16, w->roi_feat_embedding_bias, W.emb, d->R, d->feat_dim, kNmsFeat, 0,
+                              W.rel_ws, W.rel_ws_bytes, st))) return r;
+  } else {
+    lnms_rank_embed_kernel<<<cdiv(n * kRankDim / 2, 256), 256, 0, st>>>(n, W.rank_emb);
+    RN_LAUNCH_CHECK();
+    if ((r = rn_linear_fwd(W.rank_emb, w->nms_rank_weight, w->nms_rank_bias, W.rank_feat, n, kRankDim, kNmsFeat, 0,
+                           d->precision, W.rel_ws, W.rel_ws_bytes, stream))) return r;
+    if ((r = rn_linear_fwd(feat, w->roi_feat_embedding_weight, w->roi_feat_embedding_bias, W.emb, d->R, d->feat_dim,
+                           kNmsFeat, 0, d->precision, W.rel_ws, W.rel_ws_bytes, stream))) return r;
+  }
+  lnms_gather_kernel<<<dim3(n, C), 128, 0, st>>>(n, C, K, d->class_agnostic, W.rank_idx, W.refined, W.emb, rank_feat,
                                                  sorted_bbox, W.feat_cls, W.boxes_cls);
   RN_LAUNCH_CHECK();
   rn_relation_desc rd = lnms_inner_desc(d);
-  if (d->precision == RN_PREC_F16 && d->class_agnostic && n <= 512 && relation_tc_shape_ok(&rd)) {
+  if (lnms_fast_path(d)) {
     // class-agnostic boxes: every class sorts the SAME refined rois, so the per-class pair geometry is a gather from
     // one [16, Rn, Rn] table (LNMS:332 builds [C, n, n, 4] position matrices -- 9x the pairs at C = 80, n = 100)
     const int ldr = (int)align_up(Rn, 4);
     if ((r = launch_geom_weight_log2_T(st, W.refined, Rn, 16, 64, 1000.f, w->nms_pair_pos_fc1_1_weight,
                                        w->nms_pair_pos_fc1_1_bias, W.lg_roi, ldr))) return r;
     GeomGather gg = {W.lg_roi, ldr, Rn, W.rank_idx, C, 1, nullptr};
-    if ((r = relation_tc_lnms(&rd, W.feat_cls, W.emb, d->R, W.rank_feat, &gg, w->nms_query_1_weight, w->nms_query_1_bias,
+    if ((r = relation_tc_lnms(&rd, W.feat_cls, W.emb, d->R, rank_feat, &gg, w->nms_query_1_weight, w->nms_query_1_bias,
                               w->nms_key_1_weight, w->nms_key_1_bias, w->nms_linear_out_1_weight,
-                              w->nms_linear_out_1_bias, W.feat_out, W.rel_ws, W.rel_ws_bytes, st))) return r;
+                              w->nms_linear_out_1_bias, W.feat_out, W.rel_ws, W.rel_ws_bytes, st,
+                              prep ? prep->rel : nullptr))) return r;
   } else if ((r = rn_relation_fwd(&rd, W.feat_cls, W.boxes_cls, nullptr, w->nms_query_1_weight, w->nms_query_1_bias,
                            w->nms_key_1_weight, w->nms_key_1_bias, w->nms_pair_pos_fc1_1_weight,
                            w->nms_pair_pos_fc1_1_bias, w->nms_linear_out_1_weight, w->nms_linear_out_1_bias, W.feat_out,
@@ -345,6 +374,68 @@ extern "C" int rn_learn_nms_fwd(const rn_learn_nms_desc* d, const float* cls_sco
                                                            final_score);
   RN_LAUNCH_CHECK();
   return RN_OK;
+}
+
+}  // namespace rn
+
+extern "C" int rn_learn_nms_fwd(const rn_learn_nms_desc* d, const float* cls_score, const float* bbox_pred,
+                                const float* rois, const float* im_info, const float* feat,
+                                const rn_learn_nms_weights* w, const int32_t* non_gt_index, float* nms_multi_score,
+                                float* sorted_bbox, float* sorted_score, float* final_score, void* wsp, size_t ws_bytes,
+                                rn_stream_t stream) {
+  return rn::lnms_forward(d, cls_score, bbox_pred, rois, im_info, feat, w, nullptr, non_gt_index, nms_multi_score,
+                          sorted_bbox, sorted_score, final_score, wsp, ws_bytes, stream);
+}
+
+// ---- weight-only work done once per weight update (RN_PREC_F16, class-agnostic): rank embedding -> nms_rank FC, fp16
+// copies of the embedding / Q / K / V' weights, and the rank half of the factored Q/K/V' projection
+extern "C" size_t rn_learn_nms_packed_bytes(const rn_learn_nms_desc* d) {
+  if (!d || !rn::lnms_fast_path(d)) return 0;
+  size_t a, b, c;
+  return rn::lnms_prepared_layout(d, &a, &b, &c);
+}
+
+extern "C" int rn_learn_nms_pack(const rn_learn_nms_desc* d, const rn_learn_nms_weights* w, void* packed, void* wsp,
+                                 size_t ws_bytes, rn_stream_t stream) {
+  using namespace rn;
+  RN_CHECK_ARG(d && w && packed && wsp, "rn_learn_nms_pack: null argument");
+  RN_CHECK_ARG(lnms_fast_path(d), "rn_learn_nms_pack: only the RN_PREC_F16 class-agnostic path has a packed form");
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t o_rank, o_emb, o_rel;
+  lnms_prepared_layout(d, &o_rank, &o_emb, &o_rel);
+  char* base = (char*)packed;
+  float* rank_feat = (float*)(base + o_rank);
+  const int n = d->first_n;
+  Workspace ws(wsp, ws_bytes);
+  float* rank_emb = ws.take<float>((size_t)n * kRankDim);
+  if (!rank_emb) { set_error("rn_learn_nms_pack: workspace too small"); return RN_ERR_WORKSPACE; }
+  int r;
+  lnms_rank_embed_kernel<<<cdiv(n * kRankDim / 2, 256), 256, 0, st>>>(n, rank_emb);
+  RN_LAUNCH_CHECK();
+  void* gws = ws.base + ws.off; const size_t gws_bytes = ws.size - ws.off;
+  if ((r = rn_linear_fwd(rank_emb, w->nms_rank_weight, w->nms_rank_bias, rank_feat, n, kRankDim, kNmsFeat, 0, RN_PREC_F16,
+                         gws, gws_bytes, stream))) return r;
+  if ((r = linear_tc_pack(w->roi_feat_embedding_weight, d->feat_dim, kNmsFeat, base + o_emb, st))) return r;
+  rn_relation_desc rd = lnms_inner_desc(d);
+  return relation_tc_lnms_prepare(&rd, rank_feat, w->nms_query_1_weight, w->nms_query_1_bias, w->nms_key_1_weight,
+                                  w->nms_key_1_bias, w->nms_linear_out_1_weight, w->nms_linear_out_1_bias, base + o_rel,
+                                  gws, gws_bytes, st);
+}
+
+extern "C" int rn_learn_nms_packed_fwd(const rn_learn_nms_desc* d, const float* cls_score, const float* bbox_pred,
+                                       const float* rois, const float* im_info, const float* feat,
+                                       const rn_learn_nms_weights* w, const void* packed, const int32_t* non_gt_index,
+                                       float* nms_multi_score, float* sorted_bbox, float* sorted_score, float* final_score,
+                                       void* wsp, size_t ws_bytes, rn_stream_t stream) {
+  using namespace rn;
+  RN_CHECK_ARG(d && packed, "rn_learn_nms_packed_fwd: null argument");
+  RN_CHECK_ARG(lnms_fast_path(d), "rn_learn_nms_packed_fwd: only the RN_PREC_F16 class-agnostic path has a packed form");
+  size_t o_rank, o_emb, o_rel;
+  lnms_prepared_layout(d, &o_rank, &o_emb, &o_rel);
+  const char* base = (const char*)packed;
+  LnmsPrepared prep = {(const float*)(base + o_rank), base + o_emb, base + o_rel};
+  return lnms_forward(d, cls_score, bbox_pred, rois, im_info, feat, w, &prep, non_gt_index, nms_multi_score, sorted_bbox,
+                      sorted_score, final_score, wsp, ws_bytes, stream);
 }
 
 extern "C" int rn_nms_multi_target_fwd(const float* bbox, const float* gt_boxes, const float* score, int32_t n, int32_t C,

@@ -45,7 +45,13 @@ int relation_tc_gathered(const rn_relation_desc* d, const float* X, const GeomGa
 // learn-NMS: Q/K/V' of row (c, i) = (emb . W^T)[idx[i,c]] + (rank_feat . W^T + b)[i]  -- two small GEMMs + a gather-add
 int relation_tc_lnms(const rn_relation_desc* d, const float* X, const float* emb, int R_emb, const float* rank_feat,
                      const GeomGather* gg, const float* Wq, const float* bq, const float* Wk, const float* bk,
-                     const float* Wout, const float* bout, float* out, void* ws, size_t ws_bytes, cudaStream_t st);
+                     const float* Wout, const float* bout, float* out, void* ws, size_t ws_bytes, cudaStream_t st,
+                     const void* prepared = nullptr);
+// weight-only half (packed fp16 weights + RQKV), built once per weight update and passed as `prepared`
+size_t relation_tc_lnms_prepared_bytes(const rn_relation_desc* d);
+int relation_tc_lnms_prepare(const rn_relation_desc* d, const float* rank_feat, const float* Wq, const float* bq,
+                             const float* Wk, const float* bk, const float* Wout, const float* bout, void* prepared,
+                             void* ws, size_t ws_bytes, cudaStream_t st);
 size_t relation_tc_lnms_extra_bytes(const rn_relation_desc* d, int R_emb);
 bool relation_tc_shape_ok(const rn_relation_desc* d);
 int launch_geom_weight_log2_T(cudaStream_t st, const float* boxes, int N, int H, int E, float wave_length, const float* Wg,

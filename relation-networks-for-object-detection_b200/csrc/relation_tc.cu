@@ -697,29 +697,54 @@ size_t relation_tc_lnms_extra_bytes(const rn_relation_desc* d, int R_emb) {
          ws_slice((size_t)d->N * W3, 4) + ws_slice((size_t)d->batch * d->N * W3, 2) + 1024;
 }
 
-int relation_tc_lnms(const rn_relation_desc* d, const float* X, const float* emb, int R_emb, const float* rank_feat,
-                     const GeomGather* gg, const float* Wq, const float* bq, const float* Wk, const float* bk,
-                     const float* Wout, const float* bout, float* out, void* wsp, size_t ws_bytes, cudaStream_t st) {
+// The weight-only half of relation_tc_lnms: packed fp16 weights and RQKV = rank_feat . W^T + b  [n, 3*H*64] fp32
+size_t relation_tc_lnms_prepared_bytes(const rn_relation_desc* d) {
+  return relation_tc_packed_bytes(d) + ws_slice((size_t)d->N * 3 * d->H * 64, 4);
+}
+
+int relation_tc_lnms_prepare(const rn_relation_desc* d, const float* rank_feat, const float* Wq, const float* bq,
+                             const float* Wk, const float* bk, const float* Wout, const float* bout, void* prepared,
+                             void* wsp, size_t ws_bytes, cudaStream_t st) {
   const size_t pk = relation_tc_packed_bytes(d);
-  RN_CHECK_ARG(pk > 0 && gg && gg->idx, "relation_tc_lnms: unsupported shape");
-  const int B = d->batch, n = d->N, D = d->d, H = d->H, d8 = (int)align_up(D, 8), W3 = 3 * H * 64;
+  RN_CHECK_ARG(pk > 0, "relation_tc_lnms_prepare: unsupported shape");
+  const int n = d->N, D = d->d, H = d->H, d8 = (int)align_up(D, 8), W3 = 3 * H * 64;
+  char* packed = (char*)prepared;
+  float* Rk = (float*)(packed + pk);
   Workspace ws(wsp, ws_bytes);
-  char* packed = ws.take<char>(pk);
-  __half* emb16 = ws.take<__half>((size_t)R_emb * d8);
   __half* rank16 = ws.take<__half>((size_t)n * d8);
-  float* E = ws.take<float>((size_t)R_emb * W3);
-  float* Rk = ws.take<float>((size_t)n * W3);
-  __half* qkv = ws.take<__half>((size_t)B * n * W3);
-  if (!qkv) { set_error("relation_tc_lnms: workspace too small"); return RN_ERR_WORKSPACE; }
+  if (!rank16) { set_error("relation_tc_lnms_prepare: workspace too small"); return RN_ERR_WORKSPACE; }
   int r;
   if ((r = relation_tc_pack(d, Wq, bq, Wk, bk, Wout, bout, packed, st))) return r;
   const __half* w16 = (const __half*)packed;
   const float* bias = (const float*)(packed + ws_slice((size_t)W3 * d8, 2));
-  if ((r = cast_rows_f16(st, emb, emb16, R_emb, D, d8))) return r;
   if ((r = cast_rows_f16(st, rank_feat, rank16, n, D, d8))) return r;
+  return gemm_tc(st, rank16, d8, w16, d8, n, W3, d8, bias, 0, 0, Rk, W3, nullptr, 0, ws.base + ws.off, ws.size - ws.off);
+}
+
+int relation_tc_lnms(const rn_relation_desc* d, const float* X, const float* emb, int R_emb, const float* rank_feat,
+                     const GeomGather* gg, const float* Wq, const float* bq, const float* Wk, const float* bk,
+                     const float* Wout, const float* bout, float* out, void* wsp, size_t ws_bytes, cudaStream_t st,
+                     const void* prepared) {
+  const size_t pk = relation_tc_packed_bytes(d);
+  RN_CHECK_ARG(pk > 0 && gg && gg->idx, "relation_tc_lnms: unsupported shape");
+  const int B = d->batch, n = d->N, D = d->d, H = d->H, d8 = (int)align_up(D, 8), W3 = 3 * H * 64;
+  Workspace ws(wsp, ws_bytes);
+  char* prep_local = prepared ? nullptr : ws.take<char>(relation_tc_lnms_prepared_bytes(d));
+  __half* emb16 = ws.take<__half>((size_t)R_emb * d8);
+  float* E = ws.take<float>((size_t)R_emb * W3);
+  __half* qkv = ws.take<__half>((size_t)B * n * W3);
+  if (!qkv) { set_error("relation_tc_lnms: workspace too small"); return RN_ERR_WORKSPACE; }
+  int r;
   void* gws = ws.base + ws.off; const size_t gws_bytes = ws.size - ws.off;
+  if (!prepared) {      // one-shot form: build the weight-only half now
+    if ((r = relation_tc_lnms_prepare(d, rank_feat, Wq, bq, Wk, bk, Wout, bout, prep_local, gws, gws_bytes, st))) return r;
+    prepared = prep_local;
+  }
+  const char* packed = (const char*)prepared;
+  const float* Rk = (const float*)(packed + pk);
+  const __half* w16 = (const __half*)packed;
+  if ((r = cast_rows_f16(st, emb, emb16, R_emb, D, d8))) return r;
   if ((r = gemm_tc(st, emb16, d8, w16, d8, R_emb, W3, d8, nullptr, 0, 0, E, W3, nullptr, 0, gws, gws_bytes))) return r;
-  if ((r = gemm_tc(st, rank16, d8, w16, d8, n, W3, d8, bias, 0, 0, Rk, W3, nullptr, 0, gws, gws_bytes))) return r;
   {
     const size_t total = (size_t)B * n * (W3 / 8);
     size_t blocks = (total + 255) / 256;

@@ -280,6 +280,17 @@ def learn_nms(cls_score, bbox_pred, rois, im_info, feat, weights, first_n=100, n
     final = torch.empty((first_n, C_), dtype=torch.float32, device=dev)
     lib = L.lib()
     ws = _workspace(lib.rn_learn_nms_workspace_bytes(C.byref(desc)), dev)
+    pk_bytes = lib.rn_learn_nms_packed_bytes(C.byref(desc))
+    if pk_bytes:        # RN_PREC_F16 class-agnostic: weight-only work cached per weight version (like rn_relation_pack)
+        def pack(buf):
+            L.check(lib.rn_learn_nms_pack(C.byref(desc), C.byref(w), _ptr(buf), _ptr(ws), ws.numel(), _stream()),
+                    'rn_learn_nms_pack')
+        packed = _packs.get(tuple(keep), pk_bytes, pack, tag=('learn_nms', first_n, feat.shape[1]))
+        L.check(lib.rn_learn_nms_packed_fwd(C.byref(desc), _ptr(cls_score), _ptr(bbox_pred), _ptr(rois), _ptr(im_info),
+                                            _ptr(feat), C.byref(w), _ptr(packed), _ptr(kidx), _ptr(multi), _ptr(sbbox),
+                                            _ptr(sscore), _ptr(final), _ptr(ws), ws.numel(), _stream()),
+                'rn_learn_nms_packed_fwd')
+        return multi, sbbox, sscore, final
     L.check(lib.rn_learn_nms_fwd(C.byref(desc), _ptr(cls_score), _ptr(bbox_pred), _ptr(rois), _ptr(im_info), _ptr(feat),
                                  C.byref(w), _ptr(kidx), _ptr(multi), _ptr(sbbox), _ptr(sscore), _ptr(final), _ptr(ws),
                                  ws.numel(), _stream()), 'rn_learn_nms_fwd')
