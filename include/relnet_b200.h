@@ -120,6 +120,13 @@ int rn_relation_bwd(const rn_relation_desc* desc, const float* X, const float* b
                     const float* Wout, const float* bout, const float* dOut, float* dX, float* dWq, float* dbq, float* dWk,
                     float* dbk, float* dWg, float* dbg, float* dWout, float* dbout, void* workspace,
                     size_t workspace_bytes, rn_stream_t stream);
+/* rn_relation_packed_stages with fp16 side channels: X_f16 (NULL or the producer's fp16 copy of X, [batch*N, d], d % 8 == 0)
+ * replaces the module's own cast; out_f16 (NULL or [batch*N, dout] fp16) receives a copy of `out` for the consumer GEMM
+ * (rn_linear_packed_f16in_fwd).  Same arithmetic as rn_relation_packed_fwd. */
+int rn_relation_packed_fwd_f16io(const rn_relation_desc* desc, const float* X, const void* X_f16, const float* boxes,
+                                 const int32_t* key_index, const void* packed, const float* Wg, const float* bg, float* out,
+                                 void* out_f16, void* workspace, size_t workspace_bytes, int32_t stage_mask,
+                                 rn_stream_t stream);
 size_t rn_linear_packed_bytes(int32_t in, int32_t out);
 int rn_linear_pack(const float* W, int32_t in, int32_t out, void* packed, rn_stream_t stream);
 int rn_linear_packed_fwd(const float* x, const void* packed_W, const float* b, float* y, int32_t rows, int32_t in,
@@ -184,7 +191,8 @@ size_t rn_learn_nms_packed_bytes(const rn_learn_nms_desc* desc);
 int rn_learn_nms_pack(const rn_learn_nms_desc* desc, const rn_learn_nms_weights* w, void* packed, void* workspace,
                       size_t workspace_bytes, rn_stream_t stream);
 int rn_learn_nms_packed_fwd(const rn_learn_nms_desc* desc, const float* cls_score, const float* bbox_pred, const float* rois,
-                            const float* im_info, const float* feat, const rn_learn_nms_weights* w, const void* packed,
+                            const float* im_info, const float* feat, const void* feat_f16 /* fp16 copy of feat or NULL */,
+                            const rn_learn_nms_weights* w, const void* packed,
                             const int32_t* non_gt_index, float* nms_multi_score, float* sorted_bbox, float* sorted_score,
                             float* final_score, void* workspace, size_t workspace_bytes, rn_stream_t stream);
 

@@ -308,7 +308,7 @@ static size_t lnms_prepared_layout(const rn_learn_nms_desc* d, size_t* o_rank, s
 
 static int lnms_forward(const rn_learn_nms_desc* d, const float* cls_score, const float* bbox_pred, const float* rois,
                         const float* im_info, const float* feat, const rn_learn_nms_weights* w, const LnmsPrepared* prep,
-                        const int32_t* non_gt_index, float* nms_multi_score, float* sorted_bbox, float* sorted_score,
+                        const void* feat_f16, const int32_t* non_gt_index, float* nms_multi_score, float* sorted_bbox, float* sorted_score,
                         float* final_score, void* wsp, size_t ws_bytes, rn_stream_t stream) {
   RN_CHECK_ARG(d && cls_score && bbox_pred && rois && im_info && feat && w && nms_multi_score && sorted_bbox &&
                    sorted_score && wsp, "rn_learn_nms_fwd: null argument");
@@ -340,8 +340,11 @@ static int lnms_forward(const rn_learn_nms_desc* d, const float* cls_score, cons
   const float* rank_feat = W.rank_feat;
   if (prep) {
     rank_feat = prep->rank_feat;
-    if ((r = linear_tc_packed(feat, prep->w_emb16, w->roi_feat_embedding_bias, W.emb, d->R, d->feat_dim, kNmsFeat, 0,
-                              W.rel_ws, W.rel_ws_bytes, st))) return r;
+    if (feat_f16) {     // the producer's fp16 copy of feat: no cast launch
+      if ((r = linear_tc_packed_f16in(feat_f16, prep->w_emb16, w->roi_feat_embedding_bias, W.emb, nullptr, d->R, d->feat_dim,
+                                      kNmsFeat, 0, W.rel_ws, W.rel_ws_bytes, st))) return r;
+    } else if ((r = linear_tc_packed(feat, prep->w_emb16, w->roi_feat_embedding_bias, W.emb, d->R, d->feat_dim, kNmsFeat, 0,
+                                     W.rel_ws, W.rel_ws_bytes, st))) return r;
   } else {
     lnms_rank_embed_kernel<<<cdiv(n * kRankDim / 2, 256), 256, 0, st>>>(n, W.rank_emb);
     RN_LAUNCH_CHECK();
@@ -383,7 +386,7 @@ extern "C" int rn_learn_nms_fwd(const rn_learn_nms_desc* d, const float* cls_sco
                                 const rn_learn_nms_weights* w, const int32_t* non_gt_index, float* nms_multi_score,
                                 float* sorted_bbox, float* sorted_score, float* final_score, void* wsp, size_t ws_bytes,
                                 rn_stream_t stream) {
-  return rn::lnms_forward(d, cls_score, bbox_pred, rois, im_info, feat, w, nullptr, non_gt_index, nms_multi_score,
+  return rn::lnms_forward(d, cls_score, bbox_pred, rois, im_info, feat, w, nullptr, nullptr, non_gt_index, nms_multi_score,
                           sorted_bbox, sorted_score, final_score, wsp, ws_bytes, stream);
 }
 
@@ -423,7 +426,7 @@ extern "C" int rn_learn_nms_pack(const rn_learn_nms_desc* d, const rn_learn_nms_
 }
 
 extern "C" int rn_learn_nms_packed_fwd(const rn_learn_nms_desc* d, const float* cls_score, const float* bbox_pred,
-                                       const float* rois, const float* im_info, const float* feat,
+                                       const float* rois, const float* im_info, const float* feat, const void* feat_f16,
                                        const rn_learn_nms_weights* w, const void* packed, const int32_t* non_gt_index,
                                        float* nms_multi_score, float* sorted_bbox, float* sorted_score, float* final_score,
                                        void* wsp, size_t ws_bytes, rn_stream_t stream) {
@@ -434,7 +437,7 @@ extern "C" int rn_learn_nms_packed_fwd(const rn_learn_nms_desc* d, const float* 
   lnms_prepared_layout(d, &o_rank, &o_emb, &o_rel);
   const char* base = (const char*)packed;
   LnmsPrepared prep = {(const float*)(base + o_rank), base + o_emb, base + o_rel};
-  return lnms_forward(d, cls_score, bbox_pred, rois, im_info, feat, w, &prep, non_gt_index, nms_multi_score, sorted_bbox,
+  return lnms_forward(d, cls_score, bbox_pred, rois, im_info, feat, w, &prep, feat_f16, non_gt_index, nms_multi_score, sorted_bbox,
                       sorted_score, final_score, wsp, ws_bytes, stream);
 }
 

@@ -250,6 +250,19 @@ extern "C" int rn_relation_packed_stages(const rn_relation_desc* d, const float*
                                 stage_mask, nullptr);
 }
 
+// fp16 in / fp16 out variant: X_f16 (optional) is the producer's fp16 copy of X, out_f16 (optional) receives an fp16 copy
+// of the output for the consumer GEMM -- the cast launches between the layers of the head disappear
+extern "C" int rn_relation_packed_fwd_f16io(const rn_relation_desc* d, const float* X, const void* X_f16,
+                                            const float* boxes, const int32_t* key_index, const void* packed,
+                                            const float* Wg, const float* bg, float* out, void* out_f16, void* ws,
+                                            size_t ws_bytes, int32_t stage_mask, rn_stream_t stream) {
+  int r = rn::relation_check_desc(d);
+  if (r) return r;
+  RN_CHECK_ARG(X && boxes && packed && Wg && bg && out && ws, "rn_relation_packed_fwd_f16io: null pointer argument");
+  return rn::relation_tc_packed(d, X, boxes, key_index, packed, Wg, bg, out, ws, ws_bytes, (cudaStream_t)stream,
+                                stage_mask, nullptr, X_f16, out_f16);
+}
+
 extern "C" size_t rn_linear_packed_bytes(int32_t in, int32_t out) { return rn::linear_tc_packed_bytes(in, out); }
 
 extern "C" int rn_linear_pack(const float* W, int32_t in, int32_t out, void* packed, rn_stream_t stream) {

@@ -35,7 +35,8 @@ int relation_tc_pack(const rn_relation_desc* d, const float* Wq, const float* bq
                      const float* Wout, const float* bout, void* packed, cudaStream_t st);
 int relation_tc_packed(const rn_relation_desc* d, const float* X, const float* boxes, const int* key_index,
                        const void* packed, const float* Wg, const float* bg, float* out, void* ws, size_t ws_bytes,
-                       cudaStream_t st, int stage_mask, const struct GeomGather* gg = nullptr);
+                       cudaStream_t st, int stage_mask, const struct GeomGather* gg = nullptr, const void* x_f16 = nullptr,
+                       void* out_f16 = nullptr);
 // geometry gathered from one roi-level table lg_table [H, R, ld]: row i of problem b is roi idx[i*stride_i + b*stride_b]
 struct GeomGather { const float* lg_table; int ld; int R; const int* idx; int stride_i; int stride_b;
                     const void* qkv_ext; };   // qkv_ext: optional pre-computed fp16 [B*N, 3*H*64] projections (skips the GEMM)

@@ -35,6 +35,7 @@ struct AttnParams {
   const float* lg; int ldg;       // [B,H,N,ldg] log2 geometry weight
   const float* X; int ldx;        // residual source [B,N,ldx] (nullptr: none)
   float* out; int ldo;            // [B,N,ldo]
+  __half* out16; int ldo16;       // optional fp16 copy of out (the next GEMM's operand: saves its cast launch)
   int dv;                         // valid output columns per head (<= 64)
   int relu;
   float scale_log2;               // log2(e)/sqrt(dk)
@@ -254,6 +255,10 @@ __global__ void __launch_bounds__(192, 1) relation_attn_tc_kernel(const __grid_c
           }
           if (p.relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
           *reinterpret_cast<float4*>(dst + q) = y;
+          if (p.out16) {
+            __half2* d16 = reinterpret_cast<__half2*>(p.out16 + ((size_t)b * p.N + n) * p.ldo16 + (size_t)h * 64 + q);
+            d16[0] = __floats2half2_rn(y.x, y.y); d16[1] = __floats2half2_rn(y.z, y.w);
+          }
         }
       } else {
 #pragma unroll
@@ -263,6 +268,7 @@ __global__ void __launch_bounds__(192, 1) relation_attn_tc_kernel(const __grid_c
             if (res) y += res[q];
             if (p.relu) y = fmaxf(y, 0.f);
             dst[q] = y;
+            if (p.out16) p.out16[((size_t)b * p.N + n) * p.ldo16 + (size_t)h * p.dv + q] = __float2half_rn(y);
           }
       }
     }
@@ -471,6 +477,7 @@ __global__ void __launch_bounds__(256) relation_attn_combine_kernel(TileParams t
         if (res) v += res[q];
         if (p.relu) v = fmaxf(v, 0.f);
         dst[q] = v;
+        if (p.out16) p.out16[((size_t)b * p.N + n) * p.ldo16 + (size_t)h * p.dv + q] = __float2half_rn(v);
       }
     }
   }
@@ -554,7 +561,7 @@ int relation_tc_pack(const rn_relation_desc* d, const float* Wq, const float* bq
 
 int relation_tc_packed(const rn_relation_desc* d, const float* X, const float* boxes, const int* key_index,
                        const void* packed, const float* Wg, const float* bg, float* out, void* wsp, size_t ws_bytes,
-                       cudaStream_t st, int stage_mask, const GeomGather* gg) {
+                       cudaStream_t st, int stage_mask, const GeomGather* gg, const void* x_f16, void* out_f16) {
   const bool do_proj = stage_mask & 1, do_geom = stage_mask & 2, do_attn = stage_mask & 4;
   RN_CHECK_ARG(is_sm100(), "RN_PREC_F16 needs an sm_100 device (tcgen05); use RN_PREC_FP32");
   RN_CHECK_ARG(tc_shape_ok(d), "RN_PREC_F16 relation kernel supports dq == 64*H and dout/H <= 64 (got dq=%d dout=%d H=%d); "
@@ -579,7 +586,10 @@ int relation_tc_packed(const rn_relation_desc* d, const float* X, const float* b
   void* gws = ws.base + ws.off; const size_t gws_bytes = ws.size - ws.off;
   int r;
   const bool ext_qkv = gg && gg->qkv_ext;
-  if (do_proj && !ext_qkv && (r = cast_rows_f16(st, X, x16, B * N, D, d8))) return r;
+  if (x_f16) {          // the producer already wrote an fp16 copy of X ([B*N, d], d % 8 == 0): no cast launch
+    RN_CHECK_ARG(D == d8, "rn_relation: X_f16 needs d %% 8 == 0 (d = %d)", D);
+    x16 = (__half*)x_f16;
+  } else if (do_proj && !ext_qkv && (r = cast_rows_f16(st, X, x16, B * N, D, d8))) return r;
   const __half *Qp, *Kp, *Vp; long long ldq, ldk; long long bq_pitch, bk_pitch;
   if (ext_qkv) {
     const __half* e = (const __half*)gg->qkv_ext;
@@ -613,6 +623,7 @@ int relation_tc_packed(const rn_relation_desc* d, const float* X, const float* b
   if (gg) { p.lg = gg->lg_table; p.ldg = gg->ld; p.R = gg->R; p.gidx = gg->idx; p.gs_i = gg->stride_i; p.gs_b = gg->stride_b; }
   p.X = d->fuse_residual_relu ? X : nullptr; p.ldx = D;
   p.out = out; p.ldo = d->dout; p.dv = dv; p.relu = d->fuse_residual_relu;
+  p.out16 = (__half*)out_f16; p.ldo16 = d->dout;
   p.scale_log2 = 1.4426950408889634f / sqrtf(64.f);
   static thread_local bool configured = false;
   if (!configured) {

@@ -75,8 +75,10 @@ def default_precision():
 
 # ------------------------------------------------------------------------------------------------------------------
 def relation(X, boxes, Wq, bq, Wk, bk, Wg, bg, Wout, bout, key_index=None, M=None, group=16, residual_relu=False,
-             precision=None, wave_length=1000.0, return_softmax=False, stage_mask=7, workspace=None, out=None):
-    """Object-relation module (SYM_REL:30-151 + :267-268).  X [N,d] or [B,N,d]; boxes [N,4] or [B,N,4]."""
+             precision=None, wave_length=1000.0, return_softmax=False, stage_mask=7, workspace=None, out=None,
+             x_f16=None, want_f16=False):
+    """Object-relation module (SYM_REL:30-151 + :267-268).  X [N,d] or [B,N,d]; boxes [N,4] or [B,N,4].
+    RN_PREC_F16 only: x_f16 = the producer's fp16 copy of X (skips the cast launch); want_f16 -> returns (out, out_f16)."""
     precision = precision or default_precision()
     X = _f32(X, 'X'); boxes = _f32(boxes, 'boxes')
     batched = X.dim() == 3
@@ -120,6 +122,15 @@ def relation(X, boxes, Wq, bq, Wk, bk, Wg, bg, Wout, bout, key_index=None, M=Non
             L.check(lib.rn_relation_pack(C.byref(desc), _ptr(Wq), _ptr(bq), _ptr(Wk), _ptr(bk), _ptr(Wout2), _ptr(bout),
                                          _ptr(buf), _stream()), 'rn_relation_pack')
         packed = _packs.get((Wq, bq, Wk, bk, Wout2, bout), lib.rn_relation_packed_bytes(C.byref(desc)), pack)
+        if x_f16 is not None or want_f16:
+            if x_f16 is not None and not (x_f16.is_cuda and x_f16.dtype == torch.float16 and x_f16.is_contiguous()
+                                          and x_f16.numel() == X.numel()):
+                raise L.RelnetError('relation: x_f16 must be the contiguous fp16 CUDA copy of X')
+            out16 = torch.empty(out.shape, dtype=torch.float16, device=X.device) if want_f16 else None
+            L.check(lib.rn_relation_packed_fwd_f16io(C.byref(desc), _ptr(X), _ptr(x_f16), _ptr(boxes), _ptr(kidx),
+                                                     _ptr(packed), _ptr(Wg), _ptr(bg), _ptr(out), _ptr(out16), _ptr(ws),
+                                                     ws.numel(), stage_mask, _stream()), 'rn_relation_packed_fwd_f16io')
+            return (out, out16) if want_f16 else out
         if stage_mask != 7:     # measurement hook: rerun a subset of the stages on the previous call's intermediates
             L.check(lib.rn_relation_packed_stages(C.byref(desc), _ptr(X), _ptr(boxes), _ptr(kidx), _ptr(packed), _ptr(Wg),
                                                   _ptr(bg), _ptr(out), _ptr(ws), ws.numel(), stage_mask, _stream()),
@@ -218,7 +229,8 @@ def geometry_weight(boxes, Wg, bg, M=None, key_index=None, wave_length=1000.0):
     return g
 
 
-def linear(x, W, b=None, relu=False, precision=None):
+def linear(x, W, b=None, relu=False, precision=None, x_f16=None, want_f16=False):
+    """y = act(x W^T + b).  RN_PREC_F16 only: x_f16 = fp16 copy of x (no cast launch); want_f16 -> returns (y, y_f16)."""
     precision = precision or default_precision()
     x = _f32(x, 'x'); W = _f32(W, 'W'); b = _f32(b, 'b') if b is not None else None
     x2 = x.reshape(x.shape[0], -1)
@@ -232,9 +244,18 @@ def linear(x, W, b=None, relu=False, precision=None):
         def pack(buf):
             L.check(lib.rn_linear_pack(_ptr(W), cin, cout, _ptr(buf), _stream()), 'rn_linear_pack')
         packed = _packs.get((W,), lib.rn_linear_packed_bytes(cin, cout), pack)
+        if (x_f16 is not None or want_f16) and cin % 8 == 0:
+            if x_f16 is None:
+                x_f16 = x2.to(torch.float16)
+            elif not (x_f16.is_cuda and x_f16.dtype == torch.float16 and x_f16.is_contiguous() and x_f16.numel() == x2.numel()):
+                raise L.RelnetError('linear: x_f16 must be the contiguous fp16 CUDA copy of x')
+            y16 = torch.empty((rows, cout), dtype=torch.float16, device=x.device) if want_f16 else None
+            L.check(lib.rn_linear_packed_f16in_fwd(_ptr(x_f16), _ptr(packed), _ptr(b), _ptr(y), _ptr(y16), rows, cin, cout,
+                                                   int(relu), _ptr(ws), ws.numel(), _stream()), 'rn_linear_packed_f16in_fwd')
+            return (y, y16) if want_f16 else y
         L.check(lib.rn_linear_packed_fwd(_ptr(x2), _ptr(packed), _ptr(b), _ptr(y), rows, cin, cout, int(relu), _ptr(ws),
                                          ws.numel(), _stream()), 'rn_linear_packed_fwd')
-        return y
+        return (y, y.to(torch.float16)) if want_f16 else y
     L.check(lib.rn_linear_fwd(_ptr(x2), _ptr(W), _ptr(b), _ptr(y), rows, cin, cout, int(relu), PREC[precision], _ptr(ws),
                               ws.numel(), _stream()), 'rn_linear_fwd')
     return y
@@ -262,8 +283,9 @@ def _learn_nms_desc(cls_score, bbox_pred, rois, feat, first_n, num_thresh, class
 
 def learn_nms(cls_score, bbox_pred, rois, im_info, feat, weights, first_n=100, num_thresh=5, class_thresh=0.01,
               class_agnostic=True, means=None, stds=None, nongt_dim=None, non_gt_index=None, merge_method=-1,
-              precision=None):
-    """learn_nms CustomOp forward (LNMS:238-401) + merge.  ``weights``: dict by checkpoint name (LNMS:429-441)."""
+              precision=None, feat_f16=None):
+    """learn_nms CustomOp forward (LNMS:238-401) + merge.  ``weights``: dict by checkpoint name (LNMS:429-441).
+    feat_f16 (RN_PREC_F16 only): the producer's fp16 copy of feat, saves the cast launch."""
     precision = precision or default_precision()
     cls_score = _f32(cls_score, 'cls_score'); bbox_pred = _f32(bbox_pred, 'bbox_pred'); rois = _f32(rois, 'rois')
     im_info = _f32(im_info, 'im_info').reshape(-1); feat = _f32(feat, 'feat')
@@ -286,8 +308,11 @@ def learn_nms(cls_score, bbox_pred, rois, im_info, feat, weights, first_n=100, n
             L.check(lib.rn_learn_nms_pack(C.byref(desc), C.byref(w), _ptr(buf), _ptr(ws), ws.numel(), _stream()),
                     'rn_learn_nms_pack')
         packed = _packs.get(tuple(keep), pk_bytes, pack, tag=('learn_nms', first_n, feat.shape[1]))
+        if feat_f16 is not None and not (feat_f16.is_cuda and feat_f16.dtype == torch.float16 and feat_f16.is_contiguous()
+                                         and feat_f16.numel() == feat.numel() and feat.shape[1] % 8 == 0):
+            raise L.RelnetError('learn_nms: feat_f16 must be the contiguous fp16 CUDA copy of feat (feat_dim % 8 == 0)')
         L.check(lib.rn_learn_nms_packed_fwd(C.byref(desc), _ptr(cls_score), _ptr(bbox_pred), _ptr(rois), _ptr(im_info),
-                                            _ptr(feat), C.byref(w), _ptr(packed), _ptr(kidx), _ptr(multi), _ptr(sbbox),
+                                            _ptr(feat), _ptr(feat_f16), C.byref(w), _ptr(packed), _ptr(kidx), _ptr(multi), _ptr(sbbox),
                                             _ptr(sscore), _ptr(final), _ptr(ws), ws.numel(), _stream()),
                 'rn_learn_nms_packed_fwd')
         return multi, sbbox, sscore, final
@@ -458,7 +483,7 @@ def roi_pool_backward(grad_out, argmax, rois, data_shape):
     return dd
 
 
-def roi_pool_fc(data, rois, W, b, pooled_size=(7, 7), spatial_scale=0.0625, relu=False):
+def roi_pool_fc(data, rois, W, b, pooled_size=(7, 7), spatial_scale=0.0625, relu=False, want_f16=False):
     """ROIPooling + FullyConnected fused at the data-layout level (SYM_REL:252-262 with RN_PREC_F16): channels-last
     feature map -> fp16 pooled [R, PH*PW*C] -> tcgen05 GEMM against the K-permuted packed weight.  Returns fp32 [R, out].
     ``data`` is an NCHW-shaped tensor; a channels_last one is consumed without a copy."""
@@ -481,9 +506,10 @@ def roi_pool_fc(data, rois, W, b, pooled_size=(7, 7), spatial_scale=0.0625, relu
     packed = _packs.get_tagged('chw2hwc', (W,), lib.rn_linear_packed_bytes(cin, cout), pack)
     y = torch.empty((R, cout), dtype=torch.float32, device=data.device)
     ws = _workspace(lib.rn_linear_workspace_bytes(R, cin, cout, 1), data.device)
-    L.check(lib.rn_linear_packed_f16in_fwd(_ptr(pooled), _ptr(packed), _ptr(b), _ptr(y), None, R, cin, cout, int(relu),
+    y16 = torch.empty((R, cout), dtype=torch.float16, device=data.device) if want_f16 else None
+    L.check(lib.rn_linear_packed_f16in_fwd(_ptr(pooled), _ptr(packed), _ptr(b), _ptr(y), _ptr(y16), R, cin, cout, int(relu),
                                            _ptr(ws), ws.numel(), _stream()), 'rn_linear_packed_f16in_fwd')
-    return y
+    return (y, y16) if want_f16 else y
 
 
 def deform_psroi_pool(data, rois, trans=None, spatial_scale=0.0625, output_dim=256, group_size=1, pooled_size=7,

@@ -74,7 +74,7 @@ class RelationHead(object):
         self.nongt_dim = post_nms_top_n
         self._ws, self._dummy, self._side = {}, {}, None
 
-    def relation(self, x, boxes, idx, nongt_dim, stage_mask=7):
+    def relation(self, x, boxes, idx, nongt_dim, stage_mask=7, x_f16=None, want_f16=False):
         P = self.P
         ws = None
         if self.precision == 'f16':        # module-owned scratch so the geometry stage can run early on another stream
@@ -85,7 +85,8 @@ class RelationHead(object):
         return ops.relation(x, boxes, P['query_%d_weight' % idx], P['query_%d_bias' % idx], P['key_%d_weight' % idx],
                             P['key_%d_bias' % idx], P['pair_pos_fc1_%d_weight' % idx], P['pair_pos_fc1_%d_bias' % idx],
                             P['linear_out_%d_weight' % idx], P['linear_out_%d_bias' % idx], M=nongt_dim, group=16,
-                            residual_relu=True, precision=self.precision, stage_mask=stage_mask, workspace=ws)
+                            residual_relu=True, precision=self.precision, stage_mask=stage_mask, workspace=ws,
+                            x_f16=x_f16, want_f16=want_f16)
 
     def geometry_early(self, rois):
         """Both relation modules' geometry terms depend only on the rois: run them now (on whatever stream is current,
@@ -121,9 +122,26 @@ class RelationHead(object):
         P, prec = self.P, self.precision
         rel_mask = 5 if geometry_done else 7        # 1 = projection, 2 = geometry, 4 = fused attention
         boxes = rois[:, 1:].contiguous()                                                          # :337
-        if prec == 'f16':        # :335 + :344 at the layout level: channels-last pool -> fp16 -> K-permuted fc_new_1
-            fc1 = ops.roi_pool_fc(conv_feat, rois, P['fc_new_1_weight'], P['fc_new_1_bias'], (7, 7),
-                                  1.0 / self.cfg['feat_stride'])
+        if prec == 'f16':
+            # :335 + :344 at the layout level: channels-last pool -> fp16 -> K-permuted fc_new_1.  Every layer hands an
+            # fp16 copy of its output to the next GEMM (written by the producing epilogue), so no cast kernels run.
+            fc1, fc1_h = ops.roi_pool_fc(conv_feat, rois, P['fc_new_1_weight'], P['fc_new_1_bias'], (7, 7),
+                                         1.0 / self.cfg['feat_stride'], want_f16=True)
+            if join is not None:
+                torch.cuda.current_stream().wait_stream(join)
+            fc_all_1, a1_h = self.relation(fc1, boxes, 1, self.nongt_dim, rel_mask, x_f16=fc1_h, want_f16=True)   # :346-351
+            fc2, fc2_h = ops.linear(fc_all_1, P['fc_new_2_weight'], P['fc_new_2_bias'], precision=prec, x_f16=a1_h,
+                                    want_f16=True)                                                                # :353
+            fc_all_2, a2_h = self.relation(fc2, boxes, 2, self.nongt_dim, rel_mask, x_f16=fc2_h, want_f16=True)   # :354-359
+            cls_score = ops.linear(fc_all_2, P['cls_score_weight'], P['cls_score_bias'], precision=prec, x_f16=a2_h)
+            bbox_pred = ops.linear(fc_all_2, P['bbox_pred_weight'], P['bbox_pred_bias'], precision=prec, x_f16=a2_h)
+            multi, sorted_bbox, sorted_score, final = ops.learn_nms(                              # :518-560
+                cls_score, bbox_pred, rois, im_info, fc_all_2, {k: P[k] for k in NMS_NAMES}, first_n=self.first_n,
+                class_thresh=self.class_thresh, nongt_dim=self.nongt_dim, merge_method=self.merge_method, precision=prec,
+                feat_f16=a2_h)
+            return dict(rois=rois, cls_score=cls_score, bbox_pred=bbox_pred, fc_all_2_relu=fc_all_2,
+                        nms_multi_score=multi, learn_nms_sorted_bbox=sorted_bbox, sorted_score=sorted_score,
+                        nms_final_score_output=final)
         else:
             pooled = ops.roi_pool(conv_feat, rois, (7, 7), 1.0 / self.cfg['feat_stride'])         # :335
             fc1 = ops.linear(pooled, P['fc_new_1_weight'], P['fc_new_1_bias'], precision=prec)    # :344

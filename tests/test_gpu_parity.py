@@ -356,3 +356,20 @@ def test_hot_path_pipeline_matches_oracle(ops):
         print('pipeline[%s]: fc_all_2 %.2e cls_score %.2e sorted_score %.2e final %.2e' % (prec, e_feat, e_cls, e_ss, e_fin))
         tol = 3e-4 if prec == 'fp32' else 3e-3          # two relation modules + 4 fp16 GEMMs (K up to 12544) in sequence
         assert e_feat < tol and e_cls < tol and e_ss < tol and e_fin < (2 * tol if prec == 'fp32' else 2e-2)
+
+
+def test_f16_side_channels_are_bitwise_the_same_path(ops):
+    """x_f16 / want_f16 (fp16 copies handed from one layer's epilogue to the next GEMM) change launches, not results"""
+    if not ops.device_info()['sm100']:
+        pytest.skip('tcgen05 path only')
+    c = R.make_relation_case(77, 300, 1024, 16)
+    t = [T(c[k]) for k in ('X', 'boxes', 'Wq', 'bq', 'Wk', 'bk', 'Wg', 'bg', 'Wout', 'bout')]
+    ref = ops.relation(*t, group=16, residual_relu=True, precision='f16')
+    out, out_h = ops.relation(*t, group=16, residual_relu=True, precision='f16', x_f16=t[0].half(), want_f16=True)
+    assert torch.equal(out, ref) and torch.equal(out_h, ref.half())
+    W = T(np.random.RandomState(1).randn(256, 1024).astype(np.float32) * 0.03); b = T(np.zeros(256, np.float32))
+    y = ops.linear(ref, W, b, precision='f16')
+    y2, y2_h = ops.linear(ref, W, b, precision='f16', x_f16=out_h, want_f16=True)
+    assert torch.equal(y, y2) and torch.equal(y2_h, y.half())
+    with pytest.raises(Exception):
+        ops.relation(*t, group=16, residual_relu=True, precision='f16', x_f16=t[0].half()[:100])
