@@ -132,6 +132,15 @@ int rn_linear_pack(const float* W, int32_t in, int32_t out, void* packed, rn_str
 int rn_linear_packed_fwd(const float* x, const void* packed_W, const float* b, float* y, int32_t rows, int32_t in,
                          int32_t out, int32_t relu, void* workspace, size_t workspace_bytes, rn_stream_t stream);
 
+/* Several FullyConnected layers over the SAME input as one GEMM (cls_score + bbox_pred + roi_feat_embedding all read
+ * fc_all_2_relu: SYM_REL_NMS:360-365,469-472).  nout <= 4; W[i] is [outs[i], in], b[i] [outs[i]] or NULL; ys[i] receives
+ * the contiguous [rows, outs[i]] output of layer i.  x_f16 is the producer's fp16 copy of the input ([rows, in], in % 8 == 0). */
+size_t rn_linear_multi_packed_bytes(const int32_t* outs, int32_t nout, int32_t in);
+int rn_linear_multi_pack(const float* const* W, const float* const* b, const int32_t* outs, int32_t nout, int32_t in,
+                         void* packed, rn_stream_t stream);
+int rn_linear_multi_packed_f16in_fwd(const void* x_f16, const void* packed, float* const* ys, const int32_t* outs, int32_t nout,
+                                     int32_t rows, int32_t in, void* workspace, size_t workspace_bytes, rn_stream_t stream);
+
 /* Fused-head fast path (same arithmetic, fewer bytes): ROI max-pool straight from the trunk's channels-last feature map
  * to an fp16 [R, PH*PW, C] tensor, consumed by fc_new_1 through a K-permuted packed weight (no fp32 pooled tensor, no
  * cast kernel).  data_nhwc [B,H,W,C] fp32; out_f16 [R, PH*PW*C] fp16. */
@@ -192,6 +201,7 @@ int rn_learn_nms_pack(const rn_learn_nms_desc* desc, const rn_learn_nms_weights*
                       size_t workspace_bytes, rn_stream_t stream);
 int rn_learn_nms_packed_fwd(const rn_learn_nms_desc* desc, const float* cls_score, const float* bbox_pred, const float* rois,
                             const float* im_info, const float* feat, const void* feat_f16 /* fp16 copy of feat or NULL */,
+                            const float* emb /* roi_feat_embedding(feat) [R,128] if the caller already has it, else NULL */,
                             const rn_learn_nms_weights* w, const void* packed,
                             const int32_t* non_gt_index, float* nms_multi_score, float* sorted_bbox, float* sorted_score,
                             float* final_score, void* workspace, size_t workspace_bytes, rn_stream_t stream);

@@ -63,6 +63,9 @@ SIGNATURES = {
     'rn_relation_bwd_workspace_bytes': (c_sz, [C.POINTER(RelationDesc)]),
     'rn_relation_bwd': (C.c_int, [C.POINTER(RelationDesc)] + [c_p] * 21 + [c_p, c_sz, c_p]),
     'rn_relation_packed_fwd_f16io': (C.c_int, [C.POINTER(RelationDesc)] + [c_p] * 9 + [c_p, c_sz, c_i, c_p]),
+    'rn_linear_multi_packed_bytes': (c_sz, [C.POINTER(c_i), c_i, c_i]),
+    'rn_linear_multi_pack': (C.c_int, [C.POINTER(c_p), C.POINTER(c_p), C.POINTER(c_i), c_i, c_i, c_p, c_p]),
+    'rn_linear_multi_packed_f16in_fwd': (C.c_int, [c_p, c_p, C.POINTER(c_p), C.POINTER(c_i), c_i, c_i, c_i, c_p, c_sz, c_p]),
     'rn_pos_embed_fwd': (C.c_int, [c_p, c_p, c_i, c_i, c_i, c_f, c_p, c_p, c_p]),
     'rn_geometry_weight_fwd': (C.c_int, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_p, c_p, c_p, c_p]),
     'rn_linear_workspace_bytes': (c_sz, [c_i, c_i, c_i, c_i]),
@@ -82,7 +85,7 @@ SIGNATURES = {
                          [c_p, c_sz, c_p]),
     'rn_learn_nms_packed_bytes': (c_sz, [C.POINTER(LearnNmsDesc)]),
     'rn_learn_nms_pack': (C.c_int, [C.POINTER(LearnNmsDesc), C.POINTER(LearnNmsWeights), c_p, c_p, c_sz, c_p]),
-    'rn_learn_nms_packed_fwd': (C.c_int, [C.POINTER(LearnNmsDesc)] + [c_p] * 6 + [C.POINTER(LearnNmsWeights), c_p, c_p] + [c_p] * 4 +
+    'rn_learn_nms_packed_fwd': (C.c_int, [C.POINTER(LearnNmsDesc)] + [c_p] * 7 + [C.POINTER(LearnNmsWeights), c_p, c_p] + [c_p] * 4 +
                                 [c_p, c_sz, c_p]),
     'rn_learn_nms_bwd_workspace_bytes': (c_sz, [C.POINTER(LearnNmsDesc)]),
     'rn_learn_nms_bwd': (C.c_int, [C.POINTER(LearnNmsDesc)] + [c_p] * 5 + [C.POINTER(LearnNmsWeights), c_p, c_p, C.POINTER(LearnNmsWeights), c_p, c_p] +

@@ -40,6 +40,12 @@ struct GemmParams {
   float* C32; long long ldc32;        // may be nullptr
   __half* C16; long long ldc16;       // may be nullptr
   float* partial;                     // split-K partials [splits][M][N] (when gridDim.z > 1)
+  // optional output segmentation (several FC layers sharing one input run as ONE GEMM): columns [seg_begin[i],
+  // seg_begin[i] + seg_n[i]) go to the separate contiguous matrix seg_ptr[i] (leading dimension seg_n[i]).  Segment starts
+  // are multiples of 32 (one epilogue chunk never straddles two outputs); columns between segments are padding.
+  int nseg;
+  int seg_begin[4], seg_n[4];
+  float* seg_ptr[4];
 };
 
 // Persistent: CTA b processes work units b, b+grid, ... ; a unit = (K-split z, output tile (m, n)).  The smem ring and
@@ -161,7 +167,14 @@ __global__ void __launch_bounds__(192, 1) gemm_f16_tc_kernel(const __grid_consta
               if (p.relu) f[j] = fmaxf(f[j], 0.f);
             }
             const bool full_chunk = col0 + 32 <= p.N;
-            if (p.C32) {
+            if (p.nseg) {
+              int sg = 0;
+#pragma unroll
+              for (int q = 1; q < 4; ++q) if (q < p.nseg && col0 >= p.seg_begin[q]) sg = q;
+              const int off = col0 - p.seg_begin[sg], nv = p.seg_n[sg] - off;      // valid columns of this chunk
+              float* dst = p.seg_ptr[sg] + (size_t)row * p.seg_n[sg] + off;
+              for (int j = 0; j < 32 && j < nv; ++j) dst[j] = f[j];
+            } else if (p.C32) {
               float* dst = p.C32 + (size_t)row * p.ldc32 + col0;
               if (full_chunk && (p.ldc32 & 3) == 0) {
 #pragma unroll
@@ -257,7 +270,7 @@ static int launch(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tm
 
 int gemm_tc(cudaStream_t st, const __half* A, long long lda, const __half* B, long long ldb, int M, int N, int K,
             const float* bias, int bias_per_row, int relu, float* C32, long long ldc32, __half* C16, long long ldc16,
-            void* ws, size_t ws_bytes) {
+            void* ws, size_t ws_bytes, const GemmSegments* seg) {
   RN_CHECK_ARG(is_sm100(), "tcgen05 GEMM needs an sm_100 device");
   RN_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm_tc: bad sizes %dx%dx%d", M, N, K);
   RN_CHECK_ARG((lda % 8) == 0 && (ldb % 8) == 0 && (((uintptr_t)A | (uintptr_t)B) & 15) == 0,
@@ -278,6 +291,16 @@ int gemm_tc(cudaStream_t st, const __half* A, long long lda, const __half* B, lo
   splits = cdiv(kb, p.k_blocks_per_split);
   p.bias = bias; p.bias_per_row = bias_per_row; p.relu = relu;
   p.C32 = C32; p.ldc32 = ldc32; p.C16 = C16; p.ldc16 = ldc16; p.partial = nullptr;
+  p.nseg = 0;
+  if (seg && seg->n > 0) {
+    RN_CHECK_ARG(seg->n <= 4, "gemm_tc: at most 4 output segments");
+    p.nseg = seg->n;
+    for (int i = 0; i < seg->n; ++i) {
+      RN_CHECK_ARG(seg->begin[i] % 32 == 0 && seg->ptr[i], "gemm_tc: segment %d must start at a multiple of 32 columns", i);
+      p.seg_begin[i] = seg->begin[i]; p.seg_n[i] = seg->cols[i]; p.seg_ptr[i] = seg->ptr[i];
+    }
+    splits = 1; p.k_blocks_per_split = kb;       // the split-K reduce kernel does not know about segments
+  }
   if (splits > 1) {
     const size_t need = ws_slice((size_t)splits * M * N, 4);
     if (!ws || ws_bytes < need) { splits = 1; p.k_blocks_per_split = kb; }     // no room: fall back to a single pass
@@ -372,6 +395,57 @@ int linear_tc_packed_f16in(const void* x16, const void* packed_W, const float* b
   RN_CHECK_ARG(in % 8 == 0, "rn_linear_packed_f16in_fwd: in must be a multiple of 8");
   return gemm_tc(st, (const __half*)x16, in, (const __half*)packed_W, in, rows, out, in, b, 0, relu, y, out, (__half*)y16,
                  out, wsp, ws_bytes);
+}
+
+// ---- several FullyConnected layers over the same input as one GEMM (cls_score + bbox_pred + roi_feat_embedding, SURVEY 8f
+// rank 3).  packed = fp16 [Npad, in] with layer i's rows starting at a multiple of 32 (zero rows between), then the
+// fp32 bias [Npad] laid out the same way.
+static int multi_layout(const int32_t* outs, int nout, int* begin) {
+  int off = 0;
+  for (int i = 0; i < nout; ++i) { begin[i] = off; off += (int)align_up(outs[i], 32); }
+  return off;
+}
+
+size_t linear_multi_packed_bytes(const int32_t* outs, int nout, int in) {
+  int begin[4];
+  if (nout < 1 || nout > 4) return 0;
+  const int npad = multi_layout(outs, nout, begin);
+  return ws_slice((size_t)npad * in, 2) + ws_slice(npad, 4);
+}
+
+__global__ void fill_bias_kernel(const float* __restrict__ b, int n, float* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = b ? b[i] : 0.f;
+}
+
+int linear_multi_pack(const float* const* W, const float* const* b, const int32_t* outs, int nout, int in, void* packed,
+                      cudaStream_t st) {
+  RN_CHECK_ARG(nout >= 1 && nout <= 4 && in % 8 == 0, "rn_linear_multi_pack: 1..4 layers, in %% 8 == 0");
+  int begin[4];
+  const int npad = multi_layout(outs, nout, begin);
+  __half* w16 = (__half*)packed;
+  float* bias = (float*)((char*)packed + ws_slice((size_t)npad * in, 2));
+  RN_CUDA(cudaMemsetAsync(packed, 0, linear_multi_packed_bytes(outs, nout, in), st));
+  for (int i = 0; i < nout; ++i) {
+    RN_CHECK_ARG(W[i] && outs[i] > 0, "rn_linear_multi_pack: layer %d", i);
+    int r = cast_rows_f16(st, W[i], w16 + (size_t)begin[i] * in, outs[i], in, in);
+    if (r) return r;
+    fill_bias_kernel<<<cdiv(outs[i], 128), 128, 0, st>>>(b ? b[i] : nullptr, outs[i], bias + begin[i]);
+    RN_LAUNCH_CHECK();
+  }
+  return RN_OK;
+}
+
+int linear_multi_packed_f16in(const void* x16, const void* packed, float* const* ys, const int32_t* outs, int nout, int rows,
+                              int in, void* wsp, size_t ws_bytes, cudaStream_t st) {
+  RN_CHECK_ARG(nout >= 1 && nout <= 4 && in % 8 == 0, "rn_linear_multi_packed_f16in_fwd: 1..4 layers, in %% 8 == 0");
+  GemmSegments seg;
+  seg.n = nout;
+  const int npad = multi_layout(outs, nout, seg.begin);
+  for (int i = 0; i < nout; ++i) { seg.cols[i] = outs[i]; seg.ptr[i] = ys[i]; }
+  const float* bias = (const float*)((const char*)packed + ws_slice((size_t)npad * in, 2));
+  return gemm_tc(st, (const __half*)x16, in, (const __half*)packed, in, rows, npad, in, bias, 0, 0, nullptr, 0, nullptr, 0, wsp,
+                 ws_bytes, &seg);
 }
 
 int linear_tc(const float* x, const float* W, const float* b, float* y, int rows, int in, int out, int relu, void* wsp,

@@ -308,7 +308,7 @@ static size_t lnms_prepared_layout(const rn_learn_nms_desc* d, size_t* o_rank, s
 
 static int lnms_forward(const rn_learn_nms_desc* d, const float* cls_score, const float* bbox_pred, const float* rois,
                         const float* im_info, const float* feat, const rn_learn_nms_weights* w, const LnmsPrepared* prep,
-                        const void* feat_f16, const int32_t* non_gt_index, float* nms_multi_score, float* sorted_bbox, float* sorted_score,
+                        const void* feat_f16, const float* emb_ext, const int32_t* non_gt_index, float* nms_multi_score, float* sorted_bbox, float* sorted_score,
                         float* final_score, void* wsp, size_t ws_bytes, rn_stream_t stream) {
   RN_CHECK_ARG(d && cls_score && bbox_pred && rois && im_info && feat && w && nms_multi_score && sorted_bbox &&
                    sorted_score && wsp, "rn_learn_nms_fwd: null argument");
@@ -338,9 +338,11 @@ static int lnms_forward(const rn_learn_nms_desc* d, const float* cls_score, cons
   RN_LAUNCH_CHECK();
   // rank feature (depends on weights only: taken from the prepared blob when there is one) and roi feature embedding
   const float* rank_feat = W.rank_feat;
+  const float* emb = emb_ext ? emb_ext : W.emb;      // emb_ext: roi_feat_embedding already evaluated by the caller's merged GEMM
   if (prep) {
     rank_feat = prep->rank_feat;
-    if (feat_f16) {     // the producer's fp16 copy of feat: no cast launch
+    if (emb_ext) {
+    } else if (feat_f16) {     // the producer's fp16 copy of feat: no cast launch
       if ((r = linear_tc_packed_f16in(feat_f16, prep->w_emb16, w->roi_feat_embedding_bias, W.emb, nullptr, d->R, d->feat_dim,
                                       kNmsFeat, 0, W.rel_ws, W.rel_ws_bytes, st))) return r;
     } else if ((r = linear_tc_packed(feat, prep->w_emb16, w->roi_feat_embedding_bias, W.emb, d->R, d->feat_dim, kNmsFeat, 0,
@@ -353,7 +355,7 @@ static int lnms_forward(const rn_learn_nms_desc* d, const float* cls_score, cons
     if ((r = rn_linear_fwd(feat, w->roi_feat_embedding_weight, w->roi_feat_embedding_bias, W.emb, d->R, d->feat_dim,
                            kNmsFeat, 0, d->precision, W.rel_ws, W.rel_ws_bytes, stream))) return r;
   }
-  lnms_gather_kernel<<<dim3(n, C), 128, 0, st>>>(n, C, K, d->class_agnostic, W.rank_idx, W.refined, W.emb, rank_feat,
+  lnms_gather_kernel<<<dim3(n, C), 128, 0, st>>>(n, C, K, d->class_agnostic, W.rank_idx, W.refined, emb, rank_feat,
                                                  sorted_bbox, W.feat_cls, W.boxes_cls);
   RN_LAUNCH_CHECK();
   rn_relation_desc rd = lnms_inner_desc(d);
@@ -364,7 +366,7 @@ static int lnms_forward(const rn_learn_nms_desc* d, const float* cls_score, cons
     if ((r = launch_geom_weight_log2_T(st, W.refined, Rn, 16, 64, 1000.f, w->nms_pair_pos_fc1_1_weight,
                                        w->nms_pair_pos_fc1_1_bias, W.lg_roi, ldr))) return r;
     GeomGather gg = {W.lg_roi, ldr, Rn, W.rank_idx, C, 1, nullptr};
-    if ((r = relation_tc_lnms(&rd, W.feat_cls, W.emb, d->R, rank_feat, &gg, w->nms_query_1_weight, w->nms_query_1_bias,
+    if ((r = relation_tc_lnms(&rd, W.feat_cls, emb, d->R, rank_feat, &gg, w->nms_query_1_weight, w->nms_query_1_bias,
                               w->nms_key_1_weight, w->nms_key_1_bias, w->nms_linear_out_1_weight,
                               w->nms_linear_out_1_bias, W.feat_out, W.rel_ws, W.rel_ws_bytes, st,
                               prep ? prep->rel : nullptr))) return r;
@@ -386,7 +388,7 @@ extern "C" int rn_learn_nms_fwd(const rn_learn_nms_desc* d, const float* cls_sco
                                 const rn_learn_nms_weights* w, const int32_t* non_gt_index, float* nms_multi_score,
                                 float* sorted_bbox, float* sorted_score, float* final_score, void* wsp, size_t ws_bytes,
                                 rn_stream_t stream) {
-  return rn::lnms_forward(d, cls_score, bbox_pred, rois, im_info, feat, w, nullptr, nullptr, non_gt_index, nms_multi_score,
+  return rn::lnms_forward(d, cls_score, bbox_pred, rois, im_info, feat, w, nullptr, nullptr, nullptr, non_gt_index, nms_multi_score,
                           sorted_bbox, sorted_score, final_score, wsp, ws_bytes, stream);
 }
 
@@ -427,7 +429,7 @@ extern "C" int rn_learn_nms_pack(const rn_learn_nms_desc* d, const rn_learn_nms_
 
 extern "C" int rn_learn_nms_packed_fwd(const rn_learn_nms_desc* d, const float* cls_score, const float* bbox_pred,
                                        const float* rois, const float* im_info, const float* feat, const void* feat_f16,
-                                       const rn_learn_nms_weights* w, const void* packed, const int32_t* non_gt_index,
+                                       const float* emb, const rn_learn_nms_weights* w, const void* packed, const int32_t* non_gt_index,
                                        float* nms_multi_score, float* sorted_bbox, float* sorted_score, float* final_score,
                                        void* wsp, size_t ws_bytes, rn_stream_t stream) {
   using namespace rn;
@@ -437,7 +439,7 @@ extern "C" int rn_learn_nms_packed_fwd(const rn_learn_nms_desc* d, const float* 
   lnms_prepared_layout(d, &o_rank, &o_emb, &o_rel);
   const char* base = (const char*)packed;
   LnmsPrepared prep = {(const float*)(base + o_rank), base + o_emb, base + o_rel};
-  return lnms_forward(d, cls_score, bbox_pred, rois, im_info, feat, w, &prep, feat_f16, non_gt_index, nms_multi_score, sorted_bbox,
+  return lnms_forward(d, cls_score, bbox_pred, rois, im_info, feat, w, &prep, feat_f16, emb, non_gt_index, nms_multi_score, sorted_bbox,
                       sorted_score, final_score, wsp, ws_bytes, stream);
 }
 

@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "geom.cuh"
 #include "relation.cuh"
+#include "gemm_tc.cuh"
 
 namespace rn {
 
@@ -287,4 +288,22 @@ extern "C" int rn_linear_packed_f16in_fwd(const void* x_f16, const void* packed_
                                           rn_stream_t stream) {
   RN_CHECK_ARG(x_f16 && packed_W && (y || y_f16) && rows > 0 && in > 0 && out > 0, "rn_linear_packed_f16in_fwd: bad arguments");
   return rn::linear_tc_packed_f16in(x_f16, packed_W, b, y, y_f16, rows, in, out, relu, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+// ---- several FullyConnected layers over the same fp16 input as one tcgen05 GEMM
+extern "C" size_t rn_linear_multi_packed_bytes(const int32_t* outs, int32_t nout, int32_t in) {
+  return outs ? rn::linear_multi_packed_bytes(outs, nout, in) : 0;
+}
+
+extern "C" int rn_linear_multi_pack(const float* const* W, const float* const* b, const int32_t* outs, int32_t nout,
+                                    int32_t in, void* packed, rn_stream_t stream) {
+  RN_CHECK_ARG(W && outs && packed, "rn_linear_multi_pack: null argument");
+  return rn::linear_multi_pack(W, b, outs, nout, in, packed, (cudaStream_t)stream);
+}
+
+extern "C" int rn_linear_multi_packed_f16in_fwd(const void* x_f16, const void* packed, float* const* ys, const int32_t* outs,
+                                                int32_t nout, int32_t rows, int32_t in, void* ws, size_t ws_bytes,
+                                                rn_stream_t stream) {
+  RN_CHECK_ARG(x_f16 && packed && ys && outs && rows > 0 && in > 0, "rn_linear_multi_packed_f16in_fwd: bad arguments");
+  return rn::linear_multi_packed_f16in(x_f16, packed, ys, outs, nout, rows, in, ws, ws_bytes, (cudaStream_t)stream);
 }

@@ -4,6 +4,7 @@ PyTorch is used for device memory, streams and (elsewhere) torch.distributed onl
 fallback: non-CUDA tensors raise.
 """
 import ctypes as C
+c_i32 = C.c_int32
 import torch
 from . import _lib as L
 
@@ -261,6 +262,34 @@ def linear(x, W, b=None, relu=False, precision=None, x_f16=None, want_f16=False)
     return y
 
 
+def linear_multi(x_f16, layers):
+    """Several FullyConnected layers over the same fp16 input as ONE tcgen05 GEMM (rn_linear_multi_packed_f16in_fwd).
+    layers: list of (W [out_i, in], b [out_i] or None), at most 4.  Returns the list of contiguous fp32 [rows, out_i] outputs."""
+    if not (x_f16.is_cuda and x_f16.dtype == torch.float16 and x_f16.is_contiguous() and x_f16.dim() == 2):
+        raise L.RelnetError('linear_multi: x_f16 must be a contiguous 2-D fp16 CUDA tensor')
+    rows, cin = x_f16.shape
+    n = len(layers)
+    Ws = [_f32(W, 'W') for W, _ in layers]
+    bs = [(_f32(b, 'b') if b is not None else None) for _, b in layers]
+    if not (1 <= n <= 4 and cin % 8 == 0 and all(W.dim() == 2 and W.shape[1] == cin for W in Ws)):
+        raise L.RelnetError('linear_multi: 1..4 layers of [out_i, %d] weights (in %% 8 == 0)' % cin)
+    outs = (c_i32 * n)(*[W.shape[0] for W in Ws])
+    lib = L.lib()
+
+    def pack(buf):
+        wp = (C.c_void_p * n)(*[W.data_ptr() for W in Ws])
+        bp = (C.c_void_p * n)(*[(b.data_ptr() if b is not None else None) for b in bs])
+        L.check(lib.rn_linear_multi_pack(wp, bp, outs, n, cin, _ptr(buf), _stream()), 'rn_linear_multi_pack')
+    keys = tuple(Ws) + tuple(b for b in bs if b is not None)
+    packed = _packs.get(keys, lib.rn_linear_multi_packed_bytes(outs, n, cin), pack, tag=('multi', n))
+    ys = [torch.empty((rows, W.shape[0]), dtype=torch.float32, device=x_f16.device) for W in Ws]
+    yp = (C.c_void_p * n)(*[y.data_ptr() for y in ys])
+    ws = _workspace(256, x_f16.device)
+    L.check(lib.rn_linear_multi_packed_f16in_fwd(_ptr(x_f16), _ptr(packed), yp, outs, n, rows, cin, _ptr(ws), ws.numel(),
+                                                 _stream()), 'rn_linear_multi_packed_f16in_fwd')
+    return ys
+
+
 # ------------------------------------------------------------------------------------------------------------------
 def _learn_nms_desc(cls_score, bbox_pred, rois, feat, first_n, num_thresh, class_thresh, class_agnostic, means, stds,
                     nongt_dim, non_gt_index, merge_method, precision):
@@ -283,13 +312,14 @@ def _learn_nms_desc(cls_score, bbox_pred, rois, feat, first_n, num_thresh, class
 
 def learn_nms(cls_score, bbox_pred, rois, im_info, feat, weights, first_n=100, num_thresh=5, class_thresh=0.01,
               class_agnostic=True, means=None, stds=None, nongt_dim=None, non_gt_index=None, merge_method=-1,
-              precision=None, feat_f16=None):
+              precision=None, feat_f16=None, emb=None):
     """learn_nms CustomOp forward (LNMS:238-401) + merge.  ``weights``: dict by checkpoint name (LNMS:429-441).
-    feat_f16 (RN_PREC_F16 only): the producer's fp16 copy of feat, saves the cast launch."""
+    feat_f16 (RN_PREC_F16 only): the producer's fp16 copy of feat, saves the cast launch; emb (RN_PREC_F16 only):
+    roi_feat_embedding(feat) [R,128] when the caller already evaluated it (e.g. merged with cls_score / bbox_pred)."""
     precision = precision or default_precision()
     cls_score = _f32(cls_score, 'cls_score'); bbox_pred = _f32(bbox_pred, 'bbox_pred'); rois = _f32(rois, 'rois')
     im_info = _f32(im_info, 'im_info').reshape(-1); feat = _f32(feat, 'feat')
-    NC = cls_score.shape[1]
+    R_, NC = cls_score.shape
     desc, kidx = _learn_nms_desc(cls_score, bbox_pred, rois, feat, first_n, num_thresh, class_thresh, class_agnostic, means,
                                  stds, nongt_dim, non_gt_index, merge_method, precision)
     keep = [_f32(weights[n], n) for n in L.LearnNmsWeights.NAMES]
@@ -311,8 +341,12 @@ def learn_nms(cls_score, bbox_pred, rois, im_info, feat, weights, first_n=100, n
         if feat_f16 is not None and not (feat_f16.is_cuda and feat_f16.dtype == torch.float16 and feat_f16.is_contiguous()
                                          and feat_f16.numel() == feat.numel() and feat.shape[1] % 8 == 0):
             raise L.RelnetError('learn_nms: feat_f16 must be the contiguous fp16 CUDA copy of feat (feat_dim % 8 == 0)')
+        if emb is not None:
+            emb = _f32(emb, 'emb')
+            if tuple(emb.shape) != (R_, 128):
+                raise L.RelnetError('learn_nms: emb must be [R, 128]')
         L.check(lib.rn_learn_nms_packed_fwd(C.byref(desc), _ptr(cls_score), _ptr(bbox_pred), _ptr(rois), _ptr(im_info),
-                                            _ptr(feat), _ptr(feat_f16), C.byref(w), _ptr(packed), _ptr(kidx), _ptr(multi), _ptr(sbbox),
+                                            _ptr(feat), _ptr(feat_f16), _ptr(emb), C.byref(w), _ptr(packed), _ptr(kidx), _ptr(multi), _ptr(sbbox),
                                             _ptr(sscore), _ptr(final), _ptr(ws), ws.numel(), _stream()),
                 'rn_learn_nms_packed_fwd')
         return multi, sbbox, sscore, final

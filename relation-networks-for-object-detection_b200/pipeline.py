@@ -133,12 +133,14 @@ class RelationHead(object):
             fc2, fc2_h = ops.linear(fc_all_1, P['fc_new_2_weight'], P['fc_new_2_bias'], precision=prec, x_f16=a1_h,
                                     want_f16=True)                                                                # :353
             fc_all_2, a2_h = self.relation(fc2, boxes, 2, self.nongt_dim, rel_mask, x_f16=fc2_h, want_f16=True)   # :354-359
-            cls_score = ops.linear(fc_all_2, P['cls_score_weight'], P['cls_score_bias'], precision=prec, x_f16=a2_h)
-            bbox_pred = ops.linear(fc_all_2, P['bbox_pred_weight'], P['bbox_pred_bias'], precision=prec, x_f16=a2_h)
+            # cls_score, bbox_pred (:360-365) and roi_feat_embedding (LNMS:339) all read fc_all_2_relu: one GEMM
+            cls_score, bbox_pred, emb = ops.linear_multi(a2_h, [
+                (P['cls_score_weight'], P['cls_score_bias']), (P['bbox_pred_weight'], P['bbox_pred_bias']),
+                (P['roi_feat_embedding_weight'], P['roi_feat_embedding_bias'])])
             multi, sorted_bbox, sorted_score, final = ops.learn_nms(                              # :518-560
                 cls_score, bbox_pred, rois, im_info, fc_all_2, {k: P[k] for k in NMS_NAMES}, first_n=self.first_n,
                 class_thresh=self.class_thresh, nongt_dim=self.nongt_dim, merge_method=self.merge_method, precision=prec,
-                feat_f16=a2_h)
+                feat_f16=a2_h, emb=emb)
             return dict(rois=rois, cls_score=cls_score, bbox_pred=bbox_pred, fc_all_2_relu=fc_all_2,
                         nms_multi_score=multi, learn_nms_sorted_bbox=sorted_bbox, sorted_score=sorted_score,
                         nms_final_score_output=final)
@@ -167,7 +169,9 @@ class Detector(object):
 
     def __init__(self, trunk, head, im_info):
         self.trunk, self.head, self.im_info = trunk, head, im_info
-        self.side = torch.cuda.Stream()
+        # the side branch is a chain of small latency-bound kernels: high priority so its CTAs are placed as soon as res5's
+        # big grids retire blocks, instead of queueing behind them
+        self.side = torch.cuda.Stream(priority=-1)
 
     def __call__(self, image32):
         main = torch.cuda.current_stream()
@@ -177,12 +181,14 @@ class Detector(object):
         with torch.cuda.stream(self.side):
             prob, bbox = self.trunk.rpn(c4)
             rois = self.head.propose(prob, bbox, self.im_info)
-            done = self.head.geometry_early(rois)          # both modules' geometry terms, still beside res5
+            rois_ready = torch.cuda.Event()
+            rois_ready.record(self.side)
+            done = self.head.geometry_early(rois)          # both modules' geometry terms: beside res5 / ROI pool / fc_new_1
         c4.record_stream(self.side)
         feat = self.trunk.c5feat(c4)
-        main.wait_stream(self.side)
+        main.wait_event(rois_ready)                        # ROI pool + fc_new_1 only need the rois ...
         rois.record_stream(main)
-        return self.head.detect(rois, feat, self.im_info, geometry_done=done)
+        return self.head.detect(rois, feat, self.im_info, geometry_done=done, join=self.side)   # ... relation #1 the geometry
 
 
 class GraphedStep(object):

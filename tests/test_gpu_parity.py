@@ -373,3 +373,24 @@ def test_f16_side_channels_are_bitwise_the_same_path(ops):
     assert torch.equal(y, y2) and torch.equal(y2_h, y.half())
     with pytest.raises(Exception):
         ops.relation(*t, group=16, residual_relu=True, precision='f16', x_f16=t[0].half()[:100])
+
+
+def test_linear_multi_equals_separate_layers(ops):
+    """cls_score + bbox_pred + roi_feat_embedding as ONE GEMM == three rn_linear_packed calls"""
+    if not ops.device_info()['sm100']:
+        pytest.skip('tcgen05 path only')
+    rng = np.random.RandomState(5)
+    x = T(rng.randn(300, 1024).astype(np.float32))
+    layers = [(T((rng.randn(o, 1024) * 0.03).astype(np.float32)), T(rng.randn(o).astype(np.float32))) for o in (81, 8, 128)]
+    x16 = x.half()
+    ys = ops.linear_multi(x16, layers)
+    for (W, b), y in zip(layers, ys):
+        ref = ops.linear(x, W, b, precision='f16')
+        assert y.shape == ref.shape and y.is_contiguous()
+        assert torch.equal(y, ref)
+        want = x16.float().double() @ W.half().float().double().T + b.double()
+        assert rel_err(y.cpu().numpy(), want.cpu().numpy()) <= 1e-5          # fp16 operands, fp32 accumulate
+    ys1 = ops.linear_multi(x16, layers[:1])
+    assert torch.equal(ys1[0], ys[0])
+    with pytest.raises(Exception):
+        ops.linear_multi(x16, layers + layers)                               # more than 4 layers
