@@ -318,9 +318,9 @@ def main():
         torch.cuda.current_stream().synchronize()          # the caller holds the detections on the host
         return o
 
-    trunk_out = trunk(image_d)
+    trunk_out = trunk(image32_d)
     hot_graph = GraphedStep(lambda a, b, c: head.forward(a, b, c, im_info), list(trunk_out))
-    trunk_graph = GraphedStep(lambda im: trunk(im), [image_d])
+    trunk_graph = GraphedStep(lambda im: trunk(im), [image32_d])
 
     def step_hot():
         return hot_graph(*trunk_out)
@@ -333,7 +333,7 @@ def main():
         sampler.stop_flag = True
     ms_e2e = timed(step_e2e, args.steps, max(3, args.warmup // 2), dist_on)
     ms_hot = timed(step_hot, args.steps, 3, dist_on)
-    ms_trunk = timed(lambda: trunk_graph(image_d), args.steps, 3, dist_on)
+    ms_trunk = timed(lambda: trunk_graph(image32_d), args.steps, 3, dist_on)
 
     if rank == 0:
         pk = peaks()

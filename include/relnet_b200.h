@@ -346,6 +346,16 @@ int rn_deform_im2col(const rn_deform_conv_desc* desc, const float* data_b, const
                      rn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Stem helpers around the (library) trunk: both are plain HBM-bound data movement.
+ * rn_image_s2d_bf16: fp32 [3,H,W] image -> bf16 channels-last [(H+2pad)/2, (W+2pad)/2, 16]: space-to-depth(2) of the zero-
+ *   padded image, channel = c*4 + (row parity)*2 + (col parity), channels 12..15 zero.  With pad = 3 the 7x7 stride-2 conv1
+ *   (relation_rcnn/symbols/resnet_v1_101_rcnn_base.py conv1) is a 4x4 stride-1 convolution over this tensor.
+ * rn_maxpool3x3s2_nhwc_bf16: pool1 (3x3, stride 2, pooling_convention='full' = ceil mode) on a channels-last bf16 map;
+ *   out is [ceil((H-3)/2)+1, ceil((W-3)/2)+1, C], C % 8 == 0. */
+int rn_image_s2d_bf16(const float* image_chw, int32_t H, int32_t W, int32_t pad, void* out_nhwc16_bf16, rn_stream_t stream);
+int rn_maxpool3x3s2_nhwc_bf16(const void* in_nhwc, int32_t H, int32_t W, int32_t C, void* out_nhwc, rn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * tcgen05 self-test (sm_100a only): runs one 128x128x64 K-major and one 128x64x128 MN-major-B UMMA through TMA/TMEM and
  * writes the fp32 results to out_s [128,128], out_o [128,64] for checking against a host product. */
 int rn_umma_selftest(const void* a_f16, const void* b_f16, const void* p_f16, const void* v_f16, float* out_s,

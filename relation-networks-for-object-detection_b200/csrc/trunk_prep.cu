@@ -1,0 +1,85 @@
+// trunk_prep.cu -- the two memory-bound steps either side of the (library, cuDNN) stem convolution, hand-written because
+// the stock kernels were 10x off the HBM roofline in the step timeline (tools/timeline.py: 7x7/2 conv on a 3-channel input
+// 149 us incl. cuDNN's channel padding, ATen max-pool 47 us):
+//   rn_image_s2d_bf16      fp32 [3,H,W] image -> bf16 channels-last [Hs, Ws, 16] space-to-depth(2) of the 3-pixel zero-
+//                          padded image: the 7x7 stride-2 stem conv (resnet_v1_101_rcnn_base.py: conv1) becomes a 4x4
+//                          stride-1 conv over 12 (+4 zero) channels -- same arithmetic, tensor-core friendly K = 256
+//   rn_maxpool3x3s2_nhwc_bf16   3x3 / stride 2 / ceil-mode max pool (pool1, same file) on a channels-last bf16 map
+// HBM roofline: bytes in + bytes out (7.2 MB + 4.9 MB; 19.2 MB + 4.8 MB); one thread handles 16 B of output channels.
+#include "common.cuh"
+#include <cuda_bf16.h>
+
+namespace rn {
+
+// y[I][J][c*4 + r*2 + s] = xpad[c][2I + r][2J + s], xpad = image zero-padded by `pad` on every side; channels 12..15 = 0
+__global__ void __launch_bounds__(256) image_s2d_bf16_kernel(const float* __restrict__ img, int H, int W, int pad, int Hs,
+                                                             int Ws, __nv_bfloat16* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= Hs * Ws) return;
+  const int I = t / Ws, J = t - I * Ws;
+  __align__(16) __nv_bfloat16 v[16];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int y = 2 * I + r - pad, x = 2 * J + s - pad;
+        const float f = (y >= 0 && y < H && x >= 0 && x < W) ? __ldg(img + ((size_t)c * H + y) * W + x) : 0.f;
+        v[c * 4 + r * 2 + s] = __float2bfloat16_rn(f);
+      }
+#pragma unroll
+  for (int k = 12; k < 16; ++k) v[k] = __float2bfloat16_rn(0.f);
+  uint4* dst = reinterpret_cast<uint4*>(out + (size_t)t * 16);
+  dst[0] = reinterpret_cast<const uint4*>(v)[0];
+  dst[1] = reinterpret_cast<const uint4*>(v)[1];
+}
+
+// one thread = one output pixel x 8 channels (16 B); window clipped at the bottom/right edge (ceil mode, no padding)
+__global__ void __launch_bounds__(256) maxpool3x3s2_nhwc_bf16_kernel(const __nv_bfloat16* __restrict__ in, int H, int W, int C8,
+                                                                     int Ho, int Wo, __nv_bfloat16* __restrict__ out) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)Ho * Wo * C8;
+  if (t >= total) return;
+  const int c8 = (int)(t % C8);
+  const int ow = (int)((t / C8) % Wo), oh = (int)(t / ((size_t)C8 * Wo));
+  const int h0 = oh * 2, w0 = ow * 2;
+  const int h1 = min(h0 + 3, H), w1 = min(w0 + 3, W);
+  __nv_bfloat162 m[4];
+  bool first = true;
+  for (int h = h0; h < h1; ++h)
+    for (int w = w0; w < w1; ++w) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(in + ((size_t)h * W + w) * C8 * 8) + c8);
+      const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&u);
+      if (first) { m[0] = p[0]; m[1] = p[1]; m[2] = p[2]; m[3] = p[3]; first = false; }
+      else { m[0] = __hmax2(m[0], p[0]); m[1] = __hmax2(m[1], p[1]); m[2] = __hmax2(m[2], p[2]); m[3] = __hmax2(m[3], p[3]); }
+    }
+  uint4 o;
+  o.x = *reinterpret_cast<uint32_t*>(&m[0]); o.y = *reinterpret_cast<uint32_t*>(&m[1]);
+  o.z = *reinterpret_cast<uint32_t*>(&m[2]); o.w = *reinterpret_cast<uint32_t*>(&m[3]);
+  reinterpret_cast<uint4*>(out + ((size_t)oh * Wo + ow) * C8 * 8)[c8] = o;
+}
+
+}  // namespace rn
+
+extern "C" int rn_image_s2d_bf16(const float* image_chw, int32_t H, int32_t W, int32_t pad, void* out_nhwc16_bf16,
+                                 rn_stream_t stream) {
+  RN_CHECK_ARG(image_chw && out_nhwc16_bf16 && H > 0 && W > 0 && pad >= 0, "rn_image_s2d_bf16: bad arguments");
+  RN_CHECK_ARG(((H + 2 * pad) % 2) == 0 && ((W + 2 * pad) % 2) == 0, "rn_image_s2d_bf16: padded size must be even (%d x %d, pad %d)", H, W, pad);
+  const int Hs = (H + 2 * pad) / 2, Ws = (W + 2 * pad) / 2;
+  rn::image_s2d_bf16_kernel<<<rn::cdiv(Hs * Ws, 256), 256, 0, (cudaStream_t)stream>>>(image_chw, H, W, pad, Hs, Ws,
+                                                                                     (__nv_bfloat16*)out_nhwc16_bf16);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
+
+extern "C" int rn_maxpool3x3s2_nhwc_bf16(const void* in_nhwc, int32_t H, int32_t W, int32_t C, void* out_nhwc,
+                                         rn_stream_t stream) {
+  RN_CHECK_ARG(in_nhwc && out_nhwc && H >= 3 && W >= 3 && C > 0 && (C % 8) == 0, "rn_maxpool3x3s2_nhwc_bf16: bad arguments (C %% 8)");
+  const int Ho = (H - 3 + 1) / 2 + 1, Wo = (W - 3 + 1) / 2 + 1;      // ceil((H - 3) / 2) + 1
+  const size_t total = (size_t)Ho * Wo * (C / 8);
+  rn::maxpool3x3s2_nhwc_bf16_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)in_nhwc, H, W, C / 8, Ho, Wo, (__nv_bfloat16*)out_nhwc);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}

@@ -633,6 +633,31 @@ def deform_im2col(im, offset, kernel=(3, 3), pad=(2, 2), stride=(1, 1), dilate=(
     return col
 
 
+def image_s2d(image, pad=3):
+    """fp32 [1,3,H,W] (or [3,H,W]) image -> bf16 NCHW-shaped, channels-last-strided [1,16,(H+2pad)/2,(W+2pad)/2]: the
+    space-to-depth(2) form of the zero-padded image that turns the 7x7/2 stem conv into a 4x4/1 conv (rn_image_s2d_bf16)."""
+    image = _f32(image, 'image')
+    H, W = image.shape[-2], image.shape[-1]
+    if image.numel() != 3 * H * W or (H + 2 * pad) % 2 or (W + 2 * pad) % 2:
+        raise L.RelnetError('image_s2d: need one 3-channel image with even padded size, got %s' % (tuple(image.shape),))
+    Hs, Ws = (H + 2 * pad) // 2, (W + 2 * pad) // 2
+    out = torch.empty((1, Hs, Ws, 16), dtype=torch.bfloat16, device=image.device)
+    L.check(L.lib().rn_image_s2d_bf16(_ptr(image), H, W, pad, _ptr(out), _stream()), 'rn_image_s2d_bf16')
+    return out.permute(0, 3, 1, 2)
+
+
+def maxpool3x3s2_nhwc(x):
+    """3x3 / stride 2 / ceil-mode max pool of a channels-last bf16 [1,C,H,W] map (rn_maxpool3x3s2_nhwc_bf16)."""
+    if not (x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and x.shape[0] == 1
+            and x.is_contiguous(memory_format=torch.channels_last) and x.shape[1] % 8 == 0):
+        raise L.RelnetError('maxpool3x3s2_nhwc: need a channels-last bf16 CUDA tensor [1,C,H,W] with C % 8 == 0')
+    _, Cc, H, W = x.shape
+    Ho, Wo = (H - 2) // 2 + 1, (W - 2) // 2 + 1
+    out = torch.empty((1, Ho, Wo, Cc), dtype=torch.bfloat16, device=x.device)
+    L.check(L.lib().rn_maxpool3x3s2_nhwc_bf16(_ptr(x), H, W, Cc, _ptr(out), _stream()), 'rn_maxpool3x3s2_nhwc_bf16')
+    return out.permute(0, 3, 1, 2)
+
+
 def umma_selftest(a, b, p, v):
     """tcgen05/TMA self-test: a,b [128,64], p [128,128], v [128,64] fp16 -> (a b^T [128,128], p v [128,64]) fp32."""
     for t in (a, b, p, v):

@@ -175,8 +175,7 @@ class Detector(object):
 
     def __call__(self, image32):
         main = torch.cuda.current_stream()
-        img = image32.to(next(self.trunk.parameters()).dtype).contiguous(memory_format=torch.channels_last)
-        c4 = self.trunk.c4(img)
+        c4 = self.trunk.c4(image32)           # fp32 image in: the stem converts (space-to-depth bf16) in its own kernel
         self.side.wait_stream(main)
         with torch.cuda.stream(self.side):
             prob, bbox = self.trunk.rpn(c4)

@@ -86,10 +86,43 @@ class Trunk(nn.Module):
         self.conv_new_1.weight.data.div_(F.relu(self.conv_new_1(c5)).float().std().clamp_min(1e-6))
 
     @torch.no_grad()
+    def prepare(self):
+        """Inference-time rewrites (identical arithmetic): the projection shortcut's bias moves into c3's bias so the
+        shortcut is a bias-free conv (one launch), and conv1's 7x7/2 weight is re-indexed into the 4x4/1 weight over the
+        space-to-depth input that ops.image_s2d produces."""
+        for m in self.modules():
+            if isinstance(m, Bottleneck) and m.proj is not None and m.proj.bias is not None:
+                m.c3.bias.data += m.proj.bias.data
+                m.proj.bias = None
+        w = self.conv1.weight.data.float()                               # [64,3,7,7]
+        w8 = torch.zeros((w.shape[0], 3, 8, 8), dtype=torch.float32, device=w.device)
+        w8[:, :, :7, :7] = w
+        w12 = w8.view(-1, 3, 4, 2, 4, 2).permute(0, 1, 3, 5, 2, 4).reshape(-1, 12, 4, 4)   # [o, c*4 + r*2 + s, a, b]
+        w16 = torch.zeros((w.shape[0], 16, 4, 4), dtype=torch.float32, device=w.device)
+        w16[:, :12] = w12
+        self.conv1_s2d_weight = w16.to(self.conv1.weight.dtype).contiguous(memory_format=torch.channels_last)
+        return self
+
+    @torch.no_grad()
+    def stem(self, image):
+        """conv1 + relu + pool1.  fp32 CUDA image + FUSED: hand-written space-to-depth / max-pool kernels around one cuDNN
+        conv (ops.image_s2d, ops.maxpool3x3s2_nhwc); otherwise the plain module path."""
+        if FUSED and image.is_cuda and image.dtype == torch.float32 and getattr(self, 'conv1_s2d_weight', None) is not None \
+                and image.shape[0] == 1 and image.shape[2] % 2 == 0 and image.shape[3] % 2 == 0:
+            from . import ops
+            y = ops.image_s2d(image, pad=3)
+            x = torch.cudnn_convolution_relu(y, self.conv1_s2d_weight, self.conv1.bias, (1, 1), (0, 0), (1, 1), 1)
+            return ops.maxpool3x3s2_nhwc(x)
+        if image.dtype != self.conv1.weight.dtype:
+            image = image.to(self.conv1.weight.dtype)
+            if image.is_cuda:
+                image = image.contiguous(memory_format=torch.channels_last)
+        return F.max_pool2d(_conv_relu(self.conv1, image), 3, 2, ceil_mode=True)
+
+    @torch.no_grad()
     def c4(self, image):
         """conv1 .. res4: the stride-16 feature both the RPN and res5 read"""
-        x = F.max_pool2d(_conv_relu(self.conv1, image), 3, 2, ceil_mode=True)
-        return self.res4(self.res3(self.res2(x)))
+        return self.res4(self.res3(self.res2(self.stem(image))))
 
     @torch.no_grad()
     def rpn(self, c4):
@@ -122,4 +155,5 @@ def make_trunk(device, dtype=torch.bfloat16, seed=0):
     t = t.to(dtype=dtype)
     if device != 'cpu' and str(device) != 'cpu':
         t = t.to(memory_format=torch.channels_last)
+        t.prepare()
     return t

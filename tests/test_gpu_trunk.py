@@ -1,0 +1,65 @@
+"""GPU: the hand-written stem helpers around the (library) trunk -- space-to-depth image conversion and the channels-last
+bf16 max pool -- against plain torch, plus the re-indexed 4x4/1 stem weight against the original 7x7/2 convolution."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ops(cuda_device):
+    import __graft_entry__ as g
+    g.build()
+    import relnet_b200
+    torch.cuda.set_device(cuda_device)
+    return relnet_b200.ops
+
+
+def test_image_s2d_layout_and_stem_equivalence(ops):
+    torch.manual_seed(0)
+    img = torch.randn(1, 3, 60, 100, device='cuda') * 50
+    y = ops.image_s2d(img, pad=3)
+    assert y.shape == (1, 16, 33, 53) and y.dtype == torch.bfloat16 and y.is_contiguous(memory_format=torch.channels_last)
+    xp = F.pad(img.to(torch.bfloat16), (3, 3, 3, 3))
+    want = torch.zeros_like(y)
+    for c in range(3):
+        for r in range(2):
+            for s in range(2):
+                want[0, c * 4 + r * 2 + s] = xp[0, c, r::2, s::2]
+    assert torch.equal(y, want)                                   # pure data movement: bit-exact
+    # 7x7 / stride 2 / pad 3 convolution == 4x4 / stride 1 convolution over the space-to-depth tensor
+    from relnet_b200.trunk import Trunk
+    t = Trunk().cuda().eval()
+    t.prepare()
+    ref = F.conv2d(img.to(torch.bfloat16).float(), t.conv1.weight.float(), None, stride=2, padding=3)
+    got = F.conv2d(y.float(), t.conv1_s2d_weight.float(), None)
+    assert got.shape == ref.shape
+    assert (got - ref).abs().max().item() <= 1e-3 * ref.abs().max().item()      # same products, different sum order
+
+
+@pytest.mark.parametrize('H,W', [(300, 500), (31, 17)])
+def test_maxpool_nhwc_matches_torch_ceil_mode(ops, H, W):
+    torch.manual_seed(1)
+    x = torch.randn(1, 64, H, W, device='cuda').to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    got = ops.maxpool3x3s2_nhwc(x)
+    want = F.max_pool2d(x, 3, 2, ceil_mode=True)
+    assert got.shape == want.shape and torch.equal(got, want)
+    with pytest.raises(Exception):
+        ops.maxpool3x3s2_nhwc(x.float())
+
+
+def test_trunk_fast_stem_equals_plain_path(ops):
+    from relnet_b200 import trunk as TR
+    t = TR.make_trunk('cuda')
+    img = torch.randn(1, 3, 224, 320, device='cuda') * 50
+    fast = t.stem(img)
+    old = TR.FUSED
+    try:
+        TR.FUSED = False
+        plain = t.stem(img)
+    finally:
+        TR.FUSED = old
+    assert fast.shape == plain.shape
+    assert (fast.float() - plain.float()).abs().max().item() <= 2e-2 * plain.float().abs().max().item()    # bf16 conv, different algo

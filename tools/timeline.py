@@ -30,13 +30,10 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     torch.cuda.synchronize()
 ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and e.time_range.end > e.time_range.start]
 ev.sort(key=lambda e: e.time_range.start)
-# split into replays by the biggest gaps
-starts = [e.time_range.start for e in ev]
-gaps = sorted(range(1, len(ev)), key=lambda i: starts[i] - ev[i - 1].time_range.end, reverse=True)[:2]
-cut = sorted(gaps)
-last = ev[cut[1]:]
+# three identical replays were profiled: the last third of the kernel events is one replay
+last = ev[len(ev) - len(ev) // 3:]
 t0 = last[0].time_range.start
-rows = [dict(name=e.name[:60], stream=getattr(e, 'device_index', 0), start_us=round(e.time_range.start - t0, 1),
+rows = [dict(name=e.name[:60], stream=int(getattr(e, 'device_resource_id', -1) if hasattr(e, 'device_resource_id') else -1), start_us=round(e.time_range.start - t0, 1),
              dur_us=round(e.time_range.end - e.time_range.start, 1)) for e in last]
 os.makedirs('gpurun_out', exist_ok=True)
 json.dump(rows, open('gpurun_out/timeline.json', 'w'))

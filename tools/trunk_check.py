@@ -13,7 +13,7 @@ from relnet_b200 import trunk as TR
 dev = torch.device('cuda:0')
 torch.backends.cudnn.benchmark = True
 t = TR.make_trunk(dev)
-img = (torch.randn(1, 3, 600, 1000, device=dev) * 50).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+img = torch.randn(1, 3, 600, 1000, device=dev) * 50          # fp32 image, as the pipeline feeds it
 res = {}
 outs = {}
 for fused in (False, True):
