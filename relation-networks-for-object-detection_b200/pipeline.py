@@ -214,3 +214,55 @@ class GraphedStep(object):
                 dst.copy_(src, non_blocking=True)
         self.graph.replay()
         return self.out
+
+
+class StreamingDetector(object):
+    """Throughput-oriented public entry for a stream of images held in pinned host memory: `depth` in-flight slots, each
+    with its own captured graph (own static input / output buffers; weights, packed operands and workspaces are shared, the
+    graphs run one after the other on one compute stream).  submit() enqueues H2D (copy stream) -> graph replay (compute
+    stream) -> D2H of the detections into the slot's pinned buffers (copy-back stream) and returns at once; collect() waits
+    for that image's D2H only.  Every image pays its own H2D and D2H; they overlap the neighbours' compute."""
+
+    OUT = ('learn_nms_sorted_bbox', 'nms_final_score_output')
+
+    def __init__(self, trunk, head, im_info, example_image, depth=2):
+        self.depth = depth
+        det = Detector(trunk, head, im_info)
+        self.slots = []
+        for _ in range(depth):
+            g = GraphedStep(det, [example_image])
+            out = {k: torch.empty(g.out[k].shape, dtype=g.out[k].dtype).pin_memory() for k in self.OUT}
+            self.slots.append(dict(graph=g, out=out, ev_in=torch.cuda.Event(), ev_done=torch.cuda.Event(),
+                                   ev_out=torch.cuda.Event(), busy=False))
+        self.h2d, self.d2h = torch.cuda.Stream(), torch.cuda.Stream()
+        self.n = 0
+
+    def submit(self, image_pinned):
+        """image_pinned: fp32 [1,3,H,W] in pinned host memory.  Returns a ticket for collect()."""
+        k = self.n % self.depth
+        sl = self.slots[k]
+        if sl['busy']:
+            raise RuntimeError('StreamingDetector: slot %d still holds an uncollected result (depth %d)' % (k, self.depth))
+        main = torch.cuda.current_stream()
+        with torch.cuda.stream(self.h2d):
+            self.h2d.wait_event(sl['ev_done'])                 # the previous replay of this slot has consumed its input
+            sl['graph'].static_in[0].copy_(image_pinned, non_blocking=True)
+            sl['ev_in'].record(self.h2d)
+        main.wait_event(sl['ev_in'])
+        sl['graph'].graph.replay()
+        sl['ev_done'].record(main)
+        with torch.cuda.stream(self.d2h):
+            self.d2h.wait_event(sl['ev_done'])
+            for name in self.OUT:
+                sl['out'][name].copy_(sl['graph'].out[name], non_blocking=True)
+            sl['ev_out'].record(self.d2h)
+        sl['busy'] = True
+        self.n += 1
+        return k
+
+    def collect(self, ticket):
+        """blocks until the detections of that image are in host memory; returns the slot's pinned tensors"""
+        sl = self.slots[ticket]
+        sl['ev_out'].synchronize()
+        sl['busy'] = False
+        return sl['out']

@@ -104,3 +104,36 @@ def test_box_annotator_ohem_custom_op(compat):
                                        cls_score=dev('cls_score'), bbox_pred=dev('bbox_pred'), labels=dev('labels'),
                                        bbox_targets=dev('bbox_targets'), bbox_weights=dev('bbox_weights'))
     assert np.array_equal(lab.cpu().numpy(), g['labels_ohem']) and np.array_equal(w.cpu().numpy(), g['bbox_weights_ohem'])
+
+
+def test_streaming_detector_matches_single_image_path(compat):
+    """pipeline.StreamingDetector (2 slots in flight, copies on side streams) returns, image by image, exactly what the
+    one-image-at-a-time graph replay returns"""
+    import relnet_b200
+    from relnet_b200.pipeline import RelationHead, init_head_params, Detector, GraphedStep, StreamingDetector
+    from relnet_b200.trunk import make_trunk
+    dev = torch.device('cuda')
+    trunk = make_trunk(dev, torch.bfloat16)
+    head = RelationHead(init_head_params(0, dev), precision='f16' if relnet_b200.ops.device_info()['sm100'] else 'fp32')
+    im_info = torch.tensor([[224.0, 320.0, 1.0]], device=dev)
+    imgs = [(torch.randn(1, 3, 224, 320, generator=torch.Generator().manual_seed(s)) * 50).pin_memory() for s in range(5)]
+    single = GraphedStep(Detector(trunk, head, im_info), [imgs[0].to(dev)])
+    want = []
+    for im in imgs:
+        o = single(im.to(dev))
+        torch.cuda.synchronize()
+        want.append({k: o[k].cpu().clone() for k in StreamingDetector.OUT})
+    sd = StreamingDetector(trunk, head, im_info, imgs[0].to(dev), depth=2)
+    got, tickets = [], []
+    for im in imgs:
+        tickets.append(sd.submit(im))
+        if len(tickets) == 2:
+            got.append({k: v.clone() for k, v in sd.collect(tickets.pop(0)).items()})
+    while tickets:
+        got.append({k: v.clone() for k, v in sd.collect(tickets.pop(0)).items()})
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        for k in StreamingDetector.OUT:
+            assert torch.equal(g[k], w[k]), k
+    with pytest.raises(RuntimeError):
+        sd.submit(imgs[0]); sd.submit(imgs[1]); sd.submit(imgs[2])        # third submit without a collect: slot busy
