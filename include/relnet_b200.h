@@ -352,6 +352,12 @@ int rn_deform_im2col(const rn_deform_conv_desc* desc, const float* data_b, const
  *   (relation_rcnn/symbols/resnet_v1_101_rcnn_base.py conv1) is a 4x4 stride-1 convolution over this tensor.
  * rn_maxpool3x3s2_nhwc_bf16: pool1 (3x3, stride 2, pooling_convention='full' = ceil mode) on a channels-last bf16 map;
  *   out is [ceil((H-3)/2)+1, ceil((W-3)/2)+1, C], C % 8 == 0. */
+/* rn_rpn_head_fwd: the RPN head after rpn_conv (resnet_v1_101_rcnn_base.py:685-693): rpn_cls_score (2A) and rpn_bbox_pred
+ *   (4A) 1x1 convolutions over the channels-last bf16 map r [HW, Cin] (Cin % 64 == 0, A <= 16), the {bg, fg} softmax per anchor
+ *   (channel c pairs with c +- A), outputs fp32 NCHW: prob [2A, HW], bbox [4A, HW] -- what rn_proposal_fwd reads.
+ *   Weights / biases bf16 in the layout of the conv parameters ([out, Cin]). */
+int rn_rpn_head_fwd(const void* r_nhwc_bf16, int32_t HW, int32_t Cin, int32_t A, const void* Wcls_bf16, const void* bcls_bf16,
+                    const void* Wbbox_bf16, const void* bbbox_bf16, float* prob, float* bbox, rn_stream_t stream);
 int rn_image_s2d_bf16(const float* image_chw, int32_t H, int32_t W, int32_t pad, void* out_nhwc16_bf16, rn_stream_t stream);
 int rn_maxpool3x3s2_nhwc_bf16(const void* in_nhwc, int32_t H, int32_t W, int32_t C, void* out_nhwc, rn_stream_t stream);
 

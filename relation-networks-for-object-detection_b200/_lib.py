@@ -66,6 +66,7 @@ SIGNATURES = {
     'rn_linear_multi_packed_bytes': (c_sz, [C.POINTER(c_i), c_i, c_i]),
     'rn_linear_multi_pack': (C.c_int, [C.POINTER(c_p), C.POINTER(c_p), C.POINTER(c_i), c_i, c_i, c_p, c_p]),
     'rn_linear_multi_packed_f16in_fwd': (C.c_int, [c_p, c_p, C.POINTER(c_p), C.POINTER(c_i), c_i, c_i, c_i, c_p, c_sz, c_p]),
+    'rn_rpn_head_fwd': (C.c_int, [c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     'rn_image_s2d_bf16': (C.c_int, [c_p, c_i, c_i, c_i, c_p, c_p]),
     'rn_maxpool3x3s2_nhwc_bf16': (C.c_int, [c_p, c_i, c_i, c_i, c_p, c_p]),
     'rn_pos_embed_fwd': (C.c_int, [c_p, c_p, c_i, c_i, c_i, c_f, c_p, c_p, c_p]),

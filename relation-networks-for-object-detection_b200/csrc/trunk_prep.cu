@@ -60,7 +60,93 @@ __global__ void __launch_bounds__(256) maxpool3x3s2_nhwc_bf16_kernel(const __nv_
   reinterpret_cast<uint4*>(out + ((size_t)oh * Wo + ow) * C8 * 8)[c8] = o;
 }
 
+// RPN head (resnet_v1_101_rcnn_base.py:685-693 + the 2-way softmax of get_symbol): the two 1x1 convolutions rpn_cls_score
+// (2A) / rpn_bbox_pred (4A) over the 512-channel rpn_conv map, the {bg, fg} softmax per anchor and the fp32 NCHW outputs
+// `proposal` reads -- one kernel instead of ten library launches (2 GEMMs, 2 bias adds, casts, reshapes, softmax: 33 us on the
+// critical branch of the step, tools/timeline.py).  CTA = 32 positions x all 6A outputs; K streamed through shared memory in
+// chunks of 64; fp32 accumulation.  r: channels-last bf16 [HW, Cin]; Wc [2A, Cin], Wb [4A, Cin], biases bf16.
+constexpr int kRpnPos = 32, kRpnKc = 64, kRpnMaxO = 12;     // up to 8 * 12 = 96 outputs per position (A <= 16)
+__global__ void __launch_bounds__(256) rpn_head_kernel(const __nv_bfloat16* __restrict__ r, int HW, int Cin, int A,
+                                                       const __nv_bfloat16* __restrict__ Wc, const __nv_bfloat16* __restrict__ bc,
+                                                       const __nv_bfloat16* __restrict__ Wb, const __nv_bfloat16* __restrict__ bb,
+                                                       float* __restrict__ prob, float* __restrict__ bbox) {
+  extern __shared__ float sm_rpn[];
+  const int NO = 6 * A;                                   // outputs per position: 2A scores then 4A deltas
+  float* Ws = sm_rpn;                                     // [NO][kRpnKc + 1]
+  float* Rs = Ws + NO * (kRpnKc + 1);                     // [kRpnPos][kRpnKc + 1]
+  float* Ss = Rs + kRpnPos * (kRpnKc + 1);                // [NO][kRpnPos + 1]  accumulated outputs
+  const int p0 = blockIdx.x * kRpnPos, tid = threadIdx.x;
+  // thread -> (position p = lane, output group og = warp): outputs og, og + 8, ... ; a warp reads one weight (broadcast) and
+  // 32 different positions (row stride 65 words: conflict-free)
+  const int p = tid & 31, og = tid >> 5;
+  float acc[kRpnMaxO];
+#pragma unroll
+  for (int j = 0; j < kRpnMaxO; ++j) acc[j] = 0.f;
+  for (int k0 = 0; k0 < Cin; k0 += kRpnKc) {
+    for (int i = tid; i < NO * kRpnKc; i += 256) {
+      const int oo = i / kRpnKc, kk = i % kRpnKc;
+      const __nv_bfloat16 w = oo < 2 * A ? Wc[(size_t)oo * Cin + k0 + kk] : Wb[(size_t)(oo - 2 * A) * Cin + k0 + kk];
+      Ws[oo * (kRpnKc + 1) + kk] = __bfloat162float(w);
+    }
+    for (int i = tid; i < kRpnPos * kRpnKc; i += 256) {
+      const int pp = i / kRpnKc, kk = i % kRpnKc;
+      Rs[pp * (kRpnKc + 1) + kk] = p0 + pp < HW ? __bfloat162float(r[(size_t)(p0 + pp) * Cin + k0 + kk]) : 0.f;
+    }
+    __syncthreads();
+    const float* rrow = Rs + p * (kRpnKc + 1);
+#pragma unroll 4
+    for (int kk = 0; kk < kRpnKc; ++kk) {
+      const float rv = rrow[kk];
+#pragma unroll
+      for (int j = 0; j < kRpnMaxO; ++j) {
+        const int o = og + 8 * j;
+        if (o < NO) acc[j] = fmaf(Ws[o * (kRpnKc + 1) + kk], rv, acc[j]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < kRpnMaxO; ++j) {
+    const int o = og + 8 * j;
+    if (o < NO) Ss[o * (kRpnPos + 1) + p] = acc[j] + __bfloat162float(o < 2 * A ? bc[o] : bb[o - 2 * A]);
+  }
+  __syncthreads();
+  // outputs, position-fastest (NCHW): prob[c][p] = softmax over {c, c +- A}; bbox[c][p]
+  for (int i = tid; i < NO * kRpnPos; i += 256) {
+    const int oo = i / kRpnPos, pp = i % kRpnPos;
+    if (p0 + pp >= HW) continue;
+    const float v = Ss[oo * (kRpnPos + 1) + pp];
+    if (oo < 2 * A) {
+      const float other = Ss[(oo < A ? oo + A : oo - A) * (kRpnPos + 1) + pp];
+      const float m = fmaxf(v, other);
+      const float e = expf(v - m), eo = expf(other - m);
+      prob[(size_t)oo * HW + p0 + pp] = e / (e + eo);
+    } else {
+      bbox[(size_t)(oo - 2 * A) * HW + p0 + pp] = v;
+    }
+  }
+}
+
 }  // namespace rn
+
+extern "C" int rn_rpn_head_fwd(const void* r_nhwc_bf16, int32_t HW, int32_t Cin, int32_t A, const void* Wcls_bf16,
+                               const void* bcls_bf16, const void* Wbbox_bf16, const void* bbbox_bf16, float* prob,
+                               float* bbox, rn_stream_t stream) {
+  RN_CHECK_ARG(r_nhwc_bf16 && Wcls_bf16 && bcls_bf16 && Wbbox_bf16 && bbbox_bf16 && prob && bbox, "rn_rpn_head_fwd: null pointer");
+  RN_CHECK_ARG(HW > 0 && Cin > 0 && Cin % rn::kRpnKc == 0 && A >= 1 && 6 * A <= 8 * rn::kRpnMaxO, "rn_rpn_head_fwd: need Cin %% 64 == 0 and A <= 16");
+  const int NO = 6 * A;
+  const size_t smem = ((size_t)NO * (rn::kRpnKc + 1) + (size_t)rn::kRpnPos * (rn::kRpnKc + 1) + (size_t)NO * (rn::kRpnPos + 1)) * sizeof(float);
+  static thread_local size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    RN_CUDA(cudaFuncSetAttribute(rn::rpn_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  rn::rpn_head_kernel<<<rn::cdiv(HW, rn::kRpnPos), 256, smem, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)r_nhwc_bf16, HW, Cin, A, (const __nv_bfloat16*)Wcls_bf16, (const __nv_bfloat16*)bcls_bf16,
+      (const __nv_bfloat16*)Wbbox_bf16, (const __nv_bfloat16*)bbbox_bf16, prob, bbox);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
 
 extern "C" int rn_image_s2d_bf16(const float* image_chw, int32_t H, int32_t W, int32_t pad, void* out_nhwc16_bf16,
                                  rn_stream_t stream) {

@@ -633,6 +633,24 @@ def deform_im2col(im, offset, kernel=(3, 3), pad=(2, 2), stride=(1, 1), dilate=(
     return col
 
 
+def rpn_head(r, Wcls, bcls, Wbbox, bbbox):
+    """RPN head after rpn_conv: r = channels-last bf16 [1,Cin,h,w]; 1x1 conv weights/biases bf16 -> (rpn_cls_prob [1,2A,h,w],
+    rpn_bbox_pred [1,4A,h,w]) fp32 NCHW, the {bg, fg} softmax applied (rn_rpn_head_fwd)."""
+    ts = (r, Wcls, bcls, Wbbox, bbbox)
+    if not all(t.is_cuda and t.dtype == torch.bfloat16 for t in ts) or r.dim() != 4 or r.shape[0] != 1 \
+            or not r.is_contiguous(memory_format=torch.channels_last):
+        raise L.RelnetError('rpn_head: bf16 CUDA tensors, r channels-last [1,Cin,h,w]')
+    _, Cin, h, w = r.shape
+    A = Wcls.shape[0] // 2
+    if Wcls.numel() != 2 * A * Cin or Wbbox.numel() != 4 * A * Cin or bcls.numel() != 2 * A or bbbox.numel() != 4 * A:
+        raise L.RelnetError('rpn_head: inconsistent weight shapes')
+    prob = torch.empty((1, 2 * A, h, w), dtype=torch.float32, device=r.device)
+    bbox = torch.empty((1, 4 * A, h, w), dtype=torch.float32, device=r.device)
+    L.check(L.lib().rn_rpn_head_fwd(_ptr(r), h * w, Cin, A, _ptr(Wcls.contiguous()), _ptr(bcls), _ptr(Wbbox.contiguous()),
+                                    _ptr(bbbox), _ptr(prob), _ptr(bbox), _stream()), 'rn_rpn_head_fwd')
+    return prob, bbox
+
+
 def image_s2d(image, pad=3):
     """fp32 [1,3,H,W] (or [3,H,W]) image -> bf16 NCHW-shaped, channels-last-strided [1,16,(H+2pad)/2,(W+2pad)/2]: the
     space-to-depth(2) form of the zero-padded image that turns the 7x7/2 stem conv into a 4x4/1 conv (rn_image_s2d_bf16)."""

@@ -128,6 +128,9 @@ class Trunk(nn.Module):
     def rpn(self, c4):
         """-> rpn_cls_prob [1,2A,h,w] fp32, rpn_bbox_pred [1,4A,h,w] fp32 (SYM_BASE:685-693 + softmax over {bg, fg})"""
         r = _conv_relu(self.rpn_conv, c4)
+        if FUSED and r.is_cuda and r.dtype == torch.bfloat16 and r.shape[0] == 1 and self.A <= 16:
+            from . import ops          # both 1x1 heads + softmax + fp32 NCHW outputs: one hand-written kernel
+            return ops.rpn_head(r, self.rpn_cls.weight, self.rpn_cls.bias, self.rpn_bbox.weight, self.rpn_bbox.bias)
         score = self.rpn_cls(r).float()
         b, _, h, w = score.shape
         prob = F.softmax(score.reshape(b, 2, self.A * h, w), dim=1).reshape(b, 2 * self.A, h, w)

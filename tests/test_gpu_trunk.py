@@ -63,3 +63,24 @@ def test_trunk_fast_stem_equals_plain_path(ops):
         TR.FUSED = old
     assert fast.shape == plain.shape
     assert (fast.float() - plain.float()).abs().max().item() <= 2e-2 * plain.float().abs().max().item()    # bf16 conv, different algo
+
+
+def test_rpn_head_kernel_matches_module_path(ops):
+    """rn_rpn_head_fwd (1x1 cls/bbox convs + {bg,fg} softmax + fp32 NCHW layout) vs the torch module path in float32"""
+    from relnet_b200 import trunk as TR
+    t = TR.make_trunk('cuda')
+    torch.manual_seed(3)
+    r = torch.randn(1, 512, 38, 63, device='cuda').clamp_min(0).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    prob, bbox = ops.rpn_head(r, t.rpn_cls.weight, t.rpn_cls.bias, t.rpn_bbox.weight, t.rpn_bbox.bias)
+    rf = r.float()
+    score = F.conv2d(rf, t.rpn_cls.weight.float(), t.rpn_cls.bias.float())
+    want_prob = F.softmax(score.reshape(1, 2, 12 * 38, 63), dim=1).reshape(1, 24, 38, 63)
+    want_bbox = F.conv2d(rf, t.rpn_bbox.weight.float(), t.rpn_bbox.bias.float())
+    assert prob.shape == want_prob.shape and bbox.shape == want_bbox.shape and prob.dtype == torch.float32
+    assert (prob - want_prob).abs().max().item() <= 1e-4                      # fp32 accumulate on both sides
+    assert (bbox - want_bbox).abs().max().item() <= 1e-4 * max(1.0, want_bbox.abs().max().item())
+    assert torch.allclose(prob[:, :12] + prob[:, 12:], torch.ones_like(prob[:, :12]), atol=1e-6)
+    # HW not a multiple of the 32-position tile
+    r2 = r[:, :, :5, :7].contiguous(memory_format=torch.channels_last)
+    p2, b2 = ops.rpn_head(r2, t.rpn_cls.weight, t.rpn_cls.bias, t.rpn_bbox.weight, t.rpn_bbox.bias)
+    assert torch.allclose(p2, prob[:, :, :5, :7], atol=1e-6) and torch.allclose(b2, bbox[:, :, :5, :7], atol=1e-5)

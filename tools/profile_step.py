@@ -27,7 +27,7 @@ if a.what in ('step', 'hot'):
     trunk = make_trunk(dev, torch.bfloat16)
     head = RelationHead(init_head_params(0, dev))
     image, im_info = make_inputs()
-    image = image.to(dev, torch.bfloat16).contiguous(memory_format=torch.channels_last); im_info = im_info.to(dev)
+    image = image.to(dev); im_info = im_info.to(dev)          # fp32 image: the stem converts in its own kernel
     tout = trunk(image)
     fn = (lambda: head.forward(*trunk(image), im_info)) if a.what == 'step' else (lambda: head.forward(*tout, im_info))
 else:
