@@ -365,7 +365,7 @@ static int lnms_forward(const rn_learn_nms_desc* d, const float* cls_score, cons
     const int ldr = (int)align_up(Rn, 4);
     if ((r = launch_geom_weight_log2_T(st, W.refined, Rn, 16, 64, 1000.f, w->nms_pair_pos_fc1_1_weight,
                                        w->nms_pair_pos_fc1_1_bias, W.lg_roi, ldr))) return r;
-    GeomGather gg = {W.lg_roi, ldr, Rn, W.rank_idx, C, 1, nullptr};
+    GeomGather gg = {W.lg_roi, ldr, Rn, W.rank_idx, C, 1, nullptr, W.valid};     // pruned classes cost nothing
     if ((r = relation_tc_lnms(&rd, W.feat_cls, emb, d->R, rank_feat, &gg, w->nms_query_1_weight, w->nms_query_1_bias,
                               w->nms_key_1_weight, w->nms_key_1_bias, w->nms_linear_out_1_weight,
                               w->nms_linear_out_1_bias, W.feat_out, W.rel_ws, W.rel_ws_bytes, st,

@@ -39,7 +39,7 @@ int relation_tc_packed(const rn_relation_desc* d, const float* X, const float* b
                        void* out_f16 = nullptr);
 // geometry gathered from one roi-level table lg_table [H, R, ld]: row i of problem b is roi idx[i*stride_i + b*stride_b]
 struct GeomGather { const float* lg_table; int ld; int R; const int* idx; int stride_i; int stride_b;
-                    const void* qkv_ext; };   // qkv_ext: optional pre-computed fp16 [B*N, 3*H*64] projections (skips the GEMM)
+                    const void* qkv_ext; const int* active = nullptr; };   // active: optional per-problem skip mask   // qkv_ext: optional pre-computed fp16 [B*N, 3*H*64] projections (skips the GEMM)
 int relation_tc_gathered(const rn_relation_desc* d, const float* X, const GeomGather* gg, const float* Wq, const float* bq,
                          const float* Wk, const float* bk, const float* Wout, const float* bout, float* out, void* ws,
                          size_t ws_bytes, cudaStream_t st);

@@ -43,6 +43,9 @@ struct AttnParams {
   // [H, key roi, query roi]; row i of problem b is roi gidx[i*gs_i + b*gs_b] -- the per-class geometry is a gather, not
   // 80 recomputations
   const int* gidx; int gs_i, gs_b; int R;
+  // optional per-problem skip mask (learn-NMS: problem = fg class; pruned classes -- LNMS:298-303 -- never get their
+  // conditional score used): a CTA of a problem with active[b] == 0 exits before touching anything
+  const int* active;
 };
 
 __global__ void __launch_bounds__(192, 1) relation_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
@@ -310,6 +313,7 @@ __global__ void __launch_bounds__(160, 2) relation_attn_tile_kernel(const __grid
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x / tp.splits, kt = blockIdx.x % tp.splits;
   const int q0 = qt * 128, m0 = kt * 128, h = blockIdx.y, b = blockIdx.z;
+  if (p.active && !p.active[b]) return;          // uniform for the whole CTA, before any barrier / TMEM allocation
   if (p.gidx && threadIdx.x < 128) {
     const int m = m0 + threadIdx.x, nq = q0 + threadIdx.x;
     s_gidx[threadIdx.x] = m < p.M ? p.gidx[(size_t)m * p.gs_i + (size_t)b * p.gs_b] : 0;
@@ -619,7 +623,8 @@ int relation_tc_packed(const rn_relation_desc* d, const float* X, const float* b
   AttnParams p;
   p.N = N; p.M = M; p.H = H; p.T = T;
   p.lg = lg; p.ldg = ldg;
-  p.gidx = nullptr; p.gs_i = p.gs_b = 0; p.R = 0;
+  p.gidx = nullptr; p.gs_i = p.gs_b = 0; p.R = 0; p.active = nullptr;
+  if (gg) p.active = gg->active;
   if (gg) { p.lg = gg->lg_table; p.ldg = gg->ld; p.R = gg->R; p.gidx = gg->idx; p.gs_i = gg->stride_i; p.gs_b = gg->stride_b; }
   p.X = d->fuse_residual_relu ? X : nullptr; p.ldx = D;
   p.out = out; p.ldo = d->dout; p.dv = dv; p.relu = d->fuse_residual_relu;
@@ -683,13 +688,15 @@ bool relation_tc_shape_ok(const rn_relation_desc* d) { return tc_shape_ok(d); }
 // qkv16[(b*n + i), :] = fp16(E[idx[i*gs_i + b*gs_b], :] + Rk[i, :]);  8 columns per thread
 __global__ void __launch_bounds__(256) lnms_gather_add_qkv_kernel(const float* __restrict__ E, const float* __restrict__ Rk,
                                                                   const int* __restrict__ idx, int gs_i, int gs_b, int B,
-                                                                  int n, int W3, __half* __restrict__ out) {
+                                                                  int n, int W3, const int* __restrict__ active,
+                                                                  __half* __restrict__ out) {
   const int vec = W3 / 8;
   const size_t total = (size_t)B * n * vec;
   for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
     const int v = t % vec;
     const size_t row = t / vec;
     const int i = row % n, b = row / n;
+    if (active && !active[b]) continue;
     const float4* e = reinterpret_cast<const float4*>(E + (size_t)idx[(size_t)i * gs_i + (size_t)b * gs_b] * W3) + 2 * v;
     const float4* rk = reinterpret_cast<const float4*>(Rk + (size_t)i * W3) + 2 * v;
     const float4 e0 = __ldg(e), e1 = __ldg(e + 1), r0 = __ldg(rk), r1 = __ldg(rk + 1);
@@ -761,7 +768,7 @@ int relation_tc_lnms(const rn_relation_desc* d, const float* X, const float* emb
     size_t blocks = (total + 255) / 256;
     const size_t cap = (size_t)(sm_count() > 0 ? sm_count() : 148) * 16;
     lnms_gather_add_qkv_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(E, Rk, gg->idx, gg->stride_i,
-                                                                                  gg->stride_b, B, n, W3, qkv);
+                                                                                  gg->stride_b, B, n, W3, gg->active, qkv);
     RN_LAUNCH_CHECK();
   }
   GeomGather g2 = *gg;
