@@ -147,6 +147,9 @@ int rn_linear_multi_packed_f16in_fwd(const void* x_f16, const void* packed, floa
 int rn_roi_pool_nhwc_f16_fwd(const float* data_nhwc, const float* rois, int32_t R, int32_t C, int32_t H, int32_t W,
                              int32_t PH, int32_t PW, float spatial_scale, void* out_f16, rn_stream_t stream);
 /* W [out, C*S] (FC over a flattened [C, S] input, S = PH*PW) -> packed fp16 [out, S*C] */
+/* same with a bf16 channels-last feature map (what the cuDNN trunk emits): no fp32 conversion pass; identical output values */
+int rn_roi_pool_nhwc_bf16in_f16_fwd(const void* data_nhwc_bf16, const float* rois, int32_t R, int32_t C, int32_t H, int32_t W,
+                                    int32_t PH, int32_t PW, float spatial_scale, void* out_f16, rn_stream_t stream);
 int rn_linear_pack_chw_to_hwc(const float* W, int32_t out, int32_t C, int32_t S, void* packed, rn_stream_t stream);
 /* y = act(x W^T + b) with x already fp16 [rows, in] (in % 8 == 0); y (fp32) and/or y_f16 may be NULL */
 int rn_linear_packed_f16in_fwd(const void* x_f16, const void* packed_W, const float* b, float* y, void* y_f16,

@@ -81,6 +81,7 @@ SIGNATURES = {
     'rn_linear_pack': (C.c_int, [c_p, c_i, c_i, c_p, c_p]),
     'rn_linear_packed_fwd': (C.c_int, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_sz, c_p]),
     'rn_roi_pool_nhwc_f16_fwd': (C.c_int, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p, c_p]),
+    'rn_roi_pool_nhwc_bf16in_f16_fwd': (C.c_int, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p, c_p]),
     'rn_linear_pack_chw_to_hwc': (C.c_int, [c_p, c_i, c_i, c_i, c_p, c_p]),
     'rn_linear_packed_f16in_fwd': (C.c_int, [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_sz, c_p]),
     'rn_learn_nms_workspace_bytes': (c_sz, [C.POINTER(LearnNmsDesc)]),

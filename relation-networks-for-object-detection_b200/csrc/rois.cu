@@ -7,6 +7,7 @@
 // Grid: one thread per output element, blocks of 256, grid-stride capped at 148*8 CTAs.
 #include "common.cuh"
 #include <cfloat>
+#include <cuda_bf16.h>
 
 namespace rn {
 
@@ -73,6 +74,52 @@ __global__ void __launch_bounds__(128) roi_pool_nhwc_f16_kernel(const float* __r
         m0 = fmaxf(m0, v.x); m1 = fmaxf(m1, v.y);
       }
     *reinterpret_cast<__half2*>(out + ((size_t)n * PH * PW + bin) * C + c) = __floats2half2_rn(m0, m1);
+  }
+}
+
+// bf16 channels-last input (the cuDNN trunk's native output: no fp32 conversion pass, half the L2 reads).  CTA = one roi
+// x one row of bins; warp w takes bins pw = w, w + 4; lane l owns channels 8l..8l+7 of a 256-channel slab (16-byte loads,
+// 512 B per cell per warp, fully coalesced), max in bf16x2 (exact), result converted bf16 -> fp16 (exact in fp16's range:
+// a bf16 value has 8 significant bits), i.e. bitwise the value the fp32 kernel above produces.
+__global__ void __launch_bounds__(128) roi_pool_nhwc_bf16in_f16_kernel(const __nv_bfloat16* __restrict__ data,
+                                                                       const float* __restrict__ rois, int C, int H, int W,
+                                                                       int PH, int PW, float spatial_scale,
+                                                                       __half* __restrict__ out) {
+  const int ph = blockIdx.x, n = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* roi = rois + 5 * n;
+  const int b = (int)roi[0];
+  const int rsw = (int)roundf(roi[1] * spatial_scale), rsh = (int)roundf(roi[2] * spatial_scale);
+  const int rew = (int)roundf(roi[3] * spatial_scale), reh = (int)roundf(roi[4] * spatial_scale);
+  const int rh = max(reh - rsh + 1, 1), rw = max(rew - rsw + 1, 1);
+  const float bh = (float)rh / (float)PH, bw = (float)rw / (float)PW;
+  int hs = (int)floorf((float)ph * bh), he = (int)ceilf((float)(ph + 1) * bh);
+  hs = min(max(hs + rsh, 0), H); he = min(max(he + rsh, 0), H);
+  const __nv_bfloat16* d = data + (size_t)b * H * W * C;
+  for (int pw = warp; pw < PW; pw += 4) {
+    int ws = (int)floorf((float)pw * bw), we = (int)ceilf((float)(pw + 1) * bw);
+    ws = min(max(ws + rsw, 0), W); we = min(max(we + rsw, 0), W);
+    const bool empty = (he <= hs) || (we <= ws);
+    for (int c = lane * 8; c < C; c += 256) {
+      const uint32_t ninf = 0xFF80FF80u;                                    // (-inf, -inf) in bf16
+      __nv_bfloat162 m[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) m[q] = *reinterpret_cast<const __nv_bfloat162*>(&ninf);
+      for (int h = hs; h < he; ++h)
+        for (int w = ws; w < we; ++w) {
+          const uint4 u = __ldg(reinterpret_cast<const uint4*>(d + ((size_t)h * W + w) * C + c));
+          const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) m[q] = __hmax2(m[q], pv[q]);
+        }
+      __half2 o[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = __bfloat1622float2(m[q]);
+        o[q] = empty ? __floats2half2_rn(0.f, 0.f) : __floats2half2_rn(f.x, f.y);
+      }
+      *reinterpret_cast<uint4*>(out + ((size_t)n * PH * PW + ph * PW + pw) * C + c) = *reinterpret_cast<const uint4*>(o);
+    }
   }
 }
 
@@ -315,6 +362,18 @@ extern "C" int rn_deform_psroi_pool_bwd(const rn_psroi_desc* desc, int32_t B, co
   RN_CHECK_ARG(dout && top_count && data && rois, "rn_deform_psroi_pool_bwd: null pointer");
   size_t count = (size_t)p.R * p.output_dim * p.pooled_size * p.pooled_size;
   rn::deform_psroi_bwd_kernel<<<rn::grid_for(count), 256, 0, st>>>(p, count, dout, top_count, data, rois, trans, ddata, dtrans);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
+
+extern "C" int rn_roi_pool_nhwc_bf16in_f16_fwd(const void* data_nhwc_bf16, const float* rois, int32_t R, int32_t C, int32_t H,
+                                               int32_t W, int32_t PH, int32_t PW, float spatial_scale, void* out_f16,
+                                               rn_stream_t stream) {
+  RN_CHECK_ARG(data_nhwc_bf16 && rois && out_f16 && R >= 0 && C > 0 && (C % 8) == 0 && H > 0 && W > 0 && PH > 0 && PW > 0,
+               "rn_roi_pool_nhwc_bf16in_f16_fwd: bad arguments (C must be a multiple of 8)");
+  if (R == 0) return RN_OK;
+  rn::roi_pool_nhwc_bf16in_f16_kernel<<<dim3(PH, R), 128, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)data_nhwc_bf16, rois, C, H, W, PH, PW, spatial_scale, (__half*)out_f16);
   RN_LAUNCH_CHECK();
   return RN_OK;
 }

@@ -524,7 +524,6 @@ def roi_pool_fc(data, rois, W, b, pooled_size=(7, 7), spatial_scale=0.0625, relu
     if not data.is_cuda:
         raise L.RelnetError('roi_pool_fc: CUDA tensors required (no CPU path)')
     B, Cc, H, Wd = data.shape
-    nhwc = data.float().contiguous(memory_format=torch.channels_last)      # no-op for the trunk's output
     rois = _f32(rois, 'rois'); W = _f32(W, 'W'); b = _f32(b, 'b') if b is not None else None
     R = rois.shape[0]
     S = pooled_size[0] * pooled_size[1]
@@ -532,8 +531,14 @@ def roi_pool_fc(data, rois, W, b, pooled_size=(7, 7), spatial_scale=0.0625, relu
     assert W.shape[1] == cin
     lib = L.lib()
     pooled = torch.empty((R, cin), dtype=torch.float16, device=data.device)
-    L.check(lib.rn_roi_pool_nhwc_f16_fwd(_ptr(nhwc), _ptr(rois), R, Cc, H, Wd, pooled_size[0], pooled_size[1],
-                                         spatial_scale, _ptr(pooled), _stream()), 'rn_roi_pool_nhwc_f16_fwd')
+    if data.dtype == torch.bfloat16 and Cc % 8 == 0:       # the trunk's native output: pooled straight from bf16
+        nhwc = data.contiguous(memory_format=torch.channels_last)
+        L.check(lib.rn_roi_pool_nhwc_bf16in_f16_fwd(_ptr(nhwc), _ptr(rois), R, Cc, H, Wd, pooled_size[0], pooled_size[1],
+                                                    spatial_scale, _ptr(pooled), _stream()), 'rn_roi_pool_nhwc_bf16in_f16_fwd')
+    else:
+        nhwc = data.float().contiguous(memory_format=torch.channels_last)      # no-op for an fp32 channels-last map
+        L.check(lib.rn_roi_pool_nhwc_f16_fwd(_ptr(nhwc), _ptr(rois), R, Cc, H, Wd, pooled_size[0], pooled_size[1],
+                                             spatial_scale, _ptr(pooled), _stream()), 'rn_roi_pool_nhwc_f16_fwd')
 
     def pack(buf):
         L.check(lib.rn_linear_pack_chw_to_hwc(_ptr(W), cout, Cc, S, _ptr(buf), _stream()), 'rn_linear_pack_chw_to_hwc')

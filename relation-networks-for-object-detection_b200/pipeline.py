@@ -184,7 +184,7 @@ class Detector(object):
             rois_ready.record(self.side)
             done = self.head.geometry_early(rois)          # both modules' geometry terms: beside res5 / ROI pool / fc_new_1
         c4.record_stream(self.side)
-        feat = self.trunk.c5feat(c4)
+        feat = self.trunk.c5feat(c4, keep_dtype=self.head.precision == 'f16')     # f16 head pools straight from bf16
         main.wait_event(rois_ready)                        # ROI pool + fc_new_1 only need the rois ...
         rois.record_stream(main)
         return self.head.detect(rois, feat, self.im_info, geometry_done=done, join=self.side)   # ... relation #1 the geometry

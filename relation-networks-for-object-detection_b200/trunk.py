@@ -137,9 +137,11 @@ class Trunk(nn.Module):
         return prob.contiguous(), self.rpn_bbox(r).float().contiguous()
 
     @torch.no_grad()
-    def c5feat(self, c4):
-        """res5 (dilated) + conv_new_1 + relu -> [1,256,h,w] fp32, left channels-last (consumed as NHWC)"""
-        return _conv_relu(self.conv_new_1, self.res5(c4)).float()
+    def c5feat(self, c4, keep_dtype=False):
+        """res5 (dilated) + conv_new_1 + relu -> [1,256,h,w], left channels-last (consumed as NHWC); fp32 unless keep_dtype
+        (ops.roi_pool_fc pools straight from the bf16 map)"""
+        y = _conv_relu(self.conv_new_1, self.res5(c4))
+        return y if keep_dtype else y.float()
 
     @torch.no_grad()
     def forward(self, image):

@@ -84,3 +84,21 @@ def test_rpn_head_kernel_matches_module_path(ops):
     r2 = r[:, :, :5, :7].contiguous(memory_format=torch.channels_last)
     p2, b2 = ops.rpn_head(r2, t.rpn_cls.weight, t.rpn_cls.bias, t.rpn_bbox.weight, t.rpn_bbox.bias)
     assert torch.allclose(p2, prob[:, :, :5, :7], atol=1e-6) and torch.allclose(b2, bbox[:, :, :5, :7], atol=1e-5)
+
+
+def test_roi_pool_fc_from_bf16_equals_fp32_path(ops):
+    """pooling straight from the trunk's bf16 channels-last map gives bitwise the pooled values of the fp32 kernel"""
+    if not ops.device_info()['sm100']:
+        pytest.skip('tcgen05 path only')
+    rng = np.random.RandomState(4)
+    feat = torch.from_numpy(rng.randn(1, 256, 38, 63).astype(np.float32)).cuda().clamp_min(0).to(torch.bfloat16) \
+        .contiguous(memory_format=torch.channels_last)
+    R = 300
+    x1 = rng.uniform(0, 800, R); y1 = rng.uniform(0, 450, R)
+    rois = torch.from_numpy(np.stack([np.zeros(R), x1, y1, np.minimum(x1 + rng.uniform(4, 600, R), 999),
+                                      np.minimum(y1 + rng.uniform(4, 450, R), 599)], 1).astype(np.float32)).cuda()
+    rois[0] = torch.tensor([0, 990.0, 590.0, 999.0, 599.0])             # a roi whose bins fall off the map
+    W = torch.from_numpy((rng.randn(64, 256 * 49) * 0.01).astype(np.float32)).cuda(); b = torch.zeros(64, device='cuda')
+    y_bf = ops.roi_pool_fc(feat, rois, W, b)
+    y_32 = ops.roi_pool_fc(feat.float(), rois, W, b)
+    assert torch.equal(y_bf, y_32)
