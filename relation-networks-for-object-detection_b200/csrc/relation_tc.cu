@@ -298,7 +298,11 @@ struct TileParams {
   float* part_ml;                // [splits][B][H][N][2]  (row max in log2 units, row sum)
 };
 
-__global__ void __launch_bounds__(160, 2) relation_attn_tile_kernel(const __grid_constant__ CUtensorMap tmQ,
+// 288 threads: warps 0..7 are the softmax / epilogue warps -- TWO threads per query row (warp w and w + 4 share the TMEM lane
+// quarter w % 4; the first takes key columns 0..63 of the tile, the second 64..127), warp 8 issues TMA / UMMA and owns the
+// TMEM allocation.  Twice the warps per SM of the one-thread-per-row form and half the serial work per thread: the kernel is
+// bound by the latency of its dependent chain (gathered geometry loads, TMEM reads, exp2), not by a pipe.
+__global__ void __launch_bounds__(288, 2) relation_attn_tile_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                     const __grid_constant__ CUtensorMap tmK,
                                                                     const __grid_constant__ CUtensorMap tmV, TileParams tp) {
   extern __shared__ uint8_t smem_raw[];
@@ -310,6 +314,7 @@ __global__ void __launch_bounds__(160, 2) relation_attn_tile_kernel(const __grid
   uint64_t* ld_full = bars; uint64_t* s_full = bars + 1; uint64_t* p_full = bars + 2; uint64_t* pv_full = bars + 3;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
   __shared__ int s_gidx[128], s_qidx[128];
+  __shared__ float s_mx[2][128], s_sum[2][128];          // per-half row max / row sum, exchanged between the two threads of a row
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x / tp.splits, kt = blockIdx.x % tp.splits;
   const int q0 = qt * 128, m0 = kt * 128, h = blockIdx.y, b = blockIdx.z;
@@ -320,10 +325,10 @@ __global__ void __launch_bounds__(160, 2) relation_attn_tile_kernel(const __grid
     s_qidx[threadIdx.x] = nq < p.N ? p.gidx[(size_t)nq * p.gs_i + (size_t)b * p.gs_b] : 0;
   }
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
-      mbar_init(ld_full, 1); mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(pv_full, 1);
+      mbar_init(ld_full, 1); mbar_init(s_full, 1); mbar_init(p_full, 256); mbar_init(pv_full, 1);
       fence_barrier_init();
       mbar_arrive_expect_tx(ld_full, 3 * 16384);
       tma_load_3d(sQ, &tmQ, ld_full, h * 64, q0, b);
@@ -339,7 +344,7 @@ __global__ void __launch_bounds__(160, 2) relation_attn_tile_kernel(const __grid
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base, tPV = tmem_base + 128;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       mbar_wait(ld_full, 0);
       tc_fence_after();
@@ -358,25 +363,27 @@ __global__ void __launch_bounds__(160, 2) relation_attn_tile_kernel(const __grid
       mma_commit(pv_full);
     }
   } else {
-    const int r = warp * 32 + lane, n = q0 + r;
+    const int half = warp >> 2;                          // 0: key columns 0..63 of the tile, 1: 64..127
+    const int r = (warp & 3) * 32 + lane, n = q0 + r;
+    const int c0 = half * 64;
     const bool row_ok = n < p.N;
-    const uint32_t lane_base = ((uint32_t)(warp * 32) << 16);
-    // the whole geometry row of this tile, issued before the S tile is ready
-    float t[128];
+    const uint32_t lane_base = ((uint32_t)((warp & 3) * 32) << 16);
+    // this thread's half of the geometry row, issued before the S tile is ready
+    float t[64];
     if (p.gidx) {
       // gather from the TRANSPOSED roi-level table lgT[h][key roi][query roi]: for a given key column every lane of the
       // warp reads the same 1.2 KB table row (at its own query offset) -> a few cache lines per load instruction, and all
-      // 128 loads of the thread are in flight at once
+      // 64 loads of the thread are in flight at once
       const int ri = s_qidx[r];
       const float* col0 = p.lg + (size_t)h * p.R * p.ldg + ri;
 #pragma unroll
-      for (int q = 0; q < 128; ++q) t[q] = (m0 + q < p.M) ? __ldg(col0 + (size_t)s_gidx[q] * p.ldg) : -INFINITY;
+      for (int q = 0; q < 64; ++q) t[q] = (m0 + c0 + q < p.M) ? __ldg(col0 + (size_t)s_gidx[c0 + q] * p.ldg) : -INFINITY;
     } else {
-      const float* lg_row = p.lg + (((size_t)b * p.H + h) * p.N + (row_ok ? n : 0)) * p.ldg + m0;
+      const float* lg_row = p.lg + (((size_t)b * p.H + h) * p.N + (row_ok ? n : 0)) * p.ldg + m0 + c0;
 #pragma unroll
-      for (int q = 0; q < 128; q += 4) {
+      for (int q = 0; q < 64; q += 4) {
         float4 t4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-        if (m0 + q < p.M) t4 = __ldg(reinterpret_cast<const float4*>(lg_row + q));      // ldg >= M rounded up to 4
+        if (m0 + c0 + q < p.M) t4 = __ldg(reinterpret_cast<const float4*>(lg_row + q));      // ldg >= M rounded up to 4
         t[q] = t4.x; t[q + 1] = t4.y; t[q + 2] = t4.z; t[q + 3] = t4.w;
       }
     }
@@ -384,20 +391,23 @@ __global__ void __launch_bounds__(160, 2) relation_attn_tile_kernel(const __grid
     tc_fence_after();
     float mx = -INFINITY;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {
       uint32_t v[32];
-      tmem_ld_32x32b_x32(tS + c * 32 + lane_base, v);
+      tmem_ld_32x32b_x32(tS + c0 + c * 32 + lane_base, v);
       tmem_ld_wait();
 #pragma unroll
       for (int q = 0; q < 32; ++q) {
-        const float tt = (m0 + c * 32 + q < p.M) ? fmaf(__uint_as_float(v[q]), p.scale_log2, t[c * 32 + q]) : -INFINITY;
+        const float tt = (m0 + c0 + c * 32 + q < p.M) ? fmaf(__uint_as_float(v[q]), p.scale_log2, t[c * 32 + q]) : -INFINITY;
         t[c * 32 + q] = tt;
         mx = fmaxf(mx, tt);
       }
     }
+    s_mx[half][r] = mx;
+    asm volatile("bar.sync 1, 256;" ::: "memory");       // the 8 softmax warps only
+    mx = fmaxf(mx, s_mx[half ^ 1][r]);
     float lsum = 0.f;
 #pragma unroll
-    for (int kc = 0; kc < 16; ++kc) {                          // 16-byte chunks of 8 keys
+    for (int kc = 0; kc < 8; ++kc) {                           // 16-byte chunks of 8 keys of this half
       uint32_t pk[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -406,47 +416,52 @@ __global__ void __launch_bounds__(160, 2) relation_attn_tile_kernel(const __grid
         __half2 hh = __floats2half2_rn(p0, p1);
         pk[i] = *reinterpret_cast<uint32_t*>(&hh);
       }
-      *reinterpret_cast<uint4*>(sP + (kc >> 3) * 16384 + sw128_offset(r, kc & 7)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      *reinterpret_cast<uint4*>(sP + half * 16384 + sw128_offset(r, kc)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
+    s_sum[half][r] = lsum;
     fence_proxy_async_smem();
     tc_fence_before();
     mbar_arrive(p_full);
     mbar_wait(pv_full, 0);
     tc_fence_after();
-    float o[64];
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    asm volatile("bar.sync 1, 256;" ::: "memory");       // both halves' row sums are in shared memory
+    lsum += s_sum[half ^ 1][r];
+    // this thread reads output columns 32*half .. 32*half + 31 of its row
+    float o[32];
+    {
       uint32_t v[32];
-      tmem_ld_32x32b_x32(tPV + c * 32 + lane_base, v);
+      tmem_ld_32x32b_x32(tPV + half * 32 + lane_base, v);
       tmem_ld_wait();
 #pragma unroll
-      for (int q = 0; q < 32; ++q) o[c * 32 + q] = __uint_as_float(v[q]);
+      for (int q = 0; q < 32; ++q) o[q] = __uint_as_float(v[q]);
     }
     if (row_ok) {
       if (tp.splits > 1) {
         const size_t row = (((size_t)kt * gridDim.z + b) * p.H + h) * p.N + n;
-        float4* dst = reinterpret_cast<float4*>(tp.part_o + row * 64);
+        float4* dst = reinterpret_cast<float4*>(tp.part_o + row * 64 + half * 32);
 #pragma unroll
-        for (int q = 0; q < 64; q += 4) dst[q >> 2] = make_float4(o[q], o[q + 1], o[q + 2], o[q + 3]);
-        reinterpret_cast<float2*>(tp.part_ml)[row] = make_float2(mx, lsum);
+        for (int q = 0; q < 32; q += 4) dst[q >> 2] = make_float4(o[q], o[q + 1], o[q + 2], o[q + 3]);
+        if (half == 0) reinterpret_cast<float2*>(tp.part_ml)[row] = make_float2(mx, lsum);
       } else {
         const float inv = 1.f / lsum;
+        const int col0 = half * 32;
         float* dst = p.out + ((size_t)b * p.N + n) * p.ldo + (size_t)h * p.dv;
         const float* res = p.X ? p.X + ((size_t)b * p.N + n) * p.ldx + (size_t)h * p.dv : nullptr;
 #pragma unroll
-        for (int q = 0; q < 64; ++q)
-          if (q < p.dv) {
+        for (int q = 0; q < 32; ++q)
+          if (col0 + q < p.dv) {
             float y = o[q] * inv;
-            if (res) y += res[q];
+            if (res) y += res[col0 + q];
             if (p.relu) y = fmaxf(y, 0.f);
-            dst[q] = y;
+            dst[col0 + q] = y;
+            if (p.out16) p.out16[((size_t)b * p.N + n) * p.ldo16 + (size_t)h * p.dv + col0 + q] = __float2half_rn(y);
           }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc<256>(tmem_base);
+  if (warp == 8) tmem_dealloc<256>(tmem_base);
 }
 
 // merge the per-key-tile partials: one thread per (b, n, h, 4 output columns)
@@ -639,7 +654,7 @@ int relation_tc_packed(const rn_relation_desc* d, const float* X, const float* b
   if (T <= kMaxTileSplits) {
     TileParams tp;
     tp.a = p; tp.splits = T; tp.part_o = part_o; tp.part_ml = part_ml;
-    relation_attn_tile_kernel<<<dim3(cdiv(N, 128) * T, H, B), 160, kTileSmem, st>>>(tmQ, tmK, tmV, tp);
+    relation_attn_tile_kernel<<<dim3(cdiv(N, 128) * T, H, B), 288, kTileSmem, st>>>(tmQ, tmK, tmV, tp);
     RN_LAUNCH_CHECK();
     if (T > 1) {
       const size_t total = (size_t)B * N * H * 16;
