@@ -25,7 +25,8 @@ namespace rn {
 using namespace umma;
 
 constexpr int kKV = 3;                       // K/V' ring stages
-constexpr int kMaxTileSplits = 4;            // <= this many key tiles: one CTA per tile + combine
+constexpr int kMaxTileSplits = 24;           // <= this many key tiles (M <= 3072): one CTA per (query tile, key tile) + combine --
+                                             // measured faster than the streaming kernel at every sweep point (r01_relation_sweep_5)
 constexpr int kQ = 16384, kKt = 16384, kVt = 16384, kPt = 32768;
 constexpr int kAttnBar = kQ + kKV * (kKt + kVt) + 2 * kPt;      // 180224
 constexpr int kAttnSmem = kAttnBar + 256 + 1024;
