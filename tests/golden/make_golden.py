@@ -58,6 +58,31 @@ def relation_case(ns, name, seed, N, d, H, init, M=None):
     print(name, 'attention', att.a.shape, float(np.abs(att.a).max()))
 
 
+def relation_fpn_case(ns, name, seed, N, d, H, n_keys):
+    """FPN form (SYM_FPN_REL_NMS:843-977): keys = take(roi_feat, non_gt_index), pair FC as a 1x1 Convolution over the
+    [1, 64, N, M] embedding (:1122-1135 shows how get_symbol prepares it)."""
+    shim = ns.mxshim
+    c = relation_np.make_relation_case(seed, N, d, H, init='fan_in')
+    rng = np.random.default_rng(seed + 1000)
+    idx = np.sort(rng.permutation(N)[:n_keys]).astype(np.float32)            # MXNet indices are float-valued
+    Sym = ns.sym_fpn_rel_nms.resnet_v1_101_rcnn_fpn_attention_1024_pairwise_position_multi_head_16_learn_nms
+    sym = Sym()
+    shim.PARAMS.clear()
+    shim.PARAMS.update({
+        'pair_pos_fc1_1_weight': c['Wg'].reshape(H, 64, 1, 1), 'pair_pos_fc1_1_bias': c['bg'],
+        'query_1_weight': c['Wq'], 'query_1_bias': c['bq'],
+        'key_1_weight': c['Wk'], 'key_1_bias': c['bk'],
+        'linear_out_1_weight': c['Wout'].reshape(d, d, 1, 1), 'linear_out_1_bias': c['bout']})
+    pm = Sym.extract_position_matrix(shim.ND(c['boxes']), non_gt_index=shim.ND(idx))
+    pe = Sym.extract_position_embedding(pm, feat_dim=64)
+    pe_r = shim.expand_dims(shim.transpose(pe, axes=(2, 0, 1)), axis=0)
+    att = sym.attention_module_multi_head(shim.ND(c['X']), pe_r, non_gt_index=shim.ND(idx), fc_dim=H, feat_dim=d,
+                                          index=1, group=H, dim=(d, d, d))
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), N=N, d=d, H=H, seed=seed, input_checksum=checksum(c),
+                        non_gt_index=idx.astype(np.int32), position_matrix=pm.a[:8], attention=att.a)
+    print(name, 'attention', att.a.shape, float(np.abs(att.a).max()))
+
+
 def learn_nms_case(ns, name, seed, R, C, init, first_n):
     shim = ns.mxshim
     c = learn_nms_np.make_learn_nms_case(seed, R=R, C=C, init=init)
@@ -211,6 +236,7 @@ def main():
     misc_case(ns, 'misc_helpers')
     nms_multi_target_case(ns, 'nms_multi_target')
     ohem_case(ns, 'box_annotator_ohem')
+    relation_fpn_case(ns, 'relation_fpn_n90_k70', 5, 90, 256, 4, 70)
 
 
 if __name__ == '__main__':

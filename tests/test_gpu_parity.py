@@ -394,3 +394,16 @@ def test_linear_multi_equals_separate_layers(ops):
     assert torch.equal(ys1[0], ys[0])
     with pytest.raises(Exception):
         ops.linear_multi(x16, layers + layers)                               # more than 4 layers
+
+
+def test_relation_fpn_form_matches_reference_execution(ops):
+    """row a4 on the device: key_index (FPN non_gt_index) form against the golden made by executing the FPN symbol"""
+    g = golden('relation_fpn_n90_k70')
+    c = R.make_relation_case(int(g['seed']), int(g['N']), int(g['d']), int(g['H']), init='fan_in')
+    t = [T(c[k]) for k in ('X', 'boxes', 'Wq', 'bq', 'Wk', 'bk', 'Wg', 'bg', 'Wout', 'bout')]
+    kidx = torch.from_numpy(g['non_gt_index'].astype(np.int32)).cuda()
+    for prec in precisions(ops):
+        out = ops.relation(*t, key_index=kidx, group=int(g['H']), residual_relu=False, precision=prec)
+        e = rel_err(out.cpu().numpy(), g['attention'])
+        print('fpn form [%s] %.2e' % (prec, e))
+        assert e <= (3e-4 if prec == 'fp32' else 1e-3)

@@ -247,3 +247,17 @@ def test_nms_loss_oracle_gradient_is_autograd():
     (4.0 * p.sum() + n.sum()).backward()
     assert rel_err(pos, p.detach().numpy()) <= 1e-5 and rel_err(neg, n.detach().numpy()) <= 1e-5
     assert rel_err(d, tm.grad.numpy()) <= 1e-5
+
+
+def test_relation_oracle_matches_fpn_reference_execution():
+    """row a4: the FPN symbol's own extract_position_matrix / attention_module_multi_head (keys = take(non_gt_index), pair FC
+    as a 1x1 convolution) executed under the shim == oracle relation_forward(key_index=...)"""
+    from oracle import relation_np as R
+    g = golden('relation_fpn_n90_k70')
+    c = R.make_relation_case(int(g['seed']), int(g['N']), int(g['d']), int(g['H']), init='fan_in')
+    assert abs(checksum(c) - float(g['input_checksum'])) <= 1e-6 * abs(float(g['input_checksum']))
+    args = [c[k] for k in ('X', 'boxes', 'Wq', 'bq', 'Wk', 'bk', 'Wg', 'bg', 'Wout', 'bout')]
+    out = R.relation_forward(*args, key_index=g['non_gt_index'], group=int(g['H']), residual_relu=False, dtype=np.float32)
+    assert rel_err(out, g['attention']) < 2e-5
+    pm = R.position_matrix(c['boxes'], key_index=g['non_gt_index'])[:8]
+    assert rel_err(pm, g['position_matrix']) < 1e-6
