@@ -106,6 +106,30 @@ def learn_nms_case(ns, name, seed, R, C, init, first_n):
     print(name, 'multi', multi.shape, float(multi.max()), 'nonzero classes', int((multi.max(axis=(0, 2)) > 0).sum()))
 
 
+def learn_nms_nongt_case(ns, name, seed, R, C, first_n, n_keep):
+    """FPN form of the op: has_non_gt_index=True, the 20th input is the index list (LNMS:260-283), train-time means/stds"""
+    shim = ns.mxshim
+    c = learn_nms_np.make_learn_nms_case(seed, R=R, C=C, init='fan_in')
+    rng = np.random.default_rng(seed + 500)
+    idx = np.sort(rng.permutation(R)[:n_keep]).astype(np.float32)
+    prop = ns.learn_nms.LearnNmsProp(num_fg_classes=str(C), bbox_means='[0.0 0.0 0.0 0.0]', bbox_stds='[0.1 0.1 0.2 0.2]',
+                                     first_n=str(first_n), class_agnostic='True', num_thresh='5', class_thresh='0.01',
+                                     nongt_dim='None', has_non_gt_index='True')
+    op = prop.create_operator(None, None, None)
+    names = prop.list_arguments()
+    vals = dict(cls_score=c['cls_score'], bbox_pred=c['bbox_pred'], rois=c['rois'], im_info=c['im_info'],
+                fc_all_2_relu=c['feat'], non_gt_index=idx, **c['P'])
+    in_data = [shim.ND(vals[k]) for k in names]
+    _, out_shapes = prop.infer_shape([v.shape for v in in_data])
+    out_data = [shim.ND(np.zeros(s, np.float32)) for s in out_shapes]
+    op.forward(False, ['write'] * 3, in_data, out_data, [])
+    multi, sbbox, sscore = (o.a for o in out_data)
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), R=R, C=C, first_n=first_n, seed=seed, non_gt_index=idx.astype(np.int32),
+                        means=np.zeros(4, np.float32), stds=np.array([0.1, 0.1, 0.2, 0.2], np.float32),
+                        input_checksum=checksum(dict(c, **c['P'])), nms_multi_score=multi, sorted_bbox=sbbox, sorted_score=sscore)
+    print(name, 'multi', multi.shape, float(multi.max()), 'args', len(names))
+
+
 def proposal_case(ns, name, seed, H, W, im_info, pre, post, scales=(4, 8, 16, 32)):
     shim = ns.mxshim
     A = 3 * len(scales)
@@ -237,6 +261,7 @@ def main():
     nms_multi_target_case(ns, 'nms_multi_target')
     ohem_case(ns, 'box_annotator_ohem')
     relation_fpn_case(ns, 'relation_fpn_n90_k70', 5, 90, 256, 4, 70)
+    learn_nms_nongt_case(ns, 'learn_nms_nongt_index', 13, 80, 8, 30, 64)
 
 
 if __name__ == '__main__':

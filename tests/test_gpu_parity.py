@@ -407,3 +407,25 @@ def test_relation_fpn_form_matches_reference_execution(ops):
         e = rel_err(out.cpu().numpy(), g['attention'])
         print('fpn form [%s] %.2e' % (prec, e))
         assert e <= (3e-4 if prec == 'fp32' else 1e-3)
+
+
+def test_learn_nms_non_gt_index_form_matches_reference_execution(ops):
+    """FPN form of learn_nms (non_gt_index list + means/stds) on the device, through ops and through the CustomOp surface"""
+    import relnet_b200
+    g = golden('learn_nms_nongt_index')
+    c = L.make_learn_nms_case(int(g['seed']), R=int(g['R']), C=int(g['C']), init='fan_in')
+    w = {k: T(v) for k, v in c['P'].items()}
+    idx = torch.from_numpy(g['non_gt_index'].astype(np.int32)).cuda()
+    for prec in precisions(ops):
+        multi, sbbox, sscore, _ = ops.learn_nms(T(c['cls_score']), T(c['bbox_pred']), T(c['rois']), T(c['im_info']), T(c['feat']),
+                                                w, first_n=int(g['first_n']), means=tuple(g['means']), stds=tuple(g['stds']),
+                                                non_gt_index=idx, precision=prec)
+        np.testing.assert_allclose(sscore.cpu().numpy(), g['sorted_score'], rtol=2e-5, atol=1e-8)
+        np.testing.assert_allclose(sbbox.cpu().numpy(), g['sorted_bbox'], rtol=1e-5, atol=2e-3)
+        assert rel_err(multi.cpu().numpy(), g['nms_multi_score']) < 1e-3
+    out = relnet_b200.compat.Custom(op_type='learn_nms', num_fg_classes=int(g['C']), bbox_means='[0.0 0.0 0.0 0.0]',
+                                    bbox_stds='[0.1 0.1 0.2 0.2]', first_n=int(g['first_n']), class_agnostic=True, num_thresh=5,
+                                    class_thresh=0.01, nongt_dim=None, has_non_gt_index=True, cls_score=T(c['cls_score']),
+                                    bbox_pred=T(c['bbox_pred']), rois=T(c['rois']), im_info=T(c['im_info']),
+                                    fc_all_2_relu=T(c['feat']), non_gt_index=idx.float(), **w)
+    assert rel_err(out[0].cpu().numpy(), g['nms_multi_score']) < 1e-3

@@ -261,3 +261,14 @@ def test_relation_oracle_matches_fpn_reference_execution():
     assert rel_err(out, g['attention']) < 2e-5
     pm = R.position_matrix(c['boxes'], key_index=g['non_gt_index'])[:8]
     assert rel_err(pm, g['position_matrix']) < 1e-6
+
+
+def test_learn_nms_oracle_matches_reference_execution_non_gt_index():
+    """FPN form of the op (has_non_gt_index=True, 20 inputs, train-time means/stds): LNMS:260-283"""
+    g = golden('learn_nms_nongt_index')
+    c = L.make_learn_nms_case(int(g['seed']), R=int(g['R']), C=int(g['C']), init='fan_in')
+    multi, sbbox, sscore, _ = L.learn_nms_forward(c['cls_score'], c['bbox_pred'], c['rois'], c['im_info'], c['feat'], c['P'],
+                                                  first_n=int(g['first_n']), num_fg_classes=int(g['C']), means=g['means'],
+                                                  stds=g['stds'], non_gt_index=g['non_gt_index'])
+    assert np.array_equal(sscore, g['sorted_score']) and np.abs(sbbox - g['sorted_bbox']).max() <= 1e-4
+    assert rel_err(multi, g['nms_multi_score']) < 2e-5
