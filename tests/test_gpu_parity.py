@@ -411,7 +411,7 @@ def test_relation_fpn_form_matches_reference_execution(ops):
 
 def test_learn_nms_non_gt_index_form_matches_reference_execution(ops):
     """FPN form of learn_nms (non_gt_index list + means/stds) on the device, through ops and through the CustomOp surface"""
-    import relnet_b200
+    from relnet_b200 import compat
     g = golden('learn_nms_nongt_index')
     c = L.make_learn_nms_case(int(g['seed']), R=int(g['R']), C=int(g['C']), init='fan_in')
     w = {k: T(v) for k, v in c['P'].items()}
@@ -423,7 +423,7 @@ def test_learn_nms_non_gt_index_form_matches_reference_execution(ops):
         np.testing.assert_allclose(sscore.cpu().numpy(), g['sorted_score'], rtol=2e-5, atol=1e-8)
         np.testing.assert_allclose(sbbox.cpu().numpy(), g['sorted_bbox'], rtol=1e-5, atol=2e-3)
         assert rel_err(multi.cpu().numpy(), g['nms_multi_score']) < 1e-3
-    out = relnet_b200.compat.Custom(op_type='learn_nms', num_fg_classes=int(g['C']), bbox_means='[0.0 0.0 0.0 0.0]',
+    out = compat.Custom(op_type='learn_nms', num_fg_classes=int(g['C']), bbox_means='[0.0 0.0 0.0 0.0]',
                                     bbox_stds='[0.1 0.1 0.2 0.2]', first_n=int(g['first_n']), class_agnostic=True, num_thresh=5,
                                     class_thresh=0.01, nongt_dim=None, has_non_gt_index=True, cls_score=T(c['cls_score']),
                                     bbox_pred=T(c['bbox_pred']), rois=T(c['rois']), im_info=T(c['im_info']),
