@@ -263,12 +263,14 @@ int cast_f32_f16(cudaStream_t st, const float* src, __half* dst, size_t n) {
 }
 
 size_t gemm_tc_workspace_bytes(int M, int N, int K) {
-  // worst case split-K partials
-  const int tiles = cdiv(M, kBM) * cdiv(N, 64);
-  int splits = 1;
+  // worst case split-K partials over both tile widths the launcher may pick
   const int kb = cdiv(K, kBK);
   const int sms = 148;
-  if (tiles < sms) splits = std::min(std::max(sms / tiles, 1), std::max(kb / 4, 1));
+  int splits = 1;
+  for (int bn = 64; bn <= 128; bn *= 2) {
+    const int tiles = cdiv(M, kBM) * cdiv(N, bn);
+    if (tiles < sms) splits = std::max(splits, std::min(std::max(sms / tiles, 1), std::max(kb / 4, 1)));
+  }
   return splits > 1 ? ws_slice((size_t)splits * M * N, 4) : 0;
 }
 
@@ -293,11 +295,12 @@ int gemm_tc(cudaStream_t st, const __half* A, long long lda, const __half* B, lo
                "gemm_tc: operand pitch must be a multiple of 8 halfs and 16-byte aligned (lda=%lld ldb=%lld)", lda, ldb);
   const int sms = sm_count() > 0 ? sm_count() : 148;
   const int tiles_m = cdiv(M, kBM);
-  // BN = 64 when 128-wide tiles would leave most SMs idle
-  const bool bn64 = (tiles_m * cdiv(N, 128) < sms / 2) || N <= 64;
+  // BN = 64 when 128-wide tiles would leave most SMs idle -- unless K is long (fc_new_1: K = 12544): then split-K fills the
+  // machine anyway and the 128-wide tile moves a third fewer operand bytes per output (per-SM L2 ingest is the bound)
+  const int kb = cdiv(K, kBK);
+  const bool bn64 = ((tiles_m * cdiv(N, 128) < sms / 2) && kb < 64) || N <= 64;
   const int BN = bn64 ? 64 : 128;
   const int tiles = tiles_m * cdiv(N, BN);
-  const int kb = cdiv(K, kBK);
   // split K only when every split keeps >= 16 K-blocks (1024 of K): below that the separate reduce launch (~3-4 us)
   // costs more than the K loop it shortens (measured: fc_new_2 / cls_score / embedding GEMMs at M = 300, K = 1024)
   int splits = 1;
