@@ -369,7 +369,8 @@ def main():
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f16' if prec == 'f16' else 'f32', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'global_batch': world, 'parallelism': 'replicas x%d (1 image/GPU)' % world, 'launch': 'one CUDA-graph replay per image',
-                       'trunk': 'torch/cuDNN bf16 channels_last ResNet-101 (library, out of scope)',
+                       'trunk': 'ResNet-101 convolutions on cuDNN (bf16 channels_last, fused conv+bias+relu calls; library, out of scope) with our '
+                                'space-to-depth stem input, max-pool and RPN-head kernels around them',
                        'hot_path_precision': prec, 'l2': 'inputs (7.2 MB image) + 180 MB of trunk activations per step '
                        'exceed the 126 MB L2; relation kernel timed with an explicit 256 MB L2 flush'},
             'e2e': {'value': round(world * args.steps / (ms_e2e / 1e3), 3), 'unit': 'images/sec',
