@@ -367,6 +367,9 @@ int rn_maxpool3x3s2_nhwc_bf16(const void* in_nhwc, int32_t H, int32_t W, int32_t
 /* ---------------------------------------------------------------------------------------------------------------
  * tcgen05 self-test (sm_100a only): runs one 128x128x64 K-major and one 128x64x128 MN-major-B UMMA through TMA/TMEM and
  * writes the fp32 results to out_s [128,128], out_o [128,64] for checking against a host product. */
+/* measurement hook (tools/tile_trace.py): per-CTA clock64() stamps of relation_attn_tile_kernel into `buffer` (device memory,
+ * 8 x int64 per CTA); NULL switches it off */
+int rn_debug_tile_trace(void* buffer);
 int rn_umma_selftest(const void* a_f16, const void* b_f16, const void* p_f16, const void* v_f16, float* out_s,
                      float* out_o, rn_stream_t stream);
 

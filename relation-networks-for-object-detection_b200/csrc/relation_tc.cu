@@ -292,11 +292,14 @@ __global__ void __launch_bounds__(192, 1) relation_attn_tc_kernel(const __grid_c
 constexpr int kTileBar = 16384 * 3 + 32768;            // Q, K, V', P
 constexpr int kTileSmem = kTileBar + 128 + 1024;
 
+static long long* g_tile_trace = nullptr;      // set by rn_debug_tile_trace (measurement only)
+
 struct TileParams {
   AttnParams a;
   int splits;                    // key tiles per query tile (gridDim.x = qtiles * splits)
   float* part_o;                 // [splits][B][H][N][64] un-normalised partial outputs
   float* part_ml;                // [splits][B][H][N][2]  (row max in log2 units, row sum)
+  long long* trace;              // debug: per-CTA clock64() stamps at 8 points of the dependent chain (nullptr = off)
 };
 
 // 288 threads: warps 0..7 are the softmax / epilogue warps -- TWO threads per query row (warp w and w + 4 share the TMEM lane
@@ -320,6 +323,8 @@ __global__ void __launch_bounds__(288, 2) relation_attn_tile_kernel(const __grid
   const int qt = blockIdx.x / tp.splits, kt = blockIdx.x % tp.splits;
   const int q0 = qt * 128, m0 = kt * 128, h = blockIdx.y, b = blockIdx.z;
   if (p.active && !p.active[b]) return;          // uniform for the whole CTA, before any barrier / TMEM allocation
+  long long* tr = tp.trace ? tp.trace + 8 * ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) : nullptr;
+  if (tr && threadIdx.x == 0) tr[0] = clock64();
   if (p.gidx && threadIdx.x < 128) {
     const int m = m0 + threadIdx.x, nq = q0 + threadIdx.x;
     s_gidx[threadIdx.x] = m < p.M ? p.gidx[(size_t)m * p.gs_i + (size_t)b * p.gs_b] : 0;
@@ -344,10 +349,12 @@ __global__ void __launch_bounds__(288, 2) relation_attn_tile_kernel(const __grid
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base, tPV = tmem_base + 128;
+  if (tr && threadIdx.x == 0) tr[1] = clock64();          // prologue done (barriers, TMEM allocation, first sync)
 
   if (warp == 8) {
     if (lane == 0) {
       mbar_wait(ld_full, 0);
+      if (tr) tr[2] = clock64();                            // Q / K / V' tiles landed
       tc_fence_after();
       const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aP = smem_u32(sP), aV = smem_u32(sV);
 #pragma unroll
@@ -388,7 +395,9 @@ __global__ void __launch_bounds__(288, 2) relation_attn_tile_kernel(const __grid
         t[q] = t4.x; t[q + 1] = t4.y; t[q + 2] = t4.z; t[q + 3] = t4.w;
       }
     }
+    if (tr && threadIdx.x == 0) tr[3] = clock64();          // geometry row half loaded (issued) by thread 0
     mbar_wait(s_full, 0);
+    if (tr && threadIdx.x == 0) tr[4] = clock64();          // S = Q K^T visible
     tc_fence_after();
     float mx = -INFINITY;
 #pragma unroll
@@ -423,7 +432,9 @@ __global__ void __launch_bounds__(288, 2) relation_attn_tile_kernel(const __grid
     fence_proxy_async_smem();
     tc_fence_before();
     mbar_arrive(p_full);
+    if (tr && threadIdx.x == 0) tr[5] = clock64();          // P written (this thread)
     mbar_wait(pv_full, 0);
+    if (tr && threadIdx.x == 0) tr[6] = clock64();          // O = P V' visible
     tc_fence_after();
     asm volatile("bar.sync 1, 256;" ::: "memory");       // both halves' row sums are in shared memory
     lsum += s_sum[half ^ 1][r];
@@ -462,6 +473,7 @@ __global__ void __launch_bounds__(288, 2) relation_attn_tile_kernel(const __grid
   }
   tc_fence_before();
   __syncthreads();
+  if (tr && threadIdx.x == 0) tr[7] = clock64();            // epilogue stores issued, CTA about to retire
   if (warp == 8) tmem_dealloc<256>(tmem_base);
 }
 
@@ -654,7 +666,7 @@ int relation_tc_packed(const rn_relation_desc* d, const float* X, const float* b
   }
   if (T <= kMaxTileSplits) {
     TileParams tp;
-    tp.a = p; tp.splits = T; tp.part_o = part_o; tp.part_ml = part_ml;
+    tp.a = p; tp.splits = T; tp.part_o = part_o; tp.part_ml = part_ml; tp.trace = g_tile_trace;
     relation_attn_tile_kernel<<<dim3(cdiv(N, 128) * T, H, B), 288, kTileSmem, st>>>(tmQ, tmK, tmV, tp);
     RN_LAUNCH_CHECK();
     if (T > 1) {
@@ -792,3 +804,10 @@ int relation_tc_lnms(const rn_relation_desc* d, const float* X, const float* emb
   return relation_tc_packed(d, X, nullptr, nullptr, packed, nullptr, nullptr, out, gws, gws_bytes, st, 7, &g2);
 }
 }  // namespace rn
+
+// measurement hook: when `buffer` (device, 8 int64 per CTA of the next relation_attn_tile_kernel launches) is non-null, every
+// CTA records clock64() at 8 points of its dependent chain; pass NULL to switch it off.  Not part of the product path.
+extern "C" int rn_debug_tile_trace(void* buffer) {
+  rn::g_tile_trace = (long long*)buffer;
+  return RN_OK;
+}
