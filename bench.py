@@ -55,16 +55,42 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region: NVML (a few ms per sample, so even a 35 ms region gets
+    several) with the nvidia-smi query of the profiling recipe as the fallback."""
     Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+    NAMES = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rows, self.stop_flag, self.source = index, [], False, 'nvidia-smi'
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = (pynvml, pynvml.nvmlDeviceGetHandleByIndex(index))
+            self.source = 'nvml'
+        except Exception:
+            self.nvml = None
+
+    def sample_nvml(self):
+        nv, h = self.nvml
+        sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        flags = [bool(r & nv.nvmlClocksThrottleReasonHwSlowdown), bool(r & nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                 bool(r & nv.nvmlClocksThrottleReasonSwThermalSlowdown), bool(r & nv.nvmlClocksThrottleReasonSwPowerCap)]
+        return [str(sm), str(mx)] + ['Active' if f else 'Not Active' for f in flags]
 
     def run(self):
         while not self.stop_flag:
+            try:
+                if self.nvml is not None:
+                    self.rows.append(self.sample_nvml())
+                    time.sleep(0.004)
+                    continue
+            except Exception:
+                self.nvml, self.source = None, 'nvidia-smi'          # fall back for the rest of the run
             try:
                 out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
                                       '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
@@ -79,9 +105,9 @@ class ClockSampler(threading.Thread):
         if not self.rows:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
         sm = sorted(float(r[0]) for r in self.rows)
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith('active') for r in self.rows)]
-        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=float(self.rows[0][1]), reasons=reasons, samples=len(self.rows))
+        reasons = [n for i, n in enumerate(self.NAMES) if any(r[2 + i].lower().startswith('active') for r in self.rows)]
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=float(self.rows[0][1]), reasons=reasons, samples=len(self.rows),
+                    source=self.source)
 
 
 def make_inputs(seed=0):
