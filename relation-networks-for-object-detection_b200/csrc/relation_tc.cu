@@ -387,6 +387,8 @@ __global__ void __launch_bounds__(288, 2) relation_attn_tile_kernel(const __grid
 #pragma unroll
       for (int q = 0; q < 64; ++q) t[q] = (m0 + c0 + q < p.M) ? __ldg(col0 + (size_t)s_gidx[c0 + q] * p.ldg) : -INFINITY;
     } else {
+      // query-major rows, float4 per lane.  (A key-major table with one coalesced scalar load per key was tried: 64 load
+      // instructions per thread instead of 16 made this section slower, 2.8 k -> 4.9 k cycles; profiles/r01_tile_trace_n300.txt)
       const float* lg_row = p.lg + (((size_t)b * p.H + h) * p.N + (row_ok ? n : 0)) * p.ldg + m0 + c0;
 #pragma unroll
       for (int q = 0; q < 64; q += 4) {
@@ -447,14 +449,22 @@ __global__ void __launch_bounds__(288, 2) relation_attn_tile_kernel(const __grid
 #pragma unroll
       for (int q = 0; q < 32; ++q) o[q] = __uint_as_float(v[q]);
     }
-    if (row_ok) {
-      if (tp.splits > 1) {
-        const size_t row = (((size_t)kt * gridDim.z + b) * p.H + h) * p.N + n;
-        float4* dst = reinterpret_cast<float4*>(tp.part_o + row * 64 + half * 32);
+    if (tp.splits > 1) {
+      // partial outputs: transpose the warp's 32 rows x 32 columns through shared memory (the Q / K / V' tiles are dead
+      // once O is visible) so that each store instruction writes 128 contiguous bytes of ONE row instead of 16 bytes of
+      // 32 different rows (2.5 k of the 9.7 k cycles of a CTA went into that, profiles/r01_tile_trace_n300.txt)
+      float* tw = reinterpret_cast<float*>(smem) + warp * (32 * 33);
 #pragma unroll
-        for (int q = 0; q < 32; q += 4) dst[q >> 2] = make_float4(o[q], o[q + 1], o[q + 2], o[q + 3]);
-        if (half == 0) reinterpret_cast<float2*>(tp.part_ml)[row] = make_float2(mx, lsum);
-      } else {
+      for (int q = 0; q < 32; ++q) tw[lane * 33 + q] = o[q];
+      __syncwarp();
+      const int row_base = q0 + (warp & 3) * 32;
+      const size_t prow0 = (((size_t)kt * gridDim.z + b) * p.H + h) * p.N;
+#pragma unroll 4
+      for (int rr = 0; rr < 32; ++rr)
+        if (row_base + rr < p.N) tp.part_o[(prow0 + row_base + rr) * 64 + half * 32 + lane] = tw[rr * 33 + lane];
+      if (row_ok && half == 0) reinterpret_cast<float2*>(tp.part_ml)[prow0 + n] = make_float2(mx, lsum);
+    } else if (row_ok) {
+      {
         const float inv = 1.f / lsum;
         const int col0 = half * 32;
         float* dst = p.out + ((size_t)b * p.N + n) * p.ldo + (size_t)h * p.dv;
