@@ -96,6 +96,11 @@ int rn_linear_fwd(const float* x, const float* W, const float* b, float* y, int3
 /* Pre-packed fp16 operands for RN_PREC_F16: pack once per weight update (one small kernel), reuse every forward.
  * The packed relation block is [Wq; Wk; Wout padded to 64 cols/head] as fp16 [3*H*64, ceil8(d)] followed by the fp32
  * bias [bq; bk; bout padded]; the packed linear weight is fp16 [out, ceil8(in)]. */
+/* RN_PREC_F16 has two decompositions of the N x M part, both tcgen05: the FUSED one (default: pair geometry + pair FC +
+ * QK^T + softmax + P.V' in one cooperative launch, relation_fused.cu) and the round-1 one (geometry table [B,H,N,M] in
+ * HBM -> tile attention -> combine).  rn_relation_fused_enable(0) selects the latter for A/B measurements (process-wide;
+ * also RN_RELATION_UNFUSED=1 in the environment); returns the previous setting. */
+int rn_relation_fused_enable(int32_t on);
 size_t rn_relation_packed_bytes(const rn_relation_desc* desc);
 int rn_relation_pack(const rn_relation_desc* desc, const float* Wq, const float* bq, const float* Wk, const float* bk,
                      const float* Wout, const float* bout, void* packed, rn_stream_t stream);
@@ -367,9 +372,6 @@ int rn_maxpool3x3s2_nhwc_bf16(const void* in_nhwc, int32_t H, int32_t W, int32_t
 /* ---------------------------------------------------------------------------------------------------------------
  * tcgen05 self-test (sm_100a only): runs one 128x128x64 K-major and one 128x64x128 MN-major-B UMMA through TMA/TMEM and
  * writes the fp32 results to out_s [128,128], out_o [128,64] for checking against a host product. */
-/* measurement hook (tools/tile_trace.py): per-CTA clock64() stamps of relation_attn_tile_kernel into `buffer` (device memory,
- * 8 x int64 per CTA); NULL switches it off */
-int rn_debug_tile_trace(void* buffer);
 int rn_umma_selftest(const void* a_f16, const void* b_f16, const void* p_f16, const void* v_f16, float* out_s,
                      float* out_o, rn_stream_t stream);
 

@@ -69,7 +69,7 @@ SIGNATURES = {
     'rn_rpn_head_fwd': (C.c_int, [c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     'rn_image_s2d_bf16': (C.c_int, [c_p, c_i, c_i, c_i, c_p, c_p]),
     'rn_maxpool3x3s2_nhwc_bf16': (C.c_int, [c_p, c_i, c_i, c_i, c_p, c_p]),
-    'rn_debug_tile_trace': (C.c_int, [c_p]),
+    'rn_relation_fused_enable': (C.c_int, [c_i]),
     'rn_pos_embed_fwd': (C.c_int, [c_p, c_p, c_i, c_i, c_i, c_f, c_p, c_p, c_p]),
     'rn_geometry_weight_fwd': (C.c_int, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_p, c_p, c_p, c_p]),
     'rn_linear_workspace_bytes': (c_sz, [c_i, c_i, c_i, c_i]),

@@ -34,6 +34,20 @@ class PositionEmbedding(object):
                              wave_length=float(self.wave_length), want_eps=False)[1]
 
 
+class LazySoftmax(object):
+    """The second output of attention_module_nms_multi_head (aff_softmax).  The reference returns it from the graph
+    function but the learn-NMS head never reads it (SYM_REL_NMS:486 takes only the first output); it is therefore
+    computed on demand: ``materialize()`` runs the library's fp32 path, which is the one that writes the softmax."""
+
+    def __init__(self, fn):
+        self._fn, self._value = fn, None
+
+    def materialize(self):
+        if self._value is None:
+            self._value = self._fn()
+        return self._value
+
+
 class RelationSymbols(object):
     """``params``: dict name -> CUDA tensor with the checkpoint names the reference uses
     ('pair_pos_fc1_1_weight', 'query_1_weight', 'key_1_bias', 'linear_out_1_weight', ...)."""
@@ -68,23 +82,28 @@ class RelationSymbols(object):
                             precision=self.precision)
 
     def attention_module_nms_multi_head(self, roi_feat, position_mat, num_rois, dim=(1024, 1024, 128), fc_dim=(64, 16),
-                                        feat_dim=128, group=16, index=1, return_softmax=True):
+                                        feat_dim=128, group=16, index=1, return_softmax='lazy'):
         """SYM_REL_NMS:158-238 / LNMS:45-127.  roi_feat [num_rois, num_fg_classes, feat_dim]; position_mat is built from
         sorted boxes [num_rois, num_fg_classes, 4] (a lazy PositionMatrix over them or the boxes themselves).
-        Returns (output [num_rois, num_fg_classes, dim[2]], aff_softmax [num_fg_classes*fc_dim[1], num_rois, num_rois])."""
+        Returns (output [num_rois, num_fg_classes, dim[2]], aff_softmax [num_fg_classes*fc_dim[1], num_rois, num_rois]).
+        return_softmax: 'lazy' (default) -> the output comes from the configured precision (tcgen05 under f16) and
+        aff_softmax is a LazySoftmax handle; True -> both eagerly from the fp32 path; False -> (output, None)."""
         assert dim[0] == dim[1], 'Matrix multi requires the same dims!'
         assert fc_dim[1] == group, 'Check the dimensions in attention!'
         P, i = self.params, str(index)
         boxes = position_mat.bbox if isinstance(position_mat, PositionMatrix) else position_mat
         X = roi_feat.permute(1, 0, 2).contiguous()          # [C, n, feat]
         B = boxes.permute(1, 0, 2).contiguous()             # [C, n, 4]
-        res = ops.relation(X, B, P['nms_query_' + i + '_weight'], P['nms_query_' + i + '_bias'],
-                           P['nms_key_' + i + '_weight'], P['nms_key_' + i + '_bias'],
-                           P['nms_pair_pos_fc1_' + i + '_weight'], P['nms_pair_pos_fc1_' + i + '_bias'],
-                           P['nms_linear_out_' + i + '_weight'], P['nms_linear_out_' + i + '_bias'], group=group,
-                           precision='fp32' if return_softmax else self.precision, return_softmax=return_softmax)
-        if return_softmax:
-            out, sm = res                                     # sm [C, n, H, n] -> [C*H, n, n]
-            sm = sm.permute(0, 2, 1, 3).reshape(-1, num_rois, num_rois)
-            return out.permute(1, 0, 2).contiguous(), sm
-        return res.permute(1, 0, 2).contiguous(), None
+        w = (P['nms_query_' + i + '_weight'], P['nms_query_' + i + '_bias'],
+             P['nms_key_' + i + '_weight'], P['nms_key_' + i + '_bias'],
+             P['nms_pair_pos_fc1_' + i + '_weight'], P['nms_pair_pos_fc1_' + i + '_bias'],
+             P['nms_linear_out_' + i + '_weight'], P['nms_linear_out_' + i + '_bias'])
+
+        def eager():
+            out, sm = ops.relation(X, B, *w, group=group, precision='fp32', return_softmax=True)
+            return out.permute(1, 0, 2).contiguous(), sm.permute(0, 2, 1, 3).reshape(-1, num_rois, num_rois)   # [C*H, n, n]
+
+        if return_softmax is True:
+            return eager()
+        out = ops.relation(X, B, *w, group=group, precision=self.precision).permute(1, 0, 2).contiguous()
+        return out, (LazySoftmax(lambda: eager()[1]) if return_softmax == 'lazy' else None)

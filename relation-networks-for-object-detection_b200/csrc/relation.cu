@@ -184,9 +184,10 @@ int relation_fp32(const rn_relation_desc* d, const float* X, const float* boxes,
 
 extern "C" size_t rn_relation_workspace_bytes(const rn_relation_desc* d) {
   if (!d) return 0;
-  size_t a = rn::relation_fp32_ws_bytes(d);
-  size_t b = rn::relation_tc_workspace_bytes(d);
-  return (a > b ? a : b) + 256;
+  // the two precisions have disjoint layouts: size for the one the descriptor asks for (the fused tcgen05 path keeps
+  // nothing N x M, so its workspace stays small at any N)
+  if (d->precision == RN_PREC_F16) return rn::relation_tc_workspace_bytes(d) + 256;
+  return rn::relation_fp32_ws_bytes(d) + 256;
 }
 
 extern "C" int rn_relation_fwd(const rn_relation_desc* d, const float* X, const float* boxes, const int32_t* key_index,

@@ -1,0 +1,629 @@
+// relation_fused.cu -- ONE launch for the whole N x M part of the object-relation module (SYM_REL:30-151 after the
+// Q/K/V' projections): pair geometry eps -> sinusoid embedding phi -> 64->H pair FC -> max(.,1e-6) -> scores QK^T ->
+// softmax -> P.V' -> (+residual, relu).  Nothing N x M ever reaches HBM; the only inter-SM traffic is a short-lived,
+// L2-resident ring of fp16 geometry weights.
+//
+// Why a team of CTAs.  phi (4 log + 32 sincos per pair) is shared by all H heads, but the outputs of H heads do not
+// fit one SM (H x 64 fp32 accumulator columns = 1024 > 512 TMEM columns).  So H CTAs (one per head, one CTA per SM)
+// form a TEAM that walks the same (query tile, key tile) blocks in lock step.  For a 128 x 128 block, member h
+//   1. PRODUCES: evaluates phi for the 128 queries x (128/H) keys of its slice, 4 threads per pair writing the fp16 hi/lo
+//      rows of the A operand straight into SWIZZLE_128B shared memory; 12 tcgen05.mma (M=128 pairs, N=16 heads, K=64:
+//      A_hi.W_hi + A_lo.W_hi + A_hi.W_lo, fp32-accurate) give all H heads of a key at once; g = max(x+b,1e-6) is
+//      scaled by a power of two (from sum|Wg| so it sits in fp16's normal range), rounded to fp16 and written to the
+//      team's ring slot as [producer][consumer head][query][key] -- coalesced 16-byte stores;
+//   2. CONSUMES: waits for the team counter, reads its own head's 128 x 128 g tile (coalesced 16-byte L2 loads),
+//      S = Q K^T by tcgen05 (TMA operands), p = g . exp2(s/sqrt(dk) - rowmax) -- softmax(log g + s) without a log per
+//      element -- online softmax across key tiles, P (fp16, SWIZZLE_128B) -> tcgen05 P.V' (V' MN-major), O in
+//      registers (16 columns per thread, 4 threads per query row).
+// Team members only ever wait for teammates, the launch is cooperative (all CTAs co-resident), and every wait is for an
+// event that does not depend on the waiter's own later work, so the schedule cannot deadlock.
+// Key ranges: with few query tiles (N = 300) the key tiles are split over several teams; un-normalised partials
+// (O, m, l) go to the workspace and the last team to finish a (query tile, head) merges them in the same launch.
+#include "common.cuh"
+#include "geom.cuh"
+#include "relation.cuh"
+#include "umma.cuh"
+#include <algorithm>
+
+namespace rn {
+using namespace umma;
+
+constexpr int kFThreads = 544;              // 16 compute warps + 1 TMA/UMMA warp
+constexpr int kFSlots = 4;                  // ring depth of the g exchange (blocks in flight per team)
+constexpr int kOffQ = 0, kOffK = 16384, kOffV = 49152, kOffP = 81920, kOffA = 114688, kOffB = 180224,
+              kOffBar = 184320;
+constexpr int kFSmem = kOffBar + 256 + 1024;
+constexpr int kStagePitch = 68;             // floats per row of the output staging tile (aliases the A buffers)
+
+struct FusedParams {
+  int B, N, M, H, dv;
+  int QT, T, R, Tr;                         // query tiles, key tiles, key ranges, key tiles per range
+  int teams, ntasks;
+  const float* boxes; const int* key_index;
+  const float* Wg; const float* bg; float rdim[8];  // rdim = 1 / wave_length^(k/8) (kept in the constant bank, not in registers)
+  float scale_log2;                         // log2(e) / sqrt(dk)
+  const float* X; int ldx; float* out; int ldo; __half* out16; int ldo16; int relu;
+  __half* gslots;                           // [teams][kFSlots][H producers][H consumers][128 queries][128/H keys]
+  unsigned* counters;                       // [teams][32] = published[16], consumed[16] PER MEMBER ; then tickets [B*QT*H]
+  float* part_o; float* part_ml;            // [R][B][H][N][64], [R][B][H][N][2]
+};
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
+__device__ __forceinline__ void sincos_2pi_f(float x, float* s, float* c) {
+  const float n = rintf(x * 0.15915494309189535f);
+  float r = fmaf(n, -6.2831854820251465f, x);
+  r = fmaf(n, 1.7484555e-7f, r);
+  *s = __sinf(r);
+  *c = __cosf(r);
+}
+// two fp32 values -> packed fp16 hi and the packed fp16 residual
+__device__ __forceinline__ void split2_f(float v0, float v1, uint32_t* hi, uint32_t* lo) {
+  const __half2 H2 = __floats2half2_rn(v0, v1);
+  const float2 hf = __half22float2(H2);
+  const __half2 L2 = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+  *hi = *reinterpret_cast<const uint32_t*>(&H2);
+  *lo = *reinterpret_cast<const uint32_t*>(&L2);
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x4f(uint32_t taddr, uint32_t (&v)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
+}
+
+__global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                      const __grid_constant__ CUtensorMap tmK,
+                                                                      const __grid_constant__ CUtensorMap tmV,
+                                                                      const FusedParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  uint8_t* sQ = smem + kOffQ;
+  uint8_t* sK = smem + kOffK;               // 2 x 16 KB
+  uint8_t* sV = smem + kOffV;               // 2 x 16 KB
+  uint8_t* sP = smem + kOffP;               // 32 KB: two [128 x 64-key] halves
+  uint8_t* sA = smem + kOffA;               // 2 x (hi 16 KB + lo 16 KB)
+  uint8_t* sBh = smem + kOffB; uint8_t* sBl = sBh + 2048;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint64_t* q_full = bars;                  // [1]
+  uint64_t* k_full = bars + 1;              // [2]
+  uint64_t* v_full = bars + 3;              // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_full = bars + 6;
+  uint64_t* pv_full = bars + 7;
+  uint64_t* a_full = bars + 8;              // [2]
+  uint64_t* a_free = bars + 10;             // [2]
+  uint64_t* g_full = bars + 12;
+  uint64_t* g_free = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  __shared__ float s_mx[4][128], s_sum[4][128];
+  __shared__ float s_bias[16], s_rowabs[16];
+  __shared__ float s_gscale;
+  __shared__ int s_last;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int H = p.H, ks = 128 / H, rounds = ks >> 3;
+  const int team = blockIdx.x / H, h = blockIdx.x % H;
+  // per-member progress counters (an aggregate count cannot express "EVERY member has ..."): member m has published
+  // pub_ctr[m] blocks and finished reading done_ctr[m] blocks; 16 + 16 words = one 128-byte line per team
+  unsigned* pub_ctr = p.counters + 32 * team;
+  unsigned* done_ctr = pub_ctr + 16;
+  unsigned* tickets = p.counters + 32 * p.teams;
+
+  // ------------------------------------------------------------------------------------------------ prologue
+  if (warp == 16) {
+    if (lane == 0) {
+      prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
+      mbar_init(q_full, 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&a_full[i], 512); mbar_init(&a_free[i], 1);
+      }
+      mbar_init(s_full, 1); mbar_init(p_full, 512); mbar_init(pv_full, 1); mbar_init(g_full, 1); mbar_init(g_free, 512);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<512>(tmem_slot);
+  } else {
+    // B operand of the pair FC: Wg [16 head rows (>= H zero)] x [64] as fp16 hi / lo, K-major SWIZZLE_128B
+    if (tid < 128) {
+      const int row = tid >> 3, chunk = tid & 7;
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float w0 = row < H ? p.Wg[row * 64 + chunk * 8 + 2 * j] : 0.f;
+        const float w1 = row < H ? p.Wg[row * 64 + chunk * 8 + 2 * j + 1] : 0.f;
+        split2_f(w0, w1, &hi[j], &lo[j]);
+      }
+      *reinterpret_cast<uint4*>(sBh + sw128_offset(row, chunk)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(sBl + sw128_offset(row, chunk)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+    // per-head bound sum|Wg[h,:]| + |bg[h]| (fixed summation order: every CTA gets the same bits)
+    {
+      float a = 0.f;
+      if (warp < H) a = fabsf(p.Wg[warp * 64 + lane]) + fabsf(p.Wg[warp * 64 + 32 + lane]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (lane == 0) {
+        s_rowabs[warp] = warp < H ? a + fabsf(p.bg[warp]) : 0.f;
+        s_bias[warp] = warp < H ? p.bg[warp] : 0.f;
+      }
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (tid == 0) {
+    float gm = 1e-6f;
+    for (int i = 0; i < 16; ++i) gm = fmaxf(gm, s_rowabs[i]);
+    int e;
+    frexpf(gm, &e);                          // gm = f * 2^e, f in [0.5, 1)  ->  g <= 2^e
+    s_gscale = exp2f((float)(15 - e));       // g * scale <= 2^15 ; 1e-6 * scale stays a normal fp16 for gm < 512
+  }
+  __syncthreads();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tG = tmem_base + 128, tPV = tmem_base + 256;
+  const float gscale = s_gscale;
+
+  if (warp == 16) {
+    // ============================================================================================ TMA + UMMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_f16(128, 128, false, false, false);
+      const uint32_t idesc_o = make_idesc_f16(128, 64, false, false, true);
+      const uint32_t idesc_g = make_idesc_f16(128, 16, false, false, false);
+      const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
+      const uint32_t bh = smem_u32(sBh), bl = smem_u32(sBl);
+      uint32_t x = 0, u = 0, rc = 0, tc = 0;                     // blocks, pair tiles, FC rounds, tasks so far
+      auto geom_mma = [&]() {                                    // the UMMAs of one block's geometry (rounds x 8 pair tiles)
+        for (int rd = 0; rd < rounds; ++rd) {
+          if (rc >= 1) mbar_wait(g_free, (rc - 1) & 1);
+          for (int i8 = 0; i8 < 8; ++i8) {
+            const uint32_t bf = u & 1;
+            mbar_wait(&a_full[bf], (u >> 1) & 1);
+            tc_fence_after();
+            const uint32_t ah = smem_u32(sA + bf * 32768), al = ah + 16384;
+            const uint32_t d = tG + i8 * 16;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              mma_f16_ss(d, make_smem_desc_sw128(ah + k * 32, 16, 1024), make_smem_desc_sw128(bh + k * 32, 16, 1024), idesc_g, k > 0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              mma_f16_ss(d, make_smem_desc_sw128(al + k * 32, 16, 1024), make_smem_desc_sw128(bh + k * 32, 16, 1024), idesc_g, 1);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              mma_f16_ss(d, make_smem_desc_sw128(ah + k * 32, 16, 1024), make_smem_desc_sw128(bl + k * 32, 16, 1024), idesc_g, 1);
+            mma_commit(&a_free[bf]);
+            ++u;
+          }
+          mma_commit(g_full);
+          ++rc;
+        }
+      };
+      auto issue_s = [&](uint32_t xb) {
+        mbar_wait(&k_full[xb & 1], (xb >> 1) & 1);
+        tc_fence_after();
+        const uint32_t aK = smem_u32(sK + (xb & 1) * 16384);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          mma_f16_ss(tS, make_smem_desc_sw128(aQ + k * 32, 16, 1024), make_smem_desc_sw128(aK + k * 32, 16, 1024), idesc_s, k > 0);
+        mma_commit(s_full);
+      };
+      for (int task = team; task < p.ntasks; task += p.teams, ++tc) {
+        const int rg = task % p.R, qt = (task / p.R) % p.QT, b = task / (p.R * p.QT);
+        const int kt0 = rg * p.Tr, nT = min(p.T, kt0 + p.Tr) - kt0;
+        const int q0 = qt * 128;
+        if (x >= 1) mbar_wait(pv_full, (x - 1) & 1);             // the previous task has drained (Q, K, V, P buffers free)
+        mbar_arrive_expect_tx(q_full, 16384);
+        tma_load_3d(sQ, &tmQ, q_full, h * 64, q0, b);
+        mbar_arrive_expect_tx(&k_full[x & 1], 16384);
+        tma_load_3d(sK + (x & 1) * 16384, &tmK, &k_full[x & 1], h * 64, kt0 * 128, b);
+        mbar_arrive_expect_tx(&v_full[x & 1], 16384);
+        tma_load_3d(sV + (x & 1) * 16384, &tmV, &v_full[x & 1], h * 64, kt0 * 128, b);
+        if (nT > 1) {
+          mbar_arrive_expect_tx(&k_full[(x + 1) & 1], 16384);
+          tma_load_3d(sK + ((x + 1) & 1) * 16384, &tmK, &k_full[(x + 1) & 1], h * 64, (kt0 + 1) * 128, b);
+        }
+        mbar_wait(q_full, tc & 1);
+        issue_s(x);
+#pragma unroll 1
+        for (int i = -2; i < nT; ++i) {
+          if (i >= 0) {
+            mbar_wait(p_full, x & 1);                            // softmax of block x done: S and the previous PV are consumed
+            tc_fence_after();
+            if (i + 1 < nT) {
+              mbar_arrive_expect_tx(&v_full[(x + 1) & 1], 16384);
+              tma_load_3d(sV + ((x + 1) & 1) * 16384, &tmV, &v_full[(x + 1) & 1], h * 64, (kt0 + i + 1) * 128, b);
+            }
+            if (i + 2 < nT) {
+              mbar_arrive_expect_tx(&k_full[x & 1], 16384);
+              tma_load_3d(sK + (x & 1) * 16384, &tmK, &k_full[x & 1], h * 64, (kt0 + i + 2) * 128, b);
+            }
+            if (i + 1 < nT) issue_s(x + 1);
+            mbar_wait(&v_full[x & 1], (x >> 1) & 1);
+            tc_fence_after();
+            const uint32_t aV = smem_u32(sV + (x & 1) * 16384);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              mma_f16_ss(tPV, make_smem_desc_sw128(aP + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                         make_smem_desc_sw128(aV + k * 2048, 1024, 1024), idesc_o, k > 0);
+            mma_commit(pv_full);
+            ++x;
+          }
+          if (i + 2 < nT) geom_mma();
+        }
+      }
+    }
+  } else {
+    // ============================================================================================ compute warps
+    const int j = warp >> 2;                                      // coordinate (geometry) / 32-key slice (softmax) / 16-col slice (O)
+    const int r = (warp & 3) * 32 + lane;                         // pair row / query row == TMEM lane
+    const uint32_t lane_base = ((uint32_t)((warp & 3) * 32) << 16);
+    uint32_t x = 0, u = 0, rc = 0;                                // blocks consumed, pair tiles, FC rounds (CTA-local counts)
+    uint32_t tb_base = 0;                                         // team-wide sequence number of the task's first block
+    uint32_t pending_done = 0;                                    // thread 0: consumed blocks not yet reported to the team
+
+    for (int task = team; task < p.ntasks; task += p.teams) {
+      const int rg = task % p.R, qt = (task / p.R) % p.QT, b = task / (p.R * p.QT);
+      const int kt0 = rg * p.Tr, nT = min(p.T, kt0 + p.Tr) - kt0;
+      const int q0 = qt * 128, n = q0 + r;
+      const float4 bq = __ldg(reinterpret_cast<const float4*>(p.boxes) + (size_t)b * p.N + min(n, p.N - 1));
+      const float wn = bq.z - bq.x + 1.f, hn = bq.w - bq.y + 1.f;
+      const float cxn = 0.5f * (bq.x + bq.z), cyn = 0.5f * (bq.y + bq.w);
+      const float rwn = __frcp_rn(wn), rhn = __frcp_rn(hn);
+
+      // ---- producer: geometry weights of this member's key slice of block (task-local index bi)
+      auto geom = [&](int bi) {
+        const uint32_t tb = tb_base + bi;
+        const int mbase = (kt0 + bi) * 128 + h * ks;
+        __half* slot = p.gslots + ((((size_t)team * kFSlots + (tb % kFSlots)) * H + h) * H) * (size_t)(128 * ks);
+#pragma unroll 1
+        for (int rd = 0; rd < rounds; ++rd) {
+#pragma unroll 1
+          for (int i8 = 0; i8 < 8; ++i8) {
+            const int m = min(mbase + rd * 8 + i8, p.M - 1);
+            const float4 bk = __ldg(reinterpret_cast<const float4*>(p.boxes) + (size_t)b * p.N + (p.key_index ? p.key_index[m] : m));
+            float e;                                              // eps[j] of SYM_REL:56-75 (division by the QUERY box)
+            if (j == 0) e = __logf(fmaxf(fabsf((cxn - 0.5f * (bk.x + bk.z)) * rwn), 1e-3f));
+            else if (j == 1) e = __logf(fmaxf(fabsf((cyn - 0.5f * (bk.y + bk.w)) * rhn), 1e-3f));
+            else if (j == 2) e = __logf(wn * __frcp_rn(bk.z - bk.x + 1.f));
+            else e = __logf(hn * __frcp_rn(bk.w - bk.y + 1.f));
+            const float a = 100.0f * e;
+            float sn[8], cs[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) sincos_2pi_f(a * p.rdim[k], &sn[k], &cs[k]);
+            uint32_t sh[4], sl[4], ch[4], cl[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              split2_f(sn[2 * q], sn[2 * q + 1], &sh[q], &sl[q]);
+              split2_f(cs[2 * q], cs[2 * q + 1], &ch[q], &cl[q]);
+            }
+            const uint32_t bf = u & 1;
+            if (u >= 2) mbar_wait(&a_free[bf], ((u >> 1) - 1) & 1);
+            uint8_t* Ah = sA + bf * 32768; uint8_t* Al = Ah + 16384;
+            // row r of A: [coord c][sin f0..7 | cos f0..7] -> chunk 2c = sins, chunk 2c+1 = coses
+            *reinterpret_cast<uint4*>(Ah + sw128_offset(r, 2 * j)) = make_uint4(sh[0], sh[1], sh[2], sh[3]);
+            *reinterpret_cast<uint4*>(Al + sw128_offset(r, 2 * j)) = make_uint4(sl[0], sl[1], sl[2], sl[3]);
+            *reinterpret_cast<uint4*>(Ah + sw128_offset(r, 2 * j + 1)) = make_uint4(ch[0], ch[1], ch[2], ch[3]);
+            *reinterpret_cast<uint4*>(Al + sw128_offset(r, 2 * j + 1)) = make_uint4(cl[0], cl[1], cl[2], cl[3]);
+            fence_proxy_async_smem();
+            mbar_arrive(&a_full[bf]);
+            ++u;
+          }
+          // heads 4j..4j+3 of this thread's query row for the 8 keys of the round
+          mbar_wait(g_full, rc & 1);
+          tc_fence_after();
+          uint32_t v[8][4];
+#pragma unroll
+          for (int i8 = 0; i8 < 8; ++i8) tmem_ld_32x32b_x4f(tG + lane_base + i8 * 16 + 4 * j, v[i8]);
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(g_free);
+          ++rc;
+          if (rd == 0) {                                          // the ring slot must have been read by EVERY teammate
+            if (warp == 0 && tb >= (uint32_t)kFSlots) {
+              const unsigned need = tb - kFSlots + 1;             // blocks 0 .. tb - kFSlots consumed
+              if (lane < H) while (ld_acquire_gpu(done_ctr + lane) < need) {}
+              __syncwarp();
+            }
+            bar_compute();
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int hh = 4 * j + q;
+            if (hh < H) {
+              const float bb = s_bias[hh];
+              uint32_t pk[4];
+#pragma unroll
+              for (int i2 = 0; i2 < 4; ++i2) {
+                const float g0 = fmaxf(__uint_as_float(v[2 * i2][q]) + bb, 1e-6f) * gscale;
+                const float g1 = fmaxf(__uint_as_float(v[2 * i2 + 1][q]) + bb, 1e-6f) * gscale;
+                const __half2 hv = __floats2half2_rn(g0, g1);
+                pk[i2] = *reinterpret_cast<const uint32_t*>(&hv);
+              }
+              *reinterpret_cast<uint4*>(slot + ((size_t)hh * 128 + r) * ks + rd * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+          }
+        }
+        bar_compute();                                            // every store of the slab is issued ...
+        if (tid == 0) {
+          __threadfence();                                        // ... and ordered before the team counter (release)
+          if (pending_done) { atomicAdd(done_ctr + h, pending_done); pending_done = 0; }
+          atomicAdd(pub_ctr + h, 1u);
+        }
+      };
+
+      float o[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) o[i] = 0.f;
+      float m_run = -INFINITY, l_run = 0.f, alpha = 0.f;
+
+      // iteration i: softmax + P of block i, geometry of block i + 2 (two blocks ahead: hides the exchange latency and
+      // the P.V' UMMA), fold of block i.  i = -2, -1 only produce (one call site keeps the code in the instruction cache)
+#pragma unroll 1
+      for (int i = -2; i < nT; ++i) {
+        if (i >= 0) {
+        // ---------------------------------------------------------------------------------- consume block i
+        const uint32_t tb = tb_base + i;
+        const int m0 = (kt0 + i) * 128 + j * 32;                  // first key of this thread's slice
+        if (warp == 0) {                                          // EVERY teammate has published block tb
+          if (lane < H) while (ld_acquire_gpu(pub_ctr + lane) < tb + 1) {}
+          __syncwarp();
+        }
+        bar_compute();
+        uint4 gq[4];
+        {
+          const __half* slot = p.gslots + (((size_t)team * kFSlots + (tb % kFSlots)) * H) * (size_t)H * (128 * ks);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int kk = j * 32 + 8 * c, pp = kk / ks, within = kk - pp * ks;
+            gq[c] = __ldcg(reinterpret_cast<const uint4*>(slot + (((size_t)pp * H + h) * 128 + r) * ks + within));
+          }
+        }
+        mbar_wait(s_full, x & 1);
+        tc_fence_after();
+        uint32_t sv[32];
+        tmem_ld_32x32b_x32(tS + lane_base + j * 32, sv);
+        tmem_ld_wait();
+        tc_fence_before();
+        float t[32];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          t[q] = (m0 + q < p.M) ? __uint_as_float(sv[q]) * p.scale_log2 : -INFINITY;
+          mx = fmaxf(mx, t[q]);
+        }
+        s_mx[j][r] = mx;
+        bar_compute();
+        mx = fmaxf(fmaxf(s_mx[0][r], s_mx[1][r]), fmaxf(s_mx[2][r], s_mx[3][r]));
+        const float m_new = fmaxf(m_run, mx);                     // finite: every key tile holds at least one valid key
+        alpha = exp2f(m_run - m_new);                             // first block: exp2(-inf) = 0
+        m_run = m_new;
+        float lsum = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t gw[4] = {gq[c].x, gq[c].y, gq[c].z, gq[c].w};
+          uint32_t pk[4];
+#pragma unroll
+          for (int i2 = 0; i2 < 4; ++i2) {
+            const float2 g2 = __half22float2(*reinterpret_cast<const __half2*>(&gw[i2]));
+            const float p0 = g2.x * exp2f(t[c * 8 + 2 * i2] - m_new);        // exp2(-inf) = 0 masks keys >= M
+            const float p1 = g2.y * exp2f(t[c * 8 + 2 * i2 + 1] - m_new);
+            lsum += p0 + p1;
+            const __half2 hv = __floats2half2_rn(p0, p1);
+            pk[i2] = *reinterpret_cast<const uint32_t*>(&hv);
+          }
+          *reinterpret_cast<uint4*>(sP + (j >> 1) * 16384 + sw128_offset(r, (j & 1) * 4 + c)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+        l_run = fmaf(l_run, alpha, lsum);
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(p_full);
+        if (tid == 0) ++pending_done;
+        }
+        // ---------------------------------------------------------------------------------- produce two blocks ahead
+        if (i + 2 < nT) geom(i + 2);
+        if (i < 0) continue;
+        // ---------------------------------------------------------------------------------- fold O += P V'
+        mbar_wait(pv_full, x & 1);
+        tc_fence_after();
+        {
+          uint32_t pv[16];
+          tmem_ld_32x32b_x16(tPV + lane_base + j * 16, pv);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 16; ++q) o[q] = fmaf(o[q], alpha, __uint_as_float(pv[q]));
+        }
+        tc_fence_before();
+        ++x;
+      }
+      tb_base += nT;
+
+      // ------------------------------------------------------------------------------------ epilogue
+      s_sum[j][r] = l_run;
+      bar_compute();
+      const float l_tot = (s_sum[0][r] + s_sum[1][r]) + (s_sum[2][r] + s_sum[3][r]);
+      float* stage = reinterpret_cast<float*>(sA);                // [128][kStagePitch]; the A buffers are idle here
+      {
+        const float sc = p.R == 1 ? 1.f / l_tot : 1.f;
+#pragma unroll
+        for (int q = 0; q < 16; q += 4)
+          *reinterpret_cast<float4*>(stage + r * kStagePitch + j * 16 + q) = make_float4(o[q] * sc, o[q + 1] * sc, o[q + 2] * sc, o[q + 3] * sc);
+      }
+      if (p.R > 1 && j == 0 && n < p.N)
+        reinterpret_cast<float2*>(p.part_ml)[(((size_t)rg * p.B + b) * H + h) * p.N + n] = make_float2(m_run, l_tot);
+      bar_compute();
+      bool finalize = p.R == 1;
+      if (p.R > 1) {
+        // un-normalised partial tile -> workspace (row-contiguous 256-byte segments), then the ticket
+        for (int it = tid; it < 128 * 16; it += 512) {
+          const int row = it >> 4, c4 = it & 15;
+          if (q0 + row < p.N)
+            reinterpret_cast<float4*>(p.part_o + ((((size_t)rg * p.B + b) * H + h) * p.N + q0 + row) * 64)[c4] =
+                *reinterpret_cast<const float4*>(stage + row * kStagePitch + c4 * 4);
+        }
+        bar_compute();
+        if (tid == 0) {
+          __threadfence();
+          const unsigned tk = atomicAdd(&tickets[((size_t)b * p.QT + qt) * H + h], 1u);
+          s_last = (tk == (unsigned)(p.R - 1));
+          if (s_last) __threadfence();
+        }
+        bar_compute();
+        finalize = s_last != 0;
+      }
+      if (finalize) {
+        for (int it = tid; it < 128 * 16; it += 512) {
+          const int row = it >> 4, c4 = it & 15;
+          const int nn = q0 + row;
+          if (nn >= p.N || c4 * 4 >= p.dv) continue;
+          float4 y;
+          if (p.R == 1) {
+            y = *reinterpret_cast<const float4*>(stage + row * kStagePitch + c4 * 4);
+          } else {
+            float mm = -INFINITY;
+            for (int s = 0; s < p.R; ++s)
+              mm = fmaxf(mm, __ldcg(reinterpret_cast<const float2*>(p.part_ml) + (((size_t)s * p.B + b) * H + h) * p.N + nn).x);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            float l = 0.f;
+            for (int s = 0; s < p.R; ++s) {
+              const size_t prow = (((size_t)s * p.B + b) * H + h) * p.N + nn;
+              const float2 ml = __ldcg(reinterpret_cast<const float2*>(p.part_ml) + prow);
+              const float w = exp2f(ml.x - mm);
+              const float4 po = __ldcg(reinterpret_cast<const float4*>(p.part_o + prow * 64) + c4);
+              acc.x = fmaf(w, po.x, acc.x); acc.y = fmaf(w, po.y, acc.y); acc.z = fmaf(w, po.z, acc.z); acc.w = fmaf(w, po.w, acc.w);
+              l = fmaf(w, ml.y, l);
+            }
+            const float inv = 1.f / l;
+            y = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+          }
+          float yy[4] = {y.x, y.y, y.z, y.w};
+          float* dst = p.out + ((size_t)b * p.N + nn) * p.ldo + (size_t)h * p.dv + c4 * 4;
+          const float* res = p.X ? p.X + ((size_t)b * p.N + nn) * p.ldx + (size_t)h * p.dv + c4 * 4 : nullptr;
+          __half* d16 = p.out16 ? p.out16 + ((size_t)b * p.N + nn) * p.ldo16 + (size_t)h * p.dv + c4 * 4 : nullptr;
+          if (c4 * 4 + 4 <= p.dv && (p.dv & 3) == 0 && (p.ldo & 3) == 0 && (!res || (p.ldx & 3) == 0) && (!d16 || (p.ldo16 & 3) == 0)) {
+            if (res) {
+              const float4 x4 = __ldg(reinterpret_cast<const float4*>(res));
+              yy[0] += x4.x; yy[1] += x4.y; yy[2] += x4.z; yy[3] += x4.w;
+            }
+            if (p.relu) { yy[0] = fmaxf(yy[0], 0.f); yy[1] = fmaxf(yy[1], 0.f); yy[2] = fmaxf(yy[2], 0.f); yy[3] = fmaxf(yy[3], 0.f); }
+            *reinterpret_cast<float4*>(dst) = make_float4(yy[0], yy[1], yy[2], yy[3]);
+            if (d16) {
+              const __half2 a2 = __floats2half2_rn(yy[0], yy[1]), b2 = __floats2half2_rn(yy[2], yy[3]);
+              *reinterpret_cast<uint2*>(d16) = make_uint2(*reinterpret_cast<const uint32_t*>(&a2), *reinterpret_cast<const uint32_t*>(&b2));
+            }
+          } else {
+            for (int q = 0; q < 4; ++q)
+              if (c4 * 4 + q < p.dv) {
+                float vv = yy[q];
+                if (res) vv += res[q];
+                if (p.relu) vv = fmaxf(vv, 0.f);
+                dst[q] = vv;
+                if (d16) d16[q] = __float2half_rn(vv);
+              }
+          }
+        }
+      }
+      bar_compute();                                              // the staging tile aliases the next task's A buffers
+    }
+    if (tid == 0 && pending_done) atomicAdd(done_ctr + h, pending_done);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 16) tmem_dealloc<512>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------------------ host
+struct FusedPlan { int teams, QT, T, R, Tr, ntasks; };
+
+static bool fused_plan(const rn_relation_desc* d, FusedPlan* pl) {
+  const int H = d->H;
+  if (d->E != 64 || H < 1 || H > 16 || (128 % H) != 0 || (128 / H) % 8 != 0) return false;
+  if (d->dq % H || d->dq / H > 64 || d->dout % H || d->dout / H > 64) return false;
+  const int sms = sm_count() > 0 ? sm_count() : 148;
+  pl->teams = sms / H;
+  if (pl->teams < 1) return false;
+  pl->QT = cdiv(d->N, 128); pl->T = cdiv(d->M, 128);
+  const long long qtasks = (long long)d->batch * pl->QT;
+  // key ranges: split the key tiles over several teams only when that fills noticeably more of the machine (partials cost
+  // a workspace round trip and the in-kernel merge)
+  int bestR = 1; double best = -1.0;
+  for (int R = 1; R <= std::min(pl->T, 8); ++R) {
+    const int Tr = cdiv(pl->T, R);
+    if ((R - 1) * Tr >= pl->T) continue;                          // would leave an empty range
+    const long long tasks = qtasks * R;
+    const long long waves = (tasks + pl->teams - 1) / pl->teams;
+    const double eff = (double)qtasks * pl->T / ((double)waves * pl->teams * Tr);      // useful block slots / issued slots
+    if (eff > best * 1.15 + 1e-9) { best = eff; bestR = R; }
+  }
+  pl->R = bestR; pl->Tr = cdiv(pl->T, bestR);
+  pl->ntasks = (int)(qtasks * pl->R);
+  pl->teams = (int)std::min<long long>(pl->teams, pl->ntasks);
+  return true;
+}
+
+bool relation_fused_ok(const rn_relation_desc* d) { FusedPlan pl; return is_sm100() && fused_plan(d, &pl); }
+
+size_t relation_fused_ws_bytes(const rn_relation_desc* d) {
+  FusedPlan pl;
+  if (!fused_plan(d, &pl)) return 0;
+  const int sms = sm_count() > 0 ? sm_count() : 148;
+  const size_t teams_max = sms / d->H;
+  size_t t = ws_slice(teams_max * kFSlots * (size_t)d->H * 128 * 128, 2);                       // g ring
+  t += ws_slice(32 * teams_max + (size_t)d->batch * pl.QT * d->H, 4);                           // counters + tickets
+  if (pl.R > 1) t += ws_slice((size_t)pl.R * d->batch * d->H * d->N * 64, 4) + ws_slice((size_t)pl.R * d->batch * d->H * d->N * 2, 4);
+  return t;
+}
+
+int relation_fused_launch(const rn_relation_desc* d, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                          const float* boxes, const int* key_index, const float* Wg, const float* bg, const float* X,
+                          float* out, void* out_f16, void* wsp, size_t ws_bytes, cudaStream_t st) {
+  FusedPlan pl;
+  RN_CHECK_ARG(fused_plan(d, &pl), "relation_fused: shape not covered (H=%d E=%d dq=%d dout=%d)", d->H, d->E, d->dq, d->dout);
+  const int H = d->H, sms = sm_count() > 0 ? sm_count() : 148;
+  const size_t teams_max = sms / H;
+  Workspace ws(wsp, ws_bytes);
+  __half* gslots = ws.take<__half>(teams_max * kFSlots * (size_t)H * 128 * 128);
+  const size_t nctr = 32 * teams_max + (size_t)d->batch * pl.QT * H;
+  unsigned* counters = ws.take<unsigned>(nctr);
+  float *part_o = nullptr, *part_ml = nullptr;
+  if (pl.R > 1) {
+    part_o = ws.take<float>((size_t)pl.R * d->batch * H * d->N * 64);
+    part_ml = ws.take<float>((size_t)pl.R * d->batch * H * d->N * 2);
+  }
+  if (!counters || (pl.R > 1 && !part_ml)) { set_error("relation_fused: workspace too small (%zu < %zu)", ws_bytes, relation_fused_ws_bytes(d)); return RN_ERR_WORKSPACE; }
+  RN_CUDA(cudaMemsetAsync(counters, 0, nctr * sizeof(unsigned), st));
+  FusedParams p;
+  p.B = d->batch; p.N = d->N; p.M = d->M; p.H = H; p.dv = d->dout / H;
+  p.QT = pl.QT; p.T = pl.T; p.R = pl.R; p.Tr = pl.Tr; p.teams = pl.teams; p.ntasks = pl.ntasks;
+  p.boxes = boxes; p.key_index = key_index; p.Wg = Wg; p.bg = bg;
+  GeomFreq fr;
+  int r = make_freq(d->E, d->wave_length, &fr);
+  if (r) return r;
+  for (int k = 0; k < 8; ++k) p.rdim[k] = 1.0f / fr.dim[k];          // == __frcp_rn(dim) of the unfused kernels (IEEE division)
+  p.scale_log2 = 1.4426950408889634f / sqrtf((float)(d->dq / H));
+  p.X = d->fuse_residual_relu ? X : nullptr; p.ldx = d->d;
+  p.out = out; p.ldo = d->dout; p.out16 = (__half*)out_f16; p.ldo16 = d->dout; p.relu = d->fuse_residual_relu;
+  p.gslots = gslots; p.counters = counters; p.part_o = part_o; p.part_ml = part_ml;
+  static thread_local bool configured = false;
+  if (!configured) {
+    RN_CUDA(cudaFuncSetAttribute(relation_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmem));
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(pl.teams * H));
+  cfg.blockDim = dim3(kFThreads);
+  cfg.dynamicSmemBytes = kFSmem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;          // all CTAs co-resident: team members wait for each other
+  at[0].val.cooperative = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  RN_CUDA(cudaLaunchKernelEx(&cfg, relation_fused_kernel, tmQ, tmK, tmV, p));
+  return RN_OK;
+}
+
+}  // namespace rn

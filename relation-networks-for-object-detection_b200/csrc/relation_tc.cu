@@ -292,14 +292,11 @@ __global__ void __launch_bounds__(192, 1) relation_attn_tc_kernel(const __grid_c
 constexpr int kTileBar = 16384 * 3 + 32768;            // Q, K, V', P
 constexpr int kTileSmem = kTileBar + 128 + 1024;
 
-static long long* g_tile_trace = nullptr;      // set by rn_debug_tile_trace (measurement only)
-
 struct TileParams {
   AttnParams a;
   int splits;                    // key tiles per query tile (gridDim.x = qtiles * splits)
   float* part_o;                 // [splits][B][H][N][64] un-normalised partial outputs
   float* part_ml;                // [splits][B][H][N][2]  (row max in log2 units, row sum)
-  long long* trace;              // debug: per-CTA clock64() stamps at 8 points of the dependent chain (nullptr = off)
 };
 
 // 288 threads: warps 0..7 are the softmax / epilogue warps -- TWO threads per query row (warp w and w + 4 share the TMEM lane
@@ -323,8 +320,6 @@ __global__ void __launch_bounds__(288, 2) relation_attn_tile_kernel(const __grid
   const int qt = blockIdx.x / tp.splits, kt = blockIdx.x % tp.splits;
   const int q0 = qt * 128, m0 = kt * 128, h = blockIdx.y, b = blockIdx.z;
   if (p.active && !p.active[b]) return;          // uniform for the whole CTA, before any barrier / TMEM allocation
-  long long* tr = tp.trace ? tp.trace + 8 * ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) : nullptr;
-  if (tr && threadIdx.x == 0) tr[0] = clock64();
   if (p.gidx && threadIdx.x < 128) {
     const int m = m0 + threadIdx.x, nq = q0 + threadIdx.x;
     s_gidx[threadIdx.x] = m < p.M ? p.gidx[(size_t)m * p.gs_i + (size_t)b * p.gs_b] : 0;
@@ -349,12 +344,10 @@ __global__ void __launch_bounds__(288, 2) relation_attn_tile_kernel(const __grid
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base, tPV = tmem_base + 128;
-  if (tr && threadIdx.x == 0) tr[1] = clock64();          // prologue done (barriers, TMEM allocation, first sync)
 
   if (warp == 8) {
     if (lane == 0) {
       mbar_wait(ld_full, 0);
-      if (tr) tr[2] = clock64();                            // Q / K / V' tiles landed
       tc_fence_after();
       const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aP = smem_u32(sP), aV = smem_u32(sV);
 #pragma unroll
@@ -397,9 +390,7 @@ __global__ void __launch_bounds__(288, 2) relation_attn_tile_kernel(const __grid
         t[q] = t4.x; t[q + 1] = t4.y; t[q + 2] = t4.z; t[q + 3] = t4.w;
       }
     }
-    if (tr && threadIdx.x == 0) tr[3] = clock64();          // geometry row half loaded (issued) by thread 0
     mbar_wait(s_full, 0);
-    if (tr && threadIdx.x == 0) tr[4] = clock64();          // S = Q K^T visible
     tc_fence_after();
     float mx = -INFINITY;
 #pragma unroll
@@ -434,9 +425,7 @@ __global__ void __launch_bounds__(288, 2) relation_attn_tile_kernel(const __grid
     fence_proxy_async_smem();
     tc_fence_before();
     mbar_arrive(p_full);
-    if (tr && threadIdx.x == 0) tr[5] = clock64();          // P written (this thread)
     mbar_wait(pv_full, 0);
-    if (tr && threadIdx.x == 0) tr[6] = clock64();          // O = P V' visible
     tc_fence_after();
     asm volatile("bar.sync 1, 256;" ::: "memory");       // both halves' row sums are in shared memory
     lsum += s_sum[half ^ 1][r];
@@ -483,7 +472,6 @@ __global__ void __launch_bounds__(288, 2) relation_attn_tile_kernel(const __grid
   }
   tc_fence_before();
   __syncthreads();
-  if (tr && threadIdx.x == 0) tr[7] = clock64();            // epilogue stores issued, CTA about to retire
   if (warp == 8) tmem_dealloc<256>(tmem_base);
 }
 
@@ -525,21 +513,22 @@ __global__ void __launch_bounds__(256) relation_attn_combine_kernel(TileParams t
   }
 }
 
-// [Wq; Wk; Wout'] -> fp16 [3*H*64, d8] and bias [3*H*64] (Wout' / bout padded from dv to 64 columns per head)
+// [Wq; Wk; Wout'] -> fp16 [3*H*64, d8] and bias [3*H*64]: every head owns 64 columns of each part; Wq / Wk rows beyond dk
+// and Wout' / bout rows beyond dv are zero (zero Q/K columns leave q.k unchanged, zero V' columns are never stored)
 __global__ void pack_relation_weights_kernel(const float* __restrict__ Wq, const float* __restrict__ bq,
                                              const float* __restrict__ Wk, const float* __restrict__ bk,
                                              const float* __restrict__ Wout, const float* __restrict__ bout, int d, int d8,
-                                             int H, int dv, __half* __restrict__ W16, float* __restrict__ bias) {
+                                             int H, int dk, int dv, __half* __restrict__ W16, float* __restrict__ bias) {
   const int rows = 3 * H * 64;
   const size_t total = (size_t)rows * d8;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int r = i / d8, c = i % d8;
     const int part = r / (H * 64), rr = r % (H * 64);
     float v = 0.f, bv = 0.f;
-    if (part == 0) { if (c < d) v = Wq[(size_t)rr * d + c]; bv = bq[rr]; }
-    else if (part == 1) { if (c < d) v = Wk[(size_t)rr * d + c]; bv = bk[rr]; }
+    const int hh = rr / 64, jj = rr % 64;
+    if (part == 0) { if (jj < dk) { if (c < d) v = Wq[(size_t)(hh * dk + jj) * d + c]; bv = bq[hh * dk + jj]; } }
+    else if (part == 1) { if (jj < dk) { if (c < d) v = Wk[(size_t)(hh * dk + jj) * d + c]; bv = bk[hh * dk + jj]; } }
     else {
-      const int hh = rr / 64, jj = rr % 64;
       if (jj < dv) { if (c < d) v = Wout[(size_t)(hh * dv + jj) * d + c]; bv = bout[hh * dv + jj]; }
     }
     W16[i] = __float2half_rn(v);
@@ -547,8 +536,20 @@ __global__ void pack_relation_weights_kernel(const float* __restrict__ Wq, const
   }
 }
 
+// relation_fused.cu: geometry + attention in one cooperative launch
+bool relation_fused_ok(const rn_relation_desc* d);
+size_t relation_fused_ws_bytes(const rn_relation_desc* d);
+int relation_fused_launch(const rn_relation_desc* d, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                          const float* boxes, const int* key_index, const float* Wg, const float* bg, const float* X,
+                          float* out, void* out_f16, void* wsp, size_t ws_bytes, cudaStream_t st);
+// RN_RELATION_UNFUSED=1 (or rn_relation_fused_enable(0)) keeps the round-1 decomposition (geometry kernel -> [B,H,N,M]
+// table -> tile attention + combine): the A/B arm of the measurements, not a fallback -- both are tcgen05 paths
+static int g_fused_on = [] { const char* e = getenv("RN_RELATION_UNFUSED"); return (e && e[0] == '1') ? 0 : 1; }();
+static bool use_fused(const rn_relation_desc* d) { return g_fused_on && relation_fused_ok(d); }
+
 static bool tc_shape_ok(const rn_relation_desc* d) {
-  return d->dq == d->H * 64 && d->dout % d->H == 0 && d->dout / d->H <= 64 && d->dout / d->H >= 1;
+  return d->dq % d->H == 0 && d->dq / d->H <= 64 && d->dq / d->H >= 1 && d->dout % d->H == 0 && d->dout / d->H <= 64 &&
+         d->dout / d->H >= 1;
 }
 
 size_t relation_tc_workspace_bytes(const rn_relation_desc* d) {
@@ -561,8 +562,9 @@ size_t relation_tc_workspace_bytes(const rn_relation_desc* d) {
   t += relation_tc_packed_bytes(d);       // packed weights + bias (unpacked entry point)
   t += ws_slice(B * N * W3, 2);          // QKV' fp16
   t += ws_slice(B * M * 2 * H * 64, 2);  // KV' of gathered keys
-  t += ws_slice(B * H * N * ldg, 4);     // log2 geometry weight
   t += gemm_tc_workspace_bytes((int)(B * N), (int)W3, (int)d8) + 512;
+  if (use_fused(d)) return t + relation_fused_ws_bytes(d) + 512;
+  t += ws_slice(B * H * N * ldg, 4);     // log2 geometry weight
   const size_t T = (M + 127) / 128;
   if (T > 1 && T <= kMaxTileSplits) t += ws_slice(T * B * H * N * 64, 4) + ws_slice(T * B * H * N * 2, 4);
   return t;
@@ -595,8 +597,8 @@ int relation_tc_pack(const rn_relation_desc* d, const float* Wq, const float* bq
   const size_t total = (size_t)W3 * d8;
   size_t blocks = (total + 255) / 256;
   const size_t cap = (size_t)(sm_count() > 0 ? sm_count() : 148) * 8;
-  pack_relation_weights_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(Wq, bq, Wk, bk, Wout, bout, D, d8, H, dv,
-                                                                                 w16, bias);
+  pack_relation_weights_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(Wq, bq, Wk, bk, Wout, bout, D, d8, H,
+                                                                                 d->dq / H, dv, w16, bias);
   RN_LAUNCH_CHECK();
   return RN_OK;
 }
@@ -606,7 +608,7 @@ int relation_tc_packed(const rn_relation_desc* d, const float* X, const float* b
                        cudaStream_t st, int stage_mask, const GeomGather* gg, const void* x_f16, void* out_f16) {
   const bool do_proj = stage_mask & 1, do_geom = stage_mask & 2, do_attn = stage_mask & 4;
   RN_CHECK_ARG(is_sm100(), "RN_PREC_F16 needs an sm_100 device (tcgen05); use RN_PREC_FP32");
-  RN_CHECK_ARG(tc_shape_ok(d), "RN_PREC_F16 relation kernel supports dq == 64*H and dout/H <= 64 (got dq=%d dout=%d H=%d); "
+  RN_CHECK_ARG(tc_shape_ok(d), "RN_PREC_F16 relation kernel supports dq/H <= 64 and dout/H <= 64 (got dq=%d dout=%d H=%d); "
                "use RN_PREC_FP32 for this shape", d->dq, d->dout, d->H);
   const int B = d->batch, N = d->N, M = d->M, D = d->d, H = d->H, dv = d->dout / H;
   const int d8 = (int)align_up(D, 8), W3 = 3 * H * 64, ldg = (int)align_up(M, 4);
@@ -617,14 +619,16 @@ int relation_tc_packed(const rn_relation_desc* d, const float* X, const float* b
   __half* xk16 = ws.take<__half>((size_t)B * M * d8);
   __half* qkv = ws.take<__half>((size_t)B * N * W3);
   __half* kv = ws.take<__half>((size_t)B * M * 2 * H * 64);
-  float* lg = ws.take<float>((size_t)B * H * N * ldg);
+  const bool fused = !gg && use_fused(d);
+  // the [B,H,N,M] table exists only in the unfused decomposition (gathered mode brings its own roi-level table)
+  float* lg = (fused || gg) ? reinterpret_cast<float*>(kv) : ws.take<float>((size_t)B * H * N * ldg);
   const int T = cdiv(M, 128);
   float *part_o = nullptr, *part_ml = nullptr;
-  if (T > 1 && T <= kMaxTileSplits) {
+  if (!fused && T > 1 && T <= kMaxTileSplits) {
     part_o = ws.take<float>((size_t)T * B * H * N * 64);
     part_ml = ws.take<float>((size_t)T * B * H * N * 2);
   }
-  if (!lg || (T > 1 && T <= kMaxTileSplits && !part_ml)) { set_error("rn_relation_fwd(F16): workspace too small (%zu < %zu)", ws_bytes, relation_tc_workspace_bytes(d)); return RN_ERR_WORKSPACE; }
+  if (!lg || !kv || (!fused && T > 1 && T <= kMaxTileSplits && !part_ml)) { set_error("rn_relation_fwd(F16): workspace too small (%zu < %zu)", ws_bytes, relation_tc_workspace_bytes(d)); return RN_ERR_WORKSPACE; }
   void* gws = ws.base + ws.off; const size_t gws_bytes = ws.size - ws.off;
   int r;
   const bool ext_qkv = gg && gg->qkv_ext;
@@ -651,13 +655,15 @@ int relation_tc_packed(const rn_relation_desc* d, const float* X, const float* b
     Qp = qkv; Kp = qkv + H * 64; Vp = qkv + 2 * H * 64; ldq = ldk = W3; bq_pitch = bk_pitch = (long long)N * W3;
   }
   if (gg) RN_CHECK_ARG(!key_index && cdiv(M, 128) <= kMaxTileSplits, "gathered geometry needs M <= %d and no key_index", 128 * kMaxTileSplits);
-  if (!gg && do_geom && (r = launch_geom_weight_log2(st, boxes, key_index, B, N, M, H, d->E, d->wave_length, Wg, bg, lg, ldg))) return r;
+  if (!gg && !fused && do_geom && (r = launch_geom_weight_log2(st, boxes, key_index, B, N, M, H, d->E, d->wave_length, Wg, bg, lg, ldg))) return r;
   if (!do_attn) return RN_OK;
 
   CUtensorMap tmQ, tmK, tmV;
   if ((r = encode_tmap_3d_f16(&tmQ, Qp, B, N, H * 64, ldq, bq_pitch, 128, 64))) return r;
   if ((r = encode_tmap_3d_f16(&tmK, Kp, B, M, H * 64, ldk, bk_pitch, 128, 64))) return r;
   if ((r = encode_tmap_3d_f16(&tmV, Vp, B, M, H * 64, ldk, bk_pitch, 128, 64))) return r;
+  if (fused)           // geometry + attention: one cooperative launch, nothing N x M in HBM
+    return relation_fused_launch(d, tmQ, tmK, tmV, boxes, key_index, Wg, bg, X, out, out_f16, gws, gws_bytes, st);
   AttnParams p;
   p.N = N; p.M = M; p.H = H; p.T = T;
   p.lg = lg; p.ldg = ldg;
@@ -667,7 +673,7 @@ int relation_tc_packed(const rn_relation_desc* d, const float* X, const float* b
   p.X = d->fuse_residual_relu ? X : nullptr; p.ldx = D;
   p.out = out; p.ldo = d->dout; p.dv = dv; p.relu = d->fuse_residual_relu;
   p.out16 = (__half*)out_f16; p.ldo16 = d->dout;
-  p.scale_log2 = 1.4426950408889634f / sqrtf(64.f);
+  p.scale_log2 = 1.4426950408889634f / sqrtf((float)(d->dq / H));
   static thread_local bool configured = false;
   if (!configured) {
     RN_CUDA(cudaFuncSetAttribute(relation_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
@@ -676,7 +682,7 @@ int relation_tc_packed(const rn_relation_desc* d, const float* X, const float* b
   }
   if (T <= kMaxTileSplits) {
     TileParams tp;
-    tp.a = p; tp.splits = T; tp.part_o = part_o; tp.part_ml = part_ml; tp.trace = g_tile_trace;
+    tp.a = p; tp.splits = T; tp.part_o = part_o; tp.part_ml = part_ml;
     relation_attn_tile_kernel<<<dim3(cdiv(N, 128) * T, H, B), 288, kTileSmem, st>>>(tmQ, tmK, tmV, tp);
     RN_LAUNCH_CHECK();
     if (T > 1) {
@@ -699,7 +705,7 @@ int relation_tc(const rn_relation_desc* d, const float* X, const float* boxes, c
                 const float* bout, float* out, float* softmax_out, void* wsp, size_t ws_bytes, cudaStream_t st) {
   RN_CHECK_ARG(!softmax_out, "RN_PREC_F16 relation kernel never materialises the softmax; request it with RN_PREC_FP32");
   const size_t pk = relation_tc_packed_bytes(d);
-  RN_CHECK_ARG(pk > 0, "RN_PREC_F16 relation kernel supports dq == 64*H and dout/H <= 64 (got dq=%d dout=%d H=%d); use "
+  RN_CHECK_ARG(pk > 0, "RN_PREC_F16 relation kernel supports dq/H <= 64 and dout/H <= 64 (got dq=%d dout=%d H=%d); use "
                "RN_PREC_FP32 for this shape", d->dq, d->dout, d->H);
   if (ws_bytes < pk) { set_error("rn_relation_fwd(F16): workspace too small"); return RN_ERR_WORKSPACE; }
   int r = relation_tc_pack(d, Wq, bq, Wk, bk, Wout, bout, wsp, st);
@@ -749,8 +755,10 @@ __global__ void __launch_bounds__(256) lnms_gather_add_qkv_kernel(const float* _
 
 size_t relation_tc_lnms_extra_bytes(const rn_relation_desc* d, int R_emb) {
   const size_t W3 = 3 * (size_t)d->H * 64, d8 = align_up(d->d, 8);
+  const size_t T = (d->M + 127) / 128;
+  const size_t parts = T > 1 ? ws_slice(T * d->batch * d->H * d->N * 64, 4) + ws_slice(T * d->batch * d->H * d->N * 2, 4) : 0;
   return ws_slice((size_t)R_emb * d8, 2) + ws_slice((size_t)d->N * d8, 2) + ws_slice((size_t)R_emb * W3, 4) +
-         ws_slice((size_t)d->N * W3, 4) + ws_slice((size_t)d->batch * d->N * W3, 2) + 1024;
+         ws_slice((size_t)d->N * W3, 4) + ws_slice((size_t)d->batch * d->N * W3, 2) + parts + 1024;
 }
 
 // The weight-only half of relation_tc_lnms: packed fp16 weights and RQKV = rank_feat . W^T + b  [n, 3*H*64] fp32
@@ -815,9 +823,9 @@ int relation_tc_lnms(const rn_relation_desc* d, const float* X, const float* emb
 }
 }  // namespace rn
 
-// measurement hook: when `buffer` (device, 8 int64 per CTA of the next relation_attn_tile_kernel launches) is non-null, every
-// CTA records clock64() at 8 points of its dependent chain; pass NULL to switch it off.  Not part of the product path.
-extern "C" int rn_debug_tile_trace(void* buffer) {
-  rn::g_tile_trace = (long long*)buffer;
-  return RN_OK;
+extern "C" int rn_relation_fused_enable(int32_t on) {
+  const int prev = rn::g_fused_on;
+  rn::g_fused_on = on ? 1 : 0;
+  return prev;
 }
+

@@ -77,9 +77,11 @@ def default_precision():
 # ------------------------------------------------------------------------------------------------------------------
 def relation(X, boxes, Wq, bq, Wk, bk, Wg, bg, Wout, bout, key_index=None, M=None, group=16, residual_relu=False,
              precision=None, wave_length=1000.0, return_softmax=False, stage_mask=7, workspace=None, out=None,
-             x_f16=None, want_f16=False):
+             x_f16=None, want_f16=False, allow_fp32_fallback=False):
     """Object-relation module (SYM_REL:30-151 + :267-268).  X [N,d] or [B,N,d]; boxes [N,4] or [B,N,4].
-    RN_PREC_F16 only: x_f16 = the producer's fp16 copy of X (skips the cast launch); want_f16 -> returns (out, out_f16)."""
+    RN_PREC_F16 only: x_f16 = the producer's fp16 copy of X (skips the cast launch); want_f16 -> returns (out, out_f16).
+    A request the tcgen05 kernels do not cover (d_k or d_v > 64 per head, or the materialised softmax) RAISES under
+    precision='f16' unless allow_fp32_fallback=True, in which case the library's general fp32 kernels run instead."""
     precision = precision or default_precision()
     X = _f32(X, 'X'); boxes = _f32(boxes, 'boxes')
     batched = X.dim() == 3
@@ -103,7 +105,11 @@ def relation(X, boxes, Wq, bq, Wk, bk, Wg, bg, Wout, bout, key_index=None, M=Non
         M = kidx.numel()
     M = int(M) if M is not None else N
     if precision == 'f16' and not relation_tc_supported(Wq.shape[0], Wout2.shape[0], group, return_softmax):
-        precision = 'fp32'      # same library, the general fp32 kernels: the fused tcgen05 kernel is dk == 64 only
+        if not allow_fp32_fallback:
+            raise L.RelnetError('relation: precision=f16 does not cover dq/H=%d dout/H=%d return_softmax=%s (tcgen05 kernels: '
+                                'd_k, d_v <= 64, no materialised softmax); pass precision="fp32" or allow_fp32_fallback=True'
+                                % (Wq.shape[0] // group, Wout2.shape[0] // group, return_softmax))
+        precision = 'fp32'      # the library's general fp32 kernels, asked for explicitly
     desc = L.RelationDesc(B, N, M, d, Wq.shape[0], Wout2.shape[0], group, Wg.shape[1], wave_length,
                           int(residual_relu), PREC[precision])
     if out is None:
@@ -200,8 +206,16 @@ def relation_workspace_bytes(N, M, d, dq, dout, group, batch=1, E=64, precision=
 
 
 def relation_tc_supported(dq, dout, group, return_softmax=False):
-    """Shapes the fused tcgen05 relation kernel covers (relation_tc.cu:tc_shape_ok)."""
-    return dq == 64 * group and dout % group == 0 and 1 <= dout // group <= 64 and not return_softmax
+    """Shapes the tcgen05 relation kernels cover (relation_tc.cu:tc_shape_ok): d_k <= 64 and d_v <= 64 per head (narrower
+    heads are zero-padded to 64 columns at pack time)."""
+    return (dq % group == 0 and 1 <= dq // group <= 64 and dout % group == 0 and 1 <= dout // group <= 64
+            and not return_softmax)
+
+
+def relation_fused_enable(on):
+    """A/B switch of the RN_PREC_F16 relation module: 1 = fused geometry + attention launch (default), 0 = round-1
+    decomposition (geometry table -> tile attention -> combine).  Returns the previous setting."""
+    return int(L.lib().rn_relation_fused_enable(int(bool(on))))
 
 
 def pos_embed(boxes, M=None, key_index=None, E=64, wave_length=1000.0, want_eps=True, want_emb=True):

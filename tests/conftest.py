@@ -34,6 +34,16 @@ def rel_err(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
 
 
+def elem_err(a, b, rtol=1e-3, atol_frac=1e-3):
+    """Elementwise companion of rel_err: an element passes when |a-b| <= rtol*|b| + atol, atol = atol_frac * rms(b).
+    Returns (fraction of elements violating, worst |a-b| / (rtol*|b| + atol)).  Reported beside rel_err in the f16 parity
+    tests (VERDICT r1 / ADVICE: the per-tensor norm alone hides small-magnitude outputs)."""
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    atol = atol_frac * float(np.sqrt(np.mean(b * b)) + 1e-30)
+    ratio = np.abs(a - b) / (rtol * np.abs(b) + atol)
+    return float(np.mean(ratio > 1.0)), float(ratio.max())
+
+
 @pytest.fixture(scope='session')
 def cuda_device():
     import torch

@@ -1,0 +1,149 @@
+"""GPU: the fused relation kernel (relation_fused.cu: pair geometry + pair FC + QK^T + softmax + P.V' in one cooperative
+launch) against the float32 oracle, against the round-1 decomposition (geometry table -> tile attention) and at the
+largest sizes of BASELINE.json configs[3]/[4].
+
+Tolerance: max|a-b| / max|b| <= 1e-3 against the float32 oracle (north_star).  The elementwise figure
+(|a-b| <= 1e-3*|b| + 1e-3*rms(b): fraction of elements outside, worst ratio) is printed beside it and held to a loose
+bound -- fp16 operands cannot meet 1e-3 on every small-magnitude element, the printed numbers say how far off they are.
+"""
+import numpy as np
+import pytest
+import torch
+from conftest import rel_err, elem_err
+from oracle import relation_np as R
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ops(cuda_device):
+    import __graft_entry__ as g
+    g.build()
+    import relnet_b200
+    torch.cuda.set_device(cuda_device)
+    if not relnet_b200.ops.device_info()['sm100']:
+        pytest.skip('tcgen05 needs sm_100')
+    return relnet_b200.ops
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def rel_args(c):
+    return [c[k] for k in ('X', 'boxes', 'Wq', 'bq', 'Wk', 'bk', 'Wg', 'bg', 'Wout', 'bout')]
+
+
+def run(ops, args, fused, **kw):
+    prev = ops.relation_fused_enable(fused)
+    try:
+        out = ops.relation(*args, precision='f16', **kw)
+        torch.cuda.synchronize()
+        return out
+    finally:
+        ops.relation_fused_enable(prev)
+
+
+def report(tag, out, ref):
+    e = rel_err(out, ref)
+    frac, worst = elem_err(out, ref)
+    print('%s: rel_err %.2e | elementwise(1e-3 rtol + 1e-3 rms atol): %.3f%% outside, worst ratio %.1f' % (tag, e, 100 * frac, worst))
+    return e, frac
+
+
+# every sweep point of BASELINE.json configs[4] small enough for the float32 oracle, incl. d_k = 16 (d=256, H=16), partial
+# tiles, one key tile / several key tiles / several query tiles, residual + relu
+@pytest.mark.parametrize('N,M,d,H', [(100, 100, 256, 4), (300, 300, 1024, 16), (300, 300, 256, 16), (100, 100, 256, 16),
+                                     (515, 515, 1024, 16), (333, 200, 1024, 16), (1000, 1000, 256, 4), (130, 129, 512, 8)])
+def test_fused_matches_oracle_and_unfused(ops, N, M, d, H):
+    c = R.make_relation_case(N * 13 + d + H, N, d, H, M=None if M == N else M)
+    args = rel_args(c)
+    ref = R.relation_forward(*args, key_index=M, group=H, residual_relu=True, dtype=np.float32)
+    t = [T(a) for a in args]
+    fused = run(ops, t, 1, M=M, group=H, residual_relu=True).cpu().numpy()
+    e, frac = report('fused N=%d M=%d d=%d H=%d' % (N, M, d, H), fused, ref)
+    assert e < 1e-3 and frac < 0.02
+    if d // H == 64:                      # the round-1 tile kernel is the d_k = 64 arm
+        unf = run(ops, t, 0, M=M, group=H, residual_relu=True).cpu().numpy()
+        e2, _ = report('unfused', unf, ref)
+        assert rel_err(fused, unf) < 1e-3
+
+
+def test_fused_fanin_weights_and_f16_side_channel(ops):
+    """The reference initialiser (N(0, 0.01): near-uniform softmax, geometry weights of a few 1e-2 next to the 1e-6 clamp)
+    and the fp16 in / fp16 out side channels of the head."""
+    N, d, H = 300, 1024, 16
+    c = R.make_relation_case(77, N, d, H, init='ref')
+    args = rel_args(c)
+    ref = R.relation_forward(*args, group=H, residual_relu=True, dtype=np.float32)
+    t = [T(a) for a in args]
+    out, out16 = run(ops, t, 1, group=H, residual_relu=True, x_f16=t[0].half(), want_f16=True)
+    e, frac = report('fused ref-init N=300', out.cpu().numpy(), ref)
+    assert e < 1e-3 and frac < 0.02
+    assert rel_err(out16.float().cpu().numpy(), out.cpu().numpy()) < 1e-3
+
+
+def test_fused_key_index_fpn_size(ops):
+    """FPN form (SYM_FPN_REL_NMS:907-977) at its real size: N = 1000 + 37 gt rows, keys = the non-gt index list."""
+    N, d, H = 1037, 1024, 16
+    c = R.make_relation_case(5, N, d, H)
+    idx = np.sort(np.random.default_rng(3).permutation(N)[:1000]).astype(np.int32)
+    args = rel_args(c)
+    ref = R.relation_forward(*args, key_index=idx, group=H, residual_relu=True, dtype=np.float32)
+    t = [T(a) for a in args]
+    out = run(ops, t, 1, key_index=T(idx), group=H, residual_relu=True).cpu().numpy()
+    e, frac = report('fused key_index N=1037 M=1000', out, ref)
+    assert e < 1e-3 and frac < 0.02
+
+
+def test_fused_n3000_row_subset_vs_oracle(ops):
+    """Largest sweep point: 64 query rows (first / middle / last tiles) against the float32 oracle over all 3000 keys
+    (the module is row-separable given the keys: the oracle evaluates just those query rows)."""
+    N, d, H = 3000, 1024, 16
+    c = R.make_relation_case(123, N, d, H)
+    args = rel_args(c)
+    t = [T(a) for a in args]
+    out = run(ops, t, 1, group=H, residual_relu=True).cpu().numpy()
+    rows = np.concatenate([np.arange(0, 24), np.arange(1500, 1516), np.arange(2976, 3000)])
+    ref = R.relation_forward(*args, group=H, residual_relu=True, dtype=np.float32, query_index=rows)
+    e, frac = report('fused N=3000 (64-row subset)', out[rows], ref)
+    assert e < 1e-3 and frac < 0.02
+
+
+def test_fused_batched_small_dv(ops):
+    """learn-NMS-shaped problems through the fused path: batch of 5, d = 128, dq = 1024, dout = 128 (d_v = 8)."""
+    B, n = 5, 137
+    c0 = R.make_relation_case(40, n, 128, 16, dq=1024, dout=128)
+    rng = np.random.default_rng(5)
+    Xs, bs, outs = [], [], []
+    for b in range(B):
+        X = (rng.standard_normal((n, 128)) * 0.5).astype(np.float32); bx = R.make_boxes(rng, n)
+        Xs.append(X); bs.append(bx)
+        outs.append(R.relation_forward(X, bx, *rel_args(c0)[2:], group=16, residual_relu=True, dtype=np.float32))
+    t = [T(np.stack(Xs)), T(np.stack(bs))] + [T(a) for a in rel_args(c0)[2:]]
+    out = run(ops, t, 1, group=16, residual_relu=True).cpu().numpy()
+    e, frac = report('fused batched dv=8', out, np.stack(outs))
+    assert e < 1e-3 and frac < 0.02
+
+
+def test_fused_repeatable_and_graph_capturable(ops):
+    """Same inputs -> same bits (fixed schedule, no atomics on data), and the cooperative launch replays from a CUDA graph."""
+    N, d, H = 300, 1024, 16
+    c = R.make_relation_case(9, N, d, H)
+    t = [T(a) for a in rel_args(c)]
+    a = run(ops, t, 1, group=H, residual_relu=True).clone()
+    b = run(ops, t, 1, group=H, residual_relu=True).clone()
+    assert torch.equal(a, b)
+    ops.relation_fused_enable(1)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            ops.relation(*t, group=H, residual_relu=True, precision='f16')
+        s.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            o = ops.relation(*t, group=H, residual_relu=True, precision='f16')
+        for _ in range(3):
+            g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(o, a)

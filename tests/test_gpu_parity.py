@@ -109,7 +109,12 @@ def test_relation_key_index_and_softmax(ops):
     args = rel_args(c)
     ref = R.relation_forward(*args, key_index=idx, group=4, dtype=np.float32, return_all=True)
     for prec in precisions(ops):
-        out, sm = ops.relation(*[T(a) for a in args], key_index=T(idx), group=4, precision=prec, return_softmax=True)
+        if prec == 'f16':          # the tcgen05 path never materialises the softmax: asking for it must be loud
+            with pytest.raises(Exception):
+                ops.relation(*[T(a) for a in args], key_index=T(idx), group=4, precision=prec, return_softmax=True)
+            out, sm = ops.relation(*[T(a) for a in args], key_index=T(idx), group=4, precision=prec), None
+        else:
+            out, sm = ops.relation(*[T(a) for a in args], key_index=T(idx), group=4, precision=prec, return_softmax=True)
         assert rel_err(out.cpu().numpy(), ref['attn']) < 1e-3
         if sm is not None and prec == 'fp32':
             np.testing.assert_allclose(sm.cpu().numpy().sum(-1), 1.0, atol=1e-5)

@@ -272,3 +272,15 @@ def test_learn_nms_oracle_matches_reference_execution_non_gt_index():
                                                   stds=g['stds'], non_gt_index=g['non_gt_index'])
     assert np.array_equal(sscore, g['sorted_score']) and np.abs(sbbox - g['sorted_bbox']).max() <= 1e-4
     assert rel_err(multi, g['nms_multi_score']) < 2e-5
+
+
+def test_product_synth_generator_equals_oracle_generator():
+    """bench.py / tools draw their synthetic relation cases from relnet_b200.synth (so the product never imports oracle);
+    the parity tests draw theirs from oracle.relation_np: same seeds must give the same bits."""
+    import relnet_b200.synth as S
+    from oracle import relation_np as R
+    for kw in (dict(seed=2, N=30, d=64, H=4), dict(seed=5, N=17, d=128, H=16, init='ref', dq=1024, dout=128)):
+        a, b = S.make_relation_case(**kw), R.make_relation_case(**kw)
+        assert a.keys() == b.keys()
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
