@@ -99,7 +99,9 @@ int rn_linear_fwd(const float* x, const float* W, const float* b, float* y, int3
 /* RN_PREC_F16 has two decompositions of the N x M part, both tcgen05: the FUSED one (default: pair geometry + pair FC +
  * QK^T + softmax + P.V' in one cooperative launch, relation_fused.cu) and the round-1 one (geometry table [B,H,N,M] in
  * HBM -> tile attention -> combine).  rn_relation_fused_enable(0) selects the latter for A/B measurements (process-wide;
- * also RN_RELATION_UNFUSED=1 in the environment); returns the previous setting. */
+ * also RN_RELATION_UNFUSED=1 in the environment); 1 = fused with the pair embedding phi rounded to fp16 before the pair FC
+ * (default), 2 = fused with phi's fp16 residual fed to the FC as well (phi at ~fp32 accuracy; RN_FUSED_PHI_LO=1).
+ * Returns the previous setting. */
 int rn_relation_fused_enable(int32_t on);
 size_t rn_relation_packed_bytes(const rn_relation_desc* desc);
 int rn_relation_pack(const rn_relation_desc* desc, const float* Wq, const float* bq, const float* Wk, const float* bk,

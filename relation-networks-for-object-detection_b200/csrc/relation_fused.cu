@@ -40,7 +40,9 @@ struct FusedParams {
   int QT, T, R, Tr;                         // query tiles, key tiles, key ranges, key tiles per range
   int teams, ntasks;
   const float* boxes; const int* key_index;
-  const float* Wg; const float* bg; float rdim[8];  // rdim = 1 / wave_length^(k/8) (kept in the constant bank, not in registers)
+  const float* Wg; const float* bg;
+  float rdim[8];                            // 1 / wave_length^(k/8)              (constant bank, not registers)
+  float crev[8];                            // 100 ln2 / (2 pi wave_length^(k/8)): log2(x) * crev[k] = angle in revolutions
   float scale_log2;                         // log2(e) / sqrt(dk)
   const float* X; int ldx; float* out; int ldo; __half* out16; int ldo16; int relu;
   __half* gslots;                           // [teams][kFSlots][H producers][H consumers][128 queries][128/H keys]
@@ -70,15 +72,43 @@ __device__ __forceinline__ void split2_f(float v0, float v1, uint32_t* hi, uint3
   *hi = *reinterpret_cast<const uint32_t*>(&H2);
   *lo = *reinterpret_cast<const uint32_t*>(&L2);
 }
+// sin / cos of an angle given in REVOLUTIONS: exact removal of the integer part (magic-number rounding on the FMA pipe,
+// no FRND on the XU pipe), then MUFU on [-pi, pi]
+__device__ __forceinline__ void sincos_rev(float t, float* s, float* c) {
+  const float n = (t + 12582912.0f) - 12582912.0f;            // rint(t) for |t| < 2^22
+  const float y = (t - n) * 6.2831853071795865f;
+  *s = __sinf(y);
+  *c = __cosf(y);
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
 __device__ __forceinline__ void tmem_ld_32x32b_x4f(uint32_t taddr, uint32_t (&v)[4]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
 }
 
+// LO: also feed the fp16 residual of phi to the pair FC (A_lo.W_hi), i.e. phi at ~fp32 accuracy; without it phi is
+// rounded to fp16 (|err| <= 2.4e-4, the size of the reference's own float32 noise on the angles) and two key tiles share
+// one A stage (half the handshakes).  W is split hi/lo in both forms.
+template <bool LO>
 __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                       const __grid_constant__ CUtensorMap tmK,
                                                                       const __grid_constant__ CUtensorMap tmV,
                                                                       const FusedParams p) {
+  constexpr int TPS = LO ? 1 : 2;             // key tiles per A stage (a stage is 32 KB: hi + lo of one tile, or hi of two)
+  constexpr int NST = 8 / TPS;                // stages per round of 8 keys
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
@@ -86,7 +116,7 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
   uint8_t* sK = smem + kOffK;               // 2 x 16 KB
   uint8_t* sV = smem + kOffV;               // 2 x 16 KB
   uint8_t* sP = smem + kOffP;               // 32 KB: two [128 x 64-key] halves
-  uint8_t* sA = smem + kOffA;               // 2 x (hi 16 KB + lo 16 KB)
+  uint8_t* sA = smem + kOffA;               // 2 stages x 32 KB
   uint8_t* sBh = smem + kOffB; uint8_t* sBl = sBh + 2048;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint64_t* q_full = bars;                  // [1]
@@ -102,6 +132,7 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
   __shared__ float s_mx[4][128], s_sum[4][128];
   __shared__ float s_bias[16], s_rowabs[16];
+  __shared__ __align__(16) float s_ktab[2][2][8][16];   // [round parity][size coord][key][sin f0..7 | cos f0..7] of the key boxes
   __shared__ float s_gscale;
   __shared__ int s_last;
 
@@ -177,25 +208,31 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
       const uint32_t idesc_g = make_idesc_f16(128, 16, false, false, false);
       const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
       const uint32_t bh = smem_u32(sBh), bl = smem_u32(sBl);
-      uint32_t x = 0, u = 0, rc = 0, tc = 0;                     // blocks, pair tiles, FC rounds, tasks so far
+      uint32_t x = 0, u = 0, rc = 0, tc = 0;                     // blocks, A stages, FC rounds, tasks so far
       auto geom_mma = [&]() {                                    // the UMMAs of one block's geometry (rounds x 8 pair tiles)
         for (int rd = 0; rd < rounds; ++rd) {
           if (rc >= 1) mbar_wait(g_free, (rc - 1) & 1);
-          for (int i8 = 0; i8 < 8; ++i8) {
+          for (int st = 0; st < NST; ++st) {
             const uint32_t bf = u & 1;
             mbar_wait(&a_full[bf], (u >> 1) & 1);
             tc_fence_after();
-            const uint32_t ah = smem_u32(sA + bf * 32768), al = ah + 16384;
-            const uint32_t d = tG + i8 * 16;
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              mma_f16_ss(d, make_smem_desc_sw128(ah + k * 32, 16, 1024), make_smem_desc_sw128(bh + k * 32, 16, 1024), idesc_g, k > 0);
+            for (int kk = 0; kk < TPS; ++kk) {
+              const uint32_t ah = smem_u32(sA + bf * 32768) + (LO ? 0 : kk * 16384);
+              const uint32_t d = tG + (st * TPS + kk) * 16;
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              mma_f16_ss(d, make_smem_desc_sw128(al + k * 32, 16, 1024), make_smem_desc_sw128(bh + k * 32, 16, 1024), idesc_g, 1);
+              for (int k = 0; k < 4; ++k)
+                mma_f16_ss(d, make_smem_desc_sw128(ah + k * 32, 16, 1024), make_smem_desc_sw128(bh + k * 32, 16, 1024), idesc_g, k > 0);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              mma_f16_ss(d, make_smem_desc_sw128(ah + k * 32, 16, 1024), make_smem_desc_sw128(bl + k * 32, 16, 1024), idesc_g, 1);
+              for (int k = 0; k < 4; ++k)
+                mma_f16_ss(d, make_smem_desc_sw128(ah + k * 32, 16, 1024), make_smem_desc_sw128(bl + k * 32, 16, 1024), idesc_g, 1);
+              if (LO) {
+                const uint32_t al = ah + 16384;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  mma_f16_ss(d, make_smem_desc_sw128(al + k * 32, 16, 1024), make_smem_desc_sw128(bh + k * 32, 16, 1024), idesc_g, 1);
+              }
+            }
             mma_commit(&a_free[bf]);
             ++u;
           }
@@ -262,7 +299,8 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
     const int j = warp >> 2;                                      // coordinate (geometry) / 32-key slice (softmax) / 16-col slice (O)
     const int r = (warp & 3) * 32 + lane;                         // pair row / query row == TMEM lane
     const uint32_t lane_base = ((uint32_t)((warp & 3) * 32) << 16);
-    uint32_t x = 0, u = 0, rc = 0;                                // blocks consumed, pair tiles, FC rounds (CTA-local counts)
+    const uint32_t a_off0 = sw128_offset(r, 2 * j), a_off1 = sw128_offset(r, 2 * j + 1);   // this thread's two chunks of an A row
+    uint32_t x = 0, u = 0, rc = 0;                                // blocks consumed, A stages, FC rounds (CTA-local counts)
     uint32_t tb_base = 0;                                         // team-wide sequence number of the task's first block
     uint32_t pending_done = 0;                                    // thread 0: consumed blocks not yet reported to the team
 
@@ -270,10 +308,21 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
       const int rg = task % p.R, qt = (task / p.R) % p.QT, b = task / (p.R * p.QT);
       const int kt0 = rg * p.Tr, nT = min(p.T, kt0 + p.Tr) - kt0;
       const int q0 = qt * 128, n = q0 + r;
-      const float4 bq = __ldg(reinterpret_cast<const float4*>(p.boxes) + (size_t)b * p.N + min(n, p.N - 1));
-      const float wn = bq.z - bq.x + 1.f, hn = bq.w - bq.y + 1.f;
-      const float cxn = 0.5f * (bq.x + bq.z), cyn = 0.5f * (bq.y + bq.w);
-      const float rwn = __frcp_rn(wn), rhn = __frcp_rn(hn);
+      const float4* boxes4 = reinterpret_cast<const float4*>(p.boxes) + (size_t)b * p.N;
+      // query side of this thread's coordinate.  j = 0, 1 (centre distances, SYM_REL:56-69): eps = log max(|c_n - c_m| / s_n,
+      // 1e-3) needs the pair -> MUFU per pair.  j = 2, 3 (size ratios, :70-75): eps = log s_n - log s_m is separable, so
+      // sin / cos(alpha (a_n - a_m)) come from per-box tables by the angle-difference identities: no MUFU per pair.
+      float qc0, qc1;                                             // j<2: centre, 1/size
+      float qs[8], qcs[8];                                        // j>=2: sin / cos(100 log(size_n) / dim_k)
+      {
+        const float4 bq = __ldg(boxes4 + min(n, p.N - 1));
+        const float wn = bq.z - bq.x + 1.f, hn = bq.w - bq.y + 1.f;
+        qc0 = j == 0 ? 0.5f * (bq.x + bq.z) : 0.5f * (bq.y + bq.w);
+        qc1 = __frcp_rn(j == 0 ? wn : hn);
+        const float lq = log2f((j & 1) ? hn : wn);                // used by j >= 2 only (full-precision log: once per task)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sincos_rev(lq * p.crev[k], &qs[k], &qcs[k]);
+      }
 
       // ---- producer: geometry weights of this member's key slice of block (task-local index bi)
       auto geom = [&](int bi) {
@@ -282,33 +331,79 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
         __half* slot = p.gslots + ((((size_t)team * kFSlots + (tb % kFSlots)) * H + h) * H) * (size_t)(128 * ks);
 #pragma unroll 1
         for (int rd = 0; rd < rounds; ++rd) {
+          // key side of the round's 8 keys: lane i < 8 of every warp holds its coordinate's value of key i (j < 2: the
+          // centre; broadcast by shuffle per tile); warps 8..11 fill the sin/cos table of the two size coordinates
+          float kval = 0.f;
+          if (j < 2) {
+            if (lane < 8) {
+              const int m = min(mbase + rd * 8 + lane, p.M - 1);
+              const float4 bk = __ldg(boxes4 + (p.key_index ? p.key_index[m] : m));
+              kval = j == 0 ? 0.5f * (bk.x + bk.z) : 0.5f * (bk.y + bk.w);
+            }
+          } else {
+            if (warp < 12) {
+              const int tt = tid - 256, i8 = tt >> 4, cc = (tt >> 3) & 1, k = tt & 7;
+              const int m = min(mbase + rd * 8 + i8, p.M - 1);
+              const float4 bk = __ldg(boxes4 + (p.key_index ? p.key_index[m] : m));
+              const float lk = log2f(cc ? bk.w - bk.y + 1.f : bk.z - bk.x + 1.f);
+              float sk, ck;
+              sincos_rev(lk * p.crev[k], &sk, &ck);
+              s_ktab[rc & 1][cc][i8][k] = sk;
+              s_ktab[rc & 1][cc][i8][8 + k] = ck;
+            }
+            asm volatile("bar.sync 2, 256;" ::: "memory");        // warps 8..15
+          }
 #pragma unroll 1
-          for (int i8 = 0; i8 < 8; ++i8) {
-            const int m = min(mbase + rd * 8 + i8, p.M - 1);
-            const float4 bk = __ldg(reinterpret_cast<const float4*>(p.boxes) + (size_t)b * p.N + (p.key_index ? p.key_index[m] : m));
-            float e;                                              // eps[j] of SYM_REL:56-75 (division by the QUERY box)
-            if (j == 0) e = __logf(fmaxf(fabsf((cxn - 0.5f * (bk.x + bk.z)) * rwn), 1e-3f));
-            else if (j == 1) e = __logf(fmaxf(fabsf((cyn - 0.5f * (bk.y + bk.w)) * rhn), 1e-3f));
-            else if (j == 2) e = __logf(wn * __frcp_rn(bk.z - bk.x + 1.f));
-            else e = __logf(hn * __frcp_rn(bk.w - bk.y + 1.f));
-            const float a = 100.0f * e;
-            float sn[8], cs[8];
+          for (int st = 0; st < NST; ++st) {
+            uint32_t wh[TPS][8], wl[LO ? 8 : 1];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) sincos_2pi_f(a * p.rdim[k], &sn[k], &cs[k]);
-            uint32_t sh[4], sl[4], ch[4], cl[4];
+            for (int kk = 0; kk < TPS; ++kk) {
+              const int i8 = st * TPS + kk;
+              float sn[8], cs[8];
+              if (j < 2) {
+                const float km = __shfl_sync(0xffffffffu, kval, i8);
+                const float lg = lg2_approx(fmaxf(fabsf((qc0 - km) * qc1), 1e-3f));
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              split2_f(sn[2 * q], sn[2 * q + 1], &sh[q], &sl[q]);
-              split2_f(cs[2 * q], cs[2 * q + 1], &ch[q], &cl[q]);
+                for (int k = 0; k < 8; ++k) sincos_rev(lg * p.crev[k], &sn[k], &cs[k]);
+              } else {
+                const float4* kt = reinterpret_cast<const float4*>(&s_ktab[rc & 1][j & 1][i8][0]);
+                const float4 s0 = kt[0], s1 = kt[1], c0 = kt[2], c1 = kt[3];
+                const float ksn[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                const float kcs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {                     // sin(x - y) = sx cy - cx sy ; cos(x - y) = cx cy + sx sy
+                  sn[k] = fmaf(qs[k], kcs[k], -qcs[k] * ksn[k]);
+                  cs[k] = fmaf(qcs[k], kcs[k], qs[k] * ksn[k]);
+                }
+              }
+              if (LO) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  split2_f(sn[2 * q], sn[2 * q + 1], &wh[kk][q], &wl[q]);
+                  split2_f(cs[2 * q], cs[2 * q + 1], &wh[kk][4 + q], &wl[4 + q]);
+                }
+              } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  wh[kk][q] = pack_h2(sn[2 * q], sn[2 * q + 1]);
+                  wh[kk][4 + q] = pack_h2(cs[2 * q], cs[2 * q + 1]);
+                }
+              }
             }
             const uint32_t bf = u & 1;
             if (u >= 2) mbar_wait(&a_free[bf], ((u >> 1) - 1) & 1);
-            uint8_t* Ah = sA + bf * 32768; uint8_t* Al = Ah + 16384;
-            // row r of A: [coord c][sin f0..7 | cos f0..7] -> chunk 2c = sins, chunk 2c+1 = coses
-            *reinterpret_cast<uint4*>(Ah + sw128_offset(r, 2 * j)) = make_uint4(sh[0], sh[1], sh[2], sh[3]);
-            *reinterpret_cast<uint4*>(Al + sw128_offset(r, 2 * j)) = make_uint4(sl[0], sl[1], sl[2], sl[3]);
-            *reinterpret_cast<uint4*>(Ah + sw128_offset(r, 2 * j + 1)) = make_uint4(ch[0], ch[1], ch[2], ch[3]);
-            *reinterpret_cast<uint4*>(Al + sw128_offset(r, 2 * j + 1)) = make_uint4(cl[0], cl[1], cl[2], cl[3]);
+            uint8_t* As = sA + bf * 32768;
+            // row r of an A tile: [coord c][sin f0..7 | cos f0..7] -> chunk 2c = sins, chunk 2c+1 = coses
+#pragma unroll
+            for (int kk = 0; kk < TPS; ++kk) {
+              uint8_t* Ah = As + (LO ? 0 : kk * 16384);
+              *reinterpret_cast<uint4*>(Ah + a_off0) = make_uint4(wh[kk][0], wh[kk][1], wh[kk][2], wh[kk][3]);
+              *reinterpret_cast<uint4*>(Ah + a_off1) = make_uint4(wh[kk][4], wh[kk][5], wh[kk][6], wh[kk][7]);
+            }
+            if (LO) {
+              *reinterpret_cast<uint4*>(As + 16384 + a_off0) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+              *reinterpret_cast<uint4*>(As + 16384 + a_off1) = make_uint4(wl[4], wl[5], wl[6], wl[7]);
+            }
             fence_proxy_async_smem();
             mbar_arrive(&a_full[bf]);
             ++u;
@@ -338,12 +433,9 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
               const float bb = s_bias[hh];
               uint32_t pk[4];
 #pragma unroll
-              for (int i2 = 0; i2 < 4; ++i2) {
-                const float g0 = fmaxf(__uint_as_float(v[2 * i2][q]) + bb, 1e-6f) * gscale;
-                const float g1 = fmaxf(__uint_as_float(v[2 * i2 + 1][q]) + bb, 1e-6f) * gscale;
-                const __half2 hv = __floats2half2_rn(g0, g1);
-                pk[i2] = *reinterpret_cast<const uint32_t*>(&hv);
-              }
+              for (int i2 = 0; i2 < 4; ++i2)
+                pk[i2] = pack_h2(fmaxf(__uint_as_float(v[2 * i2][q]) + bb, 1e-6f) * gscale,
+                                 fmaxf(__uint_as_float(v[2 * i2 + 1][q]) + bb, 1e-6f) * gscale);
               *reinterpret_cast<uint4*>(slot + ((size_t)hh * 128 + r) * ks + rd * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
           }
@@ -366,63 +458,62 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
 #pragma unroll 1
       for (int i = -2; i < nT; ++i) {
         if (i >= 0) {
-        // ---------------------------------------------------------------------------------- consume block i
-        const uint32_t tb = tb_base + i;
-        const int m0 = (kt0 + i) * 128 + j * 32;                  // first key of this thread's slice
-        if (warp == 0) {                                          // EVERY teammate has published block tb
-          if (lane < H) while (ld_acquire_gpu(pub_ctr + lane) < tb + 1) {}
-          __syncwarp();
-        }
-        bar_compute();
-        uint4 gq[4];
-        {
-          const __half* slot = p.gslots + (((size_t)team * kFSlots + (tb % kFSlots)) * H) * (size_t)H * (128 * ks);
+          // -------------------------------------------------------------------------------- consume block i
+          const uint32_t tb = tb_base + i;
+          const int m0 = (kt0 + i) * 128 + j * 32;                // first key of this thread's slice
+          if (warp == 0) {                                        // EVERY teammate has published block tb
+            if (lane < H) while (ld_acquire_gpu(pub_ctr + lane) < tb + 1) {}
+            __syncwarp();
+          }
+          bar_compute();
+          uint4 gq[4];
+          {
+            const __half* slot = p.gslots + (((size_t)team * kFSlots + (tb % kFSlots)) * H) * (size_t)H * (128 * ks);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const int kk = j * 32 + 8 * c, pp = kk / ks, within = kk - pp * ks;
+              gq[c] = __ldcg(reinterpret_cast<const uint4*>(slot + (((size_t)pp * H + h) * 128 + r) * ks + within));
+            }
+          }
+          mbar_wait(s_full, x & 1);
+          tc_fence_after();
+          uint32_t sv[32];
+          tmem_ld_32x32b_x32(tS + lane_base + j * 32, sv);
+          tmem_ld_wait();
+          tc_fence_before();
+          if (m0 + 32 > p.M) {                                    // tail tile (warp-uniform): keys >= M never win the max, get p = 0
+#pragma unroll
+            for (int q = 0; q < 32; ++q) if (m0 + q >= p.M) sv[q] = 0xff800000u;      // -inf
+          }
+          float mx = -INFINITY;                                   // row maximum of the RAW scores (scale > 0 commutes with max)
+#pragma unroll
+          for (int q = 0; q < 32; ++q) mx = fmaxf(mx, __uint_as_float(sv[q]));
+          s_mx[j][r] = mx;
+          bar_compute();
+          mx = fmaxf(fmaxf(s_mx[0][r], s_mx[1][r]), fmaxf(s_mx[2][r], s_mx[3][r])) * p.scale_log2;
+          const float m_new = fmaxf(m_run, mx);                   // finite: every key tile holds at least one valid key
+          alpha = ex2_approx(m_run - m_new);                      // first block: 2^-inf = 0
+          m_run = m_new;
+          float lsum = 0.f;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            const int kk = j * 32 + 8 * c, pp = kk / ks, within = kk - pp * ks;
-            gq[c] = __ldcg(reinterpret_cast<const uint4*>(slot + (((size_t)pp * H + h) * 128 + r) * ks + within));
+            const uint32_t gw[4] = {gq[c].x, gq[c].y, gq[c].z, gq[c].w};
+            uint32_t pk[4];
+#pragma unroll
+            for (int i2 = 0; i2 < 4; ++i2) {
+              const float2 g2 = __half22float2(*reinterpret_cast<const __half2*>(&gw[i2]));
+              const float p0 = g2.x * ex2_approx(fmaf(__uint_as_float(sv[c * 8 + 2 * i2]), p.scale_log2, -m_new));
+              const float p1 = g2.y * ex2_approx(fmaf(__uint_as_float(sv[c * 8 + 2 * i2 + 1]), p.scale_log2, -m_new));
+              lsum += p0 + p1;
+              pk[i2] = pack_h2(p0, p1);
+            }
+            *reinterpret_cast<uint4*>(sP + (j >> 1) * 16384 + sw128_offset(r, (j & 1) * 4 + c)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }
-        }
-        mbar_wait(s_full, x & 1);
-        tc_fence_after();
-        uint32_t sv[32];
-        tmem_ld_32x32b_x32(tS + lane_base + j * 32, sv);
-        tmem_ld_wait();
-        tc_fence_before();
-        float t[32];
-        float mx = -INFINITY;
-#pragma unroll
-        for (int q = 0; q < 32; ++q) {
-          t[q] = (m0 + q < p.M) ? __uint_as_float(sv[q]) * p.scale_log2 : -INFINITY;
-          mx = fmaxf(mx, t[q]);
-        }
-        s_mx[j][r] = mx;
-        bar_compute();
-        mx = fmaxf(fmaxf(s_mx[0][r], s_mx[1][r]), fmaxf(s_mx[2][r], s_mx[3][r]));
-        const float m_new = fmaxf(m_run, mx);                     // finite: every key tile holds at least one valid key
-        alpha = exp2f(m_run - m_new);                             // first block: exp2(-inf) = 0
-        m_run = m_new;
-        float lsum = 0.f;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const uint32_t gw[4] = {gq[c].x, gq[c].y, gq[c].z, gq[c].w};
-          uint32_t pk[4];
-#pragma unroll
-          for (int i2 = 0; i2 < 4; ++i2) {
-            const float2 g2 = __half22float2(*reinterpret_cast<const __half2*>(&gw[i2]));
-            const float p0 = g2.x * exp2f(t[c * 8 + 2 * i2] - m_new);        // exp2(-inf) = 0 masks keys >= M
-            const float p1 = g2.y * exp2f(t[c * 8 + 2 * i2 + 1] - m_new);
-            lsum += p0 + p1;
-            const __half2 hv = __floats2half2_rn(p0, p1);
-            pk[i2] = *reinterpret_cast<const uint32_t*>(&hv);
-          }
-          *reinterpret_cast<uint4*>(sP + (j >> 1) * 16384 + sw128_offset(r, (j & 1) * 4 + c)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        }
-        l_run = fmaf(l_run, alpha, lsum);
-        fence_proxy_async_smem();
-        tc_fence_before();
-        mbar_arrive(p_full);
-        if (tid == 0) ++pending_done;
+          l_run = fmaf(l_run, alpha, lsum);
+          fence_proxy_async_smem();
+          tc_fence_before();
+          mbar_arrive(p_full);
+          if (tid == 0) ++pending_done;
         }
         // ---------------------------------------------------------------------------------- produce two blocks ahead
         if (i + 2 < nT) geom(i + 2);
@@ -580,7 +671,7 @@ size_t relation_fused_ws_bytes(const rn_relation_desc* d) {
 
 int relation_fused_launch(const rn_relation_desc* d, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
                           const float* boxes, const int* key_index, const float* Wg, const float* bg, const float* X,
-                          float* out, void* out_f16, void* wsp, size_t ws_bytes, cudaStream_t st) {
+                          float* out, void* out_f16, void* wsp, size_t ws_bytes, cudaStream_t st, bool phi_lo) {
   FusedPlan pl;
   RN_CHECK_ARG(fused_plan(d, &pl), "relation_fused: shape not covered (H=%d E=%d dq=%d dout=%d)", d->H, d->E, d->dq, d->dout);
   const int H = d->H, sms = sm_count() > 0 ? sm_count() : 148;
@@ -603,14 +694,18 @@ int relation_fused_launch(const rn_relation_desc* d, const CUtensorMap& tmQ, con
   GeomFreq fr;
   int r = make_freq(d->E, d->wave_length, &fr);
   if (r) return r;
-  for (int k = 0; k < 8; ++k) p.rdim[k] = 1.0f / fr.dim[k];          // == __frcp_rn(dim) of the unfused kernels (IEEE division)
+  for (int k = 0; k < 8; ++k) {
+    p.rdim[k] = 1.0f / fr.dim[k];
+    p.crev[k] = (float)(100.0 * 0.6931471805599453 / (6.283185307179586 * (double)fr.dim[k]));
+  }
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)(d->dq / H));
   p.X = d->fuse_residual_relu ? X : nullptr; p.ldx = d->d;
   p.out = out; p.ldo = d->dout; p.out16 = (__half*)out_f16; p.ldo16 = d->dout; p.relu = d->fuse_residual_relu;
   p.gslots = gslots; p.counters = counters; p.part_o = part_o; p.part_ml = part_ml;
   static thread_local bool configured = false;
   if (!configured) {
-    RN_CUDA(cudaFuncSetAttribute(relation_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmem));
+    RN_CUDA(cudaFuncSetAttribute(relation_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmem));
+    RN_CUDA(cudaFuncSetAttribute(relation_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmem));
     configured = true;
   }
   cudaLaunchConfig_t cfg = {};
@@ -622,7 +717,8 @@ int relation_fused_launch(const rn_relation_desc* d, const CUtensorMap& tmQ, con
   at[0].id = cudaLaunchAttributeCooperative;          // all CTAs co-resident: team members wait for each other
   at[0].val.cooperative = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  RN_CUDA(cudaLaunchKernelEx(&cfg, relation_fused_kernel, tmQ, tmK, tmV, p));
+  if (phi_lo) RN_CUDA(cudaLaunchKernelEx(&cfg, relation_fused_kernel<true>, tmQ, tmK, tmV, p));
+  else RN_CUDA(cudaLaunchKernelEx(&cfg, relation_fused_kernel<false>, tmQ, tmK, tmV, p));
   return RN_OK;
 }
 

@@ -541,10 +541,16 @@ bool relation_fused_ok(const rn_relation_desc* d);
 size_t relation_fused_ws_bytes(const rn_relation_desc* d);
 int relation_fused_launch(const rn_relation_desc* d, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
                           const float* boxes, const int* key_index, const float* Wg, const float* bg, const float* X,
-                          float* out, void* out_f16, void* wsp, size_t ws_bytes, cudaStream_t st);
+                          float* out, void* out_f16, void* wsp, size_t ws_bytes, cudaStream_t st, bool phi_lo);
 // RN_RELATION_UNFUSED=1 (or rn_relation_fused_enable(0)) keeps the round-1 decomposition (geometry kernel -> [B,H,N,M]
 // table -> tile attention + combine): the A/B arm of the measurements, not a fallback -- both are tcgen05 paths
-static int g_fused_on = [] { const char* e = getenv("RN_RELATION_UNFUSED"); return (e && e[0] == '1') ? 0 : 1; }();
+// g_fused_on: 0 = unfused, 1 = fused with phi rounded to fp16 (default), 2 = fused with the fp16 residual of phi as well
+static int g_fused_on = [] {
+  const char* e = getenv("RN_RELATION_UNFUSED");
+  if (e && e[0] == '1') return 0;
+  const char* l = getenv("RN_FUSED_PHI_LO");
+  return (l && l[0] == '1') ? 2 : 1;
+}();
 static bool use_fused(const rn_relation_desc* d) { return g_fused_on && relation_fused_ok(d); }
 
 static bool tc_shape_ok(const rn_relation_desc* d) {
@@ -663,7 +669,7 @@ int relation_tc_packed(const rn_relation_desc* d, const float* X, const float* b
   if ((r = encode_tmap_3d_f16(&tmK, Kp, B, M, H * 64, ldk, bk_pitch, 128, 64))) return r;
   if ((r = encode_tmap_3d_f16(&tmV, Vp, B, M, H * 64, ldk, bk_pitch, 128, 64))) return r;
   if (fused)           // geometry + attention: one cooperative launch, nothing N x M in HBM
-    return relation_fused_launch(d, tmQ, tmK, tmV, boxes, key_index, Wg, bg, X, out, out_f16, gws, gws_bytes, st);
+    return relation_fused_launch(d, tmQ, tmK, tmV, boxes, key_index, Wg, bg, X, out, out_f16, gws, gws_bytes, st, g_fused_on == 2);
   AttnParams p;
   p.N = N; p.M = M; p.H = H; p.T = T;
   p.lg = lg; p.ldg = ldg;
@@ -825,7 +831,7 @@ int relation_tc_lnms(const rn_relation_desc* d, const float* X, const float* emb
 
 extern "C" int rn_relation_fused_enable(int32_t on) {
   const int prev = rn::g_fused_on;
-  rn::g_fused_on = on ? 1 : 0;
+  rn::g_fused_on = on < 0 ? 0 : (on > 2 ? 2 : on);
   return prev;
 }
 

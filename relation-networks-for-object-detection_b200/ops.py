@@ -214,8 +214,9 @@ def relation_tc_supported(dq, dout, group, return_softmax=False):
 
 def relation_fused_enable(on):
     """A/B switch of the RN_PREC_F16 relation module: 1 = fused geometry + attention launch (default), 0 = round-1
-    decomposition (geometry table -> tile attention -> combine).  Returns the previous setting."""
-    return int(L.lib().rn_relation_fused_enable(int(bool(on))))
+    decomposition (geometry table -> tile attention -> combine), 2 = fused with phi's fp16 residual in the pair FC.
+    Returns the previous setting."""
+    return int(L.lib().rn_relation_fused_enable(int(on)))
 
 
 def pos_embed(boxes, M=None, key_index=None, E=64, wave_length=1000.0, want_eps=True, want_emb=True):

@@ -63,6 +63,9 @@ def test_fused_matches_oracle_and_unfused(ops, N, M, d, H):
     fused = run(ops, t, 1, M=M, group=H, residual_relu=True).cpu().numpy()
     e, frac = report('fused N=%d M=%d d=%d H=%d' % (N, M, d, H), fused, ref)
     assert e < 1e-3 and frac < 0.02
+    lo = run(ops, t, 2, M=M, group=H, residual_relu=True).cpu().numpy()        # phi hi + lo in the pair FC
+    e_lo, _ = report('fused + phi residual', lo, ref)
+    assert e_lo < 1e-3
     if d // H == 64:                      # the round-1 tile kernel is the d_k = 64 arm
         unf = run(ops, t, 0, M=M, group=H, residual_relu=True).cpu().numpy()
         e2, _ = report('unfused', unf, ref)

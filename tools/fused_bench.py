@@ -23,6 +23,7 @@ flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
 
 def graph_time(fn, reps=15):
+    torch.cuda.synchronize()              # the capture stream must not overlap earlier work on the same workspace
     s = torch.cuda.Stream()
     with torch.cuda.stream(s):
         for _ in range(3):
@@ -59,8 +60,11 @@ for N, d, H in points:
         ws = torch.empty(ops.relation_workspace_bytes(N, N, d, d, d, H) + 4096, dtype=torch.uint8, device=dev)
         kw = dict(group=H, residual_relu=True, precision='f16', workspace=ws)
         outs[arm] = ops.relation(*t, **kw).clone()
+        print('[%s N=%d] first call done' % (arm, N), file=sys.stderr, flush=True)
         rec[arm + '_nm_us'] = round(graph_time(lambda: ops.relation(*t, stage_mask=6, **kw)), 2)
+        print('[%s N=%d] nm timed' % (arm, N), file=sys.stderr, flush=True)
         rec[arm + '_module_us'] = round(graph_time(lambda: ops.relation(*t, **kw)), 2)
+        print('[%s N=%d] module timed' % (arm, N), file=sys.stderr, flush=True)
         ach = 4.0 * N * N * d / (rec[arm + '_nm_us'] * 1e-6) / 1e12
         rec[arm + '_tflops'] = round(ach, 2)
         rec[arm + '_frac_of_measured_bf16_peak'] = round(ach / peak, 4)
