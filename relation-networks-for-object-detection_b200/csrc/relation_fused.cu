@@ -31,7 +31,8 @@ using namespace umma;
 constexpr int kFThreads = 544;              // 16 compute warps + 1 TMA/UMMA warp
 constexpr int kFSlots = 4;                  // ring depth of the g exchange (blocks in flight per team)
 constexpr int kOffQ = 0, kOffK = 16384, kOffV = 49152, kOffP = 81920, kOffA = 114688, kOffB = 180224,
-              kOffBar = 184320;
+              kOffG = 184320, kOffBar = 217088;
+static_assert(kFSlots >= 4, "a block is published two iterations before it is read: slot reuse needs a 4-deep ring");
 constexpr int kFSmem = kOffBar + 256 + 1024;
 constexpr int kStagePitch = 68;             // floats per row of the output staging tile (aliases the A buffers)
 
@@ -46,7 +47,7 @@ struct FusedParams {
   float scale_log2;                         // log2(e) / sqrt(dk)
   const float* X; int ldx; float* out; int ldo; __half* out16; int ldo16; int relu;
   __half* gslots;                           // [teams][kFSlots][H producers][H consumers][128 queries][128/H keys]
-  unsigned* counters;                       // [teams][32] = published[16], consumed[16] PER MEMBER ; then tickets [B*QT*H]
+  unsigned* counters;                       // [teams][32]: published[16] PER MEMBER (+16 spare) ; then tickets [B*QT*H]
   float* part_o; float* part_ml;            // [R][B][H][N][64], [R][B][H][N][2]
 };
 
@@ -117,7 +118,8 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
   uint8_t* sV = smem + kOffV;               // 2 x 16 KB
   uint8_t* sP = smem + kOffP;               // 32 KB: two [128 x 64-key] halves
   uint8_t* sA = smem + kOffA;               // 2 stages x 32 KB
-  uint8_t* sBh = smem + kOffB; uint8_t* sBl = sBh + 2048;
+  uint8_t* sBh = smem + kOffB; uint8_t* sBl = sBh + 2048;       // one 32-row tile: rows 0..15 = W_hi, rows 16..31 = W_lo
+  uint8_t* sG = smem + kOffG;                 // this head's 128 x 128 fp16 g tile of the current block ([16-byte chunk][row])
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint64_t* q_full = bars;                  // [1]
   uint64_t* k_full = bars + 1;              // [2]
@@ -140,10 +142,12 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
   const int H = p.H, ks = 128 / H, rounds = ks >> 3;
   const int team = blockIdx.x / H, h = blockIdx.x % H;
   // per-member progress counters (an aggregate count cannot express "EVERY member has ..."): member m has published
-  // pub_ctr[m] blocks and finished reading done_ctr[m] blocks; 16 + 16 words = one 128-byte line per team
+  // pub_ctr[m] blocks.  No "consumed" counter is needed: a member publishes block y only after it has read block y - 2, so
+  // "every member has published block i" implies "every member has finished reading block i - 2", which is the block whose
+  // ring slot block i + 2 overwrites (kFSlots = 4).
   unsigned* pub_ctr = p.counters + 32 * team;
-  unsigned* done_ctr = pub_ctr + 16;
   unsigned* tickets = p.counters + 32 * p.teams;
+  const int ks_shift = 31 - __clz(ks);
 
   // ------------------------------------------------------------------------------------------------ prologue
   if (warp == 16) {
@@ -197,7 +201,7 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
   }
   __syncthreads();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base, tG = tmem_base + 128, tPV = tmem_base + 256;
+  const uint32_t tS = tmem_base, tG = tmem_base + 128, tPV = tmem_base + 384;       // S 128 | pair FC 8 keys x 32 | PV 64
   const float gscale = s_gscale;
 
   if (warp == 16) {
@@ -205,9 +209,10 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
     if (lane == 0) {
       const uint32_t idesc_s = make_idesc_f16(128, 128, false, false, false);
       const uint32_t idesc_o = make_idesc_f16(128, 64, false, false, true);
-      const uint32_t idesc_g = make_idesc_f16(128, 16, false, false, false);
+      const uint32_t idesc_g = make_idesc_f16(128, 32, false, false, false);     // [W_hi; W_lo] stacked: one UMMA per K step
+      const uint32_t idesc_gl = make_idesc_f16(128, 16, false, false, false);    // LO: A_lo . W_hi into the hi columns
       const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
-      const uint32_t bh = smem_u32(sBh), bl = smem_u32(sBl);
+      const uint32_t bh = smem_u32(sBh);
       uint32_t x = 0, u = 0, rc = 0, tc = 0;                     // blocks, A stages, FC rounds, tasks so far
       auto geom_mma = [&]() {                                    // the UMMAs of one block's geometry (rounds x 8 pair tiles)
         for (int rd = 0; rd < rounds; ++rd) {
@@ -219,18 +224,15 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
 #pragma unroll
             for (int kk = 0; kk < TPS; ++kk) {
               const uint32_t ah = smem_u32(sA + bf * 32768) + (LO ? 0 : kk * 16384);
-              const uint32_t d = tG + (st * TPS + kk) * 16;
+              const uint32_t d = tG + (st * TPS + kk) * 32;      // per key: columns 0..15 = A.W_hi, 16..31 = A.W_lo
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 mma_f16_ss(d, make_smem_desc_sw128(ah + k * 32, 16, 1024), make_smem_desc_sw128(bh + k * 32, 16, 1024), idesc_g, k > 0);
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                mma_f16_ss(d, make_smem_desc_sw128(ah + k * 32, 16, 1024), make_smem_desc_sw128(bl + k * 32, 16, 1024), idesc_g, 1);
               if (LO) {
                 const uint32_t al = ah + 16384;
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  mma_f16_ss(d, make_smem_desc_sw128(al + k * 32, 16, 1024), make_smem_desc_sw128(bh + k * 32, 16, 1024), idesc_g, 1);
+                  mma_f16_ss(d, make_smem_desc_sw128(al + k * 32, 16, 1024), make_smem_desc_sw128(bh + k * 32, 16, 1024), idesc_gl, 1);
               }
             }
             mma_commit(&a_free[bf]);
@@ -268,8 +270,9 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
         issue_s(x);
 #pragma unroll 1
         for (int i = -2; i < nT; ++i) {
+          if (i + 2 < nT) geom_mma();                            // the compute warps evaluate phi of block i + 2 first ...
           if (i >= 0) {
-            mbar_wait(p_full, x & 1);                            // softmax of block x done: S and the previous PV are consumed
+            mbar_wait(p_full, x & 1);                            // ... then the softmax of block x: S and the previous PV are consumed
             tc_fence_after();
             if (i + 1 < nT) {
               mbar_arrive_expect_tx(&v_full[(x + 1) & 1], 16384);
@@ -290,7 +293,6 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
             mma_commit(pv_full);
             ++x;
           }
-          if (i + 2 < nT) geom_mma();
         }
       }
     }
@@ -302,7 +304,7 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
     const uint32_t a_off0 = sw128_offset(r, 2 * j), a_off1 = sw128_offset(r, 2 * j + 1);   // this thread's two chunks of an A row
     uint32_t x = 0, u = 0, rc = 0;                                // blocks consumed, A stages, FC rounds (CTA-local counts)
     uint32_t tb_base = 0;                                         // team-wide sequence number of the task's first block
-    uint32_t pending_done = 0;                                    // thread 0: consumed blocks not yet reported to the team
+    const int qbar = 3 + (warp & 3);                              // named barrier of the 4 warps that share a TMEM lane quarter
 
     for (int task = team; task < p.ntasks; task += p.teams) {
       const int rg = task % p.R, qt = (task / p.R) % p.QT, b = task / (p.R * p.QT);
@@ -324,126 +326,131 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
         for (int k = 0; k < 8; ++k) sincos_rev(lq * p.crev[k], &qs[k], &qcs[k]);
       }
 
-      // ---- producer: geometry weights of this member's key slice of block (task-local index bi)
-      auto geom = [&](int bi) {
-        const uint32_t tb = tb_base + bi;
-        const int mbase = (kt0 + bi) * 128 + h * ks;
-        __half* slot = p.gslots + ((((size_t)team * kFSlots + (tb % kFSlots)) * H + h) * H) * (size_t)(128 * ks);
-#pragma unroll 1
-        for (int rd = 0; rd < rounds; ++rd) {
-          // key side of the round's 8 keys: lane i < 8 of every warp holds its coordinate's value of key i (j < 2: the
-          // centre; broadcast by shuffle per tile); warps 8..11 fill the sin/cos table of the two size coordinates
-          float kval = 0.f;
-          if (j < 2) {
-            if (lane < 8) {
-              const int m = min(mbase + rd * 8 + lane, p.M - 1);
-              const float4 bk = __ldg(boxes4 + (p.key_index ? p.key_index[m] : m));
-              kval = j == 0 ? 0.5f * (bk.x + bk.z) : 0.5f * (bk.y + bk.w);
-            }
-          } else {
-            if (warp < 12) {
-              const int tt = tid - 256, i8 = tt >> 4, cc = (tt >> 3) & 1, k = tt & 7;
-              const int m = min(mbase + rd * 8 + i8, p.M - 1);
-              const float4 bk = __ldg(boxes4 + (p.key_index ? p.key_index[m] : m));
-              const float lk = log2f(cc ? bk.w - bk.y + 1.f : bk.z - bk.x + 1.f);
-              float sk, ck;
-              sincos_rev(lk * p.crev[k], &sk, &ck);
-              s_ktab[rc & 1][cc][i8][k] = sk;
-              s_ktab[rc & 1][cc][i8][8 + k] = ck;
-            }
-            asm volatile("bar.sync 2, 256;" ::: "memory");        // warps 8..15
+      // ---- producer, first half: phi of this member's key slice of block bi -> A stages (the UMMA warp turns them into
+      // the pair FC).  Only for rounds == 1 (H = 16) can the read-back be deferred past the softmax; with more rounds the
+      // TMEM accumulator of a round must be drained before the next round's UMMAs.
+      auto phi_round = [&](int bi, int rd) {
+        const int mbase = (kt0 + bi) * 128 + h * ks + rd * 8;
+        // key side of the round's 8 keys: lane i < 8 of every warp holds its coordinate's value of key i (j < 2: the
+        // centre; broadcast by shuffle per tile); warps 8..11 fill the sin/cos table of the two size coordinates
+        float kval = 0.f;
+        if (j < 2) {
+          if (lane < 8) {
+            const int m = min(mbase + lane, p.M - 1);
+            const float4 bk = __ldg(boxes4 + (p.key_index ? p.key_index[m] : m));
+            kval = j == 0 ? 0.5f * (bk.x + bk.z) : 0.5f * (bk.y + bk.w);
           }
+        } else {
+          if (warp < 12) {
+            const int tt = tid - 256, i8 = tt >> 4, cc = (tt >> 3) & 1, k = tt & 7;
+            const int m = min(mbase + i8, p.M - 1);
+            const float4 bk = __ldg(boxes4 + (p.key_index ? p.key_index[m] : m));
+            const float lk = log2f(cc ? bk.w - bk.y + 1.f : bk.z - bk.x + 1.f);
+            float sk, ck;
+            sincos_rev(lk * p.crev[k], &sk, &ck);
+            s_ktab[rc & 1][cc][i8][k] = sk;
+            s_ktab[rc & 1][cc][i8][8 + k] = ck;
+          }
+          asm volatile("bar.sync 2, 256;" ::: "memory");        // warps 8..15
+        }
 #pragma unroll 1
-          for (int st = 0; st < NST; ++st) {
-            uint32_t wh[TPS][8], wl[LO ? 8 : 1];
+        for (int st = 0; st < NST; ++st) {
+          uint32_t wh[TPS][8], wl[LO ? 8 : 1];
 #pragma unroll
-            for (int kk = 0; kk < TPS; ++kk) {
-              const int i8 = st * TPS + kk;
-              float sn[8], cs[8];
-              if (j < 2) {
-                const float km = __shfl_sync(0xffffffffu, kval, i8);
-                const float lg = lg2_approx(fmaxf(fabsf((qc0 - km) * qc1), 1e-3f));
+          for (int kk = 0; kk < TPS; ++kk) {
+            const int i8 = st * TPS + kk;
+            float sn[8], cs[8];
+            if (j < 2) {
+              const float km = __shfl_sync(0xffffffffu, kval, i8);
+              const float lg = lg2_approx(fmaxf(fabsf((qc0 - km) * qc1), 1e-3f));
 #pragma unroll
-                for (int k = 0; k < 8; ++k) sincos_rev(lg * p.crev[k], &sn[k], &cs[k]);
-              } else {
-                const float4* kt = reinterpret_cast<const float4*>(&s_ktab[rc & 1][j & 1][i8][0]);
-                const float4 s0 = kt[0], s1 = kt[1], c0 = kt[2], c1 = kt[3];
-                const float ksn[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-                const float kcs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+              for (int k = 0; k < 8; ++k) sincos_rev(lg * p.crev[k], &sn[k], &cs[k]);
+            } else {
+              const float4* kt = reinterpret_cast<const float4*>(&s_ktab[rc & 1][j & 1][i8][0]);
+              const float4 s0 = kt[0], s1 = kt[1], c0 = kt[2], c1 = kt[3];
+              const float ksn[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+              const float kcs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {                     // sin(x - y) = sx cy - cx sy ; cos(x - y) = cx cy + sx sy
-                  sn[k] = fmaf(qs[k], kcs[k], -qcs[k] * ksn[k]);
-                  cs[k] = fmaf(qcs[k], kcs[k], qs[k] * ksn[k]);
-                }
+              for (int k = 0; k < 8; ++k) {                     // sin(x - y) = sx cy - cx sy ; cos(x - y) = cx cy + sx sy
+                sn[k] = fmaf(qs[k], kcs[k], -qcs[k] * ksn[k]);
+                cs[k] = fmaf(qcs[k], kcs[k], qs[k] * ksn[k]);
               }
-              if (LO) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  split2_f(sn[2 * q], sn[2 * q + 1], &wh[kk][q], &wl[q]);
-                  split2_f(cs[2 * q], cs[2 * q + 1], &wh[kk][4 + q], &wl[4 + q]);
-                }
-              } else {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  wh[kk][q] = pack_h2(sn[2 * q], sn[2 * q + 1]);
-                  wh[kk][4 + q] = pack_h2(cs[2 * q], cs[2 * q + 1]);
-                }
-              }
-            }
-            const uint32_t bf = u & 1;
-            if (u >= 2) mbar_wait(&a_free[bf], ((u >> 1) - 1) & 1);
-            uint8_t* As = sA + bf * 32768;
-            // row r of an A tile: [coord c][sin f0..7 | cos f0..7] -> chunk 2c = sins, chunk 2c+1 = coses
-#pragma unroll
-            for (int kk = 0; kk < TPS; ++kk) {
-              uint8_t* Ah = As + (LO ? 0 : kk * 16384);
-              *reinterpret_cast<uint4*>(Ah + a_off0) = make_uint4(wh[kk][0], wh[kk][1], wh[kk][2], wh[kk][3]);
-              *reinterpret_cast<uint4*>(Ah + a_off1) = make_uint4(wh[kk][4], wh[kk][5], wh[kk][6], wh[kk][7]);
             }
             if (LO) {
-              *reinterpret_cast<uint4*>(As + 16384 + a_off0) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
-              *reinterpret_cast<uint4*>(As + 16384 + a_off1) = make_uint4(wl[4], wl[5], wl[6], wl[7]);
-            }
-            fence_proxy_async_smem();
-            mbar_arrive(&a_full[bf]);
-            ++u;
-          }
-          // heads 4j..4j+3 of this thread's query row for the 8 keys of the round
-          mbar_wait(g_full, rc & 1);
-          tc_fence_after();
-          uint32_t v[8][4];
 #pragma unroll
-          for (int i8 = 0; i8 < 8; ++i8) tmem_ld_32x32b_x4f(tG + lane_base + i8 * 16 + 4 * j, v[i8]);
+              for (int q = 0; q < 4; ++q) {
+                split2_f(sn[2 * q], sn[2 * q + 1], &wh[kk][q], &wl[q]);
+                split2_f(cs[2 * q], cs[2 * q + 1], &wh[kk][4 + q], &wl[4 + q]);
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                wh[kk][q] = pack_h2(sn[2 * q], sn[2 * q + 1]);
+                wh[kk][4 + q] = pack_h2(cs[2 * q], cs[2 * q + 1]);
+              }
+            }
+          }
+          const uint32_t bf = u & 1;
+          if (u >= 2) mbar_wait(&a_free[bf], ((u >> 1) - 1) & 1);
+          uint8_t* As = sA + bf * 32768;
+          // row r of an A tile: [coord c][sin f0..7 | cos f0..7] -> chunk 2c = sins, chunk 2c+1 = coses
+#pragma unroll
+          for (int kk = 0; kk < TPS; ++kk) {
+            uint8_t* Ah = As + (LO ? 0 : kk * 16384);
+            *reinterpret_cast<uint4*>(Ah + a_off0) = make_uint4(wh[kk][0], wh[kk][1], wh[kk][2], wh[kk][3]);
+            *reinterpret_cast<uint4*>(Ah + a_off1) = make_uint4(wh[kk][4], wh[kk][5], wh[kk][6], wh[kk][7]);
+          }
+          if (LO) {
+            *reinterpret_cast<uint4*>(As + 16384 + a_off0) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+            *reinterpret_cast<uint4*>(As + 16384 + a_off1) = make_uint4(wl[4], wl[5], wl[6], wl[7]);
+          }
+          fence_proxy_async_smem();
+          mbar_arrive(&a_full[bf]);
+          ++u;
+        }
+      };
+      // ---- producer, second half: the round's FC results (heads 4j..4j+3 of this thread's query row, 8 keys; hi and lo
+      // partial sums) -> g = max(x + b, 1e-6) * scale -> fp16 -> the team's ring slot
+      auto readback_round = [&](int bi, int rd) {
+        const uint32_t tb = tb_base + bi;
+        __half* slot = p.gslots + ((((size_t)team * kFSlots + (tb % kFSlots)) * H + h) * H) * (size_t)(128 * ks);
+        mbar_wait(g_full, rc & 1);
+        tc_fence_after();
+        float gsum[8][4];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t vh[4][4], vl[4][4];
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4) {
+            tmem_ld_32x32b_x4f(tG + lane_base + (half * 4 + i4) * 32 + 4 * j, vh[i4]);
+            tmem_ld_32x32b_x4f(tG + lane_base + (half * 4 + i4) * 32 + 16 + 4 * j, vl[i4]);
+          }
           tmem_ld_wait();
-          tc_fence_before();
-          mbar_arrive(g_free);
-          ++rc;
-          if (rd == 0) {                                          // the ring slot must have been read by EVERY teammate
-            if (warp == 0 && tb >= (uint32_t)kFSlots) {
-              const unsigned need = tb - kFSlots + 1;             // blocks 0 .. tb - kFSlots consumed
-              if (lane < H) while (ld_acquire_gpu(done_ctr + lane) < need) {}
-              __syncwarp();
-            }
-            bar_compute();
-          }
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int hh = 4 * j + q;
-            if (hh < H) {
-              const float bb = s_bias[hh];
-              uint32_t pk[4];
+          for (int i4 = 0; i4 < 4; ++i4)
 #pragma unroll
-              for (int i2 = 0; i2 < 4; ++i2)
-                pk[i2] = pack_h2(fmaxf(__uint_as_float(v[2 * i2][q]) + bb, 1e-6f) * gscale,
-                                 fmaxf(__uint_as_float(v[2 * i2 + 1][q]) + bb, 1e-6f) * gscale);
-              *reinterpret_cast<uint4*>(slot + ((size_t)hh * 128 + r) * ks + rd * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            }
+            for (int q = 0; q < 4; ++q) gsum[half * 4 + i4][q] = __uint_as_float(vh[i4][q]) + __uint_as_float(vl[i4][q]);
+        }
+        tc_fence_before();
+        mbar_arrive(g_free);
+        ++rc;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int hh = 4 * j + q;
+          if (hh < H) {
+            const float bb = s_bias[hh];
+            uint32_t pk[4];
+#pragma unroll
+            for (int i2 = 0; i2 < 4; ++i2)
+              pk[i2] = pack_h2(fmaxf(gsum[2 * i2][q] + bb, 1e-6f) * gscale, fmaxf(gsum[2 * i2 + 1][q] + bb, 1e-6f) * gscale);
+            *reinterpret_cast<uint4*>(slot + ((size_t)hh * 128 + r) * ks + rd * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }
         }
+      };
+      auto publish = [&]() {
         bar_compute();                                            // every store of the slab is issued ...
         if (tid == 0) {
           __threadfence();                                        // ... and ordered before the team counter (release)
-          if (pending_done) { atomicAdd(done_ctr + h, pending_done); pending_done = 0; }
           atomicAdd(pub_ctr + h, 1u);
         }
       };
@@ -453,28 +460,38 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
       for (int i = 0; i < 16; ++i) o[i] = 0.f;
       float m_run = -INFINITY, l_run = 0.f, alpha = 0.f;
 
-      // iteration i: softmax + P of block i, geometry of block i + 2 (two blocks ahead: hides the exchange latency and
-      // the P.V' UMMA), fold of block i.  i = -2, -1 only produce (one call site keeps the code in the instruction cache)
+      // iteration i:  wait for block i's publication -> async copy of its g tile -> phi of block i + 2 (UMMAs drain while
+      // ...) -> softmax + P of block i -> read back / publish block i + 2 -> fold P.V' of block i.  Two blocks of lead hide
+      // the exchange latency; i = -2, -1 only produce.  (One call site per phase keeps the code in the instruction cache.)
 #pragma unroll 1
       for (int i = -2; i < nT; ++i) {
+        const uint32_t tb = tb_base + i;
         if (i >= 0) {
-          // -------------------------------------------------------------------------------- consume block i
-          const uint32_t tb = tb_base + i;
-          const int m0 = (kt0 + i) * 128 + j * 32;                // first key of this thread's slice
           if (warp == 0) {                                        // EVERY teammate has published block tb
             if (lane < H) while (ld_acquire_gpu(pub_ctr + lane) < tb + 1) {}
             __syncwarp();
           }
           bar_compute();
-          uint4 gq[4];
-          {
-            const __half* slot = p.gslots + (((size_t)team * kFSlots + (tb % kFSlots)) * H) * (size_t)H * (128 * ks);
+          const __half* slot = p.gslots + (((size_t)team * kFSlots + (tb % kFSlots)) * H) * (size_t)H * (128 * ks);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const int kk = j * 32 + 8 * c, pp = kk / ks, within = kk - pp * ks;
-              gq[c] = __ldcg(reinterpret_cast<const uint4*>(slot + (((size_t)pp * H + h) * 128 + r) * ks + within));
-            }
+          for (int c = 0; c < 4; ++c) {
+            const int kk = j * 32 + 8 * c, pp = kk >> ks_shift, within = kk & (ks - 1);
+            const __half* src = slot + (((size_t)pp * H + h) * 128 + r) * ks + within;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sG + ((j * 4 + c) * 128 + r) * 16)), "l"(src) : "memory");
           }
+          asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        // ---------------------------------------------------------------------------------- phi of block i + 2
+        const bool prod = i + 2 < nT;
+        if (prod) {
+          for (int rd = 0; rd < rounds; ++rd) {
+            phi_round(i + 2, rd);
+            if (rd + 1 < rounds) readback_round(i + 2, rd);       // H < 16: drain the accumulator between rounds
+          }
+        }
+        if (i >= 0) {
+          // -------------------------------------------------------------------------------- softmax + P of block i
+          const int m0 = (kt0 + i) * 128 + j * 32;                // first key of this thread's slice
           mbar_wait(s_full, x & 1);
           tc_fence_after();
           uint32_t sv[32];
@@ -489,15 +506,17 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
 #pragma unroll
           for (int q = 0; q < 32; ++q) mx = fmaxf(mx, __uint_as_float(sv[q]));
           s_mx[j][r] = mx;
-          bar_compute();
+          asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");   // the 4 warps of this lane quarter
           mx = fmaxf(fmaxf(s_mx[0][r], s_mx[1][r]), fmaxf(s_mx[2][r], s_mx[3][r])) * p.scale_log2;
           const float m_new = fmaxf(m_run, mx);                   // finite: every key tile holds at least one valid key
           alpha = ex2_approx(m_run - m_new);                      // first block: 2^-inf = 0
           m_run = m_new;
+          asm volatile("cp.async.wait_group 0;" ::: "memory");    // this thread's own 4 chunks of g
           float lsum = 0.f;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            const uint32_t gw[4] = {gq[c].x, gq[c].y, gq[c].z, gq[c].w};
+            const uint4 gq = *reinterpret_cast<const uint4*>(sG + ((j * 4 + c) * 128 + r) * 16);
+            const uint32_t gw[4] = {gq.x, gq.y, gq.z, gq.w};
             uint32_t pk[4];
 #pragma unroll
             for (int i2 = 0; i2 < 4; ++i2) {
@@ -513,10 +532,12 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
           fence_proxy_async_smem();
           tc_fence_before();
           mbar_arrive(p_full);
-          if (tid == 0) ++pending_done;
         }
-        // ---------------------------------------------------------------------------------- produce two blocks ahead
-        if (i + 2 < nT) geom(i + 2);
+        // ---------------------------------------------------------------------------------- publish block i + 2
+        if (prod) {
+          readback_round(i + 2, rounds - 1);
+          publish();
+        }
         if (i < 0) continue;
         // ---------------------------------------------------------------------------------- fold O += P V'
         mbar_wait(pv_full, x & 1);
@@ -620,7 +641,6 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
       }
       bar_compute();                                              // the staging tile aliases the next task's A buffers
     }
-    if (tid == 0 && pending_done) atomicAdd(done_ctr + h, pending_done);
   }
   tc_fence_before();
   __syncthreads();
