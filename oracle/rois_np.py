@@ -182,3 +182,94 @@ def deform_conv_backward(dout, data, offset, weight, kernel=(3, 3), pad=(2, 2), 
     if has_bias:
         res.append(dout.sum(axis=(0, 2, 3)).astype(np.float32))
     return res
+
+
+# ---------------------------------------------------------------------------------------------------------
+# The REFERENCE's own deformable kernels (oracle/_ref/libref_deform.so, built by the Makefile from
+# /root/reference/relation_rcnn/operator_cxx/{nn/deformable_im2col.cuh, deformable_psroi_pooling.cu} + ref_deform.cu).
+# They take DEVICE pointers: arguments are torch CUDA tensors (float32, contiguous).  GPU box only.
+_ref_deform = None
+
+
+def ref_deform_available():
+    return os.path.exists(os.path.join(HERE, '_ref', 'libref_deform.so'))
+
+
+def _refd():
+    global _ref_deform
+    if _ref_deform is None:
+        _ref_deform = ctypes.CDLL(os.path.join(HERE, '_ref', 'libref_deform.so'))
+    return _ref_deform
+
+
+def _dp(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def ref_deform_im2col(im, offset, kernel=(3, 3), pad=(2, 2), stride=(1, 1), dilate=(2, 2), num_deformable_group=4):
+    """deformable_im2col (deformable_im2col.cuh:283-309) on im [C,H,W], offset [dg*2*kh*kw,Ho,Wo] -> col [C*kh*kw,Ho,Wo]."""
+    import torch
+    C, H, W = im.shape
+    col = torch.empty((C * kernel[0] * kernel[1], offset.shape[1], offset.shape[2]), dtype=torch.float32, device=im.device)
+    rc = _refd().ref_deformable_im2col(_dp(im), _dp(offset), C, H, W, kernel[0], kernel[1], pad[0], pad[1], stride[0],
+                                       stride[1], dilate[0], dilate[1], num_deformable_group, _dp(col))
+    assert rc == 0, rc
+    return col
+
+
+def ref_deform_col2im(col, offset, im_shape, kernel=(3, 3), pad=(2, 2), stride=(1, 1), dilate=(2, 2), num_deformable_group=4):
+    """deformable_col2im (:381-411), req = kWriteTo semantics of the op (grad buffer zeroed by the caller: done here)."""
+    import torch
+    C, H, W = im_shape
+    g = torch.zeros((C, H, W), dtype=torch.float32, device=col.device)
+    rc = _refd().ref_deformable_col2im(_dp(col), _dp(offset), C, H, W, kernel[0], kernel[1], pad[0], pad[1], stride[0],
+                                       stride[1], dilate[0], dilate[1], num_deformable_group, _dp(g))
+    assert rc == 0, rc
+    return g
+
+
+def ref_deform_col2im_coord(col, im, offset, kernel=(3, 3), pad=(2, 2), stride=(1, 1), dilate=(2, 2), num_deformable_group=4):
+    """deformable_col2im_coord (:490-519) -> grad_offset, shaped like offset."""
+    import torch
+    C, H, W = im.shape
+    g = torch.zeros_like(offset)
+    rc = _refd().ref_deformable_col2im_coord(_dp(col), _dp(im), _dp(offset), C, H, W, kernel[0], kernel[1], pad[0], pad[1],
+                                             stride[0], stride[1], dilate[0], dilate[1], num_deformable_group, _dp(g))
+    assert rc == 0, rc
+    return g
+
+
+def ref_deform_psroi_pool(data, rois, trans=None, spatial_scale=0.0625, output_dim=256, group_size=1, pooled_size=7,
+                          part_size=0, sample_per_part=4, trans_std=0.0):
+    """DeformablePSROIPoolingOp::Forward (-inl.h:64-95 + .cu:52-175): returns (out, top_count)."""
+    import torch
+    _, C, H, W = data.shape
+    R = rois.shape[0]
+    no_trans = trans is None
+    t = torch.zeros(1, device=data.device) if no_trans else trans
+    ncls = 1 if no_trans else trans.shape[1] // 2
+    out = torch.empty((R, output_dim, pooled_size, pooled_size), dtype=torch.float32, device=data.device)
+    cnt = torch.empty_like(out)
+    rc = _refd().ref_deform_psroi_forward(_dp(data), _dp(rois), _dp(t), R, C, H, W, int(no_trans),
+                                          ctypes.c_float(spatial_scale), output_dim, group_size, pooled_size, part_size,
+                                          sample_per_part, ctypes.c_float(trans_std), ncls, _dp(out), _dp(cnt))
+    assert rc == 0, rc
+    return out, cnt
+
+
+def ref_deform_psroi_pool_backward(dout, top_count, data, rois, trans=None, spatial_scale=0.0625, output_dim=256,
+                                   group_size=1, pooled_size=7, part_size=0, sample_per_part=4, trans_std=0.0):
+    """DeformablePSROIPoolingOp::Backward (-inl.h:97-151 + .cu:177-345): returns (ddata, dtrans or None)."""
+    import torch
+    _, C, H, W = data.shape
+    R = rois.shape[0]
+    no_trans = trans is None
+    t = torch.zeros(1, device=data.device) if no_trans else trans
+    ncls = 1 if no_trans else trans.shape[1] // 2
+    dd = torch.empty_like(data)
+    dt = torch.zeros(1, device=data.device) if no_trans else torch.empty_like(trans)
+    rc = _refd().ref_deform_psroi_backward(_dp(dout), _dp(data), _dp(rois), _dp(t), _dp(top_count), R, C, H, W, int(no_trans),
+                                           ctypes.c_float(spatial_scale), output_dim, group_size, pooled_size, part_size,
+                                           sample_per_part, ctypes.c_float(trans_std), ncls, _dp(dd), _dp(dt))
+    assert rc == 0, rc
+    return dd, (None if no_trans else dt)
