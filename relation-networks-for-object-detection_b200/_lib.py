@@ -3,7 +3,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'librelnet_b200.so')
+# RELNET_LIB: measurement variants of the same sources (tools/, build.py RELNET_VARIANT); unset = the product library
+LIB_PATH = os.environ.get('RELNET_LIB') or os.path.join(HERE, 'librelnet_b200.so')
 
 c_f = C.c_float
 c_i = C.c_int32

@@ -14,8 +14,11 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 INC = os.path.join(os.path.dirname(HERE), 'include')
-OBJ = os.path.join(HERE, 'build')
-LIB = os.path.join(HERE, 'librelnet_b200.so')
+# measurement variant (tools/fused_trace.py): RELNET_VARIANT=trace builds build_trace/librelnet_b200_trace.so with
+# -DRN_FUSED_TRACE next to, never instead of, the product library
+VARIANT = os.environ.get('RELNET_VARIANT', '')
+OBJ = os.path.join(HERE, 'build' + ('_' + VARIANT if VARIANT else ''))
+LIB = os.path.join(OBJ, 'librelnet_b200_%s.so' % VARIANT) if VARIANT else os.path.join(HERE, 'librelnet_b200.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 
 COMMON = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-Xcompiler', '-fPIC',
@@ -40,7 +43,8 @@ def _stamp():
 
 def _compile(src):
     obj = os.path.join(OBJ, src[:-3] + '.o')
-    cmd = [NVCC] + COMMON + (['-fmad=false'] if src in NO_FMA else []) + ['-c', os.path.join(CSRC, src), '-o', obj]
+    cmd = [NVCC] + COMMON + (['-fmad=false'] if src in NO_FMA else []) + (['-DRN_FUSED_TRACE'] if VARIANT == 'trace' else []) + ['-D' + d for d in os.environ.get('RELNET_DEFINES', '').split() if VARIANT] + \
+        ['-c', os.path.join(CSRC, src), '-o', obj]
     p = subprocess.run(cmd, capture_output=True, text=True)
     return src, obj, p.returncode, p.stdout + p.stderr
 

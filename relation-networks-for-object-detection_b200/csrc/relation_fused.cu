@@ -34,7 +34,30 @@ constexpr int kOffQ = 0, kOffK = 16384, kOffV = 49152, kOffP = 81920, kOffA = 11
               kOffG = 184320, kOffBar = 217088;
 static_assert(kFSlots >= 4, "a block is published two iterations before it is read: slot reuse needs a 4-deep ring");
 constexpr int kFSmem = kOffBar + 256 + 1024;
+#ifdef RN_AB_NO_ELECT
+constexpr int kArriveA = 512;
+#else
+constexpr int kArriveA = 16;
+#endif
 constexpr int kStagePitch = 68;             // floats per row of the output staging tile (aliases the A buffers)
+
+// Measurement build only (tools/fused_trace.py compiles a private copy of the library with -DRN_FUSED_TRACE; the product
+// library has no trace code, no trace parameter and no trace symbol).
+#ifdef RN_FUSED_TRACE
+__device__ long long* g_fused_trace = nullptr;          // 16 stamps per CTA
+#define RN_TRACE(i) do { if (threadIdx.x == 0 && g_fused_trace) g_fused_trace[blockIdx.x * 16 + (i)] = ((i) == 0 || (i) == 15) ? (long long)globaltimer_ns() : clock64(); } while (0)
+__device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#else
+#define RN_TRACE(i) do { } while (0)
+#endif
+// second measurement variant: per-stage stamps of the first phi round, for thread 0 (a centre-coordinate warp) and thread
+// 256 (a size-coordinate warp): 32 slots per CTA
+#ifdef RN_FUSED_TRACE2
+__device__ long long* g_fused_trace2 = nullptr;
+#define RN_T2(i) do { if ((threadIdx.x == 0 || threadIdx.x == 256) && g_fused_trace2) g_fused_trace2[blockIdx.x * 32 + (threadIdx.x == 256 ? 16 : 0) + (i)] = clock64(); } while (0)
+#else
+#define RN_T2(i) do { } while (0)
+#endif
 
 struct FusedParams {
   int B, N, M, H, dv;
@@ -44,6 +67,7 @@ struct FusedParams {
   const float* Wg; const float* bg;
   float rdim[8];                            // 1 / wave_length^(k/8)              (constant bank, not registers)
   float crev[8];                            // 100 ln2 / (2 pi wave_length^(k/8)): log2(x) * crev[k] = angle in revolutions
+  float crad[8];                            // 100 ln2 / wave_length^(k/8):        log2(x) * crad[k] = angle in radians
   float scale_log2;                         // log2(e) / sqrt(dk)
   const float* X; int ldx; float* out; int ldo; __half* out16; int ldo16; int relu;
   __half* gslots;                           // [teams][kFSlots][H producers][H consumers][128 queries][128/H keys]
@@ -141,6 +165,7 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int H = p.H, ks = 128 / H, rounds = ks >> 3;
   const int team = blockIdx.x / H, h = blockIdx.x % H;
+  RN_TRACE(0); RN_TRACE(1);
   // per-member progress counters (an aggregate count cannot express "EVERY member has ..."): member m has published
   // pub_ctr[m] blocks.  No "consumed" counter is needed: a member publishes block y only after it has read block y - 2, so
   // "every member has published block i" implies "every member has finished reading block i - 2", which is the block whose
@@ -155,9 +180,9 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
       prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
       mbar_init(q_full, 1);
       for (int i = 0; i < 2; ++i) {
-        mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&a_full[i], 512); mbar_init(&a_free[i], 1);
+        mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&a_full[i], kArriveA); mbar_init(&a_free[i], 1);
       }
-      mbar_init(s_full, 1); mbar_init(p_full, 512); mbar_init(pv_full, 1); mbar_init(g_full, 1); mbar_init(g_free, 512);
+      mbar_init(s_full, 1); mbar_init(p_full, 16); mbar_init(pv_full, 1); mbar_init(g_full, 1); mbar_init(g_free, 16);   // one arrival per compute WARP
       fence_barrier_init();
     }
     __syncwarp();
@@ -200,6 +225,7 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
     s_gscale = exp2f((float)(15 - e));       // g * scale <= 2^15 ; 1e-6 * scale stays a normal fp16 for gm < 512
   }
   __syncthreads();
+  RN_TRACE(2);                              // prologue done
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base, tG = tmem_base + 128, tPV = tmem_base + 384;       // S 128 | pair FC 8 keys x 32 | PV 64
   const float gscale = s_gscale;
@@ -329,23 +355,39 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
       // ---- producer, first half: phi of this member's key slice of block bi -> A stages (the UMMA warp turns them into
       // the pair FC).  Only for rounds == 1 (H = 16) can the read-back be deferred past the softmax; with more rounds the
       // TMEM accumulator of a round must be drained before the next round's UMMAs.
-      auto phi_round = [&](int bi, int rd) {
+      // key-side value of this thread for the 8 keys of (block bi, round rd): j < 2: lane i < 8 holds the centre of key i
+      // (broadcast by shuffle per tile); warps 8..11: thread (key i8, coord cc, freq k) holds the size of key i8.  Loaded
+      // one round AHEAD (kpre) so that the L2 / DRAM latency of the box never sits at the head of a round.
+      auto key_value = [&](int bi, int rd) -> float {
         const int mbase = (kt0 + bi) * 128 + h * ks + rd * 8;
-        // key side of the round's 8 keys: lane i < 8 of every warp holds its coordinate's value of key i (j < 2: the
-        // centre; broadcast by shuffle per tile); warps 8..11 fill the sin/cos table of the two size coordinates
-        float kval = 0.f;
         if (j < 2) {
-          if (lane < 8) {
-            const int m = min(mbase + lane, p.M - 1);
-            const float4 bk = __ldg(boxes4 + (p.key_index ? p.key_index[m] : m));
-            kval = j == 0 ? 0.5f * (bk.x + bk.z) : 0.5f * (bk.y + bk.w);
-          }
-        } else {
+          if (lane >= 8) return 0.f;
+          const int m = min(mbase + lane, p.M - 1);
+          const float4 bk = __ldg(boxes4 + (p.key_index ? p.key_index[m] : m));
+          return j == 0 ? 0.5f * (bk.x + bk.z) : 0.5f * (bk.y + bk.w);
+        }
+        if (warp >= 12) return 0.f;
+        const int tt = tid - 256, i8 = tt >> 4, cc = (tt >> 3) & 1;
+        const int m = min(mbase + i8, p.M - 1);
+        const float4 bk = __ldg(boxes4 + (p.key_index ? p.key_index[m] : m));
+        return cc ? bk.w - bk.y + 1.f : bk.z - bk.x + 1.f;
+      };
+      float kpre = key_value(0, 0);
+      auto phi_round = [&](int bi, int rd) {
+        if (bi == 0) RN_T2(0);
+#ifdef RN_AB_NO_PREFETCH
+        const float kval = key_value(bi, rd);
+#else
+        const float kval = kpre;
+        {
+          const int nrd = rd + 1 < rounds ? rd + 1 : 0, nbi = rd + 1 < rounds ? bi : bi + 1;
+          if (nbi < nT) kpre = key_value(nbi, nrd);
+        }
+#endif
+        if (j >= 2) {
           if (warp < 12) {
             const int tt = tid - 256, i8 = tt >> 4, cc = (tt >> 3) & 1, k = tt & 7;
-            const int m = min(mbase + i8, p.M - 1);
-            const float4 bk = __ldg(boxes4 + (p.key_index ? p.key_index[m] : m));
-            const float lk = log2f(cc ? bk.w - bk.y + 1.f : bk.z - bk.x + 1.f);
+            const float lk = log2f(kval);
             float sk, ck;
             sincos_rev(lk * p.crev[k], &sk, &ck);
             s_ktab[rc & 1][cc][i8][k] = sk;
@@ -353,8 +395,10 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
           }
           asm volatile("bar.sync 2, 256;" ::: "memory");        // warps 8..15
         }
+        if (bi == 0) RN_T2(1);
 #pragma unroll 1
         for (int st = 0; st < NST; ++st) {
+          if (bi == 0 && st < 4) RN_T2(2 + 3 * st);
           uint32_t wh[TPS][8], wl[LO ? 8 : 1];
 #pragma unroll
           for (int kk = 0; kk < TPS; ++kk) {
@@ -363,8 +407,15 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
             if (j < 2) {
               const float km = __shfl_sync(0xffffffffu, kval, i8);
               const float lg = lg2_approx(fmaxf(fabsf((qc0 - km) * qc1), 1e-3f));
+              if (LO) {
 #pragma unroll
-              for (int k = 0; k < 8; ++k) sincos_rev(lg * p.crev[k], &sn[k], &cs[k]);
+                for (int k = 0; k < 8; ++k) sincos_rev(lg * p.crev[k], &sn[k], &cs[k]);
+              } else {
+                // phi is rounded to fp16 (2.4e-4) in this form: the MUFU's own range reduction (|angle| <= 690 rad ->
+                // <= 2.6e-4 rad) is at that level, and costs 2 FMA-pipe ops per frequency instead of 7
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { const float a = lg * p.crad[k]; sn[k] = __sinf(a); cs[k] = __cosf(a); }
+              }
             } else {
               const float4* kt = reinterpret_cast<const float4*>(&s_ktab[rc & 1][j & 1][i8][0]);
               const float4 s0 = kt[0], s1 = kt[1], c0 = kt[2], c1 = kt[3];
@@ -391,7 +442,9 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
             }
           }
           const uint32_t bf = u & 1;
+          if (bi == 0 && st < 4) RN_T2(3 + 3 * st);
           if (u >= 2) mbar_wait(&a_free[bf], ((u >> 1) - 1) & 1);
+          if (bi == 0 && st < 4) RN_T2(4 + 3 * st);
           uint8_t* As = sA + bf * 32768;
           // row r of an A tile: [coord c][sin f0..7 | cos f0..7] -> chunk 2c = sins, chunk 2c+1 = coses
 #pragma unroll
@@ -404,8 +457,14 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
             *reinterpret_cast<uint4*>(As + 16384 + a_off0) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
             *reinterpret_cast<uint4*>(As + 16384 + a_off1) = make_uint4(wl[4], wl[5], wl[6], wl[7]);
           }
+          if (bi == 0 && st < 4) RN_T2(14);                       // (overwritten per stage: last = after the final stage's stores)
           fence_proxy_async_smem();
+#ifdef RN_AB_NO_ELECT
           mbar_arrive(&a_full[bf]);
+#else
+          __syncwarp();                                           // every lane's stores are fenced: one arrival per warp
+          if (lane == 0) mbar_arrive(&a_full[bf]);
+#endif
           ++u;
         }
       };
@@ -432,7 +491,8 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
             for (int q = 0; q < 4; ++q) gsum[half * 4 + i4][q] = __uint_as_float(vh[i4][q]) + __uint_as_float(vl[i4][q]);
         }
         tc_fence_before();
-        mbar_arrive(g_free);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(g_free);
         ++rc;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -449,10 +509,12 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
       };
       auto publish = [&]() {
         bar_compute();                                            // every store of the slab is issued ...
-        if (tid == 0) {
-          __threadfence();                                        // ... and ordered before the team counter (release)
-          atomicAdd(pub_ctr + h, 1u);
-        }
+#ifdef RN_AB_NO_RED
+        if (tid == 0) { __threadfence(); atomicAdd(pub_ctr + h, 1u); }
+#else
+        if (tid == 0)                                             // ... and ordered before the team counter (release)
+          asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(pub_ctr + h) : "memory");
+#endif
       };
 
       float o[16];
@@ -472,6 +534,7 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
             __syncwarp();
           }
           bar_compute();
+          if (i == 0) RN_TRACE(6);                                // every teammate published block 0
           const __half* slot = p.gslots + (((size_t)team * kFSlots + (tb % kFSlots)) * H) * (size_t)H * (128 * ks);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
@@ -488,11 +551,13 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
             phi_round(i + 2, rd);
             if (rd + 1 < rounds) readback_round(i + 2, rd);       // H < 16: drain the accumulator between rounds
           }
+          if (i == -2) RN_TRACE(3);                               // phi of the first block written
         }
         if (i >= 0) {
           // -------------------------------------------------------------------------------- softmax + P of block i
           const int m0 = (kt0 + i) * 128 + j * 32;                // first key of this thread's slice
           mbar_wait(s_full, x & 1);
+          if (i == 0) RN_TRACE(7);                                // S visible
           tc_fence_after();
           uint32_t sv[32];
           tmem_ld_32x32b_x32(tS + lane_base + j * 32, sv);
@@ -512,6 +577,7 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
           alpha = ex2_approx(m_run - m_new);                      // first block: 2^-inf = 0
           m_run = m_new;
           asm volatile("cp.async.wait_group 0;" ::: "memory");    // this thread's own 4 chunks of g
+          if (i == 0) RN_TRACE(8);                                // g tile landed
           float lsum = 0.f;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
@@ -531,16 +597,21 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
           l_run = fmaf(l_run, alpha, lsum);
           fence_proxy_async_smem();
           tc_fence_before();
-          mbar_arrive(p_full);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(p_full);
+          if (i == 0) RN_TRACE(9);                                // P written
         }
         // ---------------------------------------------------------------------------------- publish block i + 2
         if (prod) {
           readback_round(i + 2, rounds - 1);
+          if (i == -2) RN_TRACE(4);                               // FC read back, g stored
           publish();
+          if (i == -2) RN_TRACE(5);                               // published
         }
         if (i < 0) continue;
         // ---------------------------------------------------------------------------------- fold O += P V'
         mbar_wait(pv_full, x & 1);
+        if (i == 0) RN_TRACE(10);                                 // P.V' visible
         tc_fence_after();
         {
           uint32_t pv[16];
@@ -568,6 +639,7 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
       if (p.R > 1 && j == 0 && n < p.N)
         reinterpret_cast<float2*>(p.part_ml)[(((size_t)rg * p.B + b) * H + h) * p.N + n] = make_float2(m_run, l_tot);
       bar_compute();
+      RN_TRACE(11);                                               // tile staged
       bool finalize = p.R == 1;
       if (p.R > 1) {
         // un-normalised partial tile -> workspace (row-contiguous 256-byte segments), then the ticket
@@ -586,9 +658,59 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
         }
         bar_compute();
         finalize = s_last != 0;
+        RN_TRACE(12);                                             // partials stored, ticket taken
       }
       if (finalize) {
-        for (int it = tid; it < 128 * 16; it += 512) {
+        // R > 1, last team of this (query tile, head): pull the R partial tiles through shared memory with cp.async (three
+        // 32 KB tile buffers: the two A stages and the g tile; the (m, l) pairs go to the idle P buffer) so that the whole
+        // merge costs ~one L2 round trip per group of three partials instead of five dependent round trips per item
+        float4 acc[4]; float Mx[4], Ls[4];
+        if (p.R > 1) {
+          float2* sml = reinterpret_cast<float2*>(sP);            // [R][128]
+          for (int it = tid; it < p.R * 128; it += 512) {
+            const int sidx = it >> 7, row = it & 127;
+            const int nn = min(q0 + row, p.N - 1);
+            const float2* src = reinterpret_cast<const float2*>(p.part_ml) + (((size_t)sidx * p.B + b) * H + h) * p.N + nn;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(sml + it)), "l"(src) : "memory");
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { acc[k] = make_float4(0.f, 0.f, 0.f, 0.f); Mx[k] = -INFINITY; Ls[k] = 0.f; }
+          for (int s0 = 0; s0 < p.R; s0 += 3) {
+            const int ns = min(3, p.R - s0);
+            for (int g = 0; g < ns; ++g) {
+              uint8_t* buf = g == 0 ? sA : (g == 1 ? sA + 32768 : sG);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int it = tid + k * 512, row = it >> 4, c4 = it & 15;
+                const int nn = min(q0 + row, p.N - 1);
+                const float* src = p.part_o + ((((size_t)(s0 + g) * p.B + b) * H + h) * p.N + nn) * 64 + c4 * 4;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(buf + it * 16)), "l"(src) : "memory");
+              }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            bar_compute();
+            for (int g = 0; g < ns; ++g) {
+              const uint8_t* buf = g == 0 ? sA : (g == 1 ? sA + 32768 : sG);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int it = tid + k * 512, row = it >> 4;
+                const float2 ml = sml[(s0 + g) * 128 + row];
+                const float4 po = *reinterpret_cast<const float4*>(buf + it * 16);
+                const float mn = fmaxf(Mx[k], ml.x);
+                const float wo = ex2_approx(Mx[k] - mn), wn = ex2_approx(ml.x - mn);
+                acc[k].x = fmaf(wn, po.x, acc[k].x * wo); acc[k].y = fmaf(wn, po.y, acc[k].y * wo);
+                acc[k].z = fmaf(wn, po.z, acc[k].z * wo); acc[k].w = fmaf(wn, po.w, acc[k].w * wo);
+                Ls[k] = fmaf(wn, ml.y, Ls[k] * wo);
+                Mx[k] = mn;
+              }
+            }
+            if (s0 + 3 < p.R) bar_compute();                      // the tile buffers are refilled by the next group
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int it = tid + k * 512;
           const int row = it >> 4, c4 = it & 15;
           const int nn = q0 + row;
           if (nn >= p.N || c4 * 4 >= p.dv) continue;
@@ -596,21 +718,8 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
           if (p.R == 1) {
             y = *reinterpret_cast<const float4*>(stage + row * kStagePitch + c4 * 4);
           } else {
-            float mm = -INFINITY;
-            for (int s = 0; s < p.R; ++s)
-              mm = fmaxf(mm, __ldcg(reinterpret_cast<const float2*>(p.part_ml) + (((size_t)s * p.B + b) * H + h) * p.N + nn).x);
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            float l = 0.f;
-            for (int s = 0; s < p.R; ++s) {
-              const size_t prow = (((size_t)s * p.B + b) * H + h) * p.N + nn;
-              const float2 ml = __ldcg(reinterpret_cast<const float2*>(p.part_ml) + prow);
-              const float w = exp2f(ml.x - mm);
-              const float4 po = __ldcg(reinterpret_cast<const float4*>(p.part_o + prow * 64) + c4);
-              acc.x = fmaf(w, po.x, acc.x); acc.y = fmaf(w, po.y, acc.y); acc.z = fmaf(w, po.z, acc.z); acc.w = fmaf(w, po.w, acc.w);
-              l = fmaf(w, ml.y, l);
-            }
-            const float inv = 1.f / l;
-            y = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+            const float inv = 1.f / Ls[k];
+            y = make_float4(acc[k].x * inv, acc[k].y * inv, acc[k].z * inv, acc[k].w * inv);
           }
           float yy[4] = {y.x, y.y, y.z, y.w};
           float* dst = p.out + ((size_t)b * p.N + nn) * p.ldo + (size_t)h * p.dv + c4 * 4;
@@ -640,12 +749,29 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
         }
       }
       bar_compute();                                              // the staging tile aliases the next task's A buffers
+      RN_TRACE(13);                                               // task done (merged / final rows stored)
     }
   }
   tc_fence_before();
   __syncthreads();
+  RN_TRACE(14); RN_TRACE(15);
   if (warp == 16) tmem_dealloc<512>(tmem_base);
 }
+
+#ifdef RN_FUSED_TRACE
+}  // namespace rn
+extern "C" int rn_fused_trace_set(void* buf) {
+  return (int)cudaMemcpyToSymbol(rn::g_fused_trace, &buf, sizeof(void*));
+}
+namespace rn {
+#endif
+#ifdef RN_FUSED_TRACE2
+}  // namespace rn
+extern "C" int rn_fused_trace2_set(void* buf) {
+  return (int)cudaMemcpyToSymbol(rn::g_fused_trace2, &buf, sizeof(void*));
+}
+namespace rn {
+#endif
 
 // ------------------------------------------------------------------------------------------------------------ host
 struct FusedPlan { int teams, QT, T, R, Tr, ntasks; };
@@ -717,6 +843,7 @@ int relation_fused_launch(const rn_relation_desc* d, const CUtensorMap& tmQ, con
   for (int k = 0; k < 8; ++k) {
     p.rdim[k] = 1.0f / fr.dim[k];
     p.crev[k] = (float)(100.0 * 0.6931471805599453 / (6.283185307179586 * (double)fr.dim[k]));
+    p.crad[k] = (float)(100.0 * 0.6931471805599453 / (double)fr.dim[k]);
   }
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)(d->dq / H));
   p.X = d->fuse_residual_relu ? X : nullptr; p.ldx = d->d;

@@ -212,6 +212,13 @@ def relation_tc_supported(dq, dout, group, return_softmax=False):
             and not return_softmax)
 
 
+def relation_fused_active():
+    """Current setting of the A/B switch (0 = round-1 decomposition, 1 / 2 = fused)."""
+    prev = int(L.lib().rn_relation_fused_enable(1))
+    L.lib().rn_relation_fused_enable(prev)
+    return prev
+
+
 def relation_fused_enable(on):
     """A/B switch of the RN_PREC_F16 relation module: 1 = fused geometry + attention launch (default), 0 = round-1
     decomposition (geometry table -> tile attention -> combine), 2 = fused with phi's fp16 residual in the pair FC.

@@ -91,8 +91,8 @@ class RelationHead(object):
     def geometry_early(self, rois):
         """Both relation modules' geometry terms depend only on the rois: run them now (on whatever stream is current,
         e.g. beside res5 / the ROI-pool + fc_new_1 GEMM); detect(..., geometry_done=True) then skips that stage."""
-        if self.precision != 'f16':
-            return False
+        if self.precision != 'f16' or ops.relation_fused_active():
+            return False          # fused relation kernel: the geometry is evaluated inside the attention launch
         boxes = rois[:, 1:].contiguous()
         dummy = self._dummy.get(boxes.shape[0])
         if dummy is None:
