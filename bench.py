@@ -8,8 +8,11 @@ proposal -> ROI pool -> fc_new_1 -> relation#1 -> fc_new_2 -> relation#2 -> cls/
   e2e        same through the public API with the image in pinned HOST memory (H2D inside the timed region) and the
              detections (sorted boxes + final scores) copied back to the host every step
   hot_path   the same step without the trunk (trunk outputs resident) + relation-module microseconds
-  roofline   the fused tcgen05 relation kernel (relation_attn_tile_kernel + combine at this size) timed alone with CUDA events at N=M=300, d=1024,
-             H=16: achieved = 4*N*M*d FLOP / duration against the measured bf16 peak (MEASURED_PEAKS.json)
+  roofline   the fused relation kernel (relation_fused_kernel: geometry + pair FC + QK^T + softmax + P.V' in one launch)
+             timed alone as a captured graph at N=M=300, d=1024, H=16: achieved = 4*N*M*d FLOP / duration against the
+             measured bf16 peak (MEASURED_PEAKS.json); algorithmic bytes by SURVEY 8(d)
+  sweep      BASELINE.json configs[4]: N in {100,300,1000,3000} x d in {256,1024} x H in {4,16}
+  train      the training form of the step: fwd+bwd, one flat gradient bucket, ONE NCCL SUM allreduce, SGD (per rank 1 image)
   cpu_baseline  the numpy/C oracle of the hot path (oracle/pipeline_np.py) on this host, one image
   --impl reference   the CPU arm: torch-CPU fp32 trunk + oracle hot path, same metric/config (rank 0 only)
 
@@ -41,7 +44,8 @@ def parse():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--precision', default=None, choices=[None, 'f16', 'fp32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--sweep', action='store_true', help='also print the relation-module roofline sweep (configs[4])')
+    ap.add_argument('--no-sweep', action='store_true', help='skip the relation-module roofline sweep (configs[4])')
+    ap.add_argument('--no-train', action='store_true', help='skip the data-parallel training block (gradient allreduce)')
     return ap.parse_args()
 
 
@@ -169,53 +173,138 @@ def count_launches(fn):
         return None, None, {'error': str(e)}
 
 
-def relation_kernel_roofline(ops, pk, device):
-    """Time relation_attn_tc_kernel alone (stage mask 4) at N=M=300, d=1024, H=16 with an L2 flush between launches."""
-    from oracle import relation_np as R
-    c = R.make_relation_case(2, 300, 1024, 16)
-    t = {k: torch.from_numpy(v).to(device) for k, v in c.items() if isinstance(v, np.ndarray)}
-    args = [t[k] for k in ('X', 'boxes', 'Wq', 'bq', 'Wk', 'bk', 'Wg', 'bg', 'Wout', 'bout')]
-    ops.relation(*args, group=16, residual_relu=True, precision='f16')            # full pass fills the workspace
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)     # > 126 MB L2
-    times = {}
-    for name, mask in (('attn', 4), ('geom', 2), ('proj', 1), ('module', 7)):
-        evs = []
-        for i in range(25):
-            flush.fill_(i & 1)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            ops.relation(*args, group=16, residual_relu=True, precision='f16', stage_mask=mask)
-            e1.record()
-            evs.append((e0, e1))
-        torch.cuda.synchronize()
-        ts = sorted(a.elapsed_time(b) * 1e3 for a, b in evs[5:])
-        times[name] = ts[len(ts) // 2]
-    # warm (L2-resident operands, back to back) module latency as well
-    for _ in range(10):
-        ops.relation(*args, group=16, residual_relu=True, precision='f16')
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(50):
-        ops.relation(*args, group=16, residual_relu=True, precision='f16')
-    e1.record()
+def _graph_time_us(fn, flush, reps=15):
+    """one stage as a captured graph (no host gaps, tensor-map encode outside), 256 MB L2 flush between replays,
+    CUDA events, median"""
     torch.cuda.synchronize()
-    times['module_warm'] = e0.elapsed_time(e1) * 1e3 / 50
-    flops = 4.0 * 300 * 300 * 1024
-    achieved = flops / (times['attn'] * 1e-6) / 1e12
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        for _ in range(3):
+            fn()
+        s.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            fn()
+    torch.cuda.synchronize()
+    ts = []
+    for i in range(reps):
+        flush.fill_(i & 1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); g.replay(); b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def _relation_point(ops, synth, device, flush, N, d, H, reps):
+    """module and N x M stage microseconds of one (N, d, H) point; the tcgen05 path when it covers the shape"""
+    c = synth.make_relation_case(N * 31 + d + H, N, d, H)
+    t = [torch.from_numpy(c[k]).to(device) for k in ('X', 'boxes', 'Wq', 'bq', 'Wk', 'bk', 'Wg', 'bg', 'Wout', 'bout')]
+    tc = ops.relation_tc_supported(d, d, H)
+    rec = dict(N=N, d=d, H=H, dk=d // H, F_tc_gflop=round(4.0 * N * N * d / 1e9, 4))
+    if tc:
+        ws = torch.empty(ops.relation_workspace_bytes(N, N, d, d, d, H) + 4096, dtype=torch.uint8, device=device)
+        kw = dict(group=H, residual_relu=True, precision='f16', workspace=ws)
+        ops.relation(*t, **kw)
+        rec['path'] = 'tcgen05 fused (geometry + attention, one launch)' if ops.relation_fused_active() else 'tcgen05 unfused'
+        rec['module_us'] = round(_graph_time_us(lambda: ops.relation(*t, **kw), flush, reps), 2)
+        rec['nm_us'] = round(_graph_time_us(lambda: ops.relation(*t, stage_mask=6, **kw), flush, reps), 2)
+        rec['proj_us'] = round(_graph_time_us(lambda: ops.relation(*t, stage_mask=1, **kw), flush, reps), 2)
+    else:
+        kw = dict(group=H, residual_relu=True, precision='fp32')
+        ops.relation(*t, **kw)
+        rec['path'] = 'fp32 kernels + library GEMMs (d_k = %d > 64: not covered by the tcgen05 kernels)' % (d // H)
+        rec['module_us'] = round(_graph_time_us(lambda: ops.relation(*t, **kw), flush, reps), 2)
+        rec['nm_us'] = None
+    return rec
+
+
+def relation_kernel_roofline(ops, pk, device, sweep=True):
+    """The fused relation kernel (relation_fused.cu: pair geometry + pair FC + QK^T + softmax + P.V', ONE launch) at the
+    headline size N = M = 300, d = 1024, H = 16, timed as a captured graph of that one stage with an L2 flush between
+    replays.  achieved = SURVEY 8(d) algorithmic FLOPs 4 N M d / duration against the measured bf16 peak; algorithmic bytes
+    by SURVEY 8(d): s (N d + 2 M d) + 16 max(N, M) + 4 (E H + H) + s N d, s = 2.  Also the configs[4] sweep."""
+    from relnet_b200 import synth
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)     # > 126 MB L2
+    N = M = 300; d = 1024; H = 16; E = 64
+    head = _relation_point(ops, synth, device, flush, N, d, H, 25)
+    flops = 4.0 * N * M * d
+    alg_bytes = int(2 * (N * d + 2 * M * d) + 16 * max(N, M) + 4 * (E * H + H) + 2 * N * d)
+    achieved = flops / (head['nm_us'] * 1e-6) / 1e12
     traffic = None          # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
     try:
-        recs = json.load(open(os.path.join(ROOT, 'profiles', 'r01_ncu_relation_attn_tile_full.json')))
-        r0 = [r for r in recs if r['launch__grid_size'] == '144'][0]
-        mult = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
-        traffic = int(float(r0['dram__bytes_read.sum']) * mult[r0['units']['dram__bytes_read.sum']] +
-                      float(r0['dram__bytes_write.sum']) * mult[r0['units']['dram__bytes_write.sum']])
+        r0 = json.load(open(os.path.join(ROOT, 'profiles', 'r02_ncu_relation_fused_n300.json')))
+        traffic = int(r0['dram__bytes_read.sum'] + r0['dram__bytes_write.sum'])
     except Exception:
         pass
-    return dict(bound='tensor', kernel='relation_attn_tile_kernel (+combine)', achieved=round(achieved, 3), peak=pk['tflops'],
-                unit='TFLOP/s', frac=round(achieved / pk['tflops'], 5), traffic=traffic,
-                algorithmic_bytes=int(2 * (300 + 2 * 300) * 1024 + 4 * 16 * 300 * 300 + 4 * 300 * 1024),
-                algorithmic_flops=flops, duration_us=round(times['attn'], 2), peak_source=pk['source'],
-                note='N=M=300,d=1024,H=16: 0.37 GFLOP is launch-latency sized (SURVEY 7); sweep in profiles/'), times
+    roof = dict(bound='tensor', kernel='relation_fused_kernel (geometry + pair FC + QK^T + softmax + P.V\', one cooperative launch)',
+                achieved=round(achieved, 3), peak=pk['tflops'], unit='TFLOP/s', frac=round(achieved / pk['tflops'], 5),
+                traffic=traffic, algorithmic_bytes=alg_bytes, algorithmic_flops=flops, duration_us=head['nm_us'],
+                timing='captured graph of the one stage, 256 MB L2 flush between replays, CUDA events, median of 25',
+                peak_source=pk['source'],
+                note='N=M=300: 0.37 GFLOP is ~0.25 us of tensor time; the kernel is latency / SFU bound (per pair 2 log + 16 '
+                     'sincos + H exp2 on the XU pipe), see sweep for N up to 3000')
+    times = dict(module=head['module_us'], nm_stage=head['nm_us'], proj=head['proj_us'])
+    sw = None
+    if sweep:
+        sw = []
+        for n in (100, 300, 1000, 3000):
+            for dd in (256, 1024):
+                for hh in (4, 16):
+                    rec = head if (n, dd, hh) == (N, d, H) else _relation_point(ops, synth, device, flush, n, dd, hh, 9)
+                    if rec.get('nm_us'):
+                        ach = rec['F_tc_gflop'] * 1e9 / (rec['nm_us'] * 1e-6) / 1e12
+                        rec['nm_tflops'] = round(ach, 2)
+                        rec['nm_frac_of_measured_bf16_peak'] = round(ach / pk['tflops'], 4)
+                    sw.append(rec)
+    del flush
+    return roof, times, sw
+
+
+def train_block(args, trunk_seed, device, world, rank, dist_on):
+    """Training form of the same config: fwd + bwd of one image per rank (trunk res3+ by torch/cuDNN autograd, the hot path
+    through the C-ABI forward / backward pairs), ONE flat gradient bucket, ONE NCCL SUM allreduce per step, SGD update.
+    Reports ms/step (max over ranks), the allreduce's own milliseconds and bus bandwidth, the bucket size."""
+    from relnet_b200 import replicas
+    from relnet_b200.train import TrainStep, bus_gbs
+    from relnet_b200.trunk import make_trunk
+    import torch.distributed as dist
+    ts = TrainStep(make_trunk(device, torch.bfloat16, seed=trunk_seed), device, micro_batches=1, lr=0.0)
+    image, im_info = make_inputs(seed=100 + rank)
+    image = image.to(device); im_info = im_info.to(device)
+    K, W = max(3, min(args.steps, 10)), 3
+    for _ in range(W):
+        ts.step([image], im_info)
+    # the exchange is a SUM: reduced bucket == sum over ranks of the local buckets (checked on a checksum of the bucket)
+    ts.step([image], im_info, exchange=False)
+    local = ts.bucket.flat.double().sum()
+    tot = local.clone()
+    if dist_on:
+        dist.all_reduce(tot)
+    ts.step([image], im_info, exchange=True)
+    red = ts.bucket.flat.double().sum()
+    chk = float((red - tot).abs() / tot.abs().clamp_min(1e-30))
+    torch.cuda.synchronize()
+    if dist_on:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    evs = []
+    e0.record()
+    for _ in range(K):
+        evs.append(ts.step([image], im_info))
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    ms_ar = sorted(a.elapsed_time(b) for a, b in evs)[len(evs) // 2]
+    ms = replicas.max_over_ranks(ms, device); ms_ar = replicas.max_over_ranks(ms_ar, device)
+    nbytes = ts.bucket.flat.numel() * 4
+    return dict(mode='data-parallel training step, 1 image / GPU / step', images_per_sec=round(world / (ms / 1e3), 2),
+                ms_per_step=round(ms, 3), allreduce_ms=round(ms_ar, 4), allreduce_bus_gbs=round(bus_gbs(nbytes, ms_ar, world), 1),
+                bucket_mb=round(nbytes / 1e6, 1), collectives_per_step=1 if dist_on else 0, reduce_op='sum (rescale_grad = 1.0)',
+                reduced_vs_sum_of_ranks_rel=chk, steps=K, warmup=W, rois=ts.last.get('rois'),
+                launch='eager (torch autograd for the library trunk + the C-ABI fwd/bwd pairs of the hot path); allreduce after '
+                       'backward, not overlapped', losses={k: round(v, 4) for k, v in ts.last.items() if k != 'rois'})
 
 
 def cpu_threads():
@@ -392,12 +481,17 @@ def main():
     ms_hot = timed(step_hot, args.steps, 3, dist_on)
     ms_trunk = timed(lambda: trunk_graph(image32_d), args.steps, 3, dist_on)
 
+    train = None
+    if not args.no_train:
+        del streamer, graphed, hot_graph, trunk_graph
+        torch.cuda.empty_cache()
+        train = train_block(args, 0, device, world, rank, dist_on)
     if rank == 0:
         pk = peaks()
         ours, lib, names = count_launches(lambda: full_step(image32_d))
-        roof, rel_times = (None, {})
+        roof, rel_times, sweep = (None, {}, None)
         if ops.device_info()['sm100'] and prec == 'f16':
-            roof, rel_times = relation_kernel_roofline(ops, pk, device)
+            roof, rel_times, sweep = relation_kernel_roofline(ops, pk, device, sweep=not args.no_sweep)
         line = {
             'metric': 'images/sec', 'value': round(world * args.steps / (ms / 1e3), 3), 'unit': 'images/sec',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(ms / args.steps, 4),
@@ -421,6 +515,8 @@ def main():
                          'proposals_kept_before_pad': int(ops.proposal(trunk_out[0], trunk_out[1], im_info, return_num_kept=True, **head.cfg)[2].item())},
             'clocks': sampler.summary() if sampler else None,
             'roofline': roof,
+            'train': train,
+            'sweep': sweep,
         }
         if not args.no_cpu_baseline:
             line['cpu_baseline'] = cpu_baseline()

@@ -1,0 +1,118 @@
+"""Data-parallel training step of the end-to-end graph (reference: train_end2end.py:57-177,
+core/module.py:569-591): one image per rank per micro-batch, forward + backward, every trainable gradient lands in ONE flat
+fp32 GradientBucket, ONE NCCL SUM allreduce per step (kvstore 'device' semantics: sum, rescale_grad = 1.0), SGD update.
+
+What runs where:
+  * trunk conv1 / res2 frozen (FIXED_PARAMS of the yaml), res3 .. res5 + RPN + conv_new_1: torch/cuDNN with autograd
+    (library, out of scope as kernels -- bf16 autocast over fp32 master weights so the gradients are fp32 bucket views);
+  * hot path: proposal, proposal_target, ROIPooling fwd/bwd, relation fwd/bwd (x2), learn-NMS fwd/bwd, nms_multi_target,
+    learn-NMS loss -- the repo's own C-ABI kernels through relnet_b200.autograd;
+  * fc_new_1/2, cls_score, bbox_pred and the two softmax / smooth-L1 losses: torch (library GEMMs under autocast).
+RPN anchor labels come from the data loader in the reference (lib/rpn/rpn.py:80-243, CPU, out of scope): here they are a
+seeded synthetic label map so that the RPN branch carries a gradient of the right shape.
+"""
+import torch
+import torch.nn.functional as F
+from . import autograd as AG
+from . import ops, replicas
+from .pipeline import HEAD_PARAM_SHAPES, NMS_NAMES, init_head_params
+
+FROZEN_PREFIXES = ('conv1', 'res2')            # FIXED_PARAMS: conv1, bn*, res2 (BN is folded / frozen everywhere here)
+
+
+class TrainStep(object):
+    def __init__(self, trunk, device, num_gt=8, micro_batches=1, seed=0, lr=0.0, nongt_dim=300, first_n=100):
+        self.dev, self.micro, self.lr = device, micro_batches, lr
+        self.nongt_dim, self.first_n = nongt_dim, first_n
+        self.trunk = trunk.float()                                   # fp32 master weights, bf16 autocast in the convs
+        for n, q in self.trunk.named_parameters():
+            q.requires_grad_(not n.startswith(FROZEN_PREFIXES))
+        self.head = {k: v.clone().requires_grad_(True) for k, v in init_head_params(seed, device).items()}
+        shapes = {'trunk.' + n: tuple(q.shape) for n, q in self.trunk.named_parameters() if q.requires_grad}
+        shapes.update({k: tuple(v.shape) for k, v in self.head.items()})
+        self.bucket = replicas.GradientBucket(shapes, device=device)
+        self.params = {'trunk.' + n: q for n, q in self.trunk.named_parameters() if q.requires_grad}
+        self.params.update(self.head)
+        for n, q in self.params.items():
+            q.grad = self.bucket.views[n]                            # autograd accumulates in place into the bucket windows
+        self.state = {}
+        g = torch.Generator().manual_seed(seed + 17)
+        self.gt = torch.tensor([[100. + 90 * i, 60. + 50 * i, 260. + 90 * i, 300. + 50 * i, 1. + (i % 80)] for i in range(num_gt)],
+                               device=device)
+        self.rpn_label = None
+        self.gen = g
+        self.last = {}
+
+    # ------------------------------------------------------------------------------------------------ one image
+    def forward_backward(self, image32, im_info):
+        P, t, dev = self.head, self.trunk, self.dev
+        from .trunk import plain_ops
+        with plain_ops(), torch.autocast('cuda', dtype=torch.bfloat16):
+            with torch.no_grad():                                    # frozen prefix (FIXED_PARAMS)
+                x = image32.contiguous(memory_format=torch.channels_last)
+                x = t.res2(F.max_pool2d(F.relu(t.conv1(x)), 3, 2, ceil_mode=True))
+            c4 = t.res4(t.res3(x))
+            r = F.relu(t.rpn_conv(c4))
+            score, rpn_bbox = t.rpn_cls(r).float(), t.rpn_bbox(r).float()
+            feat = F.relu(t.conv_new_1(t.res5(c4)))
+        b, _, h, w = score.shape
+        A = t.A
+        logits = score.reshape(b, 2, A * h, w)
+        if self.rpn_label is None:                                   # synthetic anchor labels: 1/8 labelled, 1/4 of them fg
+            u = torch.rand((b, A * h, w), generator=self.gen).to(dev)
+            self.rpn_label = torch.where(u < 0.03, 1, torch.where(u < 0.125, 0, -1)).long()
+            self.rpn_bbox_t = (torch.randn(rpn_bbox.shape, generator=self.gen) * 0.1).to(dev)
+        rpn_cls_loss = F.cross_entropy(logits, self.rpn_label, ignore_index=-1)
+        fg = (self.rpn_label == 1).reshape(b, A, h, w).repeat_interleave(4, dim=1).float()
+        rpn_bbox_loss = (F.smooth_l1_loss(rpn_bbox, self.rpn_bbox_t, reduction='none', beta=1.0 / 9) * fg).sum() / 256.0
+        with torch.no_grad():                                        # CustomOps with zero input gradients (proposal.py:170-173)
+            prob = F.softmax(logits, dim=1).reshape(b, 2 * A, h, w).contiguous()
+            rois = ops.proposal(prob, rpn_bbox.detach().contiguous(), im_info)[0]
+            rois, label, bbox_target, bbox_weight = ops.proposal_target(rois, self.gt)
+            boxes = rois[:, 1:].contiguous()
+        pooled = AG.roi_pool(feat.float().contiguous(), rois, (7, 7), 1.0 / 16)                   # SYM_REL_NMS:335
+        with torch.autocast('cuda', dtype=torch.bfloat16):
+            fc1 = F.linear(pooled.flatten(1), P['fc_new_1_weight'], P['fc_new_1_bias']).float()
+        rel = lambda x, i: AG.relation(x, boxes, P['query_%d_weight' % i], P['query_%d_bias' % i], P['key_%d_weight' % i],
+                                       P['key_%d_bias' % i], P['pair_pos_fc1_%d_weight' % i], P['pair_pos_fc1_%d_bias' % i],
+                                       P['linear_out_%d_weight' % i], P['linear_out_%d_bias' % i], M=self.nongt_dim, group=16,
+                                       residual_relu=True, precision='fp32')
+        a1 = rel(fc1, 1)                                                                          # :346-351
+        with torch.autocast('cuda', dtype=torch.bfloat16):
+            fc2 = F.linear(a1, P['fc_new_2_weight'], P['fc_new_2_bias']).float()
+        a2 = rel(fc2, 2)                                                                          # :354-359
+        cls_score = F.linear(a2, P['cls_score_weight'], P['cls_score_bias'])
+        bbox_pred = F.linear(a2, P['bbox_pred_weight'], P['bbox_pred_bias'])
+        cls_loss = F.cross_entropy(cls_score, label.long())
+        bbox_loss = (F.smooth_l1_loss(bbox_pred, bbox_target, reduction='none', beta=1.0) * bbox_weight).sum() / rois.shape[0]
+        multi, sbbox, sscore = AG.learn_nms(cls_score, bbox_pred, rois, im_info, a2, {k: P[k] for k in NMS_NAMES},
+                                            first_n=self.first_n, means=(0, 0, 0, 0), stds=(0.1, 0.1, 0.2, 0.2),
+                                            nongt_dim=self.nongt_dim)                             # :424-501 (train graph)
+        with torch.no_grad():
+            target = ops.nms_multi_target(sbbox, self.gt, sscore, [0.5, 0.6, 0.7, 0.8, 0.9])      # :537-538
+            pos, neg, d_multi = ops.nms_loss(multi.detach(), target)                              # :539-551
+        torch.autograd.backward([rpn_cls_loss + rpn_bbox_loss + cls_loss + bbox_loss, multi], [None, d_multi])
+        self.last = dict(rpn_cls=float(rpn_cls_loss), cls=float(cls_loss), bbox=float(bbox_loss),
+                         nms=float(pos.sum() + neg.sum()), rois=int(rois.shape[0]))
+
+    # ------------------------------------------------------------------------------------------------ one step
+    def step(self, images32, im_info, exchange=True):
+        """images32: list of `micro_batches` fp32 [1,3,H,W] images of this rank (gradients accumulate locally, like the
+        reference's 2 images per GPU in the FPN config); then ONE allreduce, then the SGD update."""
+        self.bucket.zero_()
+        for im in images32:
+            self.forward_backward(im, im_info)
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+        if exchange:
+            self.bucket.allreduce()
+        ev[1].record()
+        replicas.sgd_step({n: q.data for n, q in self.params.items()}, self.bucket, lr=self.lr, state=self.state)
+        return ev
+
+
+def bus_gbs(nbytes, ms, world):
+    """NCCL bus bandwidth of an allreduce: algorithmic bytes x 2 (n-1)/n / time"""
+    if world <= 1 or ms <= 0:
+        return 0.0
+    return nbytes * 2.0 * (world - 1) / world / (ms * 1e-3) / 1e9

@@ -17,14 +17,34 @@ import torch.nn.functional as F
 FUSED = os.environ.get('RELNET_TRUNK_FUSED', '1') != '0'
 
 
+_PLAIN = [False]
+
+
+class plain_ops(object):
+    """context: route every conv of the trunk through the plain (autograd- and autocast-aware) module calls"""
+
+    def __enter__(self):
+        self.prev = _PLAIN[0]
+        _PLAIN[0] = True
+
+    def __exit__(self, *a):
+        _PLAIN[0] = self.prev
+
+
+def _training(conv):
+    """the fused library calls have no autograd formula (and ignore autocast): when a gradient is wanted (train.py) use
+    the plain module ops"""
+    return _PLAIN[0] or (torch.is_grad_enabled() and conv.weight.requires_grad)
+
+
 def _conv_relu(conv, x):
-    if FUSED and x.is_cuda:
+    if FUSED and x.is_cuda and not _training(conv):
         return torch.cudnn_convolution_relu(x, conv.weight, conv.bias, conv.stride, conv.padding, conv.dilation, conv.groups)
     return F.relu(conv(x))
 
 
 def _conv_add_relu(conv, x, z):
-    if FUSED and x.is_cuda:
+    if FUSED and x.is_cuda and not _training(conv):
         return torch.cudnn_convolution_add_relu(x, conv.weight, z, 1.0, conv.bias, conv.stride, conv.padding, conv.dilation,
                                                 conv.groups)
     return F.relu(conv(x) + z)
