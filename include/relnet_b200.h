@@ -325,6 +325,11 @@ typedef struct rn_psroi_desc {
 } rn_psroi_desc;
 int rn_deform_psroi_pool_fwd(const rn_psroi_desc* desc, const float* data, const float* rois, const float* trans,
                              float* out, float* top_count, rn_stream_t stream);
+/* Same operator on a CHANNELS-LAST feature map [B, H, W, channels] (fp32, or bf16 when data_is_bf16: the layout the trunk's
+ * conv_new_1 leaves it in) -- the fast form: every bilinear tap is a 16-byte channel-vector load.  Same arithmetic per
+ * channel (a bf16 map is widened exactly); out / top_count keep the reference layout [R, output_dim, pooled, pooled]. */
+int rn_deform_psroi_pool_nhwc_fwd(const rn_psroi_desc* desc, const void* data_nhwc, int32_t data_is_bf16, const float* rois,
+                                  const float* trans, float* out, float* top_count, rn_stream_t stream);
 
 /* DeformablePSROIPooling backward (operator_cxx/deformable_psroi_pooling.cu:177-289).  B = batch size of data; dout and
  * top_count as produced by the forward; ddata [B,channels,H,W] and dtrans (shape of trans; NULL when no_trans) are
@@ -344,6 +349,14 @@ typedef struct rn_deform_conv_desc {
 size_t rn_deform_conv_workspace_bytes(const rn_deform_conv_desc* desc);
 int rn_deform_conv_fwd(const rn_deform_conv_desc* desc, const float* data, const float* offset, const float* weight,
                        const float* bias, float* out, void* workspace, size_t workspace_bytes, rn_stream_t stream);
+/* Channels-last fast form of the same forward (one image, num_group 1): data NHWC fp32 or bf16 (the trunk's layout), the
+ * weight packed once by rn_deform_conv_pack (fp16, K ordered tap-major to match the sampler), output NHWC as fp32 and / or
+ * fp16 with bias and optional relu fused in the tcgen05 GEMM epilogue.  workspace: rn_deform_conv_workspace_bytes. */
+size_t rn_deform_conv_packed_bytes(const rn_deform_conv_desc* desc);
+int rn_deform_conv_pack(const rn_deform_conv_desc* desc, const float* weight, void* packed, rn_stream_t stream);
+int rn_deform_conv_nhwc_fwd(const rn_deform_conv_desc* desc, const void* data_nhwc, int32_t data_is_bf16, const float* offset,
+                            const void* packed_weight, const float* bias, int32_t relu, float* out_f32, void* out_f16,
+                            void* workspace, size_t workspace_bytes, rn_stream_t stream);
 /* DeformableConvolution backward (operator_cxx/deformable_convolution-inl.h:145-233; col2im / col2im_coord kernels
  * nn/deformable_im2col.cuh:315-458).  ddata, doffset, dweight, dbias (NULL when no bias) are OVERWRITTEN; workspace as for
  * the forward (rn_deform_conv_workspace_bytes).  weight_grad_deformed = 0 is the REFERENCE: its dWeight is computed from

@@ -110,9 +110,13 @@ SIGNATURES = {
     'rn_deform_psroi_pool_bwd': (C.c_int, [C.POINTER(PsroiDesc), c_i] + [c_p] * 7 + [c_p]),
     'rn_deform_conv_bwd': (C.c_int, [C.POINTER(DeformConvDesc)] + [c_p] * 4 + [c_i] + [c_p] * 4 + [c_p, c_sz, c_p]),
     'rn_deform_psroi_pool_fwd': (C.c_int, [C.POINTER(PsroiDesc)] + [c_p] * 5 + [c_p]),
+    'rn_deform_psroi_pool_nhwc_fwd': (C.c_int, [C.POINTER(PsroiDesc), c_p, c_i] + [c_p] * 4 + [c_p]),
     'rn_deform_conv_workspace_bytes': (c_sz, [C.POINTER(DeformConvDesc)]),
     'rn_deform_conv_fwd': (C.c_int, [C.POINTER(DeformConvDesc)] + [c_p] * 5 + [c_p, c_sz, c_p]),
     'rn_deform_im2col': (C.c_int, [C.POINTER(DeformConvDesc), c_p, c_p, c_p, c_p]),
+    'rn_deform_conv_packed_bytes': (c_sz, [C.POINTER(DeformConvDesc)]),
+    'rn_deform_conv_pack': (C.c_int, [C.POINTER(DeformConvDesc), c_p, c_p, c_p]),
+    'rn_deform_conv_nhwc_fwd': (C.c_int, [C.POINTER(DeformConvDesc), c_p, c_i, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_sz, c_p]),
     'rn_umma_selftest': (C.c_int, [c_p] * 6 + [c_p]),
 }
 

@@ -23,7 +23,7 @@ NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 
 COMMON = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-Xcompiler', '-fPIC',
           '-I' + INC, '-I' + CSRC, '--expt-relaxed-constexpr', '-Xptxas', '-v']
-NO_FMA = {'rois.cu', 'deform_conv.cu', 'proposal.cu'}
+NO_FMA = {'rois.cu', 'psroi.cu', 'deform_conv.cu', 'proposal.cu'}
 
 
 def sources():

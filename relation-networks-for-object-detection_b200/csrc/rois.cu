@@ -123,67 +123,6 @@ __global__ void __launch_bounds__(128) roi_pool_nhwc_bf16in_f16_kernel(const __n
   }
 }
 
-// operator_cxx/deformable_psroi_pooling.cu:29-49
-__device__ __forceinline__ float psroi_bilinear(const float* __restrict__ data, float x, float y, int width) {
-  const int x1 = (int)floorf(x), x2 = (int)ceilf(x), y1 = (int)floorf(y), y2 = (int)ceilf(y);
-  const float dx = x - (float)x1, dy = y - (float)y1;
-  const float v11 = __ldg(data + y1 * width + x1), v12 = __ldg(data + y2 * width + x1);
-  const float v21 = __ldg(data + y1 * width + x2), v22 = __ldg(data + y2 * width + x2);
-  return (1 - dx) * (1 - dy) * v11 + (1 - dx) * dy * v12 + dx * (1 - dy) * v21 + dx * dy * v22;
-}
-
-// operator_cxx/deformable_psroi_pooling.cu:52-138, float/double mixing kept literally
-__global__ void __launch_bounds__(256) deform_psroi_fwd_kernel(rn_psroi_desc p, size_t count, const float* __restrict__ data,
-                                                               const float* __restrict__ rois,
-                                                               const float* __restrict__ trans, float* __restrict__ out,
-                                                               float* __restrict__ top_count) {
-  const int pooled = p.pooled_size, part_size = p.part_size, spp = p.sample_per_part, gs = p.group_size;
-  const int H = p.H, W = p.W;
-  const int num_classes = p.no_trans ? 1 : p.num_classes;
-  const int channels_each_class = p.no_trans ? p.output_dim : p.output_dim / num_classes;
-  for (size_t index = (size_t)blockIdx.x * blockDim.x + threadIdx.x; index < count;
-       index += (size_t)gridDim.x * blockDim.x) {
-    const int pw = index % pooled, ph = (index / pooled) % pooled;
-    const int ctop = (index / pooled / pooled) % p.output_dim;
-    const int n = index / pooled / pooled / p.output_dim;
-    const float* roi = rois + 5 * n;
-    const int b = (int)roi[0];
-    const float rsw = (float)((double)(roundf(roi[1]) * p.spatial_scale) - 0.5);
-    const float rsh = (float)((double)(roundf(roi[2]) * p.spatial_scale) - 0.5);
-    const float rew = (float)((double)((float)((double)roundf(roi[3]) + 1.) * p.spatial_scale) - 0.5);
-    const float reh = (float)((double)((float)((double)roundf(roi[4]) + 1.) * p.spatial_scale) - 0.5);
-    const float roi_w = (float)fmax((double)(rew - rsw), 0.1);
-    const float roi_h = (float)fmax((double)(reh - rsh), 0.1);
-    const float bin_h = roi_h / (float)pooled, bin_w = roi_w / (float)pooled;
-    const float sub_h = bin_h / (float)spp, sub_w = bin_w / (float)spp;
-    const int part_h = (int)floorf((float)ph / pooled * part_size);
-    const int part_w = (int)floorf((float)pw / pooled * part_size);
-    const int class_id = ctop / channels_each_class;
-    const float tx = p.no_trans ? 0.f
-        : trans[(((size_t)(n * num_classes + class_id) * 2) * part_size + part_h) * part_size + part_w] * p.trans_std;
-    const float ty = p.no_trans ? 0.f
-        : trans[(((size_t)(n * num_classes + class_id) * 2 + 1) * part_size + part_h) * part_size + part_w] * p.trans_std;
-    float wstart = (float)pw * bin_w + rsw; wstart += tx * roi_w;
-    float hstart = (float)ph * bin_h + rsh; hstart += ty * roi_h;
-    float sum = 0.f; int cnt = 0;
-    int gw = (int)floorf((float)pw * gs / pooled), gh = (int)floorf((float)ph * gs / pooled);
-    gw = min(max(gw, 0), gs - 1); gh = min(max(gh, 0), gs - 1);
-    const float* d0 = data + (size_t)b * p.channels * H * W;
-    const int c = (ctop * gs + gh) * gs + gw;
-    for (int ih = 0; ih < spp; ++ih)
-      for (int iw = 0; iw < spp; ++iw) {
-        float w = wstart + iw * sub_w, h = hstart + ih * sub_h;
-        if ((double)w < -0.5 || (double)w > W - 0.5 || (double)h < -0.5 || (double)h > H - 0.5) continue;
-        w = (float)fmin(fmax((double)w, 0.), W - 1.);
-        h = (float)fmin(fmax((double)h, 0.), H - 1.);
-        sum += psroi_bilinear(d0 + (size_t)c * H * W, w, h, W);
-        cnt++;
-      }
-    out[index] = cnt == 0 ? 0.f : sum / cnt;
-    if (top_count) top_count[index] = (float)cnt;
-  }
-}
-
 // ---- backward (training) -----------------------------------------------------------------------------------------
 // ROIPooling backward (MXNet 1.1.0 roi_pooling.cu ROIPoolBackwardAcc, not in tree): each pooled cell sends its gradient
 // to the argmax element the forward recorded.  Scatter form (one thread per pooled cell, red.global.add) instead of the
@@ -199,78 +138,6 @@ __global__ void __launch_bounds__(256) roi_pool_bwd_kernel(const float* __restri
     const int n = index / PHW / C;
     const int b = (int)rois[5 * n];
     atomicAdd(ddata + ((size_t)b * C + c) * H * W + a, dout[index]);
-  }
-}
-
-// DeformablePSROIPoolBackwardAccKernel, operator_cxx/deformable_psroi_pooling.cu:177-289 (same float/double mixing as the
-// forward above); ddata / dtrans must be zero on entry.
-__global__ void __launch_bounds__(256) deform_psroi_bwd_kernel(rn_psroi_desc p, size_t count, const float* __restrict__ dout,
-                                                               const float* __restrict__ top_count,
-                                                               const float* __restrict__ data, const float* __restrict__ rois,
-                                                               const float* __restrict__ trans, float* __restrict__ ddata,
-                                                               float* __restrict__ dtrans) {
-  const int pooled = p.pooled_size, part_size = p.part_size, spp = p.sample_per_part, gs = p.group_size;
-  const int H = p.H, W = p.W;
-  const int num_classes = p.no_trans ? 1 : p.num_classes;
-  const int channels_each_class = p.no_trans ? p.output_dim : p.output_dim / num_classes;
-  for (size_t index = (size_t)blockIdx.x * blockDim.x + threadIdx.x; index < count;
-       index += (size_t)gridDim.x * blockDim.x) {
-    const float tc = top_count[index];
-    if (tc <= 0) continue;
-    const int pw = index % pooled, ph = (index / pooled) % pooled;
-    const int ctop = (index / pooled / pooled) % p.output_dim;
-    const int n = index / pooled / pooled / p.output_dim;
-    const float* roi = rois + 5 * n;
-    const int b = (int)roi[0];
-    const float rsw = (float)((double)(roundf(roi[1]) * p.spatial_scale) - 0.5);
-    const float rsh = (float)((double)(roundf(roi[2]) * p.spatial_scale) - 0.5);
-    const float rew = (float)((double)((float)((double)roundf(roi[3]) + 1.) * p.spatial_scale) - 0.5);
-    const float reh = (float)((double)((float)((double)roundf(roi[4]) + 1.) * p.spatial_scale) - 0.5);
-    const float roi_w = (float)fmax((double)(rew - rsw), 0.1);
-    const float roi_h = (float)fmax((double)(reh - rsh), 0.1);
-    const float bin_h = roi_h / (float)pooled, bin_w = roi_w / (float)pooled;
-    const float sub_h = bin_h / (float)spp, sub_w = bin_w / (float)spp;
-    const int part_h = (int)floorf((float)ph / pooled * part_size);
-    const int part_w = (int)floorf((float)pw / pooled * part_size);
-    const int class_id = ctop / channels_each_class;
-    const size_t tix = (((size_t)(n * num_classes + class_id) * 2) * part_size + part_h) * part_size + part_w;
-    const size_t tiy = (((size_t)(n * num_classes + class_id) * 2 + 1) * part_size + part_h) * part_size + part_w;
-    const float tx = p.no_trans ? 0.f : trans[tix] * p.trans_std;
-    const float ty = p.no_trans ? 0.f : trans[tiy] * p.trans_std;
-    float wstart = (float)pw * bin_w + rsw; wstart += tx * roi_w;
-    float hstart = (float)ph * bin_h + rsh; hstart += ty * roi_h;
-    const float diff_val = dout[index] / tc;
-    int gw = (int)floorf((float)pw * gs / pooled), gh = (int)floorf((float)ph * gs / pooled);
-    gw = min(max(gw, 0), gs - 1); gh = min(max(gh, 0), gs - 1);
-    const int c = (ctop * gs + gh) * gs + gw;
-    const float* d0 = data + ((size_t)b * p.channels + c) * H * W;
-    float* g0 = ddata + ((size_t)b * p.channels + c) * H * W;
-    float acc_x = 0.f, acc_y = 0.f;
-    for (int ih = 0; ih < spp; ++ih)
-      for (int iw = 0; iw < spp; ++iw) {
-        float w = wstart + iw * sub_w, h = hstart + ih * sub_h;
-        if ((double)w < -0.5 || (double)w > W - 0.5 || (double)h < -0.5 || (double)h > H - 0.5) continue;
-        w = (float)fmin(fmax((double)w, 0.), W - 1.);
-        h = (float)fmin(fmax((double)h, 0.), H - 1.);
-        const int x0 = (int)floorf(w), x1 = (int)ceilf(w), y0 = (int)floorf(h), y1 = (int)ceilf(h);
-        const float dx = w - x0, dy = h - y0;
-        atomicAdd(g0 + y0 * W + x0, (1 - dx) * (1 - dy) * diff_val);
-        atomicAdd(g0 + y1 * W + x0, (1 - dx) * dy * diff_val);
-        atomicAdd(g0 + y0 * W + x1, dx * (1 - dy) * diff_val);
-        atomicAdd(g0 + y1 * W + x1, dx * dy * diff_val);
-        if (p.no_trans) continue;
-        const float U00 = __ldg(d0 + y0 * W + x0), U01 = __ldg(d0 + y1 * W + x0);
-        const float U10 = __ldg(d0 + y0 * W + x1), U11 = __ldg(d0 + y1 * W + x1);
-        float diff_x = (U11 * dy + U10 * (1 - dy) - U01 * dy - U00 * (1 - dy)) * p.trans_std * diff_val;
-        diff_x *= roi_w;
-        float diff_y = (U11 * dx + U01 * (1 - dx) - U10 * dx - U00 * (1 - dx)) * p.trans_std * diff_val;
-        diff_y *= roi_h;
-        acc_x += diff_x; acc_y += diff_y;
-      }
-    if (!p.no_trans) {      // one atomic pair per pooled cell (the reference issues one per sample)
-      atomicAdd(dtrans + tix, acc_x);
-      atomicAdd(dtrans + tiy, acc_y);
-    }
   }
 }
 
@@ -291,28 +158,6 @@ extern "C" int rn_roi_pool_fwd(const float* data, const float* rois, int32_t R, 
   size_t count = (size_t)R * C * PH * PW;
   rn::roi_pool_fwd_kernel<<<rn::grid_for(count), 256, 0, (cudaStream_t)stream>>>(data, rois, count, C, H, W, PH, PW,
                                                                                 spatial_scale, out, argmax);
-  RN_LAUNCH_CHECK();
-  return RN_OK;
-}
-
-extern "C" int rn_deform_psroi_pool_fwd(const rn_psroi_desc* desc, const float* data, const float* rois,
-                                        const float* trans, float* out, float* top_count, rn_stream_t stream) {
-  RN_CHECK_ARG(desc, "rn_deform_psroi_pool_fwd: null descriptor");
-  if (desc->R == 0) return RN_OK;
-  RN_CHECK_ARG(data && rois && out, "rn_deform_psroi_pool_fwd: null argument");
-  rn_psroi_desc p = *desc;
-  if (p.part_size == 0) p.part_size = p.pooled_size;
-  RN_CHECK_ARG(p.no_trans || trans, "rn_deform_psroi_pool_fwd: trans required when no_trans == 0");
-  RN_CHECK_ARG(p.group_size > 0 && p.pooled_size > 0 && p.sample_per_part > 0 && p.output_dim > 0,
-               "rn_deform_psroi_pool_fwd: bad geometry");
-  RN_CHECK_ARG(p.channels == p.output_dim * p.group_size * p.group_size,
-               "rn_deform_psroi_pool_fwd: channels %d != output_dim*group_size^2 = %d", p.channels,
-               p.output_dim * p.group_size * p.group_size);
-  if (!p.no_trans) RN_CHECK_ARG(p.num_classes > 0 && p.output_dim % p.num_classes == 0, "rn_deform_psroi_pool_fwd: bad num_classes");
-  if (p.R == 0) return RN_OK;
-  size_t count = (size_t)p.R * p.output_dim * p.pooled_size * p.pooled_size;
-  rn::deform_psroi_fwd_kernel<<<rn::grid_for(count), 256, 0, (cudaStream_t)stream>>>(p, count, data, rois, trans, out,
-                                                                                    top_count);
   RN_LAUNCH_CHECK();
   return RN_OK;
 }
@@ -338,30 +183,6 @@ extern "C" int rn_roi_pool_bwd(const float* dout, const int32_t* argmax, const f
   RN_CHECK_ARG(dout && argmax && rois, "rn_roi_pool_bwd: null pointer");
   size_t count = (size_t)R * C * PH * PW;
   rn::roi_pool_bwd_kernel<<<rn::grid_for(count), 256, 0, st>>>(dout, argmax, rois, count, C, H, W, PH * PW, ddata);
-  RN_LAUNCH_CHECK();
-  return RN_OK;
-}
-
-extern "C" int rn_deform_psroi_pool_bwd(const rn_psroi_desc* desc, int32_t B, const float* dout, const float* top_count,
-                                        const float* data, const float* rois, const float* trans, float* ddata,
-                                        float* dtrans, rn_stream_t stream) {
-  RN_CHECK_ARG(desc && B > 0 && ddata, "rn_deform_psroi_pool_bwd: bad arguments");
-  rn_psroi_desc p = *desc;
-  if (p.part_size == 0) p.part_size = p.pooled_size;
-  RN_CHECK_ARG(p.no_trans || (trans && dtrans), "rn_deform_psroi_pool_bwd: trans / dtrans required when no_trans == 0");
-  RN_CHECK_ARG(p.group_size > 0 && p.pooled_size > 0 && p.sample_per_part > 0 && p.output_dim > 0,
-               "rn_deform_psroi_pool_bwd: bad geometry");
-  RN_CHECK_ARG(p.channels == p.output_dim * p.group_size * p.group_size,
-               "rn_deform_psroi_pool_bwd: channels %d != output_dim*group_size^2", p.channels);
-  if (!p.no_trans) RN_CHECK_ARG(p.num_classes > 0 && p.output_dim % p.num_classes == 0, "rn_deform_psroi_pool_bwd: bad num_classes");
-  cudaStream_t st = (cudaStream_t)stream;
-  RN_CUDA(cudaMemsetAsync(ddata, 0, sizeof(float) * (size_t)B * p.channels * p.H * p.W, st));
-  if (!p.no_trans && p.R > 0)
-    RN_CUDA(cudaMemsetAsync(dtrans, 0, sizeof(float) * (size_t)p.R * 2 * p.num_classes * p.part_size * p.part_size, st));
-  if (p.R == 0) return RN_OK;
-  RN_CHECK_ARG(dout && top_count && data && rois, "rn_deform_psroi_pool_bwd: null pointer");
-  size_t count = (size_t)p.R * p.output_dim * p.pooled_size * p.pooled_size;
-  rn::deform_psroi_bwd_kernel<<<rn::grid_for(count), 256, 0, st>>>(p, count, dout, top_count, data, rois, trans, ddata, dtrans);
   RN_LAUNCH_CHECK();
   return RN_OK;
 }

@@ -575,7 +575,15 @@ def roi_pool_fc(data, rois, W, b, pooled_size=(7, 7), spatial_scale=0.0625, relu
 
 def deform_psroi_pool(data, rois, trans=None, spatial_scale=0.0625, output_dim=256, group_size=1, pooled_size=7,
                       part_size=0, sample_per_part=4, trans_std=0.0, no_trans=None, return_count=False):
-    data = _f32(data, 'data'); rois = _f32(rois, 'rois')
+    """DeformablePSROIPooling forward.  `data` NCHW fp32 (the reference layout) or a channels_last fp32 / bf16 map (the
+    trunk's layout: the fast form, every bilinear tap a 16-byte channel-vector load -- rn_deform_psroi_pool_nhwc_fwd)."""
+    if not isinstance(data, torch.Tensor) or not data.is_cuda:
+        raise L.RelnetError('data must be a CUDA tensor (relnet_b200 has no CPU path)')
+    nhwc = (data.dim() == 4 and data.dtype in (torch.float32, torch.bfloat16) and data.shape[1] > 1
+            and data.is_contiguous(memory_format=torch.channels_last) and not data.is_contiguous())
+    if not nhwc:
+        data = _f32(data, 'data')
+    rois = _f32(rois, 'rois')
     if no_trans is None:
         no_trans = trans is None
     t = _f32(trans, 'trans') if not no_trans else None
@@ -585,8 +593,12 @@ def deform_psroi_pool(data, rois, trans=None, spatial_scale=0.0625, output_dim=2
                        sample_per_part, trans_std, int(bool(no_trans)), 1 if no_trans else t.shape[1] // 2)
     out = torch.empty((R, output_dim, pooled_size, pooled_size), dtype=torch.float32, device=data.device)
     cnt = torch.empty_like(out) if return_count else None
-    L.check(L.lib().rn_deform_psroi_pool_fwd(C.byref(desc), _ptr(data), _ptr(rois), _ptr(t), _ptr(out), _ptr(cnt),
-                                             _stream()), 'rn_deform_psroi_pool_fwd')
+    if nhwc:
+        L.check(L.lib().rn_deform_psroi_pool_nhwc_fwd(C.byref(desc), _ptr(data), int(data.dtype == torch.bfloat16), _ptr(rois),
+                                                      _ptr(t), _ptr(out), _ptr(cnt), _stream()), 'rn_deform_psroi_pool_nhwc_fwd')
+    else:
+        L.check(L.lib().rn_deform_psroi_pool_fwd(C.byref(desc), _ptr(data), _ptr(rois), _ptr(t), _ptr(out), _ptr(cnt),
+                                                 _stream()), 'rn_deform_psroi_pool_fwd')
     return (out, cnt) if return_count else out
 
 
@@ -648,6 +660,36 @@ def deform_conv_backward(grad_out, data, offset, weight, kernel=(3, 3), pad=(2, 
                                    int(bool(weight_grad_deformed)), _ptr(dd), _ptr(do), _ptr(dw), _ptr(db), _ptr(ws),
                                    ws.numel(), _stream()), 'rn_deform_conv_bwd')
     return dd, do, dw, db
+
+
+def deform_conv_nhwc(data, offset, weight, bias=None, relu=False, kernel=(3, 3), pad=(2, 2), stride=(1, 1), dilate=(2, 2),
+                     num_deformable_group=4, out_dtype=torch.float16):
+    """DeformableConvolution on a channels_last map (fp32 or bf16, one image): rn_deform_conv_nhwc_fwd -- the sampler
+    writes an fp16 K-major column buffer from 16-byte channel vectors, the tcgen05 GEMM emits the channels_last output
+    with bias (+relu) fused.  Returns [1, Co, Ho, Wo] in channels_last memory format (fp16 or fp32)."""
+    if not (isinstance(data, torch.Tensor) and data.is_cuda and data.dim() == 4 and data.shape[0] == 1
+            and data.dtype in (torch.float32, torch.bfloat16) and data.is_contiguous(memory_format=torch.channels_last)):
+        raise L.RelnetError('deform_conv_nhwc: data must be a [1,C,H,W] channels_last fp32 / bf16 CUDA tensor')
+    offset = _f32(offset, 'offset'); weight = _f32(weight, 'weight')
+    b = _f32(bias, 'bias') if bias is not None else None
+    desc = _dc_desc(data, weight, kernel, pad, stride, dilate, 1, num_deformable_group, 'f16')
+    lib = L.lib()
+
+    def pack(buf):
+        L.check(lib.rn_deform_conv_pack(C.byref(desc), _ptr(weight), _ptr(buf), _stream()), 'rn_deform_conv_pack')
+    packed = _packs.get_tagged('deform_conv', (weight,), lib.rn_deform_conv_packed_bytes(C.byref(desc)), pack)
+    Ho, Wo = offset.shape[-2], offset.shape[-1]
+    Co = weight.shape[0]
+    out = torch.empty((1, Ho, Wo, Co), dtype=out_dtype, device=data.device)
+    ws = _workspace(lib.rn_deform_conv_workspace_bytes(C.byref(desc)), data.device)
+    o32 = out if out_dtype == torch.float32 else None
+    o16 = out if out_dtype == torch.float16 else None
+    if o32 is None and o16 is None:
+        raise L.RelnetError('deform_conv_nhwc: out_dtype must be float16 or float32')
+    L.check(lib.rn_deform_conv_nhwc_fwd(C.byref(desc), _ptr(data), int(data.dtype == torch.bfloat16), _ptr(offset), _ptr(packed),
+                                        _ptr(b), int(relu), _ptr(o32), _ptr(o16), _ptr(ws), ws.numel(), _stream()),
+            'rn_deform_conv_nhwc_fwd')
+    return out.permute(0, 3, 1, 2)
 
 
 def deform_im2col(im, offset, kernel=(3, 3), pad=(2, 2), stride=(1, 1), dilate=(2, 2), num_deformable_group=4):

@@ -100,6 +100,15 @@ def test_deform_psroi_reference_vs_oracle_vs_product(ops, refd, with_trans):
     np.testing.assert_array_equal(c_our.cpu().numpy(), c_ref)
     np.testing.assert_allclose(o_orc, o_ref, rtol=1e-5, atol=1e-5)
     np.testing.assert_allclose(o_our.cpu().numpy(), o_ref, rtol=1e-5, atol=1e-5)
+    # the channels-last forms (fp32, and bf16 = the trunk's layout): same table, vector taps
+    d_cl = T(data).contiguous(memory_format=torch.channels_last)
+    o_cl, c_cl = ops.deform_psroi_pool(d_cl, T(rois), T(tr) if with_trans else None, return_count=True, **kw)
+    np.testing.assert_array_equal(c_cl.cpu().numpy(), c_ref)
+    np.testing.assert_allclose(o_cl.cpu().numpy(), o_ref, rtol=1e-5, atol=1e-5)
+    d_bf = d_cl.to(torch.bfloat16)
+    o_bf = ops.deform_psroi_pool(d_bf, T(rois), T(tr) if with_trans else None, **kw)
+    o_ref_bf, _ = refd.ref_deform_psroi_pool(d_bf.float().contiguous(), T(rois), T(tr) if with_trans else None, **kw)
+    np.testing.assert_allclose(o_bf.cpu().numpy(), o_ref_bf.cpu().numpy(), rtol=1e-5, atol=1e-5)
     # backward of the same op (atomicAdd: summation order differs run to run)
     dout = np.random.default_rng(9).standard_normal(o_ref.shape).astype(np.float32)
     dd_ref, dt_ref = refd.ref_deform_psroi_pool_backward(T(dout), T(c_ref), T(data), T(rois), T(tr) if with_trans else None, **kw)
@@ -124,3 +133,25 @@ def test_roi_pool_vs_independent_implementation(ops):
     ours = ops.roi_pool(T(data), T(rois)).cpu().numpy()
     assert np.array_equal(orc, ref), 'oracle_c ROIPooling differs from torchvision roi_pool'
     assert np.array_equal(ours, ref)
+
+
+def test_deform_conv_channels_last_fast_path(ops):
+    """rn_deform_conv_nhwc_fwd (bf16 channels_last in, fp16 column buffer, tcgen05 GEMM, bias + relu fused) at the res5 size
+    against the float32 C oracle evaluated on the same bf16-rounded data: 2e-3 of the tensor max (fp16 operands)."""
+    if not ops.device_info()['sm100']:
+        pytest.skip('tcgen05 needs sm_100')
+    rng = np.random.default_rng(8)
+    C, H, W, Co = 512, 38, 63, 512
+    data = rng.standard_normal((1, C, H, W)).astype(np.float32)
+    off = (rng.standard_normal((1, 72, H, W)) * 2.0).astype(np.float32)
+    wgt = (rng.standard_normal((Co, C, 3, 3)) * 0.02).astype(np.float32)
+    bias = rng.standard_normal(Co).astype(np.float32)
+    d_bf = T(data).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    ref = RO.deform_conv(d_bf.float().cpu().numpy(), off, wgt, bias)
+    out = ops.deform_conv_nhwc(d_bf, T(off), T(wgt), T(bias), relu=False, out_dtype=torch.float32)
+    assert out.is_contiguous(memory_format=torch.channels_last)
+    e = rel_err(out.cpu().numpy(), ref)
+    print('deformable conv 512->512 @38x63, channels_last bf16 in: rel err vs oracle %.2e' % e)
+    assert e < 2e-3
+    out16 = ops.deform_conv_nhwc(d_bf, T(off), T(wgt), T(bias), relu=True)
+    assert rel_err(out16.float().cpu().numpy(), np.maximum(ref, 0)) < 3e-3
