@@ -10,9 +10,8 @@
 //   * channels-last maps (the hot path: the trunk's conv_new_1 output, fp32 or bf16): a thread owns a (bin, 4- or
 //     8-channel vector); every tap is one 16-byte load and consecutive threads read consecutive channels, so a warp
 //     fetches whole 128-byte lines and the 16 overlapping samples of a bin hit L1;
-//   * NCHW fp32 maps (the reference layout of the C ABI): a half warp owns a (channel, bin) and each lane one sample
-//     (all 64 taps of the bin fall in two or three cache lines of that channel's plane); the lane values are added in the
-//     reference's sample order through shuffles.
+//   * NCHW fp32 maps (the reference layout of the C ABI): a thread owns a (channel, bin), consecutive threads consecutive
+//     bins of one channel (their taps share cache lines of that channel's plane); samples are added in the reference's order.
 // Outputs are staged per bin row and written as runs of pooled_size floats.
 #include "common.cuh"
 #include <cuda_bf16.h>
@@ -92,29 +91,20 @@ __global__ void __launch_bounds__(256) psroi_fwd_kernel(rn_psroi_desc p, const v
     }
     __syncthreads();
     if (LAYOUT == 0) {
-      // half warp = one (channel, bin); lane = one sample (groups of 16 samples when spp2 > 16)
+      // NCHW: a thread owns a (channel, bin); consecutive threads take consecutive bins of one channel, whose taps share
+      // cache lines of that channel's plane.  The geometry comes from the table (no per-channel recomputation).
       const float* data = reinterpret_cast<const float*>(data_) + (size_t)r.b * p.channels * HW;
-      const int hl = threadIdx.x & 15, hw_id = threadIdx.x >> 4, nhw = blockDim.x >> 4;
-      const unsigned hmask = 0xFFFFu << (threadIdx.x & 16);
-      for (int item = hw_id; item < cec * pooled; item += nhw) {
+      for (int item = threadIdx.x; item < cec * pooled; item += blockDim.x) {
         const int cl = item / pooled, pw = item - cl * pooled;
-        const int ctop = cls * cec + cl;
         int gw = (int)floorf((float)pw * gs / pooled);
         gw = min(max(gw, 0), gs - 1);
-        const float* d0 = data + (size_t)((ctop * gs + gh) * gs + gw) * HW;
+        const float* d0 = data + (size_t)(((cls * cec + cl) * gs + gh) * gs + gw) * HW;
         float sum = 0.f;
-        for (int s0 = 0; s0 < spp2; s0 += 16) {
-          float v = 0.f;
-          if (s0 + hl < spp2) {
-            const PsSample t = tab[pw * spp2 + s0 + hl];
-            if (t.valid) v = ps_interp(t, __ldg(d0 + t.o11), __ldg(d0 + t.o12), __ldg(d0 + t.o21), __ldg(d0 + t.o22));
-          }
-          for (int s = 0; s < min(16, spp2 - s0); ++s) {           // the reference's summation order (ih outer, iw inner)
-            const float vs = __shfl_sync(hmask, v, (threadIdx.x & 16) + s);
-            if (tab[pw * spp2 + s0 + s].valid) sum += vs;
-          }
+        for (int s = 0; s < spp2; ++s) {
+          const PsSample t = tab[pw * spp2 + s];
+          if (t.valid) sum += ps_interp(t, __ldg(d0 + t.o11), __ldg(d0 + t.o12), __ldg(d0 + t.o21), __ldg(d0 + t.o22));
         }
-        if (hl == 0) stage[cl * pooled + pw] = cnt[pw] == 0 ? 0.f : sum / cnt[pw];
+        stage[cl * pooled + pw] = cnt[pw] == 0 ? 0.f : sum / cnt[pw];
       }
     } else {
       constexpr int VEC = LAYOUT == 1 ? 4 : 8;

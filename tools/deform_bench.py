@@ -37,5 +37,5 @@ bf = data.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
 for name, fn in (('nchw_fp32_entry_f16', lambda: ops.deform_conv(data, off, wgt, precision='f16')),
                  ('nhwc_bf16_fast_path', lambda: ops.deform_conv_nhwc(bf, off, wgt, relu=True))):
     us = t_us(fn)
-    print(json.dumps(dict(kernel='deform_conv_fwd', path=name, us=round(us, 2), gflop=round(gf, 2), tflops=round(gf / us * 1e-3 * 1e3, 1),
-                          frac_of_measured_bf16_peak=round(gf / us * 1e-3 * 1e3 / peak, 4))), flush=True)
+    print(json.dumps(dict(kernel='deform_conv_fwd', path=name, us=round(us, 2), gflop=round(gf, 2), tflops=round(gf / us * 1e3, 1),
+                          frac_of_measured_bf16_peak=round(gf / us * 1e3 / peak, 4))), flush=True)
