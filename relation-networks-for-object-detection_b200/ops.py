@@ -539,38 +539,59 @@ def roi_pool_backward(grad_out, argmax, rois, data_shape):
     return dd
 
 
-def roi_pool_fc(data, rois, W, b, pooled_size=(7, 7), spatial_scale=0.0625, relu=False, want_f16=False):
-    """ROIPooling + FullyConnected fused at the data-layout level (SYM_REL:252-262 with RN_PREC_F16): channels-last
-    feature map -> fp16 pooled [R, PH*PW*C] -> tcgen05 GEMM against the K-permuted packed weight.  Returns fp32 [R, out].
-    ``data`` is an NCHW-shaped tensor; a channels_last one is consumed without a copy."""
+def roi_pool_nhwc_f16(data, rois, spatial_scale, pooled_size=(7, 7), out=None):
+    """ROIPooling (max) from a channels-last map (fp32 or bf16, consumed without a copy) to fp16 [R, PH*PW*C] (bin-major,
+    channel-minor: the K order of a weight packed by rn_linear_pack_chw_to_hwc)."""
     if not data.is_cuda:
-        raise L.RelnetError('roi_pool_fc: CUDA tensors required (no CPU path)')
+        raise L.RelnetError('roi_pool_nhwc_f16: CUDA tensors required (no CPU path)')
     B, Cc, H, Wd = data.shape
-    rois = _f32(rois, 'rois'); W = _f32(W, 'W'); b = _f32(b, 'b') if b is not None else None
+    rois = _f32(rois, 'rois')
     R = rois.shape[0]
-    S = pooled_size[0] * pooled_size[1]
-    cin, cout = Cc * S, W.shape[0]
-    assert W.shape[1] == cin
+    cin = Cc * pooled_size[0] * pooled_size[1]
     lib = L.lib()
-    pooled = torch.empty((R, cin), dtype=torch.float16, device=data.device)
+    if out is None:
+        out = torch.empty((R, cin), dtype=torch.float16, device=data.device)
+    elif not (out.is_cuda and out.dtype == torch.float16 and out.is_contiguous() and tuple(out.shape) == (R, cin)):
+        raise L.RelnetError('roi_pool_nhwc_f16: out must be a contiguous fp16 [R, PH*PW*C] CUDA tensor')
+    if R == 0:
+        return out
     if data.dtype == torch.bfloat16 and Cc % 8 == 0:       # the trunk's native output: pooled straight from bf16
         nhwc = data.contiguous(memory_format=torch.channels_last)
         L.check(lib.rn_roi_pool_nhwc_bf16in_f16_fwd(_ptr(nhwc), _ptr(rois), R, Cc, H, Wd, pooled_size[0], pooled_size[1],
-                                                    spatial_scale, _ptr(pooled), _stream()), 'rn_roi_pool_nhwc_bf16in_f16_fwd')
+                                                    spatial_scale, _ptr(out), _stream()), 'rn_roi_pool_nhwc_bf16in_f16_fwd')
     else:
         nhwc = data.float().contiguous(memory_format=torch.channels_last)      # no-op for an fp32 channels-last map
         L.check(lib.rn_roi_pool_nhwc_f16_fwd(_ptr(nhwc), _ptr(rois), R, Cc, H, Wd, pooled_size[0], pooled_size[1],
-                                             spatial_scale, _ptr(pooled), _stream()), 'rn_roi_pool_nhwc_f16_fwd')
+                                             spatial_scale, _ptr(out), _stream()), 'rn_roi_pool_nhwc_f16_fwd')
+    return out
+
+
+def linear_pooled_hwc(pooled16, W, b, Cc, S, relu=False, want_f16=False):
+    """FullyConnected on a bin-major pooled tensor (roi_pool_nhwc_f16) with the reference-layout weight [out, C*S]: the
+    weight is packed once with its K axis permuted from (c, s) to (s, c)."""
+    W = _f32(W, 'W'); b = _f32(b, 'b') if b is not None else None
+    R, cin = pooled16.shape
+    cout = W.shape[0]
+    assert W.shape[1] == cin == Cc * S
+    lib = L.lib()
 
     def pack(buf):
         L.check(lib.rn_linear_pack_chw_to_hwc(_ptr(W), cout, Cc, S, _ptr(buf), _stream()), 'rn_linear_pack_chw_to_hwc')
     packed = _packs.get_tagged('chw2hwc', (W,), lib.rn_linear_packed_bytes(cin, cout), pack)
-    y = torch.empty((R, cout), dtype=torch.float32, device=data.device)
-    ws = _workspace(lib.rn_linear_workspace_bytes(R, cin, cout, 1), data.device)
-    y16 = torch.empty((R, cout), dtype=torch.float16, device=data.device) if want_f16 else None
-    L.check(lib.rn_linear_packed_f16in_fwd(_ptr(pooled), _ptr(packed), _ptr(b), _ptr(y), _ptr(y16), R, cin, cout, int(relu),
+    y = torch.empty((R, cout), dtype=torch.float32, device=pooled16.device)
+    ws = _workspace(lib.rn_linear_workspace_bytes(R, cin, cout, 1), pooled16.device)
+    y16 = torch.empty((R, cout), dtype=torch.float16, device=pooled16.device) if want_f16 else None
+    L.check(lib.rn_linear_packed_f16in_fwd(_ptr(pooled16), _ptr(packed), _ptr(b), _ptr(y), _ptr(y16), R, cin, cout, int(relu),
                                            _ptr(ws), ws.numel(), _stream()), 'rn_linear_packed_f16in_fwd')
     return (y, y16) if want_f16 else y
+
+
+def roi_pool_fc(data, rois, W, b, pooled_size=(7, 7), spatial_scale=0.0625, relu=False, want_f16=False):
+    """ROIPooling + FullyConnected fused at the data-layout level (SYM_REL:252-262 with RN_PREC_F16): channels-last
+    feature map -> fp16 pooled [R, PH*PW*C] -> tcgen05 GEMM against the K-permuted packed weight.  Returns fp32 [R, out].
+    ``data`` is an NCHW-shaped tensor; a channels_last one is consumed without a copy."""
+    pooled = roi_pool_nhwc_f16(data, rois, spatial_scale, pooled_size)
+    return linear_pooled_hwc(pooled, W, b, data.shape[1], pooled_size[0] * pooled_size[1], relu=relu, want_f16=want_f16)
 
 
 def deform_psroi_pool(data, rois, trans=None, spatial_scale=0.0625, output_dim=256, group_size=1, pooled_size=7,

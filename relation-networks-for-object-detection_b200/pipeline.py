@@ -74,17 +74,21 @@ class RelationHead(object):
         self.nongt_dim = post_nms_top_n
         self._ws, self._dummy, self._side = {}, {}, None
 
-    def relation(self, x, boxes, idx, nongt_dim, stage_mask=7, x_f16=None, want_f16=False):
+    def relation(self, x, boxes, idx, nongt_dim, stage_mask=7, x_f16=None, want_f16=False, key_index=None):
         P = self.P
         ws = None
+        if key_index is not None:
+            nongt_dim = int(key_index.numel())
         if self.precision == 'f16':        # module-owned scratch so the geometry stage can run early on another stream
-            ws = self._ws.get(idx)
+            key = (idx, boxes.shape[0], nongt_dim, ops.relation_fused_active())
+            ws = self._ws.get(key)
             if ws is None:
                 nbytes = ops.relation_workspace_bytes(boxes.shape[0], nongt_dim, 1024, 1024, 1024, 16)
-                ws = self._ws[idx] = torch.empty(nbytes + 4096, dtype=torch.uint8, device=boxes.device)
+                ws = self._ws[key] = torch.empty(nbytes + 4096, dtype=torch.uint8, device=boxes.device)
         return ops.relation(x, boxes, P['query_%d_weight' % idx], P['query_%d_bias' % idx], P['key_%d_weight' % idx],
                             P['key_%d_bias' % idx], P['pair_pos_fc1_%d_weight' % idx], P['pair_pos_fc1_%d_bias' % idx],
-                            P['linear_out_%d_weight' % idx], P['linear_out_%d_bias' % idx], M=nongt_dim, group=16,
+                            P['linear_out_%d_weight' % idx], P['linear_out_%d_bias' % idx],
+                            M=None if key_index is not None else nongt_dim, key_index=key_index, group=16,
                             residual_relu=True, precision=self.precision, stage_mask=stage_mask, workspace=ws,
                             x_f16=x_f16, want_f16=want_f16)
 
@@ -120,46 +124,137 @@ class RelationHead(object):
 
     def detect(self, rois, conv_feat, im_info, geometry_done=False, join=None):
         P, prec = self.P, self.precision
-        rel_mask = 5 if geometry_done else 7        # 1 = projection, 2 = geometry, 4 = fused attention
-        boxes = rois[:, 1:].contiguous()                                                          # :337
         if prec == 'f16':
             # :335 + :344 at the layout level: channels-last pool -> fp16 -> K-permuted fc_new_1.  Every layer hands an
             # fp16 copy of its output to the next GEMM (written by the producing epilogue), so no cast kernels run.
             fc1, fc1_h = ops.roi_pool_fc(conv_feat, rois, P['fc_new_1_weight'], P['fc_new_1_bias'], (7, 7),
                                          1.0 / self.cfg['feat_stride'], want_f16=True)
+        else:
+            pooled = ops.roi_pool(conv_feat, rois, (7, 7), 1.0 / self.cfg['feat_stride'])         # :335
+            fc1, fc1_h = ops.linear(pooled, P['fc_new_1_weight'], P['fc_new_1_bias'], precision=prec), None   # :344
+        return self.tail(rois, fc1, fc1_h, im_info, geometry_done, join)
+
+    def tail(self, rois, fc1, fc1_h, im_info, geometry_done=False, join=None, key_index=None):
+        """relation#1 -> fc_new_2 -> relation#2 -> cls/bbox -> learn_nms from the output of the first FC (SYM_REL_NMS:346-565);
+        shared by the Faster, Deformable and FPN heads (key_index: the FPN form's non_gt_index)."""
+        P, prec = self.P, self.precision
+        rel_mask = 5 if geometry_done else 7        # 1 = projection, 2 = geometry, 4 = fused attention
+        boxes = rois[:, 1:].contiguous()                                                          # :337
+        nkw = dict(non_gt_index=key_index) if key_index is not None else dict(nongt_dim=self.nongt_dim)
+        if prec == 'f16':
             if join is not None:
                 torch.cuda.current_stream().wait_stream(join)
-            fc_all_1, a1_h = self.relation(fc1, boxes, 1, self.nongt_dim, rel_mask, x_f16=fc1_h, want_f16=True)   # :346-351
+            fc_all_1, a1_h = self.relation(fc1, boxes, 1, self.nongt_dim, rel_mask, x_f16=fc1_h, want_f16=True,
+                                           key_index=key_index)                                                   # :346-351
             fc2, fc2_h = ops.linear(fc_all_1, P['fc_new_2_weight'], P['fc_new_2_bias'], precision=prec, x_f16=a1_h,
                                     want_f16=True)                                                                # :353
-            fc_all_2, a2_h = self.relation(fc2, boxes, 2, self.nongt_dim, rel_mask, x_f16=fc2_h, want_f16=True)   # :354-359
+            fc_all_2, a2_h = self.relation(fc2, boxes, 2, self.nongt_dim, rel_mask, x_f16=fc2_h, want_f16=True,
+                                           key_index=key_index)                                                   # :354-359
             # cls_score, bbox_pred (:360-365) and roi_feat_embedding (LNMS:339) all read fc_all_2_relu: one GEMM
             cls_score, bbox_pred, emb = ops.linear_multi(a2_h, [
                 (P['cls_score_weight'], P['cls_score_bias']), (P['bbox_pred_weight'], P['bbox_pred_bias']),
                 (P['roi_feat_embedding_weight'], P['roi_feat_embedding_bias'])])
             multi, sorted_bbox, sorted_score, final = ops.learn_nms(                              # :518-560
                 cls_score, bbox_pred, rois, im_info, fc_all_2, {k: P[k] for k in NMS_NAMES}, first_n=self.first_n,
-                class_thresh=self.class_thresh, nongt_dim=self.nongt_dim, merge_method=self.merge_method, precision=prec,
-                feat_f16=a2_h, emb=emb)
+                class_thresh=self.class_thresh, merge_method=self.merge_method, precision=prec,
+                feat_f16=a2_h, emb=emb, **nkw)
             return dict(rois=rois, cls_score=cls_score, bbox_pred=bbox_pred, fc_all_2_relu=fc_all_2,
                         nms_multi_score=multi, learn_nms_sorted_bbox=sorted_bbox, sorted_score=sorted_score,
                         nms_final_score_output=final)
-        else:
-            pooled = ops.roi_pool(conv_feat, rois, (7, 7), 1.0 / self.cfg['feat_stride'])         # :335
-            fc1 = ops.linear(pooled, P['fc_new_1_weight'], P['fc_new_1_bias'], precision=prec)    # :344
         if join is not None:
             torch.cuda.current_stream().wait_stream(join)
-        fc_all_1 = self.relation(fc1, boxes, 1, self.nongt_dim, rel_mask)                         # :346-351
+        fc_all_1 = self.relation(fc1, boxes, 1, self.nongt_dim, rel_mask, key_index=key_index)    # :346-351
         fc2 = ops.linear(fc_all_1, P['fc_new_2_weight'], P['fc_new_2_bias'], precision=prec)      # :353
-        fc_all_2 = self.relation(fc2, boxes, 2, self.nongt_dim, rel_mask)                         # :354-359
+        fc_all_2 = self.relation(fc2, boxes, 2, self.nongt_dim, rel_mask, key_index=key_index)    # :354-359
         cls_score = ops.linear(fc_all_2, P['cls_score_weight'], P['cls_score_bias'], precision=prec)
         bbox_pred = ops.linear(fc_all_2, P['bbox_pred_weight'], P['bbox_pred_bias'], precision=prec)
         multi, sorted_bbox, sorted_score, final = ops.learn_nms(                                  # :518-560
             cls_score, bbox_pred, rois, im_info, fc_all_2, {k: P[k] for k in NMS_NAMES}, first_n=self.first_n,
-            class_thresh=self.class_thresh, nongt_dim=self.nongt_dim, merge_method=self.merge_method, precision=prec)
+            class_thresh=self.class_thresh, merge_method=self.merge_method, precision=prec, **nkw)
         return dict(rois=rois, cls_score=cls_score, bbox_pred=bbox_pred, fc_all_2_relu=fc_all_2,
                     nms_multi_score=multi, learn_nms_sorted_bbox=sorted_bbox, sorted_score=sorted_score,
                     nms_final_score_output=final)
+
+
+class DeformableRelationHead(RelationHead):
+    """BASELINE.json configs[2]: Deformable Faster-RCNN 2FC + Relation + Learn-NMS at test time
+    (SYM_DCN_REL_NMS:1073-1080): DeformablePSROIPooling (no_trans) -> `offset` FC (12544 -> 98) -> DeformablePSROIPooling
+    with the learned part offsets (trans_std 0.1) -> fc_new_1 -> the same tail as the Faster head.  Extra parameters:
+    'offset_weight' [98, 12544], 'offset_bias' [98] (zero-initialised in the reference, :1531-1532; N(0, 0.01) here so the
+    second pooling really is deformed -- SURVEY.md section 8d config 2)."""
+
+    def __init__(self, params, **kw):
+        super().__init__(params, **kw)
+        if 'offset_weight' not in self.P:
+            g = torch.Generator().manual_seed(11)
+            dev = self.P['fc_new_1_weight'].device
+            self.P['offset_weight'] = (torch.randn((98, 12544), generator=g) * 0.01).to(dev)
+            self.P['offset_bias'] = torch.zeros(98, device=dev)
+
+    def detect(self, rois, conv_feat, im_info, geometry_done=False, join=None):
+        P, prec = self.P, self.precision
+        scale = 1.0 / self.cfg['feat_stride']
+        kw = dict(spatial_scale=scale, output_dim=256, group_size=1, pooled_size=7, part_size=7, sample_per_part=4)
+        offset_t = ops.deform_psroi_pool(conv_feat, rois, None, **kw)                             # :1073-1074
+        offset = ops.linear(offset_t, P['offset_weight'], P['offset_bias'], precision=prec)       # :1075
+        pooled = ops.deform_psroi_pool(conv_feat, rois, offset.reshape(-1, 2, 7, 7), trans_std=0.1, **kw)   # :1078-1080
+        if prec == 'f16':
+            fc1, fc1_h = ops.linear(pooled, P['fc_new_1_weight'], P['fc_new_1_bias'], precision=prec, want_f16=True)
+        else:
+            fc1, fc1_h = ops.linear(pooled, P['fc_new_1_weight'], P['fc_new_1_bias'], precision=prec), None
+        return self.tail(rois, fc1, fc1_h, im_info, geometry_done, join)
+
+
+def fpn_level(rois, k_min=2, k_max=5):
+    """FPN level of each roi: floor(2 + log2(sqrt(w h) / 224)) clipped to [2, 5], w = x2 - x1 + 1 (core/rcnn.py:55 and
+    lib/rpn/rpn.py; the data loader's job in the reference).  Returns int64 [R] in 0..3 (level - 2)."""
+    w = rois[:, 3] - rois[:, 1] + 1.0
+    h = rois[:, 4] - rois[:, 2] + 1.0
+    lvl = torch.floor(2.0 + torch.log2(torch.sqrt(w * h) / 224.0)).clamp(k_min, k_max)
+    return (lvl - k_min).long()
+
+
+class FPNRelationHead(RelationHead):
+    """BASELINE.json configs[3] at test time (SYM_FPN_REL_NMS:1061-1141, get_symbol_rcnn): the rois arrive already
+    dispatched to the four pyramid levels (rois_0..3, strides 4 / 8 / 16 / 32); ROIPooling per level, concatenated in level
+    order; roi_pool_fc1/2 with two relation modules whose keys are `non_gt_index` (all rois at test time); learn-NMS with
+    first_n = 150.  Parameter names: the reference's FPN checkpoints call the FCs roi_pool_fc1/2 -- the fc_new_1/2 keys of
+    init_head_params are used for both."""
+
+    STRIDES = (4, 8, 16, 32)
+
+    def __init__(self, params, first_n=150, **kw):
+        super().__init__(params, first_n=first_n, **kw)
+
+    def split_rois(self, rois):
+        """level-sorted rois (stable), per-level counts: what the loader hands the symbol as rois_0..3"""
+        lvl = fpn_level(rois)
+        order = torch.argsort(lvl, stable=True)
+        counts = torch.bincount(lvl, minlength=4).tolist()
+        return rois[order].contiguous(), counts
+
+    def detect(self, rois_sorted, counts, feats, im_info, non_gt_index=None):
+        """rois_sorted [R,5] in level order with `counts` rois per level; feats: 4 maps [1,256,h_l,w_l]"""
+        P, prec = self.P, self.precision
+        R = rois_sorted.shape[0]
+        self.nongt_dim = R if non_gt_index is None else int(non_gt_index.numel())
+        outs, outs_h, start = [], [], 0
+        if prec == 'f16':
+            pooled = torch.empty((R, 49 * 256), dtype=torch.float16, device=rois_sorted.device)
+            for l, n in enumerate(counts):                                                        # :1108-1115
+                if n:
+                    ops.roi_pool_nhwc_f16(feats[l], rois_sorted[start:start + n], 1.0 / self.STRIDES[l], out=pooled[start:start + n])
+                start += n
+            fc1, fc1_h = ops.linear_pooled_hwc(pooled, P['fc_new_1_weight'], P['fc_new_1_bias'], 256, 49, want_f16=True)
+        else:
+            parts = []
+            for l, n in enumerate(counts):
+                if n:
+                    parts.append(ops.roi_pool(feats[l].float().contiguous(), rois_sorted[start:start + n], (7, 7), 1.0 / self.STRIDES[l]))
+                start += n
+            fc1 = ops.linear(torch.cat(parts, 0), P['fc_new_1_weight'], P['fc_new_1_bias'], precision=prec)    # :1130
+            fc1_h = None
+        return self.tail(rois_sorted, fc1, fc1_h, im_info, key_index=non_gt_index)
 
 
 class Detector(object):

@@ -163,6 +163,39 @@ class Trunk(nn.Module):
         y = _conv_relu(self.conv_new_1, self.res5(c4))
         return y if keep_dtype else y.float()
 
+    # ---- Deformable Faster-RCNN form of res5 (BASELINE.json configs[2]; resnet_v1_101_rcnn_dcn_*.py:700-748) -------------
+    @torch.no_grad()
+    def enable_dcn(self, seed=3):
+        """Adds the three `res5{a,b,c}_branch2b_offset` convs (3x3, dilate 2, 512 -> 72 = 2*9*4 deformable groups).  The
+        reference zero-initialises them (:1525-1530: the deformable conv then equals the plain one); N(0, 0.01) here so the
+        gather is non-trivial.  The 3x3 weights of res5 become the deformable conv weights
+        (kept in fp32 for the one-time fp16 pack)."""
+        g = torch.Generator().manual_seed(seed)
+        dev, dt = self.conv1.weight.device, self.conv1.weight.dtype
+        self.dcn_offset = nn.ModuleList([nn.Conv2d(512, 72, 3, padding=2, dilation=2) for _ in range(3)]).to(device=dev, dtype=dt)
+        for m in self.dcn_offset:
+            m.weight.data.copy_((torch.randn(m.weight.shape, generator=g) * 0.01).to(dev))
+            m.bias.data.zero_()
+            if dev.type == 'cuda':
+                m.to(memory_format=torch.channels_last)
+        self.dcn_weight = [b.c2.weight.detach().float().contiguous() for b in self.res5]
+        self.dcn_bias = [b.c2.bias.detach().float().contiguous() for b in self.res5]
+        return self
+
+    @torch.no_grad()
+    def c5feat_dcn(self, c4):
+        """res5 with DeformableConvolution in the three 3x3 positions (offset conv: library; deformable conv: our
+        channels-last sampler + tcgen05 GEMM, bias + relu fused) + conv_new_1 + relu -> [1,256,h,w] channels-last."""
+        from . import ops
+        x = c4
+        for i, blk in enumerate(self.res5):
+            y1 = _conv_relu(blk.c1, x)
+            off = self.dcn_offset[i](y1).float().contiguous()                        # [1,72,h,w] NCHW fp32 (0.7 MB)
+            y2 = ops.deform_conv_nhwc(y1, off, self.dcn_weight[i], self.dcn_bias[i], relu=True)     # fp16 channels_last
+            y2 = y2.to(y1.dtype)
+            x = _conv_add_relu(blk.c3, y2, blk.proj(x) if blk.proj is not None else x)
+        return _conv_relu(self.conv_new_1, x)
+
     @torch.no_grad()
     def forward(self, image):
         """image [1,3,H,W] -> (rpn_cls_prob, rpn_bbox_pred, conv_new_1_relu)"""
@@ -181,4 +214,52 @@ def make_trunk(device, dtype=torch.bfloat16, seed=0):
     if device != 'cpu' and str(device) != 'cpu':
         t = t.to(memory_format=torch.channels_last)
         t.prepare()
+    return t
+
+
+class FPNTrunk(nn.Module):
+    """ResNet-101 + FPN feature maps for BASELINE.json configs[3] (resnet_v1_101_rcnn_fpn_*.py get_resnet_v1_fpn_conv):
+    C2..C5 at strides 4..32 (res5 NOT dilated here), 1x1 laterals + nearest 2x top-down + 3x3 smoothing -> four 256-channel
+    maps fpn_ft4 / 8 / 16 / 32.  Library plumbing (torch/cuDNN), random init, only there to feed the head realistic maps."""
+
+    def __init__(self):
+        super().__init__()
+        self.conv1 = nn.Conv2d(3, 64, 7, stride=2, padding=3)
+        self.res2 = _stage(64, 64, 256, 3, 1)
+        self.res3 = _stage(256, 128, 512, 4, 2)
+        self.res4 = _stage(512, 256, 1024, 23, 2)
+        self.res5 = _stage(1024, 512, 2048, 3, 2)
+        self.lat = nn.ModuleList([nn.Conv2d(c, 256, 1) for c in (256, 512, 1024, 2048)])
+        self.smooth = nn.ModuleList([nn.Conv2d(256, 256, 3, padding=1) for _ in range(4)])
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode='fan_in', nonlinearity='relu')
+                nn.init.zeros_(m.bias)
+        self.conv1.weight.data.mul_(1.0 / 50.0)
+        for m in self.modules():
+            if isinstance(m, Bottleneck):
+                m.c3.weight.data.mul_(0.25)
+
+    @torch.no_grad()
+    def forward(self, image):
+        """image [1,3,H,W] (H, W multiples of 32) -> [fpn_ft4, fpn_ft8, fpn_ft16, fpn_ft32]"""
+        if image.dtype != self.conv1.weight.dtype:
+            image = image.to(self.conv1.weight.dtype)
+        if image.is_cuda:
+            image = image.contiguous(memory_format=torch.channels_last)
+        c2 = self.res2(F.max_pool2d(_conv_relu(self.conv1, image), 3, 2, padding=1))
+        c3 = self.res3(c2); c4 = self.res4(c3); c5 = self.res5(c4)
+        p = self.lat[3](c5)
+        outs = [None, None, None, self.smooth[3](p)]
+        for l, c in ((2, c4), (1, c3), (0, c2)):
+            p = self.lat[l](c) + F.interpolate(p, size=c.shape[-2:], mode='nearest')
+            outs[l] = self.smooth[l](p)
+        return outs
+
+
+def make_fpn_trunk(device, dtype=torch.bfloat16, seed=0):
+    torch.manual_seed(seed)
+    t = FPNTrunk().eval().to(device=device, dtype=dtype)
+    if str(device) != 'cpu':
+        t = t.to(memory_format=torch.channels_last)
     return t
