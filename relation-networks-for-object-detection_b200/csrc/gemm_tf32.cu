@@ -1,0 +1,277 @@
+// gemm_tf32.cu -- hand-written tcgen05 GEMM on fp32 operands (kind::tf32, fp32 accumulate in TMEM) with arbitrary
+// transposes and a two-level strided batch:
+//     C[o,i][M,N] = alpha * op(A[o,i]) . op(B[o,i]) + beta * C[o,i]         row-major, fp32 in HBM
+// It is the contraction engine of the TRAINING side (rn_relation_bwd / rn_learn_nms_bwd: dV' = P^T dO, dP = dO V'^T,
+// dQ = dS K, dK = dS^T Q, the projection-weight and input gradients, and the recomputed forward), replacing the cuBLAS
+// fp32 calls of round 1.  The reference has no counterpart: MXNet differentiates SYM_REL:104-151 op by op on cuBLAS.
+//
+// Why tf32 and not fp16 operands: gradients span many decades (fp16 would need loss scaling) and the operands already
+// sit in HBM as fp32 -- TMA loads them as they are, the tensor core reads the top 19 bits, no cast kernels, no packed
+// copies.  Both operand majors come straight from the row-major matrices:
+//   op(A) = A   (A stored [M,K]):  K-major tile, ONE TMA box [128 rows x 32 k] (SWIZZLE_128B rows of 32 floats)
+//   op(A) = A^T (A stored [K,M]):  MN-major tile, FOUR boxes [32 k rows x 32 m], each a column of 8x(32-float) atoms:
+//                                  descriptor LBO = 4096 (next 32 m), SBO = 1024 (next 8 k), +1024 B per K step of 8
+//   op(B): the same with N in place of M (B stored [N,K] = "transB" is the K-major case).
+// Out-of-range rows / columns / K are zero-filled by TMA (tensor-map extents are the true per-problem extents), so no
+// operand is ever padded in memory; the epilogue masks its stores.
+//
+// Structure: one CTA = one 128 x BN output tile of one problem; warp 4 = TMA producer, warp 5 = TMEM allocation + MMA
+// issue (one lane each), warps 0-3 = epilogue (TMEM lane quarter each; alpha / beta applied on the way out).  4-stage
+// ring of (A 16 KB + B <= 16 KB) stages, full/empty mbarriers, tcgen05.commit releases a stage.
+// Roofline: tensor pipe for the weight-gradient GEMMs (K = rois is short: they are launch/latency sized), L2 bandwidth
+// for the per-head attention gradients (operands are L2 resident: written by the previous kernel).
+#include "common.cuh"
+#include "umma.cuh"
+#include <mutex>
+
+namespace rn {
+using namespace umma;
+
+namespace {
+
+constexpr int kTM = 128, kTK = 32, kTStages = 4;
+constexpr int kTA = kTM * kTK * 4;                   // 16 KB
+constexpr int kTStage = 2 * kTA;                     // A + B (B up to 128 columns)
+constexpr int kTBar = kTStages * kTStage;
+constexpr int kTSmem = kTBar + 256 + 1024;
+
+struct Tf32Params {
+  int M, N, K, BN;
+  int a_mn, b_mn;                                    // 1: operand is MN-major in shared memory (stored transposed)
+  int inner;                                         // problems per outer index (blockIdx.y = o * inner + i)
+  float alpha, beta;
+  float* C; long long ldc, sCo, sCi;
+};
+
+// kind::tf32 instruction descriptor (cute InstrDescriptor): c_format F32, a/b_format 2 = TF32
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool a_mn, bool b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(192, 1) gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                              const __grid_constant__ CUtensorMap tmB, const Tf32Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kTBar);
+  uint64_t* empty = full + kTStages;
+  uint64_t* tfull = empty + kTStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_n = (p.N + p.BN - 1) / p.BN;
+  const int m0 = (blockIdx.x / tiles_n) * kTM, n0 = (blockIdx.x % tiles_n) * p.BN;
+  const int bo = blockIdx.y / p.inner, bi = blockIdx.y % p.inner;
+  const int nkb = (p.K + kTK - 1) / kTK;
+
+  if (warp == 4 && lane == 0) {
+    prefetch_tmap(&tmA); prefetch_tmap(&tmB);
+    for (int s = 0; s < kTStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc<128>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      const uint32_t bytesA = kTA;                                  // OOB parts of a box still count as transferred bytes
+      const uint32_t bytesB = (uint32_t)p.BN * kTK * 4;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % kTStages;
+        mbar_wait(&empty[s], ((kb / kTStages) & 1) ^ 1);
+        mbar_arrive_expect_tx(&full[s], bytesA + bytesB);
+        uint8_t* sa = smem + s * kTStage;
+        uint8_t* sb = sa + kTA;
+        if (p.a_mn) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) tma_load_4d(sa + j * 4096, &tmA, &full[s], m0 + 32 * j, kb * kTK, bi, bo);
+        } else {
+          tma_load_4d(sa, &tmA, &full[s], kb * kTK, m0, bi, bo);
+        }
+        if (p.b_mn) {
+          for (int j = 0; j < p.BN / 32; ++j) tma_load_4d(sb + j * 4096, &tmB, &full[s], n0 + 32 * j, kb * kTK, bi, bo);
+        } else {
+          tma_load_4d(sb, &tmB, &full[s], kb * kTK, n0, bi, bo);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(kTM, p.BN, p.a_mn != 0, p.b_mn != 0);
+      const uint32_t stepA = p.a_mn ? 1024u : 32u, stepB = p.b_mn ? 1024u : 32u;        // bytes per K step of 8
+      const uint32_t lboA = p.a_mn ? 4096u : 16u, lboB = p.b_mn ? 4096u : 16u;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % kTStages;
+        mbar_wait(&full[s], (kb / kTStages) & 1);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * kTStage), sb = sa + kTA;
+        const int ksteps = min(kTK, p.K - kb * kTK + 7) >> 3;          // whole K steps that hold at least one real k
+        for (int k = 0; k < ksteps; ++k)
+          mma_tf32_ss(tmem_base, make_smem_desc_sw128(sa + k * stepA, lboA, 1024), make_smem_desc_sw128(sb + k * stepB, lboB, 1024),
+                      idesc, (kb > 0) || (k > 0));
+        mma_commit(&empty[s]);
+      }
+      mma_commit(tfull);
+    }
+  } else {
+    // epilogue: thread (warp, lane) owns accumulator row 32 * warp + lane
+    const int row = m0 + warp * 32 + lane;
+    float* Cb = p.C + (long long)bo * p.sCo + (long long)bi * p.sCi;
+    if (nkb > 0) { mbar_wait(tfull, 0); tc_fence_after(); }
+    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const bool vec = (p.ldc & 3) == 0 && (((size_t)Cb) & 15) == 0;
+#pragma unroll 1
+    for (int c = 0; c < p.BN; c += 16) {
+      uint32_t v[16];
+      if (nkb > 0) { tmem_ld_32x32b_x16(lane_base + c, v); tmem_ld_wait(); }
+      else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0u;
+      }
+      const int col0 = n0 + c;
+      if (row >= p.M || col0 >= p.N) continue;
+      float* dst = Cb + (long long)row * p.ldc + col0;
+      if (vec && col0 + 16 <= p.N) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          float4 o = make_float4(p.alpha * __uint_as_float(v[j]), p.alpha * __uint_as_float(v[j + 1]),
+                                 p.alpha * __uint_as_float(v[j + 2]), p.alpha * __uint_as_float(v[j + 3]));
+          if (p.beta != 0.f) {
+            const float4 old = *reinterpret_cast<const float4*>(dst + j);
+            o.x = fmaf(p.beta, old.x, o.x); o.y = fmaf(p.beta, old.y, o.y); o.z = fmaf(p.beta, old.z, o.z); o.w = fmaf(p.beta, old.w, o.w);
+          }
+          *reinterpret_cast<float4*>(dst + j) = o;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (col0 + j < p.N) {
+            float o = p.alpha * __uint_as_float(v[j]);
+            if (p.beta != 0.f) o = fmaf(p.beta, dst[j], o);
+            dst[j] = o;
+          }
+      }
+    }
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc<128>(tmem_base);
+}
+
+// ---- host: fp32 tensor maps --------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode32 = nullptr;
+std::once_flag g_once32;
+void load_encode32() {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+    g_encode32 = (EncodeTiledFn)fn;
+  else
+    cudaGetLastError();
+}
+
+// matrix stored row-major [rows, cols] (pitch ld floats) per problem, problems at base + o*sO + i*sI; box = 32 cols x box_rows
+int encode_f32_4d(CUtensorMap* out, const float* base, int rows, int cols, long long ld, int inner, int outer, long long sI,
+                  long long sO, int box_rows) {
+  std::call_once(g_once32, load_encode32);
+  if (!g_encode32) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return RN_ERR_CUDA; }
+  const long long fallback = ld * (long long)rows;            // any valid stride for extent-1 dimensions
+  cuuint64_t dims[4] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 4, (cuuint64_t)(inner > 1 ? sI : fallback) * 4, (cuuint64_t)(outer > 1 ? sO : fallback) * 4};
+  for (int i = 1; i < 3; ++i) if (strides[i] == 0) strides[i] = strides[0];
+  cuuint32_t box[4] = {32, (cuuint32_t)box_rows, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode32(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("gemm_tf32: cuTensorMapEncodeTiled failed: %d (ptr=%p rows=%d cols=%d ld=%lld inner=%d outer=%d sI=%lld sO=%lld)", (int)r,
+              (const void*)base, rows, cols, ld, inner, outer, sI, sO);
+    return RN_ERR_CUDA;
+  }
+  return RN_OK;
+}
+
+thread_local int g_backend = 0;          // 0 = cuBLAS fp32 (pedantic), 1 = tcgen05 tf32
+
+}  // namespace
+
+bool gemm_tf32_usable(const float* A, int lda, long long sAo, long long sAi, const float* B, int ldb, long long sBo, long long sBi) {
+  auto ok = [](const float* p, long long ld, long long so, long long si) {
+    return (((size_t)p) & 15) == 0 && (ld & 3) == 0 && (so & 3) == 0 && (si & 3) == 0 && ld > 0;
+  };
+  return is_sm100() && ok(A, lda, sAo, sAi) && ok(B, ldb, sBo, sBi);
+}
+
+int gemm_tf32(cudaStream_t st, bool transA, bool transB, int M, int N, int K, float alpha, const float* A, int lda,
+              long long sAo, long long sAi, const float* B, int ldb, long long sBo, long long sBi, float beta, float* C,
+              int ldc, long long sCo, long long sCi, int outer, int inner) {
+  if (M <= 0 || N <= 0 || outer <= 0 || inner <= 0) return RN_OK;
+  RN_CHECK_ARG(gemm_tf32_usable(A, lda, sAo, sAi, B, ldb, sBo, sBi),
+               "gemm_tf32: operands need 16-byte aligned bases and pitches / batch strides that are multiples of 4 floats");
+  RN_CHECK_ARG((long long)outer * inner <= 65535, "gemm_tf32: %d x %d problems exceed the grid", outer, inner);
+  Tf32Params p;
+  p.M = M; p.N = N; p.K = K;
+  p.a_mn = transA ? 1 : 0;                 // op(A) = A^T: A stored [K, M] -> M contiguous
+  p.b_mn = transB ? 0 : 1;                 // op(B) = B:   B stored [K, N] -> N contiguous
+  const int gran = p.b_mn ? 32 : 16;
+  p.BN = std::min(128, (N + gran - 1) / gran * gran);
+  p.inner = inner; p.alpha = alpha; p.beta = beta;
+  p.C = C; p.ldc = ldc; p.sCo = sCo; p.sCi = sCi;
+  CUtensorMap tmA, tmB;
+  int r;
+  if (p.a_mn) r = encode_f32_4d(&tmA, A, K, M, lda, inner, outer, sAi, sAo, kTK);
+  else r = encode_f32_4d(&tmA, A, M, K, lda, inner, outer, sAi, sAo, kTM);
+  if (r) return r;
+  if (p.b_mn) r = encode_f32_4d(&tmB, B, K, N, ldb, inner, outer, sBi, sBo, kTK);
+  else r = encode_f32_4d(&tmB, B, N, K, ldb, inner, outer, sBi, sBo, p.BN);
+  if (r) return r;
+  static thread_local bool configured = false;
+  if (!configured) {
+    RN_CUDA(cudaFuncSetAttribute(gemm_tf32_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmem));
+    configured = true;
+  }
+  const int tiles = cdiv(M, kTM) * cdiv(N, p.BN);
+  gemm_tf32_tc_kernel<<<dim3((unsigned)tiles, (unsigned)(outer * inner)), 192, kTSmem, st>>>(tmA, tmB, p);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
+
+// ---- backend switch of the general GEMM helpers (thread-local, set by the backward entry points) -----------------------
+int gemm_backend() { return g_backend; }
+void set_gemm_backend(int b) { g_backend = b; }
+
+}  // namespace rn
+
+// C ABI: exported so the contraction engine of the training side can be checked on its own (tests/test_gpu_backward.py)
+extern "C" int rn_gemm_tf32(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda, long long sAo,
+                            long long sAi, const float* B, int ldb, long long sBo, long long sBi, float beta, float* C, int ldc,
+                            long long sCo, long long sCi, int outer, int inner, rn_stream_t stream) {
+  RN_CHECK_ARG(A && B && C && M >= 0 && N >= 0 && K >= 0, "rn_gemm_tf32: bad arguments");
+  RN_CHECK_ARG(rn::is_sm100(), "rn_gemm_tf32: needs an sm_100 device");
+  return rn::gemm_tf32((cudaStream_t)stream, transA != 0, transB != 0, M, N, K, alpha, A, lda, sAo, sAi, B, ldb, sBo, sBi, beta, C,
+                       ldc, sCo, sCi, outer, inner);
+}

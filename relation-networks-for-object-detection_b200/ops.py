@@ -39,8 +39,15 @@ def _ptr(t):
 
 
 class _PackCache(object):
-    """fp16 operand cache for RN_PREC_F16: keyed by the weight tensors' storage + in-place version counter, so an
-    optimizer step (in-place update) repacks and anything else reuses the packed block."""
+    """fp16 operand cache for RN_PREC_F16.
+
+    Identity of an entry = (tag, data_ptr + shape of every source tensor); `tag` carries the descriptor fields that shape
+    the packed layout (op, group, dv ...), so the same weights used under another descriptor get their own block.  Validity =
+    the sources' in-place version counters: an optimizer step that bumps `_version` REPLACES the entry for that identity
+    (no accumulation of dead packed buffers during training).  Updates that do not bump `_version` (`p.data.copy_()`,
+    raw-pointer writes, checkpoint loaders writing through `.data`) must call `invalidate_packed()` afterwards."""
+
+    MAX = 256
 
     def __init__(self):
         self.d = {}
@@ -49,19 +56,36 @@ class _PackCache(object):
         return self.get(tensors, nbytes, pack_fn, tag)
 
     def get(self, tensors, nbytes, pack_fn, tag=None):
-        key = (tag,) + tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors)
-        hit = self.d.get(key)
-        if hit is None:
-            if len(self.d) > 256:
-                self.d.clear()
-            buf = torch.empty(nbytes, dtype=torch.uint8, device=tensors[0].device)
-            pack_fn(buf)
-            hit = (buf, tensors)          # keep the sources alive so data_ptr stays unique
-            self.d[key] = hit
-        return hit[0]
+        ident = (tag,) + tuple((t.data_ptr(), tuple(t.shape)) for t in tensors)
+        ver = tuple(t._version for t in tensors)
+        hit = self.d.get(ident)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        if hit is None and len(self.d) >= self.MAX:
+            self.d.pop(next(iter(self.d)))          # oldest identity out (dict keeps insertion order)
+        buf = hit[1] if hit is not None and hit[1].numel() == nbytes else \
+            torch.empty(nbytes, dtype=torch.uint8, device=tensors[0].device)
+        pack_fn(buf)                                # same stream as every consumer: repacking in place is ordered
+        self.d[ident] = (ver, buf, tensors)         # keep the sources alive so data_ptr stays unique
+        return buf
+
+    def invalidate(self, tensors=None):
+        """forget every packed block (tensors=None) or the ones built from any of `tensors`"""
+        if tensors is None:
+            self.d.clear()
+            return
+        ptrs = set(t.data_ptr() for t in tensors)
+        for k in [k for k in self.d if any(e[0] in ptrs for e in k[1:])]:
+            del self.d[k]
 
 
 _packs = _PackCache()
+
+
+def invalidate_packed(tensors=None):
+    """Call after weight updates that bypass torch's version counter (`.data` writes, raw-pointer kernels, checkpoint
+    loads): drops the packed fp16 blocks of `tensors` (or all of them) so the next f16 call repacks."""
+    _packs.invalidate(tensors)
 
 
 def device_info():
@@ -128,7 +152,8 @@ def relation(X, boxes, Wq, bq, Wk, bk, Wg, bg, Wout, bout, key_index=None, M=Non
         def pack(buf):
             L.check(lib.rn_relation_pack(C.byref(desc), _ptr(Wq), _ptr(bq), _ptr(Wk), _ptr(bk), _ptr(Wout2), _ptr(bout),
                                          _ptr(buf), _stream()), 'rn_relation_pack')
-        packed = _packs.get((Wq, bq, Wk, bk, Wout2, bout), lib.rn_relation_packed_bytes(C.byref(desc)), pack)
+        packed = _packs.get((Wq, bq, Wk, bk, Wout2, bout), lib.rn_relation_packed_bytes(C.byref(desc)), pack,
+                             tag=('relation', group, dq, dout))
         if x_f16 is not None or want_f16:
             if x_f16 is not None and not (x_f16.is_cuda and x_f16.dtype == torch.float16 and x_f16.is_contiguous()
                                           and x_f16.numel() == X.numel()):
@@ -266,7 +291,7 @@ def linear(x, W, b=None, relu=False, precision=None, x_f16=None, want_f16=False)
     if precision == 'f16':
         def pack(buf):
             L.check(lib.rn_linear_pack(_ptr(W), cin, cout, _ptr(buf), _stream()), 'rn_linear_pack')
-        packed = _packs.get((W,), lib.rn_linear_packed_bytes(cin, cout), pack)
+        packed = _packs.get((W,), lib.rn_linear_packed_bytes(cin, cout), pack, tag=('linear',))
         if (x_f16 is not None or want_f16) and cin % 8 == 0:
             if x_f16 is None:
                 x_f16 = x2.to(torch.float16)
