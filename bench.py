@@ -45,7 +45,8 @@ def parse():
     ap.add_argument('--precision', default=None, choices=[None, 'f16', 'fp32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-sweep', action='store_true', help='skip the relation-module roofline sweep (configs[4])')
-    ap.add_argument('--no-train', action='store_true', help='skip the data-parallel training block (gradient allreduce)')
+    ap.add_argument('--no-train', action='store_true', help='skip the data-parallel training blocks (gradient allreduce)')
+    ap.add_argument('--no-configs', action='store_true', help='skip the configs[2] (Deformable) and configs[3] (FPN) blocks')
     return ap.parse_args()
 
 
@@ -262,27 +263,23 @@ def relation_kernel_roofline(ops, pk, device, sweep=True):
     return roof, times, sw
 
 
-def train_block(args, trunk_seed, device, world, rank, dist_on):
-    """Training form of the same config: fwd + bwd of one image per rank (trunk res3+ by torch/cuDNN autograd, the hot path
+def train_block(args, ts, images, im_info, device, world, rank, dist_on, mode):
+    """Training form of a config: fwd + bwd of `len(images)` images per rank (trunk res3+ by torch/cuDNN autograd, the hot path
     through the C-ABI forward / backward pairs), ONE flat gradient bucket, ONE NCCL SUM allreduce per step, SGD update.
     Reports ms/step (max over ranks), the allreduce's own milliseconds and bus bandwidth, the bucket size."""
     from relnet_b200 import replicas
-    from relnet_b200.train import TrainStep, bus_gbs
-    from relnet_b200.trunk import make_trunk
+    from relnet_b200.train import bus_gbs
     import torch.distributed as dist
-    ts = TrainStep(make_trunk(device, torch.bfloat16, seed=trunk_seed), device, micro_batches=1, lr=0.0)
-    image, im_info = make_inputs(seed=100 + rank)
-    image = image.to(device); im_info = im_info.to(device)
-    K, W = max(3, min(args.steps, 10)), 3
+    K, W = max(3, min(args.steps, 8)), 3
     for _ in range(W):
-        ts.step([image], im_info)
+        ts.step(images, im_info)
     # the exchange is a SUM: reduced bucket == sum over ranks of the local buckets (checked on a checksum of the bucket)
-    ts.step([image], im_info, exchange=False)
+    ts.step(images, im_info, exchange=False)
     local = ts.bucket.flat.double().sum()
     tot = local.clone()
     if dist_on:
         dist.all_reduce(tot)
-    ts.step([image], im_info, exchange=True)
+    ts.step(images, im_info, exchange=True)
     red = ts.bucket.flat.double().sum()
     chk = float((red - tot).abs() / tot.abs().clamp_min(1e-30))
     torch.cuda.synchronize()
@@ -292,19 +289,82 @@ def train_block(args, trunk_seed, device, world, rank, dist_on):
     evs = []
     e0.record()
     for _ in range(K):
-        evs.append(ts.step([image], im_info))
+        evs.append(ts.step(images, im_info))
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / K
     ms_ar = sorted(a.elapsed_time(b) for a, b in evs)[len(evs) // 2]
     ms = replicas.max_over_ranks(ms, device); ms_ar = replicas.max_over_ranks(ms_ar, device)
     nbytes = ts.bucket.flat.numel() * 4
-    return dict(mode='data-parallel training step, 1 image / GPU / step', images_per_sec=round(world / (ms / 1e3), 2),
+    return dict(mode=mode, images_per_sec=round(world * len(images) / (ms / 1e3), 2), images_per_rank_per_step=len(images),
                 ms_per_step=round(ms, 3), allreduce_ms=round(ms_ar, 4), allreduce_bus_gbs=round(bus_gbs(nbytes, ms_ar, world), 1),
                 bucket_mb=round(nbytes / 1e6, 1), collectives_per_step=1 if dist_on else 0, reduce_op='sum (rescale_grad = 1.0)',
                 reduced_vs_sum_of_ranks_rel=chk, steps=K, warmup=W, rois=ts.last.get('rois'),
+                backward_contractions='tcgen05 tf32 GEMM (gemm_tf32.cu) in rn_relation_bwd / rn_learn_nms_bwd',
                 launch='eager (torch autograd for the library trunk + the C-ABI fwd/bwd pairs of the hot path); allreduce after '
-                       'backward, not overlapped', losses={k: round(v, 4) for k, v in ts.last.items() if k != 'rois'})
+                       'backward, not overlapped',
+                losses={k: (round(v, 4) if isinstance(v, float) else v) for k, v in ts.last.items() if k != 'rois'})
+
+
+def config2_block(args, prec, device, world, dist_on, image32_d, im_info):
+    """BASELINE.json configs[2]: Deformable Faster-RCNN 2FC + Relation + LearnNMS, one image per GPU, same timing as the headline
+    (resident inputs, one CUDA-graph replay per image)."""
+    from relnet_b200.pipeline import DeformableRelationHead, Detector, GraphedStep, init_head_params
+    from relnet_b200.trunk import make_trunk
+    trunk = make_trunk(device, torch.bfloat16).enable_dcn()
+    head = DeformableRelationHead(init_head_params(0, device), precision=prec)
+    det = Detector(trunk, head, im_info, dcn=True)
+    g = GraphedStep(det, [image32_d])
+    steps = max(5, min(args.steps, 30))
+    ms = timed(lambda: g(image32_d), steps, 3, dist_on)
+    c4 = trunk.c4(image32_d)
+    g5 = GraphedStep(lambda c: trunk.c5feat_dcn(c), [c4])
+    ms5 = timed(lambda: g5(c4), steps, 3, dist_on)
+    return dict(workload='deformable_faster_rcnn_2fc_relation_learnnms_r101_600x1000_n300_h16', images_per_sec=round(world * steps / (ms / 1e3), 2),
+                ms_per_step=round(ms / steps, 4), steps=steps, res5_dcn_conv_new_1_ms=round(ms5 / steps, 4),
+                note='res5: 3 deformable convs (our channels-last sampler + tcgen05 GEMM, offset convs N(0,0.01)); head: '
+                     'DeformablePSROIPooling x2 with the offset FC between (our kernels); rest as configs[1]')
+
+
+def config3_block(args, prec, device, world, rank, dist_on, train=True):
+    """BASELINE.json configs[3]: FPN 2FC + Relation + LearnNMS.  test: one 608 x 1024 image per GPU, 1000 given rois over four
+    pyramid levels, n = 150 (replicas).  train: the data-parallel step -- 2 images per GPU per step accumulated locally, ONE
+    NCCL SUM allreduce of the whole gradient bucket (batch 16 on 8 GPUs)."""
+    from relnet_b200.pipeline import FPNDetector, FPNRelationHead, GraphedStep, init_head_params
+    from relnet_b200.train import FPNTrainStep
+    from relnet_b200.trunk import make_fpn_trunk
+    g = torch.Generator().manual_seed(1000 + rank)
+    image = (torch.randn((1, 3, 608, 1024), generator=g) * 50.0).to(device)
+    im_info = torch.tensor([[608.0, 1024.0, 1.0]], device=device)
+    trunk = make_fpn_trunk(device, torch.bfloat16)
+    head = FPNRelationHead(init_head_params(0, device), precision=prec)
+    import numpy as np
+    rng = np.random.default_rng(5)
+    sz = np.exp(rng.uniform(np.log(16.0), np.log(0.95 * 608), 1000)); ar = np.exp(rng.uniform(np.log(0.5), np.log(2.0), 1000))
+    w = np.minimum(sz * np.sqrt(ar), 1022); h = np.minimum(sz / np.sqrt(ar), 606)
+    x1 = rng.uniform(0, 1, 1000) * (1023 - w); y1 = rng.uniform(0, 1, 1000) * (607 - h)
+    rois = torch.tensor(np.stack([np.zeros(1000), x1, y1, x1 + w, y1 + h], 1), dtype=torch.float32, device=device)
+    det = FPNDetector(trunk, head, im_info, rois)
+    gs = GraphedStep(det, [image])
+    steps = max(5, min(args.steps, 30))
+    ms = timed(lambda: gs(image), steps, 3, dist_on)
+    feats = trunk(image)
+    gh = GraphedStep(lambda *f: head.detect(det.rois_sorted, det.counts, list(f), im_info), list(feats))
+    msh = timed(lambda: gh(*feats), steps, 3, dist_on)
+    out = dict(workload='fpn_2fc_relation_learnnms_r101_608x1024_n1000_h16_first150',
+               test=dict(images_per_sec=round(world * steps / (ms / 1e3), 2), ms_per_step=round(ms / steps, 4), steps=steps,
+                         head_ms_per_image=round(msh / steps, 4), rois_per_level=det.counts))
+    if train:
+        del gs, gh, det, head, trunk, feats
+        torch.cuda.empty_cache()
+        ts = FPNTrainStep(make_fpn_trunk(device, torch.bfloat16), device, num_rois=1000, micro_batches=2, lr=0.0)
+        images = [image, (torch.randn((1, 3, 608, 1024), generator=g) * 50.0).to(device)]
+        out['train'] = train_block(args, ts, images, im_info, device, world, rank, dist_on,
+                                   'configs[3] data-parallel training step: 2 images / GPU / step (batch %d), N = 1000 + G rois, '
+                                   'first_n = 150' % (2 * world))
+        del ts
+        torch.cuda.empty_cache()
+    return out
 
 
 def cpu_threads():
@@ -482,10 +542,22 @@ def main():
     ms_trunk = timed(lambda: trunk_graph(image32_d), args.steps, 3, dist_on)
 
     train = None
-    if not args.no_train:
-        del streamer, graphed, hot_graph, trunk_graph
+    cfg2 = cfg3 = None
+    del streamer, graphed, hot_graph, trunk_graph
+    torch.cuda.empty_cache()
+    if not args.no_configs and prec == 'f16':
+        cfg2 = config2_block(args, prec, device, world, dist_on, image32_d, im_info)
         torch.cuda.empty_cache()
-        train = train_block(args, 0, device, world, rank, dist_on)
+        cfg3 = config3_block(args, prec, device, world, rank, dist_on, train=not args.no_train)
+        torch.cuda.empty_cache()
+    if not args.no_train:
+        from relnet_b200.train import TrainStep
+        ts = TrainStep(make_trunk(device, torch.bfloat16, seed=0), device, micro_batches=1, lr=0.0)
+        timg, _ = make_inputs(seed=100 + rank)
+        train = train_block(args, ts, [timg.to(device)], im_info, device, world, rank, dist_on,
+                            'configs[1] data-parallel training step, 1 image / GPU / step')
+        del ts
+        torch.cuda.empty_cache()
     if rank == 0:
         pk = peaks()
         ours, lib, names = count_launches(lambda: full_step(image32_d))
@@ -516,6 +588,7 @@ def main():
             'clocks': sampler.summary() if sampler else None,
             'roofline': roof,
             'train': train,
+            'configs': {'2_deformable_faster': cfg2, '3_fpn': cfg3},
             'sweep': sweep,
         }
         if not args.no_cpu_baseline:

@@ -34,7 +34,11 @@ typedef void* rn_stream_t; /* cudaStream_t */
 
 const char* rn_last_error(void);
 int rn_version(void);
-/* 1 when the running device is sm_100 (tcgen05/TMA paths usable); fills *sm_count if non-NULL */
+/* 1 when the running device is sm_100 (tcgen05/TMA paths usable); fills *sm_count if non-NULL.
+ * PROCESS MODEL: one device per process (the reference's one executor per GPU; torchrun's one rank per GPU).  The device
+ * properties, the per-kernel launch attributes (> 48 KB dynamic shared memory) and the cuBLAS handle of the parity mode
+ * are cached for the device that is current at the first call; entry points called later with another device current
+ * return RN_ERR_INVALID ("librelnet_b200 is bound to device N") instead of launching with stale attributes. */
 int rn_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
 /* ---------------------------------------------------------------------------------------------------------------
@@ -121,12 +125,25 @@ int rn_relation_packed_stages(const rn_relation_desc* desc, const float* X, cons
  * be saved from rn_relation_fwd.  dOut [batch*N, dout] is the gradient of the loss w.r.t. rn_relation_fwd's `out`; every
  * gradient buffer is OVERWRITTEN (not accumulated) and has the shape of its parameter: dX [batch*N, d], dWq/dWk [dq, d],
  * dbq/dbk [dq], dWg [H, E], dbg [H], dWout [dout, d], dbout [dout].  Boxes receive no gradient (proposal.py:170-173). */
+/* desc->precision selects the contraction engine of the WHOLE backward (the recomputed forward included):
+ * RN_PREC_F16 = the library's own tcgen05 GEMM on the fp32 operands as they lie in HBM (kind::tf32, fp32 accumulate in
+ * TMEM: rn_gemm_tf32 below; sm_100 only); RN_PREC_FP32 = cuBLAS fp32, the bit-conservative parity mode. */
 size_t rn_relation_bwd_workspace_bytes(const rn_relation_desc* desc);
 int rn_relation_bwd(const rn_relation_desc* desc, const float* X, const float* boxes, const int32_t* key_index,
                     const float* Wq, const float* bq, const float* Wk, const float* bk, const float* Wg, const float* bg,
                     const float* Wout, const float* bout, const float* dOut, float* dX, float* dWq, float* dbq, float* dWk,
                     float* dbk, float* dWg, float* dbg, float* dWout, float* dbout, void* workspace,
                     size_t workspace_bytes, rn_stream_t stream);
+/* The contraction engine of the training side, exported for checking on its own: row-major fp32
+ *   C[o,i] (M x N, pitch ldc) = alpha * op(A[o,i]) . op(B[o,i]) + beta * C[o,i],   o < outer, i < inner,
+ * problem (o, i) of an operand at base + o * s?o + i * s?i (floats).  transA: A is stored [K, M] (else [M, K]); transB: B is
+ * stored [N, K] (else [K, N]).  Operands are read by TMA exactly as they lie (no cast, no packed copy), multiplied on
+ * tcgen05 tensor cores as tf32 (10-bit mantissa operands, fp32 accumulate).  Requirements: sm_100; 16-byte aligned bases;
+ * pitches and batch strides multiples of 4 floats; outer * inner <= 65535.  Replaces cuBLAS in rn_relation_bwd /
+ * rn_learn_nms_bwd under RN_PREC_F16 (the reference's backward is MXNet autograd over cuBLAS: no source to cite). */
+int rn_gemm_tf32(int32_t transA, int32_t transB, int32_t M, int32_t N, int32_t K, float alpha, const float* A, int32_t lda,
+                 int64_t sAo, int64_t sAi, const float* B, int32_t ldb, int64_t sBo, int64_t sBi, float beta, float* C,
+                 int32_t ldc, int64_t sCo, int64_t sCi, int32_t outer, int32_t inner, rn_stream_t stream);
 /* rn_relation_packed_stages with fp16 side channels: X_f16 (NULL or the producer's fp16 copy of X, [batch*N, d], d % 8 == 0)
  * replaces the module's own cast; out_f16 (NULL or [batch*N, dout] fp16) receives a copy of `out` for the consumer GEMM
  * (rn_linear_packed_f16in_fwd).  Same arithmetic as rn_relation_packed_fwd. */
@@ -305,7 +322,9 @@ int rn_proposal_target_fwd(const rn_proposal_target_desc* desc, const float* roi
 
 /* ---------------------------------------------------------------------------------------------------------------
  * ROIPooling (max; MXNet built-in used at SYM_REL:252-253).  data [B,C,H,W], rois [R,5] -> out [R,C,PH,PW],
- * argmax int32 same shape (may be NULL). */
+ * argmax int32 same shape (may be NULL).  rois[:,0] is the image index: a NEGATIVE index marks a padding roi (output 0,
+ * argmax -1, as MXNet's kernel does); indices >= B are the caller's error -- the forward entry points carry no B and
+ * cannot check them (rn_roi_pool_bwd, which knows B, skips such rows). */
 int rn_roi_pool_fwd(const float* data, const float* rois, int32_t R, int32_t C, int32_t H, int32_t W, int32_t PH,
                     int32_t PW, float spatial_scale, float* out, int32_t* argmax, rn_stream_t stream);
 

@@ -118,6 +118,8 @@ SIGNATURES = {
     'rn_deform_conv_pack': (C.c_int, [C.POINTER(DeformConvDesc), c_p, c_p, c_p]),
     'rn_deform_conv_nhwc_fwd': (C.c_int, [C.POINTER(DeformConvDesc), c_p, c_i, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_sz, c_p]),
     'rn_umma_selftest': (C.c_int, [c_p] * 6 + [c_p]),
+    'rn_gemm_tf32': (C.c_int, [c_i] * 5 + [c_f, c_p, c_i, C.c_int64, C.c_int64, c_p, c_i, C.c_int64, C.c_int64, c_f, c_p, c_i,
+                                C.c_int64, C.c_int64, c_i, c_i, c_p]),
 }
 
 _lib = None

@@ -12,9 +12,10 @@ class RelationFunction(torch.autograd.Function):
     """relu(X + relation(X)) or relation(X): rn_relation_fwd / rn_relation_bwd"""
 
     @staticmethod
-    def forward(ctx, X, boxes, Wq, bq, Wk, bk, Wg, bg, Wout, bout, key_index, M, group, residual_relu, precision):
+    def forward(ctx, X, boxes, Wq, bq, Wk, bk, Wg, bg, Wout, bout, key_index, M, group, residual_relu, precision,
+                grad_precision=None):
         ctx.save_for_backward(X, boxes, Wq, bq, Wk, bk, Wg, bg, Wout, bout)
-        ctx.key_index, ctx.M, ctx.group, ctx.residual_relu = key_index, M, group, residual_relu
+        ctx.key_index, ctx.M, ctx.group, ctx.residual_relu, ctx.grad_precision = key_index, M, group, residual_relu, grad_precision
         return ops.relation(X, boxes, Wq, bq, Wk, bk, Wg, bg, Wout, bout, key_index=key_index, M=M, group=group,
                             residual_relu=residual_relu, precision=precision)
 
@@ -22,15 +23,18 @@ class RelationFunction(torch.autograd.Function):
     def backward(ctx, grad_out):
         X, boxes, Wq, bq, Wk, bk, Wg, bg, Wout, bout = ctx.saved_tensors
         g = ops.relation_backward(grad_out.contiguous(), X, boxes, Wq, bq, Wk, bk, Wg, bg, Wout, bout,
-                                  key_index=ctx.key_index, M=ctx.M, group=ctx.group, residual_relu=ctx.residual_relu)
+                                  key_index=ctx.key_index, M=ctx.M, group=ctx.group, residual_relu=ctx.residual_relu,
+                                  precision=ctx.grad_precision)
         return (g['X'], None, g['Wq'], g['bq'], g['Wk'], g['bk'], g['Wg'], g['bg'], g['Wout'], g['bout'],
-                None, None, None, None, None)
+                None, None, None, None, None, None)
 
 
 def relation(X, boxes, Wq, bq, Wk, bk, Wg, bg, Wout, bout, key_index=None, M=None, group=16, residual_relu=False,
-             precision='fp32'):
-    """differentiable object-relation module; `precision` selects the forward kernels (gradients are always fp32)"""
-    return RelationFunction.apply(X, boxes, Wq, bq, Wk, bk, Wg, bg, Wout, bout, key_index, M, group, residual_relu, precision)
+             precision='fp32', grad_precision=None):
+    """differentiable object-relation module; `precision` selects the forward kernels, `grad_precision` the contraction
+    engine of the backward ('f16' = tcgen05 tf32 GEMM, the default on sm_100; 'fp32' = cuBLAS fp32); gradients are fp32"""
+    return RelationFunction.apply(X, boxes, Wq, bq, Wk, bk, Wg, bg, Wout, bout, key_index, M, group, residual_relu, precision,
+                                  grad_precision)
 
 
 class LearnNmsFunction(torch.autograd.Function):
@@ -43,7 +47,7 @@ class LearnNmsFunction(torch.autograd.Function):
         ctx.names, ctx.kw = names, kw
         multi, sbbox, sscore, _ = ops.learn_nms(cls_score, bbox_pred, rois, im_info, feat, dict(zip(names, weights)),
                                                 precision=kw.get('precision', 'fp32'),
-                                                **{k: v for k, v in kw.items() if k != 'precision'})
+                                                **{k: v for k, v in kw.items() if k not in ('precision', 'grad_precision')})
         ctx.mark_non_differentiable(sbbox, sscore)
         return multi, sbbox, sscore
 
@@ -51,18 +55,18 @@ class LearnNmsFunction(torch.autograd.Function):
     def backward(ctx, g_multi, _g_bbox, _g_score):
         cls_score, bbox_pred, rois, im_info, feat = ctx.saved_tensors[:5]
         weights = dict(zip(ctx.names, ctx.saved_tensors[5:]))
-        kw = {k: v for k, v in ctx.kw.items() if k != 'precision'}
+        kw = {k: v for k, v in ctx.kw.items() if k not in ('precision', 'grad_precision')}
         grads, d_cls, d_feat = ops.learn_nms_backward(g_multi.contiguous(), cls_score, bbox_pred, rois, im_info, feat,
-                                                      weights, **kw)
+                                                      weights, precision=ctx.kw.get('grad_precision'), **kw)
         return (d_cls, None, None, None, d_feat, None, None) + tuple(grads[n] for n in ctx.names)
 
 
 def learn_nms(cls_score, bbox_pred, rois, im_info, feat, weights, first_n=100, num_thresh=5, class_agnostic=True,
-              means=None, stds=None, nongt_dim=None, precision='fp32'):
+              means=None, stds=None, nongt_dim=None, precision='fp32', grad_precision=None):
     """differentiable learn-NMS head (train graph) -> (nms_multi_score, sorted_bbox, sorted_score)"""
     names = tuple(weights.keys())
     kw = dict(first_n=first_n, num_thresh=num_thresh, class_thresh=0.0, class_agnostic=class_agnostic, means=means,
-              stds=stds, nongt_dim=nongt_dim, precision=precision)
+              stds=stds, nongt_dim=nongt_dim, precision=precision, grad_precision=grad_precision)
     return LearnNmsFunction.apply(cls_score, bbox_pred, rois, im_info, feat, names, kw, *[weights[n] for n in names])
 
 

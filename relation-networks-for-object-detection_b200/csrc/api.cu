@@ -16,17 +16,27 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-static int g_sm_count = -1, g_cc_major = -1, g_cc_minor = -1;
+static int g_sm_count = -1, g_cc_major = -1, g_cc_minor = -1, g_bound_dev = -1;
 static std::once_flag g_dev_once;
 static void query_dev() {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) { g_sm_count = 0; g_cc_major = g_cc_minor = 0; cudaGetLastError(); return; }
+  g_bound_dev = dev;
   cudaDeviceProp p;
   if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) { g_sm_count = 0; g_cc_major = g_cc_minor = 0; cudaGetLastError(); return; }
   g_sm_count = p.multiProcessorCount; g_cc_major = p.major; g_cc_minor = p.minor;
 }
 int sm_count() { std::call_once(g_dev_once, query_dev); return g_sm_count; }
-bool is_sm100() { std::call_once(g_dev_once, query_dev); return g_cc_major == 10; }
+// one device per process (header: PROCESS MODEL): every cached property / launch attribute belongs to g_bound_dev
+static bool on_bound_device() {
+  int dev = -1;
+  if (g_bound_dev < 0 || cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return true; }
+  if (dev == g_bound_dev) return true;
+  set_error("librelnet_b200 is bound to device %d (first use) but device %d is current: one device per process", g_bound_dev, dev);
+  return false;
+}
+bool is_sm100() { std::call_once(g_dev_once, query_dev); return g_cc_major == 10 && on_bound_device(); }
+int check_bound_device() { std::call_once(g_dev_once, query_dev); return on_bound_device() ? RN_OK : RN_ERR_INVALID; }
 
 struct CublasTls {
   cublasHandle_t h = nullptr;
@@ -34,7 +44,9 @@ struct CublasTls {
 };
 static thread_local CublasTls g_cublas;
 
+int check_bound_device();
 static int get_cublas(cudaStream_t st, cublasHandle_t* out) {
+  if (check_bound_device()) return RN_ERR_INVALID;
   if (!g_cublas.h) {
     cublasStatus_t s = cublasCreate(&g_cublas.h);
     if (s != CUBLAS_STATUS_SUCCESS) { set_error("cublasCreate failed: %d", (int)s); g_cublas.h = nullptr; return RN_ERR_CUDA; }
@@ -49,6 +61,8 @@ static int get_cublas(cudaStream_t st, cublasHandle_t* out) {
 // row-major C[M,N] = A[M,K] . B[N,K]^T   <=> col-major C^T[N,M] = op_T(B as [K,N] ld ldb) . A^T ([K,M] ld lda)
 int sgemm_nt(cudaStream_t st, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
              int batch, long long sA, long long sB, long long sC) {
+  if (gemm_backend() == 1 && gemm_tf32_usable(A, lda, 0, sA, B, ldb, 0, sB))
+    return gemm_tf32(st, false, true, M, N, K, 1.f, A, lda, 0, sA, B, ldb, 0, sB, 0.f, C, ldc, 0, sC, 1, batch);
   cublasHandle_t h;
   int r = get_cublas(st, &h);
   if (r) return r;
@@ -66,6 +80,8 @@ int sgemm_nt(cudaStream_t st, int M, int N, int K, const float* A, int lda, cons
 // row-major C[M,N] = A[M,K] . B[K,N]   <=> col-major C^T[N,M] = B^T ([N,K] ld ldb, op N) . A^T ([K,M] ld lda, op N)
 int sgemm_nn(cudaStream_t st, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
              int batch, long long sA, long long sB, long long sC) {
+  if (gemm_backend() == 1 && gemm_tf32_usable(A, lda, 0, sA, B, ldb, 0, sB))
+    return gemm_tf32(st, false, false, M, N, K, 1.f, A, lda, 0, sA, B, ldb, 0, sB, 0.f, C, ldc, 0, sC, 1, batch);
   cublasHandle_t h;
   int r = get_cublas(st, &h);
   if (r) return r;
@@ -83,6 +99,8 @@ int sgemm_nn(cudaStream_t st, int M, int N, int K, const float* A, int lda, cons
 // general row-major C[M,N] = alpha * op(A) . op(B) + beta * C, optional strided batch
 int sgemm_rm(cudaStream_t st, bool transA, bool transB, int M, int N, int K, float alpha, const float* A, int lda,
              const float* B, int ldb, float beta, float* C, int ldc, int batch, long long sA, long long sB, long long sC) {
+  if (gemm_backend() == 1 && gemm_tf32_usable(A, lda, 0, sA, B, ldb, 0, sB))
+    return gemm_tf32(st, transA, transB, M, N, K, alpha, A, lda, 0, sA, B, ldb, 0, sB, beta, C, ldc, 0, sC, 1, batch);
   cublasHandle_t h;
   int r = get_cublas(st, &h);
   if (r) return r;
@@ -113,6 +131,8 @@ __global__ void fill_gemm_ptrs_kernel(const float* A, long long sAo, long long s
 int sgemm_rm_2level(cudaStream_t st, bool transA, bool transB, int M, int N, int K, float alpha, const float* A, int lda,
                     long long sAo, long long sAi, const float* B, int ldb, long long sBo, long long sBi, float beta, float* C,
                     int ldc, long long sCo, long long sCi, int outer, int inner, void* ptr_ws) {
+  if (gemm_backend() == 1 && gemm_tf32_usable(A, lda, sAo, sAi, B, ldb, sBo, sBi) && (long long)outer * inner <= 65535)
+    return gemm_tf32(st, transA, transB, M, N, K, alpha, A, lda, sAo, sAi, B, ldb, sBo, sBi, beta, C, ldc, sCo, sCi, outer, inner);
   if (outer == 1) return sgemm_rm(st, transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, inner, sAi, sBi, sCi);
   cublasHandle_t h;
   int r = get_cublas(st, &h);

@@ -70,4 +70,19 @@ int sgemm_rm_2level(cudaStream_t st, bool transA, bool transB, int M, int N, int
                     long long sAo, long long sAi, const float* B, int ldb, long long sBo, long long sBi, float beta, float* C,
                     int ldc, long long sCo, long long sCi, int outer, int inner, void* ptr_ws);
 
+// tcgen05 tf32 GEMM on fp32 operands (gemm_tf32.cu): same contract as sgemm_rm_2level (no pointer workspace needed)
+bool gemm_tf32_usable(const float* A, int lda, long long sAo, long long sAi, const float* B, int ldb, long long sBo, long long sBi);
+int gemm_tf32(cudaStream_t st, bool transA, bool transB, int M, int N, int K, float alpha, const float* A, int lda,
+              long long sAo, long long sAi, const float* B, int ldb, long long sBo, long long sBi, float beta, float* C,
+              int ldc, long long sCo, long long sCi, int outer, int inner);
+// backend of sgemm_nt / sgemm_nn / sgemm_rm / sgemm_rm_2level for the calling thread: 0 = cuBLAS fp32 (pedantic; the
+// bit-conservative parity mode), 1 = the repo's tcgen05 tf32 GEMM wherever its alignment rules hold (training side)
+int gemm_backend();
+void set_gemm_backend(int b);
+struct GemmBackendScope {
+  int prev;
+  explicit GemmBackendScope(int b) : prev(gemm_backend()) { set_gemm_backend(b); }
+  ~GemmBackendScope() { set_gemm_backend(prev); }
+};
+
 }  // namespace rn

@@ -9,8 +9,10 @@
 // sit in HBM as fp32 -- TMA loads them as they are, the tensor core reads the top 19 bits, no cast kernels, no packed
 // copies.  Both operand majors come straight from the row-major matrices:
 //   op(A) = A   (A stored [M,K]):  K-major tile, ONE TMA box [128 rows x 32 k] (SWIZZLE_128B rows of 32 floats)
-//   op(A) = A^T (A stored [K,M]):  MN-major tile, FOUR boxes [32 k rows x 32 m], each a column of 8x(32-float) atoms:
-//                                  descriptor LBO = 4096 (next 32 m), SBO = 1024 (next 8 k), +1024 B per K step of 8
+//   op(A) = A^T (A stored [K,M]):  MN-major tile, FOUR boxes [32 k rows x 32 m].  MN-major tf32 has exactly one legal
+//                                  shared-memory layout, SWIZZLE_128B with a 32-byte base (cute Layout_MN_SW128_32B_Atom,
+//                                  Swizzle<2,5,2>: atoms of 32 m x 4 k): TMA writes it with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+//                                  descriptor layout type 1, LBO = 4096 (next 32 m), SBO = 512 (next 4 k), +1024 B per K step of 8
 //   op(B): the same with N in place of M (B stored [N,K] = "transB" is the K-major case).
 // Out-of-range rows / columns / K are zero-filled by TMA (tensor-map extents are the true per-problem extents), so no
 // operand is ever padded in memory; the epilogue masks its stores.
@@ -42,6 +44,17 @@ struct Tf32Params {
   float alpha, beta;
   float* C; long long ldc, sCo, sCi;
 };
+
+// shared-memory descriptor of an MN-major tf32 operand: layout type 1 = SWIZZLE_128B_BASE32B (cute UMMA::LayoutType)
+__device__ __forceinline__ uint64_t make_smem_desc_sw128_base32(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;
+  return d;
+}
 
 // kind::tf32 instruction descriptor (cute InstrDescriptor): c_format F32, a/b_format 2 = TF32
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool a_mn, bool b_mn) {
@@ -118,16 +131,17 @@ __global__ void __launch_bounds__(192, 1) gemm_tf32_tc_kernel(const __grid_const
     if (lane == 0) {
       const uint32_t idesc = make_idesc_tf32(kTM, p.BN, p.a_mn != 0, p.b_mn != 0);
       const uint32_t stepA = p.a_mn ? 1024u : 32u, stepB = p.b_mn ? 1024u : 32u;        // bytes per K step of 8
-      const uint32_t lboA = p.a_mn ? 4096u : 16u, lboB = p.b_mn ? 4096u : 16u;
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % kTStages;
         mbar_wait(&full[s], (kb / kTStages) & 1);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + s * kTStage), sb = sa + kTA;
         const int ksteps = min(kTK, p.K - kb * kTK + 7) >> 3;          // whole K steps that hold at least one real k
-        for (int k = 0; k < ksteps; ++k)
-          mma_tf32_ss(tmem_base, make_smem_desc_sw128(sa + k * stepA, lboA, 1024), make_smem_desc_sw128(sb + k * stepB, lboB, 1024),
-                      idesc, (kb > 0) || (k > 0));
+        for (int k = 0; k < ksteps; ++k) {
+          const uint64_t da = p.a_mn ? make_smem_desc_sw128_base32(sa + k * stepA, 4096, 512) : make_smem_desc_sw128(sa + k * stepA, 16, 1024);
+          const uint64_t db = p.b_mn ? make_smem_desc_sw128_base32(sb + k * stepB, 4096, 512) : make_smem_desc_sw128(sb + k * stepB, 16, 1024);
+          mma_tf32_ss(tmem_base, da, db, idesc, (kb > 0) || (k > 0));
+        }
         mma_commit(&empty[s]);
       }
       mma_commit(tfull);
@@ -195,7 +209,7 @@ void load_encode32() {
 
 // matrix stored row-major [rows, cols] (pitch ld floats) per problem, problems at base + o*sO + i*sI; box = 32 cols x box_rows
 int encode_f32_4d(CUtensorMap* out, const float* base, int rows, int cols, long long ld, int inner, int outer, long long sI,
-                  long long sO, int box_rows) {
+                  long long sO, int box_rows, bool mn_major) {
   std::call_once(g_once32, load_encode32);
   if (!g_encode32) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return RN_ERR_CUDA; }
   const long long fallback = ld * (long long)rows;            // any valid stride for extent-1 dimensions
@@ -205,8 +219,8 @@ int encode_f32_4d(CUtensorMap* out, const float* base, int rows, int cols, long 
   cuuint32_t box[4] = {32, (cuuint32_t)box_rows, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = g_encode32(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("gemm_tf32: cuTensorMapEncodeTiled failed: %d (ptr=%p rows=%d cols=%d ld=%lld inner=%d outer=%d sI=%lld sO=%lld)", (int)r,
               (const void*)base, rows, cols, ld, inner, outer, sI, sO);
@@ -243,11 +257,11 @@ int gemm_tf32(cudaStream_t st, bool transA, bool transB, int M, int N, int K, fl
   p.C = C; p.ldc = ldc; p.sCo = sCo; p.sCi = sCi;
   CUtensorMap tmA, tmB;
   int r;
-  if (p.a_mn) r = encode_f32_4d(&tmA, A, K, M, lda, inner, outer, sAi, sAo, kTK);
-  else r = encode_f32_4d(&tmA, A, M, K, lda, inner, outer, sAi, sAo, kTM);
+  if (p.a_mn) r = encode_f32_4d(&tmA, A, K, M, lda, inner, outer, sAi, sAo, kTK, true);
+  else r = encode_f32_4d(&tmA, A, M, K, lda, inner, outer, sAi, sAo, kTM, false);
   if (r) return r;
-  if (p.b_mn) r = encode_f32_4d(&tmB, B, K, N, ldb, inner, outer, sBi, sBo, kTK);
-  else r = encode_f32_4d(&tmB, B, N, K, ldb, inner, outer, sBi, sBo, p.BN);
+  if (p.b_mn) r = encode_f32_4d(&tmB, B, K, N, ldb, inner, outer, sBi, sBo, kTK, true);
+  else r = encode_f32_4d(&tmB, B, N, K, ldb, inner, outer, sBi, sBo, p.BN, false);
   if (r) return r;
   static thread_local bool configured = false;
   if (!configured) {
@@ -267,9 +281,9 @@ void set_gemm_backend(int b) { g_backend = b; }
 }  // namespace rn
 
 // C ABI: exported so the contraction engine of the training side can be checked on its own (tests/test_gpu_backward.py)
-extern "C" int rn_gemm_tf32(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda, long long sAo,
-                            long long sAi, const float* B, int ldb, long long sBo, long long sBi, float beta, float* C, int ldc,
-                            long long sCo, long long sCi, int outer, int inner, rn_stream_t stream) {
+extern "C" int rn_gemm_tf32(int32_t transA, int32_t transB, int32_t M, int32_t N, int32_t K, float alpha, const float* A,
+                            int32_t lda, int64_t sAo, int64_t sAi, const float* B, int32_t ldb, int64_t sBo, int64_t sBi, float beta,
+                            float* C, int32_t ldc, int64_t sCo, int64_t sCi, int32_t outer, int32_t inner, rn_stream_t stream) {
   RN_CHECK_ARG(A && B && C && M >= 0 && N >= 0 && K >= 0, "rn_gemm_tf32: bad arguments");
   RN_CHECK_ARG(rn::is_sm100(), "rn_gemm_tf32: needs an sm_100 device");
   return rn::gemm_tf32((cudaStream_t)stream, transA != 0, transB != 0, M, N, K, alpha, A, lda, sAo, sAi, B, ldb, sBo, sBi, beta, C,

@@ -318,6 +318,8 @@ static int lnms_forward(const rn_learn_nms_desc* d, const float* cls_score, cons
   RN_CHECK_ARG(Rn >= n && Rn <= d->R, "rn_learn_nms_fwd: need first_n=%d <= non-gt rois=%d <= R=%d", n, Rn, d->R);
   RN_CHECK_ARG(Rn <= 8192, "rn_learn_nms_fwd: %d rois exceed the per-class sort capacity 8192", Rn);
   RN_CHECK_ARG(d->class_agnostic || K == C, "rn_learn_nms_fwd: class-specific boxes need num_reg_classes == num_classes");
+  // class-agnostic boxes: one foreground regressor (the reference's Reshape(0,0,0) at LNMS:331-333 only works for K == 1)
+  RN_CHECK_ARG(!d->class_agnostic || K == 1, "rn_learn_nms_fwd: class_agnostic needs num_reg_classes == 2 (got %d)", d->num_reg_classes);
   RN_CHECK_ARG(d->merge_method >= -2 && d->merge_method < T, "rn_learn_nms_fwd: unknown merge method %d", d->merge_method);
   cudaStream_t st = (cudaStream_t)stream;
   LnmsWs W;
@@ -450,6 +452,7 @@ extern "C" int rn_nms_multi_target_fwd(const float* bbox, const float* gt_boxes,
   RN_CHECK_ARG(bbox && score && out && n >= 1 && n <= 4096 && C >= 1 && G >= 0 && T >= 1 && T <= 16 && target_thresh_host,
                "rn_nms_multi_target_fwd: bad arguments (n <= 4096, T <= 16)");
   RN_CHECK_ARG(G == 0 || gt_boxes, "rn_nms_multi_target_fwd: null gt_boxes");
+  RN_CHECK_ARG(G <= 256, "rn_nms_multi_target_fwd: %d gt boxes exceed the per-class list capacity 256", G);
   ThreshSet th; th.T = T;
   for (int i = 0; i < T; ++i) th.v[i] = target_thresh_host[i];
   const size_t smem = (size_t)n * (8 + 4 + 4) + (size_t)n * T + 16;

@@ -216,7 +216,10 @@ extern "C" int rn_learn_nms_bwd(const rn_learn_nms_desc* desc, const float* cls_
                    g->nms_linear_out_1_bias && g->nms_logit_weight && g->nms_logit_bias,
                "rn_learn_nms_bwd: null gradient pointer");
   rn_learn_nms_desc d = *desc;
-  d.precision = RN_PREC_FP32;
+  // desc->precision selects the contraction engine of the whole backward (the recomputed forward included):
+  // RN_PREC_F16 = the repo's tcgen05 tf32 GEMM (gemm_tf32.cu), RN_PREC_FP32 = cuBLAS fp32 (pedantic) parity mode
+  GemmBackendScope backend(desc->precision == RN_PREC_F16 && is_sm100() ? 1 : 0);
+  d.precision = RN_PREC_FP32;          // kernel layout of the recomputed forward (materialised P, g): the general fp32 form
   const int C = d.num_classes - 1, n = d.first_n, T = d.num_thresh, R = d.R, NC = d.num_classes;
   const int Rn = lnms_selected_rows(&d, non_gt_index);
   cudaStream_t st = (cudaStream_t)stream;

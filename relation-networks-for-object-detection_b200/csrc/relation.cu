@@ -92,6 +92,15 @@ int relation_check_desc(const rn_relation_desc* d) {
                d->d);
   RN_CHECK_ARG(d->precision == RN_PREC_FP32 || d->precision == RN_PREC_F16, "rn_relation: unknown precision %d",
                d->precision);
+  RN_CHECK_ARG(d->dq >= d->H && d->dout >= d->H, "rn_relation: dq=%d / dout=%d must be at least H=%d", d->dq, d->dout, d->H);
+  // the geometry kernels evaluate E / 8 frequencies per coordinate (4 coordinates x sin, cos): a remainder would be dropped
+  RN_CHECK_ARG(d->E >= 8 && d->E % 8 == 0 && d->E <= 128, "rn_relation: E=%d unsupported (a multiple of 8 in 8..128)", d->E);
+  return RN_OK;
+}
+
+// without a key index the keys are the FIRST M rows of X / boxes (SYM_REL:106 slice_axis): M > N would read past them
+int relation_check_keys(const rn_relation_desc* d, const int* key_index) {
+  RN_CHECK_ARG(key_index || d->M <= d->N, "rn_relation: M=%d keys but only N=%d rows and no key_index", d->M, d->N);
   return RN_OK;
 }
 
@@ -196,6 +205,7 @@ extern "C" int rn_relation_fwd(const rn_relation_desc* d, const float* X, const 
                                void* ws, size_t ws_bytes, rn_stream_t stream) {
   int r = rn::relation_check_desc(d);
   if (r) return r;
+  if ((r = rn::relation_check_keys(d, key_index))) return r;
   RN_CHECK_ARG(X && boxes && Wq && bq && Wk && bk && Wg && bg && Wout && bout && out && ws,
                "rn_relation_fwd: null pointer argument");
   cudaStream_t st = (cudaStream_t)stream;
@@ -236,6 +246,7 @@ extern "C" int rn_relation_packed_fwd(const rn_relation_desc* d, const float* X,
                                       float* out, void* ws, size_t ws_bytes, rn_stream_t stream) {
   int r = rn::relation_check_desc(d);
   if (r) return r;
+  if ((r = rn::relation_check_keys(d, key_index))) return r;
   RN_CHECK_ARG(X && boxes && packed && Wg && bg && out && ws, "rn_relation_packed_fwd: null pointer argument");
   return rn::relation_tc_packed(d, X, boxes, key_index, packed, Wg, bg, out, ws, ws_bytes, (cudaStream_t)stream, 7, nullptr);
 }
@@ -247,6 +258,7 @@ extern "C" int rn_relation_packed_stages(const rn_relation_desc* d, const float*
                                          float* out, void* ws, size_t ws_bytes, int32_t stage_mask, rn_stream_t stream) {
   int r = rn::relation_check_desc(d);
   if (r) return r;
+  if ((r = rn::relation_check_keys(d, key_index))) return r;
   RN_CHECK_ARG(X && boxes && packed && Wg && bg && out && ws, "rn_relation_packed_stages: null pointer argument");
   return rn::relation_tc_packed(d, X, boxes, key_index, packed, Wg, bg, out, ws, ws_bytes, (cudaStream_t)stream,
                                 stage_mask, nullptr);
@@ -260,6 +272,7 @@ extern "C" int rn_relation_packed_fwd_f16io(const rn_relation_desc* d, const flo
                                             size_t ws_bytes, int32_t stage_mask, rn_stream_t stream) {
   int r = rn::relation_check_desc(d);
   if (r) return r;
+  if ((r = rn::relation_check_keys(d, key_index))) return r;
   RN_CHECK_ARG(X && boxes && packed && Wg && bg && out && ws, "rn_relation_packed_fwd_f16io: null pointer argument");
   return rn::relation_tc_packed(d, X, boxes, key_index, packed, Wg, bg, out, ws, ws_bytes, (cudaStream_t)stream,
                                 stage_mask, nullptr, X_f16, out_f16);

@@ -9,6 +9,7 @@ int launch_bias_act(cudaStream_t st, float* y, const float* bias, size_t rows, i
 // fp32 path (relation.cu) -- also the recomputation step of rn_relation_bwd (relation_bwd.cu)
 struct Fp32State { float *Q, *K, *Vp, *g, *S, *O, *Xk; void** ptrs; int ld; size_t used; };
 int relation_check_desc(const rn_relation_desc* d);
+int relation_check_keys(const rn_relation_desc* d, const int* key_index);
 size_t relation_fp32_ws_bytes(const rn_relation_desc* d);
 bool relation_fp32_carve(const rn_relation_desc* d, void* ws, size_t ws_bytes, Fp32State* fs);
 int relation_fp32(const rn_relation_desc* d, const float* X, const float* boxes, const int* key_index, const float* Wq,

@@ -1,4 +1,5 @@
-// relation_bwd.cu -- rn_relation_bwd: gradients of the object-relation module (fp32, library GEMMs + small kernels).
+// relation_bwd.cu -- rn_relation_bwd: gradients of the object-relation module.  Contractions: the repo's tcgen05 tf32 GEMM
+// (gemm_tf32.cu) under RN_PREC_F16, cuBLAS fp32 under RN_PREC_FP32 (parity mode); everything else small fp32 kernels.
 //
 // The reference has no hand-written backward for this path: MXNet differentiates the symbol graph of
 // attention_module_multi_head (resnet_v1_101_rcnn_attention_1024_pairwise_position_multi_head_16.py:104-151) op by op
@@ -287,10 +288,14 @@ extern "C" int rn_relation_bwd(const rn_relation_desc* d, const float* X, const 
                                float* dbout, void* ws, size_t ws_bytes, rn_stream_t stream) {
   int r = rn::relation_check_desc(d);
   if (r) return r;
+  if ((r = rn::relation_check_keys(d, key_index))) return r;
   RN_CHECK_ARG(X && boxes && Wq && bq && Wk && bk && Wg && bg && Wout && bout && dOut && ws,
                "rn_relation_bwd: null input pointer");
   RN_CHECK_ARG(dX && dWq && dbq && dWk && dbk && dWg && dbg && dWout && dbout, "rn_relation_bwd: null gradient pointer");
   RN_CHECK_ARG(d->E >= 8 && d->E % 8 == 0 && d->E <= 128, "rn_relation_bwd: E=%d unsupported (multiple of 8, <= 128)", d->E);
+  // d->precision selects the contraction engine of the backward (recomputed forward included): RN_PREC_F16 = the repo's
+  // tcgen05 tf32 GEMM (gemm_tf32.cu: fp32 operands read by TMA, kind::tf32, fp32 accumulate), RN_PREC_FP32 = cuBLAS fp32
+  rn::GemmBackendScope backend(d->precision == RN_PREC_F16 && rn::is_sm100() ? 1 : 0);
   return rn::relation_bwd(d, X, boxes, key_index, Wq, bq, Wk, bk, Wg, bg, Wout, bout, dOut, dX, dWq, dbq, dWk, dbk, dWg,
                           dbg, dWout, dbout, ws, ws_bytes, (cudaStream_t)stream);
 }

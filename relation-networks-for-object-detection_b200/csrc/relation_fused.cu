@@ -40,6 +40,10 @@ constexpr int kArriveA = 512;
 constexpr int kArriveA = 16;
 #endif
 constexpr int kStagePitch = 68;             // floats per row of the output staging tile (aliases the A buffers)
+// MC (multi-chunk heads, d_k = d_v = 64 c): a 2-stage ring of (Q chunk | K chunk) pairs replaces the Q tile + 2 K tiles, the A
+// stages shrink to one 16 KB tile each, and P / G sit next to each other so the staging tile can alias them
+constexpr int kMOffQK = 0, kMOffV = 65536, kMOffP = 98304, kMOffG = 131072, kMOffA = 163840, kMOffB = 196608, kMOffBar = 200704;
+static_assert(kMOffBar + 256 + 1024 <= kFSmem, "MC layout must fit the common allocation");
 
 // Measurement build only (tools/fused_trace.py compiles a private copy of the library with -DRN_FUSED_TRACE; the product
 // library has no trace code, no trace parameter and no trace symbol).
@@ -60,7 +64,8 @@ __device__ long long* g_fused_trace2 = nullptr;
 #endif
 
 struct FusedParams {
-  int B, N, M, H, dv;
+  int B, N, M, H, dv;                       // H = team size = (virtual) heads of 64 columns
+  int Hr, KC;                               // real heads (rows of Wg) and 64-column chunks per real head: H = Hr * KC
   int QT, T, R, Tr;                         // query tiles, key tiles, key ranges, key tiles per range
   int teams, ntasks;
   const float* boxes; const int* key_index;
@@ -70,7 +75,7 @@ struct FusedParams {
   float crad[8];                            // 100 ln2 / wave_length^(k/8):        log2(x) * crad[k] = angle in radians
   float scale_log2;                         // log2(e) / sqrt(dk)
   const float* X; int ldx; float* out; int ldo; __half* out16; int ldo16; int relu;
-  __half* gslots;                           // [teams][kFSlots][H producers][H consumers][128 queries][128/H keys]
+  __half* gslots;                           // [teams][kFSlots][H producers][Hr heads][128 queries][128/H keys]
   unsigned* counters;                       // [teams][32]: published[16] PER MEMBER (+16 spare) ; then tickets [B*QT*H]
   float* part_o; float* part_ml;            // [R][B][H][N][64], [R][B][H][N][2]
 };
@@ -127,24 +132,26 @@ __device__ __forceinline__ void tmem_ld_32x32b_x4f(uint32_t taddr, uint32_t (&v)
 // LO: also feed the fp16 residual of phi to the pair FC (A_lo.W_hi), i.e. phi at ~fp32 accuracy; without it phi is
 // rounded to fp16 (|err| <= 2.4e-4, the size of the reference's own float32 noise on the angles) and two key tiles share
 // one A stage (half the handshakes).  W is split hi/lo in both forms.
-template <bool LO>
+template <bool LO, bool MC>
 __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                       const __grid_constant__ CUtensorMap tmK,
                                                                       const __grid_constant__ CUtensorMap tmV,
                                                                       const FusedParams p) {
-  constexpr int TPS = LO ? 1 : 2;             // key tiles per A stage (a stage is 32 KB: hi + lo of one tile, or hi of two)
+  static_assert(!(LO && MC), "the phi-residual form is not built for multi-chunk heads");
+  constexpr int TPS = (LO || MC) ? 1 : 2;     // key tiles per A stage (a stage is 32 KB: hi + lo of one tile, or hi of two; MC: 16 KB)
   constexpr int NST = 8 / TPS;                // stages per round of 8 keys
+  constexpr int kAStage = MC ? 16384 : 32768;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
-  uint8_t* sQ = smem + kOffQ;
-  uint8_t* sK = smem + kOffK;               // 2 x 16 KB
-  uint8_t* sV = smem + kOffV;               // 2 x 16 KB
-  uint8_t* sP = smem + kOffP;               // 32 KB: two [128 x 64-key] halves
-  uint8_t* sA = smem + kOffA;               // 2 stages x 32 KB
-  uint8_t* sBh = smem + kOffB; uint8_t* sBl = sBh + 2048;       // one 32-row tile: rows 0..15 = W_hi, rows 16..31 = W_lo
-  uint8_t* sG = smem + kOffG;                 // this head's 128 x 128 fp16 g tile of the current block ([16-byte chunk][row])
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint8_t* sQ = smem + (MC ? kMOffQK : kOffQ);    // MC: ring of 2 x (Q chunk 16 KB | K chunk 16 KB)
+  uint8_t* sK = smem + kOffK;               // 2 x 16 KB (unused under MC)
+  uint8_t* sV = smem + (MC ? kMOffV : kOffV);     // 2 x 16 KB
+  uint8_t* sP = smem + (MC ? kMOffP : kOffP);     // 32 KB: two [128 x 64-key] halves
+  uint8_t* sA = smem + (MC ? kMOffA : kOffA);     // 2 stages x 32 KB (MC: 2 x 16 KB)
+  uint8_t* sBh = smem + (MC ? kMOffB : kOffB); uint8_t* sBl = sBh + 2048;       // one 32-row tile: rows 0..15 = W_hi, rows 16..31 = W_lo
+  uint8_t* sG = smem + (MC ? kMOffG : kOffG);     // this head's 128 x 128 fp16 g tile of the current block ([16-byte chunk][row])
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (MC ? kMOffBar : kOffBar));
   uint64_t* q_full = bars;                  // [1]
   uint64_t* k_full = bars + 1;              // [2]
   uint64_t* v_full = bars + 3;              // [2]
@@ -155,6 +162,7 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
   uint64_t* a_free = bars + 10;             // [2]
   uint64_t* g_full = bars + 12;
   uint64_t* g_free = bars + 13;
+  uint64_t* qk_free = bars + 16;            // [2] (MC: a ring stage has been consumed by its S UMMAs)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
   __shared__ float s_mx[4][128], s_sum[4][128];
   __shared__ float s_bias[16], s_rowabs[16];
@@ -164,7 +172,9 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int H = p.H, ks = 128 / H, rounds = ks >> 3;
+  const int HR = p.Hr;                      // real heads: rows of Wg, consumer dimension of the g ring
   const int team = blockIdx.x / H, h = blockIdx.x % H;
+  const int hc = MC ? h / p.KC : h;         // the real head whose geometry weight / softmax this member consumes
   RN_TRACE(0); RN_TRACE(1);
   // per-member progress counters (an aggregate count cannot express "EVERY member has ..."): member m has published
   // pub_ctr[m] blocks.  No "consumed" counter is needed: a member publishes block y only after it has read block y - 2, so
@@ -183,6 +193,7 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
         mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&a_full[i], kArriveA); mbar_init(&a_free[i], 1);
       }
       mbar_init(s_full, 1); mbar_init(p_full, 16); mbar_init(pv_full, 1); mbar_init(g_full, 1); mbar_init(g_free, 16);   // one arrival per compute WARP
+      mbar_init(&qk_free[0], 1); mbar_init(&qk_free[1], 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -194,8 +205,8 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
       uint32_t hi[4], lo[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float w0 = row < H ? p.Wg[row * 64 + chunk * 8 + 2 * j] : 0.f;
-        const float w1 = row < H ? p.Wg[row * 64 + chunk * 8 + 2 * j + 1] : 0.f;
+        const float w0 = row < HR ? p.Wg[row * 64 + chunk * 8 + 2 * j] : 0.f;
+        const float w1 = row < HR ? p.Wg[row * 64 + chunk * 8 + 2 * j + 1] : 0.f;
         split2_f(w0, w1, &hi[j], &lo[j]);
       }
       *reinterpret_cast<uint4*>(sBh + sw128_offset(row, chunk)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -204,12 +215,12 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
     // per-head bound sum|Wg[h,:]| + |bg[h]| (fixed summation order: every CTA gets the same bits)
     {
       float a = 0.f;
-      if (warp < H) a = fabsf(p.Wg[warp * 64 + lane]) + fabsf(p.Wg[warp * 64 + 32 + lane]);
+      if (warp < HR) a = fabsf(p.Wg[warp * 64 + lane]) + fabsf(p.Wg[warp * 64 + 32 + lane]);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
       if (lane == 0) {
-        s_rowabs[warp] = warp < H ? a + fabsf(p.bg[warp]) : 0.f;
-        s_bias[warp] = warp < H ? p.bg[warp] : 0.f;
+        s_rowabs[warp] = warp < HR ? a + fabsf(p.bg[warp]) : 0.f;
+        s_bias[warp] = warp < HR ? p.bg[warp] : 0.f;
       }
     }
   }
@@ -249,7 +260,7 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
             tc_fence_after();
 #pragma unroll
             for (int kk = 0; kk < TPS; ++kk) {
-              const uint32_t ah = smem_u32(sA + bf * 32768) + (LO ? 0 : kk * 16384);
+              const uint32_t ah = smem_u32(sA + bf * kAStage) + (TPS == 2 ? kk * 16384 : 0);
               const uint32_t d = tG + (st * TPS + kk) * 32;      // per key: columns 0..15 = A.W_hi, 16..31 = A.W_lo
 #pragma unroll
               for (int k = 0; k < 4; ++k)
@@ -277,47 +288,112 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
           mma_f16_ss(tS, make_smem_desc_sw128(aQ + k * 32, 16, 1024), make_smem_desc_sw128(aK + k * 32, 16, 1024), idesc_s, k > 0);
         mma_commit(s_full);
       };
-      for (int task = team; task < p.ntasks; task += p.teams, ++tc) {
-        const int rg = task % p.R, qt = (task / p.R) % p.QT, b = task / (p.R * p.QT);
-        const int kt0 = rg * p.Tr, nT = min(p.T, kt0 + p.Tr) - kt0;
-        const int q0 = qt * 128;
-        if (x >= 1) mbar_wait(pv_full, (x - 1) & 1);             // the previous task has drained (Q, K, V, P buffers free)
-        mbar_arrive_expect_tx(q_full, 16384);
-        tma_load_3d(sQ, &tmQ, q_full, h * 64, q0, b);
-        mbar_arrive_expect_tx(&k_full[x & 1], 16384);
-        tma_load_3d(sK + (x & 1) * 16384, &tmK, &k_full[x & 1], h * 64, kt0 * 128, b);
-        mbar_arrive_expect_tx(&v_full[x & 1], 16384);
-        tma_load_3d(sV + (x & 1) * 16384, &tmV, &v_full[x & 1], h * 64, kt0 * 128, b);
-        if (nT > 1) {
-          mbar_arrive_expect_tx(&k_full[(x + 1) & 1], 16384);
-          tma_load_3d(sK + ((x + 1) & 1) * 16384, &tmK, &k_full[(x + 1) & 1], h * 64, (kt0 + 1) * 128, b);
-        }
-        mbar_wait(q_full, tc & 1);
-        issue_s(x);
-#pragma unroll 1
-        for (int i = -2; i < nT; ++i) {
-          if (i + 2 < nT) geom_mma();                            // the compute warps evaluate phi of block i + 2 first ...
-          if (i >= 0) {
-            mbar_wait(p_full, x & 1);                            // ... then the softmax of block x: S and the previous PV are consumed
-            tc_fence_after();
-            if (i + 1 < nT) {
-              mbar_arrive_expect_tx(&v_full[(x + 1) & 1], 16384);
-              tma_load_3d(sV + ((x + 1) & 1) * 16384, &tmV, &v_full[(x + 1) & 1], h * 64, (kt0 + i + 1) * 128, b);
-            }
-            if (i + 2 < nT) {
-              mbar_arrive_expect_tx(&k_full[x & 1], 16384);
-              tma_load_3d(sK + (x & 1) * 16384, &tmK, &k_full[x & 1], h * 64, (kt0 + i + 2) * 128, b);
-            }
-            if (i + 1 < nT) issue_s(x + 1);
-            mbar_wait(&v_full[x & 1], (x >> 1) & 1);
-            tc_fence_after();
-            const uint32_t aV = smem_u32(sV + (x & 1) * 16384);
+      if constexpr (MC) {
+        // multi-chunk heads: S = sum_c Q_c K_c^T over the KC 64-column chunks of this member's real head, streamed through a
+        // 2-stage ring of (Q chunk | K chunk) pairs (Q chunks are re-read from L2 per block: 16 KB each); V' / P.V' as before
+        uint32_t gl = 0, gu = 0;                                   // ring chunks loaded / consumed so far (all tasks)
+        const int KC = p.KC, col0 = hc * KC * 64;
+        for (int task = team; task < p.ntasks; task += p.teams, ++tc) {
+          const int rg = task % p.R, qt = (task / p.R) % p.QT, b = task / (p.R * p.QT);
+          const int kt0 = rg * p.Tr, nT = min(p.T, kt0 + p.Tr) - kt0;
+          const int q0 = qt * 128;
+          const uint32_t total = (uint32_t)(nT * KC);
+          uint32_t tl = 0, tu = 0;                                 // this task's chunks loaded / consumed
+          if (x >= 1) mbar_wait(pv_full, (x - 1) & 1);             // the previous task has drained (V, P buffers free)
+          mbar_arrive_expect_tx(&v_full[x & 1], 16384);
+          tma_load_3d(sV + (x & 1) * 16384, &tmV, &v_full[x & 1], h * 64, kt0 * 128, b);
+          auto load_next = [&]() {
+            const uint32_t st = gl & 1;
+            if (gl >= 2) mbar_wait(&qk_free[st], ((gl >> 1) - 1) & 1);
+            const int blk = (int)tl / KC, c = (int)tl % KC;
+            mbar_arrive_expect_tx(&k_full[st], 32768);
+            tma_load_3d(sQ + st * 32768, &tmQ, &k_full[st], col0 + c * 64, q0, b);
+            tma_load_3d(sQ + st * 32768 + 16384, &tmK, &k_full[st], col0 + c * 64, (kt0 + blk) * 128, b);
+            ++gl; ++tl;
+          };
+          auto issue_s_mc = [&]() {
+            for (int c = 0; c < KC; ++c) {
+              while (tl < total && tl < tu + 2) load_next();
+              const uint32_t st = gu & 1;
+              mbar_wait(&k_full[st], (gu >> 1) & 1);
+              tc_fence_after();
+              const uint32_t aQc = smem_u32(sQ + st * 32768), aKc = aQc + 16384;
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-              mma_f16_ss(tPV, make_smem_desc_sw128(aP + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
-                         make_smem_desc_sw128(aV + k * 2048, 1024, 1024), idesc_o, k > 0);
-            mma_commit(pv_full);
-            ++x;
+              for (int k = 0; k < 4; ++k)
+                mma_f16_ss(tS, make_smem_desc_sw128(aQc + k * 32, 16, 1024), make_smem_desc_sw128(aKc + k * 32, 16, 1024), idesc_s,
+                           (c > 0) || (k > 0));
+              mma_commit(&qk_free[st]);
+              ++gu; ++tu;
+            }
+            mma_commit(s_full);
+          };
+          issue_s_mc();
+#pragma unroll 1
+          for (int i = -2; i < nT; ++i) {
+            if (i + 2 < nT) geom_mma();
+            if (i >= 0) {
+              mbar_wait(p_full, x & 1);
+              tc_fence_after();
+              if (i + 1 < nT) {
+                mbar_arrive_expect_tx(&v_full[(x + 1) & 1], 16384);
+                tma_load_3d(sV + ((x + 1) & 1) * 16384, &tmV, &v_full[(x + 1) & 1], h * 64, (kt0 + i + 1) * 128, b);
+              }
+              if (i + 1 < nT) issue_s_mc();
+              mbar_wait(&v_full[x & 1], (x >> 1) & 1);
+              tc_fence_after();
+              const uint32_t aV = smem_u32(sV + (x & 1) * 16384);
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                mma_f16_ss(tPV, make_smem_desc_sw128(aP + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                           make_smem_desc_sw128(aV + k * 2048, 1024, 1024), idesc_o, k > 0);
+              mma_commit(pv_full);
+              ++x;
+            }
+          }
+        }
+      } else {
+        for (int task = team; task < p.ntasks; task += p.teams, ++tc) {
+          const int rg = task % p.R, qt = (task / p.R) % p.QT, b = task / (p.R * p.QT);
+          const int kt0 = rg * p.Tr, nT = min(p.T, kt0 + p.Tr) - kt0;
+          const int q0 = qt * 128;
+          if (x >= 1) mbar_wait(pv_full, (x - 1) & 1);             // the previous task has drained (Q, K, V, P buffers free)
+          mbar_arrive_expect_tx(q_full, 16384);
+          tma_load_3d(sQ, &tmQ, q_full, h * 64, q0, b);
+          mbar_arrive_expect_tx(&k_full[x & 1], 16384);
+          tma_load_3d(sK + (x & 1) * 16384, &tmK, &k_full[x & 1], h * 64, kt0 * 128, b);
+          mbar_arrive_expect_tx(&v_full[x & 1], 16384);
+          tma_load_3d(sV + (x & 1) * 16384, &tmV, &v_full[x & 1], h * 64, kt0 * 128, b);
+          if (nT > 1) {
+            mbar_arrive_expect_tx(&k_full[(x + 1) & 1], 16384);
+            tma_load_3d(sK + ((x + 1) & 1) * 16384, &tmK, &k_full[(x + 1) & 1], h * 64, (kt0 + 1) * 128, b);
+          }
+          mbar_wait(q_full, tc & 1);
+          issue_s(x);
+#pragma unroll 1
+          for (int i = -2; i < nT; ++i) {
+            if (i + 2 < nT) geom_mma();                            // the compute warps evaluate phi of block i + 2 first ...
+            if (i >= 0) {
+              mbar_wait(p_full, x & 1);                            // ... then the softmax of block x: S and the previous PV are consumed
+              tc_fence_after();
+              if (i + 1 < nT) {
+                mbar_arrive_expect_tx(&v_full[(x + 1) & 1], 16384);
+                tma_load_3d(sV + ((x + 1) & 1) * 16384, &tmV, &v_full[(x + 1) & 1], h * 64, (kt0 + i + 1) * 128, b);
+              }
+              if (i + 2 < nT) {
+                mbar_arrive_expect_tx(&k_full[x & 1], 16384);
+                tma_load_3d(sK + (x & 1) * 16384, &tmK, &k_full[x & 1], h * 64, (kt0 + i + 2) * 128, b);
+              }
+              if (i + 1 < nT) issue_s(x + 1);
+              mbar_wait(&v_full[x & 1], (x >> 1) & 1);
+              tc_fence_after();
+              const uint32_t aV = smem_u32(sV + (x & 1) * 16384);
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                mma_f16_ss(tPV, make_smem_desc_sw128(aP + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                           make_smem_desc_sw128(aV + k * 2048, 1024, 1024), idesc_o, k > 0);
+              mma_commit(pv_full);
+              ++x;
+            }
           }
         }
       }
@@ -445,11 +521,11 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
           if (bi == 0 && st < 4) RN_T2(3 + 3 * st);
           if (u >= 2) mbar_wait(&a_free[bf], ((u >> 1) - 1) & 1);
           if (bi == 0 && st < 4) RN_T2(4 + 3 * st);
-          uint8_t* As = sA + bf * 32768;
+          uint8_t* As = sA + bf * kAStage;
           // row r of an A tile: [coord c][sin f0..7 | cos f0..7] -> chunk 2c = sins, chunk 2c+1 = coses
 #pragma unroll
           for (int kk = 0; kk < TPS; ++kk) {
-            uint8_t* Ah = As + (LO ? 0 : kk * 16384);
+            uint8_t* Ah = As + (TPS == 2 ? kk * 16384 : 0);
             *reinterpret_cast<uint4*>(Ah + a_off0) = make_uint4(wh[kk][0], wh[kk][1], wh[kk][2], wh[kk][3]);
             *reinterpret_cast<uint4*>(Ah + a_off1) = make_uint4(wh[kk][4], wh[kk][5], wh[kk][6], wh[kk][7]);
           }
@@ -472,7 +548,7 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
       // partial sums) -> g = max(x + b, 1e-6) * scale -> fp16 -> the team's ring slot
       auto readback_round = [&](int bi, int rd) {
         const uint32_t tb = tb_base + bi;
-        __half* slot = p.gslots + ((((size_t)team * kFSlots + (tb % kFSlots)) * H + h) * H) * (size_t)(128 * ks);
+        __half* slot = p.gslots + ((((size_t)team * kFSlots + (tb % kFSlots)) * H + h) * HR) * (size_t)(128 * ks);
         mbar_wait(g_full, rc & 1);
         tc_fence_after();
         float gsum[8][4];
@@ -497,7 +573,7 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int hh = 4 * j + q;
-          if (hh < H) {
+          if (hh < HR) {
             const float bb = s_bias[hh];
             uint32_t pk[4];
 #pragma unroll
@@ -535,11 +611,11 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
           }
           bar_compute();
           if (i == 0) RN_TRACE(6);                                // every teammate published block 0
-          const __half* slot = p.gslots + (((size_t)team * kFSlots + (tb % kFSlots)) * H) * (size_t)H * (128 * ks);
+          const __half* slot = p.gslots + (((size_t)team * kFSlots + (tb % kFSlots)) * H) * (size_t)HR * (128 * ks);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const int kk = j * 32 + 8 * c, pp = kk >> ks_shift, within = kk & (ks - 1);
-            const __half* src = slot + (((size_t)pp * H + h) * 128 + r) * ks + within;
+            const __half* src = slot + (((size_t)pp * HR + hc) * 128 + r) * ks + within;
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sG + ((j * 4 + c) * 128 + r) * 16)), "l"(src) : "memory");
           }
           asm volatile("cp.async.commit_group;" ::: "memory");
@@ -629,7 +705,8 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
       s_sum[j][r] = l_run;
       bar_compute();
       const float l_tot = (s_sum[0][r] + s_sum[1][r]) + (s_sum[2][r] + s_sum[3][r]);
-      float* stage = reinterpret_cast<float*>(sA);                // [128][kStagePitch]; the A buffers are idle here
+      // [128][kStagePitch]; the A buffers are idle here (MC: the adjacent P and G tiles, both owned by the compute warps)
+      float* stage = reinterpret_cast<float*>(MC ? sP : sA);
       {
         const float sc = p.R == 1 ? 1.f / l_tot : 1.f;
 #pragma unroll
@@ -675,10 +752,11 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
           }
 #pragma unroll
           for (int k = 0; k < 4; ++k) { acc[k] = make_float4(0.f, 0.f, 0.f, 0.f); Mx[k] = -INFINITY; Ls[k] = 0.f; }
-          for (int s0 = 0; s0 < p.R; s0 += 3) {
-            const int ns = min(3, p.R - s0);
+          constexpr int NB = MC ? 2 : 3;                          // 32 KB tile buffers available for the merge
+          for (int s0 = 0; s0 < p.R; s0 += NB) {
+            const int ns = min(NB, p.R - s0);
             for (int g = 0; g < ns; ++g) {
-              uint8_t* buf = g == 0 ? sA : (g == 1 ? sA + 32768 : sG);
+              uint8_t* buf = MC ? (g == 0 ? sA : sG) : (g == 0 ? sA : (g == 1 ? sA + 32768 : sG));
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const int it = tid + k * 512, row = it >> 4, c4 = it & 15;
@@ -691,7 +769,7 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             bar_compute();
             for (int g = 0; g < ns; ++g) {
-              const uint8_t* buf = g == 0 ? sA : (g == 1 ? sA + 32768 : sG);
+              const uint8_t* buf = MC ? (g == 0 ? sA : sG) : (g == 0 ? sA : (g == 1 ? sA + 32768 : sG));
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const int it = tid + k * 512, row = it >> 4;
@@ -705,7 +783,7 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
                 Mx[k] = mn;
               }
             }
-            if (s0 + 3 < p.R) bar_compute();                      // the tile buffers are refilled by the next group
+            if (s0 + NB < p.R) bar_compute();                     // the tile buffers are refilled by the next group
           }
         }
 #pragma unroll
@@ -776,6 +854,7 @@ namespace rn {
 // ------------------------------------------------------------------------------------------------------------ host
 struct FusedPlan { int teams, QT, T, R, Tr, ntasks; };
 
+// d: the module as the kernels see it (H = virtual heads of 64 columns, see relation_tc.cu:virtual_heads)
 static bool fused_plan(const rn_relation_desc* d, FusedPlan* pl) {
   const int H = d->H;
   if (d->E != 64 || H < 1 || H > 16 || (128 % H) != 0 || (128 / H) % 8 != 0) return false;
@@ -817,8 +896,9 @@ size_t relation_fused_ws_bytes(const rn_relation_desc* d) {
 
 int relation_fused_launch(const rn_relation_desc* d, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
                           const float* boxes, const int* key_index, const float* Wg, const float* bg, const float* X,
-                          float* out, void* out_f16, void* wsp, size_t ws_bytes, cudaStream_t st, bool phi_lo) {
+                          float* out, void* out_f16, void* wsp, size_t ws_bytes, cudaStream_t st, bool phi_lo, int chunks) {
   FusedPlan pl;
+  RN_CHECK_ARG(chunks >= 1 && d->H % chunks == 0 && !(phi_lo && chunks > 1), "relation_fused: bad head chunking %d for H=%d", chunks, d->H);
   RN_CHECK_ARG(fused_plan(d, &pl), "relation_fused: shape not covered (H=%d E=%d dq=%d dout=%d)", d->H, d->E, d->dq, d->dout);
   const int H = d->H, sms = sm_count() > 0 ? sm_count() : 148;
   const size_t teams_max = sms / H;
@@ -835,6 +915,7 @@ int relation_fused_launch(const rn_relation_desc* d, const CUtensorMap& tmQ, con
   RN_CUDA(cudaMemsetAsync(counters, 0, nctr * sizeof(unsigned), st));
   FusedParams p;
   p.B = d->batch; p.N = d->N; p.M = d->M; p.H = H; p.dv = d->dout / H;
+  p.Hr = H / chunks; p.KC = chunks;
   p.QT = pl.QT; p.T = pl.T; p.R = pl.R; p.Tr = pl.Tr; p.teams = pl.teams; p.ntasks = pl.ntasks;
   p.boxes = boxes; p.key_index = key_index; p.Wg = Wg; p.bg = bg;
   GeomFreq fr;
@@ -845,14 +926,15 @@ int relation_fused_launch(const rn_relation_desc* d, const CUtensorMap& tmQ, con
     p.crev[k] = (float)(100.0 * 0.6931471805599453 / (6.283185307179586 * (double)fr.dim[k]));
     p.crad[k] = (float)(100.0 * 0.6931471805599453 / (double)fr.dim[k]);
   }
-  p.scale_log2 = 1.4426950408889634f / sqrtf((float)(d->dq / H));
+  p.scale_log2 = 1.4426950408889634f / sqrtf((float)(d->dq / p.Hr));           // the REAL head width d_k
   p.X = d->fuse_residual_relu ? X : nullptr; p.ldx = d->d;
   p.out = out; p.ldo = d->dout; p.out16 = (__half*)out_f16; p.ldo16 = d->dout; p.relu = d->fuse_residual_relu;
   p.gslots = gslots; p.counters = counters; p.part_o = part_o; p.part_ml = part_ml;
   static thread_local bool configured = false;
   if (!configured) {
-    RN_CUDA(cudaFuncSetAttribute(relation_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmem));
-    RN_CUDA(cudaFuncSetAttribute(relation_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmem));
+    RN_CUDA(cudaFuncSetAttribute(relation_fused_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmem));
+    RN_CUDA(cudaFuncSetAttribute(relation_fused_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmem));
+    RN_CUDA(cudaFuncSetAttribute(relation_fused_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmem));
     configured = true;
   }
   cudaLaunchConfig_t cfg = {};
@@ -864,8 +946,9 @@ int relation_fused_launch(const rn_relation_desc* d, const CUtensorMap& tmQ, con
   at[0].id = cudaLaunchAttributeCooperative;          // all CTAs co-resident: team members wait for each other
   at[0].val.cooperative = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  if (phi_lo) RN_CUDA(cudaLaunchKernelEx(&cfg, relation_fused_kernel<true>, tmQ, tmK, tmV, p));
-  else RN_CUDA(cudaLaunchKernelEx(&cfg, relation_fused_kernel<false>, tmQ, tmK, tmV, p));
+  if (chunks > 1) RN_CUDA(cudaLaunchKernelEx(&cfg, relation_fused_kernel<false, true>, tmQ, tmK, tmV, p));
+  else if (phi_lo) RN_CUDA(cudaLaunchKernelEx(&cfg, relation_fused_kernel<true, false>, tmQ, tmK, tmV, p));
+  else RN_CUDA(cudaLaunchKernelEx(&cfg, relation_fused_kernel<false, false>, tmQ, tmK, tmV, p));
   return RN_OK;
 }
 

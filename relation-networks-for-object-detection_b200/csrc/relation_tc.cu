@@ -541,7 +541,7 @@ bool relation_fused_ok(const rn_relation_desc* d);
 size_t relation_fused_ws_bytes(const rn_relation_desc* d);
 int relation_fused_launch(const rn_relation_desc* d, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
                           const float* boxes, const int* key_index, const float* Wg, const float* bg, const float* X,
-                          float* out, void* out_f16, void* wsp, size_t ws_bytes, cudaStream_t st, bool phi_lo);
+                          float* out, void* out_f16, void* wsp, size_t ws_bytes, cudaStream_t st, bool phi_lo, int chunks);
 // RN_RELATION_UNFUSED=1 (or rn_relation_fused_enable(0)) keeps the round-1 decomposition (geometry kernel -> [B,H,N,M]
 // table -> tile attention + combine): the A/B arm of the measurements, not a fallback -- both are tcgen05 paths
 // g_fused_on: 0 = unfused, 1 = fused with phi rounded to fp16 (default), 2 = fused with the fp16 residual of phi as well
@@ -553,13 +553,34 @@ static int g_fused_on = [] {
 }();
 static bool use_fused(const rn_relation_desc* d) { return g_fused_on && relation_fused_ok(d); }
 
-static bool tc_shape_ok(const rn_relation_desc* d) {
-  return d->dq % d->H == 0 && d->dq / d->H <= 64 && d->dq / d->H >= 1 && d->dout % d->H == 0 && d->dout / d->H <= 64 &&
-         d->dout / d->H >= 1;
+// Heads wider than the kernels' native 64 columns (d_k = d_v = 64 c, c > 1: BASELINE.json configs[4] d = 1024, H = 4 has
+// d_k = 256) are run as H c VIRTUAL heads of 64: packing, the projection GEMM, the Q/K/V' layout and every tensor map are
+// exactly those of the (d, H c) module; only the fused kernel knows that c consecutive virtual heads share one geometry
+// weight and one softmax (it accumulates their c Q.K^T chunks into the same TMEM tile and each member keeps its own 64
+// columns of P.V').  Returns c (1 = native shape), 0 = not covered.
+static int head_chunks(const rn_relation_desc* d) {
+  if (d->H < 1 || d->dq % d->H || d->dout % d->H) return 0;
+  const int dk = d->dq / d->H, dv = d->dout / d->H;
+  if (dk < 1 || dv < 1) return 0;
+  if (dk <= 64 && dv <= 64) return 1;
+  if (dk != dv || dk % 64) return 0;
+  const int c = dk / 64, team = d->H * c;
+  if (team > 16 || 128 % team || (128 / team) % 8) return 0;
+  return c;
+}
+static bool tc_shape_ok(const rn_relation_desc* d) { return head_chunks(d) > 0; }
+// the (d, H c) module the kernels see
+static rn_relation_desc virtual_heads(const rn_relation_desc* d) {
+  rn_relation_desc v = *d;
+  const int c = head_chunks(d);
+  if (c > 1) v.H = d->H * c;
+  return v;
 }
 
-size_t relation_tc_workspace_bytes(const rn_relation_desc* d) {
-  if (!tc_shape_ok(d)) return 0;
+size_t relation_tc_workspace_bytes(const rn_relation_desc* d0) {
+  if (!tc_shape_ok(d0)) return 0;
+  const rn_relation_desc vd = virtual_heads(d0);
+  const rn_relation_desc* d = &vd;
   const size_t B = d->batch, N = d->N, M = d->M, H = d->H;
   const size_t d8 = align_up(d->d, 8), W3 = 3 * H * 64, ldg = align_up(M, 4);
   size_t t = 0;
@@ -587,16 +608,20 @@ __global__ void gather_rows_f16_kernel(const __half* __restrict__ X, const int* 
 int launch_geom_weight_log2(cudaStream_t st, const float* boxes, const int* key_index, int B, int N, int M, int H, int E,
                             float wave_length, const float* Wg, const float* bg, float* g, int ldg);
 
-size_t relation_tc_packed_bytes(const rn_relation_desc* d) {
-  if (!tc_shape_ok(d)) return 0;
+size_t relation_tc_packed_bytes(const rn_relation_desc* d0) {
+  if (!tc_shape_ok(d0)) return 0;
+  const rn_relation_desc vd = virtual_heads(d0);
+  const rn_relation_desc* d = &vd;
   const size_t d8 = align_up(d->d, 8), W3 = 3 * (size_t)d->H * 64;
   return ws_slice(W3 * d8, 2) + ws_slice(W3, 4);
 }
 
-int relation_tc_pack(const rn_relation_desc* d, const float* Wq, const float* bq, const float* Wk, const float* bk,
+int relation_tc_pack(const rn_relation_desc* d0, const float* Wq, const float* bq, const float* Wk, const float* bk,
                      const float* Wout, const float* bout, void* packed, cudaStream_t st) {
-  RN_CHECK_ARG(tc_shape_ok(d), "rn_relation_pack: shape not covered by the tcgen05 kernel (dq=%d dout=%d H=%d)", d->dq,
-               d->dout, d->H);
+  RN_CHECK_ARG(tc_shape_ok(d0), "rn_relation_pack: shape not covered by the tcgen05 kernel (dq=%d dout=%d H=%d)", d0->dq,
+               d0->dout, d0->H);
+  const rn_relation_desc vd = virtual_heads(d0);
+  const rn_relation_desc* d = &vd;
   const int D = d->d, H = d->H, dv = d->dout / H, d8 = (int)align_up(D, 8), W3 = 3 * H * 64;
   __half* w16 = (__half*)packed;
   float* bias = (float*)((char*)packed + ws_slice((size_t)W3 * d8, 2));
@@ -609,13 +634,16 @@ int relation_tc_pack(const rn_relation_desc* d, const float* Wq, const float* bq
   return RN_OK;
 }
 
-int relation_tc_packed(const rn_relation_desc* d, const float* X, const float* boxes, const int* key_index,
+int relation_tc_packed(const rn_relation_desc* d0, const float* X, const float* boxes, const int* key_index,
                        const void* packed, const float* Wg, const float* bg, float* out, void* wsp, size_t ws_bytes,
                        cudaStream_t st, int stage_mask, const GeomGather* gg, const void* x_f16, void* out_f16) {
   const bool do_proj = stage_mask & 1, do_geom = stage_mask & 2, do_attn = stage_mask & 4;
   RN_CHECK_ARG(is_sm100(), "RN_PREC_F16 needs an sm_100 device (tcgen05); use RN_PREC_FP32");
-  RN_CHECK_ARG(tc_shape_ok(d), "RN_PREC_F16 relation kernel supports dq/H <= 64 and dout/H <= 64 (got dq=%d dout=%d H=%d); "
-               "use RN_PREC_FP32 for this shape", d->dq, d->dout, d->H);
+  RN_CHECK_ARG(tc_shape_ok(d0), "RN_PREC_F16 relation kernel supports dq/H, dout/H <= 64, or dq/H = dout/H = 64 c with H c <= 16 "
+               "(got dq=%d dout=%d H=%d); use RN_PREC_FP32 for this shape", d0->dq, d0->dout, d0->H);
+  const int chunks = head_chunks(d0);
+  const rn_relation_desc vd = virtual_heads(d0);
+  const rn_relation_desc* d = &vd;
   const int B = d->batch, N = d->N, M = d->M, D = d->d, H = d->H, dv = d->dout / H;
   const int d8 = (int)align_up(D, 8), W3 = 3 * H * 64, ldg = (int)align_up(M, 4);
   const __half* w16 = (const __half*)packed;
@@ -626,6 +654,8 @@ int relation_tc_packed(const rn_relation_desc* d, const float* X, const float* b
   __half* qkv = ws.take<__half>((size_t)B * N * W3);
   __half* kv = ws.take<__half>((size_t)B * M * 2 * H * 64);
   const bool fused = !gg && use_fused(d);
+  RN_CHECK_ARG(chunks == 1 || fused, "rn_relation (F16): heads wider than 64 columns run on the fused kernel only (enable it; no "
+               "gathered-geometry form)");
   // the [B,H,N,M] table exists only in the unfused decomposition (gathered mode brings its own roi-level table)
   float* lg = (fused || gg) ? reinterpret_cast<float*>(kv) : ws.take<float>((size_t)B * H * N * ldg);
   const int T = cdiv(M, 128);
@@ -669,7 +699,8 @@ int relation_tc_packed(const rn_relation_desc* d, const float* X, const float* b
   if ((r = encode_tmap_3d_f16(&tmK, Kp, B, M, H * 64, ldk, bk_pitch, 128, 64))) return r;
   if ((r = encode_tmap_3d_f16(&tmV, Vp, B, M, H * 64, ldk, bk_pitch, 128, 64))) return r;
   if (fused)           // geometry + attention: one cooperative launch, nothing N x M in HBM
-    return relation_fused_launch(d, tmQ, tmK, tmV, boxes, key_index, Wg, bg, X, out, out_f16, gws, gws_bytes, st, g_fused_on == 2);
+    return relation_fused_launch(d, tmQ, tmK, tmV, boxes, key_index, Wg, bg, X, out, out_f16, gws, gws_bytes, st,
+                                 g_fused_on == 2 && chunks == 1, chunks);
   AttnParams p;
   p.N = N; p.M = M; p.H = H; p.T = T;
   p.lg = lg; p.ldg = ldg;

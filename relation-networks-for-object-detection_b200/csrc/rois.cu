@@ -22,7 +22,8 @@ __global__ void __launch_bounds__(256) roi_pool_fwd_kernel(const float* __restri
     const int c = (index / PW / PH) % C;
     const int n = index / PW / PH / C;
     const float* roi = rois + 5 * n;
-    const int b = (int)roi[0];
+    const int b = max((int)roi[0], 0);
+    const bool padded = (int)roi[0] < 0;           // MXNet: roi_batch_ind < 0 marks a padding roi -> zeros, argmax -1
     const int rsw = (int)roundf(roi[1] * spatial_scale), rsh = (int)roundf(roi[2] * spatial_scale);
     const int rew = (int)roundf(roi[3] * spatial_scale), reh = (int)roundf(roi[4] * spatial_scale);
     const int rh = max(reh - rsh + 1, 1), rw = max(rew - rsw + 1, 1);
@@ -31,7 +32,8 @@ __global__ void __launch_bounds__(256) roi_pool_fwd_kernel(const float* __restri
     int he = (int)ceilf((float)(ph + 1) * bh), we = (int)ceilf((float)(pw + 1) * bw);
     hs = min(max(hs + rsh, 0), H); he = min(max(he + rsh, 0), H);
     ws = min(max(ws + rsw, 0), W); we = min(max(we + rsw, 0), W);
-    const bool empty = (he <= hs) || (we <= ws);
+    const bool empty = padded || (he <= hs) || (we <= ws);
+    if (padded) { he = hs; we = ws; }
     float m = empty ? 0.f : -FLT_MAX;
     int mi = -1;
     const float* d = data + ((size_t)b * C + c) * H * W;
@@ -55,7 +57,8 @@ __global__ void __launch_bounds__(128) roi_pool_nhwc_f16_kernel(const float* __r
   const int bin = blockIdx.x, n = blockIdx.y;
   const int ph = bin / PW, pw = bin % PW;
   const float* roi = rois + 5 * n;
-  const int b = (int)roi[0];
+  const int b = max((int)roi[0], 0);
+  const bool padded = (int)roi[0] < 0;             // padding roi (MXNet semantics): zeros
   const int rsw = (int)roundf(roi[1] * spatial_scale), rsh = (int)roundf(roi[2] * spatial_scale);
   const int rew = (int)roundf(roi[3] * spatial_scale), reh = (int)roundf(roi[4] * spatial_scale);
   const int rh = max(reh - rsh + 1, 1), rw = max(rew - rsw + 1, 1);
@@ -64,7 +67,8 @@ __global__ void __launch_bounds__(128) roi_pool_nhwc_f16_kernel(const float* __r
   int he = (int)ceilf((float)(ph + 1) * bh), we = (int)ceilf((float)(pw + 1) * bw);
   hs = min(max(hs + rsh, 0), H); he = min(max(he + rsh, 0), H);
   ws = min(max(ws + rsw, 0), W); we = min(max(we + rsw, 0), W);
-  const bool empty = (he <= hs) || (we <= ws);
+  const bool empty = padded || (he <= hs) || (we <= ws);
+  if (padded) { he = hs; we = ws; }
   const float* d = data + (size_t)b * H * W * C;
   for (int c = threadIdx.x * 2; c < C; c += blockDim.x * 2) {
     float m0 = empty ? 0.f : -FLT_MAX, m1 = m0;
@@ -88,13 +92,15 @@ __global__ void __launch_bounds__(128) roi_pool_nhwc_bf16in_f16_kernel(const __n
   const int ph = blockIdx.x, n = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* roi = rois + 5 * n;
-  const int b = (int)roi[0];
+  const int b = max((int)roi[0], 0);
+  const bool padded = (int)roi[0] < 0;             // padding roi (MXNet semantics): zeros
   const int rsw = (int)roundf(roi[1] * spatial_scale), rsh = (int)roundf(roi[2] * spatial_scale);
   const int rew = (int)roundf(roi[3] * spatial_scale), reh = (int)roundf(roi[4] * spatial_scale);
   const int rh = max(reh - rsh + 1, 1), rw = max(rew - rsw + 1, 1);
   const float bh = (float)rh / (float)PH, bw = (float)rw / (float)PW;
   int hs = (int)floorf((float)ph * bh), he = (int)ceilf((float)(ph + 1) * bh);
   hs = min(max(hs + rsh, 0), H); he = min(max(he + rsh, 0), H);
+  if (padded) he = hs;
   const __nv_bfloat16* d = data + (size_t)b * H * W * C;
   for (int pw = warp; pw < PW; pw += 4) {
     int ws = (int)floorf((float)pw * bw), we = (int)ceilf((float)(pw + 1) * bw);
@@ -128,7 +134,7 @@ __global__ void __launch_bounds__(128) roi_pool_nhwc_bf16in_f16_kernel(const __n
 // to the argmax element the forward recorded.  Scatter form (one thread per pooled cell, red.global.add) instead of the
 // reference's gather-over-all-rois form: work is R*C*PH*PW instead of B*C*H*W*R.
 __global__ void __launch_bounds__(256) roi_pool_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ argmax,
-                                                           const float* __restrict__ rois, size_t count, int C, int H,
+                                                           const float* __restrict__ rois, size_t count, int B, int C, int H,
                                                            int W, int PHW, float* __restrict__ ddata) {
   for (size_t index = (size_t)blockIdx.x * blockDim.x + threadIdx.x; index < count;
        index += (size_t)gridDim.x * blockDim.x) {
@@ -137,6 +143,7 @@ __global__ void __launch_bounds__(256) roi_pool_bwd_kernel(const float* __restri
     const int c = (index / PHW) % C;
     const int n = index / PHW / C;
     const int b = (int)rois[5 * n];
+    if (b < 0 || b >= B) continue;                 // padding roi / index outside the gradient buffer
     atomicAdd(ddata + ((size_t)b * C + c) * H * W + a, dout[index]);
   }
 }
@@ -182,7 +189,7 @@ extern "C" int rn_roi_pool_bwd(const float* dout, const int32_t* argmax, const f
   if (R == 0) return RN_OK;
   RN_CHECK_ARG(dout && argmax && rois, "rn_roi_pool_bwd: null pointer");
   size_t count = (size_t)R * C * PH * PW;
-  rn::roi_pool_bwd_kernel<<<rn::grid_for(count), 256, 0, st>>>(dout, argmax, rois, count, C, H, W, PH * PW, ddata);
+  rn::roi_pool_bwd_kernel<<<rn::grid_for(count), 256, 0, st>>>(dout, argmax, rois, count, B, C, H, W, PH * PW, ddata);
   RN_LAUNCH_CHECK();
   return RN_OK;
 }

@@ -191,9 +191,11 @@ def _grad_buffers(out, like):
 
 
 def relation_backward(grad_out, X, boxes, Wq, bq, Wk, bk, Wg, bg, Wout, bout, key_index=None, M=None, group=16,
-                      residual_relu=False, wave_length=1000.0, out=None):
-    """Gradients of `relation` (fp32; forward intermediates are recomputed) -- rn_relation_bwd.
+                      residual_relu=False, wave_length=1000.0, out=None, precision=None):
+    """Gradients of `relation` (forward intermediates are recomputed) -- rn_relation_bwd.  precision: 'f16' (default on
+    sm_100) = every contraction on the library's tcgen05 tf32 GEMM (fp32 operands, fp32 accumulate); 'fp32' = cuBLAS fp32.
     Returns a dict with the gradient of X and of every parameter, shaped like the argument it belongs to."""
+    precision = precision or default_precision()
     X = _f32(X, 'X'); boxes = _f32(boxes, 'boxes'); grad_out = _f32(grad_out, 'grad_out')
     batched = X.dim() == 3
     B = X.shape[0] if batched else 1
@@ -214,7 +216,7 @@ def relation_backward(grad_out, X, boxes, Wq, bq, Wk, bk, Wg, bg, Wout, bout, ke
         kidx = key_index.to(device=X.device, dtype=torch.int32).contiguous()
         M = kidx.numel()
     M = int(M) if M is not None else N
-    desc = L.RelationDesc(B, N, M, d, dq, dout, group, Wg.shape[1], wave_length, int(residual_relu), PREC['fp32'])
+    desc = L.RelationDesc(B, N, M, d, dq, dout, group, Wg.shape[1], wave_length, int(residual_relu), PREC[precision])
     g = _grad_buffers(out, {'X': X, 'Wq': Wq, 'bq': bq, 'Wk': Wk, 'bk': bk, 'Wg': Wg, 'bg': bg, 'Wout': Wout, 'bout': bout})
     lib = L.lib()
     ws = _workspace(lib.rn_relation_bwd_workspace_bytes(C.byref(desc)), X.device)
@@ -231,10 +233,18 @@ def relation_workspace_bytes(N, M, d, dq, dout, group, batch=1, E=64, precision=
 
 
 def relation_tc_supported(dq, dout, group, return_softmax=False):
-    """Shapes the tcgen05 relation kernels cover (relation_tc.cu:tc_shape_ok): d_k <= 64 and d_v <= 64 per head (narrower
-    heads are zero-padded to 64 columns at pack time)."""
-    return (dq % group == 0 and 1 <= dq // group <= 64 and dout % group == 0 and 1 <= dout // group <= 64
-            and not return_softmax)
+    """Shapes the tcgen05 relation kernels cover (relation_tc.cu:head_chunks): d_k <= 64 and d_v <= 64 per head (narrower
+    heads are zero-padded to 64 columns at pack time), or d_k = d_v = 64 c run as `group * c` <= 16 virtual heads of 64 columns
+    that share their head's geometry weight and softmax (fused kernel only)."""
+    if return_softmax or dq % group or dout % group or dq < group or dout < group:
+        return False
+    dk, dv = dq // group, dout // group
+    if dk <= 64 and dv <= 64:
+        return True
+    if dk != dv or dk % 64:
+        return False
+    team = group * (dk // 64)
+    return team <= 16 and 128 % team == 0 and (128 // team) % 8 == 0 and bool(relation_fused_active())
 
 
 def relation_fused_active():
@@ -405,16 +415,18 @@ def learn_nms(cls_score, bbox_pred, rois, im_info, feat, weights, first_n=100, n
 
 def learn_nms_backward(grad_multi, cls_score, bbox_pred, rois, im_info, feat, weights, first_n=100, num_thresh=5,
                        class_thresh=0.0, class_agnostic=True, means=None, stds=None, nongt_dim=None, non_gt_index=None,
-                       out=None):
-    """Gradients of nms_multi_score (train graph SYM_REL_NMS:424-501) -- rn_learn_nms_bwd.  Returns (dict of the 14 weight
+                       out=None, precision=None):
+    """Gradients of nms_multi_score (train graph SYM_REL_NMS:424-501) -- rn_learn_nms_bwd.  precision as in
+    relation_backward (contraction engine: tcgen05 tf32 GEMM / cuBLAS fp32).  Returns (dict of the 14 weight
     gradients by checkpoint name, d_cls_score [R,num_classes], d_feat [R,feat_dim])."""
+    precision = precision or default_precision()
     cls_score = _f32(cls_score, 'cls_score'); bbox_pred = _f32(bbox_pred, 'bbox_pred'); rois = _f32(rois, 'rois')
     im_info = _f32(im_info, 'im_info').reshape(-1); feat = _f32(feat, 'feat'); grad_multi = _f32(grad_multi, 'grad_multi')
     NC = cls_score.shape[1]
     if tuple(grad_multi.shape) != (first_n, NC - 1, num_thresh):
         raise L.RelnetError('learn_nms_backward: grad_multi shape %s != %s' % (tuple(grad_multi.shape), (first_n, NC - 1, num_thresh)))
     desc, kidx = _learn_nms_desc(cls_score, bbox_pred, rois, feat, first_n, num_thresh, class_thresh, class_agnostic, means,
-                                 stds, nongt_dim, non_gt_index, -1, 'fp32')
+                                 stds, nongt_dim, non_gt_index, -1, precision)
     keep = [_f32(weights[n], n) for n in L.LearnNmsWeights.NAMES]
     w = L.LearnNmsWeights(*[t.data_ptr() for t in keep])
     grads = _grad_buffers(out, dict(zip(L.LearnNmsWeights.NAMES, keep)))
@@ -789,6 +801,36 @@ def maxpool3x3s2_nhwc(x):
     out = torch.empty((1, Ho, Wo, Cc), dtype=torch.bfloat16, device=x.device)
     L.check(L.lib().rn_maxpool3x3s2_nhwc_bf16(_ptr(x), H, W, Cc, _ptr(out), _stream()), 'rn_maxpool3x3s2_nhwc_bf16')
     return out.permute(0, 3, 1, 2)
+
+
+def gemm_tf32(A, B, transA=False, transB=False, alpha=1.0, beta=0.0, out=None):
+    """C = alpha * op(A) . op(B) + beta * C on the tcgen05 tf32 GEMM (rn_gemm_tf32).  A, B: fp32 CUDA tensors, 2-D or batched
+    [..., rows, cols] with up to two leading batch dimensions (outer, inner); any strides the C ABI accepts."""
+    for t, n in ((A, 'A'), (B, 'B')):          # strided views are the point: no .contiguous() here
+        if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != torch.float32:
+            raise L.RelnetError('%s must be a float32 CUDA tensor (relnet_b200 has no CPU path)' % n)
+    def norm(t):
+        while t.dim() < 4:
+            t = t.unsqueeze(0)
+        return t
+    A4, B4 = norm(A), norm(B)
+    outer, inner = A4.shape[0], A4.shape[1]
+    M = A4.shape[3] if transA else A4.shape[2]
+    K = A4.shape[2] if transA else A4.shape[3]
+    N = B4.shape[2] if transB else B4.shape[3]
+    if out is None:
+        out = torch.zeros((outer, inner, M, N), dtype=torch.float32, device=A.device)
+        ret = out.reshape(A.shape[:-2] + (M, N))
+    else:
+        ret = out
+        out = norm(out)
+    for t in (A4, B4, out):
+        if t.stride(3) != 1:
+            raise L.RelnetError('gemm_tf32: innermost dimension must be contiguous')
+    L.check(L.lib().rn_gemm_tf32(int(transA), int(transB), M, N, K, float(alpha), _ptr(A4), A4.stride(2), A4.stride(0), A4.stride(1),
+                                 _ptr(B4), B4.stride(2), B4.stride(0), B4.stride(1), float(beta), _ptr(out), out.stride(2),
+                                 out.stride(0), out.stride(1), outer, inner, _stream()), 'rn_gemm_tf32')
+    return ret
 
 
 def umma_selftest(a, b, p, v):

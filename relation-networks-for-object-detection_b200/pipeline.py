@@ -262,8 +262,8 @@ class Detector(object):
     the whole `proposal` chain (decode, sort, NMS: mostly one-SM latency-bound kernels) run beside res5 + conv_new_1
     (SYM_REL_NMS:271-332: both only read conv4).  Captured by GraphedStep the fork/join becomes graph edges."""
 
-    def __init__(self, trunk, head, im_info):
-        self.trunk, self.head, self.im_info = trunk, head, im_info
+    def __init__(self, trunk, head, im_info, dcn=False):
+        self.trunk, self.head, self.im_info, self.dcn = trunk, head, im_info, dcn
         # the side branch is a chain of small latency-bound kernels: high priority so its CTAs are placed as soon as res5's
         # big grids retire blocks, instead of queueing behind them
         self.side = torch.cuda.Stream(priority=-1)
@@ -279,10 +279,29 @@ class Detector(object):
             rois_ready.record(self.side)
             done = self.head.geometry_early(rois)          # both modules' geometry terms: beside res5 / ROI pool / fc_new_1
         c4.record_stream(self.side)
-        feat = self.trunk.c5feat(c4, keep_dtype=self.head.precision == 'f16')     # f16 head pools straight from bf16
+        if self.dcn:      # configs[2]: res5 with our deformable convs (channels-last sampler + tcgen05 GEMM), bf16 NHWC map out
+            feat = self.trunk.c5feat_dcn(c4)
+            if self.head.precision != 'f16':
+                feat = feat.float()
+        else:
+            feat = self.trunk.c5feat(c4, keep_dtype=self.head.precision == 'f16')     # f16 head pools straight from bf16
         main.wait_event(rois_ready)                        # ROI pool + fc_new_1 only need the rois ...
         rois.record_stream(main)
         return self.head.detect(rois, feat, self.im_info, geometry_done=done, join=self.side)   # ... relation #1 the geometry
+
+
+class FPNDetector(object):
+    """BASELINE.json configs[3] at test time for one image: FPN trunk (library) -> four 256-channel maps -> FPNRelationHead
+    on rois that arrive already dispatched to the pyramid levels (the reference reads them from a proposal pickle through
+    ROIIter, SURVEY.md section 3: no proposal op in this graph)."""
+
+    def __init__(self, trunk, head, im_info, rois):
+        self.trunk, self.head, self.im_info = trunk, head, im_info
+        self.rois_sorted, self.counts = head.split_rois(rois)
+
+    def __call__(self, image32):
+        feats = self.trunk(image32)
+        return self.head.detect(self.rois_sorted, self.counts, feats, self.im_info)
 
 
 class GraphedStep(object):

@@ -111,6 +111,77 @@ class TrainStep(object):
         return ev
 
 
+class FPNTrainStep(TrainStep):
+    """BASELINE.json configs[3] as a training step (train_rcnn.py -> get_symbol_rcnn, SYM_FPN_REL_NMS:979-1233): FPN trunk with
+    autograd (library; conv1 / res2 frozen), rois GIVEN (the reference reads them from a proposal pickle through ROIIter and
+    samples / labels them on the host, core/rcnn.py:153-223 -- here: `num_rois` seeded synthetic boxes labelled on the device by
+    rn_proposal_target, which appends the gt boxes: N = num_rois + G rows, keys = the num_rois non-gt rows), ROIPooling per
+    pyramid level (strides 4..32) through the C-ABI fwd/bwd pair, roi_pool_fc1/2 + two relation modules (C-ABI fwd/bwd),
+    cls / bbox losses, learn-NMS with first_n = 150 (C-ABI fwd/bwd) and its loss.  `micro_batches` images per rank accumulate
+    into the same bucket before the ONE allreduce (the reference's 2 images per GPU: batch 16 on 8 GPUs)."""
+
+    STRIDES = (4, 8, 16, 32)
+
+    def __init__(self, trunk, device, num_rois=1000, num_gt=8, micro_batches=2, seed=0, lr=0.0, first_n=150, canvas=(1024.0, 608.0)):
+        super().__init__(trunk, device, num_gt=num_gt, micro_batches=micro_batches, seed=seed, lr=lr, nongt_dim=num_rois,
+                         first_n=first_n)
+        import numpy as np
+        rng = np.random.default_rng(seed + 5)
+        W, H = canvas
+        sz = np.exp(rng.uniform(np.log(16.0), np.log(0.95 * min(W, H)), num_rois))
+        ar = np.exp(rng.uniform(np.log(0.5), np.log(2.0), num_rois))
+        w = np.minimum(sz * np.sqrt(ar), W - 2); h = np.minimum(sz / np.sqrt(ar), H - 2)
+        x1 = rng.uniform(0, 1, num_rois) * (W - 1 - w); y1 = rng.uniform(0, 1, num_rois) * (H - 1 - h)
+        self.rois_in = torch.tensor(np.stack([np.zeros(num_rois), x1, y1, x1 + w, y1 + h], 1), dtype=torch.float32, device=device)
+
+    def forward_backward(self, image32, im_info):
+        from .pipeline import fpn_level
+        from .trunk import plain_ops
+        P, t = self.head, self.trunk
+        with plain_ops(), torch.autocast('cuda', dtype=torch.bfloat16):
+            with torch.no_grad():                                    # frozen prefix (FIXED_PARAMS)
+                x = image32.contiguous(memory_format=torch.channels_last)
+                c2 = t.res2(F.max_pool2d(F.relu(t.conv1(x)), 3, 2, padding=1))
+            c3 = t.res3(c2); c4 = t.res4(c3); c5 = t.res5(c4)
+            p = t.lat[3](c5)
+            feats = [None, None, None, t.smooth[3](p)]
+            for l, c in ((2, c4), (1, c3), (0, c2)):
+                p = t.lat[l](c) + F.interpolate(p, size=c.shape[-2:], mode='nearest')
+                feats[l] = t.smooth[l](p)
+        with torch.no_grad():
+            rois, label, bbox_target, bbox_weight = ops.proposal_target(self.rois_in, self.gt)     # appends the gt rows
+            boxes = rois[:, 1:].contiguous()
+            lvl = fpn_level(rois)
+            idx = [torch.nonzero(lvl == l).flatten() for l in range(4)]
+            inv = torch.argsort(torch.cat(idx))
+        parts = [AG.roi_pool(feats[l].float().contiguous(), rois[idx[l]].contiguous(), (7, 7), 1.0 / self.STRIDES[l])
+                 for l in range(4) if idx[l].numel()]                                             # SYM_FPN_REL_NMS:1108-1115
+        pooled = torch.cat(parts, 0)[inv]
+        with torch.autocast('cuda', dtype=torch.bfloat16):
+            fc1 = F.linear(pooled.flatten(1), P['fc_new_1_weight'], P['fc_new_1_bias']).float()   # roi_pool_fc1 :1130
+        rel = lambda x, i: AG.relation(x, boxes, P['query_%d_weight' % i], P['query_%d_bias' % i], P['key_%d_weight' % i],
+                                       P['key_%d_bias' % i], P['pair_pos_fc1_%d_weight' % i], P['pair_pos_fc1_%d_bias' % i],
+                                       P['linear_out_%d_weight' % i], P['linear_out_%d_bias' % i], M=self.nongt_dim, group=16,
+                                       residual_relu=True, precision='fp32')
+        a1 = rel(fc1, 1)                                                                          # :1122-1133
+        with torch.autocast('cuda', dtype=torch.bfloat16):
+            fc2 = F.linear(a1, P['fc_new_2_weight'], P['fc_new_2_bias']).float()                  # roi_pool_fc2 :1138
+        a2 = rel(fc2, 2)                                                                          # :1134-1141
+        cls_score = F.linear(a2, P['cls_score_weight'], P['cls_score_bias'])
+        bbox_pred = F.linear(a2, P['bbox_pred_weight'], P['bbox_pred_bias'])
+        cls_loss = F.cross_entropy(cls_score, label.long())
+        bbox_loss = (F.smooth_l1_loss(bbox_pred, bbox_target, reduction='none', beta=1.0) * bbox_weight).sum() / rois.shape[0]
+        multi, sbbox, sscore = AG.learn_nms(cls_score, bbox_pred, rois, im_info, a2, {k: P[k] for k in NMS_NAMES},
+                                            first_n=self.first_n, means=(0, 0, 0, 0), stds=(0.1, 0.1, 0.2, 0.2),
+                                            nongt_dim=self.nongt_dim)
+        with torch.no_grad():
+            target = ops.nms_multi_target(sbbox, self.gt, sscore, [0.5, 0.6, 0.7, 0.8, 0.9])
+            pos, neg, d_multi = ops.nms_loss(multi.detach(), target)
+        torch.autograd.backward([cls_loss + bbox_loss, multi], [None, d_multi])
+        self.last = dict(cls=float(cls_loss), bbox=float(bbox_loss), nms=float(pos.sum() + neg.sum()), rois=int(rois.shape[0]),
+                         per_level=[int(i.numel()) for i in idx])
+
+
 def bus_gbs(nbytes, ms, world):
     """NCCL bus bandwidth of an allreduce: algorithmic bytes x 2 (n-1)/n / time"""
     if world <= 1 or ms <= 0:

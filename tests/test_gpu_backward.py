@@ -31,12 +31,60 @@ def autograd_grads(c, dOut, dtype, **kw):
     return {k: t[k].grad.numpy() for k in NAMES}, out.detach().numpy()
 
 
+# Contraction engines of the backward (ops.relation_backward(precision=...)): 'fp32' = cuBLAS fp32 (parity mode, held to 2e-3
+# of float32 autograd, measured 2e-7..4e-5); 'f16' = the library's tcgen05 tf32 GEMM on the fp32 operands (10-bit mantissa
+# operands, fp32 accumulate: per-tensor tolerance 5e-3, written here; the recomputed forward runs on it too).
+GRAD_TOL = {'fp32': 2e-3, 'f16': 5e-3}
+ZERO_TOL = {'fp32': 1e-4, 'f16': 3e-3}       # gradients that are exactly zero in exact arithmetic, relative to a sibling's scale
+
+
+def grad_precisions(ops):
+    return ['fp32', 'f16'] if ops.device_info()['sm100'] else ['fp32']
+
+
+@pytest.mark.parametrize('tA,tB,M,N,K,outer,inner', [
+    (False, True, 300, 1024, 1024, 1, 1),     # dX = dQ Wq^T-like (both K-major)
+    (True, False, 1024, 1024, 300, 1, 1),     # dW = dQ^T X (both MN-major), K tail 300 = 9 x 32 + 12
+    (False, False, 300, 64, 300, 1, 16),      # dQ_h = dS_h K_h, heads as the inner batch of column slices
+    (True, False, 300, 64, 300, 2, 16),       # dV'_h = P_h^T dO_h, two-level batch
+    (False, True, 100, 100, 8, 80, 16),       # learn-NMS dP = dO V'^T with d_v = 8: 1280 problems, K = 8
+    (True, False, 100, 8, 100, 80, 16),       # learn-NMS dV' (N = 8 < one 32-wide atom)
+    (False, True, 131, 77, 45, 1, 3),         # ragged everything
+])
+def test_gemm_tf32_matches_float64(ops, tA, tB, M, N, K, outer, inner):
+    """rn_gemm_tf32 (the training side's contraction engine) vs float64 matmul of the same fp32 operands: relative error of a
+    tf32 product sum (operands rounded to 10-bit mantissas, fp32 accumulate) <= 2e-3 of the result's max; alpha / beta; head
+    slices of a wider matrix as the inner batch (strides that are NOT the matrix size)."""
+    g = torch.Generator(device='cpu').manual_seed(M * 7 + N * 3 + K)
+    def operand(rows, cols):
+        # inner batch = column slices of one wide matrix (like the heads of Q / dO), outer = separate matrices
+        wide = torch.randn((outer, rows, inner * ((cols + 3) // 4 * 4)), generator=g).cuda()
+        cw = (cols + 3) // 4 * 4
+        return wide.as_strided((outer, inner, rows, cols), (wide.stride(0), cw, wide.stride(1), 1))
+    A = operand(K, M) if tA else operand(M, K)
+    B = operand(N, K) if tB else operand(K, N)
+    C0 = torch.randn((outer, inner, M, N), generator=g).cuda()
+    ref = 0.5 * torch.matmul((A.transpose(-1, -2) if tA else A).double(), (B.transpose(-1, -2) if tB else B).double()) + 2.0 * C0.double()
+    out = C0.clone()
+    ops.gemm_tf32(A, B, transA=tA, transB=tB, alpha=0.5, beta=2.0, out=out)
+    torch.cuda.synchronize()
+    e = float((out.double() - ref).abs().max() / ref.abs().max())
+    print('gemm_tf32 tA=%d tB=%d %dx%dx%d x(%d,%d): rel err %.2e' % (tA, tB, M, N, K, outer, inner, e))
+    assert e <= 2e-3, e
+    out2 = ops.gemm_tf32(A, B, transA=tA, transB=tB)          # beta = 0 never reads C
+    ref2 = torch.matmul((A.transpose(-1, -2) if tA else A).double(), (B.transpose(-1, -2) if tB else B).double())
+    assert float((out2.double() - ref2).abs().max() / ref2.abs().max()) <= 2e-3
+
+
+@pytest.mark.parametrize('prec', ['fp32', 'f16'])
 @pytest.mark.parametrize('seed,N,d,H,M,kidx,res', [
     (11, 70, 256, 4, 50, False, True),        # key prefix (FPN form, SYM_REL fpn :104-151), residual + relu
     (12, 300, 1024, 16, None, False, True),   # the module at its training size
     (13, 131, 256, 16, None, True, False),    # permuted key_index (learn-NMS form), no residual
 ])
-def test_relation_backward_matches_autograd(ops, seed, N, d, H, M, kidx, res):
+def test_relation_backward_matches_autograd(ops, seed, N, d, H, M, kidx, res, prec):
+    if prec not in grad_precisions(ops):
+        pytest.skip('tcgen05 needs sm_100')
     c = R.make_relation_case(seed, N, d, H, M=M)
     rng = np.random.RandomState(seed)
     key_index = rng.permutation(N)[:97].astype(np.int32) if kidx else None
@@ -48,7 +96,8 @@ def test_relation_backward_matches_autograd(ops, seed, N, d, H, M, kidx, res):
     dev = {k: torch.from_numpy(np.ascontiguousarray(c[k])).cuda() for k in NAMES + ('boxes',)}
     got = ops.relation_backward(torch.from_numpy(dOut).cuda(), dev['X'], dev['boxes'], dev['Wq'], dev['bq'], dev['Wk'], dev['bk'],
                                 dev['Wg'], dev['bg'], dev['Wout'], dev['bout'],
-                                key_index=torch.from_numpy(key_index).cuda() if kidx else None, M=M, group=H, residual_relu=res)
+                                key_index=torch.from_numpy(key_index).cuda() if kidx else None, M=M, group=H, residual_relu=res,
+                                precision=prec)
     torch.cuda.synchronize()
     for k in NAMES:
         a = got[k].cpu().numpy().reshape(g32[k].shape)
@@ -57,12 +106,12 @@ def test_relation_backward_matches_autograd(ops, seed, N, d, H, M, kidx, res):
             # both sides are rounding noise, so hold it to the scale of the query-bias gradient instead
             scale = np.abs(g32['bq']).max()
             print('dbk    |got| %.2e  |float32 autograd| %.2e  (dbq scale %.2e)' % (np.abs(a).max(), np.abs(g32[k]).max(), scale))
-            assert np.abs(a).max() <= 1e-4 * scale
+            assert np.abs(a).max() <= ZERO_TOL[prec] * scale
             continue
         e32 = rel_err(a, g32[k])
         e64 = rel_err(a, g64[k])
-        print('d%-5s vs float32 autograd %.2e   vs float64 %.2e' % (k, e32, e64))
-        assert e32 <= 2e-3, (k, e32)
+        print('[%s] d%-5s vs float32 autograd %.2e   vs float64 %.2e' % (prec, k, e32, e64))
+        assert e32 <= GRAD_TOL[prec], (k, e32)
 
 
 def test_relation_backward_batched_and_loud(ops):
@@ -80,7 +129,7 @@ def test_relation_backward_batched_and_loud(ops):
     for k in NAMES:
         want = torch.stack([s['X'] for s in singles]) if k == 'X' else singles[0][k] + singles[1][k]
         if k == 'bk':
-            assert both[k].abs().max().item() <= 1e-4 * both['bq'].abs().max().item()
+            assert both[k].abs().max().item() <= 3e-3 * both['bq'].abs().max().item()
             continue
         assert rel_err(both[k].cpu().numpy(), want.cpu().numpy()) <= 1e-5, k
     with pytest.raises(relnet_b200._lib.RelnetError):
@@ -182,8 +231,11 @@ def test_deform_conv_backward_grouped(ops):
         assert rel_err(g.cpu().numpy(), w) <= 2e-5, name
 
 
+@pytest.mark.parametrize('prec', ['fp32', 'f16'])
 @pytest.mark.parametrize('seed,R,C,d,n,nongt', [(41, 60, 8, 256, 20, 50), (42, 300, 80, 1024, 100, 300)])
-def test_learn_nms_backward_matches_autograd(ops, seed, R, C, d, n, nongt):
+def test_learn_nms_backward_matches_autograd(ops, seed, R, C, d, n, nongt, prec):
+    if prec not in grad_precisions(ops):
+        pytest.skip('tcgen05 needs sm_100')
     """rn_learn_nms_bwd vs autograd through oracle/learn_nms_torch.py (forward pinned to the numpy oracle / reference)."""
     from oracle import learn_nms_np as LN, learn_nms_torch as LT
     c = LN.make_learn_nms_case(seed, R=R, C=C, d=d)
@@ -208,25 +260,25 @@ def test_learn_nms_backward_matches_autograd(ops, seed, R, C, d, n, nongt):
     kw = dict(first_n=n, class_thresh=0.0, means=means, stds=stds, nongt_dim=nongt)
     multi = ops.learn_nms(*args, precision='fp32', **kw)[0]
     assert rel_err(multi.cpu().numpy(), multi_ref) <= 1e-4
-    grads, d_cls, d_feat = ops.learn_nms_backward(T(d_multi), *args, **kw)
+    grads, d_cls, d_feat = ops.learn_nms_backward(T(d_multi), *args, precision=prec, **kw)
     torch.cuda.synchronize()
     worst = 0.0
     for k in gP:
         want = gP[k]
         got = grads[k].cpu().numpy().reshape(want.shape)
         if k == 'nms_key_1_bias':          # exactly zero in exact arithmetic (softmax shift invariance): rounding noise
-            assert np.abs(got).max() <= 1e-4 * np.abs(gP['nms_query_1_bias']).max()
+            assert np.abs(got).max() <= ZERO_TOL[prec] * np.abs(gP['nms_query_1_bias']).max()
             continue
         e = rel_err(got, want)
         e64, ref64 = rel_err(got, gP64[k]), rel_err(want, gP64[k])
-        print('d%-28s vs float32 autograd %.2e | vs float64 %.2e (float32 autograd itself: %.2e)' % (k, e, e64, ref64))
+        print('[%s] d%-28s vs float32 autograd %.2e | vs float64 %.2e (float32 autograd itself: %.2e)' % (prec, k, e, e64, ref64))
         worst = max(worst, e)
         # the geometry-FC gradient carries 1/g weights up to 1e6 next to the 1e-6 clamp: float32 evaluations of it differ
         # among themselves, so it is held to the float32 oracle's OWN distance from exact arithmetic instead
-        assert e <= 2e-3 or e64 <= 3.0 * ref64 + 1e-4, (k, e, e64, ref64)
+        assert e <= GRAD_TOL[prec] or e64 <= 3.0 * ref64 + 1e-4, (k, e, e64, ref64)
     e_cs, e_ft = rel_err(d_cls.cpu().numpy(), gcs), rel_err(d_feat.cpu().numpy(), gft)
-    print('d_cls_score %.2e  d_feat %.2e' % (e_cs, e_ft))
-    assert e_cs <= 2e-3 and e_ft <= 2e-3
+    print('[%s] d_cls_score %.2e  d_feat %.2e' % (prec, e_cs, e_ft))
+    assert e_cs <= GRAD_TOL[prec] and e_ft <= GRAD_TOL[prec]
     assert np.abs(d_cls.cpu().numpy()[nongt:]).max(initial=0.0) == 0.0      # gt rows are outside the non-gt slice
 
 

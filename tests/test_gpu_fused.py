@@ -72,6 +72,36 @@ def test_fused_matches_oracle_and_unfused(ops, N, M, d, H):
         assert rel_err(fused, unf) < 1e-3
 
 
+# heads wider than 64 columns (BASELINE.json configs[4]: d = 1024, H = 4 -> d_k = 256): H c virtual heads of 64 that share their
+# head's geometry weight and softmax; also d_k = 128 (team of 4 / 8), one and several key ranges, partial tiles
+@pytest.mark.parametrize('N,M,d,H', [(100, 100, 1024, 4), (300, 300, 1024, 4), (1000, 1000, 1024, 4), (333, 200, 512, 4),
+                                     (300, 300, 256, 2), (515, 515, 1024, 8)])
+def test_fused_wide_heads_match_oracle(ops, N, M, d, H):
+    assert d // H > 64 and ops.relation_tc_supported(d, d, H)
+    c = R.make_relation_case(N * 17 + d + H, N, d, H, M=None if M == N else M)
+    args = rel_args(c)
+    ref = R.relation_forward(*args, key_index=M, group=H, residual_relu=True, dtype=np.float32)
+    t = [T(a) for a in args]
+    out = run(ops, t, 1, M=M, group=H, residual_relu=True).cpu().numpy()
+    e, frac = report('fused wide heads N=%d M=%d d=%d H=%d (d_k=%d)' % (N, M, d, H, d // H), out, ref)
+    assert e < 1e-3 and frac < 0.02
+    fp32 = ops.relation(*t, M=M, group=H, residual_relu=True, precision='fp32').cpu().numpy()
+    assert rel_err(out, fp32) < 1e-3
+
+
+def test_wide_heads_n3000_row_subset(ops):
+    """configs[4] N = 3000, d = 1024, H = 4 (d_k = 256): 64 query rows against the float32 oracle over all 3000 keys"""
+    N, d, H = 3000, 1024, 4
+    c = R.make_relation_case(321, N, d, H)
+    args = rel_args(c)
+    t = [T(a) for a in args]
+    out = run(ops, t, 1, group=H, residual_relu=True).cpu().numpy()
+    rows = np.concatenate([np.arange(0, 24), np.arange(1500, 1516), np.arange(2976, 3000)])
+    ref = R.relation_forward(*args, group=H, residual_relu=True, dtype=np.float32, query_index=rows)
+    e, frac = report('fused wide heads N=3000 d_k=256 (64-row subset)', out[rows], ref)
+    assert e < 1e-3 and frac < 0.02
+
+
 def test_fused_fanin_weights_and_f16_side_channel(ops):
     """The reference initialiser (N(0, 0.01): near-uniform softmax, geometry weights of a few 1e-2 next to the 1e-6 clamp)
     and the fp16 in / fp16 out side channels of the head."""

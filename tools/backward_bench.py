@@ -11,7 +11,7 @@ import __graft_entry__ as entry
 entry.build()
 import relnet_b200
 from relnet_b200 import ops
-from oracle import relation_np as R, learn_nms_np as LN
+from oracle import relation_np as R, learn_nms_np as LN      # case generators only (a dev tool, not the product)
 
 dev = torch.device('cuda:0')
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
@@ -41,7 +41,8 @@ t = [T(c[k]) for k in ('X', 'boxes', 'Wq', 'bq', 'Wk', 'bk', 'Wg', 'bg', 'Wout',
 dO = torch.randn(300, 1024, device=dev)
 out.append(dict(op='relation N=300 d=1024 H=16', fwd_f16_us=timeit(lambda: ops.relation(*t, group=16, residual_relu=True, precision='f16')),
                 fwd_fp32_us=timeit(lambda: ops.relation(*t, group=16, residual_relu=True, precision='fp32')),
-                bwd_fp32_us=timeit(lambda: ops.relation_backward(dO, *t, group=16, residual_relu=True))))
+                bwd_fp32_us=timeit(lambda: ops.relation_backward(dO, *t, group=16, residual_relu=True, precision='fp32')),
+                bwd_tf32_tc_us=timeit(lambda: ops.relation_backward(dO, *t, group=16, residual_relu=True, precision='f16'))))
 l = LN.make_learn_nms_case(2, R=300, C=80, d=1024)
 W = {k: T(v) for k, v in l['P'].items()}
 la = (T(l['cls_score']), T(l['bbox_pred']), T(l['rois']), T(l['im_info']), T(l['feat']), W)
@@ -49,7 +50,8 @@ dM = torch.randn(100, 80, 5, device=dev)
 out.append(dict(op='learn_nms R=300 C=80 n=100 (all classes)',
                 fwd_f16_us=timeit(lambda: ops.learn_nms(*la, class_thresh=0.0, precision='f16')),
                 fwd_fp32_us=timeit(lambda: ops.learn_nms(*la, class_thresh=0.0, precision='fp32')),
-                bwd_fp32_us=timeit(lambda: ops.learn_nms_backward(dM, *la, class_thresh=0.0))))
+                bwd_fp32_us=timeit(lambda: ops.learn_nms_backward(dM, *la, class_thresh=0.0, precision='fp32')),
+                bwd_tf32_tc_us=timeit(lambda: ops.learn_nms_backward(dM, *la, class_thresh=0.0, precision='f16'))))
 out.append(dict(op='learn_nms R=300 C=80 n=100, class_thresh 0.01 (synthetic scores: ~12 of 80 classes survive the pruning of LNMS:298-303)',
                 fwd_f16_us=timeit(lambda: ops.learn_nms(*la, class_thresh=0.01, precision='f16')),
                 fwd_fp32_us=timeit(lambda: ops.learn_nms(*la, class_thresh=0.01, precision='fp32'))))
