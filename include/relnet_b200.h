@@ -53,7 +53,10 @@ int rn_device_info(int* sm_count, int* cc_major, int* cc_minor);
  *   out = fuse_residual_relu ? relu(X + o) : o
  */
 enum { RN_PREC_FP32 = 0,  /* SIMT fp32 attention + cuBLAS fp32 projections: the bit-conservative parity mode */
-       RN_PREC_F16 = 1 }; /* fp16 operands / fp32 accumulate on tcgen05 tensor cores (sm_100a only) */
+       RN_PREC_F16 = 1,   /* fp16 operands / fp32 accumulate on tcgen05 tensor cores (sm_100a only) */
+       RN_PREC_TF32 = 2 }; /* rn_relation_fwd only: the general (materialising) kernels of RN_PREC_FP32 with every GEMM on the
+                            * library's tcgen05 tf32 engine (rn_gemm_tf32) -- exactly the forward that rn_relation_bwd /
+                            * rn_learn_nms_bwd recompute under RN_PREC_F16; also serves return_softmax on tensor cores */
 
 typedef struct rn_relation_desc {
   int32_t batch;      /* independent problems sharing the weights (1 for the detection head, #classes for learn-NMS) */
@@ -134,6 +137,15 @@ int rn_relation_bwd(const rn_relation_desc* desc, const float* X, const float* b
                     const float* Wout, const float* bout, const float* dOut, float* dX, float* dWq, float* dbq, float* dWk,
                     float* dbk, float* dWg, float* dbg, float* dWout, float* dbout, void* workspace,
                     size_t workspace_bytes, rn_stream_t stream);
+/* Same with the output of the forward that was actually executed (out_fwd [batch*N, dout], any precision of rn_relation_*_fwd):
+ * under fuse_residual_relu the relu mask is then [out_fwd > 0] -- what autograd over the executed graph does -- instead of
+ * the mask of the recomputed forward.  The two differ only for units within rounding of the kink (|X + o| ~ 1e-3 max under
+ * the tf32 engine, ~1e-6 under fp32), but each such unit switches its whole dOut entry on or off. */
+int rn_relation_bwd_masked(const rn_relation_desc* desc, const float* X, const float* boxes, const int32_t* key_index,
+                           const float* Wq, const float* bq, const float* Wk, const float* bk, const float* Wg, const float* bg,
+                           const float* Wout, const float* bout, const float* out_fwd, const float* dOut, float* dX, float* dWq,
+                           float* dbq, float* dWk, float* dbk, float* dWg, float* dbg, float* dWout, float* dbout,
+                           void* workspace, size_t workspace_bytes, rn_stream_t stream);
 /* The contraction engine of the training side, exported for checking on its own: row-major fp32
  *   C[o,i] (M x N, pitch ldc) = alpha * op(A[o,i]) . op(B[o,i]) + beta * C[o,i],   o < outer, i < inner,
  * problem (o, i) of an operand at base + o * s?o + i * s?i (floats).  transA: A is stored [K, M] (else [M, K]); transB: B is
@@ -400,6 +412,15 @@ int rn_deform_im2col(const rn_deform_conv_desc* desc, const float* data_b, const
  *   Weights / biases bf16 in the layout of the conv parameters ([out, Cin]). */
 int rn_rpn_head_fwd(const void* r_nhwc_bf16, int32_t HW, int32_t Cin, int32_t A, const void* Wcls_bf16, const void* bcls_bf16,
                     const void* Wbbox_bf16, const void* bbbox_bf16, float* prob, float* bbox, rn_stream_t stream);
+/* Tensor-core form of rn_rpn_head_fwd (sm_100): the two 1x1 heads are ONE [HW, Cin] x [Cin, 6A] GEMM on the library's tcgen05
+ * kernel with the bf16 operands exactly as the trunk left them, followed by one small softmax / layout kernel.  Pack the
+ * weights once per weight update (rn_rpn_head_pack: [Wcls; Wbbox] concatenated + fp32 biases); outputs as rn_rpn_head_fwd. */
+size_t rn_rpn_head_packed_bytes(int32_t Cin, int32_t A);
+int rn_rpn_head_pack(const void* Wcls_bf16, const void* bcls_bf16, const void* Wbbox_bf16, const void* bbbox_bf16, int32_t Cin,
+                     int32_t A, void* packed, rn_stream_t stream);
+size_t rn_rpn_head_workspace_bytes(int32_t HW, int32_t Cin, int32_t A);
+int rn_rpn_head_packed_fwd(const void* r_nhwc_bf16, int32_t HW, int32_t Cin, int32_t A, const void* packed, float* prob,
+                           float* bbox, void* workspace, size_t workspace_bytes, rn_stream_t stream);
 int rn_image_s2d_bf16(const float* image_chw, int32_t H, int32_t W, int32_t pad, void* out_nhwc16_bf16, rn_stream_t stream);
 int rn_maxpool3x3s2_nhwc_bf16(const void* in_nhwc, int32_t H, int32_t W, int32_t C, void* out_nhwc, rn_stream_t stream);
 

@@ -63,11 +63,16 @@ SIGNATURES = {
     'rn_relation_fwd': (C.c_int, [C.POINTER(RelationDesc)] + [c_p] * 13 + [c_p, c_sz, c_p]),
     'rn_relation_bwd_workspace_bytes': (c_sz, [C.POINTER(RelationDesc)]),
     'rn_relation_bwd': (C.c_int, [C.POINTER(RelationDesc)] + [c_p] * 21 + [c_p, c_sz, c_p]),
+    'rn_relation_bwd_masked': (C.c_int, [C.POINTER(RelationDesc)] + [c_p] * 22 + [c_p, c_sz, c_p]),
     'rn_relation_packed_fwd_f16io': (C.c_int, [C.POINTER(RelationDesc)] + [c_p] * 9 + [c_p, c_sz, c_i, c_p]),
     'rn_linear_multi_packed_bytes': (c_sz, [C.POINTER(c_i), c_i, c_i]),
     'rn_linear_multi_pack': (C.c_int, [C.POINTER(c_p), C.POINTER(c_p), C.POINTER(c_i), c_i, c_i, c_p, c_p]),
     'rn_linear_multi_packed_f16in_fwd': (C.c_int, [c_p, c_p, C.POINTER(c_p), C.POINTER(c_i), c_i, c_i, c_i, c_p, c_sz, c_p]),
     'rn_rpn_head_fwd': (C.c_int, [c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
+    'rn_rpn_head_packed_bytes': (c_sz, [c_i, c_i]),
+    'rn_rpn_head_pack': (C.c_int, [c_p] * 4 + [c_i, c_i, c_p, c_p]),
+    'rn_rpn_head_workspace_bytes': (c_sz, [c_i, c_i, c_i]),
+    'rn_rpn_head_packed_fwd': (C.c_int, [c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_sz, c_p]),
     'rn_image_s2d_bf16': (C.c_int, [c_p, c_i, c_i, c_i, c_p, c_p]),
     'rn_maxpool3x3s2_nhwc_bf16': (C.c_int, [c_p, c_i, c_i, c_i, c_p, c_p]),
     'rn_relation_fused_enable': (C.c_int, [c_i]),

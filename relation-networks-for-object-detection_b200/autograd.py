@@ -14,17 +14,19 @@ class RelationFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, X, boxes, Wq, bq, Wk, bk, Wg, bg, Wout, bout, key_index, M, group, residual_relu, precision,
                 grad_precision=None):
-        ctx.save_for_backward(X, boxes, Wq, bq, Wk, bk, Wg, bg, Wout, bout)
         ctx.key_index, ctx.M, ctx.group, ctx.residual_relu, ctx.grad_precision = key_index, M, group, residual_relu, grad_precision
-        return ops.relation(X, boxes, Wq, bq, Wk, bk, Wg, bg, Wout, bout, key_index=key_index, M=M, group=group,
-                            residual_relu=residual_relu, precision=precision)
+        out = ops.relation(X, boxes, Wq, bq, Wk, bk, Wg, bg, Wout, bout, key_index=key_index, M=M, group=group,
+                           residual_relu=residual_relu, precision=precision)
+        # the executed output rides along: its sign pattern is the relu mask of the backward (as in any autograd graph)
+        ctx.save_for_backward(X, boxes, Wq, bq, Wk, bk, Wg, bg, Wout, bout, out)
+        return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        X, boxes, Wq, bq, Wk, bk, Wg, bg, Wout, bout = ctx.saved_tensors
+        X, boxes, Wq, bq, Wk, bk, Wg, bg, Wout, bout, out = ctx.saved_tensors
         g = ops.relation_backward(grad_out.contiguous(), X, boxes, Wq, bq, Wk, bk, Wg, bg, Wout, bout,
                                   key_index=ctx.key_index, M=ctx.M, group=ctx.group, residual_relu=ctx.residual_relu,
-                                  precision=ctx.grad_precision)
+                                  precision=ctx.grad_precision, forward_out=out if ctx.residual_relu else None)
         return (g['X'], None, g['Wq'], g['bq'], g['Wk'], g['bk'], g['Wg'], g['bg'], g['Wout'], g['bout'],
                 None, None, None, None, None, None)
 

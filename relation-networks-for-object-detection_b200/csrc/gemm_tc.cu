@@ -40,6 +40,7 @@ struct GemmParams {
   const float* bias;          // [N] (bias_per_row == 0) or [M] (bias_per_row == 1) or nullptr
   int bias_per_row;
   int relu;
+  int bf16;                           // operands are bf16 instead of fp16 (same bytes through TMA; only the instruction descriptor differs)
   float* C32; long long ldc32;        // may be nullptr
   __half* C16; long long ldc16;       // may be nullptr
   float* partial;                     // split-K partials [splits][M][N] (when gridDim.z > 1)
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(192, 1) gemm_f16_tc_kernel(const __grid_consta
     }
   } else if (warp == 5) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(kBM, BN, false, false, false);
+      const uint32_t idesc = make_idesc_f16(kBM, BN, p.bf16 != 0, false, false);
       int it = 0, li = 0;
       for (int u = blockIdx.x; u < units; u += gridDim.x, ++li) {
         const int z = u / tiles;
@@ -288,7 +289,7 @@ static int launch(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tm
 
 int gemm_tc(cudaStream_t st, const __half* A, long long lda, const __half* B, long long ldb, int M, int N, int K,
             const float* bias, int bias_per_row, int relu, float* C32, long long ldc32, __half* C16, long long ldc16,
-            void* ws, size_t ws_bytes, const GemmSegments* seg) {
+            void* ws, size_t ws_bytes, const GemmSegments* seg, bool bf16) {
   RN_CHECK_ARG(is_sm100(), "tcgen05 GEMM needs an sm_100 device");
   RN_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm_tc: bad sizes %dx%dx%d", M, N, K);
   RN_CHECK_ARG((lda % 8) == 0 && (ldb % 8) == 0 && (((uintptr_t)A | (uintptr_t)B) & 15) == 0,
@@ -308,7 +309,7 @@ int gemm_tc(cudaStream_t st, const __half* A, long long lda, const __half* B, lo
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.k_blocks_per_split = cdiv(kb, splits);
   splits = cdiv(kb, p.k_blocks_per_split);
-  p.bias = bias; p.bias_per_row = bias_per_row; p.relu = relu;
+  p.bias = bias; p.bias_per_row = bias_per_row; p.relu = relu; p.bf16 = bf16 ? 1 : 0;
   p.C32 = C32; p.ldc32 = ldc32; p.C16 = C16; p.ldc16 = ldc16; p.partial = nullptr;
   p.nseg = 0;
   if (seg && seg->n > 0) {

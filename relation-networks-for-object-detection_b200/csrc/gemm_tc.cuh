@@ -13,7 +13,7 @@ struct GemmSegments { int n; int begin[4]; int cols[4]; float* ptr[4]; };
 // bias_per_row: bias indexed by output row instead of column.  ws: optional split-K scratch (gemm_tc_workspace_bytes).
 int gemm_tc(cudaStream_t st, const __half* A, long long lda, const __half* B, long long ldb, int M, int N, int K,
             const float* bias, int bias_per_row, int relu, float* C32, long long ldc32, __half* C16, long long ldc16,
-            void* ws, size_t ws_bytes, const GemmSegments* seg = nullptr);
+            void* ws, size_t ws_bytes, const GemmSegments* seg = nullptr, bool bf16 = false);   // bf16: A, B hold bf16 bits
 size_t gemm_tc_workspace_bytes(int M, int N, int K);
 int cast_f32_f16(cudaStream_t st, const float* src, __half* dst, size_t n);
 int cast_rows_f16(cudaStream_t st, const float* src, __half* dst, int rows, int cols, int ld);

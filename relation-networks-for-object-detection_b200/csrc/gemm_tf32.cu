@@ -17,7 +17,10 @@
 // Out-of-range rows / columns / K are zero-filled by TMA (tensor-map extents are the true per-problem extents), so no
 // operand is ever padded in memory; the epilogue masks its stores.
 //
-// Structure: one CTA = one 128 x BN output tile of one problem; warp 4 = TMA producer, warp 5 = TMEM allocation + MMA
+// Small problems: short K loops run with a 2-stage ring (64 KB: three CTAs share an SM, which matters for the 1280 per-class x
+// per-head problems of the learn-NMS head); long K loops of single problems with few output tiles are split over gridDim.z
+// and combined with red.global.add.f32 (C zeroed first when beta = 0).
+// Structure: one CTA = one 128 x BN output tile of one problem (and one K split); warp 4 = TMA producer, warp 5 = TMEM allocation + MMA
 // issue (one lane each), warps 0-3 = epilogue (TMEM lane quarter each; alpha / beta applied on the way out).  4-stage
 // ring of (A 16 KB + B <= 16 KB) stages, full/empty mbarriers, tcgen05.commit releases a stage.
 // Roofline: tensor pipe for the weight-gradient GEMMs (K = rois is short: they are launch/latency sized), L2 bandwidth
@@ -31,16 +34,18 @@ using namespace umma;
 
 namespace {
 
-constexpr int kTM = 128, kTK = 32, kTStages = 4;
+constexpr int kTM = 128, kTK = 32, kTMaxStages = 4;
 constexpr int kTA = kTM * kTK * 4;                   // 16 KB
 constexpr int kTStage = 2 * kTA;                     // A + B (B up to 128 columns)
-constexpr int kTBar = kTStages * kTStage;
-constexpr int kTSmem = kTBar + 256 + 1024;
+static inline int tf32_smem(int stages) { return stages * kTStage + 256 + 1024; }
 
 struct Tf32Params {
   int M, N, K, BN;
   int a_mn, b_mn;                                    // 1: operand is MN-major in shared memory (stored transposed)
   int inner;                                         // problems per outer index (blockIdx.y = o * inner + i)
+  int stages;                                        // ring depth (2 or 4); barriers live after the ring
+  int splits, kb_per_split;                          // K splits (gridDim.z); > 1: the epilogue adds its part atomically
+  int a_i, a_o, b_i, b_o;                            // 0: the operand is shared along that batch level (stride 0) -> coordinate 0
   float alpha, beta;
   float* C; long long ldc, sCo, sCi;
 };
@@ -76,21 +81,23 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
-__global__ void __launch_bounds__(192, 1) gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(192) gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmB, const Tf32Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kTBar);
-  uint64_t* empty = full + kTStages;
-  uint64_t* tfull = empty + kTStages;
+  const int kTStages = p.stages;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kTStages * kTStage);
+  uint64_t* empty = full + kTMaxStages;
+  uint64_t* tfull = empty + kTMaxStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_n = (p.N + p.BN - 1) / p.BN;
   const int m0 = (blockIdx.x / tiles_n) * kTM, n0 = (blockIdx.x % tiles_n) * p.BN;
   const int bo = blockIdx.y / p.inner, bi = blockIdx.y % p.inner;
-  const int nkb = (p.K + kTK - 1) / kTK;
+  const int nkb_all = (p.K + kTK - 1) / kTK;
+  const int kb0 = blockIdx.z * p.kb_per_split, nkb = max(0, min(nkb_all, kb0 + p.kb_per_split) - kb0);   // this split's K blocks
 
   if (warp == 4 && lane == 0) {
     prefetch_tmap(&tmA); prefetch_tmap(&tmB);
@@ -108,22 +115,23 @@ __global__ void __launch_bounds__(192, 1) gemm_tf32_tc_kernel(const __grid_const
     if (lane == 0) {
       const uint32_t bytesA = kTA;                                  // OOB parts of a box still count as transferred bytes
       const uint32_t bytesB = (uint32_t)p.BN * kTK * 4;
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % kTStages;
-        mbar_wait(&empty[s], ((kb / kTStages) & 1) ^ 1);
+      for (int it = 0; it < nkb; ++it) {
+        const int kb = kb0 + it;
+        const int s = it % kTStages;
+        mbar_wait(&empty[s], ((it / kTStages) & 1) ^ 1);
         mbar_arrive_expect_tx(&full[s], bytesA + bytesB);
         uint8_t* sa = smem + s * kTStage;
         uint8_t* sb = sa + kTA;
         if (p.a_mn) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) tma_load_4d(sa + j * 4096, &tmA, &full[s], m0 + 32 * j, kb * kTK, bi, bo);
+          for (int j = 0; j < 4; ++j) tma_load_4d(sa + j * 4096, &tmA, &full[s], m0 + 32 * j, kb * kTK, bi * p.a_i, bo * p.a_o);
         } else {
-          tma_load_4d(sa, &tmA, &full[s], kb * kTK, m0, bi, bo);
+          tma_load_4d(sa, &tmA, &full[s], kb * kTK, m0, bi * p.a_i, bo * p.a_o);
         }
         if (p.b_mn) {
-          for (int j = 0; j < p.BN / 32; ++j) tma_load_4d(sb + j * 4096, &tmB, &full[s], n0 + 32 * j, kb * kTK, bi, bo);
+          for (int j = 0; j < p.BN / 32; ++j) tma_load_4d(sb + j * 4096, &tmB, &full[s], n0 + 32 * j, kb * kTK, bi * p.b_i, bo * p.b_o);
         } else {
-          tma_load_4d(sb, &tmB, &full[s], kb * kTK, n0, bi, bo);
+          tma_load_4d(sb, &tmB, &full[s], kb * kTK, n0, bi * p.b_i, bo * p.b_o);
         }
       }
     }
@@ -131,16 +139,17 @@ __global__ void __launch_bounds__(192, 1) gemm_tf32_tc_kernel(const __grid_const
     if (lane == 0) {
       const uint32_t idesc = make_idesc_tf32(kTM, p.BN, p.a_mn != 0, p.b_mn != 0);
       const uint32_t stepA = p.a_mn ? 1024u : 32u, stepB = p.b_mn ? 1024u : 32u;        // bytes per K step of 8
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % kTStages;
-        mbar_wait(&full[s], (kb / kTStages) & 1);
+      for (int it = 0; it < nkb; ++it) {
+        const int kb = kb0 + it;
+        const int s = it % kTStages;
+        mbar_wait(&full[s], (it / kTStages) & 1);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + s * kTStage), sb = sa + kTA;
         const int ksteps = min(kTK, p.K - kb * kTK + 7) >> 3;          // whole K steps that hold at least one real k
         for (int k = 0; k < ksteps; ++k) {
           const uint64_t da = p.a_mn ? make_smem_desc_sw128_base32(sa + k * stepA, 4096, 512) : make_smem_desc_sw128(sa + k * stepA, 16, 1024);
           const uint64_t db = p.b_mn ? make_smem_desc_sw128_base32(sb + k * stepB, 4096, 512) : make_smem_desc_sw128(sb + k * stepB, 16, 1024);
-          mma_tf32_ss(tmem_base, da, db, idesc, (kb > 0) || (k > 0));
+          mma_tf32_ss(tmem_base, da, db, idesc, (it > 0) || (k > 0));
         }
         mma_commit(&empty[s]);
       }
@@ -164,6 +173,21 @@ __global__ void __launch_bounds__(192, 1) gemm_tf32_tc_kernel(const __grid_const
       const int col0 = n0 + c;
       if (row >= p.M || col0 >= p.N) continue;
       float* dst = Cb + (long long)row * p.ldc + col0;
+      if (p.splits > 1) {                 // K split: every split adds its part (beta was applied by zeroing / keeping C)
+        if (vec && col0 + 16 <= p.N) {    // 16-byte vector reductions: a quarter of the L2 atomic transactions
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(p.alpha * __uint_as_float(v[j])),
+                         "f"(p.alpha * __uint_as_float(v[j + 1])), "f"(p.alpha * __uint_as_float(v[j + 2])),
+                         "f"(p.alpha * __uint_as_float(v[j + 3]))
+                         : "memory");
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (col0 + j < p.N) atomicAdd(dst + j, p.alpha * __uint_as_float(v[j]));
+        }
+        continue;
+      }
       if (vec && col0 + 16 <= p.N) {
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
@@ -213,9 +237,11 @@ int encode_f32_4d(CUtensorMap* out, const float* base, int rows, int cols, long 
   std::call_once(g_once32, load_encode32);
   if (!g_encode32) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return RN_ERR_CUDA; }
   const long long fallback = ld * (long long)rows;            // any valid stride for extent-1 dimensions
-  cuuint64_t dims[4] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)inner, (cuuint64_t)outer};
-  cuuint64_t strides[3] = {(cuuint64_t)ld * 4, (cuuint64_t)(inner > 1 ? sI : fallback) * 4, (cuuint64_t)(outer > 1 ? sO : fallback) * 4};
-  for (int i = 1; i < 3; ++i) if (strides[i] == 0) strides[i] = strides[0];
+  // a batch level the operand is shared along (stride 0, e.g. one weight matrix for every problem) becomes an extent-1
+  // dimension; the kernel then passes coordinate 0 for it (Tf32Params::a_i ...)
+  const bool use_i = inner > 1 && sI != 0, use_o = outer > 1 && sO != 0;
+  cuuint64_t dims[4] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)(use_i ? inner : 1), (cuuint64_t)(use_o ? outer : 1)};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 4, (cuuint64_t)(use_i ? sI : fallback) * 4, (cuuint64_t)(use_o ? sO : fallback) * 4};
   cuuint32_t box[4] = {32, (cuuint32_t)box_rows, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = g_encode32(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
@@ -254,6 +280,8 @@ int gemm_tf32(cudaStream_t st, bool transA, bool transB, int M, int N, int K, fl
   const int gran = p.b_mn ? 32 : 16;
   p.BN = std::min(128, (N + gran - 1) / gran * gran);
   p.inner = inner; p.alpha = alpha; p.beta = beta;
+  p.a_i = (inner > 1 && sAi != 0) ? 1 : 0; p.a_o = (outer > 1 && sAo != 0) ? 1 : 0;
+  p.b_i = (inner > 1 && sBi != 0) ? 1 : 0; p.b_o = (outer > 1 && sBo != 0) ? 1 : 0;
   p.C = C; p.ldc = ldc; p.sCo = sCo; p.sCi = sCi;
   CUtensorMap tmA, tmB;
   int r;
@@ -265,11 +293,23 @@ int gemm_tf32(cudaStream_t st, bool transA, bool transB, int M, int N, int K, fl
   if (r) return r;
   static thread_local bool configured = false;
   if (!configured) {
-    RN_CUDA(cudaFuncSetAttribute(gemm_tf32_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmem));
+    RN_CUDA(cudaFuncSetAttribute(gemm_tf32_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tf32_smem(kTMaxStages)));
     configured = true;
   }
-  const int tiles = cdiv(M, kTM) * cdiv(N, p.BN);
-  gemm_tf32_tc_kernel<<<dim3((unsigned)tiles, (unsigned)(outer * inner)), 192, kTSmem, st>>>(tmA, tmB, p);
+  const int tiles = cdiv(M, kTM) * cdiv(N, p.BN), nkb = cdiv(K, kTK);
+  const int sms = sm_count() > 0 ? sm_count() : 148;
+  p.splits = 1; p.kb_per_split = nkb > 0 ? nkb : 1;
+  if (outer * inner == 1 && (beta == 0.f || beta == 1.f) && nkb >= 8 && tiles * 2 <= sms) {
+    int want = std::min(std::min(sms / tiles, nkb / 4), 32);
+    if (want > 1) {
+      p.kb_per_split = cdiv(nkb, want);
+      p.splits = cdiv(nkb, p.kb_per_split);
+    }
+  }
+  if (p.splits > 1 && beta == 0.f)        // the splits accumulate into C
+    RN_CUDA(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, st));
+  p.stages = p.kb_per_split <= 2 ? 2 : kTMaxStages;
+  gemm_tf32_tc_kernel<<<dim3((unsigned)tiles, (unsigned)(outer * inner), (unsigned)p.splits), 192, tf32_smem(p.stages), st>>>(tmA, tmB, p);
   RN_LAUNCH_CHECK();
   return RN_OK;
 }

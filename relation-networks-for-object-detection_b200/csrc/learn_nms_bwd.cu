@@ -257,12 +257,15 @@ extern "C" int rn_learn_nms_bwd(const rn_learn_nms_desc* desc, const float* cls_
   if ((r = sgemm_rm(st, true, false, T, kNmsFeat, C * n, 1.f, dS, T, W.feat_out, kNmsFeat, 0.f, g->nms_logit_weight, kNmsFeat))) return r;
   if ((r = launch_colsum(st, dS, C * n, T, g->nms_logit_bias))) return r;
   if ((r = sgemm_rm(st, false, false, C * n, kNmsFeat, T, 1.f, dS, T, w->nms_logit_weight, kNmsFeat, 0.f, dF, kNmsFeat))) return r;
-  // 3. relation module over the C per-class problems
+  // 3. relation module over the C per-class problems; its forward intermediates are the ones step 1 left in W.rel_ws
+  Fp32State fwd_state;
+  if (!relation_fp32_carve(&rd, W.rel_ws, W.rel_ws_bytes, &fwd_state)) { set_error("rn_learn_nms_bwd: relation state carve failed"); return RN_ERR_WORKSPACE; }
   if ((r = relation_bwd(&rd, W.feat_cls, W.boxes_cls, nullptr, w->nms_query_1_weight, w->nms_query_1_bias,
                         w->nms_key_1_weight, w->nms_key_1_bias, w->nms_pair_pos_fc1_1_weight, w->nms_pair_pos_fc1_1_bias,
                         w->nms_linear_out_1_weight, w->nms_linear_out_1_bias, dF, d_f, g->nms_query_1_weight,
                         g->nms_query_1_bias, g->nms_key_1_weight, g->nms_key_1_bias, g->nms_pair_pos_fc1_1_weight,
-                        g->nms_pair_pos_fc1_1_bias, g->nms_linear_out_1_weight, g->nms_linear_out_1_bias, rel_ws, rel_bytes, st)))
+                        g->nms_pair_pos_fc1_1_bias, g->nms_linear_out_1_weight, g->nms_linear_out_1_bias, rel_ws, rel_bytes, st,
+                        &fwd_state, W.feat_out)))
     return r;
   // 4. gather
   RN_CUDA(cudaMemsetAsync(pos, 0xff, sizeof(int) * (size_t)C * Rn, st));

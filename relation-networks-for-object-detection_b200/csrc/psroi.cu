@@ -59,6 +59,14 @@ __device__ __forceinline__ void ps_build_table(const rn_psroi_desc& p, const PsR
   }
 }
 
+// Merged-tap form of the channels-last paths.  The 16 samples of a bin are 0.1 .. 2 cells apart, so their 64 taps fall on a
+// handful of distinct feature-map cells (9 .. 16 for a 200-pixel roi): the sample loop is regrouped per CELL,
+//   sum_s sum_tap w(s,tap) v(tap)  =  sum_cell (sum_{(s,tap) on cell} w(s,tap)) v(cell),
+// the per-cell weights being accumulated once per (roi, bin) into a kPsG x kPsG window and then shared by all channels:
+// 4 .. 7 times fewer 16-byte loads and multiply-adds per output than walking the samples (same value up to fp32
+// re-association, ~1e-7).  Bins wider than the window (rois over ~800 pixels) keep the sample walk.
+constexpr int kPsG = 8;
+
 __device__ __forceinline__ float ps_interp(const PsSample& t, float v11, float v12, float v21, float v22) {   // :44-46
   return (1 - t.dx) * (1 - t.dy) * v11 + (1 - t.dx) * t.dy * v12 + t.dx * (1 - t.dy) * v21 + t.dx * t.dy * v22;
 }
@@ -74,6 +82,10 @@ __global__ void __launch_bounds__(256) psroi_fwd_kernel(rn_psroi_desc p, const v
   int* cnt = reinterpret_cast<int*>(tab + pooled * spp2);                                // [pooled]
   float* stage = reinterpret_cast<float*>(cnt + ((pooled + 3) & ~3));                    // [cec][pooled]
   const int n = blockIdx.y, ph = blockIdx.x;
+  // channels-last forms: per bin, the bilinear weights of all its samples merged per feature-map cell (kPsG x kPsG window)
+  const int cec_all = p.no_trans ? p.output_dim : p.output_dim / (p.no_trans ? 1 : p.num_classes);
+  float* wgrid = stage + (size_t)cec_all * pooled;                                       // [pooled][kPsG * kPsG]
+  int* wfoot = reinterpret_cast<int*>(wgrid + pooled * kPsG * kPsG);                     // [pooled][4]: x_lo, y_lo, gw, gh (gw < 0: no grid)
   const int num_classes = p.no_trans ? 1 : p.num_classes;
   const int cec = p.no_trans ? p.output_dim : p.output_dim / num_classes;                // channels of one class
   const PsRoi r = ps_roi(p, rois + 5 * n);
@@ -88,6 +100,45 @@ __global__ void __launch_bounds__(256) psroi_fwd_kernel(rn_psroi_desc p, const v
       int c = 0;
       for (int s = 0; s < spp2; ++s) c += tab[threadIdx.x * spp2 + s].valid;
       cnt[threadIdx.x] = c;
+    }
+    if (LAYOUT != 0) {
+      for (int i = threadIdx.x; i < pooled * kPsG * kPsG; i += blockDim.x) wgrid[i] = 0.f;
+      if (threadIdx.x < pooled) {
+        wfoot[threadIdx.x * 4 + 0] = 1 << 30; wfoot[threadIdx.x * 4 + 1] = 1 << 30;      // x_lo, y_lo
+        wfoot[threadIdx.x * 4 + 2] = -1; wfoot[threadIdx.x * 4 + 3] = -1;                // x_hi, y_hi (turned into gw, gh below)
+      }
+      __syncthreads();
+      for (int e = threadIdx.x; e < pooled * spp2; e += blockDim.x) {                    // footprint of every bin, all samples at once
+        const PsSample t = tab[e];
+        if (!t.valid) continue;
+        const int pw = e / spp2;
+        const int y1 = t.o11 / p.W, x1 = t.o11 - y1 * p.W, y2 = t.o22 / p.W, x2 = t.o22 - y2 * p.W;
+        atomicMin(&wfoot[pw * 4 + 0], x1); atomicMin(&wfoot[pw * 4 + 1], y1);
+        atomicMax(&wfoot[pw * 4 + 2], x2); atomicMax(&wfoot[pw * 4 + 3], y2);
+      }
+      __syncthreads();
+      if (threadIdx.x < pooled) {
+        const int xl = wfoot[threadIdx.x * 4], yl = wfoot[threadIdx.x * 4 + 1], xh = wfoot[threadIdx.x * 4 + 2], yh = wfoot[threadIdx.x * 4 + 3];
+        const int gw = xh - xl + 1, gh2 = yh - yl + 1;
+        const bool ok = xh >= 0 && gw <= kPsG && gh2 <= kPsG;
+        wfoot[threadIdx.x * 4 + 2] = ok ? gw : (xh < 0 ? 0 : -1); wfoot[threadIdx.x * 4 + 3] = ok ? gh2 : 0;
+      }
+      __syncthreads();
+      for (int e = threadIdx.x; e < pooled * spp2; e += blockDim.x) {
+        const int pw = e / spp2;
+        const PsSample t = tab[e];
+        const int gw = wfoot[pw * 4 + 2];
+        if (!t.valid || gw <= 0) continue;
+        const int xl = wfoot[pw * 4], yl = wfoot[pw * 4 + 1];
+        float* g = wgrid + pw * kPsG * kPsG;
+        const int o[4] = {t.o11, t.o12, t.o21, t.o22};
+        const float w[4] = {(1 - t.dx) * (1 - t.dy), (1 - t.dx) * t.dy, t.dx * (1 - t.dy), t.dx * t.dy};     // :44-46
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int y = o[k] / p.W, x = o[k] - y * p.W;
+          atomicAdd(g + (y - yl) * kPsG + (x - xl), w[k]);
+        }
+      }
     }
     __syncthreads();
     if (LAYOUT == 0) {
@@ -117,6 +168,50 @@ __global__ void __launch_bounds__(256) psroi_fwd_kernel(rn_psroi_desc p, const v
           float sum[VEC];
 #pragma unroll
           for (int k = 0; k < VEC; ++k) sum[k] = 0.f;
+          const int fgw = wfoot[pw * 4 + 2], fgh = wfoot[pw * 4 + 3];
+          if (fgw >= 0) {                       // merged-tap form: one load per distinct cell of the bin's footprint
+            const int xl = wfoot[pw * 4], yl = wfoot[pw * 4 + 1];
+            const float* g = wgrid + pw * kPsG * kPsG;
+            const size_t base = (size_t)r.b * HW + (size_t)yl * p.W + xl;
+            const int ncell = fgw * fgh;
+            // four cells per round: their loads are issued back to back (the walk is latency bound, not bandwidth bound:
+            // one dependent L2 round trip per cell and 8 warps per CTA otherwise); zero-weight cells of the window are loaded
+            // too -- they are inside the bin's footprint, hence inside the map
+            for (int i0 = 0; i0 < ncell; i0 += 4) {
+              float wv[4];
+              size_t cell[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int i = min(i0 + u, ncell - 1), cy = i / fgw, cx = i - cy * fgw;
+                wv[u] = i0 + u < ncell ? g[cy * kPsG + cx] : 0.f;
+                cell[u] = base + (size_t)cy * p.W + cx;
+              }
+              if (LAYOUT == 1) {
+                float4 a[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                  a[u] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(data_) + cell[u] * p.channels + c0));
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  sum[0] += wv[u] * a[u].x; sum[1] += wv[u] * a[u].y; sum[2] += wv[u] * a[u].z; sum[3] += wv[u] * a[u].w;
+                }
+              } else {
+                uint4 a[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                  a[u] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(data_) + cell[u] * p.channels + c0));
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a[u]);
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    const float2 fa = __bfloat1622float2(pa[q]);
+                    sum[2 * q] += wv[u] * fa.x; sum[2 * q + 1] += wv[u] * fa.y;
+                  }
+                }
+              }
+            }
+          } else
           for (int s = 0; s < spp2; ++s) {
             const PsSample t = tab[pw * spp2 + s];
             if (!t.valid) continue;
@@ -267,7 +362,7 @@ static int psroi_check(const rn_psroi_desc* desc, rn_psroi_desc* p, const void* 
 static size_t psroi_smem(const rn_psroi_desc& p) {
   const int ncls = p.no_trans ? 1 : p.num_classes, cec = p.no_trans ? p.output_dim : p.output_dim / ncls;
   return sizeof(PsSample) * p.pooled_size * p.sample_per_part * p.sample_per_part + sizeof(int) * ((p.pooled_size + 3) & ~3) +
-         sizeof(float) * (size_t)cec * p.pooled_size;
+         sizeof(float) * (size_t)cec * p.pooled_size + sizeof(float) * p.pooled_size * kPsG * kPsG + sizeof(int) * p.pooled_size * 4;
 }
 
 template <int LAYOUT>

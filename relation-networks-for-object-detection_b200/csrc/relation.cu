@@ -90,8 +90,8 @@ int relation_check_desc(const rn_relation_desc* d) {
                d->dout, d->H);
   RN_CHECK_ARG(!d->fuse_residual_relu || d->dout == d->d, "rn_relation: residual needs dout == d (%d vs %d)", d->dout,
                d->d);
-  RN_CHECK_ARG(d->precision == RN_PREC_FP32 || d->precision == RN_PREC_F16, "rn_relation: unknown precision %d",
-               d->precision);
+  RN_CHECK_ARG(d->precision == RN_PREC_FP32 || d->precision == RN_PREC_F16 || d->precision == RN_PREC_TF32,
+               "rn_relation: unknown precision %d", d->precision);
   RN_CHECK_ARG(d->dq >= d->H && d->dout >= d->H, "rn_relation: dq=%d / dout=%d must be at least H=%d", d->dq, d->dout, d->H);
   // the geometry kernels evaluate E / 8 frequencies per coordinate (4 coordinates x sin, cos): a remainder would be dropped
   RN_CHECK_ARG(d->E >= 8 && d->E % 8 == 0 && d->E <= 128, "rn_relation: E=%d unsupported (a multiple of 8 in 8..128)", d->E);
@@ -211,6 +211,8 @@ extern "C" int rn_relation_fwd(const rn_relation_desc* d, const float* X, const 
   cudaStream_t st = (cudaStream_t)stream;
   if (d->precision == RN_PREC_F16)
     return rn::relation_tc(d, X, boxes, key_index, Wq, bq, Wk, bk, Wg, bg, Wout, bout, out, softmax_out, ws, ws_bytes, st);
+  RN_CHECK_ARG(d->precision != RN_PREC_TF32 || rn::is_sm100(), "RN_PREC_TF32 needs an sm_100 device (tcgen05)");
+  rn::GemmBackendScope backend(d->precision == RN_PREC_TF32 ? 1 : rn::gemm_backend());   // inside a backward: the caller's engine
   return rn::relation_fp32(d, X, boxes, key_index, Wq, bq, Wk, bk, Wg, bg, Wout, bout, out, softmax_out, ws, ws_bytes, st);
 }
 

@@ -21,7 +21,9 @@ size_t relation_bwd_ws_bytes(const rn_relation_desc* d);
 int relation_bwd(const rn_relation_desc* d, const float* X, const float* boxes, const int* key_index, const float* Wq,
                  const float* bq, const float* Wk, const float* bk, const float* Wg, const float* bg, const float* Wout,
                  const float* bout, const float* dOut, float* dX, float* dWq, float* dbq, float* dWk, float* dbk,
-                 float* dWg, float* dbg, float* dWout, float* dbout, void* ws, size_t ws_bytes, cudaStream_t st);
+                 float* dWg, float* dbg, float* dWout, float* dbout, void* ws, size_t ws_bytes, cudaStream_t st,
+                 const Fp32State* forward_state = nullptr, const float* forward_out = nullptr,
+                 const float* mask_out = nullptr);
 int launch_colsum(cudaStream_t st, const float* A, int rows, int cols, float* out);   // out[c] = sum_r A[r][c]
 
 // fused tcgen05 path (relation_tc.cu)

@@ -31,13 +31,24 @@ __global__ void relu_mask_kernel(const float* __restrict__ Y, const float* __res
   }
 }
 
-// out[c] = sum_r A[r][c]   (thread per column; consecutive threads read consecutive addresses)
-__global__ void colsum_kernel(const float* __restrict__ A, int rows, int cols, float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
-  float s = 0.f;
-  for (int r = 0; r < rows; ++r) s += A[(size_t)r * cols + c];
-  out[c] = s;
+// out[c] = sum_r A[r][c].  CTA = 32 columns x 32 row lanes: row lane y sums rows y, y + 32, ... (a warp reads 128 contiguous
+// bytes per row), then a shared-memory tree over the row lanes.  Deterministic (no atomics); rows x 128 B per CTA.
+__global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ A, int rows, int cols, float* __restrict__ out) {
+  __shared__ float red[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float s0 = 0.f, s1 = 0.f;
+  if (c < cols) {
+    int r = threadIdx.y;
+    for (; r + 32 < rows; r += 64) { s0 += A[(size_t)r * cols + c]; s1 += A[(size_t)(r + 32) * cols + c]; }
+    if (r < rows) s0 += A[(size_t)r * cols + c];
+  }
+  red[threadIdx.y][threadIdx.x] = s0 + s1;
+  __syncthreads();
+  for (int o = 16; o > 0; o >>= 1) {
+    if (threadIdx.y < o) red[threadIdx.y][threadIdx.x] += red[threadIdx.y + o][threadIdx.x];
+    __syncthreads();
+  }
+  if (threadIdx.y == 0 && c < cols) out[c] = red[0][threadIdx.x];
 }
 
 // warp per (b,h,n) row: dP <- scale * P o (dP - sum(P o dP));  g <- [g > 1e-6] * P o (dP - sum) / g
@@ -128,15 +139,99 @@ __global__ void __launch_bounds__(128) geom_grad_kernel(const float* __restrict_
   }
 }
 
-__global__ void reduce_partials_kernel(const float* __restrict__ partial, int nblocks, int H, int E,
-                                       float* __restrict__ dWg, float* __restrict__ dbg) {
-  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+// E = 64 form of the kernel above with a register tile: 160 threads build phi for 128 pairs (rows of 68 floats: 64 phi
+// columns, the constant 1 of the bias, 3 zeros -> 16-byte aligned float4 reads), then thread (hq, eq), hq < 8, eq < 17, owns
+// the 2 heads x 4 columns block (2 hq .. 2 hq + 1, 4 eq .. 4 eq + 3): per pair 2 scalar + 1 float4 shared loads feed 8 FMAs
+// (the one-output-per-thread form above issues 2 loads per FMA and was LDS bound: 84 us at N = 300, 618 us for the 80-class
+// learn-NMS head; profiles/r02_launches_bwd_*.csv).  phi: two-step Cody-Waite reduction + MUFU (|err| ~ 1e-6), as in the forward.
+constexpr int kGP = 68;
+__device__ __forceinline__ void sincos_cw(float x, float* s, float* c) {
+  const float n = rintf(x * 0.15915494309189535f);
+  float r = fmaf(n, -6.2831854820251465f, x);
+  r = fmaf(n, 1.7484555e-7f, r);
+  *s = __sinf(r);
+  *c = __cosf(r);
+}
+__global__ void __launch_bounds__(160) geom_grad_tiled_kernel(const float* __restrict__ boxes, const int* __restrict__ key_index,
+                                                              const float* __restrict__ dx, int B, int N, int M, int H, int ld,
+                                                              GeomFreq fr, float* __restrict__ partial) {
+  __shared__ __align__(16) float phi_s[128 * kGP];
+  __shared__ float dx_s[16 * 128];
+  const int tid = threadIdx.x;
+  const int hq = tid / 17, eq = tid - hq * 17;               // compute role (tid < 136)
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  const int tiles_m = (M + 127) >> 7;
+  const long long total = (long long)B * N * tiles_m;
+  for (long long item = blockIdx.x; item < total; item += gridDim.x) {
+    const int tm = (int)(item % tiles_m);
+    const int n = (int)((item / tiles_m) % N), b = (int)(item / ((long long)tiles_m * N));
+    __syncthreads();                                          // previous tile's dot products are done
+    if (tid < 128) {
+      const int m = tm * 128 + tid;
+      float* row = phi_s + tid * kGP;
+      if (m < M) {
+        const float4 bn = reinterpret_cast<const float4*>(boxes)[(size_t)b * N + n];
+        const float4 bm = reinterpret_cast<const float4*>(boxes)[(size_t)b * N + (key_index ? key_index[m] : m)];
+        float eps[4];
+        pair_eps(bn, bm, eps);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float a = 100.0f * eps[c];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) sincos_cw(a / fr.dim[k], &row[c * 16 + k], &row[c * 16 + 8 + k]);
+        }
+        row[64] = 1.f; row[65] = 0.f; row[66] = 0.f; row[67] = 0.f;
+        for (int h = 0; h < 16; ++h) dx_s[h * 128 + tid] = h < H ? dx[(((size_t)b * H + h) * N + n) * ld + m] : 0.f;
+      } else {
+#pragma unroll 4
+        for (int e = 0; e < kGP; ++e) row[e] = 0.f;
+        for (int h = 0; h < 16; ++h) dx_s[h * 128 + tid] = 0.f;
+      }
+    }
+    __syncthreads();
+    if (tid < 136) {
+      const float* d0 = dx_s + (2 * hq) * 128;
+      const float* d1 = d0 + 128;
+      const float4* ph = reinterpret_cast<const float4*>(phi_s) + eq;
+#pragma unroll 8
+      for (int p = 0; p < 128; ++p) {
+        const float4 f = ph[p * (kGP / 4)];
+        const float a0 = d0[p], a1 = d1[p];
+        acc[0][0] = fmaf(a0, f.x, acc[0][0]); acc[0][1] = fmaf(a0, f.y, acc[0][1]);
+        acc[0][2] = fmaf(a0, f.z, acc[0][2]); acc[0][3] = fmaf(a0, f.w, acc[0][3]);
+        acc[1][0] = fmaf(a1, f.x, acc[1][0]); acc[1][1] = fmaf(a1, f.y, acc[1][1]);
+        acc[1][2] = fmaf(a1, f.z, acc[1][2]); acc[1][3] = fmaf(a1, f.w, acc[1][3]);
+      }
+    }
+  }
+  if (tid < 136) {
+    const int nout = H * 65;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int h = 2 * hq + i;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int e = 4 * eq + j;
+        if (h < H && e < 65) partial[(size_t)blockIdx.x * nout + h * 65 + e] = acc[i][j];
+      }
+    }
+  }
+}
+
+// one warp per output: lanes stride over the per-CTA partials, shuffle tree (fixed order: deterministic)
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, int nblocks, int H, int E,
+                                                              float* __restrict__ dWg, float* __restrict__ dbg) {
+  const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int EE = E + 1, nout = H * EE;
   if (o >= nout) return;
   float s = 0.f;
-  for (int k = 0; k < nblocks; ++k) s += partial[(size_t)k * nout + o];
-  const int h = o / EE, e = o - h * EE;
-  if (e == E) dbg[h] = s; else dWg[h * E + e] = s;
+  for (int k = lane; k < nblocks; k += 32) s += partial[(size_t)k * nout + o];
+#pragma unroll
+  for (int w = 16; w > 0; w >>= 1) s += __shfl_xor_sync(0xffffffffu, s, w);
+  if (lane == 0) {
+    const int h = o / EE, e = o - h * EE;
+    if (e == E) dbg[h] = s; else dWg[h * E + e] = s;
+  }
 }
 
 // dX[b, key(m)] += dXk[b, m]
@@ -153,7 +248,7 @@ __global__ void scatter_add_rows_kernel(const float* __restrict__ dXk, const int
 }
 
 int launch_colsum(cudaStream_t st, const float* A, int rows, int cols, float* out) {
-  colsum_kernel<<<cdiv(cols, 128), 128, 0, st>>>(A, rows, cols, out);
+  colsum_kernel<<<cdiv(cols, 32), dim3(32, 32), 0, st>>>(A, rows, cols, out);
   RN_LAUNCH_CHECK();
   return RN_OK;
 }
@@ -161,7 +256,9 @@ int launch_colsum(cudaStream_t st, const float* A, int rows, int cols, float* ou
 static int geom_grad_grid(const rn_relation_desc* d) {
   const long long items = (long long)d->batch * d->N * cdiv(d->M, 128);
   const int sms = sm_count() > 0 ? sm_count() : 148;
-  return (int)std::max<long long>(1, std::min<long long>(items, (long long)sms * 2));
+  // 5 CTAs per SM: the per-tile work is a long dependent chain (log / sincos of phi, then 128 accumulation steps), so it is
+  // latency bound at 5 warps per CTA -- resident CTAs, not issue slots, set the rate (43 KB smem / 160 threads each)
+  return (int)std::max<long long>(1, std::min<long long>(items, (long long)sms * 5));
 }
 
 size_t relation_bwd_ws_bytes(const rn_relation_desc* d) {
@@ -181,11 +278,18 @@ int relation_bwd(const rn_relation_desc* d, const float* X, const float* boxes, 
                         const float* Wq, const float* bq, const float* Wk, const float* bk, const float* Wg,
                         const float* bg, const float* Wout, const float* bout, const float* dOut, float* dX, float* dWq,
                         float* dbq, float* dWk, float* dbk, float* dWg, float* dbg, float* dWout, float* dbout,
-                        void* wsp, size_t ws_bytes, cudaStream_t st) {
+                        void* wsp, size_t ws_bytes, cudaStream_t st, const Fp32State* forward_state, const float* forward_out,
+                        const float* mask_out) {
   const int B = d->batch, N = d->N, M = d->M, D = d->d, dq = d->dq, dout = d->dout, H = d->H, E = d->E;
   const int dk = dq / H, dv = dout / H;
+  // forward_state / forward_out: the intermediates (Q, K, V', g, P, gathered keys) and output of a relation_fp32 call the
+  // caller has just made with the same arguments (the learn-NMS backward recomputes its whole forward anyway): no second
+  // recomputation here.  g is consumed (overwritten with dx) either way.
   Fp32State fs;
-  if (!relation_fp32_carve(d, wsp, ws_bytes, &fs)) {
+  if (forward_state) {
+    fs = *forward_state;
+    fs.used = 0;
+  } else if (!relation_fp32_carve(d, wsp, ws_bytes, &fs)) {
     set_error("rn_relation_bwd: workspace too small (%zu < %zu)", ws_bytes, relation_bwd_ws_bytes(d));
     return RN_ERR_WORKSPACE;
   }
@@ -208,16 +312,18 @@ int relation_bwd(const rn_relation_desc* d, const float* X, const float* boxes, 
   int r;
   if ((r = make_freq(E, d->wave_length, &fr))) return r;
   // 1. recompute the forward: leaves Q, K, V', g, P (in fs.S), gathered keys (fs.Xk) in the workspace, out in Y
-  if ((r = relation_fp32(d, X, boxes, key_index, Wq, bq, Wk, bk, Wg, bg, Wout, bout, Y, nullptr, wsp, fs.used, st))) return r;
+  if (forward_state) Y = const_cast<float*>(forward_out);
+  else if ((r = relation_fp32(d, X, boxes, key_index, Wq, bq, Wk, bk, Wg, bg, Wout, bout, Y, nullptr, wsp, fs.used, st))) return r;
   const float* P = fs.S;
   // 2. dO, residual part of dX
   {
     const size_t total = (size_t)B * N * dout;
     if (!d->fuse_residual_relu) RN_CUDA(cudaMemsetAsync(dX, 0, (size_t)B * N * D * sizeof(float), st));
     int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
-    relu_mask_kernel<<<blocks, 256, 0, st>>>(Y, dOut, total, d->fuse_residual_relu, dO, dX);
+    // relu mask: the executed forward's output when the caller has it, else the recomputed one
+    relu_mask_kernel<<<blocks, 256, 0, st>>>(mask_out ? mask_out : Y, dOut, total, d->fuse_residual_relu, dO, dX);
     RN_LAUNCH_CHECK();
-    colsum_kernel<<<cdiv(dout, 128), 128, 0, st>>>(dO, B * N, dout, dbout);
+    colsum_kernel<<<cdiv(dout, 32), dim3(32, 32), 0, st>>>(dO, B * N, dout, dbout);
     RN_LAUNCH_CHECK();
   }
   // 3. dV'_h = P_h^T dO_h,  dP_h = dO_h V'_h^T   (heads batched)
@@ -241,16 +347,17 @@ int relation_bwd(const rn_relation_desc* d, const float* X, const float* boxes, 
   {
     const size_t smem = ((size_t)128 * (E + 1) + (size_t)H * 128) * sizeof(float);
     RN_CUDA(cudaFuncSetAttribute(geom_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    geom_grad_kernel<<<ggrid, 128, smem, st>>>(boxes, key_index, fs.g, B, N, M, H, E, ld, fr, partial);
+    if (E == 64 && H <= 16) geom_grad_tiled_kernel<<<ggrid, 160, 0, st>>>(boxes, key_index, fs.g, B, N, M, H, ld, fr, partial);
+    else geom_grad_kernel<<<ggrid, 128, smem, st>>>(boxes, key_index, fs.g, B, N, M, H, E, ld, fr, partial);
     RN_LAUNCH_CHECK();
-    reduce_partials_kernel<<<cdiv(H * (E + 1), 128), 128, 0, st>>>(partial, ggrid, H, E, dWg, dbg);
+    reduce_partials_kernel<<<cdiv(H * (E + 1) * 32, 256), 256, 0, st>>>(partial, ggrid, H, E, dWg, dbg);
     RN_LAUNCH_CHECK();
   }
   // 7. projection weights / biases
   if ((r = sgemm_rm(st, true, false, dq, D, B * N, 1.f, dQ, dq, X, D, 0.f, dWq, D))) return r;
-  colsum_kernel<<<cdiv(dq, 128), 128, 0, st>>>(dQ, B * N, dq, dbq);
+  colsum_kernel<<<cdiv(dq, 32), dim3(32, 32), 0, st>>>(dQ, B * N, dq, dbq);
   RN_LAUNCH_CHECK();
-  colsum_kernel<<<cdiv(dq, 128), 128, 0, st>>>(dK, B * M, dq, dbk);
+  colsum_kernel<<<cdiv(dq, 32), dim3(32, 32), 0, st>>>(dK, B * M, dq, dbk);
   RN_LAUNCH_CHECK();
   if (key_index || M == N || B == 1) {
     // key rows are one contiguous [B*M, D] matrix (gathered copy, or X itself): a single GEMM each
@@ -281,9 +388,9 @@ extern "C" size_t rn_relation_bwd_workspace_bytes(const rn_relation_desc* d) {
   return rn::relation_bwd_ws_bytes(d) + 256;
 }
 
-extern "C" int rn_relation_bwd(const rn_relation_desc* d, const float* X, const float* boxes, const int32_t* key_index,
+extern "C" int rn_relation_bwd_masked(const rn_relation_desc* d, const float* X, const float* boxes, const int32_t* key_index,
                                const float* Wq, const float* bq, const float* Wk, const float* bk, const float* Wg,
-                               const float* bg, const float* Wout, const float* bout, const float* dOut, float* dX,
+                               const float* bg, const float* Wout, const float* bout, const float* out_fwd, const float* dOut, float* dX,
                                float* dWq, float* dbq, float* dWk, float* dbk, float* dWg, float* dbg, float* dWout,
                                float* dbout, void* ws, size_t ws_bytes, rn_stream_t stream) {
   int r = rn::relation_check_desc(d);
@@ -297,5 +404,14 @@ extern "C" int rn_relation_bwd(const rn_relation_desc* d, const float* X, const 
   // tcgen05 tf32 GEMM (gemm_tf32.cu: fp32 operands read by TMA, kind::tf32, fp32 accumulate), RN_PREC_FP32 = cuBLAS fp32
   rn::GemmBackendScope backend(d->precision == RN_PREC_F16 && rn::is_sm100() ? 1 : 0);
   return rn::relation_bwd(d, X, boxes, key_index, Wq, bq, Wk, bk, Wg, bg, Wout, bout, dOut, dX, dWq, dbq, dWk, dbk, dWg,
-                          dbg, dWout, dbout, ws, ws_bytes, (cudaStream_t)stream);
+                          dbg, dWout, dbout, ws, ws_bytes, (cudaStream_t)stream, nullptr, nullptr, out_fwd);
+}
+
+extern "C" int rn_relation_bwd(const rn_relation_desc* d, const float* X, const float* boxes, const int32_t* key_index,
+                               const float* Wq, const float* bq, const float* Wk, const float* bk, const float* Wg,
+                               const float* bg, const float* Wout, const float* bout, const float* dOut, float* dX,
+                               float* dWq, float* dbq, float* dWk, float* dbk, float* dWg, float* dbg, float* dWout,
+                               float* dbout, void* ws, size_t ws_bytes, rn_stream_t stream) {
+  return rn_relation_bwd_masked(d, X, boxes, key_index, Wq, bq, Wk, bk, Wg, bg, Wout, bout, nullptr, dOut, dX, dWq, dbq, dWk, dbk,
+                                dWg, dbg, dWout, dbout, ws, ws_bytes, stream);
 }

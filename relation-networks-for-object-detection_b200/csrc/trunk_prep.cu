@@ -7,6 +7,7 @@
 //   rn_maxpool3x3s2_nhwc_bf16   3x3 / stride 2 / ceil-mode max pool (pool1, same file) on a channels-last bf16 map
 // HBM roofline: bytes in + bytes out (7.2 MB + 4.9 MB; 19.2 MB + 4.8 MB); one thread handles 16 B of output channels.
 #include "common.cuh"
+#include "gemm_tc.cuh"
 #include <cuda_bf16.h>
 
 namespace rn {
@@ -127,7 +128,91 @@ __global__ void __launch_bounds__(256) rpn_head_kernel(const __nv_bfloat16* __re
   }
 }
 
+// ---- tensor-core form of the same head (the hot path).  The SIMT kernel above is 79 us at 38 x 63 x 512 -- alone on the
+// critical branch rpn_conv -> proposal (profiles/r02_timeline_step.json) -- because every FMA costs two shared loads; the
+// head is a [HW, Cin] x [Cin, 6A] GEMM, so it goes through the tcgen05 GEMM with bf16 operands exactly as cuDNN left them
+// (weights of both 1x1 convs concatenated once into one [6A, Cin] block), then one small kernel does the {bg, fg} softmax
+// and the position-fastest (NCHW) fp32 layout `proposal` reads.
+__global__ void rpn_pack_kernel(const __nv_bfloat16* __restrict__ Wc, const __nv_bfloat16* __restrict__ bc,
+                                const __nv_bfloat16* __restrict__ Wb, const __nv_bfloat16* __restrict__ bb, int Cin, int A,
+                                __nv_bfloat16* __restrict__ W, float* __restrict__ bias) {
+  const int NO = 6 * A;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < NO * Cin; i += gridDim.x * blockDim.x) {
+    const int o = i / Cin, k = i - o * Cin;
+    W[i] = o < 2 * A ? Wc[(size_t)o * Cin + k] : Wb[(size_t)(o - 2 * A) * Cin + k];
+  }
+  for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < NO; o += gridDim.x * blockDim.x)
+    bias[o] = __bfloat162float(o < 2 * A ? bc[o] : bb[o - 2 * A]);
+}
+
+// y [HW, NO] fp32 (bias added) -> prob [2A, HW] (softmax over {c, c +- A}), bbox [4A, HW]; 32 positions per CTA through smem
+__global__ void __launch_bounds__(256) rpn_finish_kernel(const float* __restrict__ y, int HW, int A, float* __restrict__ prob,
+                                                         float* __restrict__ bbox) {
+  extern __shared__ float ys[];                             // [32][NO + 1]
+  const int NO = 6 * A, p0 = blockIdx.x * 32;
+  for (int i = threadIdx.x; i < 32 * NO; i += blockDim.x) {
+    const int pp = i / NO, o = i - pp * NO;
+    ys[pp * (NO + 1) + o] = p0 + pp < HW ? y[(size_t)(p0 + pp) * NO + o] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NO * 32; i += blockDim.x) {
+    const int o = i >> 5, pp = i & 31;
+    if (p0 + pp >= HW) continue;
+    const float v = ys[pp * (NO + 1) + o];
+    if (o < 2 * A) {
+      const float other = ys[pp * (NO + 1) + (o < A ? o + A : o - A)];
+      const float m = fmaxf(v, other);
+      const float e = expf(v - m), eo = expf(other - m);
+      prob[(size_t)o * HW + p0 + pp] = e / (e + eo);
+    } else {
+      bbox[(size_t)(o - 2 * A) * HW + p0 + pp] = v;
+    }
+  }
+}
+
 }  // namespace rn
+
+extern "C" size_t rn_rpn_head_packed_bytes(int32_t Cin, int32_t A) {
+  if (Cin <= 0 || A <= 0) return 0;
+  return rn::ws_slice((size_t)6 * A * Cin, 2) + rn::ws_slice((size_t)6 * A, 4);
+}
+
+extern "C" int rn_rpn_head_pack(const void* Wcls_bf16, const void* bcls_bf16, const void* Wbbox_bf16, const void* bbbox_bf16,
+                                int32_t Cin, int32_t A, void* packed, rn_stream_t stream) {
+  RN_CHECK_ARG(Wcls_bf16 && bcls_bf16 && Wbbox_bf16 && bbbox_bf16 && packed && Cin > 0 && A >= 1, "rn_rpn_head_pack: bad arguments");
+  __nv_bfloat16* W = (__nv_bfloat16*)packed;
+  float* bias = (float*)((char*)packed + rn::ws_slice((size_t)6 * A * Cin, 2));
+  rn::rpn_pack_kernel<<<rn::cdiv(6 * A * Cin, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)Wcls_bf16, (const __nv_bfloat16*)bcls_bf16, (const __nv_bfloat16*)Wbbox_bf16,
+      (const __nv_bfloat16*)bbbox_bf16, Cin, A, W, bias);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
+
+extern "C" size_t rn_rpn_head_workspace_bytes(int32_t HW, int32_t Cin, int32_t A) {
+  if (HW <= 0 || Cin <= 0 || A <= 0) return 0;
+  return rn::ws_slice((size_t)HW * 6 * A, 4) + rn::gemm_tc_workspace_bytes(HW, 6 * A, Cin) + 512;
+}
+
+extern "C" int rn_rpn_head_packed_fwd(const void* r_nhwc_bf16, int32_t HW, int32_t Cin, int32_t A, const void* packed, float* prob,
+                                      float* bbox, void* wsp, size_t ws_bytes, rn_stream_t stream) {
+  using namespace rn;
+  RN_CHECK_ARG(r_nhwc_bf16 && packed && prob && bbox && wsp, "rn_rpn_head_packed_fwd: null pointer");
+  RN_CHECK_ARG(HW > 0 && Cin > 0 && Cin % 8 == 0 && A >= 1 && A <= 64, "rn_rpn_head_packed_fwd: need Cin %% 8 == 0 and A <= 64");
+  RN_CHECK_ARG(is_sm100(), "rn_rpn_head_packed_fwd: tcgen05 GEMM needs an sm_100 device (rn_rpn_head_fwd is the portable form)");
+  const int NO = 6 * A;
+  Workspace ws(wsp, ws_bytes);
+  float* y = ws.take<float>((size_t)HW * NO);
+  if (!y) { set_error("rn_rpn_head_packed_fwd: workspace too small (%zu < %zu)", ws_bytes, rn_rpn_head_workspace_bytes(HW, Cin, A)); return RN_ERR_WORKSPACE; }
+  const float* bias = (const float*)((const char*)packed + ws_slice((size_t)NO * Cin, 2));
+  cudaStream_t st = (cudaStream_t)stream;
+  int r = gemm_tc(st, (const __half*)r_nhwc_bf16, Cin, (const __half*)packed, Cin, HW, NO, Cin, bias, 0, 0, y, NO, nullptr, 0,
+                  ws.base + ws.off, ws.size - ws.off, nullptr, /*bf16=*/true);
+  if (r) return r;
+  rpn_finish_kernel<<<cdiv(HW, 32), 256, (size_t)32 * (NO + 1) * sizeof(float), st>>>(y, HW, A, prob, bbox);
+  RN_LAUNCH_CHECK();
+  return RN_OK;
+}
 
 extern "C" int rn_rpn_head_fwd(const void* r_nhwc_bf16, int32_t HW, int32_t Cin, int32_t A, const void* Wcls_bf16,
                                const void* bcls_bf16, const void* Wbbox_bf16, const void* bbbox_bf16, float* prob,

@@ -8,7 +8,7 @@ c_i32 = C.c_int32
 import torch
 from . import _lib as L
 
-PREC = {'fp32': 0, 'f16': 1, 0: 0, 1: 1}
+PREC = {'fp32': 0, 'f16': 1, 'tf32': 2, 0: 0, 1: 1, 2: 2}
 _ws = {}
 
 
@@ -191,9 +191,11 @@ def _grad_buffers(out, like):
 
 
 def relation_backward(grad_out, X, boxes, Wq, bq, Wk, bk, Wg, bg, Wout, bout, key_index=None, M=None, group=16,
-                      residual_relu=False, wave_length=1000.0, out=None, precision=None):
+                      residual_relu=False, wave_length=1000.0, out=None, precision=None, forward_out=None):
     """Gradients of `relation` (forward intermediates are recomputed) -- rn_relation_bwd.  precision: 'f16' (default on
     sm_100) = every contraction on the library's tcgen05 tf32 GEMM (fp32 operands, fp32 accumulate); 'fp32' = cuBLAS fp32.
+    forward_out: the output of the forward that was executed (any precision); with residual_relu its sign pattern is the relu
+    mask (autograd semantics) instead of the recomputed forward's -- they differ only for units within rounding of zero.
     Returns a dict with the gradient of X and of every parameter, shaped like the argument it belongs to."""
     precision = precision or default_precision()
     X = _f32(X, 'X'); boxes = _f32(boxes, 'boxes'); grad_out = _f32(grad_out, 'grad_out')
@@ -220,10 +222,15 @@ def relation_backward(grad_out, X, boxes, Wq, bq, Wk, bk, Wg, bg, Wout, bout, ke
     g = _grad_buffers(out, {'X': X, 'Wq': Wq, 'bq': bq, 'Wk': Wk, 'bk': bk, 'Wg': Wg, 'bg': bg, 'Wout': Wout, 'bout': bout})
     lib = L.lib()
     ws = _workspace(lib.rn_relation_bwd_workspace_bytes(C.byref(desc)), X.device)
-    L.check(lib.rn_relation_bwd(C.byref(desc), _ptr(X), _ptr(boxes), _ptr(kidx), _ptr(Wq), _ptr(bq), _ptr(Wk), _ptr(bk),
-                                _ptr(Wg), _ptr(bg), _ptr(Wout2), _ptr(bout), _ptr(grad_out), _ptr(g['X']), _ptr(g['Wq']),
-                                _ptr(g['bq']), _ptr(g['Wk']), _ptr(g['bk']), _ptr(g['Wg']), _ptr(g['bg']), _ptr(g['Wout']),
-                                _ptr(g['bout']), _ptr(ws), ws.numel(), _stream()), 'rn_relation_bwd')
+    fo = None
+    if forward_out is not None:
+        fo = _f32(forward_out, 'forward_out')
+        if fo.numel() != B * N * dout:
+            raise L.RelnetError('relation_backward: forward_out has %d elements, expected %d' % (fo.numel(), B * N * dout))
+    L.check(lib.rn_relation_bwd_masked(C.byref(desc), _ptr(X), _ptr(boxes), _ptr(kidx), _ptr(Wq), _ptr(bq), _ptr(Wk), _ptr(bk),
+                                       _ptr(Wg), _ptr(bg), _ptr(Wout2), _ptr(bout), _ptr(fo), _ptr(grad_out), _ptr(g['X']),
+                                       _ptr(g['Wq']), _ptr(g['bq']), _ptr(g['Wk']), _ptr(g['bk']), _ptr(g['Wg']), _ptr(g['bg']),
+                                       _ptr(g['Wout']), _ptr(g['bout']), _ptr(ws), ws.numel(), _stream()), 'rn_relation_bwd_masked')
     return g
 
 
@@ -760,7 +767,7 @@ def deform_im2col(im, offset, kernel=(3, 3), pad=(2, 2), stride=(1, 1), dilate=(
     return col
 
 
-def rpn_head(r, Wcls, bcls, Wbbox, bbbox):
+def rpn_head(r, Wcls, bcls, Wbbox, bbbox, simt=False):
     """RPN head after rpn_conv: r = channels-last bf16 [1,Cin,h,w]; 1x1 conv weights/biases bf16 -> (rpn_cls_prob [1,2A,h,w],
     rpn_bbox_pred [1,4A,h,w]) fp32 NCHW, the {bg, fg} softmax applied (rn_rpn_head_fwd)."""
     ts = (r, Wcls, bcls, Wbbox, bbbox)
@@ -773,6 +780,18 @@ def rpn_head(r, Wcls, bcls, Wbbox, bbbox):
         raise L.RelnetError('rpn_head: inconsistent weight shapes')
     prob = torch.empty((1, 2 * A, h, w), dtype=torch.float32, device=r.device)
     bbox = torch.empty((1, 4 * A, h, w), dtype=torch.float32, device=r.device)
+    lib = L.lib()
+    if device_info()['sm100'] and Cin % 8 == 0 and not simt:
+        # tensor-core form: one bf16 tcgen05 GEMM over the concatenated heads + a softmax / layout kernel
+        Wc, Wb = Wcls.contiguous(), Wbbox.contiguous()
+
+        def pack(buf):
+            L.check(lib.rn_rpn_head_pack(_ptr(Wc), _ptr(bcls), _ptr(Wb), _ptr(bbbox), Cin, A, _ptr(buf), _stream()), 'rn_rpn_head_pack')
+        packed = _packs.get((Wcls, bcls, Wbbox, bbbox), lib.rn_rpn_head_packed_bytes(Cin, A), pack, tag=('rpn_head',))
+        ws = _workspace(lib.rn_rpn_head_workspace_bytes(h * w, Cin, A), r.device)
+        L.check(lib.rn_rpn_head_packed_fwd(_ptr(r), h * w, Cin, A, _ptr(packed), _ptr(prob), _ptr(bbox), _ptr(ws), ws.numel(),
+                                           _stream()), 'rn_rpn_head_packed_fwd')
+        return prob, bbox
     L.check(L.lib().rn_rpn_head_fwd(_ptr(r), h * w, Cin, A, _ptr(Wcls.contiguous()), _ptr(bcls), _ptr(Wbbox.contiguous()),
                                     _ptr(bbbox), _ptr(prob), _ptr(bbox), _stream()), 'rn_rpn_head_fwd')
     return prob, bbox

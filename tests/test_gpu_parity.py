@@ -150,6 +150,26 @@ def test_relation_sweep_points(ops, N, d, H):
         assert rel_err(out, ref) < 1e-3
 
 
+@pytest.mark.parametrize('N,M,d,H,kidx', [(70, 50, 256, 4, False), (300, 300, 1024, 16, False), (131, 97, 256, 16, True),
+                                          (300, 300, 1024, 4, False)])
+def test_relation_tf32_forward_matches_oracle(ops, N, M, d, H, kidx):
+    """RN_PREC_TF32: the general (materialising) kernels with every GEMM on the library's tcgen05 tf32 engine -- the forward
+    that rn_relation_bwd recomputes.  Output and softmax against the float32 oracle at the relation tolerance 1e-3."""
+    if not ops.device_info()['sm100']:
+        pytest.skip('tcgen05 needs sm_100')
+    c = R.make_relation_case(N * 11 + d + H, N, d, H, M=None if (M == N or kidx) else M)
+    args = rel_args(c)
+    key_index = np.random.RandomState(N).permutation(N)[:M].astype(np.int32) if kidx else None
+    allr = R.relation_forward(*args, key_index=key_index if kidx else M, group=H, residual_relu=True, dtype=np.float32,
+                              return_all=True)
+    ref, ref_sm = allr['out'], allr['softmax']
+    out, sm = ops.relation(*[T(a) for a in args], key_index=T(key_index) if kidx else None, M=None if kidx else M, group=H,
+                           residual_relu=True, precision='tf32', return_softmax=True)
+    e, es = rel_err(out.cpu().numpy(), ref), rel_err(sm.cpu().numpy(), ref_sm)
+    print('tf32 forward N=%d M=%d d=%d H=%d: out %.2e softmax %.2e' % (N, M, d, H, e, es))
+    assert e < 1e-3 and es < 2e-3
+
+
 def test_relation_full_size_properties(ops):
     """N=3000, d=1024 (largest sweep point): oracle-free properties -- permutation equivariance and convexity of the
     aggregation (with Wout = I, bout = 0 every output row is a convex combination of the key rows)."""

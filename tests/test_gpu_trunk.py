@@ -80,6 +80,9 @@ def test_rpn_head_kernel_matches_module_path(ops):
     assert (prob - want_prob).abs().max().item() <= 1e-4                      # fp32 accumulate on both sides
     assert (bbox - want_bbox).abs().max().item() <= 1e-4 * max(1.0, want_bbox.abs().max().item())
     assert torch.allclose(prob[:, :12] + prob[:, 12:], torch.ones_like(prob[:, :12]), atol=1e-6)
+    # the portable SIMT form (rn_rpn_head_fwd) and the tcgen05 form (rn_rpn_head_packed_fwd, the default on sm_100) agree
+    ps, bs = ops.rpn_head(r, t.rpn_cls.weight, t.rpn_cls.bias, t.rpn_bbox.weight, t.rpn_bbox.bias, simt=True)
+    assert (ps - prob).abs().max().item() <= 1e-5 and (bs - bbox).abs().max().item() <= 1e-4 * max(1.0, bbox.abs().max().item())
     # HW not a multiple of the 32-position tile
     r2 = r[:, :, :5, :7].contiguous(memory_format=torch.channels_last)
     p2, b2 = ops.rpn_head(r2, t.rpn_cls.weight, t.rpn_cls.bias, t.rpn_bbox.weight, t.rpn_bbox.bias)
