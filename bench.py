@@ -273,15 +273,24 @@ def train_block(args, ts, images, im_info, device, world, rank, dist_on, mode):
     K, W = max(3, min(args.steps, 8)), 3
     for _ in range(W):
         ts.step(images, im_info)
-    # the exchange is a SUM: reduced bucket == sum over ranks of the local buckets (checked on a checksum of the bucket)
-    ts.step(images, im_info, exchange=False)
-    local = ts.bucket.flat.double().sum()
-    tot = local.clone()
+    # the exchange is a SUM: allreduce the bucket of ONE backward and compare it, element by element, with the sum of the
+    # ranks' own copies of that same bucket (gathered separately) -- independent of step-to-step atomics / ordering noise
+    ts.bucket.zero_()
+    for im in images:
+        ts.forward_backward(im, im_info)
+    local = ts.bucket.flat.clone()
     if dist_on:
-        dist.all_reduce(tot)
-    ts.step(images, im_info, exchange=True)
-    red = ts.bucket.flat.double().sum()
-    chk = float((red - tot).abs() / tot.abs().clamp_min(1e-30))
+        parts = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(parts, local)
+        want = torch.zeros_like(local, dtype=torch.float64)
+        for q in parts:
+            want += q.double()
+        del parts
+    else:
+        want = local.double()
+    ts.bucket.allreduce()
+    chk = float((ts.bucket.flat.double() - want).abs().max() / want.abs().max().clamp_min(1e-30))
+    del want, local
     torch.cuda.synchronize()
     if dist_on:
         dist.barrier()
@@ -295,9 +304,23 @@ def train_block(args, ts, images, im_info, device, world, rank, dist_on, mode):
     ms = e0.elapsed_time(e1) / K
     ms_ar = sorted(a.elapsed_time(b) for a, b in evs)[len(evs) // 2]
     ms = replicas.max_over_ranks(ms, device); ms_ar = replicas.max_over_ranks(ms_ar, device)
+    # the collective on its own (ranks aligned by a barrier first): what the exchange costs without the arrival skew of the
+    # eager backward that the in-step figure includes
+    ms_alone = 0.0
+    if dist_on:
+        al = []
+        for _ in range(5):
+            dist.barrier()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); ts.bucket.allreduce(); b.record()
+            torch.cuda.synchronize()
+            al.append(a.elapsed_time(b))
+        ms_alone = replicas.max_over_ranks(sorted(al)[len(al) // 2], device)
     nbytes = ts.bucket.flat.numel() * 4
     return dict(mode=mode, images_per_sec=round(world * len(images) / (ms / 1e3), 2), images_per_rank_per_step=len(images),
-                ms_per_step=round(ms, 3), allreduce_ms=round(ms_ar, 4), allreduce_bus_gbs=round(bus_gbs(nbytes, ms_ar, world), 1),
+                ms_per_step=round(ms, 3), allreduce_ms_in_step=round(ms_ar, 4), allreduce_ms=round(ms_alone, 4),
+                allreduce_bus_gbs=round(bus_gbs(nbytes, ms_alone, world), 1),
                 bucket_mb=round(nbytes / 1e6, 1), collectives_per_step=1 if dist_on else 0, reduce_op='sum (rescale_grad = 1.0)',
                 reduced_vs_sum_of_ranks_rel=chk, steps=K, warmup=W, rois=ts.last.get('rois'),
                 backward_contractions='tcgen05 tf32 GEMM (gemm_tf32.cu) in rn_relation_bwd / rn_learn_nms_bwd',

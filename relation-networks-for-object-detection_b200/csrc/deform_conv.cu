@@ -43,7 +43,11 @@ __device__ __forceinline__ DcSample dc_sample(const DcGeom& q, const float* __re
   return t;
 }
 
-constexpr int kDcTile = 64;                  // output positions per CTA
+constexpr int kDcTile = 64;                  // output positions per CTA (NCHW form and the backward kernels)
+// channels-last forms: 16 positions per CTA -> 4x the CTAs (600 at 38 x 63, 4 per SM).  The walk is a chain of table lookup ->
+// four dependent 16-byte taps per item, i.e. latency bound: at 64 positions the grid was 152 CTAs = 8 warps per SM and the
+// sampler took 31 us for 22 MB of output (profiles/r02_launches_deform.csv)
+constexpr int kDcTileCl = 16;
 
 // MODE 0: data NCHW fp32 -> col fp32 [C*kh*kw, Ho*Wo] (K index c*kh*kw + tap: the reference's column buffer, bit-comparable)
 // MODE 1: data NHWC fp32 / MODE 2: data NHWC bf16 -> colT fp16 [Ho*Wo, ldk] with K index tap*C + c (tap-major: the 8
@@ -56,11 +60,12 @@ __global__ void __launch_bounds__(256) deform_sample_kernel(DcGeom q, int C, int
   extern __shared__ __align__(16) unsigned char dc_smem[];
   DcSample* tab = reinterpret_cast<DcSample*>(dc_smem);
   const int taps = q.kh * q.kw, Nsp = q.Ho * q.Wo;
-  const int p0 = blockIdx.x * kDcTile, g = blockIdx.y;
-  const int npos = min(kDcTile, Nsp - p0);
+  constexpr int kTile = MODE == 0 ? kDcTile : kDcTileCl;
+  const int p0 = blockIdx.x * kTile, g = blockIdx.y;
+  const int npos = min(kTile, Nsp - p0);
   const float* off_g = off + (size_t)g * 2 * taps * Nsp;
-  for (int e = threadIdx.x; e < taps * kDcTile; e += blockDim.x) {
-    const int tap = e / kDcTile, px = e - tap * kDcTile;
+  for (int e = threadIdx.x; e < taps * kTile; e += blockDim.x) {
+    const int tap = e / kTile, px = e - tap * kTile;
     if (px < npos) tab[e] = dc_sample(q, off_g, tap, p0 + px);
   }
   __syncthreads();
@@ -73,7 +78,7 @@ __global__ void __launch_bounds__(256) deform_sample_kernel(DcGeom q, int C, int
       const float* d = im + (size_t)c * q.H * q.W;
       float* dst = col + ((size_t)c * taps) * Nsp + p0 + px;
       for (int tap = 0; tap < taps; ++tap) {
-        const DcSample t = tab[tap * kDcTile + px];
+        const DcSample t = tab[tap * kTile + px];
         dst[(size_t)tap * Nsp] = t.w1 * __ldg(d + t.o1) + t.w2 * __ldg(d + t.o2) + t.w3 * __ldg(d + t.o3) + t.w4 * __ldg(d + t.o4);
       }
     }
@@ -81,7 +86,7 @@ __global__ void __launch_bounds__(256) deform_sample_kernel(DcGeom q, int C, int
     const int nv = cpg / 8;                                // 8-channel vectors of the group
     for (int item = threadIdx.x; item < npos * taps * nv; item += blockDim.x) {
       const int cv = item % nv, pt = item / nv, tap = pt % taps, px = pt / taps;
-      const DcSample t = tab[tap * kDcTile + px];
+      const DcSample t = tab[tap * kTile + px];
       const int c0 = g * cpg + cv * 8;
       float v[4][8];
       const int o[4] = {t.o1, t.o2, t.o3, t.o4};
@@ -322,10 +327,11 @@ static int launch_sample(const rn_deform_conv_desc* d, int mode, const void* im,
                          int ldk, cudaStream_t st) {
   const DcGeom q = dc_geom(d);
   const int taps = d->kh * d->kw, cpg = d->C / d->num_deformable_group;
-  const size_t smem = sizeof(DcSample) * taps * kDcTile;
+  const int tile = mode == 0 ? kDcTile : kDcTileCl;
+  const size_t smem = sizeof(DcSample) * taps * tile;
   RN_CHECK_ARG(smem <= 96 * 1024, "deformable conv: kernel %dx%d too large for the sample table", d->kh, d->kw);
   RN_CHECK_ARG(mode == 0 || (cpg % 8 == 0 && d->C % 8 == 0), "deformable conv (channels-last): C / num_deformable_group must be a multiple of 8");
-  const dim3 grid(cdiv(q.Ho * q.Wo, kDcTile), d->num_deformable_group);
+  const dim3 grid(cdiv(q.Ho * q.Wo, tile), d->num_deformable_group);
   if (smem > 48 * 1024) {
     RN_CUDA(cudaFuncSetAttribute(deform_sample_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     RN_CUDA(cudaFuncSetAttribute(deform_sample_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -299,6 +299,8 @@ int gemm_tc(cudaStream_t st, const __half* A, long long lda, const __half* B, lo
   // BN = 64 when 128-wide tiles would leave most SMs idle -- unless K is long (fc_new_1: K = 12544): then split-K fills the
   // machine anyway and the 128-wide tile moves a third fewer operand bytes per output (per-SM L2 ingest is the bound)
   const int kb = cdiv(K, kBK);
+  // (tried for the deformable-conv GEMM, 19 x 4 tiles of 128 on 76 of 148 SMs: 19 x 8 tiles of 64 = 152 units need a second
+  // wave on 148 SMs and measured slower, 58 -> 67 us per layer)
   const bool bn64 = ((tiles_m * cdiv(N, 128) < sms / 2) && kb < 64) || N <= 64;
   const int BN = bn64 ? 64 : 128;
   const int tiles = tiles_m * cdiv(N, BN);

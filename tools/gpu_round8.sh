@@ -1,0 +1,15 @@
+#!/bin/bash
+tag=${1:-run}; out=gpurun_out/$tag; mkdir -p $out; export PYTHONUNBUFFERED=1
+timeout 400 python -m pytest tests/test_gpu_refpin.py tests/test_gpu_parity.py tests/test_gpu_pipelines.py -q -rA --timeout 300 --timeout-method thread -k "psroi or deformable" > $out/pytest_psroi.log 2>&1; echo "pytest rc=$?"
+grep -E "passed|failed|FAILED|PS-ROI" $out/pytest_psroi.log | tail
+timeout 200 python tools/psroi_bench.py 2>/dev/null | tee $out/psroi_bench.jsonl
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $out/launches_deform.csv python tools/deform_bench.py > $out/deform.log 2>&1
+python - <<PY
+import csv
+rows=list(csv.reader(open('$out/launches_deform.csv')))
+for i,r in enumerate(rows):
+    if 'Kernel Name' in r: h=r; start=i; break
+ix={k:i for i,k in enumerate(h)}
+for r in rows[start+2:][-14:]:
+    if len(r)>=len(h): print(r[ix['Kernel Name']].split('(')[0][-50:], float(r[ix['Metric Value']])/1000, r[ix['Grid Size']])
+PY
