@@ -273,6 +273,26 @@ def train_block(args, ts, images, im_info, device, world, rank, dist_on, mode):
     K, W = max(3, min(args.steps, 8)), 3
     for _ in range(W):
         ts.step(images, im_info)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        ts.step(images, im_info)
+    e1.record()
+    torch.cuda.synchronize()
+    eager_ms = replicas.max_over_ranks(e0.elapsed_time(e1) / 3, device)
+    # the accumulate phase (zero + fwd + bwd of every micro-batch) as ONE CUDA graph; the allreduce + SGD update follow the replay
+    launch = 'one CUDA-graph replay for the whole forward + backward (library trunk autograd + the C-ABI fwd/bwd pairs), then the ' \
+             'NCCL allreduce and the SGD update; allreduce after backward, not overlapped'
+    try:
+        ts.capture(images, im_info)
+        for _ in range(W):
+            ts.step(images, im_info)
+        torch.cuda.synchronize()
+    except Exception as e:           # stay measurable: report the eager step and say why
+        ts.graph = None
+        launch = 'eager (graph capture failed: %s)' % (str(e).splitlines()[0][:160] if str(e) else type(e).__name__)
+        torch.cuda.synchronize()
     # the exchange is a SUM: allreduce the bucket of ONE backward and compare it, element by element, with the sum of the
     # ranks' own copies of that same bucket (gathered separately) -- independent of step-to-step atomics / ordering noise
     ts.bucket.zero_()
@@ -323,9 +343,9 @@ def train_block(args, ts, images, im_info, device, world, rank, dist_on, mode):
                 allreduce_bus_gbs=round(bus_gbs(nbytes, ms_alone, world), 1),
                 bucket_mb=round(nbytes / 1e6, 1), collectives_per_step=1 if dist_on else 0, reduce_op='sum (rescale_grad = 1.0)',
                 reduced_vs_sum_of_ranks_rel=chk, steps=K, warmup=W, rois=ts.last.get('rois'),
-                backward_contractions='tcgen05 tf32 GEMM (gemm_tf32.cu) in rn_relation_bwd / rn_learn_nms_bwd',
-                launch='eager (torch autograd for the library trunk + the C-ABI fwd/bwd pairs of the hot path); allreduce after '
-                       'backward, not overlapped',
+                contractions='forward (general kernels) and backward of the relation / learn-NMS ops on the tcgen05 tf32 GEMM '
+                             '(gemm_tf32.cu); no cuBLAS in the hot path',
+                launch=launch, eager_ms_per_step=round(eager_ms, 3),
                 losses={k: (round(v, 4) if isinstance(v, float) else v) for k, v in ts.last.items() if k != 'rois'})
 
 

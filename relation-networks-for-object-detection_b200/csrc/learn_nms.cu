@@ -390,6 +390,10 @@ extern "C" int rn_learn_nms_fwd(const rn_learn_nms_desc* d, const float* cls_sco
                                 const rn_learn_nms_weights* w, const int32_t* non_gt_index, float* nms_multi_score,
                                 float* sorted_bbox, float* sorted_score, float* final_score, void* wsp, size_t ws_bytes,
                                 rn_stream_t stream) {
+  // RN_PREC_TF32: the general kernels of RN_PREC_FP32 with every GEMM on the library's tcgen05 tf32 engine (the forward that
+  // rn_learn_nms_bwd recomputes under RN_PREC_F16); inside a backward the caller's engine stays in force
+  RN_CHECK_ARG(d && (d->precision != RN_PREC_TF32 || rn::is_sm100()), "rn_learn_nms_fwd: RN_PREC_TF32 needs an sm_100 device");
+  rn::GemmBackendScope backend(d->precision == RN_PREC_TF32 ? 1 : rn::gemm_backend());
   return rn::lnms_forward(d, cls_score, bbox_pred, rois, im_info, feat, w, nullptr, nullptr, nullptr, non_gt_index, nms_multi_score,
                           sorted_bbox, sorted_score, final_score, wsp, ws_bytes, stream);
 }

@@ -41,7 +41,14 @@ class TrainStep(object):
                                device=device)
         self.rpn_label = None
         self.gen = g
-        self.last = {}
+        self._last = {}
+        self.graph = None            # set by capture(): the whole accumulate phase (zero + fwd + bwd of every micro-batch) as ONE CUDA graph
+        self.fwd_precision = 'tf32' if ops.device_info()['sm100'] else 'fp32'   # general kernels, GEMMs on the tcgen05 tf32 engine
+
+    @property
+    def last(self):
+        """losses of the most recent step as Python numbers (one host sync, outside the step)"""
+        return {k: (float(v) if isinstance(v, torch.Tensor) else v) for k, v in self._last.items()}
 
     # ------------------------------------------------------------------------------------------------ one image
     def forward_backward(self, image32, im_info):
@@ -76,7 +83,7 @@ class TrainStep(object):
         rel = lambda x, i: AG.relation(x, boxes, P['query_%d_weight' % i], P['query_%d_bias' % i], P['key_%d_weight' % i],
                                        P['key_%d_bias' % i], P['pair_pos_fc1_%d_weight' % i], P['pair_pos_fc1_%d_bias' % i],
                                        P['linear_out_%d_weight' % i], P['linear_out_%d_bias' % i], M=self.nongt_dim, group=16,
-                                       residual_relu=True, precision='fp32')
+                                       residual_relu=True, precision=self.fwd_precision)
         a1 = rel(fc1, 1)                                                                          # :346-351
         with torch.autocast('cuda', dtype=torch.bfloat16):
             fc2 = F.linear(a1, P['fc_new_2_weight'], P['fc_new_2_bias']).float()
@@ -87,21 +94,51 @@ class TrainStep(object):
         bbox_loss = (F.smooth_l1_loss(bbox_pred, bbox_target, reduction='none', beta=1.0) * bbox_weight).sum() / rois.shape[0]
         multi, sbbox, sscore = AG.learn_nms(cls_score, bbox_pred, rois, im_info, a2, {k: P[k] for k in NMS_NAMES},
                                             first_n=self.first_n, means=(0, 0, 0, 0), stds=(0.1, 0.1, 0.2, 0.2),
-                                            nongt_dim=self.nongt_dim)                             # :424-501 (train graph)
+                                            nongt_dim=self.nongt_dim, precision=self.fwd_precision)   # :424-501 (train graph)
         with torch.no_grad():
             target = ops.nms_multi_target(sbbox, self.gt, sscore, [0.5, 0.6, 0.7, 0.8, 0.9])      # :537-538
             pos, neg, d_multi = ops.nms_loss(multi.detach(), target)                              # :539-551
         torch.autograd.backward([rpn_cls_loss + rpn_bbox_loss + cls_loss + bbox_loss, multi], [None, d_multi])
-        self.last = dict(rpn_cls=float(rpn_cls_loss), cls=float(cls_loss), bbox=float(bbox_loss),
-                         nms=float(pos.sum() + neg.sum()), rois=int(rois.shape[0]))
+        # loss values stay on the device (no host sync inside the step: it must be capturable); `last` reads them on demand
+        self._last = dict(rpn_cls=rpn_cls_loss.detach(), cls=cls_loss.detach(), bbox=bbox_loss.detach(),
+                          nms=(pos.sum() + neg.sum()).detach(), rois=int(rois.shape[0]))
+
+    def accumulate(self, images32, im_info):
+        """bucket <- sum over this rank's micro-batches of the gradients (zero, then fwd + bwd per image)"""
+        self.bucket.zero_()
+        for im in images32:
+            self.forward_backward(im, im_info)
+
+    def capture(self, images32, im_info, warmup=3):
+        """Capture the accumulate phase as ONE CUDA graph (every launch of the step -- the library trunk's autograd, the C-ABI
+        forward / backward pairs, the memsets -- is allocation-free after warm-up and host-sync-free); step() then replays it and
+        runs the allreduce + SGD update behind it.  The eager step is CPU bound (≈20 ms of launches for ≈8 ms of GPU work)."""
+        self._static_images = [im.clone() for im in images32]
+        self._static_info = im_info.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.accumulate(self._static_images, self._static_info)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.accumulate(self._static_images, self._static_info)
+        self.graph = g
+        return self
 
     # ------------------------------------------------------------------------------------------------ one step
     def step(self, images32, im_info, exchange=True):
         """images32: list of `micro_batches` fp32 [1,3,H,W] images of this rank (gradients accumulate locally, like the
         reference's 2 images per GPU in the FPN config); then ONE allreduce, then the SGD update."""
-        self.bucket.zero_()
-        for im in images32:
-            self.forward_backward(im, im_info)
+        if self.graph is not None:
+            for dst, src in zip(self._static_images, images32):
+                if dst.data_ptr() != src.data_ptr():
+                    dst.copy_(src, non_blocking=True)
+            self.graph.replay()
+        else:
+            self.accumulate(images32, im_info)
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         ev[0].record()
         if exchange:
@@ -133,6 +170,13 @@ class FPNTrainStep(TrainStep):
         w = np.minimum(sz * np.sqrt(ar), W - 2); h = np.minimum(sz / np.sqrt(ar), H - 2)
         x1 = rng.uniform(0, 1, num_rois) * (W - 1 - w); y1 = rng.uniform(0, 1, num_rois) * (H - 1 - h)
         self.rois_in = torch.tensor(np.stack([np.zeros(num_rois), x1, y1, x1 + w, y1 + h], 1), dtype=torch.float32, device=device)
+        # pyramid dispatch of the (given, fixed) rois: done once on the host side, like the reference's loader (core/rcnn.py:153-223)
+        from .pipeline import fpn_level
+        with torch.no_grad():
+            rois0 = ops.proposal_target(self.rois_in, self.gt)[0]
+            lvl = fpn_level(rois0)
+            self._idx = [torch.nonzero(lvl == l).flatten() for l in range(4)]
+            self._inv = torch.argsort(torch.cat(self._idx))
 
     def forward_backward(self, image32, im_info):
         from .pipeline import fpn_level
@@ -151,9 +195,7 @@ class FPNTrainStep(TrainStep):
         with torch.no_grad():
             rois, label, bbox_target, bbox_weight = ops.proposal_target(self.rois_in, self.gt)     # appends the gt rows
             boxes = rois[:, 1:].contiguous()
-            lvl = fpn_level(rois)
-            idx = [torch.nonzero(lvl == l).flatten() for l in range(4)]
-            inv = torch.argsort(torch.cat(idx))
+            idx, inv = self._idx, self._inv
         parts = [AG.roi_pool(feats[l].float().contiguous(), rois[idx[l]].contiguous(), (7, 7), 1.0 / self.STRIDES[l])
                  for l in range(4) if idx[l].numel()]                                             # SYM_FPN_REL_NMS:1108-1115
         pooled = torch.cat(parts, 0)[inv]
@@ -162,7 +204,7 @@ class FPNTrainStep(TrainStep):
         rel = lambda x, i: AG.relation(x, boxes, P['query_%d_weight' % i], P['query_%d_bias' % i], P['key_%d_weight' % i],
                                        P['key_%d_bias' % i], P['pair_pos_fc1_%d_weight' % i], P['pair_pos_fc1_%d_bias' % i],
                                        P['linear_out_%d_weight' % i], P['linear_out_%d_bias' % i], M=self.nongt_dim, group=16,
-                                       residual_relu=True, precision='fp32')
+                                       residual_relu=True, precision=self.fwd_precision)
         a1 = rel(fc1, 1)                                                                          # :1122-1133
         with torch.autocast('cuda', dtype=torch.bfloat16):
             fc2 = F.linear(a1, P['fc_new_2_weight'], P['fc_new_2_bias']).float()                  # roi_pool_fc2 :1138
@@ -173,13 +215,13 @@ class FPNTrainStep(TrainStep):
         bbox_loss = (F.smooth_l1_loss(bbox_pred, bbox_target, reduction='none', beta=1.0) * bbox_weight).sum() / rois.shape[0]
         multi, sbbox, sscore = AG.learn_nms(cls_score, bbox_pred, rois, im_info, a2, {k: P[k] for k in NMS_NAMES},
                                             first_n=self.first_n, means=(0, 0, 0, 0), stds=(0.1, 0.1, 0.2, 0.2),
-                                            nongt_dim=self.nongt_dim)
+                                            nongt_dim=self.nongt_dim, precision=self.fwd_precision)
         with torch.no_grad():
             target = ops.nms_multi_target(sbbox, self.gt, sscore, [0.5, 0.6, 0.7, 0.8, 0.9])
             pos, neg, d_multi = ops.nms_loss(multi.detach(), target)
         torch.autograd.backward([cls_loss + bbox_loss, multi], [None, d_multi])
-        self.last = dict(cls=float(cls_loss), bbox=float(bbox_loss), nms=float(pos.sum() + neg.sum()), rois=int(rois.shape[0]),
-                         per_level=[int(i.numel()) for i in idx])
+        self._last = dict(cls=cls_loss.detach(), bbox=bbox_loss.detach(), nms=(pos.sum() + neg.sum()).detach(),
+                          rois=int(rois.shape[0]), per_level=[int(i.numel()) for i in idx])
 
 
 def bus_gbs(nbytes, ms, world):
