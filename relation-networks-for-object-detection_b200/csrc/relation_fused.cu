@@ -199,35 +199,14 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
     __syncwarp();
     tmem_alloc<512>(tmem_slot);
   } else {
-    // B operand of the pair FC: Wg [16 head rows (>= H zero)] x [64] as fp16 hi / lo, K-major SWIZZLE_128B
-    if (tid < 128) {
-      const int row = tid >> 3, chunk = tid & 7;
-      uint32_t hi[4], lo[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float w0 = row < HR ? p.Wg[row * 64 + chunk * 8 + 2 * j] : 0.f;
-        const float w1 = row < HR ? p.Wg[row * 64 + chunk * 8 + 2 * j + 1] : 0.f;
-        split2_f(w0, w1, &hi[j], &lo[j]);
-      }
-      *reinterpret_cast<uint4*>(sBh + sw128_offset(row, chunk)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<uint4*>(sBl + sw128_offset(row, chunk)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-    }
     // per-head bound sum|Wg[h,:]| + |bg[h]| (fixed summation order: every CTA gets the same bits)
-    {
-      float a = 0.f;
-      if (warp < HR) a = fabsf(p.Wg[warp * 64 + lane]) + fabsf(p.Wg[warp * 64 + 32 + lane]);
+    float a = 0.f;
+    if (warp < HR) a = fabsf(p.Wg[warp * 64 + lane]) + fabsf(p.Wg[warp * 64 + 32 + lane]);
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-      if (lane == 0) {
-        s_rowabs[warp] = warp < HR ? a + fabsf(p.bg[warp]) : 0.f;
-        s_bias[warp] = warp < HR ? p.bg[warp] : 0.f;
-      }
-    }
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) s_rowabs[warp] = warp < HR ? a + fabsf(p.bg[warp]) : 0.f;
   }
-  fence_proxy_async_smem();
-  tc_fence_before();
   __syncthreads();
-  tc_fence_after();
   if (tid == 0) {
     float gm = 1e-6f;
     for (int i = 0; i < 16; ++i) gm = fmaxf(gm, s_rowabs[i]);
@@ -236,17 +215,41 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
     s_gscale = exp2f((float)(15 - e));       // g * scale <= 2^15 ; 1e-6 * scale stays a normal fp16 for gm < 512
   }
   __syncthreads();
+  const float gscale = s_gscale;
+  if (warp < 16) {
+    // B operand of the pair FC: scale * Wg [16 head rows (>= H zero)] x [64] as fp16 hi / lo, K-major SWIZZLE_128B.  The power-of-two
+    // scale that puts g into fp16's normal range is folded into the weights and the bias here (exact), not applied per element
+    if (tid < 128) {
+      const int row = tid >> 3, chunk = tid & 7;
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float w0 = row < HR ? p.Wg[row * 64 + chunk * 8 + 2 * j] * gscale : 0.f;
+        const float w1 = row < HR ? p.Wg[row * 64 + chunk * 8 + 2 * j + 1] * gscale : 0.f;
+        split2_f(w0, w1, &hi[j], &lo[j]);
+      }
+      *reinterpret_cast<uint4*>(sBh + sw128_offset(row, chunk)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(sBl + sw128_offset(row, chunk)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+    if (tid < 16) s_bias[tid] = tid < HR ? p.bg[tid] * gscale : 0.f;
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
   RN_TRACE(2);                              // prologue done
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base, tG = tmem_base + 128, tPV = tmem_base + 384;       // S 128 | pair FC 8 keys x 32 | PV 64
-  const float gscale = s_gscale;
+  const float gfloor = 1e-6f * gscale;      // the reference's max(., 1e-6) in the scaled domain
 
   if (warp == 16) {
     // ============================================================================================ TMA + UMMA issuer
     if (lane == 0) {
       const uint32_t idesc_s = make_idesc_f16(128, 128, false, false, false);
       const uint32_t idesc_o = make_idesc_f16(128, 64, false, false, true);
-      const uint32_t idesc_g = make_idesc_f16(128, 32, false, false, false);     // [W_hi; W_lo] stacked: one UMMA per K step
+      // [W_hi; W_lo] stacked as 32 B rows: ONE UMMA per K step (two N = 16 UMMAs into one accumulator were measured: the per-
+      // instruction cost of an M = 128 UMMA is its A read, so doubling the count put ~1 k cycles per block on the g_full wait)
+      const uint32_t idesc_g = make_idesc_f16(128, 32, false, false, false);
       const uint32_t idesc_gl = make_idesc_f16(128, 16, false, false, false);    // LO: A_lo . W_hi into the hi columns
       const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
       const uint32_t bh = smem_u32(sBh);
@@ -578,7 +581,7 @@ __global__ void __launch_bounds__(kFThreads, 1) relation_fused_kernel(const __gr
             uint32_t pk[4];
 #pragma unroll
             for (int i2 = 0; i2 < 4; ++i2)
-              pk[i2] = pack_h2(fmaxf(gsum[2 * i2][q] + bb, 1e-6f) * gscale, fmaxf(gsum[2 * i2 + 1][q] + bb, 1e-6f) * gscale);
+              pk[i2] = pack_h2(fmaxf(gsum[2 * i2][q] + bb, gfloor), fmaxf(gsum[2 * i2 + 1][q] + bb, gfloor));
             *reinterpret_cast<uint4*>(slot + ((size_t)hh * 128 + r) * ks + rd * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }
         }

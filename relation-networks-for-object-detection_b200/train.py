@@ -34,7 +34,13 @@ class TrainStep(object):
         self.params = {'trunk.' + n: q for n, q in self.trunk.named_parameters() if q.requires_grad}
         self.params.update(self.head)
         for n, q in self.params.items():
-            q.grad = self.bucket.views[n]                            # autograd accumulates in place into the bucket windows
+            # autograd accumulates in place into the bucket windows.  A channels-last conv weight gets a window with ITS strides
+            # (same bytes, dense permutation): otherwise every accumulation converts the layout (one extra kernel per weight)
+            v = self.bucket.views[n]
+            if q.dim() == 4 and not q.is_contiguous() and q.is_contiguous(memory_format=torch.channels_last):
+                v = v.view(-1).as_strided(q.shape, q.stride())
+                self.bucket.views[n] = v
+            q.grad = v
         self.state = {}
         g = torch.Generator().manual_seed(seed + 17)
         self.gt = torch.tensor([[100. + 90 * i, 60. + 50 * i, 260. + 90 * i, 300. + 50 * i, 1. + (i % 80)] for i in range(num_gt)],
