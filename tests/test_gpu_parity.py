@@ -263,8 +263,11 @@ def test_nms_matches_oracle_and_reference_kernel(ops):
     if RO.ref_gpu_nms_available():
         # the REFERENCE's own lib/nms/nms_kernel.cu (oracle/_ref), run on this GPU
         np.testing.assert_array_equal(k, RO.ref_gpu_nms(dets, 0.7))
-    keep2, num2 = ops.nms(T(dets), 0.7, max_keep=50)
-    np.testing.assert_array_equal(keep2.cpu().numpy()[:int(num2.item())], k[:50])
+    # early exit at max_keep: the list must be the prefix of the full sweep's list
+    for mk in (50, 300, 2000):
+        keep2, num2 = ops.nms(T(dets), 0.7, max_keep=mk)
+        assert int(num2.item()) == min(mk, len(k))
+        np.testing.assert_array_equal(keep2.cpu().numpy()[:int(num2.item())], k[:mk])
     # edge cases: single box, all identical boxes
     keep3, num3 = ops.nms(T(dets[:1]), 0.7)
     assert int(num3.item()) == 1
