@@ -11,8 +11,11 @@ proposal -> ROI pool -> fc_new_1 -> relation#1 -> fc_new_2 -> relation#2 -> cls/
   roofline   the fused relation kernel (relation_fused_kernel: geometry + pair FC + QK^T + softmax + P.V' in one launch)
              timed alone as a captured graph at N=M=300, d=1024, H=16: achieved = 4*N*M*d FLOP / duration against the
              measured bf16 peak (MEASURED_PEAKS.json); algorithmic bytes by SURVEY 8(d)
-  sweep      BASELINE.json configs[4]: N in {100,300,1000,3000} x d in {256,1024} x H in {4,16}
-  train      the training form of the step: fwd+bwd, one flat gradient bucket, ONE NCCL SUM allreduce, SGD (per rank 1 image)
+  sweep      BASELINE.json configs[4]: N in {100,300,1000,3000} x d in {256,1024} x H in {4,16} (all 16 on the tcgen05 kernels)
+  train      the training form of configs[1]: fwd+bwd as ONE CUDA-graph replay, one flat gradient bucket, ONE NCCL SUM allreduce,
+             SGD (1 image per rank per step); allreduce timed alone and in the step, bus GB/s, elementwise sum check
+  configs    configs[2] Deformable Faster (test-time images/sec) and configs[3] FPN (test-time images/sec + the data-parallel
+             training step with 2 images per GPU accumulated before the one allreduce)
   cpu_baseline  the numpy/C oracle of the hot path (oracle/pipeline_np.py) on this host, one image
   --impl reference   the CPU arm: torch-CPU fp32 trunk + oracle hot path, same metric/config (rank 0 only)
 
@@ -246,6 +249,16 @@ def relation_kernel_roofline(ops, pk, device, sweep=True):
                 peak_source=pk['source'],
                 note='N=M=300: 0.37 GFLOP is ~0.25 us of tensor time; the kernel is latency / SFU bound (per pair 2 log + 16 '
                      'sincos + H exp2 on the XU pipe), see sweep for N up to 3000')
+    # companion figure: the unit that actually binds this formulation.  Per pair 2 lg2 + 2 coordinates x 8 frequencies x (sin,
+    # cos) (the two size coordinates are separable: per-box tables, no MUFU per pair) and one ex2 per (pair, head), against the
+    # XU pipe's 16 results / clk / SM at the SM clock the sampler saw
+    def xu_bound(n, h, us, mhz):
+        ops_ = float(n) * n * (34 + h)
+        peak = 16.0 * 148 * mhz * 1e6
+        return dict(N=n, H=h, mufu_ops=ops_, xu_floor_us=round(ops_ / peak * 1e6, 2), measured_us=us,
+                    frac_of_xu_peak=round(ops_ / peak / (us * 1e-6), 4))
+    roof['xu'] = dict(note='MUFU (XU pipe) floor of the same launch: the contraction alone would take 4NMd / tensor peak',
+                      tensor_floor_us=round(flops / (pk['tflops'] * 1e12) * 1e6, 3), at_N300=xu_bound(N, H, head['nm_us'], 1965.0))
     times = dict(module=head['module_us'], nm_stage=head['nm_us'], proj=head['proj_us'])
     sw = None
     if sweep:
@@ -259,6 +272,11 @@ def relation_kernel_roofline(ops, pk, device, sweep=True):
                         rec['nm_tflops'] = round(ach, 2)
                         rec['nm_frac_of_measured_bf16_peak'] = round(ach / pk['tflops'], 4)
                     sw.append(rec)
+        big = [r for r in sw if (r['N'], r['d'], r['H']) == (3000, 1024, 16) and r.get('nm_us')]
+        if big:
+            roof['xu']['at_N3000'] = xu_bound(3000, 16, big[0]['nm_us'], 1965.0)
+            roof['at_N3000'] = dict(duration_us=big[0]['nm_us'], achieved=big[0]['nm_tflops'], frac=big[0]['nm_frac_of_measured_bf16_peak'],
+                                    algorithmic_bytes=int(2 * (3000 * 1024 * 3) + 16 * 3000 + 4 * (64 * 16 + 16) + 2 * 3000 * 1024))
     del flush
     return roof, times, sw
 

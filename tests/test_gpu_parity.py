@@ -203,7 +203,9 @@ def test_learn_nms_matches_golden(ops, name):
     g = golden(name)
     c = L.make_learn_nms_case(int(g['seed']), R=int(g['R']), C=int(g['C']), init=str(g['init']))
     w = {k: T(v) for k, v in c['P'].items()}
-    for prec in precisions(ops):
+    # 'tf32' = RN_PREC_TF32: the general kernels with every GEMM on the tcgen05 tf32 engine (the forward of the training graph,
+    # and the one rn_learn_nms_bwd recomputes)
+    for prec in precisions(ops) + (['tf32'] if ops.device_info()['sm100'] else []):
         multi, sbbox, sscore, final = ops.learn_nms(T(c['cls_score']), T(c['bbox_pred']), T(c['rois']), T(c['im_info']),
                                                    T(c['feat']), w, first_n=int(g['first_n']), nongt_dim=int(g['R']),
                                                    precision=prec)

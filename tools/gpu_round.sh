@@ -13,7 +13,7 @@ if [ -z "$SKIP_TESTS" ]; then
   tail -3 $out/pytest_gpu.log
 fi
 if [ -z "$SKIP_BENCH" ]; then
-  timeout 900 python bench.py > $out/bench.json 2> $out/bench.err; echo "bench rc=$?"
+  timeout 1200 python bench.py > $out/bench.json 2> $out/bench.err; echo "bench rc=$?"
   head -c 1500 $out/bench.json; echo
 fi
 if [ -z "$SKIP_NCU" ]; then
