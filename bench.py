@@ -50,6 +50,9 @@ def parse():
     ap.add_argument('--no-sweep', action='store_true', help='skip the relation-module roofline sweep (configs[4])')
     ap.add_argument('--no-train', action='store_true', help='skip the data-parallel training blocks (gradient allreduce)')
     ap.add_argument('--no-configs', action='store_true', help='skip the configs[2] (Deformable) and configs[3] (FPN) blocks')
+    ap.add_argument('--extras-budget', type=float, default=float(os.environ.get('RELNET_EXTRAS_BUDGET_S', '150')),
+                    help='seconds the optional blocks (configs[2]/[3], training steps) may take after the headline measurement; past '
+                         'it every rank stops and rank 0 prints the line without them')
     return ap.parse_args()
 
 
@@ -281,42 +284,44 @@ def relation_kernel_roofline(ops, pk, device, sweep=True):
     return roof, times, sw
 
 
-def train_block(args, ts, images, im_info, device, world, rank, dist_on, mode):
+def train_block(args, ts, images, im_info, device, world, rank, dist_on, mode, report=None):
     """Training form of a config: fwd + bwd of `len(images)` images per rank (trunk res3+ by torch/cuDNN autograd, the hot path
     through the C-ABI forward / backward pairs), ONE flat gradient bucket, ONE NCCL SUM allreduce per step, SGD update.
-    Reports ms/step (max over ranks), the allreduce's own milliseconds and bus bandwidth, the bucket size."""
+    Reports ms/step (max over ranks), the allreduce's own milliseconds and bus bandwidth, the bucket size.
+    Order: the EAGER step is measured first, with the collective's cost and the sum check, and handed to `report` (rank 0 puts
+    it into the bench line at once); only then the step is captured as a CUDA graph and measured again."""
     from relnet_b200 import replicas
     from relnet_b200.train import bus_gbs
     import torch.distributed as dist
     K, W = max(3, min(args.steps, 8)), 3
+    nbytes = ts.bucket.flat.numel() * 4
+
+    def timed_steps(k):
+        torch.cuda.synchronize()
+        if dist_on:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        evs = []
+        e0.record()
+        for _ in range(k):
+            evs.append(ts.step(images, im_info))
+        e1.record()
+        torch.cuda.synchronize()
+        ms_ = replicas.max_over_ranks(e0.elapsed_time(e1) / k, device)
+        ar_ = replicas.max_over_ranks(sorted(a.elapsed_time(b) for a, b in evs)[len(evs) // 2], device)
+        return ms_, ar_
+
+    # ---- eager
     for _ in range(W):
         ts.step(images, im_info)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(3):
-        ts.step(images, im_info)
-    e1.record()
-    torch.cuda.synchronize()
-    eager_ms = replicas.max_over_ranks(e0.elapsed_time(e1) / 3, device)
-    # the accumulate phase (zero + fwd + bwd of every micro-batch) as ONE CUDA graph; the allreduce + SGD update follow the replay
-    launch = 'one CUDA-graph replay for the whole forward + backward (library trunk autograd + the C-ABI fwd/bwd pairs), then the ' \
-             'NCCL allreduce and the SGD update; allreduce after backward, not overlapped'
-    try:
-        ts.capture(images, im_info)
-        for _ in range(W):
-            ts.step(images, im_info)
-        torch.cuda.synchronize()
-    except Exception as e:           # stay measurable: report the eager step and say why
-        ts.graph = None
-        launch = 'eager (graph capture failed: %s)' % (str(e).splitlines()[0][:160] if str(e) else type(e).__name__)
-        torch.cuda.synchronize()
+    eager_ms, eager_ar = timed_steps(max(3, K // 2))
     # the exchange is a SUM: allreduce the bucket of ONE backward and compare it, element by element, with the sum of the
     # ranks' own copies of that same bucket (gathered separately) -- independent of step-to-step atomics / ordering noise
     ts.bucket.zero_()
     for im in images:
         ts.forward_backward(im, im_info)
-    local = ts.bucket.flat.clone()
+    ncheck = min(ts.bucket.flat.numel(), 8 << 20)                 # the last 8 Mi elements of the bucket (head + late trunk layers)
+    local = ts.bucket.flat[-ncheck:].clone()
     if dist_on:
         parts = [torch.empty_like(local) for _ in range(world)]
         dist.all_gather(parts, local)
@@ -327,23 +332,10 @@ def train_block(args, ts, images, im_info, device, world, rank, dist_on, mode):
     else:
         want = local.double()
     ts.bucket.allreduce()
-    chk = float((ts.bucket.flat.double() - want).abs().max() / want.abs().max().clamp_min(1e-30))
+    chk = float((ts.bucket.flat[-ncheck:].double() - want).abs().max() / want.abs().max().clamp_min(1e-30))
     del want, local
-    torch.cuda.synchronize()
-    if dist_on:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    evs = []
-    e0.record()
-    for _ in range(K):
-        evs.append(ts.step(images, im_info))
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / K
-    ms_ar = sorted(a.elapsed_time(b) for a, b in evs)[len(evs) // 2]
-    ms = replicas.max_over_ranks(ms, device); ms_ar = replicas.max_over_ranks(ms_ar, device)
     # the collective on its own (ranks aligned by a barrier first): what the exchange costs without the arrival skew of the
-    # eager backward that the in-step figure includes
+    # backward that the in-step figure includes
     ms_alone = 0.0
     if dist_on:
         al = []
@@ -355,16 +347,43 @@ def train_block(args, ts, images, im_info, device, world, rank, dist_on, mode):
             torch.cuda.synchronize()
             al.append(a.elapsed_time(b))
         ms_alone = replicas.max_over_ranks(sorted(al)[len(al) // 2], device)
-    nbytes = ts.bucket.flat.numel() * 4
-    return dict(mode=mode, images_per_sec=round(world * len(images) / (ms / 1e3), 2), images_per_rank_per_step=len(images),
-                ms_per_step=round(ms, 3), allreduce_ms_in_step=round(ms_ar, 4), allreduce_ms=round(ms_alone, 4),
-                allreduce_bus_gbs=round(bus_gbs(nbytes, ms_alone, world), 1),
-                bucket_mb=round(nbytes / 1e6, 1), collectives_per_step=1 if dist_on else 0, reduce_op='sum (rescale_grad = 1.0)',
-                reduced_vs_sum_of_ranks_rel=chk, steps=K, warmup=W, rois=ts.last.get('rois'),
-                contractions='forward (general kernels) and backward of the relation / learn-NMS ops on the tcgen05 tf32 GEMM '
-                             '(gemm_tf32.cu); no cuBLAS in the hot path',
-                launch=launch, eager_ms_per_step=round(eager_ms, 3),
-                losses={k: (round(v, 4) if isinstance(v, float) else v) for k, v in ts.last.items() if k != 'rois'})
+    res = dict(mode=mode, images_per_sec=round(world * len(images) / (eager_ms / 1e3), 2), images_per_rank_per_step=len(images),
+               ms_per_step=round(eager_ms, 3), allreduce_ms_in_step=round(eager_ar, 4), allreduce_ms=round(ms_alone, 4),
+               allreduce_bus_gbs=round(bus_gbs(nbytes, ms_alone, world), 1),
+               bucket_mb=round(nbytes / 1e6, 1), collectives_per_step=1 if dist_on else 0, reduce_op='sum (rescale_grad = 1.0)',
+               reduced_vs_sum_of_ranks_rel=chk, steps=K, warmup=W, rois=ts.last.get('rois'),
+               contractions='forward (general kernels) and backward of the relation / learn-NMS ops on the tcgen05 tf32 GEMM '
+                            '(gemm_tf32.cu); no cuBLAS in the hot path',
+               launch='eager (torch autograd drives the library trunk and the C-ABI fwd/bwd pairs); allreduce after backward, not overlapped',
+               eager_ms_per_step=round(eager_ms, 3),
+               losses={k: (round(v, 4) if isinstance(v, float) else v) for k, v in ts.last.items() if k != 'rois'})
+    if report:
+        report(dict(res))
+    # ---- the accumulate phase (zero + fwd + bwd of every micro-batch) as ONE CUDA graph; the allreduce + SGD update follow the replay
+    ok, why = 1.0, ''
+    try:
+        ts.capture(images, im_info)
+        torch.cuda.synchronize()
+    except Exception as e:           # stay measurable: keep the eager result and say why
+        ok, why = 0.0, ' (graph capture failed on this rank: %s)' % (str(e).splitlines()[0][:160] if str(e) else type(e).__name__)
+        torch.cuda.synchronize()
+    if dist_on:                      # one decision for the whole job: every rank replays the graph, or none does
+        flag = torch.tensor([ok], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if float(flag.item()) < 1.0 and ok == 1.0:
+            why = ' (graph capture failed on another rank)'
+        ok = float(flag.item())
+    if ok < 1.0:
+        ts.graph = None
+        res['launch'] += why
+        return res
+    for _ in range(W):
+        ts.step(images, im_info)
+    ms, ms_ar = timed_steps(K)
+    res.update(images_per_sec=round(world * len(images) / (ms / 1e3), 2), ms_per_step=round(ms, 3), allreduce_ms_in_step=round(ms_ar, 4),
+               launch='one CUDA-graph replay for the whole forward + backward (library trunk autograd + the C-ABI fwd/bwd pairs), then '
+                      'the NCCL allreduce and the SGD update; allreduce after backward, not overlapped')
+    return res
 
 
 def config2_block(args, prec, device, world, dist_on, image32_d, im_info):
@@ -387,7 +406,7 @@ def config2_block(args, prec, device, world, dist_on, image32_d, im_info):
                      'DeformablePSROIPooling x2 with the offset FC between (our kernels); rest as configs[1]')
 
 
-def config3_block(args, prec, device, world, rank, dist_on, train=True):
+def config3_block(args, prec, device, world, rank, dist_on, train=True, report=None):
     """BASELINE.json configs[3]: FPN 2FC + Relation + LearnNMS.  test: one 608 x 1024 image per GPU, 1000 given rois over four
     pyramid levels, n = 150 (replicas).  train: the data-parallel step -- 2 images per GPU per step accumulated locally, ONE
     NCCL SUM allreduce of the whole gradient bucket (batch 16 on 8 GPUs)."""
@@ -415,14 +434,20 @@ def config3_block(args, prec, device, world, rank, dist_on, train=True):
     out = dict(workload='fpn_2fc_relation_learnnms_r101_608x1024_n1000_h16_first150',
                test=dict(images_per_sec=round(world * steps / (ms / 1e3), 2), ms_per_step=round(ms / steps, 4), steps=steps,
                          head_ms_per_image=round(msh / steps, 4), rois_per_level=det.counts))
+    if report:
+        report(dict(out))
     if train:
         del gs, gh, det, head, trunk, feats
         torch.cuda.empty_cache()
         ts = FPNTrainStep(make_fpn_trunk(device, torch.bfloat16), device, num_rois=1000, micro_batches=2, lr=0.0)
         images = [image, (torch.randn((1, 3, 608, 1024), generator=g) * 50.0).to(device)]
+        def rep(partial):
+            out['train'] = partial
+            if report:
+                report(dict(out))
         out['train'] = train_block(args, ts, images, im_info, device, world, rank, dist_on,
                                    'configs[3] data-parallel training step: 2 images / GPU / step (batch %d), N = 1000 + G rois, '
-                                   'first_n = 150' % (2 * world))
+                                   'first_n = 150' % (2 * world), report=rep)
         del ts
         torch.cuda.empty_cache()
     return out
@@ -602,23 +627,12 @@ def main():
     ms_hot = timed(step_hot, args.steps, 3, dist_on)
     ms_trunk = timed(lambda: trunk_graph(image32_d), args.steps, 3, dist_on)
 
-    train = None
-    cfg2 = cfg3 = None
+    t_headline = time.time()                 # every rank leaves the last timed() together (barrier + max-reduce inside)
     del streamer, graphed, hot_graph, trunk_graph
     torch.cuda.empty_cache()
-    if not args.no_configs and prec == 'f16':
-        cfg2 = config2_block(args, prec, device, world, dist_on, image32_d, im_info)
-        torch.cuda.empty_cache()
-        cfg3 = config3_block(args, prec, device, world, rank, dist_on, train=not args.no_train)
-        torch.cuda.empty_cache()
-    if not args.no_train:
-        from relnet_b200.train import TrainStep
-        ts = TrainStep(make_trunk(device, torch.bfloat16, seed=0), device, micro_batches=1, lr=0.0)
-        timg, _ = make_inputs(seed=100 + rank)
-        train = train_block(args, ts, [timg.to(device)], im_info, device, world, rank, dist_on,
-                            'configs[1] data-parallel training step, 1 image / GPU / step')
-        del ts
-        torch.cuda.empty_cache()
+
+    # ---- rank 0: everything the contract line needs, BEFORE the optional blocks (they only add keys to it)
+    line = None
     if rank == 0:
         pk = peaks()
         ours, lib, names = count_launches(lambda: full_step(image32_d))
@@ -632,7 +646,7 @@ def main():
             'dtype': 'f16' if prec == 'f16' else 'f32', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'global_batch': world, 'parallelism': 'replicas x%d (1 image/GPU)' % world, 'launch': 'one CUDA-graph replay per image',
                        'trunk': 'ResNet-101 convolutions on cuDNN (bf16 channels_last, fused conv+bias+relu calls; library, out of scope) with our '
-                                'space-to-depth stem input, max-pool and RPN-head kernels around them',
+                                'space-to-depth stem input, max-pool and RPN-head (bf16 tcgen05 GEMM) kernels around them',
                        'hot_path_precision': prec, 'l2': 'inputs (7.2 MB image) + 180 MB of trunk activations per step '
                        'exceed the 126 MB L2; relation kernel timed with an explicit 256 MB L2 flush'},
             'e2e': {'value': round(world * args.steps / (ms_e2e / 1e3), 3), 'unit': 'images/sec',
@@ -648,18 +662,75 @@ def main():
                          'proposals_kept_before_pad': int(ops.proposal(trunk_out[0], trunk_out[1], im_info, return_num_kept=True, **head.cfg)[2].item())},
             'clocks': sampler.summary() if sampler else None,
             'roofline': roof,
-            'train': train,
-            'configs': {'2_deformable_faster': cfg2, '3_fpn': cfg3},
+            'train': None,
+            'configs': {'2_deformable_faster': None, '3_fpn': None},
             'sweep': sweep,
         }
         if not args.no_cpu_baseline:
             line['cpu_baseline'] = cpu_baseline()
         line['kernels'] = names
+
+    # ---- optional blocks: configs[2] / configs[3] and the data-parallel training steps (the one collective of the path).  They run
+    # under a deadline counted from the end of the headline measurement: if it passes (a slow or stuck collective, host contention
+    # with 8 processes ...) every rank stops there and rank 0 prints the line it already has -- the headline never depends on them.
+    done = threading.Event()
+    emit_lock = threading.Lock()
+
+    def bail():
+        with emit_lock:
+            if done.is_set():
+                return
+            done.set()
+            if rank == 0 and line is not None:
+                line['extras'] = 'stopped at the %.0f s deadline (--extras-budget); blocks finished until then are in the line' % args.extras_budget
+                emit(line)
+            os._exit(0)
+    timer = threading.Timer(max(5.0, t_headline + args.extras_budget + (0.0 if rank == 0 else 10.0) - time.time()), bail)
+    timer.daemon = True
+    timer.start()
+
+    def put(key, sub, val):
+        if line is not None:
+            if sub is None:
+                line[key] = val
+            else:
+                line[key][sub] = val
+
+    def guarded(fn):
+        try:
+            return fn()
+        except Exception as e:       # a failed optional block is reported, not fatal (collectives stay symmetric inside the blocks)
+            torch.cuda.synchronize()
+            return {'failed': (str(e).splitlines()[0][:200] if str(e) else type(e).__name__)}
+    if not args.no_configs and prec == 'f16':
+        put('configs', '2_deformable_faster', guarded(lambda: config2_block(args, prec, device, world, dist_on, image32_d, im_info)))
+        torch.cuda.empty_cache()
+    if not args.no_train:
+        def cfg1_train():
+            from relnet_b200.train import TrainStep
+            ts = TrainStep(make_trunk(device, torch.bfloat16, seed=0), device, micro_batches=1, lr=0.0)
+            timg, _ = make_inputs(seed=100 + rank)
+            return train_block(args, ts, [timg.to(device)], im_info, device, world, rank, dist_on,
+                               'configs[1] data-parallel training step, 1 image / GPU / step', report=lambda r: put('train', None, r))
+        put('train', None, guarded(cfg1_train))
+        torch.cuda.empty_cache()
+    if not args.no_configs and prec == 'f16':
+        put('configs', '3_fpn', guarded(lambda: config3_block(args, prec, device, world, rank, dist_on, train=not args.no_train,
+                                                                report=lambda r: put('configs', '3_fpn', r))))
+        torch.cuda.empty_cache()
+    with emit_lock:
+        stopped = done.is_set()
+        done.set()
+    timer.cancel()
+    if rank == 0 and not stopped:
         emit(line)
     if dist_on:
         import torch.distributed as dist
-        dist.barrier()
-        dist.destroy_process_group()
+        try:
+            dist.barrier()
+            dist.destroy_process_group()
+        except Exception:
+            pass
 
 
 if __name__ == '__main__':
