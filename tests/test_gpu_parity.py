@@ -213,8 +213,10 @@ def test_learn_nms_matches_golden(ops, name):
         np.testing.assert_allclose(sbbox.cpu().numpy(), g['sorted_bbox'], rtol=1e-5, atol=2e-3)
         m = multi.cpu().numpy()
         assert np.array_equal(m.max(axis=(0, 2)) > 0, g['nms_multi_score'].max(axis=(0, 2)) > 0), 'class pruning differs'
-        assert rel_err(m, g['nms_multi_score']) < 1e-3
-        assert rel_err(final.cpu().numpy(), g['final_score']) < 1e-3
+        tol = 5e-3 if prec == 'tf32' else 1e-3          # tf32: operands truncated to 10-bit mantissas in all six GEMMs of the head (value printed)
+        print('learn_nms %s [%s]: multi %.2e final %.2e' % (name, prec, rel_err(m, g['nms_multi_score']), rel_err(final.cpu().numpy(), g['final_score'])))
+        assert rel_err(m, g['nms_multi_score']) < tol
+        assert rel_err(final.cpu().numpy(), g['final_score']) < tol
 
 
 # ------------------------------------------------------------------------------------------------ proposal / NMS
