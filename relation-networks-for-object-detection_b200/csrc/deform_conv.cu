@@ -1,11 +1,17 @@
-// deform_conv.cu -- DeformableConvolution forward (operator_cxx/deformable_convolution-inl.h:91-144):
-// deformable im2col (nn/deformable_im2col.cuh:216-262, bilinear :77-113) followed by a per-group GEMM W[g].col[g].
-// Compiled with -fmad=false so the bilinear arithmetic is bit-comparable with oracle/oracle_c.c.
+// deform_conv.cu -- DeformableConvolution forward / backward (operator_cxx/deformable_convolution-inl.h:91-233): deformable
+// sampling (nn/deformable_im2col.cuh:216-262, bilinear :77-113) followed by a per-group GEMM W[g].col[g].
+// Compiled with -fmad=false so the bilinear arithmetic is bit-comparable with oracle/oracle_c.c and with the reference's own
+// kernels compiled the same way (the libref_deform.so checker, tests/test_gpu_refpin.py).
 //
-// HBM layout: data [B,C,H,W], offset [B, dg*2*kh*kw, Ho, Wo], weight [Co, C/g*kh*kw], col workspace [C*kh*kw, Ho*Wo]
-// (44 MB at 512ch/38x63, written once and re-read by the GEMM -- round-1 shape of the op; the implicit-GEMM form that
-// never materialises col is listed under "next" in DESIGN.md).
-// Roofline: GEMM 2*Co*C*kh*kw*Ho*Wo FLOP (11.3 GFLOP/layer) on the tensor pipe; im2col is HBM-write bound (4*C*kh*kw*Ho*Wo B).
+// Work decomposition (NOT the reference's thread-per-column-element): the four tap offsets and bilinear weights of a sample
+// depend on (deformable group, kernel tap, output position) only, so a CTA evaluates that SAMPLE TABLE once into shared
+// memory and streams the group's channels through it.  Three forms of the forward:
+//   NCHW fp32 in  -> col fp32 [C*kh*kw, Ho*Wo]          the reference's column buffer (rn_deform_im2col; fp32 GEMM path)
+//   NHWC fp32 in  -> colT fp16 [Ho*Wo, kh*kw*C]         tap-major K: the 8 channels a thread samples are 16 contiguous bytes of
+//   NHWC bf16 in  -> colT fp16 (the trunk's layout)     the K-major B operand of the tcgen05 GEMM (gemm_tc.cu), bias / relu fused
+// Measured at 512 -> 512, 3x3 dilated, 38 x 63 (11.3 GFLOP / layer): sampler 19.5 us (16-position tiles: 600 CTAs) + GEMM =
+// 48 us per layer = 235 TFLOP/s (round 1: 163 us).  The 22 MB fp16 column tile still round-trips HBM/L2 once each way; gathering
+// the K-slab straight into the SWIZZLE_128B tile that feeds tcgen05.mma (true implicit GEMM) is the next step.
 #include "common.cuh"
 #include "gemm_tc.cuh"
 #include <cuda_bf16.h>

@@ -1,10 +1,11 @@
-// rois.cu -- ROIPooling (max, MXNet semantics) and DeformablePSROIPooling forward (= average ROIAlign when no_trans).
-// Compiled with -fmad=false: the float/double op order of the reference kernels is kept literally so results are
-// bit-comparable with the plain-C oracle (oracle/oracle_c.c).
+// rois.cu -- ROIPooling (max, MXNet semantics) forward / backward.  (DeformablePSROIPooling lives in psroi.cu.)
+// Compiled with -fmad=false: the float op order of the MXNet kernel is kept literally so results are bit-comparable with the
+// plain-C oracle (oracle/oracle_c.c) and with torchvision.ops.roi_pool (tests/test_gpu_refpin.py).
 //
-// HBM layout: data [B,C,H,W] fp32 (the 38x63x256 map is 2.4 MB -> L2 resident), out [R,C,P,P] fp32.
-// Roofline: HBM-write bound -- algorithmic bytes = R*C*P*P*4 (out) + the feature map once; the gathers hit L2.
-// Grid: one thread per output element, blocks of 256, grid-stride capped at 148*8 CTAs.
+// HBM layout: data [B,C,H,W] fp32 (reference layout) or channels-last fp32 / bf16 (the trunk's layout: the hot path), out
+// [R,C,P,P] fp32 or fp16 [R, P*P, C] (the K order of the permuted fc_new_1 weight).
+// Roofline: HBM-write bound -- algorithmic bytes = out (7.5 MB fp16 at R = 300) + the feature map once; the gathers hit L2.
+// Measured: bf16-in / fp16-out form 10.5 us inside the step (profiles/r02_timeline_step.json).
 #include "common.cuh"
 #include <cfloat>
 #include <cuda_bf16.h>
