@@ -702,7 +702,11 @@ def main():
         except Exception as e:       # a failed optional block is reported, not fatal (collectives stay symmetric inside the blocks)
             torch.cuda.synchronize()
             return {'failed': (str(e).splitlines()[0][:200] if str(e) else type(e).__name__)}
-    # most important first: the training step of configs[1] carries the one collective of the path
+    # cheap replica block first, then the training step of configs[1] (the one collective of the path; its eager result enters the
+    # line before graph capture is attempted), then configs[3]
+    if not args.no_configs and prec == 'f16':
+        put('configs', '2_deformable_faster', guarded(lambda: config2_block(args, prec, device, world, dist_on, image32_d, im_info)))
+        torch.cuda.empty_cache()
     if not args.no_train:
         def cfg1_train():
             from relnet_b200.train import TrainStep
@@ -711,9 +715,6 @@ def main():
             return train_block(args, ts, [timg.to(device)], im_info, device, world, rank, dist_on,
                                'configs[1] data-parallel training step, 1 image / GPU / step', report=lambda r: put('train', None, r))
         put('train', None, guarded(cfg1_train))
-        torch.cuda.empty_cache()
-    if not args.no_configs and prec == 'f16':
-        put('configs', '2_deformable_faster', guarded(lambda: config2_block(args, prec, device, world, dist_on, image32_d, im_info)))
         torch.cuda.empty_cache()
     if not args.no_configs and prec == 'f16':
         put('configs', '3_fpn', guarded(lambda: config3_block(args, prec, device, world, rank, dist_on, train=not args.no_train,
