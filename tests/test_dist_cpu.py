@@ -93,3 +93,70 @@ def test_gradient_bucket_allreduce_sum():
         assert g == [3.0, 6.0, 9.0]                                                          # (1 + 2) * (i + 1)
         assert all(abs(p - (1.0 - 0.1 * gg)) < 1e-6 for p, gg in zip(pvals, g))
         assert numel % 64 == 0
+
+
+def _train_block_worker(rank, world, port, q):
+    """bench.train_block on gloo with a stand-in training step whose graph capture FAILS ON RANK 1 ONLY: every rank must issue
+    the same sequence of collectives (no deadlock), take the same job-wide decision (eager), and the allreduce of the real
+    GradientBucket must equal the sum of the ranks' buckets."""
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import sys
+    import time
+    import types
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import relnet_b200
+    from relnet_b200 import replicas
+    import bench
+
+    class Ev(object):
+        def __init__(self, enable_timing=True): self.t = None
+        def record(self): self.t = time.time()
+        def elapsed_time(self, o): return (o.t - self.t) * 1e3
+    torch.cuda.Event = Ev
+    torch.cuda.synchronize = lambda *a, **k: None
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+
+    class TS(object):
+        def __init__(self):
+            self.bucket = replicas.GradientBucket({'w': (64, 64), 'b': (64,)}, device='cpu')
+            self.graph, self.last, self.allreduces = None, {'rois': 308, 'cls': 1.0}, 0
+        def forward_backward(self, im, info):
+            self.bucket.flat.add_(float(rank + 1))
+        def step(self, images, info):
+            self.bucket.zero_()
+            for im in images:
+                self.forward_backward(im, info)
+            a, b = Ev(), Ev()
+            a.record(); self.bucket.allreduce(); self.allreduces += 1; b.record()
+            return (a, b)
+        def capture(self, images, info):
+            if rank == 1:
+                raise RuntimeError('capture failed here')
+            self.graph = 'captured'
+    ts = TS()
+    reported = []
+    r = bench.train_block(types.SimpleNamespace(steps=6), ts, [torch.zeros(1)], torch.zeros(1), 'cpu', world, rank, True, 'mode',
+                          report=reported.append)
+    q.put((rank, r['launch'], ts.graph, ts.allreduces, r['reduced_vs_sum_of_ranks_rel'], r['collectives_per_step'], len(reported)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_train_block_collectives_stay_symmetric_when_capture_fails_on_one_rank():
+    world, port = 2, _free_port()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_train_block_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, l0, g0, n0, c0, k0, rep0), (r1, l1, g1, n1, c1, k1, rep1) = res
+    assert g0 is None and g1 is None                      # one decision for the whole job: nobody replays a graph
+    assert 'another rank' in l0 and 'this rank' in l1 and l0.startswith('eager') and l1.startswith('eager')
+    assert n0 == n1                                       # same number of allreduces on both ranks
+    assert c0 < 1e-12 and c1 < 1e-12 and k0 == k1 == 1    # allreduced bucket == sum of the ranks' buckets
+    assert rep0 == rep1 == 1                              # the eager result was reported before the capture attempt
