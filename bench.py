@@ -50,7 +50,7 @@ def parse():
     ap.add_argument('--no-sweep', action='store_true', help='skip the relation-module roofline sweep (configs[4])')
     ap.add_argument('--no-train', action='store_true', help='skip the data-parallel training blocks (gradient allreduce)')
     ap.add_argument('--no-configs', action='store_true', help='skip the configs[2] (Deformable) and configs[3] (FPN) blocks')
-    ap.add_argument('--extras-budget', type=float, default=float(os.environ.get('RELNET_EXTRAS_BUDGET_S', '150')),
+    ap.add_argument('--extras-budget', type=float, default=float(os.environ.get('RELNET_EXTRAS_BUDGET_S', '120')),
                     help='seconds the optional blocks (configs[2]/[3], training steps) may take after the headline measurement; past '
                          'it every rank stops and rank 0 prints the line without them')
     return ap.parse_args()
