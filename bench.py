@@ -666,7 +666,7 @@ def main():
             'configs': {'2_deformable_faster': None, '3_fpn': None},
             'sweep': sweep,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:          # the contract asks for it on rank 0 at N=1 only
             line['cpu_baseline'] = cpu_baseline()
         line['kernels'] = names
 
