@@ -7,9 +7,11 @@ the golden vectors under ``tests/golden/``.
 
 MXNet 1.1.0 is not vendored in the reference (README.md:15,68) and cannot be imported here, so the op
 semantics below are a restatement of the MXNet operator documentation, one function per ``mx.nd.*`` /
-``mx.sym.*`` call the reference makes ("parity unpinned" for the op semantics themselves; the *composition*
-is the reference's own code).  float32 everywhere, like MXNet's default dtype; ``sort/argsort/arange``
-return float32 like MXNet.
+``mx.sym.*`` call the reference makes (the *composition* is the reference's own code).  MXNet itself was never
+executed against them: what pins the single ops is ``tests/test_mxshim_cpu.py`` -- the worked examples of
+MXNet's operator documentation (Reshape codes, take / pick / slice_axis / broadcast_to) and torch's independent
+CPU implementations of the ops both libraries have (grouped convolution, linear, bmm, softmax, sort, gather,
+smooth-L1).  float32 everywhere, like MXNet's default dtype; ``sort/argsort/arange`` return float32 like MXNet.
 
 Symbols are evaluated eagerly: ``mx.sym.FullyConnected(name='query_1', data=x, num_hidden=n)`` with no
 explicit weight looks ``query_1_weight`` / ``query_1_bias`` up in ``mxshim.PARAMS`` (a dict the caller fills),
