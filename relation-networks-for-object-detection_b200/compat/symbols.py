@@ -13,10 +13,20 @@ import torch
 from .. import ops
 
 
+def _keys_arg(nongt_dim, non_gt_index):
+    """The reference has two spellings of the same slot: ``extract_position_matrix(bbox, nongt_dim)`` with an int (SYM_REL:52) and
+    ``extract_position_matrix(bbox, non_gt_index)`` with an index array (SYM_FPN_REL_NMS:860; likewise the third argument of
+    ``attention_module_multi_head``).  A positional call of the FPN form lands in ``nongt_dim``: an array there is the index list."""
+    if nongt_dim is not None and non_gt_index is None and not isinstance(nongt_dim, (int, float)) and getattr(nongt_dim, 'ndim', 0) >= 1:
+        return None, nongt_dim
+    return nongt_dim, non_gt_index
+
+
 class PositionMatrix(object):
     """Lazy [num_rois, nongt_dim, 4] (SYM_REL:47-83); ``non_gt_index`` for the FPN form (SYM_FPN_REL_NMS:860-905)."""
 
     def __init__(self, bbox, nongt_dim=None, non_gt_index=None):
+        nongt_dim, non_gt_index = _keys_arg(nongt_dim, non_gt_index)
         self.bbox, self.nongt_dim, self.non_gt_index = bbox, nongt_dim, non_gt_index
 
     def materialize(self):
@@ -72,6 +82,7 @@ class RelationSymbols(object):
         assert fc_dim == group, 'fc_dim != group'
         P, i = self.params, str(index)
         pm = position_embedding.pm
+        nongt_dim, non_gt_index = _keys_arg(nongt_dim, non_gt_index)
         key_index = non_gt_index if non_gt_index is not None else pm.non_gt_index
         M = None if key_index is not None else (nongt_dim if nongt_dim is not None else pm.nongt_dim)
         return ops.relation(roi_feat, pm.bbox, P['query_' + i + '_weight'], P['query_' + i + '_bias'],
@@ -81,9 +92,10 @@ class RelationSymbols(object):
                             residual_relu=residual_relu, wave_length=float(position_embedding.wave_length),
                             precision=self.precision)
 
-    def attention_module_nms_multi_head(self, roi_feat, position_mat, num_rois, dim=(1024, 1024, 128), fc_dim=(64, 16),
-                                        feat_dim=128, group=16, index=1, return_softmax='lazy'):
-        """SYM_REL_NMS:158-238 / LNMS:45-127.  roi_feat [num_rois, num_fg_classes, feat_dim]; position_mat is built from
+    def attention_module_nms_multi_head(self, roi_feat, position_mat, num_rois, dim=(1024, 1024, 1024), fc_dim=(64, 16),
+                                        feat_dim=1024, group=16, index=1, return_softmax='lazy'):
+        """SYM_REL_NMS:158-238 / LNMS:45-127 (same defaults; the call site passes dim=(1024, 1024, 128), feat_dim=128 -- the
+        sizes that count are those of the weights).  roi_feat [num_rois, num_fg_classes, feat_dim]; position_mat is built from
         sorted boxes [num_rois, num_fg_classes, 4] (a lazy PositionMatrix over them or the boxes themselves).
         Returns (output [num_rois, num_fg_classes, dim[2]], aff_softmax [num_fg_classes*fc_dim[1], num_rois, num_rois]).
         return_softmax: 'lazy' (default) -> the output comes from the configured precision (tcgen05 under f16) and
