@@ -11,7 +11,8 @@ semantics below are a restatement of the MXNet operator documentation, one funct
 executed against them: what pins the single ops is ``tests/test_mxshim_cpu.py`` -- the worked examples of
 MXNet's operator documentation (Reshape codes, take / pick / slice_axis / broadcast_to) and torch's independent
 CPU implementations of the ops both libraries have (grouped convolution, linear, bmm, softmax, sort, gather,
-smooth-L1).  float32 everywhere, like MXNet's default dtype; ``sort/argsort/arange`` return float32 like MXNet.
+smooth-L1).  Label for this file: parity PARTIAL -- pinned by published examples and an independent implementation, not by
+an execution of MXNet.  float32 everywhere, like MXNet's default dtype; ``sort/argsort/arange`` return float32 like MXNet.
 
 Symbols are evaluated eagerly: ``mx.sym.FullyConnected(name='query_1', data=x, num_hidden=n)`` with no
 explicit weight looks ``query_1_weight`` / ``query_1_bias`` up in ``mxshim.PARAMS`` (a dict the caller fills),
