@@ -1,5 +1,6 @@
 """CPU: the oracle restatement (oracle/*.py) against golden vectors produced by executing the reference's own
 Python (tests/golden/make_golden.py).  No GPU, no /root/reference needed."""
+import os
 import numpy as np
 import pytest
 from conftest import golden, checksum, rel_err
@@ -284,3 +285,27 @@ def test_product_synth_generator_equals_oracle_generator():
         assert a.keys() == b.keys()
         for k in a:
             assert np.array_equal(a[k], b[k]), k
+
+
+def test_committed_goldens_regenerate_bitwise_from_the_reference(tmp_path):
+    """The fixtures under tests/golden/ are what the reference's own code produces today: re-execute the reference
+    (tests/golden/make_golden.py -> oracle/refexec.py) into a scratch directory and compare every array bit for bit.
+    Only where /root/reference exists (this container); the GPU box carries the committed files."""
+    import importlib.util
+    from oracle import refexec
+    if not refexec.available():
+        pytest.skip('reference tree not present')
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+    spec = importlib.util.spec_from_file_location('make_golden_regen', os.path.join(here, 'make_golden.py'))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    mg.HERE = str(tmp_path)
+    mg.main()
+    made = sorted(f for f in os.listdir(str(tmp_path)) if f.endswith('.npz'))
+    assert made == sorted(f for f in os.listdir(here) if f.endswith('.npz'))
+    for f in made:
+        a, b = np.load(os.path.join(str(tmp_path), f)), np.load(os.path.join(here, f))
+        assert sorted(a.files) == sorted(b.files), f
+        for k in a.files:
+            assert a[k].dtype == b[k].dtype and a[k].shape == b[k].shape, (f, k)
+            assert np.array_equal(a[k], b[k], equal_nan=a[k].dtype.kind == 'f'), (f, k)
