@@ -65,7 +65,8 @@ def build(force=False, verbose=False):
             objs.append(obj)
     with open(os.path.join(OBJ, 'ptxas.log'), 'w') as f:
         f.write('\n'.join(logs))
-    cmd = [NVCC, '-shared', '-o', LIB] + objs + ['-lcublas', '-Xlinker', '-rpath,/usr/local/cuda/lib64']
+    # -gencode at link time as well: the (empty) device-link stub is then sm_100a too, not nvcc's default architecture
+    cmd = [NVCC, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', LIB] + objs + ['-lcublas', '-Xlinker', '-rpath,/usr/local/cuda/lib64']
     p = subprocess.run(cmd, capture_output=True, text=True)
     if p.returncode != 0:
         sys.stderr.write(p.stdout + p.stderr)
