@@ -94,3 +94,17 @@ def test_position_matrix_accepts_both_spellings_of_the_key_slot():
     assert int(d.nongt_dim) == 7 and d.non_gt_index is None
     e = RelationSymbols.extract_position_embedding(b, 64)
     assert e.pm is b and e.feat_dim == 64 and e.wave_length == 1000
+
+
+def test_schema_golden_regenerates_from_the_reference(tmp_path):
+    """prop_schema.json is what the reference's classes answer today (only where /root/reference exists)."""
+    import importlib.util
+    from oracle import refexec
+    if not refexec.available():
+        pytest.skip('reference tree not present')
+    spec = importlib.util.spec_from_file_location('make_prop_schema_regen', os.path.join(HERE, 'golden', 'make_prop_schema.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.HERE = str(tmp_path)
+    mod.main()
+    assert json.load(open(os.path.join(str(tmp_path), 'prop_schema.json'))) == G
