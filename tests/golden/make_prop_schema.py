@@ -94,8 +94,19 @@ def main():
                 ps = inspect.signature(getattr(k, fn)).parameters
                 sigs.setdefault(modname, {})[fn] = [[n, None if q.default is inspect.Parameter.empty else tolist(q.default),
                                                      q.default is not inspect.Parameter.empty] for n, q in ps.items()]
+    # dmlc::Parameter fields (name, declared default) of the two C++ operators the path uses
+    import re
+    cxx = {}
+    for op, rel in [('DeformableConvolution', 'relation_rcnn/operator_cxx/deformable_convolution-inl.h'),
+                    ('DeformablePSROIPooling', 'relation_rcnn/operator_cxx/deformable_psroi_pooling-inl.h')]:
+        src = open(os.path.join(refexec.REF, rel)).read()
+        fields = []
+        for m in re.finditer(r'DMLC_DECLARE_FIELD\((\w+)\)(.*?);', src, re.S):
+            d = re.search(r'\.set_default\(([^()]*(?:\([^()]*\))?[^()]*)\)', m.group(2))
+            fields.append([m.group(1), d.group(1).strip() if d else None])
+        cxx[op] = fields
     with open(os.path.join(HERE, 'prop_schema.json'), 'w') as f:
-        json.dump({'cfg': CFG, 'cases': out, 'symbol_signatures': sigs}, f, indent=1, sort_keys=True)
+        json.dump({'cfg': CFG, 'cases': out, 'symbol_signatures': sigs, 'cxx_params': cxx}, f, indent=1, sort_keys=True)
     print('wrote %d cases' % len(out))
 
 

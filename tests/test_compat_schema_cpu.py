@@ -108,3 +108,28 @@ def test_schema_golden_regenerates_from_the_reference(tmp_path):
     mod.HERE = str(tmp_path)
     mod.main()
     assert json.load(open(os.path.join(str(tmp_path), 'prop_schema.json'))) == G
+
+
+@pytest.mark.parametrize('op', sorted(G['cxx_params']))
+def test_cxx_operator_keywords_are_the_dmlc_parameter_fields(op):
+    """compat.DeformableConvolution / DeformablePSROIPooling take every field of the reference's dmlc::Parameter struct
+    (deformable_convolution-inl.h:39-76, deformable_psroi_pooling-inl.h:32-54) as a keyword, with the declared default where
+    there is one (an empty TShape() default means stride / dilate 1, pad 0 -- MXNet's convention)."""
+    import inspect
+    fn = getattr(C, op)
+    ps = inspect.signature(fn).parameters
+    has_kw = any(q.kind is inspect.Parameter.VAR_KEYWORD for q in ps.values())
+    shape_defaults = {'stride': (1, 1), 'dilate': (1, 1), 'pad': (0, 0)}
+    for name, default in G['cxx_params'][op]:
+        if name not in ps:
+            assert has_kw and name in ('workspace', 'layout'), (op, name)      # accepted and ignored (no meaning for this library)
+            continue
+        if default is None:
+            continue
+        got = ps[name].default
+        if default == 'TShape()':
+            assert tuple(got) == shape_defaults[name], (op, name, got)
+        elif default in ('true', 'false'):
+            assert got is (default == 'true'), (op, name, got)
+        else:
+            assert float(got) == float(default), (op, name, got)
