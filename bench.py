@@ -700,26 +700,44 @@ def main():
         try:
             return fn()
         except Exception as e:       # a failed optional block is reported, not fatal (collectives stay symmetric inside the blocks)
-            torch.cuda.synchronize()
-            return {'failed': (str(e).splitlines()[0][:200] if str(e) else type(e).__name__)}
+            msg = (str(e).splitlines()[0][:200] if str(e) else type(e).__name__)
+            try:
+                torch.cuda.synchronize()
+            except Exception as e2:  # a sticky device error: nothing further can run on this rank, the line still goes out
+                raise RuntimeError('%s; device unusable afterwards (%s)' % (msg, str(e2).splitlines()[0][:120] if str(e2) else type(e2).__name__))
+            return {'failed': msg}
     # cheap replica block first, then the training step of configs[1] (the one collective of the path; its eager result enters the
     # line before graph capture is attempted), then configs[3]
-    if not args.no_configs and prec == 'f16':
-        put('configs', '2_deformable_faster', guarded(lambda: config2_block(args, prec, device, world, dist_on, image32_d, im_info)))
-        torch.cuda.empty_cache()
-    if not args.no_train:
-        def cfg1_train():
-            from relnet_b200.train import TrainStep
-            ts = TrainStep(make_trunk(device, torch.bfloat16, seed=0), device, micro_batches=1, lr=0.0)
-            timg, _ = make_inputs(seed=100 + rank)
-            return train_block(args, ts, [timg.to(device)], im_info, device, world, rank, dist_on,
-                               'configs[1] data-parallel training step, 1 image / GPU / step', report=lambda r: put('train', None, r))
-        put('train', None, guarded(cfg1_train))
-        torch.cuda.empty_cache()
-    if not args.no_configs and prec == 'f16':
-        put('configs', '3_fpn', guarded(lambda: config3_block(args, prec, device, world, rank, dist_on, train=not args.no_train,
-                                                                report=lambda r: put('configs', '3_fpn', r))))
-        torch.cuda.empty_cache()
+    try:
+        if not args.no_configs and prec == 'f16':
+            put('configs', '2_deformable_faster', guarded(lambda: config2_block(args, prec, device, world, dist_on, image32_d, im_info)))
+            torch.cuda.empty_cache()
+        if not args.no_train:
+            def cfg1_train():
+                from relnet_b200.train import TrainStep
+                ts = TrainStep(make_trunk(device, torch.bfloat16, seed=0), device, micro_batches=1, lr=0.0)
+                timg, _ = make_inputs(seed=100 + rank)
+                return train_block(args, ts, [timg.to(device)], im_info, device, world, rank, dist_on,
+                                   'configs[1] data-parallel training step, 1 image / GPU / step', report=lambda r: put('train', None, r))
+            put('train', None, guarded(cfg1_train))
+            torch.cuda.empty_cache()
+        if not args.no_configs and prec == 'f16':
+            put('configs', '3_fpn', guarded(lambda: config3_block(args, prec, device, world, rank, dist_on, train=not args.no_train,
+                                                                    report=lambda r: put('configs', '3_fpn', r))))
+            torch.cuda.empty_cache()
+    except BaseException as e:       # whatever escapes the optional blocks on any rank must not cost the job its headline line:
+        # this rank stops here; rank 0 prints what it has, the others leave with status 0 (peers still inside a collective are
+        # released by their own deadline)
+        sys.stderr.write('bench.py: optional blocks aborted on rank %d: %s\n' % (rank, (str(e).splitlines()[0][:300] if str(e) else type(e).__name__)))
+        if line is not None:
+            line['extras'] = 'aborted: %s' % (str(e).splitlines()[0][:200] if str(e) else type(e).__name__)
+        with emit_lock:
+            if not done.is_set():
+                done.set()
+                if rank == 0 and line is not None:
+                    emit(line)
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
     with emit_lock:
         stopped = done.is_set()
         done.set()

@@ -1,6 +1,7 @@
 """bench.py's host-side control flow with every GPU-touching piece replaced by a stand-in (no CUDA in the CPU suite): used by
 tests/test_bench_contract_cpu.py to check the ONE-JSON-line contract, the contract keys, a failing optional block and the
---extras-budget deadline.  MOCK_FAIL=1: the training block raises; MOCK_HANG=1: the configs[3] block stalls for 30 s."""
+--extras-budget deadline.  MOCK_FAIL=1: the training block raises; MOCK_STICKY=1: it raises and every later synchronize raises too (sticky device error);
+MOCK_HANG=1: the configs[3] block stalls for 30 s."""
 import sys, types, time, json, io, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -8,7 +9,11 @@ import bench
 # ---- fakes
 torch.cuda.is_available = lambda: True
 torch.cuda.set_device = lambda *a, **k: None
-torch.cuda.synchronize = lambda *a, **k: None
+_sync_state = {'armed': False}
+def _sync(*a, **k):
+    if _sync_state['armed']:           # MOCK_STICKY: a device error that every later CUDA call reports again
+        raise RuntimeError('CUDA error: an illegal memory access was encountered')
+torch.cuda.synchronize = _sync
 torch.cuda.empty_cache = lambda: None
 _real_device = torch.device
 class FakeTensorOps: pass
@@ -25,6 +30,9 @@ bench.config3_block = fake_cfg3
 def fake_train(args, ts, images, im_info, device, world, rank, dist_on, mode, report=None):
     if report: report({'eager': True})
     if os.environ.get('MOCK_FAIL'): raise RuntimeError('boom')
+    if os.environ.get('MOCK_STICKY'):
+        _sync_state['armed'] = True
+        raise RuntimeError('CUDA error: an illegal memory access was encountered')
     return {'graph': True}
 bench.train_block = fake_train
 class ClockSampler:

@@ -41,3 +41,10 @@ def test_deadline_keeps_the_headline():
     d = run({'MOCK_HANG': '1'}, ['--extras-budget', '6'])
     assert 'stopped at the 6 s deadline' in d['extras']
     assert d['value'] > 0 and d['configs']['3_fpn'] == {'test': 1}          # the part reported before the stall is kept
+
+
+def test_sticky_device_error_in_an_optional_block_still_prints_the_line():
+    d = run({'MOCK_STICKY': '1'})
+    assert d['value'] > 0 and d['train'] == {'eager': True}                # the part reported before the error is kept
+    assert d['extras'].startswith('aborted: ') and 'device unusable' in d['extras']
+    assert d['configs']['2_deformable_faster'] == {'images_per_sec': 700} and d['configs']['3_fpn'] is None
