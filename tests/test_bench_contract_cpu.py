@@ -48,3 +48,44 @@ def test_sticky_device_error_in_an_optional_block_still_prints_the_line():
     assert d['value'] > 0 and d['train'] == {'eager': True}                # the part reported before the error is kept
     assert d['extras'].startswith('aborted: ') and 'device unusable' in d['extras']
     assert d['configs']['2_deformable_faster'] == {'images_per_sec': 700} and d['configs']['3_fpn'] is None
+
+
+def test_roofline_object_and_sweep_keys_with_a_stand_in_timer(monkeypatch):
+    """bench.relation_kernel_roofline on its real code with the per-point GPU timing replaced: the contract's roofline keys, the
+    SURVEY 8(d) algorithmic bytes, the N=3000 entry with its ncu traffic, 16 sweep points; a failing sweep point is reported inside
+    `sweep` and leaves the headline roofline intact."""
+    sys.path.insert(0, ROOT)
+    import torch
+    import bench
+    import relnet_b200  # noqa: F401
+
+    def point(ops, synth, device, flush, N, d, H, reps):
+        return dict(N=N, d=d, H=H, dk=d // H, F_tc_gflop=round(4.0 * N * N * d / 1e9, 4), path='stand-in',
+                    module_us=45.0 + N / 10, nm_us=30.0 + N / 5, proj_us=18.0)
+    real_empty = torch.empty
+    monkeypatch.setattr(torch, 'empty', lambda *a, **k: real_empty(16, dtype=torch.uint8))
+    monkeypatch.setattr(bench, '_relation_point', point)
+    pk = dict(hbm_gbs=6570.6, tflops=1720.8, tflops_sustained=1500.0, source='test')
+    roof, times, sw = bench.relation_kernel_roofline(None, pk, 'cpu', sweep=True)
+    assert {'bound', 'achieved', 'peak', 'unit', 'frac', 'traffic'} <= set(roof)
+    assert roof['bound'] == 'tensor' and roof['unit'] == 'TFLOP/s' and roof['peak'] == 1720.8
+    N = M = 300; d = 1024; E = 64; H = 16
+    assert roof['algorithmic_bytes'] == 2 * (N * d + 2 * M * d) + 16 * max(N, M) + 4 * (E * H + H) + 2 * N * d       # SURVEY 8(d), s = 2
+    assert abs(roof['achieved'] - 4.0 * N * M * d / (roof['duration_us'] * 1e-6) / 1e12) < 1e-3
+    assert abs(roof['frac'] - roof['achieved'] / roof['peak']) < 1e-5
+    assert len(sw) == 16 and {(r['N'], r['d'], r['H']) for r in sw} == {(n, dd, hh) for n in (100, 300, 1000, 3000) for dd in (256, 1024) for hh in (4, 16)}
+    big = roof['at_N3000']
+    assert big['algorithmic_bytes'] == 2 * (3000 * 1024 * 3) + 16 * 3000 + 4 * (64 * 16 + 16) + 2 * 3000 * 1024
+    assert big['traffic'] is None or big['traffic'] >= big['algorithmic_bytes']
+    assert roof['xu']['at_N3000']['mufu_ops'] == 3000.0 * 3000 * (34 + 16)
+    json.dumps(roof), json.dumps(sw)                                    # serialisable as they are
+    assert set(times) == {'module', 'nm_stage', 'proj'}
+
+    def flaky(ops, synth, device, flush, N, d, H, reps):
+        if N == 1000:
+            raise RuntimeError('CUDA error: launch failed')
+        return point(ops, synth, device, flush, N, d, H, reps)
+    monkeypatch.setattr(bench, '_relation_point', flaky)
+    roof2, _, sw2 = bench.relation_kernel_roofline(None, pk, 'cpu', sweep=True)
+    assert roof2['frac'] == roof['frac'] and 'at_N3000' not in roof2
+    assert sw2[-1] == {'failed': 'CUDA error: launch failed'} and len(sw2) == 9
