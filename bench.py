@@ -692,14 +692,16 @@ def main():
 
     def bail():
         with emit_lock:
-            if done.is_set():
-                return
-            done.set()
-            if rank == 0 and line is not None:
-                line['extras'] = 'stopped at the %.0f s deadline (--extras-budget); blocks finished until then are in the line' % args.extras_budget
-                emit(line)
-            os._exit(0)
-    timer = threading.Timer(max(5.0, t_headline + args.extras_budget + (0.0 if rank == 0 else 10.0) - time.time()), bail)
+            if not done.is_set():
+                done.set()
+                if rank == 0 and line is not None:
+                    line['extras'] = 'stopped at the %.0f s deadline (--extras-budget); blocks finished until then are in the line' % args.extras_budget
+                    emit(line)
+        os._exit(0)
+    # every rank leaves at (nearly) the same moment, rank 0 a little earlier so that its line is out before any peer can notice a
+    # missing process
+    t_deadline = t_headline + args.extras_budget + (0.0 if rank == 0 else 1.5)
+    timer = threading.Timer(max(5.0, t_deadline - time.time()), bail)
     timer.daemon = True
     timer.start()
 
@@ -751,13 +753,15 @@ def main():
                 if rank == 0 and line is not None:
                     emit(line)
         sys.stdout.flush(); sys.stderr.flush()
+        if dist_on:                  # leave together with the peers (at the deadline), not before them: a process that disappears
+            time.sleep(max(0.0, t_deadline - time.time()) + 5.0)     # while the others sit in a collective turns a reported failure into a job abort
         os._exit(0)
-    with emit_lock:
-        stopped = done.is_set()
-        done.set()
-    timer.cancel()
-    if rank == 0 and not stopped:
-        emit(line)
+    with emit_lock:                  # exactly once: either this or bail() prints the line
+        timer.cancel()
+        if not done.is_set():
+            done.set()
+            if rank == 0:
+                emit(line)
     if dist_on:
         import torch.distributed as dist
         try:

@@ -79,5 +79,11 @@ torch.Tensor.to = to
 torch.Tensor.pin_memory = lambda self: self
 _orig_randn = torch.randn
 torch.randn = lambda *a, **k: _orig_randn(*((8, 8) if a[:2] == (4096, 4096) else a), **{kk: v for kk, v in k.items() if kk != "device"})
+if os.environ.get('MOCK_RANK'):        # one rank of a 2-process job, process-group calls replaced (peers are not simulated)
+    import torch.distributed as dist
+    os.environ.update(WORLD_SIZE='2', RANK=os.environ['MOCK_RANK'], LOCAL_RANK='0')
+    dist.init_process_group = lambda *a, **k: None
+    dist.barrier = lambda *a, **k: None
+    dist.destroy_process_group = lambda *a, **k: None
 sys.argv = ['bench.py', '--steps', '4', '--warmup', '3'] + sys.argv[1:]
 bench.main()

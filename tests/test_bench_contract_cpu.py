@@ -89,3 +89,23 @@ def test_roofline_object_and_sweep_keys_with_a_stand_in_timer(monkeypatch):
     roof2, _, sw2 = bench.relation_kernel_roofline(None, pk, 'cpu', sweep=True)
     assert roof2['frac'] == roof['frac'] and 'at_N3000' not in roof2
     assert sw2[-1] == {'failed': 'CUDA error: launch failed'} and len(sw2) == 9
+
+
+def test_a_rank_that_aborts_its_optional_blocks_leaves_with_its_peers_not_before_them():
+    """Under torchrun a process that disappears while the others sit in a collective turns a reported failure into a job abort:
+    the aborting rank stays until the common deadline (rank 0 prints its line at once), then every rank exits 0."""
+    import time
+    e = dict(os.environ, MOCK_STICKY='1', MOCK_RANK='1')
+    t0 = time.time()
+    p = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', '_mock_bench.py'), '--extras-budget', '7'], capture_output=True,
+                       text=True, env=e, timeout=120)
+    assert p.returncode == 0 and p.stdout.strip() == ''                  # rank 1 never prints the line
+    assert 'optional blocks aborted on rank 1' in p.stderr
+    assert time.time() - t0 >= 7.0                                       # it waited for the deadline
+    e['MOCK_RANK'] = '0'
+    p = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', '_mock_bench.py'), '--extras-budget', '7'], capture_output=True,
+                       text=True, env=e, timeout=120)
+    lines = [l for l in p.stdout.splitlines() if l.strip()]
+    assert p.returncode == 0 and len(lines) == 1
+    d = json.loads(lines[0])
+    assert d['n_gpus'] == 2 and d['extras'].startswith('aborted: ') and 'cpu_baseline' not in d      # cpu_baseline: N = 1 only
